@@ -1,0 +1,163 @@
+// common.cuh -- session state and helpers shared by the CUDA translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+#include <string>
+#include <vector>
+#include "../../include/ehmm.h"
+
+namespace ehmm {
+
+void set_error(const char *fmt, ...);
+
+#define EHMM_CK(call)                                                                  \
+    do {                                                                               \
+        cudaError_t e_ = (call);                                                       \
+        if (e_ != cudaSuccess) {                                                       \
+            ehmm::set_error("%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+            return (e_ == cudaErrorMemoryAllocation) ? EHMM_ERR_NOMEM : EHMM_ERR_CUDA; \
+        }                                                                              \
+    } while (0)
+
+#define EHMM_REQUIRE(cond, code, ...)      \
+    do {                                   \
+        if (!(cond)) {                     \
+            ehmm::set_error(__VA_ARGS__);  \
+            return (code);                 \
+        }                                  \
+    } while (0)
+
+#define EHMM_TRY(expr)              \
+    do {                            \
+        int rc_ = (expr);           \
+        if (rc_ != EHMM_OK) return rc_; \
+    } while (0)
+
+// grow-only device buffer
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+    int reserve(size_t n) {
+        if (n <= bytes) return EHMM_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+        cudaError_t e = cudaMalloc(&p, n);
+        if (e != cudaSuccess) {
+            set_error("cudaMalloc(%zu bytes): %s", n, cudaGetErrorString(e));
+            return EHMM_ERR_NOMEM;
+        }
+        bytes = n;
+        return EHMM_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+    }
+    template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+enum : unsigned {
+    DS_LOGF = 1, DS_FP = 2, DS_BP = 4, DS_P1 = 8, DS_P2 = 16, DS_ETA = 32, DS_VIT = 64,
+    DS_ESTEP = DS_FP | DS_BP | DS_P1 | DS_P2
+};
+
+// forward-backward tiling (fb.cu)
+constexpr int FB_MAX_STATS = EHMM_MAX_K * EHMM_MAX_K + 1;
+
+}  // namespace ehmm
+
+struct ehmm_session {
+    std::string key;
+    int device = 0;
+    int64_t M = 0;      // bins in this block
+    int K = 0;          // hidden states
+    int64_t m0 = 0;     // first global bin of this block
+    int64_t Mtot = 0;   // bins in the global chain
+    cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;  // side stream (uniform generation)
+    cudaEvent_t ev = nullptr;
+
+    // ---- data (dt) ----
+    int N = 0;
+    int B = 0;
+    int64_t G = 0;
+    ehmm::DevBuf counts_own, offsets_own, controls_own;  // owned copies (host upload)
+    const int32_t *d_counts = nullptr;
+    const double *d_offsets = nullptr;
+    const double *d_controls = nullptr;
+    ehmm::DevBuf group;                     // int32 M x N
+    ehmm::DevBuf u_chip, u_off, u_ctrl;     // dtUnique columns, index 0..G (0 unused)
+    ehmm::DevBuf u_dsg;                     // uint8 (G+1) x B
+    uint8_t design[EHMM_MAX_B * 64] = {0};  // B x N
+    bool have_design = false;
+
+    // ---- datasets ----
+    ehmm::DevBuf logf, logFP, logBP, logProb1, logProb2, eta, viterbi;
+    unsigned valid = 0;        // DS_* bits: which datasets hold data
+    bool stats_stale = false;  // datasets were replaced from the host; statistics must be recomputed
+
+    // ---- forward-backward scratch ----
+    ehmm::DevBuf tileops, carries, tilestats, fbscal;  // fbscal: [ll, stats..., total op...]
+    double h_pi[EHMM_MAX_K] = {0};
+    double h_gamma[EHMM_MAX_K * EHMM_MAX_K] = {0};  // column-major as given
+    double h_stats[ehmm::FB_MAX_STATS] = {0};       // K*K joint sums, then sum(P1*logf)
+    double h_lp1_row0[EHMM_MAX_K] = {0};
+    double h_ll = 0;
+    bool stats_on_host = false;
+    bool reduce_pending = false;
+    const double *cur_logf = nullptr;  // logf the pending sharded E-step was reduced from
+
+    // ---- rejection control ----
+    uint32_t rng_state[625] = {624};
+    bool rng_set = false;
+    ehmm::DevBuf rc_w, rc_flag, rc_scan, rc_buckets, rc_unif, rc_tmp, mt_raw;
+    int rc_columns = 0;
+    int rc_N = 0;
+
+    // ---- emission / GLM scratch ----
+    ehmm::DevBuf lgtab, glm_part, misc;
+    int64_t count_max = -1;
+    double *h_pinned = nullptr;  // small pinned staging buffer (256 doubles)
+};
+
+namespace ehmm {
+
+inline int check_session(ehmm_session *s) {
+    EHMM_REQUIRE(s != nullptr, EHMM_ERR_ARG, "null session");
+    cudaError_t e = cudaSetDevice(s->device);
+    if (e != cudaSuccess) {
+        set_error("cudaSetDevice(%d): %s", s->device, cudaGetErrorString(e));
+        return EHMM_ERR_CUDA;
+    }
+    return EHMM_OK;
+}
+
+// fb.cu
+int fb_expstep(ehmm_session *s, const double *d_logf);
+int fb_reduce(ehmm_session *s, const double *d_logf, double *op_host);
+int fb_apply(ehmm_session *s, const double *fwd_carry, const double *bwd_carry, double *fwd_out);
+int fb_fetch_stats(ehmm_session *s);
+inline bool has(const ehmm_session *s, unsigned bits) { return (s->valid & bits) == bits; }
+// emission.cu
+int emis_consensus(ehmm_session *s, const double *th1, const double *th2, int P, double minZero);
+int emis_init(ehmm_session *s, const double *psi1, const double *psi2);
+int emis_differential_hmm(ehmm_session *s, const double *delta, const double *psi, double minZero);
+int emis_inner_estep(ehmm_session *s, const double *delta, const double *psi, double minZero);
+int inner_maxstepprob(ehmm_session *s, double *delta_out);
+// rc.cu
+int rc_consensus(ehmm_session *s, double p, const double *uniforms, int64_t n_uniforms, int64_t *consumed);
+int rc_differential(ehmm_session *s, double p, int N, const double *uniforms, int64_t n_uniforms, int64_t *consumed);
+int rc_table_rows(ehmm_session *s, int column, int64_t *rows);
+int rc_table_fetch(ehmm_session *s, int column, double *sums, double *ids);
+int rc_reweight(int device, double *x, int64_t n, double p, const double *uniforms, int64_t n_uniforms, int64_t *consumed);
+int rc_aggregate(int device, const double *x, int64_t n, const int32_t *f, int64_t G, double *buckets);
+// glm.cu
+int glm_nb(ehmm_session *s, int column, const double *par, int P, double *value, double *grad);
+int glm_mix_nb(ehmm_session *s, const double *par, double minZero, double *value, double *grad);
+// viterbi.cu
+int viterbi(ehmm_session *s, const double *pi, const double *gamma, double *states_out);
+
+}  // namespace ehmm

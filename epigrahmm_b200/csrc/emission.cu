@@ -1,0 +1,357 @@
+// emission.cu -- negative-binomial emission log-likelihoods streamed from the bins x samples
+// count matrix (replaces R/base-loglikelihood.R:11-143 and R/base-EM.R:24-30,302-314, which call
+// stats::dnbinom once per (bin, sample, component) from R).
+//
+// NB log-density in the (mu, size) parameterisation, with t = log(mu/size) = eta - log(size):
+//   log f(x) = [lgamma(x+size) - lgamma(size) - lgamma(x+1)] - size*softplus(t) - x*softplus(-t)
+// The bracket depends only on the integer count and the state's size, so it is tabulated once per
+// call (lgtab); the rest costs one exp and one log1p per (bin, sample, density).
+#include "common.cuh"
+
+namespace ehmm {
+
+namespace {
+
+constexpr int EM_NT = 256;
+constexpr int TAB_MAX = 8192;  // counts >= TAB_MAX fall back to lgamma in the kernel
+constexpr int MAX_DENS = 4;    // distinct (size) values per launch
+
+struct EmisParams {
+    double b0[MAX_DENS];     // intercept
+    double b1[MAX_DENS];     // control coefficient (consensus) -- 0 when unused
+    double size[MAX_DENS];   // NB size
+    double lsize[MAX_DENS];  // log(size)
+    double lgs[MAX_DENS];    // lgamma(size)
+    double minZero, lminZero, thr;
+    int tabn;
+};
+
+struct MixParams {
+    uint64_t mask[EHMM_MAX_B + 2];  // bit i set <=> Dsg.Mix_b of sample i is 1
+    double ldelta[EHMM_MAX_B + 2];  // log(delta_b)
+    int B;
+};
+
+// tab[d*tabn + x] = lgamma(x+size_d) - lgamma(size_d) - lgamma(x+1)
+__global__ void lgtab_kernel(EmisParams P, int nd, double *__restrict__ tab) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nd * P.tabn) return;
+    int d = i / P.tabn, x = i % P.tabn;
+    tab[i] = (lgamma((double)x + P.size[d]) - P.lgs[d]) - lgamma((double)x + 1.0);
+}
+
+__device__ __forceinline__ double nb_logpmf(int x, double eta, int d, const EmisParams &P,
+                                            const double *__restrict__ tab) {
+    const double t = eta - P.lsize[d];
+    const double w = log1p(exp(-fabs(t)));
+    const double sp = (t > 0.0) ? t + w : w;   // softplus(t)  = log(1 + mu/size)
+    const double spm = (t > 0.0) ? w : w - t;  // softplus(-t) = log(1 + size/mu)
+    const double c = (x < P.tabn) ? __ldg(tab + d * P.tabn + x)
+                                  : (lgamma((double)x + P.size[d]) - P.lgs[d]) - lgamma((double)x + 1.0);
+    return (c - P.size[d] * sp) - (double)x * spm;
+}
+
+// log(dnbinom(log=FALSE) + minZero), R/base-loglikelihood.R:115,121
+__device__ __forceinline__ double plus_min_zero(double l, const EmisParams &P) {
+    return (l > P.thr) ? l : log(exp(l) + P.minZero);
+}
+
+// loglikConsensusHMM (NB): LL[j,k] = sum_i log(NB(y_ji; mu=exp(th_k0 [+ th_k1*ctrl_ji] + o_ji), size_k) + minZero)
+template <bool CTRL, bool PLUS_MZ>
+__global__ void __launch_bounds__(EM_NT)
+    emis_consensus_kernel(int64_t M, int N, const int32_t *__restrict__ y, const double *__restrict__ off,
+                          const double *__restrict__ ctrl, const __grid_constant__ EmisParams P,
+                          const double *__restrict__ tab, double *__restrict__ LL) {
+    for (int64_t j = (int64_t)blockIdx.x * EM_NT + threadIdx.x; j < M; j += (int64_t)gridDim.x * EM_NT) {
+        double a0 = 0.0, a1 = 0.0;
+        for (int i = 0; i < N; i++) {
+            const int64_t c = j + (int64_t)i * M;
+            const int x = __ldg(y + c);
+            const double o = __ldg(off + c);
+            double e0, e1;
+            if (CTRL) {
+                const double cv = __ldg(ctrl + c);
+                e0 = (P.b0[0] + P.b1[0] * cv) + o;
+                e1 = (P.b0[1] + P.b1[1] * cv) + o;
+            } else {
+                e0 = P.b0[0] + o;
+                e1 = P.b0[1] + o;
+            }
+            double l0 = nb_logpmf(x, e0, 0, P, tab), l1 = nb_logpmf(x, e1, 1, P, tab);
+            if (PLUS_MZ) { l0 = plus_min_zero(l0, P); l1 = plus_min_zero(l1, P); }
+            a0 += l0;
+            a1 += l1;
+        }
+        LL[j] = a0;
+        LL[j + M] = a1;
+    }
+}
+
+// per-bin pieces of the differential model: LL0 = sum_i l0_i, LL2 = sum_i l1_i, d_i = l1_i - l0_i
+template <int NMAX>
+__device__ __forceinline__ void diff_cells(int64_t j, int64_t M, int N, const int32_t *__restrict__ y,
+                                           const double *__restrict__ off, const EmisParams &P,
+                                           const double *__restrict__ tab, double &LL0, double &LL2, double *d) {
+    LL0 = 0.0;
+    LL2 = 0.0;
+#pragma unroll
+    for (int i = 0; i < NMAX; i++) {
+        if (i < N) {
+            const int64_t c = j + (int64_t)i * M;
+            const int x = __ldg(y + c);
+            const double o = __ldg(off + c);
+            const double l0 = nb_logpmf(x, P.b0[0] + o, 0, P, tab);
+            const double l1 = nb_logpmf(x, P.b0[1] + o, 1, P, tab);
+            LL0 += l0;
+            LL2 += l1;
+            d[i] = l1 - l0;
+        } else {
+            d[i] = 0.0;
+        }
+    }
+}
+
+template <int NMAX>
+__device__ __forceinline__ double mix_ll(int b, double LL0, const double *d, const MixParams &X) {
+    double s = 0.0;
+    const uint64_t mk = X.mask[b];
+#pragma unroll
+    for (int i = 0; i < NMAX; i++) s += ((mk >> i) & 1ull) ? d[i] : 0.0;
+    return X.ldelta[b] + (LL0 + s);
+}
+
+// loglikDifferentialHMM (NB), R/base-loglikelihood.R:45-71,96
+template <int NMAX>
+__global__ void __launch_bounds__(EM_NT)
+    emis_diff_hmm_kernel(int64_t M, int N, const int32_t *__restrict__ y, const double *__restrict__ off,
+                         const __grid_constant__ EmisParams P, const __grid_constant__ MixParams X,
+                         const double *__restrict__ tab, double *__restrict__ LL) {
+    for (int64_t j = (int64_t)blockIdx.x * EM_NT + threadIdx.x; j < M; j += (int64_t)gridDim.x * EM_NT) {
+        double LL0, LL2, d[NMAX];
+        diff_cells<NMAX>(j, M, N, y, off, P, tab, LL0, LL2, d);
+        double s = 0.0;
+        for (int b = 0; b < X.B; b++) s += exp(mix_ll<NMAX>(b, LL0, d, X));  // not max-shifted, as in the reference
+        double LL1 = log(s);
+        LL[j] = isinf(LL0) ? P.lminZero : LL0;
+        LL[j + M] = isinf(LL1) ? P.lminZero : LL1;
+        LL[j + 2 * M] = isinf(LL2) ? P.lminZero : LL2;
+    }
+}
+
+// innerExpStep, R/base-EM.R:302-314: eta[j,b] = exp(ll_b)/sum_b exp(ll_b) with exp(ll_b)==0 -> minZero
+template <int NMAX>
+__global__ void __launch_bounds__(EM_NT)
+    emis_inner_kernel(int64_t M, int N, const int32_t *__restrict__ y, const double *__restrict__ off,
+                      const __grid_constant__ EmisParams P, const __grid_constant__ MixParams X,
+                      const double *__restrict__ tab, double *__restrict__ eta) {
+    for (int64_t j = (int64_t)blockIdx.x * EM_NT + threadIdx.x; j < M; j += (int64_t)gridDim.x * EM_NT) {
+        double LL0, LL2, d[NMAX];
+        diff_cells<NMAX>(j, M, N, y, off, P, tab, LL0, LL2, d);
+        double s = 0.0;
+        for (int b = 0; b < X.B; b++) {
+            double v = exp(mix_ll<NMAX>(b, LL0, d, X));
+            if (v == 0.0) v = P.minZero;
+            eta[j + (int64_t)b * M] = v;
+            s += v;
+        }
+        for (int b = 0; b < X.B; b++) {
+            // own write, served from L1/L2; division as in the reference (exp(ll)/sumExpLL)
+            eta[j + (int64_t)b * M] = eta[j + (int64_t)b * M] / s;
+        }
+    }
+}
+
+// innerMaxStepProb partial sums: part[blk*(B+1) + b] = sum_j p1[j]*eta[j,b], [.. + B] = sum_j p1[j]
+__global__ void __launch_bounds__(256) inner_mstep_kernel(int64_t M, int B, const double *__restrict__ lp1_col1,
+                                                          const double *__restrict__ eta, double *__restrict__ part) {
+    __shared__ double sh[8];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int b = 0; b <= B; b++) {
+        double s = 0.0;
+        for (int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x; j < M; j += (int64_t)gridDim.x * 256) {
+            const double p = exp(__ldg(lp1_col1 + j));
+            s += (b < B) ? p * __ldg(eta + j + (int64_t)b * M) : p;
+        }
+        for (int dd = 16; dd > 0; dd >>= 1) s += __shfl_down_sync(0xffffffffu, s, dd);
+        if (lane == 0) sh[w] = s;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = sh[0];
+            for (int i = 1; i < 8; i++) t += sh[i];
+            part[(int64_t)blockIdx.x * (B + 1) + b] = t;
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256) colsum_kernel(const double *__restrict__ part, int nblk, int ncol,
+                                                     double *__restrict__ out) {
+    __shared__ double sh[256];
+    for (int c = 0; c < ncol; c++) {
+        double s = 0.0;
+        for (int i = threadIdx.x; i < nblk; i += 256) s += part[(int64_t)i * ncol + c];
+        sh[threadIdx.x] = s;
+        __syncthreads();
+        for (int d = 128; d > 0; d >>= 1) {
+            if ((int)threadIdx.x < d) sh[threadIdx.x] += sh[threadIdx.x + d];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) out[c] = sh[0];
+        __syncthreads();
+    }
+}
+
+int grid_for(int64_t M) {
+    int64_t g = (M + EM_NT - 1) / EM_NT;
+    const int64_t cap = 148 * 8 * 4;  // a few waves of 8 resident CTAs per SM
+    return (int)(g < cap ? (g < 1 ? 1 : g) : cap);
+}
+
+int require_data(ehmm_session *s, const char *who) {
+    EHMM_REQUIRE(s->d_counts && s->d_offsets && s->N > 0, EHMM_ERR_STATE, "%s: ehmm_set_data has not been called", who);
+    return EHMM_OK;
+}
+
+void fill_density(EmisParams &P, int d, double b0, double b1, double size) {
+    P.b0[d] = b0;
+    P.b1[d] = b1;
+    P.size[d] = size;
+    P.lsize[d] = log(size);
+    P.lgs[d] = lgamma(size);
+}
+
+int prepare_tab(ehmm_session *s, EmisParams &P, int nd, double minZero) {
+    P.minZero = minZero;
+    P.lminZero = log(minZero);
+    P.thr = P.lminZero + 40.0;  // exp(l) + minZero == exp(l) in fp64 above this
+    int64_t tabn = s->count_max + 1;
+    if (tabn < 1) tabn = 1;
+    if (tabn > TAB_MAX) tabn = TAB_MAX;
+    P.tabn = (int)tabn;
+    EHMM_TRY(s->lgtab.reserve(sizeof(double) * MAX_DENS * TAB_MAX));
+    int n = nd * P.tabn;
+    lgtab_kernel<<<(n + 255) / 256, 256, 0, s->stream>>>(P, nd, s->lgtab.as<double>());
+    EHMM_CK(cudaGetLastError());
+    return EHMM_OK;
+}
+
+int fill_mix(ehmm_session *s, MixParams &X, const double *delta) {
+    EHMM_REQUIRE(s->have_design && s->B > 0, EHMM_ERR_STATE, "ehmm_set_design has not been called");
+    EHMM_REQUIRE(s->N <= 64, EHMM_ERR_ARG, "differential model supports at most 64 samples (N=%d)", s->N);
+    X.B = s->B;
+    for (int b = 0; b < s->B; b++) {
+        uint64_t m = 0;
+        for (int i = 0; i < s->N; i++)
+            if (s->design[b * s->N + i]) m |= (1ull << i);
+        X.mask[b] = m;
+        X.ldelta[b] = log(delta[b]);
+    }
+    return EHMM_OK;
+}
+
+void fill_diff(EmisParams &P, const double *psi) {
+    // psi = (b_bg, l_bg, db, dl): mu_D = exp(psi1 + psi3*D + o), size_D = exp(psi2 + psi4*D)
+    fill_density(P, 0, psi[0], 0.0, exp(psi[1]));
+    fill_density(P, 1, psi[0] + psi[2], 0.0, exp(psi[1] + psi[3]));
+}
+
+}  // namespace
+
+int emis_consensus(ehmm_session *s, const double *th1, const double *th2, int P_, double minZero) {
+    EHMM_TRY(require_data(s, "loglikConsensusHMM"));
+    EHMM_REQUIRE(s->K == 2, EHMM_ERR_ARG, "loglikConsensusHMM needs a K=2 session (K=%d)", s->K);
+    EHMM_REQUIRE(P_ == 2 || P_ == 3, EHMM_ERR_ARG, "P must be 2 (beta0,size) or 3 (beta0,beta_ctrl,size)");
+    EHMM_REQUIRE(P_ == 2 || s->d_controls, EHMM_ERR_STATE, "P=3 needs a controls matrix");
+    EmisParams P = {};
+    fill_density(P, 0, th1[0], P_ == 3 ? th1[1] : 0.0, th1[P_ - 1]);
+    fill_density(P, 1, th2[0], P_ == 3 ? th2[1] : 0.0, th2[P_ - 1]);
+    EHMM_TRY(prepare_tab(s, P, 2, minZero));
+    EHMM_TRY(s->logf.reserve(sizeof(double) * s->M * 2));
+    const int g = grid_for(s->M);
+    if (P_ == 3)
+        emis_consensus_kernel<true, true><<<g, EM_NT, 0, s->stream>>>(s->M, s->N, s->d_counts, s->d_offsets,
+                                                                     s->d_controls, P, s->lgtab.as<double>(),
+                                                                     s->logf.as<double>());
+    else
+        emis_consensus_kernel<false, true><<<g, EM_NT, 0, s->stream>>>(s->M, s->N, s->d_counts, s->d_offsets, nullptr,
+                                                                      P, s->lgtab.as<double>(), s->logf.as<double>());
+    EHMM_CK(cudaGetLastError());
+    s->valid |= DS_LOGF;
+    return EHMM_OK;
+}
+
+int emis_init(ehmm_session *s, const double *psi1, const double *psi2) {
+    EHMM_TRY(require_data(s, "emInitialization"));
+    EHMM_REQUIRE(s->K == 2 && s->N == 1, EHMM_ERR_ARG, "the initializer supports one sample and K=2 (N=%d, K=%d)",
+                 s->N, s->K);
+    EmisParams P = {};
+    fill_density(P, 0, psi1[0], 0.0, psi1[1]);
+    fill_density(P, 1, psi2[0], 0.0, psi2[1]);
+    EHMM_TRY(prepare_tab(s, P, 2, 2.2250738585072014e-308));
+    EHMM_TRY(s->logf.reserve(sizeof(double) * s->M * 2));
+    emis_consensus_kernel<false, false><<<grid_for(s->M), EM_NT, 0, s->stream>>>(
+        s->M, 1, s->d_counts, s->d_offsets, nullptr, P, s->lgtab.as<double>(), s->logf.as<double>());
+    EHMM_CK(cudaGetLastError());
+    s->valid |= DS_LOGF;
+    return EHMM_OK;
+}
+
+int emis_differential_hmm(ehmm_session *s, const double *delta, const double *psi, double minZero) {
+    EHMM_TRY(require_data(s, "loglikDifferentialHMM"));
+    EHMM_REQUIRE(s->K == 3, EHMM_ERR_ARG, "loglikDifferentialHMM needs a K=3 session (K=%d)", s->K);
+    EmisParams P = {};
+    MixParams X = {};
+    fill_diff(P, psi);
+    EHMM_TRY(fill_mix(s, X, delta));
+    EHMM_TRY(prepare_tab(s, P, 2, minZero));
+    EHMM_TRY(s->logf.reserve(sizeof(double) * s->M * 3));
+    const int g = grid_for(s->M);
+    if (s->N <= 16)
+        emis_diff_hmm_kernel<16><<<g, EM_NT, 0, s->stream>>>(s->M, s->N, s->d_counts, s->d_offsets, P, X,
+                                                            s->lgtab.as<double>(), s->logf.as<double>());
+    else
+        emis_diff_hmm_kernel<64><<<g, EM_NT, 0, s->stream>>>(s->M, s->N, s->d_counts, s->d_offsets, P, X,
+                                                            s->lgtab.as<double>(), s->logf.as<double>());
+    EHMM_CK(cudaGetLastError());
+    s->valid |= DS_LOGF;
+    return EHMM_OK;
+}
+
+int emis_inner_estep(ehmm_session *s, const double *delta, const double *psi, double minZero) {
+    EHMM_TRY(require_data(s, "innerExpStep"));
+    EmisParams P = {};
+    MixParams X = {};
+    fill_diff(P, psi);
+    EHMM_TRY(fill_mix(s, X, delta));
+    EHMM_TRY(prepare_tab(s, P, 2, minZero));
+    EHMM_TRY(s->eta.reserve(sizeof(double) * s->M * s->B));
+    const int g = grid_for(s->M);
+    if (s->N <= 16)
+        emis_inner_kernel<16><<<g, EM_NT, 0, s->stream>>>(s->M, s->N, s->d_counts, s->d_offsets, P, X,
+                                                         s->lgtab.as<double>(), s->eta.as<double>());
+    else
+        emis_inner_kernel<64><<<g, EM_NT, 0, s->stream>>>(s->M, s->N, s->d_counts, s->d_offsets, P, X,
+                                                         s->lgtab.as<double>(), s->eta.as<double>());
+    EHMM_CK(cudaGetLastError());
+    s->valid |= DS_ETA;
+    return EHMM_OK;
+}
+
+int inner_maxstepprob(ehmm_session *s, double *delta_out) {
+    EHMM_REQUIRE(has(s, DS_ETA | DS_P1), EHMM_ERR_STATE, "innerMaxStepProb needs mixtureProb and logProb1");
+    EHMM_REQUIRE(s->K == 3, EHMM_ERR_ARG, "innerMaxStepProb needs K=3");
+    const int B = s->B;
+    const int nblk = 148 * 4;
+    EHMM_TRY(s->misc.reserve(sizeof(double) * ((size_t)nblk * (B + 1) + B + 1)));
+    double *part = s->misc.as<double>(), *out = part + (size_t)nblk * (B + 1);
+    inner_mstep_kernel<<<nblk, 256, 0, s->stream>>>(s->M, B, s->logProb1.as<double>() + s->M, s->eta.as<double>(), part);
+    EHMM_CK(cudaGetLastError());
+    colsum_kernel<<<1, 256, 0, s->stream>>>(part, nblk, B + 1, out);
+    EHMM_CK(cudaGetLastError());
+    EHMM_CK(cudaMemcpyAsync(s->h_pinned + 64, out, sizeof(double) * (B + 1), cudaMemcpyDeviceToHost, s->stream));
+    EHMM_CK(cudaStreamSynchronize(s->stream));
+    for (int b = 0; b < B; b++) delta_out[b] = s->h_pinned[64 + b] / s->h_pinned[64 + B];
+    return EHMM_OK;
+}
+
+}  // namespace ehmm

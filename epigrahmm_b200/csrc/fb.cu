@@ -1,0 +1,884 @@
+// fb.cu -- E-step of the HMM: forward-backward + posteriors as a parallel scan of
+// scaled K x K transition operators (replaces src/expStep.cpp:45-123 of the
+// reference, whose single loop over all M bins is sequential and unscaled).
+//
+// Operator of bin j:  T_j = Gamma * diag(e_j),  e_j[k] = exp(logf[j,k] - m_j),  m_j = max_k logf[j,k]
+// (bin 0 of the chain: T_0 = diag(e_0), start vector pi).  Forward: alpha_j = alpha_{j-1} T_j,
+// backward: beta_{j-1} = T_j beta_j.  Every operator / vector carries a log-scale so the mantissas
+// stay O(1) (exact power-of-two renormalisation), which is the log semiring under exp() but costs
+// K^3 FMAs per combine instead of K^3 exp/log.
+//
+// Three launches per E-step over tiles of TB = NT*L bins:
+//   fb_reduce_kernel : tile -> product of its operators                       (reads 8K B/bin)
+//   fb_carry_kernel  : one CTA, scan over tile operators -> forward carry into and backward carry
+//                      out of every tile, log-likelihood
+//   fb_apply_kernel  : tile -> logFP, logBP, logProb1, logProb2 + fused sufficient statistics
+//                      (reads 8K, writes 24K + 8K^2 B/bin)
+// followed by a deterministic reduction of the per-tile statistics.
+#include "common.cuh"
+
+namespace ehmm {
+
+namespace {
+
+constexpr double LN2 = 0.693147180559945309417232121458;
+constexpr double TINY_LIN = 1e-290;  // below this a stored linear forward value is recomputed in log space
+
+template <int K> struct Op {
+    double m[K * K];  // row-major mantissa, m[i*K+l]
+    double ls;        // natural-log scale
+};
+template <int K> struct Vec {
+    double v[K];
+    double ls;
+};
+struct CarryIn {
+    double start[EHMM_MAX_K + 1];  // forward vector entering the block + log scale
+    double end[EHMM_MAX_K + 1];    // backward vector behind the block + log scale
+};
+struct FBParams {
+    double g[EHMM_MAX_K * EHMM_MAX_K];   // Gamma row-major g[i*K+l] = gamma(i,l)
+    double lg[EHMM_MAX_K * EHMM_MAX_K];  // log Gamma (host libm, same values the reference would use)
+};
+
+template <int K> struct FBCfg;
+template <> struct FBCfg<2> { static constexpr int NT = 256, L = 5; };
+template <> struct FBCfg<3> { static constexpr int NT = 192, L = 5; };
+constexpr int CARRY_NT = 1024;
+
+// 2^-e for the binary exponent e of mx (mx normal, positive); e = 0 otherwise
+__device__ __forceinline__ double inv_pow2(double mx, int &e) {
+    int hi = __double2hiint(mx);
+    e = ((hi >> 20) & 0x7ff) - 1023;
+    if (!(mx >= 2.2250738585072014e-308) || e >= 1023) e = 0;
+    return __hiloint2double((1023 - e) << 20, 0);
+}
+
+template <int K> __device__ __forceinline__ void op_identity(Op<K> &X) {
+#pragma unroll
+    for (int i = 0; i < K; i++)
+#pragma unroll
+        for (int l = 0; l < K; l++) X.m[i * K + l] = (i == l) ? 1.0 : 0.0;
+    X.ls = 0.0;
+}
+
+template <int K> __device__ __forceinline__ void op_renorm(Op<K> &X) {
+    double mx = X.m[0];
+#pragma unroll
+    for (int i = 1; i < K * K; i++) mx = fmax(mx, X.m[i]);
+    int e;
+    double sc = inv_pow2(mx, e);
+#pragma unroll
+    for (int i = 0; i < K * K; i++) X.m[i] *= sc;
+    X.ls += e * LN2;
+}
+
+template <int K> __device__ __forceinline__ void vec_renorm(Vec<K> &x) {
+    double mx = x.v[0];
+#pragma unroll
+    for (int i = 1; i < K; i++) mx = fmax(mx, x.v[i]);
+    int e;
+    double sc = inv_pow2(mx, e);
+#pragma unroll
+    for (int i = 0; i < K; i++) x.v[i] *= sc;
+    x.ls += e * LN2;
+}
+
+// A applied first, then B (time order): C = A * B
+template <int K> __device__ __forceinline__ Op<K> op_mul(const Op<K> &A, const Op<K> &B) {
+    Op<K> C;
+#pragma unroll
+    for (int i = 0; i < K; i++)
+#pragma unroll
+        for (int l = 0; l < K; l++) {
+            double acc = A.m[i * K] * B.m[l];
+#pragma unroll
+            for (int q = 1; q < K; q++) acc = fma(A.m[i * K + q], B.m[q * K + l], acc);
+            C.m[i * K + l] = acc;
+        }
+    C.ls = A.ls + B.ls;
+    op_renorm(C);
+    return C;
+}
+
+template <int K> __device__ __forceinline__ Vec<K> vec_mul_op(const Vec<K> &x, const Op<K> &A) {
+    Vec<K> r;
+#pragma unroll
+    for (int l = 0; l < K; l++) {
+        double acc = x.v[0] * A.m[l];
+#pragma unroll
+        for (int i = 1; i < K; i++) acc = fma(x.v[i], A.m[i * K + l], acc);
+        r.v[l] = acc;
+    }
+    r.ls = x.ls + A.ls;
+    vec_renorm(r);
+    return r;
+}
+
+template <int K> __device__ __forceinline__ Vec<K> op_mul_vec(const Op<K> &A, const Vec<K> &x) {
+    Vec<K> r;
+#pragma unroll
+    for (int i = 0; i < K; i++) {
+        double acc = A.m[i * K] * x.v[0];
+#pragma unroll
+        for (int l = 1; l < K; l++) acc = fma(A.m[i * K + l], x.v[l], acc);
+        r.v[i] = acc;
+    }
+    r.ls = x.ls + A.ls;
+    vec_renorm(r);
+    return r;
+}
+
+template <int K> __device__ __forceinline__ Op<K> op_shfl_up(const Op<K> &X, int d) {
+    Op<K> R;
+#pragma unroll
+    for (int i = 0; i < K * K; i++) R.m[i] = __shfl_up_sync(0xffffffffu, X.m[i], d);
+    R.ls = __shfl_up_sync(0xffffffffu, X.ls, d);
+    return R;
+}
+template <int K> __device__ __forceinline__ Op<K> op_shfl_down(const Op<K> &X, int d) {
+    Op<K> R;
+#pragma unroll
+    for (int i = 0; i < K * K; i++) R.m[i] = __shfl_down_sync(0xffffffffu, X.m[i], d);
+    R.ls = __shfl_down_sync(0xffffffffu, X.ls, d);
+    return R;
+}
+
+template <int K> __device__ __forceinline__ void op_store(double *dst, const Op<K> &X) {
+#pragma unroll
+    for (int i = 0; i < K * K; i++) dst[i] = X.m[i];
+    dst[K * K] = X.ls;
+}
+template <int K> __device__ __forceinline__ Op<K> op_load(const double *src) {
+    Op<K> X;
+#pragma unroll
+    for (int i = 0; i < K * K; i++) X.m[i] = src[i];
+    X.ls = src[K * K];
+    return X;
+}
+
+// Striped load of one tile: thread t takes bins t, t+NT, ... (coalesced); stores
+// f (optional), m_j and e_j = exp(f - m_j) column-wise in shared memory.
+template <int K, int NT, int L, bool KEEP_F>
+__device__ __forceinline__ void load_tile(const double *__restrict__ logf, int64_t M, int64_t s0, int nvalid,
+                                          double *sF, double *sM, double *sE) {
+    constexpr int TB = NT * L;
+    double f[L][K];
+#pragma unroll
+    for (int r = 0; r < L; r++) {
+        int b = r * NT + threadIdx.x;
+#pragma unroll
+        for (int k = 0; k < K; k++) f[r][k] = (b < nvalid) ? __ldg(logf + (int64_t)k * M + s0 + b) : 0.0;
+    }
+#pragma unroll
+    for (int r = 0; r < L; r++) {
+        int b = r * NT + threadIdx.x;
+        double m = f[r][0];
+#pragma unroll
+        for (int k = 1; k < K; k++) m = fmax(m, f[r][k]);
+        sM[b] = m;
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            if (KEEP_F) sF[k * TB + b] = f[r][k];
+            sE[k * TB + b] = exp(f[r][k] - m);
+        }
+    }
+}
+
+// Product of the operators of thread t's chunk of L consecutive bins.
+template <int K, int L, int TB>
+__device__ __forceinline__ Op<K> chunk_product(const double *sE, const double *sM, int t, int nvalid, bool special0,
+                                               const FBParams &P) {
+    Op<K> X;
+    X.ls = 0.0;
+    bool has = false;
+#pragma unroll
+    for (int i = 0; i < L; i++) {
+        int b = t * L + i;
+        if (b < nvalid) {
+            double e[K];
+#pragma unroll
+            for (int k = 0; k < K; k++) e[k] = sE[k * TB + b];
+            if (!has) {
+                if (special0 && b == 0) {
+#pragma unroll
+                    for (int r = 0; r < K; r++)
+#pragma unroll
+                        for (int c = 0; c < K; c++) X.m[r * K + c] = (r == c) ? e[c] : 0.0;
+                } else {
+#pragma unroll
+                    for (int r = 0; r < K; r++)
+#pragma unroll
+                        for (int c = 0; c < K; c++) X.m[r * K + c] = P.g[r * K + c] * e[c];
+                }
+                has = true;
+            } else {
+                double T[K * K];
+#pragma unroll
+                for (int r = 0; r < K; r++)
+#pragma unroll
+                    for (int c = 0; c < K; c++) {
+                        double acc = X.m[r * K] * P.g[c];
+#pragma unroll
+                        for (int q = 1; q < K; q++) acc = fma(X.m[r * K + q], P.g[q * K + c], acc);
+                        T[r * K + c] = acc;
+                    }
+#pragma unroll
+                for (int r = 0; r < K; r++)
+#pragma unroll
+                    for (int c = 0; c < K; c++) X.m[r * K + c] = T[r * K + c] * e[c];
+            }
+            X.ls += sM[b];
+        }
+    }
+    if (!has) op_identity(X);
+    op_renorm(X);
+    return X;
+}
+
+// ---- kernel A: tile -> operator product ---------------------------------------------------------
+template <int K, int NT, int L>
+__global__ void __launch_bounds__(NT) fb_reduce_kernel(const double *__restrict__ logf, int64_t M, int first_is_start,
+                                                       const __grid_constant__ FBParams P,
+                                                       double *__restrict__ tileops) {
+    constexpr int TB = NT * L, NW = NT / 32;
+    extern __shared__ double smem[];
+    double *sM = smem;
+    double *sE = smem + TB;
+    double *sWarp = sE + K * TB;  // NW * (K*K+1)
+    const int64_t s0 = (int64_t)blockIdx.x * TB;
+    const int nvalid = (int)min((int64_t)TB, M - s0);
+    load_tile<K, NT, L, false>(logf, M, s0, nvalid, nullptr, sM, sE);
+    __syncthreads();
+    Op<K> X = chunk_product<K, L, TB>(sE, sM, threadIdx.x, nvalid, first_is_start && blockIdx.x == 0, P);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        Op<K> O = op_shfl_down<K>(X, d);
+        X = op_mul<K>(X, O);  // lane 0 ends with the ordered product of all 32 lanes
+    }
+    if (lane == 0) op_store<K>(sWarp + w * (K * K + 1), X);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        Op<K> T = op_load<K>(sWarp);
+        for (int i = 1; i < NW; i++) T = op_mul<K>(T, op_load<K>(sWarp + i * (K * K + 1)));
+        op_store<K>(tileops + (int64_t)blockIdx.x * (K * K + 1), T);
+    }
+}
+
+// ---- kernel B: scan over tile operators ---------------------------------------------------------
+// mode 0: only the product of all tile operators -> scal[1 .. K*K+1]          (sharded phase 1)
+// mode 1: carries[t] = { A_t[K], lfT, B_t[K], lbT } for every tile, scal[0] = log-likelihood,
+//         scal[K*K+2 .. ] = forward vector after the last tile (K + 1 doubles)
+template <int K>
+__global__ void __launch_bounds__(CARRY_NT) fb_carry_kernel(const double *__restrict__ tileops, int64_t nT, int mode,
+                                                            const __grid_constant__ CarryIn cin,
+                                                            double *__restrict__ carries, double *__restrict__ scal) {
+    const double *startvec = cin.start, *endvec = cin.end;
+    constexpr int OPN = K * K + 1, NW = CARRY_NT / 32;
+    __shared__ double sWarp[NW * OPN];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int64_t q = (nT + CARRY_NT - 1) / CARRY_NT;
+    const int64_t t0 = min(nT, (int64_t)tid * q), t1 = min(nT, t0 + q);
+    Op<K> X;
+    op_identity(X);
+    for (int64_t t = t0; t < t1; t++) X = op_mul<K>(X, op_load<K>(tileops + t * OPN));
+    Op<K> Pi = X, Si = X;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        Op<K> O = op_shfl_up<K>(Pi, d);
+        if (lane >= d) Pi = op_mul<K>(O, Pi);
+    }
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        Op<K> O = op_shfl_down<K>(Si, d);
+        if (lane + d < 32) Si = op_mul<K>(Si, O);
+    }
+    if (lane == 31) op_store<K>(sWarp + w * OPN, Pi);
+    Op<K> Pe = op_shfl_up<K>(Pi, 1), Se = op_shfl_down<K>(Si, 1);
+    if (lane == 0) op_identity(Pe);
+    if (lane == 31) op_identity(Se);
+    __syncthreads();
+    if (mode == 0) {
+        if (tid == 0) {
+            Op<K> T = op_load<K>(sWarp);
+            for (int i = 1; i < NW; i++) T = op_mul<K>(T, op_load<K>(sWarp + i * OPN));
+            op_store<K>(scal + 1, T);
+        }
+        return;
+    }
+    // forward carries
+    Vec<K> v;
+#pragma unroll
+    for (int k = 0; k < K; k++) v.v[k] = startvec[k];
+    v.ls = startvec[K];
+    vec_renorm(v);
+    for (int i = 0; i < w; i++) v = vec_mul_op<K>(v, op_load<K>(sWarp + i * OPN));
+    v = vec_mul_op<K>(v, Pe);
+    for (int64_t t = t0; t < t1; t++) {
+        double *c = carries + t * (2 * K + 2);
+#pragma unroll
+        for (int k = 0; k < K; k++) c[k] = v.v[k];
+        c[K] = v.ls;
+        v = vec_mul_op<K>(v, op_load<K>(tileops + t * OPN));
+    }
+    if (t1 == nT && t0 < nT) {  // owner of the last tile: v = alpha at the last bin
+        double sum = v.v[0];
+#pragma unroll
+        for (int k = 1; k < K; k++) sum += v.v[k];
+        scal[0] = v.ls + log(sum);
+#pragma unroll
+        for (int k = 0; k < K; k++) scal[OPN + 1 + k] = v.v[k];
+        scal[OPN + 1 + K] = v.ls;
+    }
+    // backward carries
+    Vec<K> u;
+#pragma unroll
+    for (int k = 0; k < K; k++) u.v[k] = endvec[k];
+    u.ls = endvec[K];
+    vec_renorm(u);
+    for (int i = NW - 1; i > w; i--) u = op_mul_vec<K>(op_load<K>(sWarp + i * OPN), u);
+    u = op_mul_vec<K>(Se, u);
+    for (int64_t t = t1 - 1; t >= t0; t--) {
+        double *c = carries + t * (2 * K + 2) + K + 1;
+#pragma unroll
+        for (int k = 0; k < K; k++) c[k] = u.v[k];
+        c[K] = u.ls;
+        u = op_mul_vec<K>(op_load<K>(tileops + t * OPN), u);
+    }
+    if (t0 == 0 && t1 > 0) {  // backward vector in front of the block (for the previous bin block)
+#pragma unroll
+        for (int k = 0; k < K; k++) scal[OPN + 2 + K + k] = u.v[k];
+        scal[OPN + 2 + 2 * K] = u.ls;
+    }
+}
+
+// ---- kernel C: tile -> all outputs + statistics -------------------------------------------------
+template <int K, int NT, int L>
+__global__ void __launch_bounds__(NT)
+    fb_apply_kernel(const double *__restrict__ logf, int64_t M, int first_is_start, const __grid_constant__ FBParams P,
+                    const double *__restrict__ carries, double *__restrict__ logFP, double *__restrict__ logBP,
+                    double *__restrict__ logProb1, double *__restrict__ logProb2, double *__restrict__ tilestats) {
+    constexpr int TB = NT * L, NW = NT / 32, OPN = K * K + 1, NS = K * K + 1;
+    extern __shared__ double smem[];
+    double *sF = smem;             // K*TB  logf
+    double *sM = sF + K * TB;      // TB    per-bin max
+    double *sA = sM + TB;          // K*TB  e_j, then alpha~_j (post-emission, chunk scale)
+    double *sB = sA + K * TB;      // K*TB  beta~_j
+    double *sScF = sB + K * TB;    // TB    tile-local log scale of alpha~_j
+    double *sScB = sScF + TB;      // TB    tile-local log scale of beta~_j
+    double *sX = sScB + TB;        // 2*NT*K  lf exchange between neighbouring bins
+    double *sLast = sX + 2 * NT * K;  // L*K
+    double *sWarp = sLast + L * K;    // NW*OPN, later NW*NS for the statistics
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int64_t s0 = (int64_t)blockIdx.x * TB;
+    const int nvalid = (int)min((int64_t)TB, M - s0);
+    const bool special0 = first_is_start && blockIdx.x == 0;
+    const double *cr = carries + (int64_t)blockIdx.x * (2 * K + 2);
+
+    load_tile<K, NT, L, true>(logf, M, s0, nvalid, sF, sM, sA);
+    __syncthreads();
+    {
+        Op<K> X = chunk_product<K, L, TB>(sA, sM, tid, nvalid, special0, P);
+        Op<K> Pi = X, Si = X;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            Op<K> O = op_shfl_up<K>(Pi, d);
+            if (lane >= d) Pi = op_mul<K>(O, Pi);
+        }
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            Op<K> O = op_shfl_down<K>(Si, d);
+            if (lane + d < 32) Si = op_mul<K>(Si, O);
+        }
+        if (lane == 31) op_store<K>(sWarp + w * OPN, Pi);
+        Op<K> Pe = op_shfl_up<K>(Pi, 1), Se = op_shfl_down<K>(Si, 1);
+        if (lane == 0) op_identity(Pe);
+        if (lane == 31) op_identity(Se);
+        __syncthreads();
+        Vec<K> va, ub;
+#pragma unroll
+        for (int k = 0; k < K; k++) { va.v[k] = cr[k]; ub.v[k] = cr[K + 1 + k]; }
+        va.ls = 0.0;
+        ub.ls = 0.0;
+        for (int i = 0; i < w; i++) va = vec_mul_op<K>(va, op_load<K>(sWarp + i * OPN));
+        va = vec_mul_op<K>(va, Pe);
+        for (int i = NW - 1; i > w; i--) ub = op_mul_vec<K>(op_load<K>(sWarp + i * OPN), ub);
+        ub = op_mul_vec<K>(Se, ub);
+
+        // backward pass over the chunk (reads e_j from sA before the forward pass overwrites it)
+        {
+            double u[K], s = ub.ls;
+#pragma unroll
+            for (int k = 0; k < K; k++) u[k] = ub.v[k];
+#pragma unroll
+            for (int i = L - 1; i >= 0; i--) {
+                int b = tid * L + i;
+                if (b < nvalid) {
+                    double wv[K];
+#pragma unroll
+                    for (int k = 0; k < K; k++) { sB[k * TB + b] = u[k]; wv[k] = sA[k * TB + b] * u[k]; }
+                    sScB[b] = s;
+#pragma unroll
+                    for (int r = 0; r < K; r++) {
+                        double acc = P.g[r * K] * wv[0];
+#pragma unroll
+                        for (int c = 1; c < K; c++) acc = fma(P.g[r * K + c], wv[c], acc);
+                        u[r] = acc;
+                    }
+                    s += sM[b];
+                }
+            }
+        }
+        // forward pass over the chunk (overwrites e_j with alpha~_j)
+        {
+            double v[K], s = va.ls;
+#pragma unroll
+            for (int k = 0; k < K; k++) v[k] = va.v[k];
+#pragma unroll
+            for (int i = 0; i < L; i++) {
+                int b = tid * L + i;
+                if (b < nvalid) {
+                    double a[K];
+                    if (special0 && b == 0) {
+#pragma unroll
+                        for (int k = 0; k < K; k++) a[k] = v[k];
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < K; c++) {
+                            double acc = v[0] * P.g[c];
+#pragma unroll
+                            for (int r = 1; r < K; r++) acc = fma(v[r], P.g[r * K + c], acc);
+                            a[c] = acc;
+                        }
+                    }
+                    s += sM[b];
+#pragma unroll
+                    for (int k = 0; k < K; k++) { v[k] = a[k] * sA[k * TB + b]; sA[k * TB + b] = v[k]; }
+                    sScF[b] = s;
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- epilogue: striped over bins, everything coalesced ----
+    const double lfT = cr[K], lbT = cr[2 * K + 1];
+    double acc[NS];
+#pragma unroll
+    for (int i = 0; i < NS; i++) acc[i] = 0.0;
+    const double lKK = -log((double)(K * K));
+#pragma unroll 1
+    for (int r = 0; r < L; r++) {
+        const int b = r * NT + tid;
+        const bool valid = b < nvalid;
+        const int64_t j = s0 + b;
+        const bool isfirst = special0 && b == 0;
+        double al[K], be[K], f[K], alp[K], lf[K], lb[K];
+        double scf = 0, scfp = 0, scb = 0, m = 0;
+        if (valid) {
+#pragma unroll
+            for (int k = 0; k < K; k++) { al[k] = sA[k * TB + b]; be[k] = sB[k * TB + b]; f[k] = sF[k * TB + b]; }
+            scf = sScF[b];
+            scb = sScB[b];
+            m = sM[b];
+            if (b > 0) {
+#pragma unroll
+                for (int k = 0; k < K; k++) alp[k] = sA[k * TB + b - 1];
+                scfp = sScF[b - 1];
+            } else {
+#pragma unroll
+                for (int k = 0; k < K; k++) alp[k] = cr[k];
+                scfp = 0.0;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < K; k++) { al[k] = 1.0; be[k] = 1.0; f[k] = 0.0; alp[k] = 1.0; }
+        }
+        // pre-emission forward vector a = alpha~_{j-1} Gamma (in the scale of bin j-1)
+        double a[K];
+        if (isfirst) {
+#pragma unroll
+            for (int k = 0; k < K; k++) a[k] = alp[k];
+        } else {
+#pragma unroll
+            for (int c = 0; c < K; c++) {
+                double s = alp[0] * P.g[c];
+#pragma unroll
+                for (int i = 1; i < K; i++) s = fma(alp[i], P.g[i * K + c], s);
+                a[c] = s;
+            }
+        }
+        double Z = 0.0;
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            lf[k] = (al[k] >= TINY_LIN) ? log(al[k]) : (log(a[k]) + f[k] + (scfp - scf));
+            lb[k] = log(be[k]);
+            Z = fma(al[k], be[k], Z);
+        }
+        sX[(r & 1) * NT * K + tid * K + 0] = lf[0];
+#pragma unroll
+        for (int k = 1; k < K; k++) sX[(r & 1) * NT * K + tid * K + k] = lf[k];
+        if (tid == NT - 1) {
+#pragma unroll
+            for (int k = 0; k < K; k++) sLast[r * K + k] = lf[k];
+        }
+        __syncthreads();
+        double lfp[K];
+        if (tid > 0) {
+#pragma unroll
+            for (int k = 0; k < K; k++) lfp[k] = sX[(r & 1) * NT * K + (tid - 1) * K + k];
+        } else if (r > 0) {
+#pragma unroll
+            for (int k = 0; k < K; k++) lfp[k] = sLast[(r - 1) * K + k];
+        } else {
+#pragma unroll
+            for (int k = 0; k < K; k++) lfp[k] = log(fmax(alp[k], 4.9406564584124654e-324));
+        }
+        if (valid) {
+            const double lZ = log(Z), rZ = 1.0 / Z;
+            double lp1[K], p1[K];
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+                lp1[k] = (lf[k] + lb[k]) - lZ;
+                p1[k] = al[k] * be[k] * rZ;
+                logFP[(int64_t)k * M + j] = lfT + (scf + lf[k]);
+                logBP[(int64_t)k * M + j] = lbT + (scb + lb[k]);
+                logProb1[(int64_t)k * M + j] = lp1[k];
+                acc[K * K] = fma(p1[k], f[k], acc[K * K]);
+            }
+            if (isfirst) {
+#pragma unroll
+                for (int c = 0; c < K * K; c++) logProb2[(int64_t)c * M + j] = lKK;
+            } else {
+                const double d = scfp - scf;
+#pragma unroll
+                for (int l = 0; l < K; l++) {
+                    const double ra = p1[l] / a[l];
+#pragma unroll
+                    for (int i = 0; i < K; i++) {
+                        logProb2[(int64_t)(i * K + l) * M + j] = lp1[l] + ((((lfp[i] + d) + P.lg[i * K + l]) + f[l]) - lf[l]);
+                        acc[i * K + l] = fma(alp[i] * P.g[i * K + l], ra, acc[i * K + l]);
+                    }
+                }
+            }
+        }
+    }
+    // ---- block reduction of the statistics (fixed order -> deterministic) ----
+#pragma unroll
+    for (int i = 0; i < NS; i++) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) acc[i] += __shfl_down_sync(0xffffffffu, acc[i], d);
+    }
+    __syncthreads();
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < NS; i++) sWarp[w * NS + i] = acc[i];
+    }
+    __syncthreads();
+    if (tid < NS) {
+        double s = sWarp[tid];
+        for (int i = 1; i < NW; i++) s += sWarp[i * NS + tid];
+        tilestats[(int64_t)blockIdx.x * NS + tid] = s;
+    }
+}
+
+// First bin of every tile but the first: its joint posterior needs log alpha of the previous bin,
+// which the apply kernel only has as the linear carry.  Where that carry underflowed (an emission
+// below exp(-690) in the previous tile's last bin) the entry is rebuilt from the log-domain logFP.
+template <int K>
+__global__ void fb_boundary_fix_kernel(int64_t M, int64_t nT, int TB, const __grid_constant__ FBParams P,
+                                       const double *__restrict__ carries, const double *__restrict__ logf,
+                                       const double *__restrict__ logFP, const double *__restrict__ logProb1,
+                                       double *__restrict__ logProb2) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x + 1;
+    if (t >= nT) return;
+    const double *cr = carries + t * (2 * K + 2);
+    const int64_t j = t * TB;
+#pragma unroll
+    for (int i = 0; i < K; i++) {
+        if (cr[i] < TINY_LIN) {
+#pragma unroll
+            for (int l = 0; l < K; l++)
+                logProb2[(int64_t)(i * K + l) * M + j] =
+                    logProb1[(int64_t)l * M + j] +
+                    (((logFP[(int64_t)i * M + j - 1] - logFP[(int64_t)l * M + j]) + P.lg[i * K + l]) + logf[(int64_t)l * M + j]);
+        }
+    }
+}
+
+// deterministic sum of the per-tile statistics: out[i] = sum_t tilestats[t*NS + i]
+__global__ void __launch_bounds__(256) fb_stats_kernel(const double *__restrict__ tilestats, int64_t nT, int NS,
+                                                       double *__restrict__ out) {
+    __shared__ double sh[256];
+    for (int i = 0; i < NS; i++) {
+        double s = 0.0;
+        for (int64_t t = threadIdx.x; t < nT; t += 256) s += tilestats[t * NS + i];
+        sh[threadIdx.x] = s;
+        __syncthreads();
+        for (int d = 128; d > 0; d >>= 1) {
+            if ((int)threadIdx.x < d) sh[threadIdx.x] += sh[threadIdx.x + d];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) out[i] = sh[0];
+        __syncthreads();
+    }
+}
+
+// statistics straight from the datasets (used when logProb1/logProb2 were stored from the host,
+// i.e. maxStepProb / computeQFunction called on their own inputs as the reference allows)
+template <int K>
+__global__ void __launch_bounds__(256)
+    fb_stats_from_datasets_kernel(int64_t M, const double *__restrict__ logf, const double *__restrict__ lp1,
+                                  const double *__restrict__ lp2, double *__restrict__ part) {
+    constexpr int NS = K * K + 1;
+    __shared__ double sh[8 * NS];
+    double acc[NS];
+#pragma unroll
+    for (int i = 0; i < NS; i++) acc[i] = 0.0;
+    for (int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x; j < M; j += (int64_t)gridDim.x * 256) {
+        if (j >= 1) {
+#pragma unroll
+            for (int c = 0; c < K * K; c++) acc[c] += exp(__ldg(lp2 + (int64_t)c * M + j));
+        }
+        if (logf) {
+#pragma unroll
+            for (int k = 0; k < K; k++)
+                acc[K * K] = fma(exp(__ldg(lp1 + (int64_t)k * M + j)), __ldg(logf + (int64_t)k * M + j), acc[K * K]);
+        }
+    }
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < NS; i++) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) acc[i] += __shfl_down_sync(0xffffffffu, acc[i], d);
+        if (lane == 0) sh[w * NS + i] = acc[i];
+    }
+    __syncthreads();
+    if (threadIdx.x < NS) {
+        double t = sh[threadIdx.x];
+        for (int i = 1; i < 8; i++) t += sh[i * NS + threadIdx.x];
+        part[(int64_t)blockIdx.x * NS + threadIdx.x] = t;
+    }
+}
+
+template <int K> size_t reduce_smem() {
+    using C = FBCfg<K>;
+    return sizeof(double) * ((size_t)(K + 1) * C::NT * C::L + (C::NT / 32) * (K * K + 1));
+}
+template <int K> size_t apply_smem() {
+    using C = FBCfg<K>;
+    size_t TB = (size_t)C::NT * C::L;
+    return sizeof(double) * ((3 * K + 3) * TB + 2 * C::NT * K + C::L * K + (C::NT / 32) * (K * K + 1));
+}
+
+void fill_params(const ehmm_session *s, FBParams &P) {
+    const int K = s->K;
+    for (int i = 0; i < K; i++)
+        for (int l = 0; l < K; l++) {
+            double g = s->h_gamma[i + l * K];
+            P.g[i * K + l] = g;
+            P.lg[i * K + l] = log(g);
+        }
+}
+
+// scal layout (doubles): [0] ll | [1 .. OPN] block operator | [OPN+1 .. OPN+1+K] fwd vector after block
+// | [OPN+2+K .. OPN+2+2K] bwd vector in front of block | [OPN+3+2K ..] statistics (NS)
+template <int K> constexpr int scal_stats_off() { return (K * K + 1) + 3 + 2 * K; }
+template <int K> constexpr int scal_len() { return scal_stats_off<K>() + K * K + 1; }
+
+template <int K> int64_t num_tiles(int64_t M) {
+    constexpr int64_t TB = (int64_t)FBCfg<K>::NT * FBCfg<K>::L;
+    return (M + TB - 1) / TB;
+}
+
+template <int K> int ensure_scratch(ehmm_session *s) {
+    const int64_t nT = num_tiles<K>(s->M);
+    EHMM_TRY(s->tileops.reserve(sizeof(double) * nT * (K * K + 1)));
+    EHMM_TRY(s->carries.reserve(sizeof(double) * nT * (2 * K + 2)));
+    EHMM_TRY(s->tilestats.reserve(sizeof(double) * nT * (K * K + 1)));
+    EHMM_TRY(s->fbscal.reserve(sizeof(double) * scal_len<K>()));
+    EHMM_TRY(s->logFP.reserve(sizeof(double) * s->M * K));
+    EHMM_TRY(s->logBP.reserve(sizeof(double) * s->M * K));
+    EHMM_TRY(s->logProb1.reserve(sizeof(double) * s->M * K));
+    EHMM_TRY(s->logProb2.reserve(sizeof(double) * s->M * K * K));
+    static bool attr_done[EHMM_MAX_K + 1] = {false};
+    if (!attr_done[K]) {
+        using C = FBCfg<K>;
+        EHMM_CK(cudaFuncSetAttribute(fb_reduce_kernel<K, C::NT, C::L>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)reduce_smem<K>()));
+        EHMM_CK(cudaFuncSetAttribute(fb_apply_kernel<K, C::NT, C::L>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)apply_smem<K>()));
+        attr_done[K] = true;
+    }
+    return EHMM_OK;
+}
+
+template <int K> int launch_reduce(ehmm_session *s, const double *d_logf, int mode0_total) {
+    using C = FBCfg<K>;
+    FBParams P;
+    fill_params(s, P);
+    const int64_t nT = num_tiles<K>(s->M);
+    const int first = (s->m0 == 0) ? 1 : 0;
+    fb_reduce_kernel<K, C::NT, C::L><<<(unsigned)nT, C::NT, reduce_smem<K>(), s->stream>>>(
+        d_logf, s->M, first, P, s->tileops.as<double>());
+    EHMM_CK(cudaGetLastError());
+    if (mode0_total) {
+        CarryIn cin = {};
+        fb_carry_kernel<K><<<1, CARRY_NT, 0, s->stream>>>(s->tileops.as<double>(), nT, 0, cin, nullptr,
+                                                         s->fbscal.as<double>());
+        EHMM_CK(cudaGetLastError());
+    }
+    return EHMM_OK;
+}
+
+template <int K> int launch_apply(ehmm_session *s, const double *d_logf, const CarryIn &cin) {
+    using C = FBCfg<K>;
+    FBParams P;
+    fill_params(s, P);
+    const int64_t nT = num_tiles<K>(s->M);
+    const int first = (s->m0 == 0) ? 1 : 0;
+    double *scal = s->fbscal.as<double>();
+    fb_carry_kernel<K><<<1, CARRY_NT, 0, s->stream>>>(s->tileops.as<double>(), nT, 1, cin, s->carries.as<double>(),
+                                                     scal);
+    EHMM_CK(cudaGetLastError());
+    fb_apply_kernel<K, C::NT, C::L><<<(unsigned)nT, C::NT, apply_smem<K>(), s->stream>>>(
+        d_logf, s->M, first, P, s->carries.as<double>(), s->logFP.as<double>(), s->logBP.as<double>(),
+        s->logProb1.as<double>(), s->logProb2.as<double>(), s->tilestats.as<double>());
+    EHMM_CK(cudaGetLastError());
+    if (nT > 1) {
+        fb_boundary_fix_kernel<K><<<(unsigned)((nT - 1 + 255) / 256), 256, 0, s->stream>>>(
+            s->M, nT, C::NT * C::L, P, s->carries.as<double>(), d_logf, s->logFP.as<double>(), s->logProb1.as<double>(),
+            s->logProb2.as<double>());
+        EHMM_CK(cudaGetLastError());
+    }
+    fb_stats_kernel<<<1, 256, 0, s->stream>>>(s->tilestats.as<double>(), nT, K * K + 1, scal + scal_stats_off<K>());
+    EHMM_CK(cudaGetLastError());
+    return EHMM_OK;
+}
+
+template <int K> int expstep_impl(ehmm_session *s, const double *d_logf) {
+    EHMM_TRY(ensure_scratch<K>(s));
+    EHMM_TRY(launch_reduce<K>(s, d_logf, 0));
+    CarryIn cin = {};  // start vector (pi, 0), end vector (1, 0)
+    for (int k = 0; k < K; k++) { cin.start[k] = s->h_pi[k]; cin.end[k] = 1.0; }
+    EHMM_TRY(launch_apply<K>(s, d_logf, cin));
+    return EHMM_OK;
+}
+
+template <int K> int reduce_impl(ehmm_session *s, const double *d_logf, double *op_host) {
+    EHMM_TRY(ensure_scratch<K>(s));
+    EHMM_TRY(launch_reduce<K>(s, d_logf, 1));
+    EHMM_CK(cudaMemcpyAsync(s->h_pinned, s->fbscal.as<double>() + 1, sizeof(double) * (K * K + 1),
+                            cudaMemcpyDeviceToHost, s->stream));
+    EHMM_CK(cudaStreamSynchronize(s->stream));
+    memcpy(op_host, s->h_pinned, sizeof(double) * (K * K + 1));
+    return EHMM_OK;
+}
+
+template <int K> int apply_impl(ehmm_session *s, const double *d_logf, const double *fwd, const double *bwd,
+                                double *fwd_out) {
+    double *scal = s->fbscal.as<double>();
+    CarryIn cin = {};
+    for (int k = 0; k <= K; k++) { cin.start[k] = fwd[k]; cin.end[k] = bwd[k]; }
+    EHMM_TRY(launch_apply<K>(s, d_logf, cin));
+    if (fwd_out) {
+        EHMM_CK(cudaMemcpyAsync(s->h_pinned + 16, scal + (K * K + 1) + 1, sizeof(double) * (K + 1),
+                                cudaMemcpyDeviceToHost, s->stream));
+        EHMM_CK(cudaStreamSynchronize(s->stream));
+        memcpy(fwd_out, s->h_pinned + 16, sizeof(double) * (K + 1));
+    }
+    return EHMM_OK;
+}
+
+template <int K> int fetch_stats_impl(ehmm_session *s) {
+    constexpr int NS = K * K + 1;
+    double *hp = s->h_pinned + 32;
+    if (s->stats_stale) {
+        const int nblk = 148 * 4;
+        EHMM_TRY(s->fbscal.reserve(sizeof(double) * scal_len<K>()));
+        EHMM_TRY(s->tilestats.reserve(sizeof(double) * nblk * NS));
+        const bool p12 = has(s, DS_P1 | DS_P2);
+        if (p12) {
+            fb_stats_from_datasets_kernel<K><<<nblk, 256, 0, s->stream>>>(
+                s->M, has(s, DS_LOGF) ? s->logf.as<double>() : nullptr, s->logProb1.as<double>(),
+                s->logProb2.as<double>(), s->tilestats.as<double>());
+            EHMM_CK(cudaGetLastError());
+            fb_stats_kernel<<<1, 256, 0, s->stream>>>(s->tilestats.as<double>(), nblk, NS,
+                                                     s->fbscal.as<double>() + scal_stats_off<K>());
+            EHMM_CK(cudaGetLastError());
+            EHMM_CK(cudaMemcpyAsync(hp + 1, s->fbscal.as<double>() + scal_stats_off<K>(), sizeof(double) * NS,
+                                    cudaMemcpyDeviceToHost, s->stream));
+            for (int k = 0; k < K; k++)
+                EHMM_CK(cudaMemcpyAsync(hp + 1 + NS + k, s->logProb1.as<double>() + (int64_t)k * s->M, sizeof(double),
+                                        cudaMemcpyDeviceToHost, s->stream));
+        }
+        if (has(s, DS_FP))
+            for (int k = 0; k < K; k++)
+                EHMM_CK(cudaMemcpyAsync(hp + 1 + NS + K + k, s->logFP.as<double>() + (int64_t)k * s->M + (s->M - 1),
+                                        sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+        EHMM_CK(cudaStreamSynchronize(s->stream));
+        if (p12) {
+            for (int i = 0; i < NS; i++) s->h_stats[i] = hp[1 + i];
+            for (int k = 0; k < K; k++) s->h_lp1_row0[k] = hp[1 + NS + k];
+        }
+        if (has(s, DS_FP)) {  // lse(logFP[M-1,]) as src/computeBIC.cpp:23-26
+            const double *d = hp + 1 + NS + K;
+            double C = d[0], sum = 0;
+            for (int k = 1; k < K; k++) C = d[k] > C ? d[k] : C;
+            for (int k = 0; k < K; k++) sum += exp(d[k] - C);
+            s->h_ll = C + log(sum);
+        }
+        s->stats_on_host = true;
+        return EHMM_OK;
+    }
+    double *scal = s->fbscal.as<double>();
+    EHMM_CK(cudaMemcpyAsync(hp, scal, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    EHMM_CK(cudaMemcpyAsync(hp + 1, scal + scal_stats_off<K>(), sizeof(double) * (K * K + 1), cudaMemcpyDeviceToHost,
+                            s->stream));
+    for (int k = 0; k < K; k++)
+        EHMM_CK(cudaMemcpyAsync(hp + 1 + K * K + 1 + k, s->logProb1.as<double>() + (int64_t)k * s->M, sizeof(double),
+                                cudaMemcpyDeviceToHost, s->stream));
+    EHMM_CK(cudaStreamSynchronize(s->stream));
+    s->h_ll = hp[0];
+    for (int i = 0; i < K * K + 1; i++) s->h_stats[i] = hp[1 + i];
+    for (int k = 0; k < K; k++) s->h_lp1_row0[k] = hp[1 + K * K + 1 + k];
+    s->stats_on_host = true;
+    return EHMM_OK;
+}
+
+}  // namespace
+
+int fb_expstep(ehmm_session *s, const double *d_logf) {
+    s->stats_on_host = false;
+    if (s->K == 2) return expstep_impl<2>(s, d_logf);
+    if (s->K == 3) return expstep_impl<3>(s, d_logf);
+    set_error("expStep: K=%d unsupported (K must be 2 or 3)", s->K);
+    return EHMM_ERR_ARG;
+}
+
+int fb_reduce(ehmm_session *s, const double *d_logf, double *op_host) {
+    s->stats_on_host = false;
+    s->cur_logf = d_logf;
+    if (s->K == 2) return reduce_impl<2>(s, d_logf, op_host);
+    if (s->K == 3) return reduce_impl<3>(s, d_logf, op_host);
+    set_error("expStep: K=%d unsupported (K must be 2 or 3)", s->K);
+    return EHMM_ERR_ARG;
+}
+
+int fb_apply(ehmm_session *s, const double *fwd_carry, const double *bwd_carry, double *fwd_out) {
+    const double *d_logf = s->cur_logf;
+    if (s->K == 2) return apply_impl<2>(s, d_logf, fwd_carry, bwd_carry, fwd_out);
+    if (s->K == 3) return apply_impl<3>(s, d_logf, fwd_carry, bwd_carry, fwd_out);
+    set_error("expStep: K=%d unsupported (K must be 2 or 3)", s->K);
+    return EHMM_ERR_ARG;
+}
+
+int fb_fetch_stats(ehmm_session *s) {
+    if (s->stats_on_host) return EHMM_OK;
+    if (s->K == 2) return fetch_stats_impl<2>(s);
+    if (s->K == 3) return fetch_stats_impl<3>(s);
+    return EHMM_ERR_ARG;
+}
+
+}  // namespace ehmm

@@ -1,0 +1,228 @@
+// glm.cu -- weighted NB-GLM objective and gradient over the rejection tables (replaces glmNB/derivNB
+// and glmMixNB/derivMixNB, R/base-optim.R:109-130,187-255, which R's optim(L-BFGS-B) evaluates over
+// the aggregated group table).  The tables stay on the device as dense bucket vectors indexed by
+// group id; a zero bucket contributes exactly 0, so summing over all G groups equals summing over
+// the reference's non-zero rows.  Block partial sums are reduced in a fixed order (deterministic).
+#include "common.cuh"
+
+namespace ehmm {
+
+namespace {
+
+constexpr int GLM_NT = 256;
+constexpr int GLM_MAXOUT = 8;
+
+// digamma for x > 0: recurrence up to x >= 12, then the asymptotic series (same form as the oracle)
+__device__ __forceinline__ double digamma_pos(double x) {
+    double r = 0.0;
+    while (x < 12.0) { r -= 1.0 / x; x += 1.0; }
+    const double xi = 1.0 / x, x2 = xi * xi;
+    const double s = x2 * (1.0 / 12 - x2 * (1.0 / 120 - x2 * (1.0 / 252 - x2 * (1.0 / 240 -
+                     x2 * (1.0 / 132 - x2 * (691.0 / 32760 - x2 * (1.0 / 12)))))));
+    return r + (log(x) - 0.5 * xi - s);
+}
+
+// log NB(y; size, mu = exp(eta)) with lsize = log(size), lgs = lgamma(size)
+__device__ __forceinline__ double nb_logpmf_direct(double y, double eta, double size, double lsize, double lgs) {
+    const double t = eta - lsize;
+    const double w = log1p(exp(-fabs(t)));
+    const double sp = (t > 0.0) ? t + w : w;
+    const double spm = (t > 0.0) ? w : w - t;
+    const double c = (lgamma(y + size) - lgs) - lgamma(y + 1.0);
+    return (c - size * sp) - y * spm;
+}
+
+template <int NOUT> __device__ __forceinline__ void block_store(double *acc, double *__restrict__ part) {
+    __shared__ double sh[(GLM_NT / 32) * NOUT];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < NOUT; i++) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) acc[i] += __shfl_down_sync(0xffffffffu, acc[i], d);
+        if (lane == 0) sh[w * NOUT + i] = acc[i];
+    }
+    __syncthreads();
+    if (threadIdx.x < NOUT) {
+        double t = sh[threadIdx.x];
+        for (int i = 1; i < GLM_NT / 32; i++) t += sh[i * NOUT + threadIdx.x];
+        part[(int64_t)blockIdx.x * NOUT + threadIdx.x] = t;
+    }
+}
+
+struct NBPar {
+    double b0, b1, phi, size, lsize, lgs, dg_size;
+    int has_ctrl;
+};
+
+// out: [0] = sum w*l, [1] = sum w*r, [2] = sum w*r*ctrl, [3] = sum w*dphi
+__global__ void __launch_bounds__(GLM_NT)
+    glm_nb_kernel(int64_t G, const double *__restrict__ wt, const double *__restrict__ y, const double *__restrict__ off,
+                  const double *__restrict__ ctrl, NBPar P, double *__restrict__ part) {
+    double acc[4] = {0, 0, 0, 0};
+    for (int64_t g = 1 + (int64_t)blockIdx.x * GLM_NT + threadIdx.x; g <= G; g += (int64_t)gridDim.x * GLM_NT) {
+        const double w = wt[g];
+        if (w == 0.0) continue;
+        const double yy = y[g], cv = P.has_ctrl ? ctrl[g] : 0.0;
+        const double eta = (P.has_ctrl ? (P.b0 + cv * P.b1) : P.b0) + off[g];
+        const double mu = exp(eta);
+        double l = nb_logpmf_direct(yy, eta, P.size, P.lsize, P.lgs);
+        if (isinf(l)) l = -690.77552789821368;  // log(1e-300), R/base-optim.R:112
+        const double den = 1.0 + P.phi * mu;
+        const double r = (yy - mu) / den;
+        const double dphi = (log(den) + P.phi * (yy - mu) / den - digamma_pos(yy + P.size) + P.dg_size) / (P.phi * P.phi);
+        acc[0] += w * l;
+        acc[1] += w * r;
+        acc[2] += w * r * cv;
+        acc[3] += w * dphi;
+    }
+    block_store<4>(acc, part);
+}
+
+struct MixPar {
+    double b, db, l, dl, minZero, thr;
+    double size[2], lsize[2], lgs[2], dg[2];  // D = 0 / 1
+    int B;
+};
+
+// out: [0] = value, [1..4] = gradient wrt (b, db, l, dl)
+__global__ void __launch_bounds__(GLM_NT)
+    glm_mix_kernel(int64_t G, int ncol, const double *__restrict__ buckets, const double *__restrict__ y,
+                   const double *__restrict__ off, const uint8_t *__restrict__ dsg, MixPar P, double *__restrict__ part) {
+    double acc[5] = {0, 0, 0, 0, 0};
+    const int64_t total = (int64_t)ncol * (G + 1);
+    for (int64_t idx = (int64_t)blockIdx.x * GLM_NT + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * GLM_NT) {
+        const double w = buckets[idx];
+        if (w == 0.0) continue;
+        const int c = (int)(idx / (G + 1));
+        const int64_t g = idx - (int64_t)c * (G + 1);
+        int D;
+        if (c == 0) D = 0;
+        else if (c == ncol - 1) D = 1;
+        else D = dsg[g + (int64_t)(c - 1) * (G + 1)];
+        const double yy = y[g];
+        // background: b + off; mixture: (b + db*D) + off; enrichment: (b + db) + off  -- same values
+        const double eta = (D ? (P.b + P.db) : P.b) + off[g];
+        const double mu = exp(eta), ph = P.size[D];
+        const double lpmf = nb_logpmf_direct(yy, eta, ph, P.lsize[D], P.lgs[D]);
+        const double lv = (lpmf > P.thr) ? lpmf : log(exp(lpmf) + P.minZero);
+        acc[0] += -w * lv;
+        const double a = -w * (yy / mu - ((yy + ph) / (mu + ph))) * mu;
+        const double cc = -w * (digamma_pos(yy + ph) - P.dg[D] + 1.0 + P.lsize[D] - (yy + ph) / (mu + ph) - log(mu + ph)) * ph;
+        acc[1] += a;
+        acc[2] += a * D;
+        acc[3] += cc;
+        acc[4] += cc * D;
+    }
+    block_store<5>(acc, part);
+}
+
+__global__ void __launch_bounds__(256) glm_final_kernel(const double *__restrict__ part, int nblk, int ncol,
+                                                        double *__restrict__ out) {
+    __shared__ double sh[256];
+    for (int c = 0; c < ncol; c++) {
+        double s = 0.0;
+        for (int i = threadIdx.x; i < nblk; i += 256) s += part[(int64_t)i * ncol + c];
+        sh[threadIdx.x] = s;
+        __syncthreads();
+        for (int d = 128; d > 0; d >>= 1) {
+            if ((int)threadIdx.x < d) sh[threadIdx.x] += sh[threadIdx.x + d];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) out[c] = sh[0];
+        __syncthreads();
+    }
+}
+
+double host_digamma(double x) {
+    double r = 0.0;
+    while (x < 12.0) { r -= 1.0 / x; x += 1.0; }
+    const double xi = 1.0 / x, x2 = xi * xi;
+    const double s = x2 * (1.0 / 12 - x2 * (1.0 / 120 - x2 * (1.0 / 252 - x2 * (1.0 / 240 -
+                     x2 * (1.0 / 132 - x2 * (691.0 / 32760 - x2 * (1.0 / 12)))))));
+    return r + (log(x) - 0.5 * xi - s);
+}
+
+int blocks_for(int64_t n) {
+    int64_t b = (n + GLM_NT - 1) / GLM_NT;
+    if (b < 1) b = 1;
+    if (b > 148 * 4) b = 148 * 4;
+    return (int)b;
+}
+
+int finish(ehmm_session *s, int nblk, int nout, double *host_out) {
+    double *part = s->glm_part.as<double>();
+    double *out = part + (size_t)148 * 4 * GLM_MAXOUT;
+    glm_final_kernel<<<1, 256, 0, s->stream>>>(part, nblk, nout, out);
+    EHMM_CK(cudaGetLastError());
+    EHMM_CK(cudaMemcpyAsync(s->h_pinned + 128, out, sizeof(double) * nout, cudaMemcpyDeviceToHost, s->stream));
+    EHMM_CK(cudaStreamSynchronize(s->stream));
+    for (int i = 0; i < nout; i++) host_out[i] = s->h_pinned[128 + i];
+    return EHMM_OK;
+}
+
+}  // namespace
+
+int glm_nb(ehmm_session *s, int column, const double *par, int P_, double *value, double *grad) {
+    EHMM_REQUIRE(P_ == 1 || P_ == 2, EHMM_ERR_ARG, "glmNB: P must be 1 (Intercept) or 2 (Intercept, controls)");
+    EHMM_REQUIRE(P_ == 1 || s->u_ctrl.p, EHMM_ERR_STATE, "glmNB: dtUnique has no controls column");
+    const double phi = par[P_];
+    EHMM_REQUIRE(phi > 0 && isfinite(phi), EHMM_ERR_ARG, "glmNB: dispersion %g must be positive", phi);
+    NBPar P;
+    P.b0 = par[0];
+    P.b1 = P_ == 2 ? par[1] : 0.0;
+    P.phi = phi;
+    P.size = 1.0 / phi;
+    P.lsize = log(P.size);
+    P.lgs = lgamma(P.size);
+    P.dg_size = host_digamma(P.size);
+    P.has_ctrl = (P_ == 2);
+    EHMM_TRY(s->glm_part.reserve(sizeof(double) * ((size_t)148 * 4 * GLM_MAXOUT + GLM_MAXOUT)));
+    const int nblk = blocks_for(s->G);
+    glm_nb_kernel<<<nblk, GLM_NT, 0, s->stream>>>(s->G, s->rc_buckets.as<double>() + (size_t)column * (s->G + 1),
+                                                 s->u_chip.as<double>(), s->u_off.as<double>(),
+                                                 s->u_ctrl.as<double>(), P, s->glm_part.as<double>());
+    EHMM_CK(cudaGetLastError());
+    double o[4];
+    EHMM_TRY(finish(s, nblk, 4, o));
+    *value = -o[0];
+    if (grad) {
+        grad[0] = -o[1];
+        if (P_ == 2) grad[1] = -o[2];
+        grad[P_] = -o[3];
+    }
+    return EHMM_OK;
+}
+
+int glm_mix_nb(ehmm_session *s, const double *par, double minZero, double *value, double *grad) {
+    EHMM_REQUIRE(s->u_dsg.p, EHMM_ERR_STATE, "glmMixNB: dtUnique has no Dsg.Mix columns (ehmm_set_groups)");
+    MixPar P;
+    P.b = par[0];
+    P.db = par[1];
+    P.l = par[2];
+    P.dl = par[3];
+    P.minZero = minZero;
+    P.thr = log(minZero) + 40.0;
+    P.B = s->B;
+    for (int D = 0; D < 2; D++) {
+        const double ls = D ? (par[2] + par[3]) : par[2];
+        P.size[D] = exp(ls);
+        P.lsize[D] = log(P.size[D]);
+        P.lgs[D] = lgamma(P.size[D]);
+        P.dg[D] = host_digamma(P.size[D]);
+    }
+    EHMM_TRY(s->glm_part.reserve(sizeof(double) * ((size_t)148 * 4 * GLM_MAXOUT + GLM_MAXOUT)));
+    const int ncol = s->B + 2;
+    const int nblk = blocks_for((int64_t)ncol * (s->G + 1));
+    glm_mix_kernel<<<nblk, GLM_NT, 0, s->stream>>>(s->G, ncol, s->rc_buckets.as<double>(), s->u_chip.as<double>(),
+                                                  s->u_off.as<double>(), s->u_dsg.as<uint8_t>(), P,
+                                                  s->glm_part.as<double>());
+    EHMM_CK(cudaGetLastError());
+    double o[5];
+    EHMM_TRY(finish(s, nblk, 5, o));
+    *value = o[0];
+    if (grad)
+        for (int i = 0; i < 4; i++) grad[i] = o[1 + i];
+    return EHMM_OK;
+}
+
+}  // namespace ehmm

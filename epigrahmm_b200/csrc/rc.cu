@@ -1,0 +1,421 @@
+// rc.cu -- rejection-controlled reweighting and aggregation by group (replaces
+// src/consensusRejectionControlled.cpp, src/differentialRejectionControlled.cpp, src/reweight.cpp,
+// src/rbinomVectorized.cpp and src/aggregate.cpp, which loop sequentially over bins drawing from
+// R's global Mersenne-Twister).
+//
+// The r-th bin (state-major, then ascending bin) whose posterior weight x satisfies 0 < x < p
+// consumes the r-th uniform of the stream.  That order is recovered with a stream compaction:
+//   rc_count_kernel : flags per (column, block)                      (reads 8 B/bin/column)
+//   rc_scan_kernel  : exclusive scan of the block counts (column-major) -> uniform offsets
+//   rc_apply_kernel : in-block ranks, Bernoulli thinning exactly as R's rbinom(1, x/p), and
+//                     scatter-add of the surviving weights into the group buckets
+// Uniforms come either from a caller-supplied buffer (parity harness: the oracle consumes the same
+// buffer) or from R's MT19937 stream generated on the device from the session's .Random.seed.
+#include "common.cuh"
+#include <vector>
+
+namespace ehmm {
+
+namespace {
+
+constexpr int RC_NT = 256;
+constexpr int RC_STRIPS = 8;
+constexpr int RC_TB = RC_NT * RC_STRIPS;  // bins per block
+constexpr int MT_N = 624, MT_M = 397;
+
+// ---- R's unif_rand() (Mersenne-Twister) ------------------------------------------------------
+__device__ __forceinline__ uint32_t mt_twist(uint32_t a, uint32_t b) {
+    uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
+    return (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+}
+__device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
+    y ^= (y >> 11);
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    y ^= (y >> 18);
+    return y;
+}
+// MT_genrand() * 2^-32 followed by fixup() into (0,1)
+__device__ __forceinline__ double mt_to_unif(uint32_t tempered) {
+    const double i2_32m1 = 2.328306437080797e-10;
+    double x = (double)tempered * 2.3283064365386963e-10;
+    if (x <= 0.0) return 0.5 * i2_32m1;
+    if ((1.0 - x) <= 0.0) return 1.0 - 0.5 * i2_32m1;
+    return x;
+}
+
+// Sequential-in-blocks MT19937: one CTA advances the 624-word state; within a block of 624 the
+// recurrence is 227-wide parallel (three phases).  Writes n tempered words and the final state.
+__global__ void __launch_bounds__(256) mt_generate_kernel(uint32_t *__restrict__ state, int64_t n,
+                                                          uint32_t *__restrict__ out) {
+    __shared__ uint32_t buf[2][MT_N];
+    const int tid = threadIdx.x;
+    for (int i = tid; i < MT_N; i += 256) buf[0][i] = state[1 + i];
+    int pos = (int)state[0];
+    __syncthreads();
+    int cur = 0;
+    int64_t produced = 0;
+    while (true) {
+        int64_t cnt = min((int64_t)(MT_N - pos), n - produced);
+        for (int kk = tid; kk < cnt; kk += 256) out[produced + kk] = mt_temper(buf[cur][pos + kk]);
+        produced += cnt;
+        pos += (int)cnt;
+        if (produced >= n) break;
+        const uint32_t *od = buf[cur];
+        uint32_t *nw = buf[cur ^ 1];
+        for (int kk = tid; kk < MT_N - MT_M; kk += 256) nw[kk] = od[kk + MT_M] ^ mt_twist(od[kk], od[kk + 1]);
+        __syncthreads();
+        for (int kk = MT_N - MT_M + tid; kk < 2 * (MT_N - MT_M); kk += 256)
+            nw[kk] = nw[kk - (MT_N - MT_M)] ^ mt_twist(od[kk], od[kk + 1]);
+        __syncthreads();
+        for (int kk = 2 * (MT_N - MT_M) + tid; kk < MT_N; kk += 256)
+            nw[kk] = nw[kk - (MT_N - MT_M)] ^ ((kk == MT_N - 1) ? mt_twist(od[kk], nw[0]) : mt_twist(od[kk], od[kk + 1]));
+        __syncthreads();
+        cur ^= 1;
+        pos = 0;
+    }
+    __syncthreads();
+    for (int i = tid; i < MT_N; i += 256) state[1 + i] = buf[cur][i];
+    if (tid == 0) state[0] = (uint32_t)pos;
+}
+
+// ---- weights -----------------------------------------------------------------------------------
+// column c of the consensus model: exp(logProb1[:,c]); of the differential model: background,
+// B mixture components P1[:,1]*eta[:,b], enrichment (src/differentialRejectionControlled.cpp:34-45)
+struct RCSrc {
+    const double *lp1;
+    const double *eta;
+    int64_t M;
+    int B;         // 0 = consensus
+    int columns;
+};
+
+__device__ __forceinline__ double rc_weight(const RCSrc &S, int c, int64_t j) {
+    if (S.B == 0) return exp(__ldg(S.lp1 + (int64_t)c * S.M + j));
+    if (c == 0) return exp(__ldg(S.lp1 + j));
+    if (c == S.B + 1) return exp(__ldg(S.lp1 + 2 * S.M + j));
+    return exp(__ldg(S.lp1 + S.M + j)) * __ldg(S.eta + (int64_t)(c - 1) * S.M + j);
+}
+
+__global__ void __launch_bounds__(RC_NT) rc_count_kernel(RCSrc S, double p, int64_t nblk, int *__restrict__ counts) {
+    __shared__ int sh[RC_NT / 32];
+    const int c = blockIdx.y;
+    const int64_t base = (int64_t)blockIdx.x * RC_TB;
+    int cnt = 0;
+#pragma unroll
+    for (int r = 0; r < RC_STRIPS; r++) {
+        const int64_t j = base + r * RC_NT + threadIdx.x;
+        if (j < S.M) {
+            const double x = rc_weight(S, c, j);
+            cnt += (x < p && x / p != 0.0) ? 1 : 0;
+        }
+    }
+    for (int d = 16; d > 0; d >>= 1) cnt += __shfl_down_sync(0xffffffffu, cnt, d);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int i = 0; i < RC_NT / 32; i++) t += sh[i];
+        counts[(int64_t)c * nblk + blockIdx.x] = t;
+    }
+}
+
+// exclusive scan of n ints into int64 offsets; offsets[n] = total.  One CTA.
+__global__ void __launch_bounds__(1024) rc_scan_kernel(const int *__restrict__ counts, int64_t n,
+                                                       int64_t *__restrict__ offsets) {
+    __shared__ int64_t sh[1024];
+    __shared__ int64_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int64_t base = 0; base < n; base += 1024) {
+        const int64_t i = base + threadIdx.x;
+        const int64_t v = (i < n) ? counts[i] : 0;
+        sh[threadIdx.x] = v;
+        __syncthreads();
+        for (int d = 1; d < 1024; d <<= 1) {
+            int64_t t = (threadIdx.x >= d) ? sh[threadIdx.x - d] : 0;
+            __syncthreads();
+            sh[threadIdx.x] += t;
+            __syncthreads();
+        }
+        if (i < n) offsets[i] = carry + sh[threadIdx.x] - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry += sh[1023];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) offsets[n] = carry;
+}
+
+// R::rbinom(1, pp) by inversion given the uniform it would draw (nmath/rbinom.c, n*min(p,1-p) < 30).
+// For n = 1 the inner loop ends at ix = 0 when u < q and at ix = 1 otherwise (u - q < q*(p/q) holds
+// for every u unif_rand() can return), so no second uniform is ever consumed.
+__device__ __forceinline__ double rbinom1(double pp, double u) {
+    const double pm = fmin(pp, 1.0 - pp), q = 1.0 - pm;
+    int ix = (u < q) ? 0 : 1;
+    if (pp > 0.5) ix = 1 - ix;
+    return (double)ix;
+}
+
+template <typename UT> __device__ __forceinline__ double get_unif(const UT *u, int64_t i);
+template <> __device__ __forceinline__ double get_unif<double>(const double *u, int64_t i) { return __ldg(u + i); }
+template <> __device__ __forceinline__ double get_unif<uint32_t>(const uint32_t *u, int64_t i) {
+    return mt_to_unif(__ldg(u + i));
+}
+
+// nrep = 1 with group stride 0 for the consensus model (only f[0..M-1] is read, Q6 in SURVEY.md);
+// nrep = N for the differential model (repmat(w, N, 1) against the M*N group ids).
+template <typename UT>
+__global__ void __launch_bounds__(RC_NT)
+    rc_apply_kernel(RCSrc S, double p, int64_t nblk, const int64_t *__restrict__ offsets, const UT *__restrict__ unif,
+                    const int32_t *__restrict__ group, int nrep, int64_t G, double *__restrict__ buckets,
+                    double *__restrict__ wout) {
+    __shared__ int sh[RC_NT / 32];
+    __shared__ int running;
+    const int c = blockIdx.y;
+    const int64_t base = (int64_t)blockIdx.x * RC_TB;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t ubase = offsets[(int64_t)c * nblk + blockIdx.x];
+    double *bk = buckets + (int64_t)c * (G + 1);
+    if (threadIdx.x == 0) running = 0;
+    __syncthreads();
+    for (int r = 0; r < RC_STRIPS; r++) {
+        const int64_t j = base + r * RC_NT + threadIdx.x;
+        double x = 0.0;
+        bool flag = false;
+        if (j < S.M) {
+            x = rc_weight(S, c, j);
+            flag = (x < p && x / p != 0.0);
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, flag);
+        if (lane == 0) sh[w] = __popc(bal);
+        __syncthreads();
+        int before = running;
+        for (int i = 0; i < w; i++) before += sh[i];
+        const int rank = before + __popc(bal & ((1u << lane) - 1u));
+        if (j < S.M) {
+            double wt = x;
+            if (x < p) wt = flag ? rbinom1(x / p, get_unif<UT>(unif, ubase + rank)) * p : 0.0;
+            if (wout) wout[(int64_t)c * S.M + j] = wt;
+            if (wt != 0.0) {
+                for (int i = 0; i < nrep; i++) atomicAdd(bk + __ldg(group + j + (int64_t)i * S.M), wt);
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int t = 0;
+            for (int i = 0; i < RC_NT / 32; i++) t += sh[i];
+            running += t;
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void aggregate_kernel(const double *__restrict__ x, int64_t n, const int32_t *__restrict__ f,
+                                 double *__restrict__ buckets) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double v = x[i];
+        if (v != 0.0) atomicAdd(buckets + f[i], v);
+    }
+}
+
+// x -> exp-free variant for the exported reweight(): weights are given directly
+__global__ void __launch_bounds__(RC_NT) rw_count_kernel(const double *__restrict__ x, int64_t n, double p,
+                                                         int *__restrict__ counts) {
+    __shared__ int sh[RC_NT / 32];
+    const int64_t base = (int64_t)blockIdx.x * RC_TB;
+    int cnt = 0;
+    for (int r = 0; r < RC_STRIPS; r++) {
+        const int64_t j = base + r * RC_NT + threadIdx.x;
+        if (j < n) cnt += (x[j] < p && x[j] / p != 0.0) ? 1 : 0;
+    }
+    for (int d = 16; d > 0; d >>= 1) cnt += __shfl_down_sync(0xffffffffu, cnt, d);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int i = 0; i < RC_NT / 32; i++) t += sh[i];
+        counts[blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(RC_NT) rw_apply_kernel(double *__restrict__ x, int64_t n, double p,
+                                                         const int64_t *__restrict__ offsets,
+                                                         const double *__restrict__ unif) {
+    __shared__ int sh[RC_NT / 32];
+    __shared__ int running;
+    const int64_t base = (int64_t)blockIdx.x * RC_TB;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t ubase = offsets[blockIdx.x];
+    if (threadIdx.x == 0) running = 0;
+    __syncthreads();
+    for (int r = 0; r < RC_STRIPS; r++) {
+        const int64_t j = base + r * RC_NT + threadIdx.x;
+        double v = (j < n) ? x[j] : 1.0e300;
+        const bool flag = (j < n) && (v < p && v / p != 0.0);
+        const unsigned bal = __ballot_sync(0xffffffffu, flag);
+        if (lane == 0) sh[w] = __popc(bal);
+        __syncthreads();
+        int before = running;
+        for (int i = 0; i < w; i++) before += sh[i];
+        const int rank = before + __popc(bal & ((1u << lane) - 1u));
+        if (j < n && v < p) x[j] = flag ? rbinom1(v / p, __ldg(unif + ubase + rank)) * p : 0.0;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int t = 0;
+            for (int i = 0; i < RC_NT / 32; i++) t += sh[i];
+            running += t;
+        }
+        __syncthreads();
+    }
+}
+
+int run_rc(ehmm_session *s, const RCSrc &S, double p, int nrep, const double *uniforms, int64_t n_uniforms,
+           int64_t *consumed) {
+    const int64_t nblk = (s->M + RC_TB - 1) / RC_TB;
+    const int64_t ncnt = nblk * S.columns;
+    EHMM_TRY(s->rc_flag.reserve(sizeof(int) * ncnt));
+    EHMM_TRY(s->rc_scan.reserve(sizeof(int64_t) * (ncnt + 1)));
+    EHMM_TRY(s->rc_buckets.reserve(sizeof(double) * (size_t)S.columns * (s->G + 1)));
+    EHMM_CK(cudaMemsetAsync(s->rc_buckets.p, 0, sizeof(double) * (size_t)S.columns * (s->G + 1), s->stream));
+    dim3 grid((unsigned)nblk, (unsigned)S.columns);
+    int64_t total = 0;
+    if (p > 0.0) {
+        rc_count_kernel<<<grid, RC_NT, 0, s->stream>>>(S, p, nblk, s->rc_flag.as<int>());
+        EHMM_CK(cudaGetLastError());
+        rc_scan_kernel<<<1, 1024, 0, s->stream>>>(s->rc_flag.as<int>(), ncnt, s->rc_scan.as<int64_t>());
+        EHMM_CK(cudaGetLastError());
+        EHMM_CK(cudaMemcpyAsync(s->h_pinned + 200, s->rc_scan.as<int64_t>() + ncnt, sizeof(int64_t), cudaMemcpyDeviceToHost,
+                                s->stream));
+        EHMM_CK(cudaStreamSynchronize(s->stream));
+        memcpy(&total, s->h_pinned + 200, sizeof(int64_t));
+    } else {
+        EHMM_CK(cudaMemsetAsync(s->rc_scan.p, 0, sizeof(int64_t) * (ncnt + 1), s->stream));
+    }
+    const int32_t *grp = s->group.as<int32_t>();
+    if (uniforms) {
+        EHMM_REQUIRE(total <= n_uniforms, EHMM_ERR_RNG, "rejection control needs %lld uniforms, buffer holds %lld",
+                     (long long)total, (long long)n_uniforms);
+        EHMM_TRY(s->rc_unif.reserve(sizeof(double) * (size_t)(total > 0 ? total : 1)));
+        if (total > 0)
+            EHMM_CK(cudaMemcpyAsync(s->rc_unif.p, uniforms, sizeof(double) * total, cudaMemcpyHostToDevice, s->stream));
+        rc_apply_kernel<double><<<grid, RC_NT, 0, s->stream>>>(S, p, nblk, s->rc_scan.as<int64_t>(),
+                                                               s->rc_unif.as<double>(), grp, nrep, s->G,
+                                                               s->rc_buckets.as<double>(), nullptr);
+    } else {
+        EHMM_REQUIRE(s->rng_set || total == 0, EHMM_ERR_RNG,
+                     "rejection control needs %lld uniforms: pass a buffer or call ehmm_rng_set_state", (long long)total);
+        EHMM_TRY(s->rc_unif.reserve(sizeof(uint32_t) * (size_t)(total > 0 ? total : 1)));
+        EHMM_TRY(s->mt_raw.reserve(sizeof(uint32_t) * 625));
+        if (total > 0) {
+            EHMM_CK(cudaMemcpyAsync(s->mt_raw.p, s->rng_state, sizeof(uint32_t) * 625, cudaMemcpyHostToDevice, s->stream));
+            mt_generate_kernel<<<1, 256, 0, s->stream>>>(s->mt_raw.as<uint32_t>(), total, s->rc_unif.as<uint32_t>());
+            EHMM_CK(cudaGetLastError());
+            EHMM_CK(cudaMemcpyAsync(s->rng_state, s->mt_raw.p, sizeof(uint32_t) * 625, cudaMemcpyDeviceToHost, s->stream));
+        }
+        rc_apply_kernel<uint32_t><<<grid, RC_NT, 0, s->stream>>>(S, p, nblk, s->rc_scan.as<int64_t>(),
+                                                                 s->rc_unif.as<uint32_t>(), grp, nrep, s->G,
+                                                                 s->rc_buckets.as<double>(), nullptr);
+    }
+    EHMM_CK(cudaGetLastError());
+    EHMM_CK(cudaStreamSynchronize(s->stream));
+    s->rc_columns = S.columns;
+    s->rc_N = nrep;
+    if (consumed) *consumed = total;
+    return EHMM_OK;
+}
+
+struct TmpDev {
+    void *p = nullptr;
+    ~TmpDev() { if (p) cudaFree(p); }
+    int alloc(size_t n) {
+        cudaError_t e = cudaMalloc(&p, n ? n : 8);
+        if (e != cudaSuccess) { set_error("cudaMalloc(%zu): %s", n, cudaGetErrorString(e)); return EHMM_ERR_NOMEM; }
+        return EHMM_OK;
+    }
+};
+
+}  // namespace
+
+int rc_consensus(ehmm_session *s, double p, const double *uniforms, int64_t n_uniforms, int64_t *consumed) {
+    RCSrc S = {s->logProb1.as<double>(), nullptr, s->M, 0, s->K};
+    return run_rc(s, S, p, 1, uniforms, n_uniforms, consumed);
+}
+
+int rc_differential(ehmm_session *s, double p, int N, const double *uniforms, int64_t n_uniforms, int64_t *consumed) {
+    EHMM_REQUIRE(s->K == 3 && s->B > 0, EHMM_ERR_ARG, "differentialRejectionControlled needs K=3 and mixture components");
+    RCSrc S = {s->logProb1.as<double>(), s->eta.as<double>(), s->M, s->B, s->B + 2};
+    return run_rc(s, S, p, N, uniforms, n_uniforms, consumed);
+}
+
+static int fetch_column(ehmm_session *s, int column, std::vector<double> &h) {
+    h.resize((size_t)s->G + 1);
+    EHMM_CK(cudaMemcpyAsync(h.data(), s->rc_buckets.as<double>() + (size_t)column * (s->G + 1), sizeof(double) * (s->G + 1),
+                            cudaMemcpyDeviceToHost, s->stream));
+    EHMM_CK(cudaStreamSynchronize(s->stream));
+    return EHMM_OK;
+}
+
+int rc_table_rows(ehmm_session *s, int column, int64_t *rows) {
+    std::vector<double> h;
+    EHMM_TRY(fetch_column(s, column, h));
+    int64_t n = 0;
+    for (double v : h) n += (v != 0.0);
+    *rows = n;
+    return EHMM_OK;
+}
+
+int rc_table_fetch(ehmm_session *s, int column, double *sums, double *ids) {
+    std::vector<double> h;
+    EHMM_TRY(fetch_column(s, column, h));
+    int64_t n = 0;
+    for (size_t g = 0; g < h.size(); g++)
+        if (h[g] != 0.0) { sums[n] = h[g]; ids[n] = (double)g; n++; }
+    return EHMM_OK;
+}
+
+int rc_reweight(int device, double *x, int64_t n, double p, const double *uniforms, int64_t n_uniforms, int64_t *consumed) {
+    EHMM_CK(cudaSetDevice(device));
+    if (consumed) *consumed = 0;
+    if (n == 0 || !(p > 0.0)) return EHMM_OK;
+    const int64_t nblk = (n + RC_TB - 1) / RC_TB;
+    TmpDev dx, dc, doff, du;
+    EHMM_TRY(dx.alloc(sizeof(double) * n));
+    EHMM_TRY(dc.alloc(sizeof(int) * nblk));
+    EHMM_TRY(doff.alloc(sizeof(int64_t) * (nblk + 1)));
+    EHMM_CK(cudaMemcpy(dx.p, x, sizeof(double) * n, cudaMemcpyHostToDevice));
+    rw_count_kernel<<<(unsigned)nblk, RC_NT>>>((const double *)dx.p, n, p, (int *)dc.p);
+    rc_scan_kernel<<<1, 1024>>>((const int *)dc.p, nblk, (int64_t *)doff.p);
+    EHMM_CK(cudaGetLastError());
+    int64_t total = 0;
+    EHMM_CK(cudaMemcpy(&total, (int64_t *)doff.p + nblk, sizeof(int64_t), cudaMemcpyDeviceToHost));
+    EHMM_REQUIRE(uniforms || total == 0, EHMM_ERR_RNG, "reweight needs %lld uniforms", (long long)total);
+    EHMM_REQUIRE(total <= n_uniforms, EHMM_ERR_RNG, "reweight needs %lld uniforms, buffer holds %lld", (long long)total,
+                 (long long)n_uniforms);
+    EHMM_TRY(du.alloc(sizeof(double) * total));
+    if (total) EHMM_CK(cudaMemcpy(du.p, uniforms, sizeof(double) * total, cudaMemcpyHostToDevice));
+    rw_apply_kernel<<<(unsigned)nblk, RC_NT>>>((double *)dx.p, n, p, (const int64_t *)doff.p, (const double *)du.p);
+    EHMM_CK(cudaGetLastError());
+    EHMM_CK(cudaMemcpy(x, dx.p, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    if (consumed) *consumed = total;
+    return EHMM_OK;
+}
+
+int rc_aggregate(int device, const double *x, int64_t n, const int32_t *f, int64_t G, double *buckets) {
+    EHMM_CK(cudaSetDevice(device));
+    for (int64_t i = 0; i < n; i++)
+        EHMM_REQUIRE(f[i] >= 0 && f[i] <= G, EHMM_ERR_ARG, "aggregate: group id %d at %lld outside [0, %lld]", f[i],
+                     (long long)i, (long long)G);
+    TmpDev dx, df, db;
+    EHMM_TRY(dx.alloc(sizeof(double) * n));
+    EHMM_TRY(df.alloc(sizeof(int32_t) * n));
+    EHMM_TRY(db.alloc(sizeof(double) * (G + 1)));
+    EHMM_CK(cudaMemcpy(dx.p, x, sizeof(double) * n, cudaMemcpyHostToDevice));
+    EHMM_CK(cudaMemcpy(df.p, f, sizeof(int32_t) * n, cudaMemcpyHostToDevice));
+    EHMM_CK(cudaMemset(db.p, 0, sizeof(double) * (G + 1)));
+    if (n) aggregate_kernel<<<148 * 4, 256>>>((const double *)dx.p, n, (const int32_t *)df.p, (double *)db.p);
+    EHMM_CK(cudaGetLastError());
+    EHMM_CK(cudaMemcpy(buckets, db.p, sizeof(double) * (G + 1), cudaMemcpyDeviceToHost));
+    return EHMM_OK;
+}
+
+}  // namespace ehmm

@@ -1,0 +1,601 @@
+// session.cu -- the extern "C" boundary (include/ehmm.h): session registry, data upload,
+// dataset access and the small host-side finishing steps of the M-step (maxStepProb's floor and
+// renormalisation, Q and BIC from the fused sufficient statistics).
+#include "common.cuh"
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <map>
+#include <mutex>
+
+namespace ehmm {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+static std::mutex g_mu;
+static std::map<std::string, ehmm_session *> g_sessions;
+
+namespace {
+
+__global__ void minmax_i32_kernel(const int32_t *__restrict__ x, int64_t n, int *__restrict__ out) {
+    int mx = INT_MIN, mn = INT_MAX;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        int v = __ldg(x + i);
+        mx = max(mx, v);
+        mn = min(mn, v);
+    }
+    for (int d = 16; d > 0; d >>= 1) {
+        mx = max(mx, __shfl_down_sync(0xffffffffu, mx, d));
+        mn = min(mn, __shfl_down_sync(0xffffffffu, mn, d));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMax(out, mx);
+        atomicMin(out + 1, mn);
+    }
+}
+
+__global__ void exp_kernel(const double *__restrict__ x, int64_t n, double *__restrict__ y) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        y[i] = exp(x[i]);
+}
+
+int scan_counts(ehmm_session *s) {
+    int h[2] = {INT_MIN, INT_MAX};
+    EHMM_TRY(s->misc.reserve(64));
+    int *d = s->misc.as<int>();
+    EHMM_CK(cudaMemcpyAsync(d, h, sizeof(h), cudaMemcpyHostToDevice, s->stream));
+    minmax_i32_kernel<<<148 * 8, 256, 0, s->stream>>>(s->d_counts, s->M * s->N, d);
+    EHMM_CK(cudaGetLastError());
+    EHMM_CK(cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, s->stream));
+    EHMM_CK(cudaStreamSynchronize(s->stream));
+    EHMM_REQUIRE(h[1] >= 0, EHMM_ERR_ARG, "counts must be non-negative (min = %d)", h[1]);
+    s->count_max = h[0];
+    return EHMM_OK;
+}
+
+struct DS {
+    ehmm::DevBuf *buf;
+    int64_t rows, cols;
+    unsigned bit;
+};
+
+int lookup(ehmm_session *s, const char *name, DS &d) {
+    const int64_t M = s->M;
+    const int K = s->K;
+    if (!strcmp(name, "logLikelihood")) d = {&s->logf, M, K, DS_LOGF};
+    else if (!strcmp(name, "logFP")) d = {&s->logFP, M, K, DS_FP};
+    else if (!strcmp(name, "logBP")) d = {&s->logBP, M, K, DS_BP};
+    else if (!strcmp(name, "logProb1")) d = {&s->logProb1, M, K, DS_P1};
+    else if (!strcmp(name, "logProb2")) d = {&s->logProb2, M, K * K, DS_P2};
+    else if (!strcmp(name, "mixtureProb")) d = {&s->eta, M, s->B, DS_ETA};
+    else if (!strcmp(name, "viterbi")) d = {&s->viterbi, M, 1, DS_VIT};
+    else {
+        set_error("unknown dataset '%s'", name);
+        return EHMM_ERR_ARG;
+    }
+    return EHMM_OK;
+}
+
+int set_theta(ehmm_session *s, const double *pi, const double *gamma) {
+    EHMM_REQUIRE(pi && gamma, EHMM_ERR_ARG, "pi/gamma must not be null");
+    const int K = s->K;
+    for (int k = 0; k < K; k++) {
+        EHMM_REQUIRE(pi[k] >= 0 && isfinite(pi[k]), EHMM_ERR_ARG, "pi[%d] = %g is not a probability", k, pi[k]);
+        s->h_pi[k] = pi[k];
+    }
+    for (int i = 0; i < K * K; i++) {
+        EHMM_REQUIRE(gamma[i] >= 0 && isfinite(gamma[i]), EHMM_ERR_ARG, "gamma[%d] = %g is not a probability", i, gamma[i]);
+        s->h_gamma[i] = gamma[i];
+    }
+    return EHMM_OK;
+}
+
+int upload_logf(ehmm_session *s, const double *logf, const double **d_out) {
+    if (logf) {
+        EHMM_TRY(s->logf.reserve(sizeof(double) * s->M * s->K));
+        EHMM_CK(cudaMemcpyAsync(s->logf.p, logf, sizeof(double) * s->M * s->K, cudaMemcpyHostToDevice, s->stream));
+        s->valid |= DS_LOGF;
+    }
+    EHMM_REQUIRE(has(s, DS_LOGF), EHMM_ERR_STATE, "expStep: no logf given and no emission has been computed");
+    *d_out = s->logf.as<double>();
+    return EHMM_OK;
+}
+
+}  // namespace
+}  // namespace ehmm
+
+using namespace ehmm;
+
+extern "C" {
+
+const char *ehmm_last_error(void) { return g_err; }
+int ehmm_version(void) { return 100; }
+
+int ehmm_device_count(int *n) {
+    EHMM_REQUIRE(n, EHMM_ERR_ARG, "null pointer");
+    EHMM_CK(cudaGetDeviceCount(n));
+    return EHMM_OK;
+}
+
+int ehmm_session_open(const char *key, int64_t M, int K, int device, ehmm_session **out) {
+    EHMM_REQUIRE(key && out, EHMM_ERR_ARG, "null pointer");
+    EHMM_REQUIRE(M >= 1, EHMM_ERR_ARG, "M must be >= 1 (M=%lld)", (long long)M);
+    EHMM_REQUIRE(K == 2 || K == 3, EHMM_ERR_ARG, "K must be 2 or 3 (K=%d)", K);
+    int ndev = 0;
+    EHMM_CK(cudaGetDeviceCount(&ndev));
+    EHMM_REQUIRE(device >= 0 && device < ndev, EHMM_ERR_CUDA, "device %d not available (%d CUDA devices)", device, ndev);
+    EHMM_CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    EHMM_CK(cudaGetDeviceProperties(&prop, device));
+    EHMM_REQUIRE(prop.major == 10, EHMM_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device,
+                 prop.major, prop.minor);
+    ehmm_session *s = new ehmm_session();
+    s->key = key;
+    s->device = device;
+    s->M = M;
+    s->Mtot = M;
+    s->K = K;
+    EHMM_CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    EHMM_CK(cudaStreamCreateWithFlags(&s->stream2, cudaStreamNonBlocking));
+    EHMM_CK(cudaEventCreateWithFlags(&s->ev, cudaEventDisableTiming));
+    EHMM_CK(cudaMallocHost(&s->h_pinned, sizeof(double) * 256));
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        auto it = g_sessions.find(s->key);
+        if (it != g_sessions.end()) {
+            // same key re-opened: the reference would overwrite the HDF5 file (hdf5_opts::replace)
+            ehmm_session *old = it->second;
+            g_sessions.erase(it);
+            ehmm_session_close(old);
+        }
+        g_sessions[s->key] = s;
+    }
+    *out = s;
+    return EHMM_OK;
+}
+
+int ehmm_session_find(const char *key, ehmm_session **out) {
+    EHMM_REQUIRE(key && out, EHMM_ERR_ARG, "null pointer");
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_sessions.find(key);
+    EHMM_REQUIRE(it != g_sessions.end(), EHMM_ERR_STATE, "no session for '%s' (the reference would fail to open the HDF5 file)", key);
+    *out = it->second;
+    return EHMM_OK;
+}
+
+int ehmm_session_close(ehmm_session *s) {
+    if (!s) return EHMM_OK;
+    cudaSetDevice(s->device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    if (s->stream2) cudaStreamSynchronize(s->stream2);
+    {
+        std::unique_lock<std::mutex> lk(g_mu, std::try_to_lock);
+        auto it = g_sessions.find(s->key);
+        if (it != g_sessions.end() && it->second == s) g_sessions.erase(it);
+    }
+    DevBuf *bufs[] = {&s->counts_own, &s->offsets_own, &s->controls_own, &s->group, &s->u_chip, &s->u_off, &s->u_ctrl,
+                      &s->u_dsg, &s->logf, &s->logFP, &s->logBP, &s->logProb1, &s->logProb2, &s->eta, &s->viterbi,
+                      &s->tileops, &s->carries, &s->tilestats, &s->fbscal, &s->rc_w, &s->rc_flag, &s->rc_scan,
+                      &s->rc_buckets, &s->rc_unif, &s->rc_tmp, &s->mt_raw, &s->lgtab, &s->glm_part, &s->misc};
+    for (DevBuf *b : bufs) b->release();
+    if (s->h_pinned) cudaFreeHost(s->h_pinned);
+    if (s->ev) cudaEventDestroy(s->ev);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    if (s->stream2) cudaStreamDestroy(s->stream2);
+    delete s;
+    return EHMM_OK;
+}
+
+int ehmm_session_stream(ehmm_session *s, void **stream) {
+    EHMM_REQUIRE(s && stream, EHMM_ERR_ARG, "null pointer");
+    *stream = (void *)s->stream;
+    return EHMM_OK;
+}
+
+int ehmm_session_sync(ehmm_session *s) {
+    EHMM_TRY(check_session(s));
+    EHMM_CK(cudaStreamSynchronize(s->stream));
+    return EHMM_OK;
+}
+
+int ehmm_session_set_block(ehmm_session *s, int64_t m0, int64_t Mtot) {
+    EHMM_TRY(check_session(s));
+    EHMM_REQUIRE(m0 >= 0 && m0 + s->M <= Mtot, EHMM_ERR_ARG, "block [%lld, %lld) outside chain of %lld bins", (long long)m0,
+                 (long long)(m0 + s->M), (long long)Mtot);
+    s->m0 = m0;
+    s->Mtot = Mtot;
+    return EHMM_OK;
+}
+
+int ehmm_set_data(ehmm_session *s, int N, const int32_t *counts, const double *offsets, const double *controls) {
+    EHMM_TRY(check_session(s));
+    EHMM_REQUIRE(N >= 1 && counts && offsets, EHMM_ERR_ARG, "set_data: N >= 1, counts and offsets required");
+    const size_t n = (size_t)s->M * N;
+    EHMM_TRY(s->counts_own.reserve(n * sizeof(int32_t)));
+    EHMM_TRY(s->offsets_own.reserve(n * sizeof(double)));
+    EHMM_CK(cudaMemcpyAsync(s->counts_own.p, counts, n * sizeof(int32_t), cudaMemcpyHostToDevice, s->stream));
+    EHMM_CK(cudaMemcpyAsync(s->offsets_own.p, offsets, n * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    const double *dc = nullptr;
+    if (controls) {
+        EHMM_TRY(s->controls_own.reserve(n * sizeof(double)));
+        EHMM_CK(cudaMemcpyAsync(s->controls_own.p, controls, n * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+        dc = s->controls_own.as<double>();
+    }
+    s->N = N;
+    s->d_counts = s->counts_own.as<int32_t>();
+    s->d_offsets = s->offsets_own.as<double>();
+    s->d_controls = dc;
+    return scan_counts(s);
+}
+
+int ehmm_set_data_device(ehmm_session *s, int N, const int32_t *counts, const double *offsets, const double *controls) {
+    EHMM_TRY(check_session(s));
+    EHMM_REQUIRE(N >= 1 && counts && offsets, EHMM_ERR_ARG, "set_data: N >= 1, counts and offsets required");
+    s->N = N;
+    s->d_counts = counts;
+    s->d_offsets = offsets;
+    s->d_controls = controls;
+    return scan_counts(s);
+}
+
+int ehmm_set_groups(ehmm_session *s, const int32_t *group, int64_t G, const double *u_chip, const double *u_offsets,
+                    const double *u_controls, const uint8_t *u_dsg) {
+    EHMM_TRY(check_session(s));
+    EHMM_REQUIRE(s->N > 0, EHMM_ERR_STATE, "set_groups: call ehmm_set_data first");
+    EHMM_REQUIRE(group && G >= 1 && u_chip && u_offsets, EHMM_ERR_ARG, "set_groups: group, G, ChIP and offsets required");
+    const size_t n = (size_t)s->M * s->N;
+    EHMM_TRY(s->group.reserve(n * sizeof(int32_t)));
+    EHMM_CK(cudaMemcpyAsync(s->group.p, group, n * sizeof(int32_t), cudaMemcpyHostToDevice, s->stream));
+    // dtUnique columns are stored with a leading unused slot so that the 1-based group id indexes them
+    const size_t gb = (size_t)(G + 1) * sizeof(double);
+    EHMM_TRY(s->u_chip.reserve(gb));
+    EHMM_TRY(s->u_off.reserve(gb));
+    EHMM_CK(cudaMemsetAsync(s->u_chip.p, 0, sizeof(double), s->stream));
+    EHMM_CK(cudaMemsetAsync(s->u_off.p, 0, sizeof(double), s->stream));
+    EHMM_CK(cudaMemcpyAsync(s->u_chip.as<double>() + 1, u_chip, gb - sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    EHMM_CK(cudaMemcpyAsync(s->u_off.as<double>() + 1, u_offsets, gb - sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    if (u_controls) {
+        EHMM_TRY(s->u_ctrl.reserve(gb));
+        EHMM_CK(cudaMemsetAsync(s->u_ctrl.p, 0, sizeof(double), s->stream));
+        EHMM_CK(cudaMemcpyAsync(s->u_ctrl.as<double>() + 1, u_controls, gb - sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    } else {
+        s->u_ctrl.release();
+    }
+    if (u_dsg) {
+        EHMM_REQUIRE(s->B > 0, EHMM_ERR_STATE, "set_groups: Dsg.Mix columns given before ehmm_set_design");
+        // host layout G x B column-major -> device (G+1) x B column-major
+        EHMM_TRY(s->u_dsg.reserve((size_t)(G + 1) * s->B));
+        EHMM_CK(cudaMemsetAsync(s->u_dsg.p, 0, (size_t)(G + 1) * s->B, s->stream));
+        for (int b = 0; b < s->B; b++)
+            EHMM_CK(cudaMemcpyAsync(s->u_dsg.as<uint8_t>() + (size_t)b * (G + 1) + 1, u_dsg + (size_t)b * G, (size_t)G,
+                                    cudaMemcpyHostToDevice, s->stream));
+    }
+    EHMM_CK(cudaStreamSynchronize(s->stream));
+    s->G = G;
+    s->rc_columns = 0;
+    return EHMM_OK;
+}
+
+int ehmm_set_design(ehmm_session *s, int B, const uint8_t *design) {
+    EHMM_TRY(check_session(s));
+    EHMM_REQUIRE(s->N > 0, EHMM_ERR_STATE, "set_design: call ehmm_set_data first");
+    EHMM_REQUIRE(B >= 1 && B <= EHMM_MAX_B && design, EHMM_ERR_ARG, "set_design: 1 <= B <= %d", EHMM_MAX_B);
+    EHMM_REQUIRE(s->N <= 64, EHMM_ERR_ARG, "set_design: at most 64 samples");
+    memcpy(s->design, design, (size_t)B * s->N);
+    s->B = B;
+    s->have_design = true;
+    return EHMM_OK;
+}
+
+int ehmm_loglik_consensus(ehmm_session *s, const double *theta1, const double *theta2, int P, double minZero) {
+    EHMM_TRY(check_session(s));
+    EHMM_REQUIRE(theta1 && theta2, EHMM_ERR_ARG, "null parameters");
+    return emis_consensus(s, theta1, theta2, P, minZero);
+}
+
+int ehmm_loglik_init(ehmm_session *s, const double *psi1, const double *psi2) {
+    EHMM_TRY(check_session(s));
+    EHMM_REQUIRE(psi1 && psi2, EHMM_ERR_ARG, "null parameters");
+    return emis_init(s, psi1, psi2);
+}
+
+int ehmm_loglik_differential_hmm(ehmm_session *s, const double *delta, const double *psi, double minZero) {
+    EHMM_TRY(check_session(s));
+    EHMM_REQUIRE(delta && psi, EHMM_ERR_ARG, "null parameters");
+    return emis_differential_hmm(s, delta, psi, minZero);
+}
+
+int ehmm_inner_expstep(ehmm_session *s, const double *delta, const double *psi, double minZero) {
+    EHMM_TRY(check_session(s));
+    EHMM_REQUIRE(delta && psi, EHMM_ERR_ARG, "null parameters");
+    return emis_inner_estep(s, delta, psi, minZero);
+}
+
+int ehmm_expstep(ehmm_session *s, const double *pi, const double *gamma, const double *logf) {
+    EHMM_TRY(check_session(s));
+    EHMM_TRY(set_theta(s, pi, gamma));
+    const double *d_logf = nullptr;
+    EHMM_TRY(upload_logf(s, logf, &d_logf));
+    EHMM_TRY(fb_expstep(s, d_logf));
+    s->valid |= DS_ESTEP;
+    s->stats_stale = false;
+    return EHMM_OK;
+}
+
+int ehmm_expstep_device(ehmm_session *s, const double *pi, const double *gamma, const double *logf_device) {
+    EHMM_TRY(check_session(s));
+    EHMM_TRY(set_theta(s, pi, gamma));
+    EHMM_REQUIRE(logf_device, EHMM_ERR_ARG, "null logf");
+    EHMM_TRY(fb_expstep(s, logf_device));
+    s->valid |= DS_ESTEP;
+    s->stats_stale = false;
+    return EHMM_OK;
+}
+
+int ehmm_expstep_reduce(ehmm_session *s, const double *pi, const double *gamma, const double *logf, double *op) {
+    EHMM_TRY(check_session(s));
+    EHMM_TRY(set_theta(s, pi, gamma));
+    EHMM_REQUIRE(op, EHMM_ERR_ARG, "null op");
+    const double *d_logf = nullptr;
+    EHMM_TRY(upload_logf(s, logf, &d_logf));
+    EHMM_TRY(fb_reduce(s, d_logf, op));
+    s->reduce_pending = true;
+    return EHMM_OK;
+}
+
+int ehmm_expstep_apply(ehmm_session *s, const double *fwd_carry, const double *bwd_carry, double *fwd_out) {
+    EHMM_TRY(check_session(s));
+    EHMM_REQUIRE(s->reduce_pending, EHMM_ERR_STATE, "expstep_apply without expstep_reduce");
+    EHMM_REQUIRE(fwd_carry && bwd_carry, EHMM_ERR_ARG, "null carry");
+    EHMM_TRY(fb_apply(s, fwd_carry, bwd_carry, fwd_out));
+    s->reduce_pending = false;
+    s->valid |= DS_ESTEP;
+    s->stats_stale = false;
+    return EHMM_OK;
+}
+
+int ehmm_estep_stats(ehmm_session *s, double *stats) {
+    EHMM_TRY(check_session(s));
+    EHMM_REQUIRE(has(s, DS_P1 | DS_P2) && stats, EHMM_ERR_STATE, "estep_stats: expStep has not run");
+    EHMM_TRY(fb_fetch_stats(s));
+    for (int i = 0; i < s->K * s->K + 1; i++) stats[i] = s->h_stats[i];
+    return EHMM_OK;
+}
+
+int ehmm_estep_set_stats(ehmm_session *s, const double *stats, const double *logprob1_row0, double loglik) {
+    EHMM_TRY(check_session(s));
+    EHMM_REQUIRE(stats && logprob1_row0, EHMM_ERR_ARG, "null pointer");
+    for (int i = 0; i < s->K * s->K + 1; i++) s->h_stats[i] = stats[i];
+    for (int k = 0; k < s->K; k++) s->h_lp1_row0[k] = logprob1_row0[k];
+    s->h_ll = loglik;
+    s->stats_on_host = true;
+    return EHMM_OK;
+}
+
+int ehmm_loglik_value(ehmm_session *s, double *ll) {
+    EHMM_TRY(check_session(s));
+    EHMM_REQUIRE(has(s, DS_FP) && ll, EHMM_ERR_STATE, "loglik: expStep has not run");
+    EHMM_TRY(fb_fetch_stats(s));
+    *ll = s->h_ll;
+    return EHMM_OK;
+}
+
+// maxStepProb (src/maxStepProb.cpp:58-77): the sums over bins come from the statistics fused into
+// the E-step kernel; only the K*K divisions, the 1e-6 floor and the renormalisation run here.
+int ehmm_maxstepprob(ehmm_session *s, double *pi_out, double *gamma_out) {
+    EHMM_TRY(check_session(s));
+    EHMM_REQUIRE(has(s, DS_P1 | DS_P2), EHMM_ERR_STATE, "maxStepProb: expStep has not run for '%s'", s->key.c_str());
+    EHMM_REQUIRE(pi_out && gamma_out, EHMM_ERR_ARG, "null output");
+    EHMM_TRY(fb_fetch_stats(s));
+    const int K = s->K;
+    for (int k1 = 0; k1 < K; k1++) {
+        double denom = 0;
+        for (int k2 = 0; k2 < K; k2++) denom += s->h_stats[k1 * K + k2];
+        for (int k2 = 0; k2 < K; k2++) gamma_out[k1 + k2 * K] = s->h_stats[k1 * K + k2] / denom;
+    }
+    double sum = 0;
+    for (int k = 0; k < K; k++) {
+        double p = exp(s->h_lp1_row0[k]);
+        if (p < 0.000001) p = 0.000001;
+        pi_out[k] = p;
+    }
+    {   // Armadillo accu order: two running sums
+        double v1 = 0, v2 = 0;
+        for (int k = 0; k < K; k++) ((k & 1) ? v2 : v1) += pi_out[k];
+        sum = v1 + v2;
+    }
+    for (int k = 0; k < K; k++) pi_out[k] /= sum;
+    for (int i = 0; i < K * K; i++)
+        if (gamma_out[i] < 0.000001) gamma_out[i] = 0.000001;
+    for (int k1 = 0; k1 < K; k1++) {
+        double v1 = 0, v2 = 0;
+        for (int k2 = 0; k2 < K; k2++) ((k2 & 1) ? v2 : v1) += fabs(gamma_out[k1 + k2 * K]);
+        const double nrm = v1 + v2;
+        for (int k2 = 0; k2 < K; k2++) gamma_out[k1 + k2 * K] /= nrm;
+    }
+    return EHMM_OK;
+}
+
+// computeQFunction (src/computeQFunction.cpp:30)
+int ehmm_qfunction(ehmm_session *s, const double *pi, const double *gamma, double *q) {
+    EHMM_TRY(check_session(s));
+    EHMM_REQUIRE(has(s, DS_LOGF | DS_P1 | DS_P2), EHMM_ERR_STATE, "computeQFunction: expStep has not run");
+    EHMM_REQUIRE(pi && gamma && q, EHMM_ERR_ARG, "null pointer");
+    EHMM_TRY(fb_fetch_stats(s));
+    const int K = s->K;
+    double q0 = 0, q2 = 0;
+    for (int k = 0; k < K; k++) q0 += exp(s->h_lp1_row0[k]) * log(pi[k]);
+    for (int i = 0; i < K; i++)
+        for (int l = 0; l < K; l++) q2 += s->h_stats[i * K + l] * log(gamma[i + l * K]);
+    *q = q0 + s->h_stats[K * K] + q2;
+    return EHMM_OK;
+}
+
+// computeBIC (src/computeBIC.cpp:23-26)
+int ehmm_bic(ehmm_session *s, int numPar, int numSamples, double *bic) {
+    EHMM_TRY(check_session(s));
+    EHMM_REQUIRE(has(s, DS_FP) && bic, EHMM_ERR_STATE, "computeBIC: expStep has not run");
+    EHMM_TRY(fb_fetch_stats(s));
+    *bic = -2 * s->h_ll + numPar * log((double)((int64_t)numSamples * s->Mtot));
+    return EHMM_OK;
+}
+
+int ehmm_inner_maxstepprob(ehmm_session *s, double *delta_out) {
+    EHMM_TRY(check_session(s));
+    EHMM_REQUIRE(delta_out, EHMM_ERR_ARG, "null output");
+    return inner_maxstepprob(s, delta_out);
+}
+
+int ehmm_marginal_probability(ehmm_session *s, double *out) {
+    EHMM_TRY(check_session(s));
+    EHMM_REQUIRE(has(s, DS_P1) && out, EHMM_ERR_STATE, "getMarginalProbability: expStep has not run");
+    const int64_t n = s->M * s->K;
+    EHMM_TRY(s->rc_tmp.reserve(sizeof(double) * n));
+    exp_kernel<<<148 * 8, 256, 0, s->stream>>>(s->logProb1.as<double>(), n, s->rc_tmp.as<double>());
+    EHMM_CK(cudaGetLastError());
+    EHMM_CK(cudaMemcpyAsync(out, s->rc_tmp.p, sizeof(double) * n, cudaMemcpyDeviceToHost, s->stream));
+    EHMM_CK(cudaStreamSynchronize(s->stream));
+    return EHMM_OK;
+}
+
+int ehmm_viterbi(ehmm_session *s, const double *pi, const double *gamma, double *states_out) {
+    EHMM_TRY(check_session(s));
+    EHMM_REQUIRE(has(s, DS_FP), EHMM_ERR_STATE, "computeViterbiSequence: no logFP dataset (expStep has not run)");
+    EHMM_REQUIRE(pi && gamma, EHMM_ERR_ARG, "null pointer");
+    return viterbi(s, pi, gamma, states_out);
+}
+
+int ehmm_rng_set_state(ehmm_session *s, const uint32_t *state625) {
+    EHMM_REQUIRE(s && state625, EHMM_ERR_ARG, "null pointer");
+    EHMM_REQUIRE(state625[0] <= 624, EHMM_ERR_ARG, "mti = %u out of range", state625[0]);
+    memcpy(s->rng_state, state625, sizeof(uint32_t) * 625);
+    s->rng_set = true;
+    return EHMM_OK;
+}
+
+int ehmm_rng_get_state(ehmm_session *s, uint32_t *state625) {
+    EHMM_REQUIRE(s && state625, EHMM_ERR_ARG, "null pointer");
+    memcpy(state625, s->rng_state, sizeof(uint32_t) * 625);
+    return EHMM_OK;
+}
+
+int ehmm_rc_consensus(ehmm_session *s, double p, const double *uniforms, int64_t n_uniforms, int64_t *consumed) {
+    EHMM_TRY(check_session(s));
+    EHMM_REQUIRE(has(s, DS_P1), EHMM_ERR_STATE, "consensusRejectionControlled: expStep has not run");
+    EHMM_REQUIRE(s->G > 0, EHMM_ERR_STATE, "consensusRejectionControlled: ehmm_set_groups has not been called");
+    return rc_consensus(s, p, uniforms, n_uniforms, consumed);
+}
+
+int ehmm_rc_differential(ehmm_session *s, double p, int N, const double *uniforms, int64_t n_uniforms, int64_t *consumed) {
+    EHMM_TRY(check_session(s));
+    EHMM_REQUIRE(has(s, DS_P1 | DS_ETA), EHMM_ERR_STATE, "differentialRejectionControlled: needs logProb1 and mixtureProb");
+    EHMM_REQUIRE(s->G > 0, EHMM_ERR_STATE, "differentialRejectionControlled: ehmm_set_groups has not been called");
+    EHMM_REQUIRE(N == s->N, EHMM_ERR_ARG, "N=%d does not match the data (N=%d)", N, s->N);
+    return rc_differential(s, p, N, uniforms, n_uniforms, consumed);
+}
+
+int ehmm_rc_table_rows(ehmm_session *s, int column, int64_t *rows) {
+    EHMM_TRY(check_session(s));
+    EHMM_REQUIRE(rows && column >= 0 && column < s->rc_columns, EHMM_ERR_ARG, "bad column %d (have %d)", column, s->rc_columns);
+    return rc_table_rows(s, column, rows);
+}
+
+int ehmm_rc_table_fetch(ehmm_session *s, int column, double *sums, double *ids) {
+    EHMM_TRY(check_session(s));
+    EHMM_REQUIRE(sums && ids && column >= 0 && column < s->rc_columns, EHMM_ERR_ARG, "bad column %d (have %d)", column, s->rc_columns);
+    return rc_table_fetch(s, column, sums, ids);
+}
+
+int ehmm_rc_buckets_fetch(ehmm_session *s, int column, double *buckets) {
+    EHMM_TRY(check_session(s));
+    EHMM_REQUIRE(buckets && column >= 0 && column < s->rc_columns, EHMM_ERR_ARG, "bad column %d (have %d)", column, s->rc_columns);
+    EHMM_CK(cudaMemcpyAsync(buckets, s->rc_buckets.as<double>() + (size_t)column * (s->G + 1), sizeof(double) * (s->G + 1),
+                            cudaMemcpyDeviceToHost, s->stream));
+    EHMM_CK(cudaStreamSynchronize(s->stream));
+    return EHMM_OK;
+}
+
+int ehmm_reweight(int device, double *x, int64_t n, double p, const double *uniforms, int64_t n_uniforms, int64_t *consumed) {
+    EHMM_REQUIRE(x && n >= 0, EHMM_ERR_ARG, "null pointer");
+    return rc_reweight(device, x, n, p, uniforms, n_uniforms, consumed);
+}
+
+int ehmm_aggregate(int device, const double *x, int64_t n, const int32_t *f, int64_t G, double *buckets) {
+    EHMM_REQUIRE(x && f && buckets && n >= 0 && G >= 0, EHMM_ERR_ARG, "null pointer");
+    return rc_aggregate(device, x, n, f, G, buckets);
+}
+
+int ehmm_glm_nb(ehmm_session *s, int column, const double *par, int P, double *value, double *grad) {
+    EHMM_TRY(check_session(s));
+    EHMM_REQUIRE(par && value, EHMM_ERR_ARG, "null pointer");
+    EHMM_REQUIRE(column >= 0 && column < s->rc_columns, EHMM_ERR_STATE, "glmNB: rejection table %d not available", column);
+    return glm_nb(s, column, par, P, value, grad);
+}
+
+int ehmm_glm_mix_nb(ehmm_session *s, const double *par, double minZero, double *value, double *grad) {
+    EHMM_TRY(check_session(s));
+    EHMM_REQUIRE(par && value, EHMM_ERR_ARG, "null pointer");
+    EHMM_REQUIRE(s->rc_columns == s->B + 2 && s->B > 0, EHMM_ERR_STATE, "glmMixNB: differential rejection tables not available");
+    return glm_mix_nb(s, par, minZero, value, grad);
+}
+
+int ehmm_dataset_dims(ehmm_session *s, const char *name, int64_t *rows, int64_t *cols) {
+    EHMM_REQUIRE(s && name && rows && cols, EHMM_ERR_ARG, "null pointer");
+    DS d;
+    EHMM_TRY(lookup(s, name, d));
+    EHMM_REQUIRE(has(s, d.bit), EHMM_ERR_STATE, "dataset '%s' has not been written", name);
+    *rows = d.rows;
+    *cols = d.cols;
+    return EHMM_OK;
+}
+
+int ehmm_fetch(ehmm_session *s, const char *name, double *dst, int64_t n) {
+    EHMM_TRY(check_session(s));
+    EHMM_REQUIRE(name && dst, EHMM_ERR_ARG, "null pointer");
+    DS d;
+    EHMM_TRY(lookup(s, name, d));
+    EHMM_REQUIRE(has(s, d.bit), EHMM_ERR_STATE, "dataset '%s' has not been written", name);
+    EHMM_REQUIRE(n == d.rows * d.cols, EHMM_ERR_ARG, "dataset '%s' has %lld elements, buffer has %lld", name,
+                 (long long)(d.rows * d.cols), (long long)n);
+    EHMM_CK(cudaMemcpyAsync(dst, d.buf->p, sizeof(double) * n, cudaMemcpyDeviceToHost, s->stream));
+    EHMM_CK(cudaStreamSynchronize(s->stream));
+    return EHMM_OK;
+}
+
+int ehmm_device_ptr(ehmm_session *s, const char *name, void **ptr) {
+    EHMM_REQUIRE(s && name && ptr, EHMM_ERR_ARG, "null pointer");
+    DS d;
+    EHMM_TRY(lookup(s, name, d));
+    EHMM_REQUIRE(has(s, d.bit), EHMM_ERR_STATE, "dataset '%s' has not been written", name);
+    *ptr = d.buf->p;
+    return EHMM_OK;
+}
+
+int ehmm_store(ehmm_session *s, const char *name, const double *src, int64_t rows, int64_t cols) {
+    EHMM_TRY(check_session(s));
+    EHMM_REQUIRE(name && src, EHMM_ERR_ARG, "null pointer");
+    DS d;
+    if (!strcmp(name, "mixtureProb") && s->B == 0) s->B = (int)cols;
+    EHMM_TRY(lookup(s, name, d));
+    EHMM_REQUIRE(rows == d.rows && cols == d.cols, EHMM_ERR_ARG, "dataset '%s' must be %lld x %lld (got %lld x %lld)", name,
+                 (long long)d.rows, (long long)d.cols, (long long)rows, (long long)cols);
+    EHMM_TRY(d.buf->reserve(sizeof(double) * rows * cols));
+    EHMM_CK(cudaMemcpyAsync(d.buf->p, src, sizeof(double) * rows * cols, cudaMemcpyHostToDevice, s->stream));
+    EHMM_CK(cudaStreamSynchronize(s->stream));
+    s->valid |= d.bit;
+    if (d.bit & (DS_ESTEP | DS_LOGF)) {
+        // a dataset was replaced from the host: the fused statistics no longer describe it
+        s->stats_on_host = false;
+        s->stats_stale = true;
+    }
+    return EHMM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,286 @@
+"""Device-resident EM session: a thin object wrapper over the C ABI.
+
+A session plays the role of the reference's HDF5 file (``metadata(object)$output``):
+it is created per fit, keyed by the same path string, and holds the datasets
+logLikelihood / logFP / logBP / logProb1 / logProb2 / mixtureProb / viterbi in HBM.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import bptr, check, dptr, iptr, lib
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _cm(a, dtype=np.float64):
+    """column-major (R / Armadillo) copy"""
+    return np.asfortranarray(a, dtype=dtype)
+
+
+class Session:
+    def __init__(self, key: str, M: int, K: int, device: int = 0):
+        self._h = C.c_void_p()
+        check(lib.ehmm_session_open(str(key).encode(), int(M), int(K), int(device), C.byref(self._h)))
+        self.key, self.M, self.K, self.device = str(key), int(M), int(K), int(device)
+        self.N = 0
+        self.B = 0
+        self.G = 0
+
+    # -- lifetime --------------------------------------------------------------------------
+    def close(self):
+        if self._h:
+            check(lib.ehmm_session_close(self._h))
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def stream(self) -> int:
+        p = C.c_void_p()
+        check(lib.ehmm_session_stream(self._h, C.byref(p)))
+        return p.value or 0
+
+    def sync(self):
+        check(lib.ehmm_session_sync(self._h))
+
+    def set_block(self, m0: int, Mtot: int):
+        check(lib.ehmm_session_set_block(self._h, int(m0), int(Mtot)))
+
+    # -- data ------------------------------------------------------------------------------
+    def set_data(self, counts, offsets, controls=None):
+        counts = _cm(counts, np.int32).reshape(self.M, -1, order="F")
+        N = counts.shape[1]
+        offsets = _cm(offsets).reshape(self.M, N, order="F")
+        ctrl = None if controls is None else _cm(controls).reshape(self.M, N, order="F")
+        check(lib.ehmm_set_data(self._h, N, iptr(counts), dptr(offsets), dptr(ctrl)))
+        self.N = N
+
+    def set_data_device(self, N, counts_ptr, offsets_ptr, controls_ptr=None):
+        check(lib.ehmm_set_data_device(self._h, int(N), C.c_void_p(counts_ptr), C.c_void_p(offsets_ptr),
+                                       C.c_void_p(controls_ptr) if controls_ptr else None))
+        self.N = int(N)
+
+    def set_design(self, design):
+        d = np.ascontiguousarray(design, dtype=np.uint8)
+        assert d.ndim == 2 and d.shape[1] == self.N, "design must be B x N"
+        check(lib.ehmm_set_design(self._h, d.shape[0], bptr(d)))
+        self.B = d.shape[0]
+
+    def set_groups(self, group, u_chip, u_offsets, u_controls=None, u_dsg=None):
+        g = _cm(group, np.int32).reshape(self.M, self.N, order="F")
+        uc, uo = _f64(u_chip), _f64(u_offsets)
+        G = uc.size
+        uctrl = None if u_controls is None else _f64(u_controls)
+        udsg = None if u_dsg is None else np.asfortranarray(u_dsg, dtype=np.uint8)
+        check(lib.ehmm_set_groups(self._h, iptr(g), G, dptr(uc), dptr(uo), dptr(uctrl), bptr(udsg)))
+        self.G = G
+
+    # -- emission --------------------------------------------------------------------------
+    def loglik_consensus(self, psi, minZero):
+        t1, t2 = _f64(psi[0]), _f64(psi[1])
+        check(lib.ehmm_loglik_consensus(self._h, dptr(t1), dptr(t2), t1.size, float(minZero)))
+
+    def loglik_init(self, psi):
+        t1, t2 = _f64(psi[0]), _f64(psi[1])
+        check(lib.ehmm_loglik_init(self._h, dptr(t1), dptr(t2)))
+
+    def loglik_differential_hmm(self, delta, psi, minZero):
+        d, p = _f64(delta), _f64(np.concatenate([np.ravel(x) for x in psi]) if isinstance(psi, (list, tuple)) else psi)
+        check(lib.ehmm_loglik_differential_hmm(self._h, dptr(d), dptr(p), float(minZero)))
+
+    def inner_expstep(self, delta, psi, minZero):
+        d, p = _f64(delta), _f64(np.concatenate([np.ravel(x) for x in psi]) if isinstance(psi, (list, tuple)) else psi)
+        check(lib.ehmm_inner_expstep(self._h, dptr(d), dptr(p), float(minZero)))
+
+    # -- E-step / M-step -------------------------------------------------------------------
+    def expstep(self, pi, gamma, logf=None):
+        pi, gamma = _f64(pi), _cm(gamma)
+        lf = None if logf is None else _cm(logf)
+        if lf is not None:
+            assert lf.shape == (self.M, self.K), "logf must be M x K"
+        check(lib.ehmm_expstep(self._h, dptr(pi), dptr(gamma), dptr(lf)))
+
+    def expstep_device(self, pi, gamma, logf_ptr: int):
+        pi, gamma = _f64(pi), _cm(gamma)
+        check(lib.ehmm_expstep_device(self._h, dptr(pi), dptr(gamma), C.c_void_p(logf_ptr)))
+
+    def expstep_reduce(self, pi, gamma, logf=None):
+        pi, gamma = _f64(pi), _cm(gamma)
+        lf = None if logf is None else _cm(logf)
+        op = np.empty(self.K * self.K + 1)
+        check(lib.ehmm_expstep_reduce(self._h, dptr(pi), dptr(gamma), dptr(lf), dptr(op)))
+        return op
+
+    def expstep_apply(self, fwd, bwd):
+        fwd, bwd = _f64(fwd), _f64(bwd)
+        out = np.empty(self.K + 1)
+        check(lib.ehmm_expstep_apply(self._h, dptr(fwd), dptr(bwd), dptr(out)))
+        return out
+
+    def estep_stats(self):
+        st = np.empty(self.K * self.K + 1)
+        check(lib.ehmm_estep_stats(self._h, dptr(st)))
+        return st
+
+    def estep_set_stats(self, stats, lp1_row0, loglik):
+        check(lib.ehmm_estep_set_stats(self._h, dptr(_f64(stats)), dptr(_f64(lp1_row0)), float(loglik)))
+
+    def loglik(self) -> float:
+        v = C.c_double()
+        check(lib.ehmm_loglik_value(self._h, C.byref(v)))
+        return v.value
+
+    def maxstepprob(self):
+        pi = np.empty(self.K)
+        gamma = np.empty((self.K, self.K), order="F")
+        check(lib.ehmm_maxstepprob(self._h, dptr(pi), dptr(gamma)))
+        return {"pi": pi, "gamma": gamma}
+
+    def qfunction(self, pi, gamma) -> float:
+        v = C.c_double()
+        check(lib.ehmm_qfunction(self._h, dptr(_f64(pi)), dptr(_cm(gamma)), C.byref(v)))
+        return v.value
+
+    def bic(self, numPar, numSamples) -> float:
+        v = C.c_double()
+        check(lib.ehmm_bic(self._h, int(numPar), int(numSamples), C.byref(v)))
+        return v.value
+
+    def inner_maxstepprob(self):
+        d = np.empty(self.B)
+        check(lib.ehmm_inner_maxstepprob(self._h, dptr(d)))
+        return d
+
+    def marginal_probability(self):
+        out = np.empty((self.M, self.K), order="F")
+        check(lib.ehmm_marginal_probability(self._h, dptr(out)))
+        return out
+
+    def viterbi(self, pi, gamma, fetch=True):
+        out = np.empty(self.M) if fetch else None
+        check(lib.ehmm_viterbi(self._h, dptr(_f64(pi)), dptr(_cm(gamma)), dptr(out)))
+        return out
+
+    # -- rejection control -----------------------------------------------------------------
+    def rng_set_state(self, state625):
+        st = np.ascontiguousarray(state625, dtype=np.uint32)
+        assert st.size == 625
+        check(lib.ehmm_rng_set_state(self._h, st.ctypes.data_as(C.POINTER(C.c_uint32))))
+
+    def rng_get_state(self):
+        st = np.empty(625, dtype=np.uint32)
+        check(lib.ehmm_rng_get_state(self._h, st.ctypes.data_as(C.POINTER(C.c_uint32))))
+        return st
+
+    def rc_consensus(self, p, uniforms=None) -> int:
+        u = None if uniforms is None else _f64(uniforms)
+        n = C.c_int64()
+        check(lib.ehmm_rc_consensus(self._h, float(p), dptr(u), 0 if u is None else u.size, C.byref(n)))
+        self.rc_columns = self.K
+        return n.value
+
+    def rc_differential(self, p, uniforms=None) -> int:
+        u = None if uniforms is None else _f64(uniforms)
+        n = C.c_int64()
+        check(lib.ehmm_rc_differential(self._h, float(p), self.N, dptr(u), 0 if u is None else u.size, C.byref(n)))
+        self.rc_columns = self.B + 2
+        return n.value
+
+    def rc_table(self, column):
+        """(rows x 2) matrix of (weight sum, group id): one element of the reference's field<mat>."""
+        n = C.c_int64()
+        check(lib.ehmm_rc_table_rows(self._h, int(column), C.byref(n)))
+        sums, ids = np.empty(n.value), np.empty(n.value)
+        check(lib.ehmm_rc_table_fetch(self._h, int(column), dptr(sums), dptr(ids)))
+        return np.column_stack([sums, ids])
+
+    def rc_buckets(self, column):
+        b = np.empty(self.G + 1)
+        check(lib.ehmm_rc_buckets_fetch(self._h, int(column), dptr(b)))
+        return b
+
+    # -- GLM -------------------------------------------------------------------------------
+    def glm_nb(self, column, par, grad=True):
+        par = _f64(par)
+        v = C.c_double()
+        g = np.empty(par.size) if grad else None
+        check(lib.ehmm_glm_nb(self._h, int(column), dptr(par), par.size - 1, C.byref(v), dptr(g)))
+        return v.value, g
+
+    def glm_mix_nb(self, par, minZero, grad=True):
+        par = _f64(par)
+        v = C.c_double()
+        g = np.empty(4) if grad else None
+        check(lib.ehmm_glm_mix_nb(self._h, dptr(par), float(minZero), C.byref(v), dptr(g)))
+        return v.value, g
+
+    # -- datasets --------------------------------------------------------------------------
+    def dims(self, name):
+        r, c = C.c_int64(), C.c_int64()
+        check(lib.ehmm_dataset_dims(self._h, name.encode(), C.byref(r), C.byref(c)))
+        return r.value, c.value
+
+    def fetch(self, name):
+        r, c = self.dims(name)
+        out = np.empty((r, c), order="F")
+        check(lib.ehmm_fetch(self._h, name.encode(), dptr(out), r * c))
+        return out
+
+    def store(self, name, a):
+        a = _cm(a)
+        if a.ndim == 1:
+            a = a.reshape(-1, 1, order="F")
+        check(lib.ehmm_store(self._h, name.encode(), dptr(a), a.shape[0], a.shape[1]))
+        if name == "mixtureProb":
+            self.B = a.shape[1]
+
+    def device_ptr(self, name) -> int:
+        p = C.c_void_p()
+        check(lib.ehmm_device_ptr(self._h, name.encode(), C.byref(p)))
+        return p.value
+
+    def datasets(self):
+        """all datasets the reference's HDF5 file would hold at this point"""
+        out = {}
+        for n in ("logLikelihood", "logFP", "logBP", "logProb1", "logProb2", "mixtureProb", "viterbi"):
+            try:
+                out[n] = self.fetch(n)
+            except _lib.EhmmError:
+                pass
+        return out
+
+
+def reweight(x, p, uniforms, device=0):
+    """src/reweight.cpp:16-22 on the device; returns (weights, uniforms consumed)."""
+    x = _f64(x).copy()
+    u = _f64(uniforms)
+    n = C.c_int64()
+    check(lib.ehmm_reweight(int(device), dptr(x), x.size, float(p), dptr(u), u.size, C.byref(n)))
+    return x, n.value
+
+
+def aggregate(x, f, device=0):
+    """src/aggregate.cpp:20-45 on the device; (rows x 2) of (sum, id) with non-zero sum."""
+    x = _f64(x)
+    f = np.ascontiguousarray(f, dtype=np.int32)
+    G = int(f[: x.size].max()) if x.size else 0
+    b = np.zeros(G + 1)
+    check(lib.ehmm_aggregate(int(device), dptr(x), x.size, iptr(f), G, dptr(b)))
+    ids = np.nonzero(b)[0]
+    return np.column_stack([b[ids], ids.astype(float)])

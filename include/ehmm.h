@@ -1,0 +1,152 @@
+/*
+ * ehmm.h -- C ABI of libehmm_b200.so: the B200 (sm_100a) implementation of
+ * epigraHMM's EM hot path.
+ *
+ * Each entry point replaces one function of the reference (citations are
+ * relative to the reference tree, plbaldoni/epigraHMM v1.9.2).  The
+ * reference passes state between its native calls through an HDF5 file whose
+ * path is the only handle (src/expStep.cpp:50-51,116-122); here the same path
+ * string keys a device-resident session and the "datasets" (logLikelihood,
+ * logFP, logBP, logProb1, logProb2, mixtureProb, viterbi) are HBM arrays that
+ * ehmm_fetch copies out on demand.
+ *
+ * Conventions
+ *   - every function returns EHMM_OK (0) or an EHMM_ERR_* code; the message is
+ *     available from ehmm_last_error() (thread local).  Nothing throws or
+ *     longjmps across this boundary.
+ *   - all matrices are column-major fp64 exactly as R / Armadillo hold them
+ *     (gamma[i + k*K] = gamma(i,k)); counts are int32 (the reference holds
+ *     as.numeric(counts), R/base-core.R:182), group ids are 1-based int32
+ *     (data.table .GRP, R/base-core.R:97,187-193).
+ *   - pointers are HOST pointers unless the name ends in _device.
+ *   - there is no CPU fallback: every call fails with EHMM_ERR_CUDA when no
+ *     sm_100 device is usable.
+ */
+#ifndef EHMM_H
+#define EHMM_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EHMM_OK 0
+#define EHMM_ERR_ARG 1    /* bad argument (null pointer, bad shape, K unsupported) */
+#define EHMM_ERR_CUDA 2   /* CUDA runtime failure (message holds cudaGetErrorString) */
+#define EHMM_ERR_STATE 3  /* call order violated (e.g. maxStepProb before expStep) */
+#define EHMM_ERR_NOMEM 4  /* device allocation failed */
+#define EHMM_ERR_RNG 5    /* uniform buffer exhausted */
+
+#define EHMM_MAX_K 3      /* the reference only ever uses K = 2 (consensus) or 3 (differential) */
+#define EHMM_MAX_B 62     /* mixture components (2^G - 2 patterns) */
+
+typedef struct ehmm_session ehmm_session;
+
+const char *ehmm_last_error(void);
+int ehmm_version(void);
+int ehmm_device_count(int *n);
+
+/* ---- session = the reference's HDF5 path handle ------------------------------- */
+/* key: the hdf5 path string the R glue receives (src/expStep.cpp:50-51). */
+int ehmm_session_open(const char *key, int64_t M, int K, int device, ehmm_session **out);
+int ehmm_session_find(const char *key, ehmm_session **out);
+int ehmm_session_close(ehmm_session *s);
+/* CUDA stream the session launches on (cudaStream_t as void*), for event timing. */
+int ehmm_session_stream(ehmm_session *s, void **stream);
+int ehmm_session_sync(ehmm_session *s);
+
+/* This session holds bins [m0, m0+M) of one global chain of Mtot bins (bin-block
+ * sharding; the chain is single and global, R/base-core.R:181-183). */
+int ehmm_session_set_block(ehmm_session *s, int64_t m0, int64_t Mtot);
+
+/* ---- data: the long table `dt` (R/base-core.R:89-104,181-198) ------------------- */
+/* counts M x N int32, offsets M x N fp64, controls (already log1p'd, R/base-core.R:186) or NULL. */
+int ehmm_set_data(ehmm_session *s, int N, const int32_t *counts, const double *offsets, const double *controls);
+int ehmm_set_data_device(ehmm_session *s, int N, const int32_t *counts, const double *offsets, const double *controls);
+/* dt$Group (M x N, 1-based) and dtUnique rows for groups 1..G: ChIP, offsets[, controls]
+ * [, Dsg.Mix 0/1 as G x B column-major] (R/base-core.R:99-104,190-198). */
+int ehmm_set_groups(ehmm_session *s, const int32_t *group, int64_t G, const double *u_chip, const double *u_offsets,
+                    const double *u_controls, const uint8_t *u_dsg);
+/* design[b*N + i] = Dsg.Mix_b of sample i (generateMixtureIntercepts, R/base-utils.R:242-264). */
+int ehmm_set_design(ehmm_session *s, int B, const uint8_t *design);
+
+/* ---- emission log-likelihoods -> dataset logLikelihood (device) ------------------ */
+/* loglikConsensusHMM NB branch, R/base-loglikelihood.R:104-122. P = 2 or 3 parameters per state. */
+int ehmm_loglik_consensus(ehmm_session *s, const double *theta1, const double *theta2, int P, double minZero);
+/* emInitialization emission, R/base-EM.R:24-30 (N = 1, dnbinom(log=TRUE)). */
+int ehmm_loglik_init(ehmm_session *s, const double *psi1, const double *psi2);
+/* loglikDifferentialHMM NB branch, R/base-loglikelihood.R:45-71,96. psi = (b, l, db, dl). */
+int ehmm_loglik_differential_hmm(ehmm_session *s, const double *delta, const double *psi, double minZero);
+/* innerExpStep, R/base-EM.R:302-314 -> dataset mixtureProb. */
+int ehmm_inner_expstep(ehmm_session *s, const double *delta, const double *psi, double minZero);
+
+/* ---- E-step / M-step (src/*.cpp) ---------------------------------------------------- */
+/* expStep, src/expStep.cpp:45-123. logf: host M x K matrix, or NULL to use the
+ * device-resident logLikelihood written by an ehmm_loglik_* call. */
+int ehmm_expstep(ehmm_session *s, const double *pi, const double *gamma, const double *logf);
+/* same, logf already in HBM (M x K column-major). */
+int ehmm_expstep_device(ehmm_session *s, const double *pi, const double *gamma, const double *logf_device);
+/* log-likelihood lse(logFP[M-1,]) of the last expStep (src/expStep.cpp:91-92). */
+int ehmm_loglik_value(ehmm_session *s, double *ll);
+/* maxStepProb, src/maxStepProb.cpp:37-81. */
+int ehmm_maxstepprob(ehmm_session *s, double *pi_out, double *gamma_out);
+/* computeQFunction, src/computeQFunction.cpp:12-33. */
+int ehmm_qfunction(ehmm_session *s, const double *pi, const double *gamma, double *q);
+/* computeBIC, src/computeBIC.cpp:12-29. */
+int ehmm_bic(ehmm_session *s, int numPar, int numSamples, double *bic);
+/* innerMaxStepProb, src/innerMaxStepProb.cpp:15-38. */
+int ehmm_inner_maxstepprob(ehmm_session *s, double *delta_out);
+/* getMarginalProbability, src/getMarginalProbability.cpp:12-21 (out: M x K). */
+int ehmm_marginal_probability(ehmm_session *s, double *out);
+/* computeViterbiSequence, src/computeViterbiSequence.cpp:12-54 (states_out: M doubles or NULL). */
+int ehmm_viterbi(ehmm_session *s, const double *pi, const double *gamma, double *states_out);
+
+/* Sharded E-step (bin blocks across GPUs): phase 1 reduces this block to one
+ * scaled K x K operator (op: K*K + 1 doubles = mantissa matrix row-major + log scale);
+ * phase 2 applies the carries the host computed from all blocks' operators
+ * (fwd/bwd: K + 1 doubles = vector + log scale). */
+int ehmm_expstep_reduce(ehmm_session *s, const double *pi, const double *gamma, const double *logf, double *op);
+int ehmm_expstep_apply(ehmm_session *s, const double *fwd_carry, const double *bwd_carry, double *fwd_out);
+/* raw sufficient statistics of the last expStep: K*K joint sums (j >= 1) then sum(P1 * logf). */
+int ehmm_estep_stats(ehmm_session *s, double *stats);
+int ehmm_estep_set_stats(ehmm_session *s, const double *stats, const double *logprob1_row0, double loglik);
+
+/* ---- rejection control (src/reweight.cpp, rbinomVectorized.cpp, aggregate.cpp) ---- */
+/* R's Mersenne-Twister state: state[0] = mti, state[1..624] = mt (.Random.seed[2:626]). */
+int ehmm_rng_set_state(ehmm_session *s, const uint32_t *state625);
+int ehmm_rng_get_state(ehmm_session *s, uint32_t *state625);
+/* consensusRejectionControlled, src/consensusRejectionControlled.cpp:14-31.
+ * uniforms: host buffer of unif_rand() draws to consume in order, or NULL to draw
+ * from the session's Mersenne-Twister on the device.  consumed: draws used. */
+int ehmm_rc_consensus(ehmm_session *s, double p, const double *uniforms, int64_t n_uniforms, int64_t *consumed);
+/* differentialRejectionControlled, src/differentialRejectionControlled.cpp:14-48. */
+int ehmm_rc_differential(ehmm_session *s, double p, int N, const double *uniforms, int64_t n_uniforms, int64_t *consumed);
+/* the field<mat> result: table `column` has `rows` (sum, id) pairs with non-zero sum, ascending id. */
+int ehmm_rc_table_rows(ehmm_session *s, int column, int64_t *rows);
+int ehmm_rc_table_fetch(ehmm_session *s, int column, double *sums, double *ids);
+/* dense bucket sums (G+1 doubles, index = group id) of one column. */
+int ehmm_rc_buckets_fetch(ehmm_session *s, int column, double *buckets);
+/* stand-alone exported helpers: reweight (src/reweight.cpp:16-22), aggregate (src/aggregate.cpp:20-45). */
+int ehmm_reweight(int device, double *x, int64_t n, double p, const double *uniforms, int64_t n_uniforms, int64_t *consumed);
+int ehmm_aggregate(int device, const double *x, int64_t n, const int32_t *f, int64_t G, double *buckets);
+
+/* ---- NB-GLM objective + gradient over the rejection tables (R/base-optim.R) -------- */
+/* glmNB / derivNB, R/base-optim.R:109-130, over table `column` joined with dtUnique.
+ * par = (beta0[, beta_ctrl], phi); value and grad (P + 1) are the NEGATIVE log-lik as in R. */
+int ehmm_glm_nb(ehmm_session *s, int column, const double *par, int P, double *value, double *grad);
+/* glmMixNB / derivMixNB, R/base-optim.R:187-255, over all B+2 tables. par = (b, db, l, dl). */
+int ehmm_glm_mix_nb(ehmm_session *s, const double *par, double minZero, double *value, double *grad);
+
+/* ---- dataset access ------------------------------------------------------------------ */
+/* name in {logLikelihood, logFP, logBP, logProb1, logProb2, mixtureProb, viterbi}. */
+int ehmm_dataset_dims(ehmm_session *s, const char *name, int64_t *rows, int64_t *cols);
+int ehmm_fetch(ehmm_session *s, const char *name, double *dst, int64_t n);
+int ehmm_device_ptr(ehmm_session *s, const char *name, void **ptr);
+/* load a dataset from the host (lets each exported function be called on its own inputs). */
+int ehmm_store(ehmm_session *s, const char *name, const double *src, int64_t rows, int64_t cols);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EHMM_H */

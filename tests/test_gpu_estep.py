@@ -1,0 +1,197 @@
+"""GPU parity: emission + expStep + maxStepProb + Q + BIC through the C ABI against the oracle.
+
+Tolerances (BASELINE.json north_star): posteriors <= 1e-8 absolute, log-likelihood (and the
+logFP/logBP it is built from) <= 1e-9 relative, parameters <= 1e-9 relative.
+"""
+import numpy as np
+import pytest
+
+from epigrahmm_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+MINZERO = 2.2250738585072014e-308
+
+
+def _theta(K):
+    t = synth.THETA_CONSENSUS if K == 2 else synth.THETA_DIFFERENTIAL
+    return t["pi"], t["gamma"]
+
+
+def _check_estep(h, g, M, K):
+    for n in ("logFP", "logBP"):
+        rel = np.max(np.abs(h[n] - g[n]) / np.maximum(1.0, np.abs(h[n])))
+        assert rel <= 1e-9, (n, rel)
+    for n in ("logProb1", "logProb2"):
+        d = np.max(np.abs(np.exp(h[n]) - np.exp(g[n])))
+        assert d <= 1e-8, (n, d)
+        # the raw log datasets agree too wherever the probability is not negligible
+        m = h[n] > -30
+        assert np.max(np.abs(h[n][m] - g[n][m])) <= 1e-6, n
+        assert np.all(np.isfinite(g[n])), n
+    assert np.allclose(g["logProb2"][0], -np.log(K * K))
+
+
+@pytest.mark.parametrize("K", [2, 3])
+@pytest.mark.parametrize("M", [1, 2, 7, 400, 959, 960, 961, 1280, 1281, 7000, 100003])
+def test_expstep_matches_oracle(ehmm, oracle, K, M):
+    rng = np.random.default_rng(1000 * K + M)
+    z = synth.markov_chain(M, synth.GAMMA2 if K == 2 else synth.GAMMA3, rng)
+    logf = rng.normal(-6.0, 2.0, (M, K))
+    logf[np.arange(M), z] += 5.0
+    pi, gamma = _theta(K)
+    h = oracle.expStep(pi, gamma, logf)
+    with ehmm.Session("t_estep", M, K) as s:
+        s.expstep(pi, gamma, logf)
+        g = s.datasets()
+        _check_estep(h, g, M, K)
+        assert np.array_equal(g["logLikelihood"], np.asfortranarray(logf))
+        ll = oracle.computeBIC(h, 0, 1) / -2.0
+        assert abs(s.loglik() - ll) <= 1e-9 * abs(ll)
+        if M >= 2:
+            mo, mg = oracle.maxStepProb(h), s.maxstepprob()
+            assert np.allclose(mo["pi"], mg["pi"], rtol=1e-9, atol=0)
+            assert np.allclose(mo["gamma"], mg["gamma"], rtol=1e-9, atol=0)
+            qo, qg = oracle.computeQFunction(h, pi, gamma), s.qfunction(pi, gamma)
+            assert abs(qo - qg) <= 1e-9 * abs(qo)
+        bo, bg = oracle.computeBIC(h, 7, 3), s.bic(7, 3)
+        assert abs(bo - bg) <= 1e-9 * abs(bo)
+        assert np.allclose(s.marginal_probability(), np.exp(h["logProb1"]), atol=1e-8, rtol=0)
+
+
+@pytest.mark.parametrize("K", [2, 3])
+def test_expstep_emission_underflow(ehmm, oracle, K):
+    """states whose emission underflows exp() must keep finite log posteriors (rejection control
+    distinguishes exp(logProb1) == 0 from a subnormal)"""
+    M = 3000
+    rng = np.random.default_rng(7)
+    logf = rng.normal(-5.0, 1.0, (M, K))
+    for j in (0, 4, 5, 100, 959, 960, 1500, M - 1):
+        logf[j, 1] = -900.0
+    logf[2000, 0] = -1500.0
+    pi, gamma = _theta(K)
+    h = oracle.expStep(pi, gamma, logf)
+    with ehmm.Session("t_underflow", M, K) as s:
+        s.expstep(pi, gamma, logf)
+        g = s.datasets()
+    _check_estep(h, g, M, K)
+    for n in ("logProb1", "logProb2"):
+        m = h[n] < -300
+        assert m.any()
+        assert np.max(np.abs(h[n][m] - g[n][m]) / np.abs(h[n][m])) <= 1e-9
+
+
+def test_expstep_errors(ehmm):
+    with pytest.raises(ehmm.EhmmError):
+        ehmm.Session("bad", 10, 5)
+    with ehmm.Session("t_err", 10, 2) as s:
+        with pytest.raises(ehmm.EhmmError):
+            s.maxstepprob()          # the reference would fail to load logProb1 from the file
+        with pytest.raises(ehmm.EhmmError):
+            s.expstep([0.5, 0.5], [[0.9, 0.1], [0.1, 0.9]])  # no logf anywhere
+
+
+def test_functions_on_stored_datasets(ehmm, oracle):
+    """maxStepProb / computeQFunction / computeBIC read their inputs from the 'file': feeding the
+    oracle's datasets must reproduce the oracle's outputs (function-boundary parity)."""
+    M, K = 5000, 3
+    rng = np.random.default_rng(5)
+    logf = rng.normal(-4.0, 2.0, (M, K))
+    pi, gamma = _theta(K)
+    h = oracle.expStep(pi, gamma, logf)
+    with ehmm.Session("t_stored", M, K) as s:
+        for n in ("logLikelihood", "logFP", "logBP", "logProb1", "logProb2"):
+            s.store(n, h[n])
+        mo, mg = oracle.maxStepProb(h), s.maxstepprob()
+        assert np.allclose(mo["pi"], mg["pi"], rtol=1e-12, atol=0)
+        assert np.allclose(mo["gamma"], mg["gamma"], rtol=1e-12, atol=0)
+        assert abs(oracle.computeQFunction(h, pi, gamma) - s.qfunction(pi, gamma)) <= 1e-12 * abs(s.qfunction(pi, gamma))
+        assert abs(oracle.computeBIC(h, 4, 2) - s.bic(4, 2)) <= 1e-13 * abs(s.bic(4, 2))
+
+
+@pytest.mark.parametrize("controls", [False, True])
+def test_loglik_consensus(ehmm, oracle, controls):
+    M, N = 20011, 3
+    d = synth.make_consensus(M, N, seed=11, controls=controls)
+    d["counts"][5, 0] = 9000  # beyond the lgamma table
+    d["counts"][6, 1] = 40000
+    psi = [np.array([np.log(2.0), 0.3, 3.0]), np.array([np.log(12.0), 0.1, 4.0])] if controls else \
+        [np.array([np.log(2.0), 3.0]), np.array([np.log(12.0), 4.0])]
+    ref = oracle.loglikConsensusHMM(d["counts"], d["offsets"], psi, MINZERO, d["controls"])
+    with ehmm.Session("t_cons", M, 2) as s:
+        s.set_data(d["counts"], d["offsets"], d["controls"])
+        s.loglik_consensus(psi, MINZERO)
+        got = s.fetch("logLikelihood")
+    assert np.max(np.abs(got - ref) / np.maximum(1.0, np.abs(ref))) <= 1e-11
+
+
+def test_loglik_init(ehmm, oracle):
+    M = 9001
+    d = synth.make_consensus(M, 1, seed=12)
+    psi = [np.array([0.4, 2.5]), np.array([2.2, 900.0])]
+    ref = oracle.loglikInit(d["counts"], d["offsets"], psi)
+    with ehmm.Session("t_init", M, 2) as s:
+        s.set_data(d["counts"], d["offsets"])
+        s.loglik_init(psi)
+        got = s.fetch("logLikelihood")
+    assert np.max(np.abs(got - ref) / np.maximum(1.0, np.abs(ref))) <= 1e-11
+
+
+@pytest.mark.parametrize("n_cond,n_rep", [(2, 1), (3, 2), (4, 3), (5, 2)])
+def test_loglik_differential(ehmm, oracle, n_cond, n_rep):
+    M = 6007
+    d = synth.make_differential(M, n_cond, n_rep, seed=13)
+    B = d["B"]
+    delta = np.random.default_rng(1).dirichlet(np.ones(B))
+    psi = synth.THETA_DIFFERENTIAL["psi"]
+    ref = oracle.loglikDifferentialHMM(d["counts"], d["offsets"], d["design"], delta, psi, MINZERO)
+    eta_ref = oracle.innerExpStep(d["counts"], d["offsets"], d["design"], delta, psi, MINZERO)
+    with ehmm.Session("t_diff", M, 3) as s:
+        s.set_data(d["counts"], d["offsets"])
+        s.set_design(d["design"])
+        s.loglik_differential_hmm(delta, psi, MINZERO)
+        got = s.fetch("logLikelihood")
+        s.inner_expstep(delta, psi, MINZERO)
+        eta = s.fetch("mixtureProb")
+    assert np.max(np.abs(got - ref) / np.maximum(1.0, np.abs(ref))) <= 1e-11
+    assert np.max(np.abs(eta - eta_ref)) <= 1e-10
+    assert np.allclose(eta.sum(1), 1.0, atol=1e-12)
+
+
+def test_reference_kat_loglik_differential(ehmm, oracle):
+    """the reference's only emission known-answer test (tests/testthat/test-base.R:6-42):
+    ChIP = 1, offsets = -1, psi = (0,1;0,1), delta = (.1,.9): three unique rows with closed forms."""
+    M = 1000
+    counts = np.ones((M, 2), dtype=np.int32)
+    offsets = -np.ones((M, 2))
+    design = np.array([[1, 0], [0, 1]], dtype=np.uint8)
+    psi = np.array([0.0, 1.0, 0.0, 1.0])  # unlist(list(betas=c(0,1), lambdas=c(0,1)))
+    with ehmm.Session("t_kat", M, 3) as s:
+        s.set_data(counts, offsets)
+        s.set_design(design)
+        s.loglik_differential_hmm([0.1, 0.9], psi, 1e-32)
+        ll = s.fetch("logLikelihood")
+    rows = np.unique(ll, axis=0)
+    assert rows.shape == (1, 3)
+    # psi order follows unlist(theta$psi) = (0,1,0,1): mu = exp(0 + 0*D - 1), size = exp(1 + 1*D)
+    d1 = oracle.dnbinom(1, np.exp(1.0), np.exp(-1.0), log=True)
+    d2 = oracle.dnbinom(1, np.exp(2.0), np.exp(-1.0), log=True)
+    assert abs(rows[0, 0] - 2 * d1) <= 1.5e-8
+    assert abs(rows[0, 1] - (d1 + d2)) <= 1.5e-8
+    assert abs(rows[0, 2] - 2 * d2) <= 1.5e-8
+
+
+def test_inner_maxstepprob(ehmm, oracle):
+    M, K = 4001, 3
+    rng = np.random.default_rng(3)
+    logf = rng.normal(-4.0, 2.0, (M, K))
+    pi, gamma = _theta(K)
+    h = oracle.expStep(pi, gamma, logf)
+    eta = rng.dirichlet(np.ones(6), M)
+    h["mixtureProb"] = eta
+    ref = oracle.innerMaxStepProb(h)
+    with ehmm.Session("t_inner", M, K) as s:
+        s.store("logProb1", h["logProb1"])
+        s.store("mixtureProb", eta)
+        got = s.inner_maxstepprob()
+    assert np.allclose(got, ref, rtol=1e-12, atol=0)

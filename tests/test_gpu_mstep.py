@@ -1,0 +1,201 @@
+"""GPU parity: rejection control, aggregation, NB-GLM objective/gradient and Viterbi through the
+C ABI against the oracle, on shared inputs (function-boundary protocol)."""
+import numpy as np
+import pytest
+
+from epigrahmm_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+MINZERO = 2.2250738585072014e-308
+
+
+def _consensus_case(oracle, M=20011, N=3, seed=21, controls=False):
+    d = synth.make_consensus(M, N, seed=seed, controls=controls)
+    g = synth.make_groups(d["counts"], d["offsets"], d["controls"])
+    th = synth.THETA_CONSENSUS
+    psi = th["psi"] if not controls else [np.array([np.log(2.0), 0.2, 3.0]), np.array([np.log(12.0), 0.1, 4.0])]
+    logf = oracle.loglikConsensusHMM(d["counts"], d["offsets"], psi, MINZERO, d["controls"])
+    h = oracle.expStep(th["pi"], th["gamma"], logf)
+    return d, g, h, psi
+
+
+def _differential_case(oracle, M=8009, n_cond=3, n_rep=2, seed=22):
+    d = synth.make_differential(M, n_cond, n_rep, seed=seed)
+    g = synth.make_groups(d["counts"], d["offsets"], design=d["design"])
+    th = synth.THETA_DIFFERENTIAL
+    delta = np.full(d["B"], 1.0 / d["B"])
+    logf = oracle.loglikDifferentialHMM(d["counts"], d["offsets"], d["design"], delta, th["psi"], MINZERO)
+    h = oracle.expStep(th["pi"], th["gamma"], logf)
+    h["mixtureProb"] = oracle.innerExpStep(d["counts"], d["offsets"], d["design"], delta, th["psi"], MINZERO)
+    return d, g, h, delta
+
+
+def _open(ehmm, key, d, g, K, h, design=None):
+    s = ehmm.Session(key, d["counts"].shape[0], K)
+    s.set_data(d["counts"], d["offsets"], d.get("controls"))
+    if design is not None:
+        s.set_design(design)
+    s.set_groups(g["group"], g["u_chip"], g["u_offsets"], g["u_controls"], g["u_dsg"])
+    for n in ("logLikelihood", "logFP", "logBP", "logProb1", "logProb2"):
+        s.store(n, h[n])
+    if "mixtureProb" in h:
+        s.store("mixtureProb", h["mixtureProb"])
+    return s
+
+
+@pytest.mark.parametrize("p", [0.9, 0.05, 0.0])
+def test_rc_consensus_shared_uniforms(ehmm, oracle, p):
+    d, g, h, _ = _consensus_case(oracle)
+    M = d["counts"].shape[0]
+    u = oracle.RNG.set_seed(210423).runif(2 * M)
+    ref, n_ref = oracle.consensusRejectionControlled(h, g["group"], p, uniforms=u, dense=True)
+    with _open(ehmm, "t_rc", d, g, 2, h) as s:
+        n = s.rc_consensus(p, uniforms=u)
+        assert n == n_ref
+        for k in range(2):
+            b = s.rc_buckets(k)
+            assert np.array_equal(b != 0, ref[k] != 0)            # identical support
+            assert np.allclose(b, ref[k], rtol=1e-12, atol=0)
+            tab = s.rc_table(k)
+            ids = np.nonzero(ref[k])[0]
+            assert np.array_equal(tab[:, 1], ids.astype(float))   # ascending group id, non-zero rows only
+    if p == 0.0:
+        assert n_ref == 0
+
+
+def test_rc_consensus_device_rng(ehmm, oracle):
+    """uniforms drawn on the device from R's Mersenne-Twister state: same draws, same final state"""
+    d, g, h, _ = _consensus_case(oracle, M=30011)
+    rng = oracle.RNG.set_seed(42)
+    rng.runif(1000)                      # start from mti in the middle of a block
+    st0 = rng.state()
+    ref, n_ref = oracle.consensusRejectionControlled(h, g["group"], 0.05, rng=rng, dense=True)
+    assert n_ref > 2 * 624
+    with _open(ehmm, "t_rc_rng", d, g, 2, h) as s:
+        s.rng_set_state(st0)
+        n = s.rc_consensus(0.05)
+        assert n == n_ref
+        assert np.array_equal(s.rng_get_state(), rng.state())
+        for k in range(2):
+            assert np.allclose(s.rc_buckets(k), ref[k], rtol=1e-12, atol=0)
+        # a second call continues the stream exactly where R would
+        ref2, n2 = oracle.consensusRejectionControlled(h, g["group"], 0.3, rng=rng, dense=True)
+        assert s.rc_consensus(0.3) == n2
+        assert np.array_equal(s.rng_get_state(), rng.state())
+        assert np.allclose(s.rc_buckets(1), ref2[1], rtol=1e-12, atol=0)
+
+
+def test_rc_uniform_buffer_too_short(ehmm, oracle):
+    d, g, h, _ = _consensus_case(oracle, M=5000)
+    with _open(ehmm, "t_rc_short", d, g, 2, h) as s:
+        with pytest.raises(ehmm.EhmmError):
+            s.rc_consensus(0.5, uniforms=np.full(3, 0.5))
+
+
+@pytest.mark.parametrize("p", [0.9, 0.05])
+def test_rc_differential(ehmm, oracle, p):
+    d, g, h, _ = _differential_case(oracle)
+    M, N = d["counts"].shape
+    B = d["B"]
+    u = oracle.RNG.set_seed(7).runif((B + 2) * M)
+    ref, n_ref = oracle.differentialRejectionControlled(h, g["group"], p, N, uniforms=u, dense=True)
+    with _open(ehmm, "t_rcd", d, g, 3, h, design=d["design"]) as s:
+        n = s.rc_differential(p, uniforms=u)
+        assert n == n_ref
+        for c in range(B + 2):
+            b = s.rc_buckets(c)
+            assert np.array_equal(b != 0, ref[c] != 0)
+            assert np.allclose(b, ref[c], rtol=1e-12, atol=0)
+
+
+def test_reweight_and_aggregate_helpers(ehmm, oracle):
+    rng = np.random.default_rng(3)
+    x = rng.random(50001) ** 4
+    x[::97] = 0.0
+    u = oracle.RNG.set_seed(1).runif(x.size)
+    ref, n_ref = oracle.reweight(x, 0.3, uniforms=u)
+    got, n = ehmm.reweight(x, 0.3, u)
+    assert n == n_ref and np.array_equal(got, ref)
+    f = rng.integers(1, 400, x.size)
+    a_ref, a = oracle.aggregate(ref, f), ehmm.aggregate(ref, f)
+    assert np.array_equal(a[:, 1], a_ref[:, 1]) and np.allclose(a[:, 0], a_ref[:, 0], rtol=1e-12, atol=0)
+    # empty input
+    assert ehmm.aggregate(np.zeros(0), np.zeros(0, dtype=np.int32)).shape == (0, 2)
+
+
+@pytest.mark.parametrize("controls", [False, True])
+def test_glm_nb(ehmm, oracle, controls):
+    d, g, h, psi = _consensus_case(oracle, controls=controls)
+    M = d["counts"].shape[0]
+    u = oracle.RNG.set_seed(5).runif(2 * M)
+    ref, _ = oracle.consensusRejectionControlled(h, g["group"], 0.05, uniforms=u, dense=True)
+    with _open(ehmm, "t_glm", d, g, 2, h) as s:
+        s.rc_consensus(0.05, uniforms=u)
+        for k in range(2):
+            ids = np.nonzero(ref[k])[0]
+            y, off, w = g["u_chip"][ids - 1], g["u_offsets"][ids - 1], ref[k][ids]
+            x = np.ones((ids.size, 1)) if not controls else np.column_stack([np.ones(ids.size), g["u_controls"][ids - 1]])
+            for par in ([psi[k][0]] + ([psi[k][1]] if controls else []) + [1.0 / psi[k][-1]],
+                        [0.3] + ([-0.2] if controls else []) + [0.01], [2.0] + ([0.4] if controls else []) + [1.7]):
+                v_ref, g_ref = oracle.glmNB(par, y, x, off, w)
+                v, gr = s.glm_nb(k, par)
+                assert abs(v - v_ref) <= 1e-11 * abs(v_ref), (k, par)
+                assert np.allclose(gr, g_ref, rtol=1e-9, atol=1e-9 * abs(v_ref)), (k, par, gr, g_ref)
+
+
+def test_glm_mix_nb(ehmm, oracle):
+    d, g, h, delta = _differential_case(oracle)
+    M, N = d["counts"].shape
+    B = d["B"]
+    u = oracle.RNG.set_seed(9).runif((B + 2) * M)
+    ref, _ = oracle.differentialRejectionControlled(h, g["group"], 0.05, N, uniforms=u, dense=True)
+    # the long table rbindlist(rcWeights, idcol='id') of R/base-EM.R:204-209
+    rows = [(c + 1, np.nonzero(ref[c])[0]) for c in range(B + 2)]
+    id_ = np.concatenate([np.full(ix.size, c) for c, ix in rows])
+    gi = np.concatenate([ix for _, ix in rows])
+    w = np.concatenate([ref[c - 1][ix] for c, ix in rows])
+    y, off, dsg = g["u_chip"][gi - 1], g["u_offsets"][gi - 1], g["u_dsg"][gi - 1]
+    with _open(ehmm, "t_mix", d, g, 3, h, design=d["design"]) as s:
+        s.rc_differential(0.05, uniforms=u)
+        for par in ([np.log(2), np.log(6), np.log(3), np.log(4 / 3)], [0.2, 0.9, 0.5, -0.3], [1.5, 0.1, 3.0, 1.0]):
+            v_ref, g_ref = oracle.glmMixNB(par, id_, w, y, off, dsg, B + 2, MINZERO)
+            v, gr = s.glm_mix_nb(par, MINZERO)
+            assert abs(v - v_ref) <= 1e-11 * abs(v_ref), par
+            assert np.allclose(gr, g_ref, rtol=1e-9, atol=1e-9 * abs(v_ref)), (par, gr, g_ref)
+
+
+@pytest.mark.parametrize("K", [2, 3])
+@pytest.mark.parametrize("M", [1, 2, 3, 2047, 2048, 2049, 50001, 300007])
+def test_viterbi_bit_exact(ehmm, oracle, K, M):
+    """same logFP bits in -> identical state sequence out (LOGV reaches ~1e12 at M = 3e5, so late
+    decisions are taken at coarse ulp granularity)"""
+    rng = np.random.default_rng(100 * K + M % 97)
+    gam = synth.GAMMA2 if K == 2 else synth.GAMMA3
+    z = synth.markov_chain(M, gam, rng)
+    logf = rng.normal(-6.0, 2.0, (M, K))
+    logf[np.arange(M), z] += 4.0
+    th = synth.THETA_CONSENSUS if K == 2 else synth.THETA_DIFFERENTIAL
+    h = oracle.expStep(th["pi"], th["gamma"], logf)
+    ref = oracle.computeViterbiSequence(h, th["pi"], th["gamma"])
+    with ehmm.Session("t_vit", M, K) as s:
+        s.store("logFP", h["logFP"])
+        got = s.viterbi(th["pi"], th["gamma"])
+        assert np.array_equal(got, ref)
+        assert np.array_equal(s.fetch("viterbi")[:, 0], ref)
+
+
+def test_viterbi_end_to_end_small(ehmm, oracle):
+    """at test sizes the GPU's own logFP (scan order differs from the reference's sequential
+    recursion in the last bits) still decodes to the reference's path"""
+    M, K = 7000, 3
+    d = synth.make_differential(M, 3, 2, seed=31)
+    th = synth.THETA_DIFFERENTIAL
+    delta = np.full(d["B"], 1.0 / d["B"])
+    logf = oracle.loglikDifferentialHMM(d["counts"], d["offsets"], d["design"], delta, th["psi"], MINZERO)
+    h = oracle.expStep(th["pi"], th["gamma"], logf)
+    ref = oracle.computeViterbiSequence(h, th["pi"], th["gamma"])
+    with ehmm.Session("t_vit2", M, K) as s:
+        s.expstep(th["pi"], th["gamma"], logf)
+        got = s.viterbi(th["pi"], th["gamma"])
+    assert np.mean(got != ref) <= 1e-3
