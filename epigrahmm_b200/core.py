@@ -1,0 +1,144 @@
+"""Callers either side of the EM loop: R/base-core.R (initializerHMM, consensusHMM,
+differentialHMM) and the initialisation helpers of R/base-utils.R, on plain arrays.
+
+These run once per fit on the host (SURVEY.md section 8f ranks them "next" after the loop body);
+the loop body itself is :mod:`epigrahmm_b200.em` over a :class:`~epigrahmm_b200.session.Session`.
+``counts`` / ``offsets`` are M x N matrices whose columns are sorted by condition, ``condition`` the
+per-column condition labels (``colData(object)$condition``).
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+from . import em
+from .session import Session
+from .synth import make_groups
+
+
+def _pattern_table(n_cond):
+    """ref of enumeratePatterns (R/base-utils.R:196-204): expand.grid of 0/1 ordered by row sum"""
+    grid = np.array([[(r >> c) & 1 for c in range(n_cond)] for r in range(2 ** n_cond)], dtype=np.uint8)
+    return grid[np.argsort(grid.sum(1), kind="stable")]
+
+
+def enumeratePatterns(peaks, condition):
+    """Group (1-based row of the pattern table) of every window from the initial peak calls."""
+    cond = list(dict.fromkeys(condition))
+    chain = np.column_stack([(peaks[:, [i for i, c in enumerate(condition) if c == u]].sum(1) > 0) for u in cond])
+    ref = _pattern_table(len(cond))
+    code = {tuple(r): i + 1 for i, r in enumerate(ref.tolist())}
+    group = np.array([code[tuple(r)] for r in chain.astype(np.uint8).tolist()])
+    return group, ref
+
+
+def estimateCoefficients(z, counts, offsets, control, type_):
+    """R/base-utils.R:282-320 (dist = 'nb')"""
+    r = (np.asarray(counts, dtype=np.float64) + 1.0) / np.exp(offsets)
+    par = []
+    for x in (z.min(), z.max()):
+        v = r[z == x].ravel()
+        mu, s2 = v.mean(), v.var(ddof=1)
+        disp = control["maxDisp"] if s2 <= mu else min(mu ** 2 / (s2 - mu), control["maxDisp"])
+        par.append((mu, disp))
+    if type_ == "differential":
+        p1 = np.log(np.array(par[0]))
+        return [p1, np.log(np.array(par[1])) - p1]
+    return [np.array([math.log(par[0][0]), par[0][1]]), np.array([math.log(par[1][0]), par[1][1]])]
+
+
+def initializer(counts, offsets, control, device=0, key="initializer"):
+    """initializer() (R/initializer.R:42-60): one 2-state fit per sample; returns the M x N 0/1
+    'peaks' assay.  The N fits are independent (one Session each, reusing the hot path with N=1)."""
+    counts = np.asarray(counts)
+    M, N = counts.shape
+    peaks = np.zeros((M, N))
+    for i in range(N):
+        with Session("%s.%d" % (key, i), M, 2, device) as s:
+            c, o = counts[:, [i]], np.asarray(offsets)[:, [i]]
+            s.set_data(c, o)
+            g = make_groups(c, o)
+            s.set_groups(g["group"], g["u_chip"], g["u_offsets"])
+            s.rng_set_state(_stream().state)
+            peaks[:, i], _ = em.initializerHMM(c, o, s, control)
+            _stream().state[:] = s.rng_get_state()
+    return peaks
+
+
+def _stream():
+    from . import rng
+    return rng.GLOBAL
+
+
+def consensusHMM(counts, offsets, peaks, condition, control, controls=None, device=0, key=None, session=None):
+    """R/base-core.R:163-228 (dist = 'nb').  Returns dict(session, theta, history)."""
+    counts = np.asarray(counts)
+    M, N = counts.shape
+    z, _ = enumeratePatterns(np.asarray(peaks), condition)
+    ctrl = None if controls is None else np.log1p(np.asarray(controls, dtype=np.float64))
+    s = session or Session(key or "epigraHMM.h5", M, 2, device)
+    s.set_data(counts, offsets, ctrl)
+    g = make_groups(counts, offsets, ctrl)
+    s.set_groups(g["group"], g["u_chip"], g["u_offsets"], g["u_controls"])
+    psi = estimateCoefficients(z, counts, offsets, control, "consensus")
+    if ctrl is not None:
+        psi = [np.array([p[0], 0.0, p[1]]) for p in psi]
+    theta = dict(pi=np.array([0.999, 0.001]), gamma=em.estimateTransitionProb(z, 2), psi=psi)
+    s.rng_set_state(_stream().state)
+    fit = em.emConsensus(theta, s, N, control)
+    _stream().state[:] = s.rng_get_state()
+    th = fit["theta_new"]
+    s.viterbi(th["pi"], th["gamma"], fetch=False)
+    return dict(session=s, theta=th, history=fit)
+
+
+def differentialHMM(counts, offsets, peaks, condition, control, device=0, key=None, session=None):
+    """R/base-core.R:69-157 (dist = 'nb', control$pattern = NULL -> all 2^G - 2 patterns)."""
+    counts = np.asarray(counts)
+    M, N = counts.shape
+    cond = list(dict.fromkeys(condition))
+    nG = len(cond)
+    z, ref = enumeratePatterns(np.asarray(peaks), condition)
+    if control.get("pattern"):
+        want = []
+        for pat in control["pattern"]:  # 1-based condition indices, as in R
+            row = np.zeros(nG, dtype=np.uint8)
+            row[[p - 1 for p in pat]] = 1
+            want.append(int(np.where((ref == row).all(1))[0][0]) + 1)
+        zseq = want
+    else:
+        zseq = list(range(2, 2 ** nG))
+    B = len(zseq)
+    cond_of = np.array([cond.index(c) for c in condition])
+    design = np.stack([ref[zq - 1][cond_of] for zq in zseq]).astype(np.uint8)  # B x N
+    s = session or Session(key or "epigraHMM.h5", M, 3, device)
+    s.set_data(counts, offsets)
+    s.set_design(design)
+    g = make_groups(counts, offsets, design=design)
+    s.set_groups(g["group"], g["u_chip"], g["u_offsets"], None, g["u_dsg"])
+    zmin, zmax = z.min(), z.max()
+    chain = np.where(z == zmin, 0, np.where(z == zmax, 2, 1))
+    diff = z[(z != 1) & (z != zmax)]
+    sub = diff[np.isin(diff, zseq)]
+    delta = np.array([(sub == zq).sum() / max(sub.size, 1) for zq in zseq], dtype=np.float64)
+    theta = dict(pi=np.array([0.999, 0.0005, 0.0005]), gamma=em.estimateTransitionProb(chain, 3), delta=delta,
+                 psi=estimateCoefficients(z, counts, offsets, control, "differential"))
+    s.rng_set_state(_stream().state)
+    fit = em.outerEMDifferential(theta, s, N, control)
+    _stream().state[:] = s.rng_get_state()
+    th = fit["theta_new"]
+    s.viterbi(th["pi"], th["gamma"], fetch=False)
+    patterns = ["".join("E" if v else "B" for v in ref[zq - 1]) for zq in zseq]
+    return dict(session=s, theta=th, history=fit, mixturePatterns=patterns, design=design)
+
+
+def epigraHMM(counts, offsets, peaks, condition, control, type="consensus", dist="nb", **kw):
+    """epigraHMM() (R/epigraHMM.R:39-90) on arrays."""
+    if dist != "nb":
+        raise NotImplementedError("dist='zinb' is not on the accelerated path yet")
+    if type == "consensus":
+        return consensusHMM(counts, offsets, peaks, condition, control, **kw)
+    if type == "differential":
+        return differentialHMM(counts, offsets, peaks, condition, control, **kw)
+    raise ValueError("type must be 'consensus' or 'differential'")

@@ -540,7 +540,7 @@ __global__ void __launch_bounds__(NT)
             double lp1[K], p1[K];
 #pragma unroll
             for (int k = 0; k < K; k++) {
-                lp1[k] = (lf[k] + lb[k]) - lZ;
+                lp1[k] = fmin((lf[k] + lb[k]) - lZ, 0.0);  // a log-probability; > 0 only by rounding
                 p1[k] = al[k] * be[k] * rZ;
                 logFP[(int64_t)k * M + j] = lfT + (scf + lf[k]);
                 logBP[(int64_t)k * M + j] = lbT + (scb + lb[k]);
@@ -557,7 +557,8 @@ __global__ void __launch_bounds__(NT)
                     const double ra = p1[l] / a[l];
 #pragma unroll
                     for (int i = 0; i < K; i++) {
-                        logProb2[(int64_t)(i * K + l) * M + j] = lp1[l] + ((((lfp[i] + d) + P.lg[i * K + l]) + f[l]) - lf[l]);
+                        logProb2[(int64_t)(i * K + l) * M + j] =
+                            fmin(lp1[l] + ((((lfp[i] + d) + P.lg[i * K + l]) + f[l]) - lf[l]), 0.0);
                         acc[i * K + l] = fma(alp[i] * P.g[i * K + l], ra, acc[i * K + l]);
                     }
                 }

@@ -282,7 +282,7 @@ def innerExpStep(y, offsets, design, delta, psi, minZero):
 
 def glmNB(par, y, x, offset, weights, grad=True):
     """R/base-optim.R:109-130 -> (value, gradient)."""
-    x = _colmajor(np.asarray(x, float).reshape(len(y), -1))
+    x = _colmajor(np.asarray(x, float).reshape(len(y), -1) if len(y) else np.zeros((0, 1)))
     G, P = x.shape
     g = np.empty(P + 1)
     v = lib().eo_glm_nb(C.c_int64(G), P, _p(_f64(par)), _p(_f64(y)), _p(x), _p(_f64(offset)), _p(_f64(weights)),

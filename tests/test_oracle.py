@@ -1,0 +1,178 @@
+"""Pins the CPU oracle: known answers the reference's own tests state, independent library
+implementations of the third-party arithmetic, a numpy twin of the native recursions, and the
+committed golden vectors."""
+import os
+
+import numpy as np
+import pytest
+from scipy.special import digamma as sp_digamma, logsumexp
+from scipy.stats import nbinom
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+MINZERO = 2.2250738585072014e-308
+
+
+def test_dnbinom_matches_scipy(oracle):
+    rng = np.random.default_rng(1)
+    x = rng.integers(0, 300, 4000).astype(float)
+    size = np.exp(rng.normal(1, 2, 4000))
+    mu = np.exp(rng.normal(1, 2, 4000))
+    a = oracle.dnbinom(x, size, mu, log=True)
+    b = nbinom.logpmf(x, size, size / (size + mu))
+    assert np.max(np.abs(a - b) / np.maximum(1, np.abs(b))) < 1e-11  # scipy's gammaln differences lose digits
+    # 50-digit truth on a subsample: the saddle-point algorithm stays at a few ulp
+    import mpmath as mp
+    mp.mp.dps = 50
+    for i in range(0, 4000, 20):
+        xx, ss, mm = mp.mpf(x[i]), mp.mpf(size[i]), mp.mpf(mu[i])
+        t = mp.loggamma(xx + ss) - mp.loggamma(ss) - mp.loggamma(xx + 1) + ss * mp.log(ss / (ss + mm)) + xx * mp.log(mm / (ss + mm))
+        assert abs(a[i] - float(t)) <= 2e-14 * max(1.0, abs(float(t))), (x[i], size[i], mu[i])
+    assert np.allclose(oracle.dnbinom(x, size, mu), np.exp(a), rtol=1e-12)
+    # branches of dnbinom_mu: x == 0, x < 1e-10*size, size >> mu, mu >> size
+    for xx, ss, mm in [(0, 3.0, 2.0), (0, 2.0, 30.0), (1, 1e12, 2.0), (5, 1000.0, 0.01), (7, 0.01, 500.0)]:
+        X, S, Mu = mp.mpf(xx), mp.mpf(ss), mp.mpf(mm)
+        ref = float(mp.loggamma(X + S) - mp.loggamma(S) - mp.loggamma(X + 1) + S * mp.log(S / (S + Mu)) + X * mp.log(Mu / (S + Mu)))
+        assert abs(oracle.dnbinom(xx, ss, mm, log=True) - ref) < 1e-11 * max(1, abs(ref))  # the x < 1e-10*size branch is O(mu^2/size) approximate in R itself
+
+
+def test_reference_kat_loglik_differential_hmm(oracle):
+    """tests/testthat/test-base.R:6-42: three unique rows equal to closed-form dnbinom sums"""
+    M = 1000
+    counts = np.ones((M, 2), dtype=np.int32)
+    offsets = -np.ones((M, 2))
+    design = np.array([[1, 0], [0, 1]], dtype=np.uint8)
+    ll = oracle.loglikDifferentialHMM(counts, offsets, design, [0.1, 0.9], [0.0, 1.0, 0.0, 1.0], 1e-32)
+    rows = np.unique(ll, axis=0)
+    assert rows.shape == (1, 3)
+    e = np.e
+    d1 = nbinom.logpmf(1, e, e / (e + np.exp(-1.0)))
+    d2 = nbinom.logpmf(1, e * e, e * e / (e * e + np.exp(-1.0)))
+    assert np.allclose(rows[0], [2 * d1, d1 + d2, 2 * d2], rtol=0, atol=1.5e-8)  # expect_equal tolerance
+
+
+def test_digamma(oracle):
+    x = np.exp(np.random.default_rng(2).uniform(-4, 8, 3000))
+    assert np.max(np.abs(oracle.digamma(x) - sp_digamma(x)) / np.maximum(1, np.abs(sp_digamma(x)))) < 1e-14
+
+
+def test_r_rng_known_answers(oracle):
+    """values printed by R: set.seed(1); runif(3)  and  set.seed(42); runif(2)"""
+    assert np.allclose(oracle.RNG.set_seed(1).runif(3), [0.2655087, 0.3721239, 0.5728534], atol=5e-8)
+    assert np.allclose(oracle.RNG.set_seed(42).runif(2), [0.9148060, 0.9370754], atol=5e-8)
+    g = oracle.RNG.set_seed(123)  # set.seed(123); runif(1) = 0.2875775
+    assert abs(g.unif_rand() - 0.2875775) < 5e-8
+
+
+def test_product_rng_matches_oracle(oracle):
+    from epigrahmm_b200.rng import RState
+    a, b = RState(210423), oracle.RNG.set_seed(210423)
+    assert np.array_equal(a.runif(5000), b.runif(5000))
+    assert np.array_equal(a.state, b.state())
+
+
+def _twin_expstep(pi, gamma, logf):
+    """textbook log-space forward-backward written independently of the oracle"""
+    M, K = logf.shape
+    lg = np.log(gamma)
+    F = np.empty((M, K))
+    B = np.zeros((M, K))
+    F[0] = np.log(pi) + logf[0]
+    for j in range(1, M):
+        F[j] = logsumexp(F[j - 1][:, None] + lg, axis=0) + logf[j]
+    for j in range(M - 2, -1, -1):
+        B[j] = logsumexp(lg + (logf[j + 1] + B[j + 1])[None, :], axis=1)
+    ll = logsumexp(F[-1])
+    L1 = F + B - ll
+    L1 -= logsumexp(L1, axis=1, keepdims=True)
+    L2 = np.zeros((M, K * K))
+    for j in range(1, M):
+        L2[j] = (F[j - 1][:, None] + lg + (logf[j] + B[j])[None, :] - ll).ravel()
+    L2 -= logsumexp(L2, axis=1, keepdims=True)
+    return F, B, L1, L2, ll
+
+
+@pytest.mark.parametrize("K", [2, 3])
+def test_expstep_against_numpy_twin(oracle, K):
+    from epigrahmm_b200 import synth
+    M = 3000
+    rng = np.random.default_rng(K)
+    logf = rng.normal(-5, 2, (M, K))
+    th = synth.THETA_CONSENSUS if K == 2 else synth.THETA_DIFFERENTIAL
+    h = oracle.expStep(th["pi"], th["gamma"], logf)
+    F, B, L1, L2, ll = _twin_expstep(th["pi"], th["gamma"], logf)
+    assert np.allclose(h["logFP"], F, rtol=1e-12) and np.allclose(h["logBP"], B, rtol=1e-12, atol=1e-12)
+    assert np.allclose(h["logProb1"], L1, atol=1e-9) and np.allclose(h["logProb2"], L2, atol=1e-9)
+    # maxStepProb / Q / BIC from their definitions
+    P2 = np.exp(L2[1:])
+    gam = (P2.sum(0).reshape(K, K).T / P2.sum(0).reshape(K, K).sum(1)).T
+    gam = np.maximum(gam, 1e-6)
+    gam /= gam.sum(1, keepdims=True)
+    m = oracle.maxStepProb(h)
+    assert np.allclose(m["gamma"], gam, rtol=1e-9)
+    p0 = np.maximum(np.exp(L1[0]), 1e-6)
+    assert np.allclose(m["pi"], p0 / p0.sum(), rtol=1e-9)
+    q = np.exp(L1[0]) @ np.log(th["pi"]) + np.sum(np.exp(L1) * logf) + np.sum(P2 * np.log(th["gamma"]).ravel())
+    assert abs(oracle.computeQFunction(h, th["pi"], th["gamma"]) - q) < 1e-9 * abs(q)
+    assert abs(oracle.computeBIC(h, 6, 4) - (-2 * ll + 6 * np.log(4 * M))) < 1e-9 * abs(ll)
+    # Viterbi: the reference's recursion scores bins with logFP (src/computeViterbiSequence.cpp:20)
+    V = np.log(th["pi"]) + F[0]
+    lg = np.log(th["gamma"])
+    psi = np.zeros((M, K), dtype=int)
+    for j in range(1, M):
+        c = V[:, None] + lg
+        psi[j] = c.argmax(0)
+        V = c.max(0) + F[j]
+    S = np.empty(M)
+    S[-1] = V.argmax()
+    for j in range(M - 2, -1, -1):
+        S[j] = psi[j + 1][int(S[j + 1])]
+    assert np.array_equal(oracle.computeViterbiSequence(h, th["pi"], th["gamma"]), S)
+
+
+def test_reweight_aggregate_semantics(oracle):
+    x = np.array([0.0, 0.5, 0.01, 0.2, 0.9, 1e-320])
+    u = np.array([0.5, 0.1, 0.3])  # consumed by 0.01, 0.2 and the subnormal, in that order; 0.0 draws nothing
+    w, n = oracle.reweight(x, 0.3, uniforms=u)
+    assert n == 3
+    # rbinom(1, q): q <= .5 -> [u >= 1-q];  q > .5 -> 1 - [u >= 1-(1-q)]
+    assert np.array_equal(w, [0.0, 0.5, 0.0, 0.3, 0.9, 0.0])
+    w3, _ = oracle.reweight(x, 0.3, uniforms=np.array([0.97, 0.999, 0.3]))
+    assert np.array_equal(w3, [0.0, 0.5, 0.3, 0.0, 0.9, 0.0])
+    w2, n2 = oracle.reweight(x, 0.0, uniforms=u)
+    assert n2 == 0 and np.array_equal(w2, x)
+    # aggregate: only non-zero sums, ascending id, only the first len(x) ids are read
+    a = oracle.aggregate(np.array([1.0, 0.0, 2.0, 0.5]), np.array([3, 1, 3, 7, 9, 9]))
+    assert np.array_equal(a, [[3.0, 3.0], [0.5, 7.0]])
+
+
+def test_rbinom_probability(oracle):
+    rng = oracle.RNG.set_seed(99)
+    x = np.full(200000, 0.06)
+    w, n = oracle.reweight(x, 0.3, rng=rng)
+    assert n == x.size and abs((w > 0).mean() - 0.2) < 0.005 and set(np.unique(w)) == {0.0, 0.3}
+
+
+def test_oracle_reproduces_golden(oracle):
+    from epigrahmm_b200 import synth
+    g = np.load(os.path.join(GOLD, "golden_small.npz"))
+    th = synth.THETA_CONSENSUS
+    logf = oracle.loglikConsensusHMM(g["c_counts"], g["c_offsets"], th["psi"], MINZERO)
+    assert np.array_equal(logf, g["c_logf"])
+    h = oracle.expStep(th["pi"], th["gamma"], logf)
+    for n in ("logFP", "logBP", "logProb1", "logProb2"):
+        assert np.array_equal(h[n], g["c_" + n])
+    assert np.array_equal(oracle.computeViterbiSequence(h, th["pi"], th["gamma"]), g["c_viterbi"])
+    rc, n = oracle.consensusRejectionControlled(h, g["c_group"], 0.05, uniforms=g["c_unif"], dense=True)
+    assert n == g["c_rc_n"] and np.array_equal(rc, g["c_rc"])
+    th = synth.THETA_DIFFERENTIAL
+    delta = np.full(6, 1 / 6)
+    logf = oracle.loglikDifferentialHMM(g["d_counts"], g["d_offsets"], g["d_design"], delta, th["psi"], MINZERO)
+    assert np.array_equal(logf, g["d_logf"])
+    assert np.array_equal(oracle.innerExpStep(g["d_counts"], g["d_offsets"], g["d_design"], delta, th["psi"], MINZERO),
+                          g["d_eta"])
+
+
+def test_helas3_fixture():
+    a = np.load(os.path.join(GOLD, "helas3_counts.npz"))["counts"]
+    assert a.shape == (9994, 6) and a.dtype == np.int32
+    assert a.sum(0).tolist() == [104862, 75257, 86302, 59193, 91121, 85604] and a.max() == 191
