@@ -79,12 +79,16 @@ PROTOTYPES = {
     "ehmm_aggregate": [C.c_int, _dp, C.c_int64, _ip, C.c_int64, _dp],
     "ehmm_glm_nb": [_sess, C.c_int, _dp, C.c_int, _dp, _dp],
     "ehmm_glm_mix_nb": [_sess, _dp, C.c_double, _dp, _dp],
+    "ehmm_profile_kernels": [],
+    "ehmm_profile_name": [C.c_int],
+    "ehmm_profile": [_sess, C.c_int],
+    "ehmm_profile_read": [_sess, _lp, _dp],
     "ehmm_dataset_dims": [_sess, C.c_char_p, _lp, _lp],
     "ehmm_fetch": [_sess, C.c_char_p, _dp, C.c_int64],
     "ehmm_device_ptr": [_sess, C.c_char_p, C.POINTER(C.c_void_p)],
     "ehmm_store": [_sess, C.c_char_p, _dp, C.c_int64, C.c_int64],
 }
-_RESTYPE = {"ehmm_last_error": C.c_char_p}
+_RESTYPE = {"ehmm_last_error": C.c_char_p, "ehmm_profile_name": C.c_char_p}
 
 for _name, _args in PROTOTYPES.items():
     _fn = getattr(lib, _name)  # AttributeError here = header and library out of sync

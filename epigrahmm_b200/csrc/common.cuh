@@ -64,6 +64,19 @@ enum : unsigned {
     DS_ESTEP = DS_FP | DS_BP | DS_P1 | DS_P2
 };
 
+// kernel ids for the launch counters / optional CUDA-event profile (ehmm_profile*)
+enum KernelId : int {
+    KID_EMIS_TAB, KID_EMIS_CONSENSUS, KID_EMIS_DIFF, KID_EMIS_INNER, KID_INNER_MSTEP,
+    KID_FB_REDUCE, KID_FB_CARRY, KID_FB_APPLY, KID_FB_FIX, KID_FB_STATS,
+    KID_RC_COUNT, KID_RC_SCAN, KID_MT, KID_RC_APPLY, KID_GLM, KID_GLM_FINAL,
+    KID_VIT_FWD, KID_VIT_BWD, KID_MISC, KID_COUNT
+};
+static const char *const kKernelNames[KID_COUNT] = {
+    "lgtab", "emis_consensus", "emis_diff_hmm", "emis_inner", "inner_mstep",
+    "fb_reduce", "fb_carry", "fb_apply", "fb_boundary_fix", "fb_stats",
+    "rc_count", "rc_scan", "mt_generate", "rc_apply", "glm", "glm_final",
+    "viterbi_forward", "viterbi_backtrace", "misc"};
+
 // forward-backward tiling (fb.cu)
 constexpr int FB_MAX_STATS = EHMM_MAX_K * EHMM_MAX_K + 1;
 
@@ -121,6 +134,22 @@ struct ehmm_session {
     ehmm::DevBuf lgtab, glm_part, misc;
     int64_t count_max = -1;
     double *h_pinned = nullptr;  // small pinned staging buffer (256 doubles)
+
+    // ---- launch counters and optional per-kernel CUDA-event timing ----
+    int64_t launches[ehmm::KID_COUNT] = {0};
+    bool prof_on = false;
+    struct ProfRec { int kid; cudaEvent_t e0, e1; };
+    std::vector<cudaEvent_t> prof_pool;
+    size_t prof_used = 0;
+    std::vector<ProfRec> prof_recs;
+    cudaEvent_t prof_event() {
+        if (prof_used == prof_pool.size()) {
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            prof_pool.push_back(e);
+        }
+        return prof_pool[prof_used++];
+    }
 };
 
 namespace ehmm {
@@ -134,6 +163,26 @@ inline int check_session(ehmm_session *s) {
     }
     return EHMM_OK;
 }
+
+// counts every launch; with profiling on, brackets it with CUDA events on the session stream.
+// Used as a temporary in front of the launch: `PROF(s, KID_X), kernel<<<...>>>(...);`
+struct ProfScope {
+    ehmm_session *s;
+    cudaEvent_t e1 = nullptr;
+    ProfScope(ehmm_session *s_, int kid) : s(s_) {
+        s->launches[kid]++;
+        if (s->prof_on) {
+            cudaEvent_t e0 = s->prof_event();
+            e1 = s->prof_event();
+            cudaEventRecord(e0, s->stream);
+            s->prof_recs.push_back({kid, e0, e1});
+        }
+    }
+    ~ProfScope() {
+        if (e1) cudaEventRecord(e1, s->stream);
+    }
+};
+#define PROF(s, kid) ehmm::ProfScope(s, ehmm::kid)
 
 // fb.cu
 int fb_expstep(ehmm_session *s, const double *d_logf);

@@ -230,7 +230,7 @@ int prepare_tab(ehmm_session *s, EmisParams &P, int nd, double minZero) {
     P.tabn = (int)tabn;
     EHMM_TRY(s->lgtab.reserve(sizeof(double) * MAX_DENS * TAB_MAX));
     int n = nd * P.tabn;
-    lgtab_kernel<<<(n + 255) / 256, 256, 0, s->stream>>>(P, nd, s->lgtab.as<double>());
+    PROF(s, KID_EMIS_TAB), lgtab_kernel<<<(n + 255) / 256, 256, 0, s->stream>>>(P, nd, s->lgtab.as<double>());
     EHMM_CK(cudaGetLastError());
     return EHMM_OK;
 }
@@ -269,11 +269,11 @@ int emis_consensus(ehmm_session *s, const double *th1, const double *th2, int P_
     EHMM_TRY(s->logf.reserve(sizeof(double) * s->M * 2));
     const int g = grid_for(s->M);
     if (P_ == 3)
-        emis_consensus_kernel<true, true><<<g, EM_NT, 0, s->stream>>>(s->M, s->N, s->d_counts, s->d_offsets,
+        PROF(s, KID_EMIS_CONSENSUS), emis_consensus_kernel<true, true><<<g, EM_NT, 0, s->stream>>>(s->M, s->N, s->d_counts, s->d_offsets,
                                                                      s->d_controls, P, s->lgtab.as<double>(),
                                                                      s->logf.as<double>());
     else
-        emis_consensus_kernel<false, true><<<g, EM_NT, 0, s->stream>>>(s->M, s->N, s->d_counts, s->d_offsets, nullptr,
+        PROF(s, KID_EMIS_CONSENSUS), emis_consensus_kernel<false, true><<<g, EM_NT, 0, s->stream>>>(s->M, s->N, s->d_counts, s->d_offsets, nullptr,
                                                                       P, s->lgtab.as<double>(), s->logf.as<double>());
     EHMM_CK(cudaGetLastError());
     s->valid |= DS_LOGF;
@@ -289,7 +289,7 @@ int emis_init(ehmm_session *s, const double *psi1, const double *psi2) {
     fill_density(P, 1, psi2[0], 0.0, psi2[1]);
     EHMM_TRY(prepare_tab(s, P, 2, 2.2250738585072014e-308));
     EHMM_TRY(s->logf.reserve(sizeof(double) * s->M * 2));
-    emis_consensus_kernel<false, false><<<grid_for(s->M), EM_NT, 0, s->stream>>>(
+    PROF(s, KID_EMIS_CONSENSUS), emis_consensus_kernel<false, false><<<grid_for(s->M), EM_NT, 0, s->stream>>>(
         s->M, 1, s->d_counts, s->d_offsets, nullptr, P, s->lgtab.as<double>(), s->logf.as<double>());
     EHMM_CK(cudaGetLastError());
     s->valid |= DS_LOGF;
@@ -307,10 +307,10 @@ int emis_differential_hmm(ehmm_session *s, const double *delta, const double *ps
     EHMM_TRY(s->logf.reserve(sizeof(double) * s->M * 3));
     const int g = grid_for(s->M);
     if (s->N <= 16)
-        emis_diff_hmm_kernel<16><<<g, EM_NT, 0, s->stream>>>(s->M, s->N, s->d_counts, s->d_offsets, P, X,
+        PROF(s, KID_EMIS_DIFF), emis_diff_hmm_kernel<16><<<g, EM_NT, 0, s->stream>>>(s->M, s->N, s->d_counts, s->d_offsets, P, X,
                                                             s->lgtab.as<double>(), s->logf.as<double>());
     else
-        emis_diff_hmm_kernel<64><<<g, EM_NT, 0, s->stream>>>(s->M, s->N, s->d_counts, s->d_offsets, P, X,
+        PROF(s, KID_EMIS_DIFF), emis_diff_hmm_kernel<64><<<g, EM_NT, 0, s->stream>>>(s->M, s->N, s->d_counts, s->d_offsets, P, X,
                                                             s->lgtab.as<double>(), s->logf.as<double>());
     EHMM_CK(cudaGetLastError());
     s->valid |= DS_LOGF;
@@ -327,10 +327,10 @@ int emis_inner_estep(ehmm_session *s, const double *delta, const double *psi, do
     EHMM_TRY(s->eta.reserve(sizeof(double) * s->M * s->B));
     const int g = grid_for(s->M);
     if (s->N <= 16)
-        emis_inner_kernel<16><<<g, EM_NT, 0, s->stream>>>(s->M, s->N, s->d_counts, s->d_offsets, P, X,
+        PROF(s, KID_EMIS_INNER), emis_inner_kernel<16><<<g, EM_NT, 0, s->stream>>>(s->M, s->N, s->d_counts, s->d_offsets, P, X,
                                                          s->lgtab.as<double>(), s->eta.as<double>());
     else
-        emis_inner_kernel<64><<<g, EM_NT, 0, s->stream>>>(s->M, s->N, s->d_counts, s->d_offsets, P, X,
+        PROF(s, KID_EMIS_INNER), emis_inner_kernel<64><<<g, EM_NT, 0, s->stream>>>(s->M, s->N, s->d_counts, s->d_offsets, P, X,
                                                          s->lgtab.as<double>(), s->eta.as<double>());
     EHMM_CK(cudaGetLastError());
     s->valid |= DS_ETA;
@@ -344,9 +344,9 @@ int inner_maxstepprob(ehmm_session *s, double *delta_out) {
     const int nblk = 148 * 4;
     EHMM_TRY(s->misc.reserve(sizeof(double) * ((size_t)nblk * (B + 1) + B + 1)));
     double *part = s->misc.as<double>(), *out = part + (size_t)nblk * (B + 1);
-    inner_mstep_kernel<<<nblk, 256, 0, s->stream>>>(s->M, B, s->logProb1.as<double>() + s->M, s->eta.as<double>(), part);
+    PROF(s, KID_INNER_MSTEP), inner_mstep_kernel<<<nblk, 256, 0, s->stream>>>(s->M, B, s->logProb1.as<double>() + s->M, s->eta.as<double>(), part);
     EHMM_CK(cudaGetLastError());
-    colsum_kernel<<<1, 256, 0, s->stream>>>(part, nblk, B + 1, out);
+    PROF(s, KID_MISC), colsum_kernel<<<1, 256, 0, s->stream>>>(part, nblk, B + 1, out);
     EHMM_CK(cudaGetLastError());
     EHMM_CK(cudaMemcpyAsync(s->h_pinned + 64, out, sizeof(double) * (B + 1), cudaMemcpyDeviceToHost, s->stream));
     EHMM_CK(cudaStreamSynchronize(s->stream));

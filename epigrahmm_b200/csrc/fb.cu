@@ -721,12 +721,12 @@ template <int K> int launch_reduce(ehmm_session *s, const double *d_logf, int mo
     fill_params(s, P);
     const int64_t nT = num_tiles<K>(s->M);
     const int first = (s->m0 == 0) ? 1 : 0;
-    fb_reduce_kernel<K, C::NT, C::L><<<(unsigned)nT, C::NT, reduce_smem<K>(), s->stream>>>(
+    PROF(s, KID_FB_REDUCE), fb_reduce_kernel<K, C::NT, C::L><<<(unsigned)nT, C::NT, reduce_smem<K>(), s->stream>>>(
         d_logf, s->M, first, P, s->tileops.as<double>());
     EHMM_CK(cudaGetLastError());
     if (mode0_total) {
         CarryIn cin = {};
-        fb_carry_kernel<K><<<1, CARRY_NT, 0, s->stream>>>(s->tileops.as<double>(), nT, 0, cin, nullptr,
+        PROF(s, KID_FB_CARRY), fb_carry_kernel<K><<<1, CARRY_NT, 0, s->stream>>>(s->tileops.as<double>(), nT, 0, cin, nullptr,
                                                          s->fbscal.as<double>());
         EHMM_CK(cudaGetLastError());
     }
@@ -740,20 +740,20 @@ template <int K> int launch_apply(ehmm_session *s, const double *d_logf, const C
     const int64_t nT = num_tiles<K>(s->M);
     const int first = (s->m0 == 0) ? 1 : 0;
     double *scal = s->fbscal.as<double>();
-    fb_carry_kernel<K><<<1, CARRY_NT, 0, s->stream>>>(s->tileops.as<double>(), nT, 1, cin, s->carries.as<double>(),
+    PROF(s, KID_FB_CARRY), fb_carry_kernel<K><<<1, CARRY_NT, 0, s->stream>>>(s->tileops.as<double>(), nT, 1, cin, s->carries.as<double>(),
                                                      scal);
     EHMM_CK(cudaGetLastError());
-    fb_apply_kernel<K, C::NT, C::L><<<(unsigned)nT, C::NT, apply_smem<K>(), s->stream>>>(
+    PROF(s, KID_FB_APPLY), fb_apply_kernel<K, C::NT, C::L><<<(unsigned)nT, C::NT, apply_smem<K>(), s->stream>>>(
         d_logf, s->M, first, P, s->carries.as<double>(), s->logFP.as<double>(), s->logBP.as<double>(),
         s->logProb1.as<double>(), s->logProb2.as<double>(), s->tilestats.as<double>());
     EHMM_CK(cudaGetLastError());
     if (nT > 1) {
-        fb_boundary_fix_kernel<K><<<(unsigned)((nT - 1 + 255) / 256), 256, 0, s->stream>>>(
+        PROF(s, KID_FB_FIX), fb_boundary_fix_kernel<K><<<(unsigned)((nT - 1 + 255) / 256), 256, 0, s->stream>>>(
             s->M, nT, C::NT * C::L, P, s->carries.as<double>(), d_logf, s->logFP.as<double>(), s->logProb1.as<double>(),
             s->logProb2.as<double>());
         EHMM_CK(cudaGetLastError());
     }
-    fb_stats_kernel<<<1, 256, 0, s->stream>>>(s->tilestats.as<double>(), nT, K * K + 1, scal + scal_stats_off<K>());
+    PROF(s, KID_FB_STATS), fb_stats_kernel<<<1, 256, 0, s->stream>>>(s->tilestats.as<double>(), nT, K * K + 1, scal + scal_stats_off<K>());
     EHMM_CK(cudaGetLastError());
     return EHMM_OK;
 }
@@ -801,11 +801,11 @@ template <int K> int fetch_stats_impl(ehmm_session *s) {
         EHMM_TRY(s->tilestats.reserve(sizeof(double) * nblk * NS));
         const bool p12 = has(s, DS_P1 | DS_P2);
         if (p12) {
-            fb_stats_from_datasets_kernel<K><<<nblk, 256, 0, s->stream>>>(
+            PROF(s, KID_MISC), fb_stats_from_datasets_kernel<K><<<nblk, 256, 0, s->stream>>>(
                 s->M, has(s, DS_LOGF) ? s->logf.as<double>() : nullptr, s->logProb1.as<double>(),
                 s->logProb2.as<double>(), s->tilestats.as<double>());
             EHMM_CK(cudaGetLastError());
-            fb_stats_kernel<<<1, 256, 0, s->stream>>>(s->tilestats.as<double>(), nblk, NS,
+            PROF(s, KID_FB_STATS), fb_stats_kernel<<<1, 256, 0, s->stream>>>(s->tilestats.as<double>(), nblk, NS,
                                                      s->fbscal.as<double>() + scal_stats_off<K>());
             EHMM_CK(cudaGetLastError());
             EHMM_CK(cudaMemcpyAsync(hp + 1, s->fbscal.as<double>() + scal_stats_off<K>(), sizeof(double) * NS,

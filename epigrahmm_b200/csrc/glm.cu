@@ -152,7 +152,7 @@ int blocks_for(int64_t n) {
 int finish(ehmm_session *s, int nblk, int nout, double *host_out) {
     double *part = s->glm_part.as<double>();
     double *out = part + (size_t)148 * 4 * GLM_MAXOUT;
-    glm_final_kernel<<<1, 256, 0, s->stream>>>(part, nblk, nout, out);
+    PROF(s, KID_GLM_FINAL), glm_final_kernel<<<1, 256, 0, s->stream>>>(part, nblk, nout, out);
     EHMM_CK(cudaGetLastError());
     EHMM_CK(cudaMemcpyAsync(s->h_pinned + 128, out, sizeof(double) * nout, cudaMemcpyDeviceToHost, s->stream));
     EHMM_CK(cudaStreamSynchronize(s->stream));
@@ -178,7 +178,7 @@ int glm_nb(ehmm_session *s, int column, const double *par, int P_, double *value
     P.has_ctrl = (P_ == 2);
     EHMM_TRY(s->glm_part.reserve(sizeof(double) * ((size_t)148 * 4 * GLM_MAXOUT + GLM_MAXOUT)));
     const int nblk = blocks_for(s->G);
-    glm_nb_kernel<<<nblk, GLM_NT, 0, s->stream>>>(s->G, s->rc_buckets.as<double>() + (size_t)column * (s->G + 1),
+    PROF(s, KID_GLM), glm_nb_kernel<<<nblk, GLM_NT, 0, s->stream>>>(s->G, s->rc_buckets.as<double>() + (size_t)column * (s->G + 1),
                                                  s->u_chip.as<double>(), s->u_off.as<double>(),
                                                  s->u_ctrl.as<double>(), P, s->glm_part.as<double>());
     EHMM_CK(cudaGetLastError());
@@ -213,7 +213,7 @@ int glm_mix_nb(ehmm_session *s, const double *par, double minZero, double *value
     EHMM_TRY(s->glm_part.reserve(sizeof(double) * ((size_t)148 * 4 * GLM_MAXOUT + GLM_MAXOUT)));
     const int ncol = s->B + 2;
     const int nblk = blocks_for((int64_t)ncol * (s->G + 1));
-    glm_mix_kernel<<<nblk, GLM_NT, 0, s->stream>>>(s->G, ncol, s->rc_buckets.as<double>(), s->u_chip.as<double>(),
+    PROF(s, KID_GLM), glm_mix_kernel<<<nblk, GLM_NT, 0, s->stream>>>(s->G, ncol, s->rc_buckets.as<double>(), s->u_chip.as<double>(),
                                                   s->u_off.as<double>(), s->u_dsg.as<uint8_t>(), P,
                                                   s->glm_part.as<double>());
     EHMM_CK(cudaGetLastError());

@@ -280,9 +280,9 @@ int run_rc(ehmm_session *s, const RCSrc &S, double p, int nrep, const double *un
     dim3 grid((unsigned)nblk, (unsigned)S.columns);
     int64_t total = 0;
     if (p > 0.0) {
-        rc_count_kernel<<<grid, RC_NT, 0, s->stream>>>(S, p, nblk, s->rc_flag.as<int>());
+        PROF(s, KID_RC_COUNT), rc_count_kernel<<<grid, RC_NT, 0, s->stream>>>(S, p, nblk, s->rc_flag.as<int>());
         EHMM_CK(cudaGetLastError());
-        rc_scan_kernel<<<1, 1024, 0, s->stream>>>(s->rc_flag.as<int>(), ncnt, s->rc_scan.as<int64_t>());
+        PROF(s, KID_RC_SCAN), rc_scan_kernel<<<1, 1024, 0, s->stream>>>(s->rc_flag.as<int>(), ncnt, s->rc_scan.as<int64_t>());
         EHMM_CK(cudaGetLastError());
         EHMM_CK(cudaMemcpyAsync(s->h_pinned + 200, s->rc_scan.as<int64_t>() + ncnt, sizeof(int64_t), cudaMemcpyDeviceToHost,
                                 s->stream));
@@ -298,7 +298,7 @@ int run_rc(ehmm_session *s, const RCSrc &S, double p, int nrep, const double *un
         EHMM_TRY(s->rc_unif.reserve(sizeof(double) * (size_t)(total > 0 ? total : 1)));
         if (total > 0)
             EHMM_CK(cudaMemcpyAsync(s->rc_unif.p, uniforms, sizeof(double) * total, cudaMemcpyHostToDevice, s->stream));
-        rc_apply_kernel<double><<<grid, RC_NT, 0, s->stream>>>(S, p, nblk, s->rc_scan.as<int64_t>(),
+        PROF(s, KID_RC_APPLY), rc_apply_kernel<double><<<grid, RC_NT, 0, s->stream>>>(S, p, nblk, s->rc_scan.as<int64_t>(),
                                                                s->rc_unif.as<double>(), grp, nrep, s->G,
                                                                s->rc_buckets.as<double>(), nullptr);
     } else {
@@ -308,11 +308,11 @@ int run_rc(ehmm_session *s, const RCSrc &S, double p, int nrep, const double *un
         EHMM_TRY(s->mt_raw.reserve(sizeof(uint32_t) * 625));
         if (total > 0) {
             EHMM_CK(cudaMemcpyAsync(s->mt_raw.p, s->rng_state, sizeof(uint32_t) * 625, cudaMemcpyHostToDevice, s->stream));
-            mt_generate_kernel<<<1, 256, 0, s->stream>>>(s->mt_raw.as<uint32_t>(), total, s->rc_unif.as<uint32_t>());
+            PROF(s, KID_MT), mt_generate_kernel<<<1, 256, 0, s->stream>>>(s->mt_raw.as<uint32_t>(), total, s->rc_unif.as<uint32_t>());
             EHMM_CK(cudaGetLastError());
             EHMM_CK(cudaMemcpyAsync(s->rng_state, s->mt_raw.p, sizeof(uint32_t) * 625, cudaMemcpyDeviceToHost, s->stream));
         }
-        rc_apply_kernel<uint32_t><<<grid, RC_NT, 0, s->stream>>>(S, p, nblk, s->rc_scan.as<int64_t>(),
+        PROF(s, KID_RC_APPLY), rc_apply_kernel<uint32_t><<<grid, RC_NT, 0, s->stream>>>(S, p, nblk, s->rc_scan.as<int64_t>(),
                                                                  s->rc_unif.as<uint32_t>(), grp, nrep, s->G,
                                                                  s->rc_buckets.as<double>(), nullptr);
     }

@@ -51,7 +51,7 @@ int scan_counts(ehmm_session *s) {
     EHMM_TRY(s->misc.reserve(64));
     int *d = s->misc.as<int>();
     EHMM_CK(cudaMemcpyAsync(d, h, sizeof(h), cudaMemcpyHostToDevice, s->stream));
-    minmax_i32_kernel<<<148 * 8, 256, 0, s->stream>>>(s->d_counts, s->M * s->N, d);
+    PROF(s, KID_MISC), minmax_i32_kernel<<<148 * 8, 256, 0, s->stream>>>(s->d_counts, s->M * s->N, d);
     EHMM_CK(cudaGetLastError());
     EHMM_CK(cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, s->stream));
     EHMM_CK(cudaStreamSynchronize(s->stream));
@@ -185,6 +185,7 @@ int ehmm_session_close(ehmm_session *s) {
                       &s->tileops, &s->carries, &s->tilestats, &s->fbscal, &s->rc_w, &s->rc_flag, &s->rc_scan,
                       &s->rc_buckets, &s->rc_unif, &s->rc_tmp, &s->mt_raw, &s->lgtab, &s->glm_part, &s->misc};
     for (DevBuf *b : bufs) b->release();
+    for (cudaEvent_t e : s->prof_pool) cudaEventDestroy(e);
     if (s->h_pinned) cudaFreeHost(s->h_pinned);
     if (s->ev) cudaEventDestroy(s->ev);
     if (s->stream) cudaStreamDestroy(s->stream);
@@ -458,7 +459,7 @@ int ehmm_marginal_probability(ehmm_session *s, double *out) {
     EHMM_REQUIRE(has(s, DS_P1) && out, EHMM_ERR_STATE, "getMarginalProbability: expStep has not run");
     const int64_t n = s->M * s->K;
     EHMM_TRY(s->rc_tmp.reserve(sizeof(double) * n));
-    exp_kernel<<<148 * 8, 256, 0, s->stream>>>(s->logProb1.as<double>(), n, s->rc_tmp.as<double>());
+    PROF(s, KID_MISC), exp_kernel<<<148 * 8, 256, 0, s->stream>>>(s->logProb1.as<double>(), n, s->rc_tmp.as<double>());
     EHMM_CK(cudaGetLastError());
     EHMM_CK(cudaMemcpyAsync(out, s->rc_tmp.p, sizeof(double) * n, cudaMemcpyDeviceToHost, s->stream));
     EHMM_CK(cudaStreamSynchronize(s->stream));
@@ -544,6 +545,35 @@ int ehmm_glm_mix_nb(ehmm_session *s, const double *par, double minZero, double *
     EHMM_REQUIRE(par && value, EHMM_ERR_ARG, "null pointer");
     EHMM_REQUIRE(s->rc_columns == s->B + 2 && s->B > 0, EHMM_ERR_STATE, "glmMixNB: differential rejection tables not available");
     return glm_mix_nb(s, par, minZero, value, grad);
+}
+
+int ehmm_profile_kernels(void) { return KID_COUNT; }
+
+const char *ehmm_profile_name(int kernel_id) {
+    return (kernel_id >= 0 && kernel_id < KID_COUNT) ? kKernelNames[kernel_id] : "";
+}
+
+int ehmm_profile(ehmm_session *s, int enable) {
+    EHMM_TRY(check_session(s));
+    EHMM_CK(cudaStreamSynchronize(s->stream));
+    for (int i = 0; i < KID_COUNT; i++) s->launches[i] = 0;
+    s->prof_recs.clear();
+    s->prof_used = 0;
+    s->prof_on = enable != 0;
+    return EHMM_OK;
+}
+
+int ehmm_profile_read(ehmm_session *s, int64_t *launches, double *ms) {
+    EHMM_TRY(check_session(s));
+    EHMM_REQUIRE(launches && ms, EHMM_ERR_ARG, "null pointer");
+    EHMM_CK(cudaStreamSynchronize(s->stream));
+    for (int i = 0; i < KID_COUNT; i++) { launches[i] = s->launches[i]; ms[i] = 0.0; }
+    for (const auto &r : s->prof_recs) {
+        float t = 0.f;
+        EHMM_CK(cudaEventElapsedTime(&t, r.e0, r.e1));
+        ms[r.kid] += t;
+    }
+    return EHMM_OK;
 }
 
 int ehmm_dataset_dims(ehmm_session *s, const char *name, int64_t *rows, int64_t *cols) {

@@ -143,9 +143,9 @@ template <int K> int run(ehmm_session *s, const VitPar &P, double *states_out) {
         EHMM_CK(cudaFuncSetAttribute(viterbi_forward_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr[K] = true;
     }
-    viterbi_forward_kernel<K><<<1, VT_NT, smem, s->stream>>>(s->logFP.as<double>(), M, P, bp, vlast);
+    PROF(s, KID_VIT_FWD), viterbi_forward_kernel<K><<<1, VT_NT, smem, s->stream>>>(s->logFP.as<double>(), M, P, bp, vlast);
     EHMM_CK(cudaGetLastError());
-    viterbi_backtrace_kernel<K><<<1, VT_NT, 0, s->stream>>>(bp, M, vlast, s->viterbi.as<double>());
+    PROF(s, KID_VIT_BWD), viterbi_backtrace_kernel<K><<<1, VT_NT, 0, s->stream>>>(bp, M, vlast, s->viterbi.as<double>());
     EHMM_CK(cudaGetLastError());
     if (states_out)
         EHMM_CK(cudaMemcpyAsync(states_out, s->viterbi.p, sizeof(double) * M, cudaMemcpyDeviceToHost, s->stream));

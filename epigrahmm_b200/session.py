@@ -230,6 +230,18 @@ class Session:
         check(lib.ehmm_glm_mix_nb(self._h, dptr(par), float(minZero), C.byref(v), dptr(g)))
         return v.value, g
 
+    # -- launch accounting -----------------------------------------------------------------
+    def profile(self, enable=True):
+        check(lib.ehmm_profile(self._h, 1 if enable else 0))
+
+    def profile_read(self):
+        """{kernel name: (launches, summed CUDA-event ms)} since the last profile() call"""
+        n = lib.ehmm_profile_kernels()
+        cnt = np.zeros(n, dtype=np.int64)
+        ms = np.zeros(n)
+        check(lib.ehmm_profile_read(self._h, cnt.ctypes.data_as(C.POINTER(C.c_int64)), dptr(ms)))
+        return {lib.ehmm_profile_name(i).decode(): (int(cnt[i]), float(ms[i])) for i in range(n)}
+
     # -- datasets --------------------------------------------------------------------------
     def dims(self, name):
         r, c = C.c_int64(), C.c_int64()

@@ -73,29 +73,39 @@ def make_differential(M: int, n_cond: int, n_rep: int, seed: int):
 
 def make_groups(counts, offsets, controls=None, design=None):
     """dt$Group and dtUnique (R/base-core.R:97-104,187-198): 1-based ids in order of first
-    appearance over the column-major long table, keyed by (ChIP[, controls], offsets[, Dsg.Mix*])."""
+    appearance over the column-major long table, keyed by (ChIP[, controls], offsets[, Dsg.Mix*]).
+    Each key column is ranked on its own and the ranks are packed into one int64 so that a single
+    1-D sort finds the groups (M*N can be 1e8)."""
+    counts = np.asarray(counts)
     M, N = counts.shape
-    cols = [np.asarray(counts, dtype=np.float64).ravel(order="F")]
+    cols = [counts.ravel(order="F").astype(np.float64)]
     if controls is not None:
         cols.append(np.asarray(controls, dtype=np.float64).ravel(order="F"))
     cols.append(np.asarray(offsets, dtype=np.float64).ravel(order="F"))
+    key = np.zeros(M * N, dtype=np.int64)
+    for c in cols:
+        u, inv = np.unique(c, return_inverse=True)
+        if key.max(initial=0) > (2 ** 62) // max(u.size, 1):
+            raise OverflowError("too many distinct key values to pack")
+        key = key * u.size + inv.ravel()
     if design is not None:
-        for b in range(design.shape[0]):
-            cols.append(np.repeat(design[b].astype(np.float64), M))
-    key = np.column_stack(cols)
-    _, first, inv = np.unique(key, axis=0, return_index=True, return_inverse=True)
+        # the Dsg.Mix columns depend on the sample only: one code per distinct design column
+        _, dcode = np.unique(np.asarray(design).T, axis=0, return_inverse=True)
+        dcode = np.asarray(dcode).ravel()
+        key = key * (int(dcode.max()) + 1) + np.repeat(dcode.astype(np.int64), M)
+    _, first, inv = np.unique(key, return_index=True, return_inverse=True)
     inv = np.asarray(inv).ravel()
     order = np.argsort(first, kind="stable")          # groups numbered by first appearance (.GRP)
     rank = np.empty_like(order)
     rank[order] = np.arange(order.size)
     group = (rank[inv] + 1).astype(np.int32)
-    uniq_rows = key[first[order]]
+    rows = first[order]
     out = dict(group=np.asfortranarray(group.reshape(M, N, order="F")), G=int(order.size),
-               u_chip=uniq_rows[:, 0].copy(), u_offsets=uniq_rows[:, 2 if controls is not None else 1].copy())
-    out["u_controls"] = uniq_rows[:, 1].copy() if controls is not None else None
+               u_chip=cols[0][rows].copy(), u_offsets=cols[-1][rows].copy())
+    out["u_controls"] = cols[1][rows].copy() if controls is not None else None
     if design is not None:
-        nb = design.shape[0]
-        out["u_dsg"] = np.asfortranarray(uniq_rows[:, -nb:].astype(np.uint8))
+        sample_of = rows // M
+        out["u_dsg"] = np.asfortranarray(np.asarray(design, dtype=np.uint8).T[sample_of])
     else:
         out["u_dsg"] = None
     return out

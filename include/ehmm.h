@@ -138,6 +138,16 @@ int ehmm_glm_nb(ehmm_session *s, int column, const double *par, int P, double *v
 /* glmMixNB / derivMixNB, R/base-optim.R:187-255, over all B+2 tables. par = (b, db, l, dl). */
 int ehmm_glm_mix_nb(ehmm_session *s, const double *par, double minZero, double *value, double *grad);
 
+/* ---- launch accounting and per-kernel timing --------------------------------------------- */
+/* Number of distinct kernels the library tracks and their names (index = kernel id). */
+int ehmm_profile_kernels(void);
+const char *ehmm_profile_name(int kernel_id);
+/* enable != 0: reset the counters and bracket every launch with CUDA events on the session stream
+ * (for the bench's roofline figures); enable == 0: stop timing, keep counting launches. */
+int ehmm_profile(ehmm_session *s, int enable);
+/* launches[id] = launches since the last reset; ms[id] = summed event time (0 unless enabled). */
+int ehmm_profile_read(ehmm_session *s, int64_t *launches, double *ms);
+
 /* ---- dataset access ------------------------------------------------------------------ */
 /* name in {logLikelihood, logFP, logBP, logProb1, logProb2, mixtureProb, viterbi}. */
 int ehmm_dataset_dims(ehmm_session *s, const char *name, int64_t *rows, int64_t *cols);
