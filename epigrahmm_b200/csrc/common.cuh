@@ -91,7 +91,7 @@ struct ehmm_session {
     int64_t Mtot = 0;   // bins in the global chain
     cudaStream_t stream = nullptr;
     cudaStream_t stream2 = nullptr;  // side stream (uniform generation)
-    cudaEvent_t ev = nullptr;
+    cudaEvent_t ev = nullptr, ev2 = nullptr;
 
     // ---- data (dt) ----
     int N = 0;
@@ -126,7 +126,10 @@ struct ehmm_session {
     // ---- rejection control ----
     uint32_t rng_state[625] = {624};
     bool rng_set = false;
-    ehmm::DevBuf rc_w, rc_flag, rc_scan, rc_buckets, rc_unif, rc_tmp, mt_raw;
+    ehmm::DevBuf rc_w, rc_flag, rc_scan, rc_buckets, rc_unif, rc_tmp, mt_raw, mt_raw2, mt_windows;
+    int64_t mtj_valid = 0;       // sub-stream windows valid for the state in mt_raw
+    bool mtj_pending = false;    // ... being computed on stream2 (event ev)
+    bool rng_dev_valid = false;  // mt_raw holds rng_state
     int rc_columns = 0;
     int rc_N = 0;
 
@@ -203,6 +206,9 @@ int rc_table_rows(ehmm_session *s, int column, int64_t *rows);
 int rc_table_fetch(ehmm_session *s, int column, double *sums, double *ids);
 int rc_reweight(int device, double *x, int64_t n, double p, const double *uniforms, int64_t n_uniforms, int64_t *consumed);
 int rc_aggregate(int device, const double *x, int64_t n, const int32_t *f, int64_t G, double *buckets);
+// mtjump.cu
+int mt_generate(ehmm_session *s, int64_t n, uint32_t *out);
+int mt_prefetch(ehmm_session *s, int64_t max_draws);
 // glm.cu
 int glm_nb(ehmm_session *s, int column, const double *par, int P, double *value, double *grad);
 int glm_mix_nb(ehmm_session *s, const double *par, double minZero, double *value, double *grad);

@@ -1,0 +1,220 @@
+// mtjump.cu -- R's Mersenne-Twister stream generated in parallel on the device.
+//
+// rbinom() in the reference consumes unif_rand() draws one by one (src/rbinomVectorized.cpp:17);
+// at 15 M bins that is ~1.5e7 draws per EM iteration and a single sequential MT19937 is the
+// slowest step of the iteration.  MT19937 is GF(2)-linear, so sub-stream s (words
+// [1 + s*J, 1 + (s+1)*J) of the stream, J = 2^18) can start from a window obtained by jumping
+// ahead: w[m + J*2^k] = XOR_{i : c_i = 1} w[m + i] with c = x^(J*2^k) mod phi (mtpoly.h).
+//   mt_jump_kernel     : round k doubles the number of known windows (window 2^k + c from window c)
+//   mt_generate_kernel : one CTA per sub-stream runs the recurrence (227-wide) and writes tempered
+//                        words; the CTA that reaches the end also writes R's next .Random.seed
+// The windows depend only on the RNG state, not on the data, so they are prepared on the side
+// stream while the E-step runs.
+#include "common.cuh"
+#include "mtpoly.h"
+#include <map>
+#include <mutex>
+
+namespace ehmm {
+
+namespace {
+
+constexpr int LOG2J = 18;
+constexpr int64_t JW = (int64_t)1 << LOG2J;  // words per sub-stream
+constexpr int LEVELS = 14;                   // up to 2^14 sub-streams = 4.3e9 draws per call
+constexpr int MT_N = 624, MT_M = 397, MT_D = MT_N - MT_M;  // 227
+constexpr int EXPW = mtpoly::DEG + MT_N - 1;               // words a jump needs (20560)
+constexpr int JUMP_NT = 320;
+constexpr int GEN_NT = 256;
+
+__device__ __forceinline__ uint32_t twist(uint32_t a, uint32_t b) {
+    const uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
+    return (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+}
+__device__ __forceinline__ uint32_t temper(uint32_t y) {
+    y ^= (y >> 11);
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    y ^= (y >> 18);
+    return y;
+}
+
+// window 0 = absolute words [1, 625) of the stream whose array `state` holds words [0, 624)
+__global__ void mt_base_kernel(const uint32_t *__restrict__ state, uint32_t *__restrict__ S) {
+    for (int i = threadIdx.x; i < MT_N; i += blockDim.x)
+        S[i] = (i < MT_N - 1) ? state[1 + i + 1] : (state[1 + MT_M] ^ twist(state[1], state[2]));
+}
+
+// S[(base + c)] = jump(S[c]) by the polynomial `mask` (624 words of coefficient bits)
+__global__ void __launch_bounds__(JUMP_NT) mt_jump_kernel(const uint32_t *__restrict__ mask, uint32_t *__restrict__ S,
+                                                          int base) {
+    extern __shared__ uint32_t sm[];
+    uint32_t *buf = sm;             // EXPW (+ slack)
+    uint32_t *smask = sm + EXPW + 8;  // 624
+    const int tid = threadIdx.x;
+    const uint32_t *src = S + (size_t)blockIdx.x * MT_N;
+    uint32_t *dst = S + (size_t)(base + blockIdx.x) * MT_N;
+    for (int i = tid; i < MT_N; i += JUMP_NT) { buf[i] = src[i]; smask[i] = mask[i]; }
+    __syncthreads();
+    for (int b0 = MT_N; b0 < EXPW; b0 += MT_D) {
+        const int idx = b0 + tid;
+        if (tid < MT_D && idx < EXPW) buf[idx] = buf[idx - MT_D] ^ twist(buf[idx - MT_N], buf[idx - MT_N + 1]);
+        __syncthreads();
+    }
+    if (tid < MT_N / 2) {
+        uint32_t a0 = 0, a1 = 0;
+        const uint32_t *b0p = buf + tid, *b1p = buf + tid + MT_N / 2;
+        for (int q = 0; q < MT_N; q++) {
+            uint32_t mw = smask[q];
+            const int o = q * 32;
+            while (mw) {
+                const int b = __ffs(mw) - 1;
+                mw &= mw - 1;
+                a0 ^= b0p[o + b];
+                a1 ^= b1p[o + b];
+            }
+        }
+        dst[tid] = a0;
+        dst[tid + MT_N / 2] = a1;
+    }
+}
+
+// CTA s generates the absolute words of sub-stream s that fall into [pos, pos + n) as tempered
+// 32-bit words (out[a - pos]) and the raw words of R's next state array.
+__global__ void __launch_bounds__(GEN_NT)
+    mt_generate_kernel(const uint32_t *__restrict__ state, const uint32_t *__restrict__ S, int64_t n,
+                       uint32_t *__restrict__ out, uint32_t *__restrict__ state_out) {
+    __shared__ uint32_t buf[2][MT_N];
+    const int tid = threadIdx.x;
+    const int s = blockIdx.x;
+    const int64_t pos = state[0];
+    const int64_t E = pos + n;                    // exclusive end (absolute)
+    const int64_t bf = (E - 1) / MT_N;            // R's array will hold absolute [624*bf, 624*bf + 624)
+    const int64_t st_lo = bf * MT_N, st_hi = st_lo + MT_N;
+    const int64_t a0 = (s == 0) ? 0 : 1 + (int64_t)s * JW;
+    const int64_t lo = (s == 0) ? pos : a0;
+    const int64_t nxt = 1 + (int64_t)(s + 1) * JW;
+    const int64_t hi = min(E, nxt);
+    const bool last = (hi == E);
+    const int64_t gen_end = last ? max(hi, st_hi) : hi;
+    const uint32_t *src = (s == 0) ? state + 1 : S + (size_t)s * MT_N;
+    for (int i = tid; i < MT_N; i += GEN_NT) buf[0][i] = src[i];
+    __syncthreads();
+    int cur = 0;
+    for (int64_t cb = a0;; cb += MT_N) {
+        const uint32_t *bc = buf[cur];
+        for (int kk = tid; kk < MT_N; kk += GEN_NT) {
+            const int64_t a = cb + kk;
+            const uint32_t v = bc[kk];
+            if (a >= lo && a < hi) out[a - pos] = temper(v);
+            if (a >= st_lo && a < st_hi && a < gen_end) state_out[1 + (a - st_lo)] = v;
+        }
+        if (cb + MT_N >= gen_end) break;
+        uint32_t *nw = buf[cur ^ 1];
+        for (int kk = tid; kk < MT_D; kk += GEN_NT) nw[kk] = bc[kk + MT_M] ^ twist(bc[kk], bc[kk + 1]);
+        __syncthreads();
+        for (int kk = MT_D + tid; kk < 2 * MT_D; kk += GEN_NT) nw[kk] = nw[kk - MT_D] ^ twist(bc[kk], bc[kk + 1]);
+        __syncthreads();
+        for (int kk = 2 * MT_D + tid; kk < MT_N; kk += GEN_NT)
+            nw[kk] = nw[kk - MT_D] ^ ((kk == MT_N - 1) ? twist(bc[kk], nw[0]) : twist(bc[kk], bc[kk + 1]));
+        __syncthreads();
+        cur ^= 1;
+    }
+    if (last && tid == 0) state_out[0] = (uint32_t)(E - st_lo);
+}
+
+// jump polynomials: computed once per process on the host, uploaded once per device
+std::mutex g_mu;
+std::vector<uint32_t> g_masks;  // LEVELS * 624 words
+std::map<int, uint32_t *> g_dev_masks;
+
+int device_masks(int device, const uint32_t **out) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_masks.empty()) {
+        std::vector<mtpoly::Poly> polys = mtpoly::jump_polys(LOG2J, LEVELS);
+        EHMM_REQUIRE((int)polys.size() == LEVELS, EHMM_ERR_RNG, "MT19937 characteristic polynomial has the wrong degree");
+        g_masks.assign((size_t)LEVELS * MT_N, 0u);
+        for (int k = 0; k < LEVELS; k++)
+            for (int w = 0; w < mtpoly::NW; w++) {
+                g_masks[(size_t)k * MT_N + 2 * w] = (uint32_t)(polys[k][w] & 0xffffffffull);
+                g_masks[(size_t)k * MT_N + 2 * w + 1] = (uint32_t)(polys[k][w] >> 32);
+            }
+    }
+    auto it = g_dev_masks.find(device);
+    if (it == g_dev_masks.end()) {
+        uint32_t *d = nullptr;
+        EHMM_CK(cudaMalloc(&d, sizeof(uint32_t) * g_masks.size()));
+        EHMM_CK(cudaMemcpy(d, g_masks.data(), sizeof(uint32_t) * g_masks.size(), cudaMemcpyHostToDevice));
+        size_t smem = sizeof(uint32_t) * (EXPW + 8 + MT_N);
+        EHMM_CK(cudaFuncSetAttribute(mt_jump_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        it = g_dev_masks.emplace(device, d).first;
+    }
+    *out = it->second;
+    return EHMM_OK;
+}
+
+int64_t substreams_for(int64_t pos, int64_t n) {  // CTAs mt_generate_kernel needs
+    if (n <= 0) return 0;
+    const int64_t E = pos + n;
+    return (E - 1 - 1) / JW + 1;  // sub-stream s >= 1 is active iff 1 + s*J < E
+}
+
+}  // namespace
+
+// Prepare the windows of sub-streams 1..P-1 for the stream whose state is in s->mt_raw (device).
+int mt_prepare(ehmm_session *s, cudaStream_t st, int64_t max_draws) {
+    const int64_t P = substreams_for(624, max_draws);
+    if (P <= 1) { s->mtj_valid = 1; return EHMM_OK; }
+    EHMM_REQUIRE(P <= ((int64_t)1 << LEVELS), EHMM_ERR_RNG, "too many uniforms in one call (%lld)", (long long)max_draws);
+    const uint32_t *masks = nullptr;
+    EHMM_TRY(device_masks(s->device, &masks));
+    EHMM_TRY(s->mt_windows.reserve(sizeof(uint32_t) * MT_N * (size_t)P));
+    uint32_t *S = s->mt_windows.as<uint32_t>();
+    mt_base_kernel<<<1, 256, 0, st>>>(s->mt_raw.as<uint32_t>(), S);
+    EHMM_CK(cudaGetLastError());
+    s->launches[KID_MT]++;
+    const size_t smem = sizeof(uint32_t) * (EXPW + 8 + MT_N);
+    for (int k = 0; ((int64_t)1 << k) < P; k++) {
+        const int64_t base = (int64_t)1 << k;
+        const int64_t cnt = (P - base < base) ? (P - base) : base;
+        mt_jump_kernel<<<(unsigned)cnt, JUMP_NT, smem, st>>>(masks + (size_t)k * MT_N, S, (int)base);
+        EHMM_CK(cudaGetLastError());
+        s->launches[KID_MT]++;
+    }
+    s->mtj_valid = P;
+    return EHMM_OK;
+}
+
+// Generate n tempered words of the stream into `out` (device) and advance s->mt_raw.
+int mt_generate(ehmm_session *s, int64_t n, uint32_t *out) {
+    if (n <= 0) return EHMM_OK;
+    const int64_t pos = s->rng_state[0];
+    const int64_t P = substreams_for(pos, n);
+    EHMM_TRY(s->mt_raw2.reserve(sizeof(uint32_t) * 625));
+    if (s->mtj_pending) {  // windows being prepared on the side stream
+        EHMM_CK(cudaStreamWaitEvent(s->stream, s->ev, 0));
+        s->mtj_pending = false;
+    }
+    if (P > 1 && s->mtj_valid < P) EHMM_TRY(mt_prepare(s, s->stream, n + 624));
+    {
+        PROF(s, KID_MT), mt_generate_kernel<<<(unsigned)P, GEN_NT, 0, s->stream>>>(
+            s->mt_raw.as<uint32_t>(), s->mt_windows.as<uint32_t>(), n, out, s->mt_raw2.as<uint32_t>());
+    }
+    EHMM_CK(cudaGetLastError());
+    std::swap(s->mt_raw, s->mt_raw2);
+    s->mtj_valid = 0;
+    return EHMM_OK;
+}
+
+// After a call: start preparing the windows for the next one on the side stream.
+int mt_prefetch(ehmm_session *s, int64_t max_draws) {
+    if (substreams_for(624, max_draws) <= 1) return EHMM_OK;
+    EHMM_CK(cudaEventRecord(s->ev2, s->stream));
+    EHMM_CK(cudaStreamWaitEvent(s->stream2, s->ev2, 0));
+    EHMM_TRY(mt_prepare(s, s->stream2, max_draws));
+    EHMM_CK(cudaEventRecord(s->ev, s->stream2));
+    s->mtj_pending = true;
+    return EHMM_OK;
+}
+
+}  // namespace ehmm

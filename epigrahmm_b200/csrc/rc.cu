@@ -21,20 +21,8 @@ namespace {
 constexpr int RC_NT = 256;
 constexpr int RC_STRIPS = 8;
 constexpr int RC_TB = RC_NT * RC_STRIPS;  // bins per block
-constexpr int MT_N = 624, MT_M = 397;
 
 // ---- R's unif_rand() (Mersenne-Twister) ------------------------------------------------------
-__device__ __forceinline__ uint32_t mt_twist(uint32_t a, uint32_t b) {
-    uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
-    return (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
-}
-__device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
-    y ^= (y >> 11);
-    y ^= (y << 7) & 0x9d2c5680u;
-    y ^= (y << 15) & 0xefc60000u;
-    y ^= (y >> 18);
-    return y;
-}
 // MT_genrand() * 2^-32 followed by fixup() into (0,1)
 __device__ __forceinline__ double mt_to_unif(uint32_t tempered) {
     const double i2_32m1 = 2.328306437080797e-10;
@@ -42,41 +30,6 @@ __device__ __forceinline__ double mt_to_unif(uint32_t tempered) {
     if (x <= 0.0) return 0.5 * i2_32m1;
     if ((1.0 - x) <= 0.0) return 1.0 - 0.5 * i2_32m1;
     return x;
-}
-
-// Sequential-in-blocks MT19937: one CTA advances the 624-word state; within a block of 624 the
-// recurrence is 227-wide parallel (three phases).  Writes n tempered words and the final state.
-__global__ void __launch_bounds__(256) mt_generate_kernel(uint32_t *__restrict__ state, int64_t n,
-                                                          uint32_t *__restrict__ out) {
-    __shared__ uint32_t buf[2][MT_N];
-    const int tid = threadIdx.x;
-    for (int i = tid; i < MT_N; i += 256) buf[0][i] = state[1 + i];
-    int pos = (int)state[0];
-    __syncthreads();
-    int cur = 0;
-    int64_t produced = 0;
-    while (true) {
-        int64_t cnt = min((int64_t)(MT_N - pos), n - produced);
-        for (int kk = tid; kk < cnt; kk += 256) out[produced + kk] = mt_temper(buf[cur][pos + kk]);
-        produced += cnt;
-        pos += (int)cnt;
-        if (produced >= n) break;
-        const uint32_t *od = buf[cur];
-        uint32_t *nw = buf[cur ^ 1];
-        for (int kk = tid; kk < MT_N - MT_M; kk += 256) nw[kk] = od[kk + MT_M] ^ mt_twist(od[kk], od[kk + 1]);
-        __syncthreads();
-        for (int kk = MT_N - MT_M + tid; kk < 2 * (MT_N - MT_M); kk += 256)
-            nw[kk] = nw[kk - (MT_N - MT_M)] ^ mt_twist(od[kk], od[kk + 1]);
-        __syncthreads();
-        for (int kk = 2 * (MT_N - MT_M) + tid; kk < MT_N; kk += 256)
-            nw[kk] = nw[kk - (MT_N - MT_M)] ^ ((kk == MT_N - 1) ? mt_twist(od[kk], nw[0]) : mt_twist(od[kk], od[kk + 1]));
-        __syncthreads();
-        cur ^= 1;
-        pos = 0;
-    }
-    __syncthreads();
-    for (int i = tid; i < MT_N; i += 256) state[1 + i] = buf[cur][i];
-    if (tid == 0) state[0] = (uint32_t)pos;
 }
 
 // ---- weights -----------------------------------------------------------------------------------
@@ -307,9 +260,12 @@ int run_rc(ehmm_session *s, const RCSrc &S, double p, int nrep, const double *un
         EHMM_TRY(s->rc_unif.reserve(sizeof(uint32_t) * (size_t)(total > 0 ? total : 1)));
         EHMM_TRY(s->mt_raw.reserve(sizeof(uint32_t) * 625));
         if (total > 0) {
-            EHMM_CK(cudaMemcpyAsync(s->mt_raw.p, s->rng_state, sizeof(uint32_t) * 625, cudaMemcpyHostToDevice, s->stream));
-            PROF(s, KID_MT), mt_generate_kernel<<<1, 256, 0, s->stream>>>(s->mt_raw.as<uint32_t>(), total, s->rc_unif.as<uint32_t>());
-            EHMM_CK(cudaGetLastError());
+            if (!s->rng_dev_valid) {
+                EHMM_CK(cudaMemcpyAsync(s->mt_raw.p, s->rng_state, sizeof(uint32_t) * 625, cudaMemcpyHostToDevice, s->stream));
+                s->rng_dev_valid = true;
+                s->mtj_valid = 0;
+            }
+            EHMM_TRY(mt_generate(s, total, s->rc_unif.as<uint32_t>()));
             EHMM_CK(cudaMemcpyAsync(s->rng_state, s->mt_raw.p, sizeof(uint32_t) * 625, cudaMemcpyDeviceToHost, s->stream));
         }
         PROF(s, KID_RC_APPLY), rc_apply_kernel<uint32_t><<<grid, RC_NT, 0, s->stream>>>(S, p, nblk, s->rc_scan.as<int64_t>(),
@@ -317,6 +273,8 @@ int run_rc(ehmm_session *s, const RCSrc &S, double p, int nrep, const double *un
                                                                  s->rc_buckets.as<double>(), nullptr);
     }
     EHMM_CK(cudaGetLastError());
+    // the next call's sub-stream windows depend only on the RNG state: prepare them on the side stream
+    if (!uniforms && total > 0) EHMM_TRY(mt_prefetch(s, (int64_t)S.columns * s->M));
     EHMM_CK(cudaStreamSynchronize(s->stream));
     s->rc_columns = S.columns;
     s->rc_N = nrep;

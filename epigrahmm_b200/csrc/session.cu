@@ -145,6 +145,7 @@ int ehmm_session_open(const char *key, int64_t M, int K, int device, ehmm_sessio
     EHMM_CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     EHMM_CK(cudaStreamCreateWithFlags(&s->stream2, cudaStreamNonBlocking));
     EHMM_CK(cudaEventCreateWithFlags(&s->ev, cudaEventDisableTiming));
+    EHMM_CK(cudaEventCreateWithFlags(&s->ev2, cudaEventDisableTiming));
     EHMM_CK(cudaMallocHost(&s->h_pinned, sizeof(double) * 256));
     {
         std::lock_guard<std::mutex> lk(g_mu);
@@ -183,11 +184,12 @@ int ehmm_session_close(ehmm_session *s) {
     DevBuf *bufs[] = {&s->counts_own, &s->offsets_own, &s->controls_own, &s->group, &s->u_chip, &s->u_off, &s->u_ctrl,
                       &s->u_dsg, &s->logf, &s->logFP, &s->logBP, &s->logProb1, &s->logProb2, &s->eta, &s->viterbi,
                       &s->tileops, &s->carries, &s->tilestats, &s->fbscal, &s->rc_w, &s->rc_flag, &s->rc_scan,
-                      &s->rc_buckets, &s->rc_unif, &s->rc_tmp, &s->mt_raw, &s->lgtab, &s->glm_part, &s->misc};
+                      &s->rc_buckets, &s->rc_unif, &s->rc_tmp, &s->mt_raw, &s->mt_raw2, &s->mt_windows, &s->lgtab, &s->glm_part, &s->misc};
     for (DevBuf *b : bufs) b->release();
     for (cudaEvent_t e : s->prof_pool) cudaEventDestroy(e);
     if (s->h_pinned) cudaFreeHost(s->h_pinned);
     if (s->ev) cudaEventDestroy(s->ev);
+    if (s->ev2) cudaEventDestroy(s->ev2);
     if (s->stream) cudaStreamDestroy(s->stream);
     if (s->stream2) cudaStreamDestroy(s->stream2);
     delete s;
@@ -478,6 +480,7 @@ int ehmm_rng_set_state(ehmm_session *s, const uint32_t *state625) {
     EHMM_REQUIRE(state625[0] <= 624, EHMM_ERR_ARG, "mti = %u out of range", state625[0]);
     memcpy(s->rng_state, state625, sizeof(uint32_t) * 625);
     s->rng_set = true;
+    s->rng_dev_valid = false;
     return EHMM_OK;
 }
 

@@ -199,3 +199,29 @@ def test_viterbi_end_to_end_small(ehmm, oracle):
         s.expstep(th["pi"], th["gamma"], logf)
         got = s.viterbi(th["pi"], th["gamma"])
     assert np.mean(got != ref) <= 1e-3
+
+
+def test_rc_device_rng_parallel_substreams(ehmm, oracle):
+    """more draws than one sub-stream holds (2^18 words): the jump-ahead windows must continue R's
+    stream exactly, across calls, from any position inside a 624-word block"""
+    M = 700001
+    rng_np = np.random.default_rng(8)
+    lp1 = np.log(np.column_stack([rng_np.random(M) * 0.04 + 1e-6, np.ones(M)]))
+    lp1[:, 1] = np.log1p(-np.exp(lp1[:, 0]))
+    lp1[::5, 0] = -np.inf                                      # zero posterior: no draw
+    f = rng_np.integers(1, 5000, (M, 2)).astype(np.int32)
+    h = {"logProb1": np.asfortranarray(lp1)}
+    rng = oracle.RNG.set_seed(2024)
+    rng.runif(333)
+    with ehmm.Session("t_rc_par", M, 2) as s:
+        s.set_data(np.zeros((M, 2), dtype=np.int32), np.zeros((M, 2)))
+        s.set_groups(f, np.zeros(4999), np.zeros(4999))
+        s.store("logProb1", lp1)
+        s.rng_set_state(rng.state())
+        for p in (0.05, 0.9, 0.05):
+            ref, n_ref = oracle.consensusRejectionControlled(h, f, p, rng=rng, dense=True)
+            n = s.rc_consensus(p)
+            assert n == n_ref and n_ref > 2 ** 18
+            assert np.array_equal(s.rng_get_state(), rng.state())
+            for k in range(2):
+                assert np.allclose(s.rc_buckets(k), ref[k], rtol=1e-12, atol=0)
