@@ -66,13 +66,13 @@ enum : unsigned {
 
 // kernel ids for the launch counters / optional CUDA-event profile (ehmm_profile*)
 enum KernelId : int {
-    KID_EMIS_TAB, KID_EMIS_CONSENSUS, KID_EMIS_DIFF, KID_EMIS_INNER, KID_INNER_MSTEP,
+    KID_EMIS_TAB, KID_EMIS_GATHER, KID_EMIS_CONSENSUS, KID_EMIS_DIFF, KID_EMIS_INNER, KID_INNER_MSTEP,
     KID_FB_REDUCE, KID_FB_CARRY, KID_FB_APPLY, KID_FB_FIX, KID_FB_STATS,
     KID_RC_COUNT, KID_RC_SCAN, KID_MT, KID_RC_APPLY, KID_GLM, KID_GLM_FINAL,
     KID_VIT_FWD, KID_VIT_BWD, KID_MISC, KID_COUNT
 };
 static const char *const kKernelNames[KID_COUNT] = {
-    "lgtab", "emis_consensus", "emis_diff_hmm", "emis_inner", "inner_mstep",
+    "emis_tables", "emis_gather", "emis_consensus", "emis_diff_hmm", "emis_inner", "inner_mstep",
     "fb_reduce", "fb_carry", "fb_apply", "fb_boundary_fix", "fb_stats",
     "rc_count", "rc_scan", "mt_generate", "rc_apply", "glm", "glm_final",
     "viterbi_forward", "viterbi_backtrace", "misc"};
@@ -134,7 +134,8 @@ struct ehmm_session {
     int rc_N = 0;
 
     // ---- emission / GLM scratch ----
-    ehmm::DevBuf lgtab, glm_part, misc;
+    ehmm::DevBuf lgtab, glm_part, misc, gtab;
+    bool groups_consistent = false;  // dtUnique[group] reproduces (counts, offsets[, controls]) cell by cell
     int64_t count_max = -1;
     double *h_pinned = nullptr;  // small pinned staging buffer (256 doubles)
 

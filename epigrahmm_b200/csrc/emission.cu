@@ -87,7 +87,67 @@ __global__ void __launch_bounds__(EM_NT)
     }
 }
 
+// ---- dictionary-encoded path ------------------------------------------------------------------
+// dt$Group maps every (bin, sample) cell to a row of dtUnique (distinct (count, offset[, control])
+// tuples; offsets are rounded to 3 decimals upstream, so G << M*N).  The densities are evaluated
+// once per group into a table and each bin gathers them: 4N B/bin of ids instead of 12N B/bin of
+// counts+offsets, and no transcendental work in the M*N stream.  Values are bit-identical to the
+// per-cell kernels (same function of the same inputs, same summation order).
+template <bool CTRL, bool PLUS_MZ>
+__global__ void __launch_bounds__(EM_NT)
+    group_table_consensus_kernel(int64_t G, const double *__restrict__ uy, const double *__restrict__ uoff,
+                                 const double *__restrict__ uctrl, const __grid_constant__ EmisParams P,
+                                 const double *__restrict__ tab, double2 *__restrict__ E) {
+    const int64_t g = (int64_t)blockIdx.x * EM_NT + threadIdx.x;
+    if (g > G) return;
+    if (g == 0) { E[0] = make_double2(0.0, 0.0); return; }
+    const int x = (int)uy[g];
+    const double o = uoff[g];
+    double e0, e1;
+    if (CTRL) {
+        const double cv = uctrl[g];
+        e0 = (P.b0[0] + P.b1[0] * cv) + o;
+        e1 = (P.b0[1] + P.b1[1] * cv) + o;
+    } else {
+        e0 = P.b0[0] + o;
+        e1 = P.b0[1] + o;
+    }
+    double l0 = nb_logpmf(x, e0, 0, P, tab), l1 = nb_logpmf(x, e1, 1, P, tab);
+    if (PLUS_MZ) { l0 = plus_min_zero(l0, P); l1 = plus_min_zero(l1, P); }
+    E[g] = make_double2(l0, l1);
+}
+
+__global__ void __launch_bounds__(EM_NT)
+    gather_consensus_kernel(int64_t M, int N, const int32_t *__restrict__ group, const double2 *__restrict__ E,
+                            double *__restrict__ LL) {
+    for (int64_t j = (int64_t)blockIdx.x * EM_NT + threadIdx.x; j < M; j += (int64_t)gridDim.x * EM_NT) {
+        double a0 = 0.0, a1 = 0.0;
+        for (int i = 0; i < N; i++) {
+            const double2 e = __ldg(E + __ldg(group + j + (int64_t)i * M));
+            a0 += e.x;
+            a1 += e.y;
+        }
+        LL[j] = a0;
+        LL[j + M] = a1;
+    }
+}
+
+// differential model: E[g] = (l0, l1) = log NB under D = 0 / D = 1
+__global__ void __launch_bounds__(EM_NT)
+    group_table_diff_kernel(int64_t G, const double *__restrict__ uy, const double *__restrict__ uoff,
+                            const __grid_constant__ EmisParams P, const double *__restrict__ tab,
+                            double2 *__restrict__ E) {
+    const int64_t g = (int64_t)blockIdx.x * EM_NT + threadIdx.x;
+    if (g > G) return;
+    if (g == 0) { E[0] = make_double2(0.0, 0.0); return; }
+    const int x = (int)uy[g];
+    const double o = uoff[g];
+    E[g] = make_double2(nb_logpmf(x, P.b0[0] + o, 0, P, tab), nb_logpmf(x, P.b0[1] + o, 1, P, tab));
+}
+
 // per-bin pieces of the differential model: LL0 = sum_i l0_i, LL2 = sum_i l1_i, d_i = l1_i - l0_i
+// (y == nullptr selects the dictionary-encoded source: `off` then points at the group table and
+// `tab` at the int32 group ids)
 template <int NMAX>
 __device__ __forceinline__ void diff_cells(int64_t j, int64_t M, int N, const int32_t *__restrict__ y,
                                            const double *__restrict__ off, const EmisParams &P,
@@ -98,10 +158,18 @@ __device__ __forceinline__ void diff_cells(int64_t j, int64_t M, int N, const in
     for (int i = 0; i < NMAX; i++) {
         if (i < N) {
             const int64_t c = j + (int64_t)i * M;
-            const int x = __ldg(y + c);
-            const double o = __ldg(off + c);
-            const double l0 = nb_logpmf(x, P.b0[0] + o, 0, P, tab);
-            const double l1 = nb_logpmf(x, P.b0[1] + o, 1, P, tab);
+            double l0, l1;
+            if (y == nullptr) {
+                const double2 e = __ldg(reinterpret_cast<const double2 *>(off) +
+                                        __ldg(reinterpret_cast<const int32_t *>(tab) + c));
+                l0 = e.x;
+                l1 = e.y;
+            } else {
+                const int x = __ldg(y + c);
+                const double o = __ldg(off + c);
+                l0 = nb_logpmf(x, P.b0[0] + o, 0, P, tab);
+                l1 = nb_logpmf(x, P.b0[1] + o, 1, P, tab);
+            }
             LL0 += l0;
             LL2 += l1;
             d[i] = l1 - l0;
@@ -235,6 +303,10 @@ int prepare_tab(ehmm_session *s, EmisParams &P, int nd, double minZero) {
     return EHMM_OK;
 }
 
+bool use_groups(const ehmm_session *s, int K) {
+    return s->groups_consistent && s->G > 0 && (size_t)(s->G + 1) * 16 <= ((size_t)64 << 20) && K <= 3;
+}
+
 int fill_mix(ehmm_session *s, MixParams &X, const double *delta) {
     EHMM_REQUIRE(s->have_design && s->B > 0, EHMM_ERR_STATE, "ehmm_set_design has not been called");
     EHMM_REQUIRE(s->N <= 64, EHMM_ERR_ARG, "differential model supports at most 64 samples (N=%d)", s->N);
@@ -246,6 +318,21 @@ int fill_mix(ehmm_session *s, MixParams &X, const double *delta) {
         X.mask[b] = m;
         X.ldelta[b] = log(delta[b]);
     }
+    return EHMM_OK;
+}
+
+// dictionary-encoded source for the differential kernels: evaluates the per-group (l0, l1) table
+// and redirects (y, off, tab) to (nullptr, table, group ids); leaves them untouched otherwise
+int diff_source(ehmm_session *s, const EmisParams &P, const int32_t *&y, const double *&off, const double *&tab) {
+    if (!use_groups(s, 3)) return EHMM_OK;
+    EHMM_TRY(s->gtab.reserve(sizeof(double2) * (size_t)(s->G + 1)));
+    const unsigned gb = (unsigned)((s->G + 1 + EM_NT - 1) / EM_NT);
+    PROF(s, KID_EMIS_TAB), group_table_diff_kernel<<<gb, EM_NT, 0, s->stream>>>(
+        s->G, s->u_chip.as<double>(), s->u_off.as<double>(), P, s->lgtab.as<double>(), s->gtab.as<double2>());
+    EHMM_CK(cudaGetLastError());
+    y = nullptr;
+    off = s->gtab.as<double>();
+    tab = reinterpret_cast<const double *>(s->group.as<int32_t>());
     return EHMM_OK;
 }
 
@@ -268,6 +355,24 @@ int emis_consensus(ehmm_session *s, const double *th1, const double *th2, int P_
     EHMM_TRY(prepare_tab(s, P, 2, minZero));
     EHMM_TRY(s->logf.reserve(sizeof(double) * s->M * 2));
     const int g = grid_for(s->M);
+    if (use_groups(s, 2)) {
+        EHMM_TRY(s->gtab.reserve(sizeof(double2) * (size_t)(s->G + 1)));
+        const unsigned gb = (unsigned)((s->G + 1 + EM_NT - 1) / EM_NT);
+        if (P_ == 3)
+            PROF(s, KID_EMIS_TAB), group_table_consensus_kernel<true, true><<<gb, EM_NT, 0, s->stream>>>(
+                s->G, s->u_chip.as<double>(), s->u_off.as<double>(), s->u_ctrl.as<double>(), P, s->lgtab.as<double>(),
+                s->gtab.as<double2>());
+        else
+            PROF(s, KID_EMIS_TAB), group_table_consensus_kernel<false, true><<<gb, EM_NT, 0, s->stream>>>(
+                s->G, s->u_chip.as<double>(), s->u_off.as<double>(), nullptr, P, s->lgtab.as<double>(),
+                s->gtab.as<double2>());
+        EHMM_CK(cudaGetLastError());
+        PROF(s, KID_EMIS_GATHER), gather_consensus_kernel<<<g, EM_NT, 0, s->stream>>>(
+            s->M, s->N, s->group.as<int32_t>(), s->gtab.as<double2>(), s->logf.as<double>());
+        EHMM_CK(cudaGetLastError());
+        s->valid |= DS_LOGF;
+        return EHMM_OK;
+    }
     if (P_ == 3)
         PROF(s, KID_EMIS_CONSENSUS), emis_consensus_kernel<true, true><<<g, EM_NT, 0, s->stream>>>(s->M, s->N, s->d_counts, s->d_offsets,
                                                                      s->d_controls, P, s->lgtab.as<double>(),
@@ -289,6 +394,18 @@ int emis_init(ehmm_session *s, const double *psi1, const double *psi2) {
     fill_density(P, 1, psi2[0], 0.0, psi2[1]);
     EHMM_TRY(prepare_tab(s, P, 2, 2.2250738585072014e-308));
     EHMM_TRY(s->logf.reserve(sizeof(double) * s->M * 2));
+    if (use_groups(s, 2)) {
+        EHMM_TRY(s->gtab.reserve(sizeof(double2) * (size_t)(s->G + 1)));
+        const unsigned gb = (unsigned)((s->G + 1 + EM_NT - 1) / EM_NT);
+        PROF(s, KID_EMIS_TAB), group_table_consensus_kernel<false, false><<<gb, EM_NT, 0, s->stream>>>(
+            s->G, s->u_chip.as<double>(), s->u_off.as<double>(), nullptr, P, s->lgtab.as<double>(), s->gtab.as<double2>());
+        EHMM_CK(cudaGetLastError());
+        PROF(s, KID_EMIS_GATHER), gather_consensus_kernel<<<grid_for(s->M), EM_NT, 0, s->stream>>>(
+            s->M, 1, s->group.as<int32_t>(), s->gtab.as<double2>(), s->logf.as<double>());
+        EHMM_CK(cudaGetLastError());
+        s->valid |= DS_LOGF;
+        return EHMM_OK;
+    }
     PROF(s, KID_EMIS_CONSENSUS), emis_consensus_kernel<false, false><<<grid_for(s->M), EM_NT, 0, s->stream>>>(
         s->M, 1, s->d_counts, s->d_offsets, nullptr, P, s->lgtab.as<double>(), s->logf.as<double>());
     EHMM_CK(cudaGetLastError());
@@ -306,12 +423,15 @@ int emis_differential_hmm(ehmm_session *s, const double *delta, const double *ps
     EHMM_TRY(prepare_tab(s, P, 2, minZero));
     EHMM_TRY(s->logf.reserve(sizeof(double) * s->M * 3));
     const int g = grid_for(s->M);
+    const int32_t *src_y = s->d_counts;
+    const double *src_off = s->d_offsets, *src_tab = s->lgtab.as<double>();
+    EHMM_TRY(diff_source(s, P, src_y, src_off, src_tab));
     if (s->N <= 16)
-        PROF(s, KID_EMIS_DIFF), emis_diff_hmm_kernel<16><<<g, EM_NT, 0, s->stream>>>(s->M, s->N, s->d_counts, s->d_offsets, P, X,
-                                                            s->lgtab.as<double>(), s->logf.as<double>());
+        PROF(s, KID_EMIS_DIFF), emis_diff_hmm_kernel<16><<<g, EM_NT, 0, s->stream>>>(s->M, s->N, src_y, src_off, P, X,
+                                                            src_tab, s->logf.as<double>());
     else
-        PROF(s, KID_EMIS_DIFF), emis_diff_hmm_kernel<64><<<g, EM_NT, 0, s->stream>>>(s->M, s->N, s->d_counts, s->d_offsets, P, X,
-                                                            s->lgtab.as<double>(), s->logf.as<double>());
+        PROF(s, KID_EMIS_DIFF), emis_diff_hmm_kernel<64><<<g, EM_NT, 0, s->stream>>>(s->M, s->N, src_y, src_off, P, X,
+                                                            src_tab, s->logf.as<double>());
     EHMM_CK(cudaGetLastError());
     s->valid |= DS_LOGF;
     return EHMM_OK;
@@ -326,12 +446,15 @@ int emis_inner_estep(ehmm_session *s, const double *delta, const double *psi, do
     EHMM_TRY(prepare_tab(s, P, 2, minZero));
     EHMM_TRY(s->eta.reserve(sizeof(double) * s->M * s->B));
     const int g = grid_for(s->M);
+    const int32_t *src_y = s->d_counts;
+    const double *src_off = s->d_offsets, *src_tab = s->lgtab.as<double>();
+    EHMM_TRY(diff_source(s, P, src_y, src_off, src_tab));
     if (s->N <= 16)
-        PROF(s, KID_EMIS_INNER), emis_inner_kernel<16><<<g, EM_NT, 0, s->stream>>>(s->M, s->N, s->d_counts, s->d_offsets, P, X,
-                                                         s->lgtab.as<double>(), s->eta.as<double>());
+        PROF(s, KID_EMIS_INNER), emis_inner_kernel<16><<<g, EM_NT, 0, s->stream>>>(s->M, s->N, src_y, src_off, P, X,
+                                                         src_tab, s->eta.as<double>());
     else
-        PROF(s, KID_EMIS_INNER), emis_inner_kernel<64><<<g, EM_NT, 0, s->stream>>>(s->M, s->N, s->d_counts, s->d_offsets, P, X,
-                                                         s->lgtab.as<double>(), s->eta.as<double>());
+        PROF(s, KID_EMIS_INNER), emis_inner_kernel<64><<<g, EM_NT, 0, s->stream>>>(s->M, s->N, src_y, src_off, P, X,
+                                                         src_tab, s->eta.as<double>());
     EHMM_CK(cudaGetLastError());
     s->valid |= DS_ETA;
     return EHMM_OK;

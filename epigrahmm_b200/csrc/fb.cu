@@ -46,12 +46,41 @@ template <> struct FBCfg<2> { static constexpr int NT = 256, L = 5; };
 template <> struct FBCfg<3> { static constexpr int NT = 192, L = 5; };
 constexpr int CARRY_NT = 1024;
 
-// 2^-e for the binary exponent e of mx (mx normal, positive); e = 0 otherwise
-__device__ __forceinline__ double inv_pow2(double mx, int &e) {
-    int hi = __double2hiint(mx);
-    e = ((hi >> 20) & 0x7ff) - 1023;
-    if (!(mx >= 2.2250738585072014e-308) || e >= 1023) e = 0;
+// 2^-e for the binary exponent e encoded in the high word `hi` of a non-negative double
+// (normal numbers only; e = 0 for zero / subnormal / inf / nan)
+__device__ __forceinline__ double inv_pow2(int hi, int &e) {
+    e = (hi >> 20) - 1023;
+    if (hi < 0x00100000 || hi >= 0x7fe00000) e = 0;
     return __hiloint2double((1023 - e) << 20, 0);
+}
+
+// 1/x for normal positive x: hardware seed (2^-23) + two Newton steps (~1 ulp)
+__device__ __forceinline__ double rcp_fast(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);
+}
+
+// log(x) for positive normal x (the fdlibm e_log.c kernel, < 1 ulp), without the library
+// version's special-case paths; anything else falls back to log().
+__device__ __forceinline__ double log_pos(double x) {
+    int hi = __double2hiint(x);
+    const int lo = __double2loint(x);
+    if ((unsigned)(hi - 0x00100000) >= 0x7fe00000u) return log(x);
+    int e = (hi >> 20) - 1023;
+    hi = (hi & 0x000fffff) | 0x3ff00000;
+    if (hi > 0x3ff6a09e) { hi -= 0x00100000; e += 1; }  // mantissa above sqrt(2): halve it
+    const double f = __hiloint2double(hi, lo) - 1.0;
+    const double s = f * rcp_fast(2.0 + f);
+    const double z = s * s, w = z * z;
+    const double t1 = w * fma(w, fma(w, 1.531383769920937332e-01, 2.222219843214978396e-01), 3.999999999940941908e-01);
+    const double t2 = z * fma(w, fma(w, fma(w, 1.479819860511658591e-01, 1.818357216161805012e-01),
+                                     2.857142874366239149e-01), 6.666666666666735130e-01);
+    const double R = t2 + t1, hfsq = 0.5 * f * f, dk = (double)e;
+    return dk * 6.93147180369123816490e-01 - ((hfsq - (s * (hfsq + R) + dk * 1.90821492927058770002e-10)) - f);
 }
 
 template <int K> __device__ __forceinline__ void op_identity(Op<K> &X) {
@@ -63,9 +92,9 @@ template <int K> __device__ __forceinline__ void op_identity(Op<K> &X) {
 }
 
 template <int K> __device__ __forceinline__ void op_renorm(Op<K> &X) {
-    double mx = X.m[0];
+    int mx = __double2hiint(X.m[0]);  // entries are >= 0: the high words order them (to 2^-20)
 #pragma unroll
-    for (int i = 1; i < K * K; i++) mx = fmax(mx, X.m[i]);
+    for (int i = 1; i < K * K; i++) mx = max(mx, __double2hiint(X.m[i]));
     int e;
     double sc = inv_pow2(mx, e);
 #pragma unroll
@@ -74,9 +103,9 @@ template <int K> __device__ __forceinline__ void op_renorm(Op<K> &X) {
 }
 
 template <int K> __device__ __forceinline__ void vec_renorm(Vec<K> &x) {
-    double mx = x.v[0];
+    int mx = __double2hiint(x.v[0]);
 #pragma unroll
-    for (int i = 1; i < K; i++) mx = fmax(mx, x.v[i]);
+    for (int i = 1; i < K; i++) mx = max(mx, __double2hiint(x.v[i]));
     int e;
     double sc = inv_pow2(mx, e);
 #pragma unroll
@@ -512,8 +541,8 @@ __global__ void __launch_bounds__(NT)
         double Z = 0.0;
 #pragma unroll
         for (int k = 0; k < K; k++) {
-            lf[k] = (al[k] >= TINY_LIN) ? log(al[k]) : (log(a[k]) + f[k] + (scfp - scf));
-            lb[k] = log(be[k]);
+            lf[k] = (al[k] >= TINY_LIN) ? log_pos(al[k]) : (log(a[k]) + f[k] + (scfp - scf));
+            lb[k] = log_pos(be[k]);
             Z = fma(al[k], be[k], Z);
         }
         sX[(r & 1) * NT * K + tid * K + 0] = lf[0];
@@ -536,7 +565,7 @@ __global__ void __launch_bounds__(NT)
             for (int k = 0; k < K; k++) lfp[k] = log(fmax(alp[k], 4.9406564584124654e-324));
         }
         if (valid) {
-            const double lZ = log(Z), rZ = 1.0 / Z;
+            const double lZ = log_pos(Z), rZ = rcp_fast(Z);
             double lp1[K], p1[K];
 #pragma unroll
             for (int k = 0; k < K; k++) {
@@ -554,7 +583,7 @@ __global__ void __launch_bounds__(NT)
                 const double d = scfp - scf;
 #pragma unroll
                 for (int l = 0; l < K; l++) {
-                    const double ra = p1[l] / a[l];
+                    const double ra = p1[l] * rcp_fast(a[l]);
 #pragma unroll
                     for (int i = 0; i < K; i++) {
                         logProb2[(int64_t)(i * K + l) * M + j] =

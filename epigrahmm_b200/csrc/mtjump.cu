@@ -25,6 +25,9 @@ constexpr int LEVELS = 14;                   // up to 2^14 sub-streams = 4.3e9 d
 constexpr int MT_N = 624, MT_M = 397, MT_D = MT_N - MT_M;  // 227
 constexpr int EXPW = mtpoly::DEG + MT_N - 1;               // words a jump needs (20560)
 constexpr int JUMP_NT = 320;
+constexpr int ZERO_IDX = EXPW + 8;                         // index whose word is 0 for every output lane
+constexpr int BUFW = ZERO_IDX + MT_N + 8;                  // expanded words + zeroed tail
+constexpr int MAX_IDX = 20480;                             // index-list capacity per level (uint16)
 constexpr int GEN_NT = 256;
 
 __device__ __forceinline__ uint32_t twist(uint32_t a, uint32_t b) {
@@ -45,33 +48,37 @@ __global__ void mt_base_kernel(const uint32_t *__restrict__ state, uint32_t *__r
         S[i] = (i < MT_N - 1) ? state[1 + i + 1] : (state[1 + MT_M] ^ twist(state[1], state[2]));
 }
 
-// S[(base + c)] = jump(S[c]) by the polynomial `mask` (624 words of coefficient bits)
-__global__ void __launch_bounds__(JUMP_NT) mt_jump_kernel(const uint32_t *__restrict__ mask, uint32_t *__restrict__ S,
-                                                          int base) {
+// S[(base + c)] = jump(S[c]) by the polynomial whose set coefficients are listed in `idx`
+// (nidx entries, padded to a multiple of 8 with ZERO_IDX, which addresses a zeroed region)
+__global__ void __launch_bounds__(JUMP_NT) mt_jump_kernel(const uint16_t *__restrict__ idx, int nidx,
+                                                          uint32_t *__restrict__ S, int base) {
     extern __shared__ uint32_t sm[];
-    uint32_t *buf = sm;             // EXPW (+ slack)
-    uint32_t *smask = sm + EXPW + 8;  // 624
+    uint32_t *buf = sm;                                                   // EXPW words + zero pad
+    uint16_t *sidx = reinterpret_cast<uint16_t *>(sm + BUFW);             // nidx entries
     const int tid = threadIdx.x;
     const uint32_t *src = S + (size_t)blockIdx.x * MT_N;
     uint32_t *dst = S + (size_t)(base + blockIdx.x) * MT_N;
-    for (int i = tid; i < MT_N; i += JUMP_NT) { buf[i] = src[i]; smask[i] = mask[i]; }
+    for (int i = tid; i < MT_N; i += JUMP_NT) buf[i] = src[i];
+    for (int i = EXPW + tid; i < BUFW; i += JUMP_NT) buf[i] = 0u;
+    for (int i = tid; i < nidx / 2; i += JUMP_NT)
+        reinterpret_cast<uint32_t *>(sidx)[i] = reinterpret_cast<const uint32_t *>(idx)[i];
     __syncthreads();
     for (int b0 = MT_N; b0 < EXPW; b0 += MT_D) {
-        const int idx = b0 + tid;
-        if (tid < MT_D && idx < EXPW) buf[idx] = buf[idx - MT_D] ^ twist(buf[idx - MT_N], buf[idx - MT_N + 1]);
+        const int i = b0 + tid;
+        if (tid < MT_D && i < EXPW) buf[i] = buf[i - MT_D] ^ twist(buf[i - MT_N], buf[i - MT_N + 1]);
         __syncthreads();
     }
     if (tid < MT_N / 2) {
         uint32_t a0 = 0, a1 = 0;
         const uint32_t *b0p = buf + tid, *b1p = buf + tid + MT_N / 2;
-        for (int q = 0; q < MT_N; q++) {
-            uint32_t mw = smask[q];
-            const int o = q * 32;
-            while (mw) {
-                const int b = __ffs(mw) - 1;
-                mw &= mw - 1;
-                a0 ^= b0p[o + b];
-                a1 ^= b1p[o + b];
+        for (int q = 0; q < nidx; q += 8) {
+            const uint4 pk = *reinterpret_cast<const uint4 *>(sidx + q);  // 8 indices, broadcast
+            const unsigned w[4] = {pk.x, pk.y, pk.z, pk.w};
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const unsigned i0 = w[j] & 0xffffu, i1 = w[j] >> 16;
+                a0 ^= b0p[i0] ^ b0p[i1];
+                a1 ^= b1p[i0] ^ b1p[i1];
             }
         }
         dst[tid] = a0;
@@ -125,29 +132,34 @@ __global__ void __launch_bounds__(GEN_NT)
 
 // jump polynomials: computed once per process on the host, uploaded once per device
 std::mutex g_mu;
-std::vector<uint32_t> g_masks;  // LEVELS * 624 words
-std::map<int, uint32_t *> g_dev_masks;
+std::vector<uint16_t> g_idx;    // LEVELS * MAX_IDX coefficient positions
+int g_nidx[LEVELS] = {0};
+std::map<int, uint16_t *> g_dev_idx;
+constexpr size_t JUMP_SMEM = sizeof(uint32_t) * BUFW + sizeof(uint16_t) * MAX_IDX;
 
-int device_masks(int device, const uint32_t **out) {
+int device_polys(int device, const uint16_t **out) {
     std::lock_guard<std::mutex> lk(g_mu);
-    if (g_masks.empty()) {
+    if (g_idx.empty()) {
         std::vector<mtpoly::Poly> polys = mtpoly::jump_polys(LOG2J, LEVELS);
         EHMM_REQUIRE((int)polys.size() == LEVELS, EHMM_ERR_RNG, "MT19937 characteristic polynomial has the wrong degree");
-        g_masks.assign((size_t)LEVELS * MT_N, 0u);
-        for (int k = 0; k < LEVELS; k++)
-            for (int w = 0; w < mtpoly::NW; w++) {
-                g_masks[(size_t)k * MT_N + 2 * w] = (uint32_t)(polys[k][w] & 0xffffffffull);
-                g_masks[(size_t)k * MT_N + 2 * w + 1] = (uint32_t)(polys[k][w] >> 32);
-            }
+        g_idx.assign((size_t)LEVELS * MAX_IDX, (uint16_t)ZERO_IDX);
+        for (int k = 0; k < LEVELS; k++) {
+            int n = 0;
+            for (int i = 0; i < mtpoly::DEG; i++)
+                if (mtpoly::get(polys[k], i)) {
+                    EHMM_REQUIRE(n < MAX_IDX, EHMM_ERR_RNG, "jump polynomial denser than expected");
+                    g_idx[(size_t)k * MAX_IDX + n++] = (uint16_t)i;
+                }
+            g_nidx[k] = (n + 7) & ~7;
+        }
     }
-    auto it = g_dev_masks.find(device);
-    if (it == g_dev_masks.end()) {
-        uint32_t *d = nullptr;
-        EHMM_CK(cudaMalloc(&d, sizeof(uint32_t) * g_masks.size()));
-        EHMM_CK(cudaMemcpy(d, g_masks.data(), sizeof(uint32_t) * g_masks.size(), cudaMemcpyHostToDevice));
-        size_t smem = sizeof(uint32_t) * (EXPW + 8 + MT_N);
-        EHMM_CK(cudaFuncSetAttribute(mt_jump_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        it = g_dev_masks.emplace(device, d).first;
+    auto it = g_dev_idx.find(device);
+    if (it == g_dev_idx.end()) {
+        uint16_t *d = nullptr;
+        EHMM_CK(cudaMalloc(&d, sizeof(uint16_t) * g_idx.size()));
+        EHMM_CK(cudaMemcpy(d, g_idx.data(), sizeof(uint16_t) * g_idx.size(), cudaMemcpyHostToDevice));
+        EHMM_CK(cudaFuncSetAttribute(mt_jump_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)JUMP_SMEM));
+        it = g_dev_idx.emplace(device, d).first;
     }
     *out = it->second;
     return EHMM_OK;
@@ -166,18 +178,17 @@ int mt_prepare(ehmm_session *s, cudaStream_t st, int64_t max_draws) {
     const int64_t P = substreams_for(624, max_draws);
     if (P <= 1) { s->mtj_valid = 1; return EHMM_OK; }
     EHMM_REQUIRE(P <= ((int64_t)1 << LEVELS), EHMM_ERR_RNG, "too many uniforms in one call (%lld)", (long long)max_draws);
-    const uint32_t *masks = nullptr;
-    EHMM_TRY(device_masks(s->device, &masks));
+    const uint16_t *idx = nullptr;
+    EHMM_TRY(device_polys(s->device, &idx));
     EHMM_TRY(s->mt_windows.reserve(sizeof(uint32_t) * MT_N * (size_t)P));
     uint32_t *S = s->mt_windows.as<uint32_t>();
     mt_base_kernel<<<1, 256, 0, st>>>(s->mt_raw.as<uint32_t>(), S);
     EHMM_CK(cudaGetLastError());
     s->launches[KID_MT]++;
-    const size_t smem = sizeof(uint32_t) * (EXPW + 8 + MT_N);
     for (int k = 0; ((int64_t)1 << k) < P; k++) {
         const int64_t base = (int64_t)1 << k;
         const int64_t cnt = (P - base < base) ? (P - base) : base;
-        mt_jump_kernel<<<(unsigned)cnt, JUMP_NT, smem, st>>>(masks + (size_t)k * MT_N, S, (int)base);
+        mt_jump_kernel<<<(unsigned)cnt, JUMP_NT, JUMP_SMEM, st>>>(idx + (size_t)k * MAX_IDX, g_nidx[k], S, (int)base);
         EHMM_CK(cudaGetLastError());
         s->launches[KID_MT]++;
     }

@@ -41,6 +41,22 @@ __global__ void minmax_i32_kernel(const int32_t *__restrict__ x, int64_t n, int 
     }
 }
 
+// does dtUnique[group] reproduce the data cell by cell?  (it must, for the dictionary-encoded
+// emission path; the reference builds Group from exactly these columns, R/base-core.R:97,187-193)
+__global__ void group_check_kernel(int64_t n, const int32_t *__restrict__ group, int64_t G,
+                                   const int32_t *__restrict__ y, const double *__restrict__ off,
+                                   const double *__restrict__ ctrl, const double *__restrict__ uy,
+                                   const double *__restrict__ uoff, const double *__restrict__ uctrl,
+                                   int *__restrict__ bad) {
+    int b = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t g = group[i];
+        if (g < 1 || g > G) { b |= 2; continue; }
+        if (uy[g] != (double)y[i] || uoff[g] != off[i] || (ctrl && uctrl && uctrl[g] != ctrl[i])) b |= 1;
+    }
+    if (b) atomicOr(bad, b);
+}
+
 __global__ void exp_kernel(const double *__restrict__ x, int64_t n, double *__restrict__ y) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         y[i] = exp(x[i]);
@@ -184,7 +200,7 @@ int ehmm_session_close(ehmm_session *s) {
     DevBuf *bufs[] = {&s->counts_own, &s->offsets_own, &s->controls_own, &s->group, &s->u_chip, &s->u_off, &s->u_ctrl,
                       &s->u_dsg, &s->logf, &s->logFP, &s->logBP, &s->logProb1, &s->logProb2, &s->eta, &s->viterbi,
                       &s->tileops, &s->carries, &s->tilestats, &s->fbscal, &s->rc_w, &s->rc_flag, &s->rc_scan,
-                      &s->rc_buckets, &s->rc_unif, &s->rc_tmp, &s->mt_raw, &s->mt_raw2, &s->mt_windows, &s->lgtab, &s->glm_part, &s->misc};
+                      &s->rc_buckets, &s->rc_unif, &s->rc_tmp, &s->mt_raw, &s->mt_raw2, &s->mt_windows, &s->gtab, &s->lgtab, &s->glm_part, &s->misc};
     for (DevBuf *b : bufs) b->release();
     for (cudaEvent_t e : s->prof_pool) cudaEventDestroy(e);
     if (s->h_pinned) cudaFreeHost(s->h_pinned);
@@ -232,6 +248,7 @@ int ehmm_set_data(ehmm_session *s, int N, const int32_t *counts, const double *o
         dc = s->controls_own.as<double>();
     }
     s->N = N;
+    s->groups_consistent = false;
     s->d_counts = s->counts_own.as<int32_t>();
     s->d_offsets = s->offsets_own.as<double>();
     s->d_controls = dc;
@@ -242,6 +259,7 @@ int ehmm_set_data_device(ehmm_session *s, int N, const int32_t *counts, const do
     EHMM_TRY(check_session(s));
     EHMM_REQUIRE(N >= 1 && counts && offsets, EHMM_ERR_ARG, "set_data: N >= 1, counts and offsets required");
     s->N = N;
+    s->groups_consistent = false;
     s->d_counts = counts;
     s->d_offsets = offsets;
     s->d_controls = controls;
@@ -280,7 +298,19 @@ int ehmm_set_groups(ehmm_session *s, const int32_t *group, int64_t G, const doub
             EHMM_CK(cudaMemcpyAsync(s->u_dsg.as<uint8_t>() + (size_t)b * (G + 1) + 1, u_dsg + (size_t)b * G, (size_t)G,
                                     cudaMemcpyHostToDevice, s->stream));
     }
+    // validate the ids and find out whether dtUnique matches the data (enables the gather path)
+    EHMM_TRY(s->misc.reserve(64));
+    int *bad = s->misc.as<int>();
+    EHMM_CK(cudaMemsetAsync(bad, 0, sizeof(int), s->stream));
+    PROF(s, KID_MISC), group_check_kernel<<<148 * 8, 256, 0, s->stream>>>(
+        (int64_t)n, s->group.as<int32_t>(), G, s->d_counts, s->d_offsets, s->d_controls, s->u_chip.as<double>(),
+        s->u_off.as<double>(), u_controls ? s->u_ctrl.as<double>() : nullptr, bad);
+    EHMM_CK(cudaGetLastError());
+    int hb = 0;
+    EHMM_CK(cudaMemcpyAsync(&hb, bad, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
     EHMM_CK(cudaStreamSynchronize(s->stream));
+    EHMM_REQUIRE(!(hb & 2), EHMM_ERR_ARG, "set_groups: group ids must lie in [1, G]");
+    s->groups_consistent = (hb == 0) && (!s->d_controls || u_controls);
     s->G = G;
     s->rc_columns = 0;
     return EHMM_OK;

@@ -195,3 +195,51 @@ def test_inner_maxstepprob(ehmm, oracle):
         s.store("mixtureProb", eta)
         got = s.inner_maxstepprob()
     assert np.allclose(got, ref, rtol=1e-12, atol=0)
+
+
+@pytest.mark.parametrize("model", ["consensus", "consensus_ctrl", "differential"])
+def test_dictionary_encoded_emission_is_bit_identical(ehmm, model):
+    """with dt$Group / dtUnique uploaded the emission gathers per-group densities instead of
+    evaluating every cell; both paths must give the same bits"""
+    M = 30011
+    if model == "differential":
+        d = synth.make_differential(M, 3, 2, seed=41)
+        g = synth.make_groups(d["counts"], d["offsets"], design=d["design"])
+        delta = np.random.default_rng(2).dirichlet(np.ones(d["B"]))
+        psi = synth.THETA_DIFFERENTIAL["psi"]
+        with ehmm.Session("t_dict", M, 3) as s:
+            s.set_data(d["counts"], d["offsets"])
+            s.set_design(d["design"])
+            s.loglik_differential_hmm(delta, psi, MINZERO)
+            a = s.fetch("logLikelihood")
+            s.inner_expstep(delta, psi, MINZERO)
+            ea = s.fetch("mixtureProb")
+            s.set_groups(g["group"], g["u_chip"], g["u_offsets"], None, g["u_dsg"])
+            s.profile(True)
+            s.loglik_differential_hmm(delta, psi, MINZERO)
+            b = s.fetch("logLikelihood")
+            s.inner_expstep(delta, psi, MINZERO)
+            eb = s.fetch("mixtureProb")
+            assert s.profile_read()["emis_tables"][0] >= 2
+        assert np.array_equal(a, b) and np.array_equal(ea, eb)
+        return
+    ctrl = model == "consensus_ctrl"
+    d = synth.make_consensus(M, 3, seed=42, controls=ctrl)
+    g = synth.make_groups(d["counts"], d["offsets"], d["controls"])
+    psi = [np.array([np.log(2.0), 0.3, 3.0]), np.array([np.log(12.0), 0.1, 4.0])] if ctrl else synth.THETA_CONSENSUS["psi"]
+    with ehmm.Session("t_dict", M, 2) as s:
+        s.set_data(d["counts"], d["offsets"], d["controls"])
+        s.loglik_consensus(psi, MINZERO)
+        a = s.fetch("logLikelihood")
+        s.set_groups(g["group"], g["u_chip"], g["u_offsets"], g["u_controls"])
+        s.profile(True)
+        s.loglik_consensus(psi, MINZERO)
+        b = s.fetch("logLikelihood")
+        assert s.profile_read()["emis_gather"][0] == 1
+        # a dtUnique that does not describe the data must not be used for the emission
+        s.set_groups(g["group"], g["u_chip"] + 1.0, g["u_offsets"], g["u_controls"])
+        s.profile(True)
+        s.loglik_consensus(psi, MINZERO)
+        c = s.fetch("logLikelihood")
+        assert s.profile_read()["emis_gather"][0] == 0
+    assert np.array_equal(a, b) and np.array_equal(a, c)
