@@ -137,7 +137,7 @@ struct ehmm_session {
     ehmm::DevBuf lgtab, glm_part, misc, gtab;
     bool groups_consistent = false;  // dtUnique[group] reproduces (counts, offsets[, controls]) cell by cell
     int64_t count_max = -1;
-    double *h_pinned = nullptr;  // small pinned staging buffer (256 doubles)
+    double *h_pinned = nullptr;  // small pinned staging buffer (1024 doubles; [512..] = RNG state)
 
     // ---- launch counters and optional per-kernel CUDA-event timing ----
     int64_t launches[ehmm::KID_COUNT] = {0};

@@ -115,51 +115,51 @@ template <> __device__ __forceinline__ double get_unif<uint32_t>(const uint32_t 
     return mt_to_unif(__ldg(u + i));
 }
 
-// nrep = 1 with group stride 0 for the consensus model (only f[0..M-1] is read, Q6 in SURVEY.md);
-// nrep = N for the differential model (repmat(w, N, 1) against the M*N group ids).
+// nrep = 1 for the consensus model (only f[0..M-1] is read, Q6 in SURVEY.md); nrep = N for the
+// differential model (repmat(w, N, 1) against the M*N group ids).
+// Each thread owns RC_STRIPS consecutive bins, so ranks inside the block come from one warp scan
+// and one block barrier; the weight loads of a warp still cover one contiguous 2 KB span.
 template <typename UT>
 __global__ void __launch_bounds__(RC_NT)
     rc_apply_kernel(RCSrc S, double p, int64_t nblk, const int64_t *__restrict__ offsets, const UT *__restrict__ unif,
                     const int32_t *__restrict__ group, int nrep, int64_t G, double *__restrict__ buckets,
                     double *__restrict__ wout) {
     __shared__ int sh[RC_NT / 32];
-    __shared__ int running;
     const int c = blockIdx.y;
-    const int64_t base = (int64_t)blockIdx.x * RC_TB;
+    const int64_t j0 = (int64_t)blockIdx.x * RC_TB + (int64_t)threadIdx.x * RC_STRIPS;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int64_t ubase = offsets[(int64_t)c * nblk + blockIdx.x];
     double *bk = buckets + (int64_t)c * (G + 1);
-    if (threadIdx.x == 0) running = 0;
-    __syncthreads();
+    double x[RC_STRIPS];
+    unsigned flags = 0;
+#pragma unroll
     for (int r = 0; r < RC_STRIPS; r++) {
-        const int64_t j = base + r * RC_NT + threadIdx.x;
-        double x = 0.0;
-        bool flag = false;
+        const int64_t j = j0 + r;
+        x[r] = (j < S.M) ? rc_weight(S, c, j) : 2.0;  // 2.0: never below p <= 1, never stored
+        if (x[r] < p && x[r] / p != 0.0) flags |= 1u << r;
+    }
+    const int cnt = __popc(flags);
+    int incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+    }
+    if (lane == 31) sh[w] = incl;
+    __syncthreads();
+    int before = incl - cnt;
+    for (int i = 0; i < w; i++) before += sh[i];
+    int64_t u = offsets[(int64_t)c * nblk + blockIdx.x] + before;
+#pragma unroll
+    for (int r = 0; r < RC_STRIPS; r++) {
+        const int64_t j = j0 + r;
         if (j < S.M) {
-            x = rc_weight(S, c, j);
-            flag = (x < p && x / p != 0.0);
-        }
-        const unsigned bal = __ballot_sync(0xffffffffu, flag);
-        if (lane == 0) sh[w] = __popc(bal);
-        __syncthreads();
-        int before = running;
-        for (int i = 0; i < w; i++) before += sh[i];
-        const int rank = before + __popc(bal & ((1u << lane) - 1u));
-        if (j < S.M) {
-            double wt = x;
-            if (x < p) wt = flag ? rbinom1(x / p, get_unif<UT>(unif, ubase + rank)) * p : 0.0;
+            double wt = x[r];
+            if (wt < p) wt = ((flags >> r) & 1u) ? rbinom1(wt / p, get_unif<UT>(unif, u++)) * p : 0.0;
             if (wout) wout[(int64_t)c * S.M + j] = wt;
             if (wt != 0.0) {
                 for (int i = 0; i < nrep; i++) atomicAdd(bk + __ldg(group + j + (int64_t)i * S.M), wt);
             }
         }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            int t = 0;
-            for (int i = 0; i < RC_NT / 32; i++) t += sh[i];
-            running += t;
-        }
-        __syncthreads();
     }
 }
 
@@ -245,6 +245,7 @@ int run_rc(ehmm_session *s, const RCSrc &S, double p, int nrep, const double *un
         EHMM_CK(cudaMemsetAsync(s->rc_scan.p, 0, sizeof(int64_t) * (ncnt + 1), s->stream));
     }
     const int32_t *grp = s->group.as<int32_t>();
+    bool state_back = false;
     if (uniforms) {
         EHMM_REQUIRE(total <= n_uniforms, EHMM_ERR_RNG, "rejection control needs %lld uniforms, buffer holds %lld",
                      (long long)total, (long long)n_uniforms);
@@ -261,12 +262,14 @@ int run_rc(ehmm_session *s, const RCSrc &S, double p, int nrep, const double *un
         EHMM_TRY(s->mt_raw.reserve(sizeof(uint32_t) * 625));
         if (total > 0) {
             if (!s->rng_dev_valid) {
-                EHMM_CK(cudaMemcpyAsync(s->mt_raw.p, s->rng_state, sizeof(uint32_t) * 625, cudaMemcpyHostToDevice, s->stream));
+                memcpy(s->h_pinned + 512, s->rng_state, sizeof(uint32_t) * 625);
+                EHMM_CK(cudaMemcpyAsync(s->mt_raw.p, s->h_pinned + 512, sizeof(uint32_t) * 625, cudaMemcpyHostToDevice, s->stream));
                 s->rng_dev_valid = true;
                 s->mtj_valid = 0;
             }
             EHMM_TRY(mt_generate(s, total, s->rc_unif.as<uint32_t>()));
-            EHMM_CK(cudaMemcpyAsync(s->rng_state, s->mt_raw.p, sizeof(uint32_t) * 625, cudaMemcpyDeviceToHost, s->stream));
+            EHMM_CK(cudaMemcpyAsync(s->h_pinned + 512, s->mt_raw.p, sizeof(uint32_t) * 625, cudaMemcpyDeviceToHost, s->stream));
+            state_back = true;
         }
         PROF(s, KID_RC_APPLY), rc_apply_kernel<uint32_t><<<grid, RC_NT, 0, s->stream>>>(S, p, nblk, s->rc_scan.as<int64_t>(),
                                                                  s->rc_unif.as<uint32_t>(), grp, nrep, s->G,
@@ -276,6 +279,7 @@ int run_rc(ehmm_session *s, const RCSrc &S, double p, int nrep, const double *un
     // the next call's sub-stream windows depend only on the RNG state: prepare them on the side stream
     if (!uniforms && total > 0) EHMM_TRY(mt_prefetch(s, (int64_t)S.columns * s->M));
     EHMM_CK(cudaStreamSynchronize(s->stream));
+    if (state_back) memcpy(s->rng_state, s->h_pinned + 512, sizeof(uint32_t) * 625);
     s->rc_columns = S.columns;
     s->rc_N = nrep;
     if (consumed) *consumed = total;

@@ -162,7 +162,7 @@ int ehmm_session_open(const char *key, int64_t M, int K, int device, ehmm_sessio
     EHMM_CK(cudaStreamCreateWithFlags(&s->stream2, cudaStreamNonBlocking));
     EHMM_CK(cudaEventCreateWithFlags(&s->ev, cudaEventDisableTiming));
     EHMM_CK(cudaEventCreateWithFlags(&s->ev2, cudaEventDisableTiming));
-    EHMM_CK(cudaMallocHost(&s->h_pinned, sizeof(double) * 256));
+    EHMM_CK(cudaMallocHost(&s->h_pinned, sizeof(double) * 1024));
     {
         std::lock_guard<std::mutex> lk(g_mu);
         auto it = g_sessions.find(s->key);
