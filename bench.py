@@ -101,20 +101,23 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def pin_workload(d, g):
+    import torch
+    for k, src in (("counts", d), ("offsets", d), ("group", g)):
+        a = src[k]
+        t = torch.empty(a.size, dtype=torch.int32 if a.dtype == np.int32 else torch.float64).pin_memory()
+        v = t.numpy().reshape(a.shape, order="F")
+        v[...] = a
+        src[k] = v
+        src["_pin_" + k] = t  # keep the pinned tensor alive
+    return d, g
+
+
 def make_workload(M, N, seed, pinned=False):
     from epigrahmm_b200 import synth
     d = synth.make_consensus(M, N, seed)
     g = synth.make_groups(d["counts"], d["offsets"])
-    if pinned:
-        import torch
-        for k, src in (("counts", d), ("offsets", d), ("group", g)):
-            a = src[k]
-            t = torch.empty(a.size, dtype=torch.int32 if a.dtype == np.int32 else torch.float64).pin_memory()
-            v = t.numpy().reshape(a.shape, order="F")
-            v[...] = a
-            src[k] = v
-            src["_pin_" + k] = t  # keep the pinned tensor alive
-    return d, g
+    return pin_workload(d, g) if pinned else (d, g)
 
 
 def em_iteration(be, theta, control, N, upload=None):
@@ -216,15 +219,19 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     M = args.bins
-    d, g = make_workload(M, N_SAMPLES, SEED + rank, pinned=True)
     th = synth.THETA_CONSENSUS
     theta = dict(pi=th["pi"], gamma=th["gamma"], psi=th["psi"])
     ctl = em.controlEM()
 
     if world > 1:
-        from epigrahmm_b200.sharded import ShardedSession
-        s = ShardedSession("bench", M, K, local, dist)
+        from epigrahmm_b200 import sharded
+        s = sharded.ShardedSession("bench", M, K, local, dist)
+        d = synth.make_consensus(M, N_SAMPLES, SEED + rank)
+        # one dt$Group dictionary for the whole sharded table
+        g = sharded.global_groups(d["counts"], d["offsets"], s.comm, s.m0, s.Mtot)
+        d, g = pin_workload(d, g)
     else:
+        d, g = make_workload(M, N_SAMPLES, SEED + rank, pinned=True)
         s = E.Session("bench", M, K, local)
     s.set_data(d["counts"], d["offsets"])
     s.set_groups(g["group"], g["u_chip"], g["u_offsets"])

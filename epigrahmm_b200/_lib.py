@@ -67,11 +67,16 @@ PROTOTYPES = {
     "ehmm_expstep_reduce": [_sess, _dp, _dp, _dp, _dp],
     "ehmm_expstep_apply": [_sess, _dp, _dp, _dp],
     "ehmm_estep_stats": [_sess, _dp],
+    "ehmm_estep_row0": [_sess, _dp],
     "ehmm_estep_set_stats": [_sess, _dp, _dp, C.c_double],
     "ehmm_rng_set_state": [_sess, _up],
     "ehmm_rng_get_state": [_sess, _up],
     "ehmm_rc_consensus": [_sess, C.c_double, _dp, C.c_int64, _lp],
     "ehmm_rc_differential": [_sess, C.c_double, C.c_int, _dp, C.c_int64, _lp],
+    "ehmm_rc_count": [_sess, C.c_int, C.c_double, _lp],
+    "ehmm_rc_apply_at": [_sess, C.c_int, C.c_double, _lp, C.c_int64],
+    "ehmm_rc_buckets_device": [_sess, C.POINTER(C.c_void_p), _lp],
+    "ehmm_inner_mstep_sums": [_sess, _dp],
     "ehmm_rc_table_rows": [_sess, C.c_int, _lp],
     "ehmm_rc_table_fetch": [_sess, C.c_int, _dp, _dp],
     "ehmm_rc_buckets_fetch": [_sess, C.c_int, _dp],

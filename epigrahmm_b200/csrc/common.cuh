@@ -132,6 +132,9 @@ struct ehmm_session {
     bool rng_dev_valid = false;  // mt_raw holds rng_state
     int rc_columns = 0;
     int rc_N = 0;
+    int64_t rc_colcount[64] = {0};  // sharded form: flagged counts of this block per column
+    double rc_count_p = -1.0;
+    int rc_count_cols = 0;
 
     // ---- emission / GLM scratch ----
     ehmm::DevBuf lgtab, glm_part, misc, gtab;
@@ -200,15 +203,20 @@ int emis_init(ehmm_session *s, const double *psi1, const double *psi2);
 int emis_differential_hmm(ehmm_session *s, const double *delta, const double *psi, double minZero);
 int emis_inner_estep(ehmm_session *s, const double *delta, const double *psi, double minZero);
 int inner_maxstepprob(ehmm_session *s, double *delta_out);
+int inner_mstep_sums(ehmm_session *s, double *sums);
 // rc.cu
 int rc_consensus(ehmm_session *s, double p, const double *uniforms, int64_t n_uniforms, int64_t *consumed);
 int rc_differential(ehmm_session *s, double p, int N, const double *uniforms, int64_t n_uniforms, int64_t *consumed);
+int rc_count(ehmm_session *s, int differential, double p, int64_t *counts);
+int rc_apply_at(ehmm_session *s, int differential, double p, const int64_t *col_offsets, int64_t total);
 int rc_table_rows(ehmm_session *s, int column, int64_t *rows);
 int rc_table_fetch(ehmm_session *s, int column, double *sums, double *ids);
 int rc_reweight(int device, double *x, int64_t n, double p, const double *uniforms, int64_t n_uniforms, int64_t *consumed);
 int rc_aggregate(int device, const double *x, int64_t n, const int32_t *f, int64_t G, double *buckets);
 // mtjump.cu
 int mt_generate(ehmm_session *s, int64_t n, uint32_t *out);
+int mt_generate_range(ehmm_session *s, int64_t lo_rel, int64_t n, uint32_t *out);
+int mt_advance(ehmm_session *s, int64_t n);
 int mt_prefetch(ehmm_session *s, int64_t max_draws);
 // glm.cu
 int glm_nb(ehmm_session *s, int column, const double *par, int P, double *value, double *grad);

@@ -460,7 +460,8 @@ int emis_inner_estep(ehmm_session *s, const double *delta, const double *psi, do
     return EHMM_OK;
 }
 
-int inner_maxstepprob(ehmm_session *s, double *delta_out) {
+// sums[b] = sum_j P1[j,1]*eta[j,b] (b < B), sums[B] = sum_j P1[j,1]  (additive across bin blocks)
+int inner_mstep_sums(ehmm_session *s, double *sums) {
     EHMM_REQUIRE(has(s, DS_ETA | DS_P1), EHMM_ERR_STATE, "innerMaxStepProb needs mixtureProb and logProb1");
     EHMM_REQUIRE(s->K == 3, EHMM_ERR_ARG, "innerMaxStepProb needs K=3");
     const int B = s->B;
@@ -473,7 +474,14 @@ int inner_maxstepprob(ehmm_session *s, double *delta_out) {
     EHMM_CK(cudaGetLastError());
     EHMM_CK(cudaMemcpyAsync(s->h_pinned + 64, out, sizeof(double) * (B + 1), cudaMemcpyDeviceToHost, s->stream));
     EHMM_CK(cudaStreamSynchronize(s->stream));
-    for (int b = 0; b < B; b++) delta_out[b] = s->h_pinned[64 + b] / s->h_pinned[64 + B];
+    for (int b = 0; b <= B; b++) sums[b] = s->h_pinned[64 + b];
+    return EHMM_OK;
+}
+
+int inner_maxstepprob(ehmm_session *s, double *delta_out) {
+    double sums[EHMM_MAX_B + 2];
+    EHMM_TRY(inner_mstep_sums(s, sums));
+    for (int b = 0; b < s->B; b++) delta_out[b] = sums[b] / sums[s->B];
     return EHMM_OK;
 }
 

@@ -86,35 +86,49 @@ __global__ void __launch_bounds__(JUMP_NT) mt_jump_kernel(const uint16_t *__rest
     }
 }
 
-// CTA s generates the absolute words of sub-stream s that fall into [pos, pos + n) as tempered
-// 32-bit words (out[a - pos]) and the raw words of R's next state array.
+// CTA b handles sub-stream s = s_first + b.  It writes the tempered words of the absolute range
+// [pos + lo_rel, pos + hi_rel) that fall into its sub-stream (out[a - (pos + lo_rel)]) and, when
+// n_state > 0, the raw words of R's state array after n_state draws (the aligned 624-word block
+// containing the last drawn word, and mti).
 __global__ void __launch_bounds__(GEN_NT)
-    mt_generate_kernel(const uint32_t *__restrict__ state, const uint32_t *__restrict__ S, int64_t n,
-                       uint32_t *__restrict__ out, uint32_t *__restrict__ state_out) {
+    mt_generate_kernel(const uint32_t *__restrict__ state, const uint32_t *__restrict__ S, int s_first, int64_t lo_rel,
+                       int64_t hi_rel, uint32_t *__restrict__ out, int64_t n_state, uint32_t *__restrict__ state_out) {
     __shared__ uint32_t buf[2][MT_N];
     const int tid = threadIdx.x;
-    const int s = blockIdx.x;
+    const int s = s_first + blockIdx.x;
     const int64_t pos = state[0];
-    const int64_t E = pos + n;                    // exclusive end (absolute)
-    const int64_t bf = (E - 1) / MT_N;            // R's array will hold absolute [624*bf, 624*bf + 624)
-    const int64_t st_lo = bf * MT_N, st_hi = st_lo + MT_N;
+    const int64_t lo_abs = pos + lo_rel, hi_abs = pos + hi_rel;
     const int64_t a0 = (s == 0) ? 0 : 1 + (int64_t)s * JW;
-    const int64_t lo = (s == 0) ? pos : a0;
     const int64_t nxt = 1 + (int64_t)(s + 1) * JW;
-    const int64_t hi = min(E, nxt);
-    const bool last = (hi == E);
-    const int64_t gen_end = last ? max(hi, st_hi) : hi;
+    const int64_t lo = max(lo_abs, a0), hi = min(hi_abs, nxt);
+    int64_t gen_end = (lo < hi) ? hi : a0;
+    int64_t st_lo = 0, st_hi = 0, st_end = 0;  // this CTA writes state words [max(a0, st_lo), st_end)
+    bool last = false;
+    if (n_state > 0) {
+        const int64_t E = pos + n_state;
+        st_lo = ((E - 1) / MT_N) * MT_N;
+        st_hi = st_lo + MT_N;
+        last = (E > a0 && E <= nxt);
+        if (last) st_end = st_hi;
+        else if (nxt < E) st_end = min(nxt, st_hi);
+        if (st_end > max(a0, st_lo)) gen_end = max(gen_end, st_end);
+        else st_end = 0;
+        if (last && tid == 0) state_out[0] = (uint32_t)(E - st_lo);
+    }
+    if (gen_end <= a0) return;
     const uint32_t *src = (s == 0) ? state + 1 : S + (size_t)s * MT_N;
     for (int i = tid; i < MT_N; i += GEN_NT) buf[0][i] = src[i];
     __syncthreads();
     int cur = 0;
     for (int64_t cb = a0;; cb += MT_N) {
         const uint32_t *bc = buf[cur];
-        for (int kk = tid; kk < MT_N; kk += GEN_NT) {
-            const int64_t a = cb + kk;
-            const uint32_t v = bc[kk];
-            if (a >= lo && a < hi) out[a - pos] = temper(v);
-            if (a >= st_lo && a < st_hi && a < gen_end) state_out[1 + (a - st_lo)] = v;
+        if (cb + MT_N > lo || cb + MT_N > st_lo) {
+            for (int kk = tid; kk < MT_N; kk += GEN_NT) {
+                const int64_t a = cb + kk;
+                const uint32_t v = bc[kk];
+                if (a >= lo && a < hi) out[a - lo_abs] = temper(v);
+                if (a >= st_lo && a < st_end) state_out[1 + (a - st_lo)] = v;
+            }
         }
         if (cb + MT_N >= gen_end) break;
         uint32_t *nw = buf[cur ^ 1];
@@ -127,7 +141,6 @@ __global__ void __launch_bounds__(GEN_NT)
         __syncthreads();
         cur ^= 1;
     }
-    if (last && tid == 0) state_out[0] = (uint32_t)(E - st_lo);
 }
 
 // jump polynomials: computed once per process on the host, uploaded once per device
@@ -165,10 +178,10 @@ int device_polys(int device, const uint16_t **out) {
     return EHMM_OK;
 }
 
-int64_t substreams_for(int64_t pos, int64_t n) {  // CTAs mt_generate_kernel needs
+int64_t substreams_for(int64_t pos, int64_t n) {  // sub-streams touched by draws [pos, pos + n)
     if (n <= 0) return 0;
-    const int64_t E = pos + n;
-    return (E - 1 - 1) / JW + 1;  // sub-stream s >= 1 is active iff 1 + s*J < E
+    const int64_t last = pos + n - 1;
+    return (last <= 0 ? 0 : (last - 1) / JW) + 1;
 }
 
 }  // namespace
@@ -196,21 +209,56 @@ int mt_prepare(ehmm_session *s, cudaStream_t st, int64_t max_draws) {
     return EHMM_OK;
 }
 
-// Generate n tempered words of the stream into `out` (device) and advance s->mt_raw.
-int mt_generate(ehmm_session *s, int64_t n, uint32_t *out) {
-    if (n <= 0) return EHMM_OK;
-    const int64_t pos = s->rng_state[0];
-    const int64_t P = substreams_for(pos, n);
-    EHMM_TRY(s->mt_raw2.reserve(sizeof(uint32_t) * 625));
+static int64_t substream_of(int64_t a) { return a <= 0 ? 0 : (a - 1) / JW; }
+
+static int ensure_windows(ehmm_session *s, int64_t P) {
     if (s->mtj_pending) {  // windows being prepared on the side stream
         EHMM_CK(cudaStreamWaitEvent(s->stream, s->ev, 0));
         s->mtj_pending = false;
     }
-    if (P > 1 && s->mtj_valid < P) EHMM_TRY(mt_prepare(s, s->stream, n + 624));
+    if (P > 1 && s->mtj_valid < P) EHMM_TRY(mt_prepare(s, s->stream, (P - 1) * JW + 2));
+    return EHMM_OK;
+}
+
+// Generate n tempered words of the stream into `out` (device) and advance s->mt_raw.
+int mt_generate(ehmm_session *s, int64_t n, uint32_t *out) {
+    if (n <= 0) return EHMM_OK;
+    const int64_t pos = s->rng_state[0];
+    const int64_t P = substream_of(pos + n - 1) + 1;
+    EHMM_TRY(s->mt_raw2.reserve(sizeof(uint32_t) * 625));
+    EHMM_TRY(ensure_windows(s, P));
     {
         PROF(s, KID_MT), mt_generate_kernel<<<(unsigned)P, GEN_NT, 0, s->stream>>>(
-            s->mt_raw.as<uint32_t>(), s->mt_windows.as<uint32_t>(), n, out, s->mt_raw2.as<uint32_t>());
+            s->mt_raw.as<uint32_t>(), s->mt_windows.as<uint32_t>(), 0, 0, n, out, n, s->mt_raw2.as<uint32_t>());
     }
+    EHMM_CK(cudaGetLastError());
+    std::swap(s->mt_raw, s->mt_raw2);
+    s->mtj_valid = 0;
+    return EHMM_OK;
+}
+
+// Words [lo_rel, lo_rel + n) of the stream (relative to the current position) without advancing it.
+int mt_generate_range(ehmm_session *s, int64_t lo_rel, int64_t n, uint32_t *out) {
+    if (n <= 0) return EHMM_OK;
+    const int64_t pos = s->rng_state[0];
+    const int64_t s0 = substream_of(pos + lo_rel), s1 = substream_of(pos + lo_rel + n - 1);
+    EHMM_TRY(ensure_windows(s, s1 + 1));
+    PROF(s, KID_MT), mt_generate_kernel<<<(unsigned)(s1 - s0 + 1), GEN_NT, 0, s->stream>>>(
+        s->mt_raw.as<uint32_t>(), s->mt_windows.as<uint32_t>(), (int)s0, lo_rel, lo_rel + n, out, -1, nullptr);
+    EHMM_CK(cudaGetLastError());
+    return EHMM_OK;
+}
+
+// Advance the stream by n draws (R's state array afterwards) without producing output.
+int mt_advance(ehmm_session *s, int64_t n) {
+    if (n <= 0) return EHMM_OK;
+    const int64_t pos = s->rng_state[0];
+    const int64_t E = pos + n, st_lo = ((E - 1) / 624) * 624;
+    const int64_t s0 = substream_of(st_lo), s1 = substream_of(E - 1);
+    EHMM_TRY(s->mt_raw2.reserve(sizeof(uint32_t) * 625));
+    EHMM_TRY(ensure_windows(s, s1 + 1));
+    PROF(s, KID_MT), mt_generate_kernel<<<(unsigned)(s1 - s0 + 1), GEN_NT, 0, s->stream>>>(
+        s->mt_raw.as<uint32_t>(), s->mt_windows.as<uint32_t>(), (int)s0, 0, 0, nullptr, n, s->mt_raw2.as<uint32_t>());
     EHMM_CK(cudaGetLastError());
     std::swap(s->mt_raw, s->mt_raw2);
     s->mtj_valid = 0;

@@ -286,6 +286,81 @@ int run_rc(ehmm_session *s, const RCSrc &S, double p, int nrep, const double *un
     return EHMM_OK;
 }
 
+// ---- sharded form: the caller owns the ordering across bin blocks --------------------------------
+// phase 1: flagged counts of this block per column (count + scan kernels; results stay in rc_scan)
+int rc_count_block(ehmm_session *s, const RCSrc &S, double p, int64_t *counts) {
+    const int64_t nblk = (s->M + RC_TB - 1) / RC_TB;
+    const int64_t ncnt = nblk * S.columns;
+    EHMM_REQUIRE(S.columns <= 64, EHMM_ERR_ARG, "too many columns");
+    EHMM_TRY(s->rc_flag.reserve(sizeof(int) * ncnt));
+    EHMM_TRY(s->rc_scan.reserve(sizeof(int64_t) * (ncnt + 1)));
+    dim3 grid((unsigned)nblk, (unsigned)S.columns);
+    if (p > 0.0) {
+        PROF(s, KID_RC_COUNT), rc_count_kernel<<<grid, RC_NT, 0, s->stream>>>(S, p, nblk, s->rc_flag.as<int>());
+        EHMM_CK(cudaGetLastError());
+        PROF(s, KID_RC_SCAN), rc_scan_kernel<<<1, 1024, 0, s->stream>>>(s->rc_flag.as<int>(), ncnt, s->rc_scan.as<int64_t>());
+        EHMM_CK(cudaGetLastError());
+    } else {
+        EHMM_CK(cudaMemsetAsync(s->rc_scan.p, 0, sizeof(int64_t) * (ncnt + 1), s->stream));
+    }
+    int64_t *hp = reinterpret_cast<int64_t *>(s->h_pinned + 200);
+    for (int c = 0; c <= S.columns; c++)
+        EHMM_CK(cudaMemcpyAsync(hp + c, s->rc_scan.as<int64_t>() + (int64_t)c * nblk, sizeof(int64_t), cudaMemcpyDeviceToHost,
+                                s->stream));
+    EHMM_CK(cudaStreamSynchronize(s->stream));
+    for (int c = 0; c < S.columns; c++) { counts[c] = hp[c + 1] - hp[c]; s->rc_colcount[c] = counts[c]; }
+    s->rc_count_p = p;
+    s->rc_count_cols = S.columns;
+    return EHMM_OK;
+}
+
+// phase 2: this block's draws of column c start at stream offset col_offsets[c] (relative to the
+// current RNG position); the stream advances by `total` (the draws of all blocks).
+int rc_apply_block(ehmm_session *s, const RCSrc &S, double p, int nrep, const int64_t *col_offsets, int64_t total) {
+    EHMM_REQUIRE(s->rc_count_cols == S.columns && s->rc_count_p == p, EHMM_ERR_STATE,
+                 "rc_apply_at must follow rc_count with the same p");
+    EHMM_REQUIRE(s->rng_set || total == 0, EHMM_ERR_RNG, "rejection control needs the RNG state (ehmm_rng_set_state)");
+    const int64_t nblk = (s->M + RC_TB - 1) / RC_TB;
+    int64_t local = 0;
+    for (int c = 0; c < S.columns; c++) local += s->rc_colcount[c];
+    EHMM_TRY(s->rc_buckets.reserve(sizeof(double) * (size_t)S.columns * (s->G + 1)));
+    EHMM_CK(cudaMemsetAsync(s->rc_buckets.p, 0, sizeof(double) * (size_t)S.columns * (s->G + 1), s->stream));
+    EHMM_TRY(s->rc_unif.reserve(sizeof(uint32_t) * (size_t)(local > 0 ? local : 1)));
+    EHMM_TRY(s->mt_raw.reserve(sizeof(uint32_t) * 625));
+    bool state_back = false;
+    if (total > 0) {
+        if (!s->rng_dev_valid) {
+            memcpy(s->h_pinned + 512, s->rng_state, sizeof(uint32_t) * 625);
+            EHMM_CK(cudaMemcpyAsync(s->mt_raw.p, s->h_pinned + 512, sizeof(uint32_t) * 625, cudaMemcpyHostToDevice, s->stream));
+            s->rng_dev_valid = true;
+            s->mtj_valid = 0;
+        }
+        int64_t at = 0;
+        for (int c = 0; c < S.columns; c++) {
+            EHMM_REQUIRE(col_offsets[c] >= 0 && col_offsets[c] + s->rc_colcount[c] <= total, EHMM_ERR_ARG,
+                         "column %d: draws [%lld, %lld) outside [0, %lld)", c, (long long)col_offsets[c],
+                         (long long)(col_offsets[c] + s->rc_colcount[c]), (long long)total);
+            EHMM_TRY(mt_generate_range(s, col_offsets[c], s->rc_colcount[c], s->rc_unif.as<uint32_t>() + at));
+            at += s->rc_colcount[c];
+        }
+        EHMM_TRY(mt_advance(s, total));
+        EHMM_CK(cudaMemcpyAsync(s->h_pinned + 512, s->mt_raw.p, sizeof(uint32_t) * 625, cudaMemcpyDeviceToHost, s->stream));
+        state_back = true;
+    }
+    dim3 grid((unsigned)nblk, (unsigned)S.columns);
+    PROF(s, KID_RC_APPLY), rc_apply_kernel<uint32_t><<<grid, RC_NT, 0, s->stream>>>(
+        S, p, nblk, s->rc_scan.as<int64_t>(), s->rc_unif.as<uint32_t>(), s->group.as<int32_t>(), nrep, s->G,
+        s->rc_buckets.as<double>(), nullptr);
+    EHMM_CK(cudaGetLastError());
+    if (total > 0) EHMM_TRY(mt_prefetch(s, total + 624));
+    EHMM_CK(cudaStreamSynchronize(s->stream));
+    if (state_back) memcpy(s->rng_state, s->h_pinned + 512, sizeof(uint32_t) * 625);
+    s->rc_columns = S.columns;
+    s->rc_N = nrep;
+    s->rc_count_cols = 0;
+    return EHMM_OK;
+}
+
 struct TmpDev {
     void *p = nullptr;
     ~TmpDev() { if (p) cudaFree(p); }
@@ -307,6 +382,19 @@ int rc_differential(ehmm_session *s, double p, int N, const double *uniforms, in
     EHMM_REQUIRE(s->K == 3 && s->B > 0, EHMM_ERR_ARG, "differentialRejectionControlled needs K=3 and mixture components");
     RCSrc S = {s->logProb1.as<double>(), s->eta.as<double>(), s->M, s->B, s->B + 2};
     return run_rc(s, S, p, N, uniforms, n_uniforms, consumed);
+}
+
+static RCSrc rc_source(ehmm_session *s, int differential) {
+    if (differential) return RCSrc{s->logProb1.as<double>(), s->eta.as<double>(), s->M, s->B, s->B + 2};
+    return RCSrc{s->logProb1.as<double>(), nullptr, s->M, 0, s->K};
+}
+
+int rc_count(ehmm_session *s, int differential, double p, int64_t *counts) {
+    return rc_count_block(s, rc_source(s, differential), p, counts);
+}
+
+int rc_apply_at(ehmm_session *s, int differential, double p, const int64_t *col_offsets, int64_t total) {
+    return rc_apply_block(s, rc_source(s, differential), p, differential ? s->N : 1, col_offsets, total);
 }
 
 static int fetch_column(ehmm_session *s, int column, std::vector<double> &h) {

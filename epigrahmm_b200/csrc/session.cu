@@ -402,6 +402,14 @@ int ehmm_estep_stats(ehmm_session *s, double *stats) {
     return EHMM_OK;
 }
 
+int ehmm_estep_row0(ehmm_session *s, double *row0) {
+    EHMM_TRY(check_session(s));
+    EHMM_REQUIRE(has(s, DS_P1) && row0, EHMM_ERR_STATE, "estep_row0: expStep has not run");
+    EHMM_TRY(fb_fetch_stats(s));
+    for (int k = 0; k < s->K; k++) row0[k] = s->h_lp1_row0[k];
+    return EHMM_OK;
+}
+
 int ehmm_estep_set_stats(ehmm_session *s, const double *stats, const double *logprob1_row0, double loglik) {
     EHMM_TRY(check_session(s));
     EHMM_REQUIRE(stats && logprob1_row0, EHMM_ERR_ARG, "null pointer");
@@ -533,6 +541,34 @@ int ehmm_rc_differential(ehmm_session *s, double p, int N, const double *uniform
     EHMM_REQUIRE(s->G > 0, EHMM_ERR_STATE, "differentialRejectionControlled: ehmm_set_groups has not been called");
     EHMM_REQUIRE(N == s->N, EHMM_ERR_ARG, "N=%d does not match the data (N=%d)", N, s->N);
     return rc_differential(s, p, N, uniforms, n_uniforms, consumed);
+}
+
+int ehmm_rc_count(ehmm_session *s, int differential, double p, int64_t *counts) {
+    EHMM_TRY(check_session(s));
+    EHMM_REQUIRE(counts, EHMM_ERR_ARG, "null pointer");
+    EHMM_REQUIRE(has(s, differential ? (DS_P1 | DS_ETA) : DS_P1), EHMM_ERR_STATE, "rc_count: posteriors not available");
+    EHMM_REQUIRE(s->G > 0, EHMM_ERR_STATE, "rc_count: ehmm_set_groups has not been called");
+    return rc_count(s, differential, p, counts);
+}
+
+int ehmm_rc_apply_at(ehmm_session *s, int differential, double p, const int64_t *col_offsets, int64_t total) {
+    EHMM_TRY(check_session(s));
+    EHMM_REQUIRE(col_offsets && total >= 0, EHMM_ERR_ARG, "bad arguments");
+    return rc_apply_at(s, differential, p, col_offsets, total);
+}
+
+int ehmm_rc_buckets_device(ehmm_session *s, void **ptr, int64_t *n) {
+    EHMM_REQUIRE(s && ptr && n, EHMM_ERR_ARG, "null pointer");
+    EHMM_REQUIRE(s->rc_columns > 0, EHMM_ERR_STATE, "no rejection tables");
+    *ptr = s->rc_buckets.p;
+    *n = (int64_t)s->rc_columns * (s->G + 1);
+    return EHMM_OK;
+}
+
+int ehmm_inner_mstep_sums(ehmm_session *s, double *sums) {
+    EHMM_TRY(check_session(s));
+    EHMM_REQUIRE(sums, EHMM_ERR_ARG, "null output");
+    return inner_mstep_sums(s, sums);
 }
 
 int ehmm_rc_table_rows(ehmm_session *s, int column, int64_t *rows) {

@@ -138,6 +138,11 @@ class Session:
         check(lib.ehmm_estep_stats(self._h, dptr(st)))
         return st
 
+    def fetch_logprob1_row0(self):
+        r = np.empty(self.K)
+        check(lib.ehmm_estep_row0(self._h, dptr(r)))
+        return r
+
     def estep_set_stats(self, stats, lp1_row0, loglik):
         check(lib.ehmm_estep_set_stats(self._h, dptr(_f64(stats)), dptr(_f64(lp1_row0)), float(loglik)))
 
@@ -201,6 +206,29 @@ class Session:
         check(lib.ehmm_rc_differential(self._h, float(p), self.N, dptr(u), 0 if u is None else u.size, C.byref(n)))
         self.rc_columns = self.B + 2
         return n.value
+
+    def rc_count(self, p, differential=False):
+        cols = self.B + 2 if differential else self.K
+        cnt = np.zeros(cols, dtype=np.int64)
+        check(lib.ehmm_rc_count(self._h, 1 if differential else 0, float(p), cnt.ctypes.data_as(C.POINTER(C.c_int64))))
+        return cnt
+
+    def rc_apply_at(self, p, col_offsets, total, differential=False):
+        off = np.ascontiguousarray(col_offsets, dtype=np.int64)
+        check(lib.ehmm_rc_apply_at(self._h, 1 if differential else 0, float(p), off.ctypes.data_as(C.POINTER(C.c_int64)),
+                                   int(total)))
+        self.rc_columns = off.size
+
+    def rc_buckets_device(self):
+        """(device pointer, element count) of the dense bucket sums"""
+        p, n = C.c_void_p(), C.c_int64()
+        check(lib.ehmm_rc_buckets_device(self._h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def inner_mstep_sums(self):
+        out = np.empty(self.B + 1)
+        check(lib.ehmm_inner_mstep_sums(self._h, dptr(out)))
+        return out
 
     def rc_table(self, column):
         """(rows x 2) matrix of (weight sum, group id): one element of the reference's field<mat>."""

@@ -1,0 +1,202 @@
+"""Bin-block sharding of one EM fit across GPUs (one process per GPU, torch.distributed).
+
+The reference treats the whole genome as ONE Markov chain (R/base-core.R:181-183, src/expStep.cpp:
+69-83), so GPUs hold contiguous bin blocks and exchange what keeps the result identical to the
+single-process run:
+
+* E-step: every block reduces to one scaled K x K operator (``ehmm_expstep_reduce``); the P
+  operators are all-gathered (P*(K*K+1) doubles), each rank forms its forward carry
+  ``pi * prod(ops[:r])`` and backward carry ``prod(ops[r+1:]) * 1`` on the host and applies them
+  (``ehmm_expstep_apply``).  Sufficient statistics are all-reduced; the log-likelihood comes from
+  the last block, pi's posterior row from the first.
+* Rejection control: R draws uniforms column-major, then in ascending global bin order, so the
+  per-column flagged counts are all-gathered and each rank consumes its own slice of the single
+  Mersenne-Twister stream (``ehmm_rc_count`` / ``ehmm_rc_apply_at``); bucket sums are all-reduced
+  in place in HBM, after which every rank holds the complete rejection tables and evaluates the
+  NB-GLM objective redundantly (no further communication in the optimiser loop).
+
+Everything exchanged is a few hundred bytes except the bucket vectors (columns x (G+1) doubles).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .session import Session
+
+
+# ---- scaled operator algebra on the host (tiny: P operators of K x K) --------------------------
+
+def _renorm(m, ls):
+    mx = float(np.max(m))
+    if not (mx > 0.0) or not np.isfinite(mx):
+        return m, ls
+    e = np.floor(np.log2(mx))
+    return m * 2.0 ** (-e), ls + e * np.log(2.0)
+
+
+def combine_carries(ops, rank, start, K):
+    """ops: (P, K*K+1) block operators (row-major mantissa + log scale); start: (K+1,) forward vector
+    entering block 0 (pi, 0).  Returns (fwd, bwd) for block `rank`, each (K+1,)."""
+    ops = np.asarray(ops, dtype=np.float64)
+    v, ls = np.array(start[:K], dtype=np.float64), float(start[K])
+    for r in range(rank):
+        v, ls = _renorm(v @ ops[r, :K * K].reshape(K, K), ls + ops[r, K * K])
+    u, lu = np.ones(K), 0.0
+    for r in range(ops.shape[0] - 1, rank, -1):
+        u, lu = _renorm(ops[r, :K * K].reshape(K, K) @ u, lu + ops[r, K * K])
+    return np.append(v, ls), np.append(u, lu)
+
+
+def rc_offsets(all_counts, rank):
+    """all_counts: (P, C) flagged counts per block and column.  R's order is column-major, then
+    ascending bin, so block r's column c starts after all columns < c and blocks < r of column c."""
+    all_counts = np.asarray(all_counts, dtype=np.int64)
+    col_tot = all_counts.sum(axis=0)
+    col_base = np.concatenate([[0], np.cumsum(col_tot)[:-1]])
+    before = all_counts[:rank].sum(axis=0)
+    return col_base + before, int(col_tot.sum())
+
+
+class TorchComm:
+    """the handful of collectives the sharded driver needs, over torch.distributed (nccl or gloo)"""
+
+    def __init__(self, dist, device=None):
+        import torch
+        self.torch, self.dist = torch, dist
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.device = device if dist.get_backend() == "nccl" else "cpu"
+
+    def all_gather(self, a):
+        t = self.torch.as_tensor(np.ascontiguousarray(a)).to(self.device)
+        out = [self.torch.empty_like(t) for _ in range(self.world)]
+        self.dist.all_gather(out, t)
+        return np.stack([o.cpu().numpy() for o in out])
+
+    def all_reduce_sum(self, a):
+        t = self.torch.as_tensor(np.ascontiguousarray(a)).to(self.device)
+        self.dist.all_reduce(t)
+        return t.cpu().numpy()
+
+    def broadcast(self, a, src):
+        t = self.torch.as_tensor(np.ascontiguousarray(a)).to(self.device)
+        self.dist.broadcast(t, src)
+        return t.cpu().numpy()
+
+    def all_reduce_device(self, ptr, n):
+        """in-place sum of n doubles at device pointer ptr (NCCL over NVLink)"""
+        class _Buf:
+            __cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 3}
+        t = self.torch.as_tensor(_Buf(), device=self.device)
+        self.dist.all_reduce(t)
+        self.torch.cuda.current_stream().synchronize()
+
+
+def global_groups(counts, offsets, comm, m0, Mtot, controls=None, design=None):
+    """dt$Group over the whole sharded table: every rank gets the same dictionary, numbered by first
+    appearance in the column-major global table exactly as data.table's .GRP (R/base-core.R:97,187)."""
+    from .synth import make_groups
+    loc = make_groups(counts, offsets, controls, design)
+    M, N = np.asarray(counts).shape
+    # first appearance of each local group as a global column-major cell index
+    g = loc["group"].ravel(order="F")
+    first_local = np.full(loc["G"], M * N, dtype=np.int64)
+    np.minimum.at(first_local, g - 1, np.arange(M * N, dtype=np.int64))
+    first_global = (first_local // M) * Mtot + m0 + (first_local % M)
+    cols = [loc["u_chip"], loc["u_offsets"]]
+    if controls is not None:
+        cols.append(loc["u_controls"])
+    if design is not None:
+        cols.append(first_local // M)  # the sample decides the Dsg.Mix columns
+    rec = np.column_stack(cols + [first_global.astype(np.float64)])
+    sizes = comm.all_gather(np.array([rec.shape[0]], dtype=np.int64)).ravel()
+    pad = np.full((int(sizes.max()), rec.shape[1]), np.nan)
+    pad[:rec.shape[0]] = rec
+    allrec = comm.all_gather(pad)
+    rows = np.concatenate([allrec[r, :sizes[r]] for r in range(comm.world)])
+    key = rows[:, :-1].copy()
+    if design is not None:  # samples with equal design columns share groups
+        _, dcode = np.unique(np.asarray(design).T, axis=0, return_inverse=True)
+        key[:, -1] = np.asarray(dcode).ravel()[key[:, -1].astype(np.int64)]
+    uk, inv = np.unique(key, axis=0, return_inverse=True)
+    inv = np.asarray(inv).ravel()
+    first = np.full(uk.shape[0], np.inf)
+    np.minimum.at(first, inv, rows[:, -1])
+    order = np.argsort(first, kind="stable")
+    rank_of = np.empty(order.size, dtype=np.int64)
+    rank_of[order] = np.arange(order.size)
+    gid = rank_of[inv] + 1                      # global id of every gathered record
+    start = int(sizes[:comm.rank].sum())
+    mine = gid[start:start + loc["G"]]          # local group -> global id
+    out = dict(group=np.asfortranarray(mine[loc["group"] - 1].astype(np.int32)), G=int(order.size))
+    rep = np.empty(order.size, dtype=np.int64)  # one gathered record per global group
+    rep[gid - 1] = np.arange(gid.size)
+    out["u_chip"], out["u_offsets"] = rows[rep, 0].copy(), rows[rep, 1].copy()
+    out["u_controls"] = rows[rep, 2].copy() if controls is not None else None
+    if design is not None:
+        samp = rows[rep, -2].astype(np.int64)
+        out["u_dsg"] = np.asfortranarray(np.asarray(design, dtype=np.uint8).T[samp])
+    else:
+        out["u_dsg"] = None
+    return out
+
+
+class ShardedSession:
+    """Session-compatible backend for epigrahmm_b200.em over one bin block per rank."""
+
+    def __init__(self, key, M, K, device, dist, local=None, comm=None):
+        self.comm = comm or TorchComm(dist, device="cuda:%d" % device)
+        self.rank, self.world = self.comm.rank, self.comm.world
+        sizes = self.comm.all_gather(np.array([M], dtype=np.int64)).ravel()
+        self.Mtot, self.m0 = int(sizes.sum()), int(sizes[:self.rank].sum())
+        self.local = local if local is not None else Session("%s.rank%d" % (key, self.rank), M, K, device)
+        self.local.set_block(self.m0, self.Mtot)
+        self.M, self.K = M, K
+
+    # plain delegation -----------------------------------------------------------------------
+    def __getattr__(self, name):
+        return getattr(self.local, name)
+
+    def close(self):
+        self.local.close()
+
+    # E-step ----------------------------------------------------------------------------------
+    def expstep(self, pi, gamma, logf=None):
+        K = self.K
+        op = self.local.expstep_reduce(pi, gamma, logf)
+        ops = self.comm.all_gather(op)
+        fwd, bwd = combine_carries(ops, self.rank, np.append(np.asarray(pi, dtype=np.float64), 0.0), K)
+        tail = self.local.expstep_apply(fwd, bwd)          # forward vector after this block
+        stats = self.comm.all_reduce_sum(self.local.estep_stats())
+        row0 = self.comm.broadcast(self.local.fetch_logprob1_row0(), 0)
+        ll_local = float(tail[K] + np.log(np.sum(tail[:K])))
+        ll = float(self.comm.broadcast(np.array([ll_local]), self.world - 1)[0])
+        self.local.estep_set_stats(stats, row0, ll)
+
+    # rejection control -----------------------------------------------------------------------
+    def _rc(self, p, differential):
+        cnt = self.local.rc_count(p, differential)
+        offs, total = rc_offsets(self.comm.all_gather(cnt), self.rank)
+        self.local.rc_apply_at(p, offs, total, differential)
+        if hasattr(self.local, "rc_buckets_host"):   # host-resident backend (CPU tests)
+            self.local.rc_buckets_set(self.comm.all_reduce_sum(self.local.rc_buckets_host()))
+        else:
+            ptr, n = self.local.rc_buckets_device()
+            self.comm.all_reduce_device(ptr, n)
+        return total
+
+    def rc_consensus(self, p, uniforms=None):
+        if uniforms is not None:
+            raise ValueError("the sharded driver draws from the device generator")
+        return self._rc(p, False)
+
+    def rc_differential(self, p, uniforms=None):
+        if uniforms is not None:
+            raise ValueError("the sharded driver draws from the device generator")
+        return self._rc(p, True)
+
+    def inner_maxstepprob(self):
+        s = self.comm.all_reduce_sum(self.local.inner_mstep_sums())
+        return s[:-1] / s[-1]
+
+    def viterbi(self, pi, gamma, fetch=True):
+        raise NotImplementedError("Viterbi runs on the whole chain: gather logFP into one Session")

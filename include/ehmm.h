@@ -97,6 +97,8 @@ int ehmm_qfunction(ehmm_session *s, const double *pi, const double *gamma, doubl
 int ehmm_bic(ehmm_session *s, int numPar, int numSamples, double *bic);
 /* innerMaxStepProb, src/innerMaxStepProb.cpp:15-38. */
 int ehmm_inner_maxstepprob(ehmm_session *s, double *delta_out);
+/* additive form for bin blocks: sums[b] = sum_j P1[j,1] eta[j,b] (b < B), sums[B] = sum_j P1[j,1]. */
+int ehmm_inner_mstep_sums(ehmm_session *s, double *sums);
 /* getMarginalProbability, src/getMarginalProbability.cpp:12-21 (out: M x K). */
 int ehmm_marginal_probability(ehmm_session *s, double *out);
 /* computeViterbiSequence, src/computeViterbiSequence.cpp:12-54 (states_out: M doubles or NULL). */
@@ -110,6 +112,8 @@ int ehmm_expstep_reduce(ehmm_session *s, const double *pi, const double *gamma, 
 int ehmm_expstep_apply(ehmm_session *s, const double *fwd_carry, const double *bwd_carry, double *fwd_out);
 /* raw sufficient statistics of the last expStep: K*K joint sums (j >= 1) then sum(P1 * logf). */
 int ehmm_estep_stats(ehmm_session *s, double *stats);
+/* logProb1[0,] of this block (K doubles): maxStepProb's pi comes from the first block's row. */
+int ehmm_estep_row0(ehmm_session *s, double *row0);
 int ehmm_estep_set_stats(ehmm_session *s, const double *stats, const double *logprob1_row0, double loglik);
 
 /* ---- rejection control (src/reweight.cpp, rbinomVectorized.cpp, aggregate.cpp) ---- */
@@ -122,6 +126,15 @@ int ehmm_rng_get_state(ehmm_session *s, uint32_t *state625);
 int ehmm_rc_consensus(ehmm_session *s, double p, const double *uniforms, int64_t n_uniforms, int64_t *consumed);
 /* differentialRejectionControlled, src/differentialRejectionControlled.cpp:14-48. */
 int ehmm_rc_differential(ehmm_session *s, double p, int N, const double *uniforms, int64_t n_uniforms, int64_t *consumed);
+/* Sharded form (bin blocks across GPUs; the draw order is global: column-major, then ascending
+ * global bin).  ehmm_rc_count returns this block's flagged counts per column; after the caller has
+ * combined the counts of all blocks, ehmm_rc_apply_at thins and aggregates this block with its
+ * column c draws starting at stream offset col_offsets[c] (relative to the current RNG position)
+ * and advances the stream by `total` draws.  differential = 0: K columns; 1: B + 2 columns. */
+int ehmm_rc_count(ehmm_session *s, int differential, double p, int64_t *counts);
+int ehmm_rc_apply_at(ehmm_session *s, int differential, double p, const int64_t *col_offsets, int64_t total);
+/* device pointer to the dense bucket sums (columns x (G+1) doubles), e.g. for an NCCL all-reduce. */
+int ehmm_rc_buckets_device(ehmm_session *s, void **ptr, int64_t *n);
 /* the field<mat> result: table `column` has `rows` (sum, id) pairs with non-zero sum, ascending id. */
 int ehmm_rc_table_rows(ehmm_session *s, int column, int64_t *rows);
 int ehmm_rc_table_fetch(ehmm_session *s, int column, double *sums, double *ids);
