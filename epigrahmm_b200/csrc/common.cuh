@@ -138,6 +138,8 @@ struct ehmm_session {
 
     // ---- emission / GLM scratch ----
     ehmm::DevBuf lgtab, glm_part, misc, gtab;
+    bool encoded = false;       // data given as dt$Group + dtUnique only (no count / offset matrices)
+    bool encoded_ctrl = false;
     bool groups_consistent = false;  // dtUnique[group] reproduces (counts, offsets[, controls]) cell by cell
     int64_t count_max = -1;
     double *h_pinned = nullptr;  // small pinned staging buffer (1024 doubles; [512..] = RNG state)

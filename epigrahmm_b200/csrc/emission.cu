@@ -276,7 +276,8 @@ int grid_for(int64_t M) {
 }
 
 int require_data(ehmm_session *s, const char *who) {
-    EHMM_REQUIRE(s->d_counts && s->d_offsets && s->N > 0, EHMM_ERR_STATE, "%s: ehmm_set_data has not been called", who);
+    EHMM_REQUIRE(s->N > 0 && (s->encoded || (s->d_counts && s->d_offsets)), EHMM_ERR_STATE,
+                 "%s: ehmm_set_data has not been called", who);
     return EHMM_OK;
 }
 
@@ -348,7 +349,7 @@ int emis_consensus(ehmm_session *s, const double *th1, const double *th2, int P_
     EHMM_TRY(require_data(s, "loglikConsensusHMM"));
     EHMM_REQUIRE(s->K == 2, EHMM_ERR_ARG, "loglikConsensusHMM needs a K=2 session (K=%d)", s->K);
     EHMM_REQUIRE(P_ == 2 || P_ == 3, EHMM_ERR_ARG, "P must be 2 (beta0,size) or 3 (beta0,beta_ctrl,size)");
-    EHMM_REQUIRE(P_ == 2 || s->d_controls, EHMM_ERR_STATE, "P=3 needs a controls matrix");
+    EHMM_REQUIRE(P_ == 2 || s->d_controls || (s->encoded && s->encoded_ctrl), EHMM_ERR_STATE, "P=3 needs a controls matrix");
     EmisParams P = {};
     fill_density(P, 0, th1[0], P_ == 3 ? th1[1] : 0.0, th1[P_ - 1]);
     fill_density(P, 1, th2[0], P_ == 3 ? th2[1] : 0.0, th2[P_ - 1]);

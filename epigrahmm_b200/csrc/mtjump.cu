@@ -3,7 +3,7 @@
 // rbinom() in the reference consumes unif_rand() draws one by one (src/rbinomVectorized.cpp:17);
 // at 15 M bins that is ~1.5e7 draws per EM iteration and a single sequential MT19937 is the
 // slowest step of the iteration.  MT19937 is GF(2)-linear, so sub-stream s (words
-// [1 + s*J, 1 + (s+1)*J) of the stream, J = 2^18) can start from a window obtained by jumping
+// [1 + s*J, 1 + (s+1)*J) of the stream, J = 2^17) can start from a window obtained by jumping
 // ahead: w[m + J*2^k] = XOR_{i : c_i = 1} w[m + i] with c = x^(J*2^k) mod phi (mtpoly.h).
 //   mt_jump_kernel     : round k doubles the number of known windows (window 2^k + c from window c)
 //   mt_generate_kernel : one CTA per sub-stream runs the recurrence (227-wide) and writes tempered
@@ -19,9 +19,9 @@ namespace ehmm {
 
 namespace {
 
-constexpr int LOG2J = 18;
+constexpr int LOG2J = 17;
 constexpr int64_t JW = (int64_t)1 << LOG2J;  // words per sub-stream
-constexpr int LEVELS = 14;                   // up to 2^14 sub-streams = 4.3e9 draws per call
+constexpr int LEVELS = 15;                   // up to 2^15 sub-streams = 4.3e9 draws per call
 constexpr int MT_N = 624, MT_M = 397, MT_D = MT_N - MT_M;  // 227
 constexpr int EXPW = mtpoly::DEG + MT_N - 1;               // words a jump needs (20560)
 constexpr int JUMP_NT = 320;

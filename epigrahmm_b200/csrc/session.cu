@@ -76,6 +76,44 @@ int scan_counts(ehmm_session *s) {
     return EHMM_OK;
 }
 
+// dtUnique columns are stored with a leading unused slot so that the 1-based group id indexes them
+int upload_unique(ehmm_session *s, int64_t G, const double *u_chip, const double *u_offsets, const double *u_controls,
+                  const uint8_t *u_dsg) {
+    const size_t gb = (size_t)(G + 1) * sizeof(double);
+    EHMM_TRY(s->u_chip.reserve(gb));
+    EHMM_TRY(s->u_off.reserve(gb));
+    EHMM_CK(cudaMemsetAsync(s->u_chip.p, 0, sizeof(double), s->stream));
+    EHMM_CK(cudaMemsetAsync(s->u_off.p, 0, sizeof(double), s->stream));
+    EHMM_CK(cudaMemcpyAsync(s->u_chip.as<double>() + 1, u_chip, gb - sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    EHMM_CK(cudaMemcpyAsync(s->u_off.as<double>() + 1, u_offsets, gb - sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    if (u_controls) {
+        EHMM_TRY(s->u_ctrl.reserve(gb));
+        EHMM_CK(cudaMemsetAsync(s->u_ctrl.p, 0, sizeof(double), s->stream));
+        EHMM_CK(cudaMemcpyAsync(s->u_ctrl.as<double>() + 1, u_controls, gb - sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    } else {
+        s->u_ctrl.release();
+    }
+    if (u_dsg) {
+        EHMM_REQUIRE(s->B > 0, EHMM_ERR_STATE, "set_groups: Dsg.Mix columns given before ehmm_set_design");
+        // host layout G x B column-major -> device (G+1) x B column-major
+        EHMM_TRY(s->u_dsg.reserve((size_t)(G + 1) * s->B));
+        EHMM_CK(cudaMemsetAsync(s->u_dsg.p, 0, (size_t)(G + 1) * s->B, s->stream));
+        for (int b = 0; b < s->B; b++)
+            EHMM_CK(cudaMemcpyAsync(s->u_dsg.as<uint8_t>() + (size_t)b * (G + 1) + 1, u_dsg + (size_t)b * G, (size_t)G,
+                                    cudaMemcpyHostToDevice, s->stream));
+    }
+    return EHMM_OK;
+}
+
+__global__ void group_range_kernel(int64_t n, const int32_t *__restrict__ group, int64_t G, int *__restrict__ bad) {
+    int b = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t g = group[i];
+        if (g < 1 || g > G) b = 1;
+    }
+    if (b) atomicOr(bad, 1);
+}
+
 struct DS {
     ehmm::DevBuf *buf;
     int64_t rows, cols;
@@ -249,6 +287,7 @@ int ehmm_set_data(ehmm_session *s, int N, const int32_t *counts, const double *o
     }
     s->N = N;
     s->groups_consistent = false;
+    s->encoded = false;
     s->d_counts = s->counts_own.as<int32_t>();
     s->d_offsets = s->offsets_own.as<double>();
     s->d_controls = dc;
@@ -260,6 +299,7 @@ int ehmm_set_data_device(ehmm_session *s, int N, const int32_t *counts, const do
     EHMM_REQUIRE(N >= 1 && counts && offsets, EHMM_ERR_ARG, "set_data: N >= 1, counts and offsets required");
     s->N = N;
     s->groups_consistent = false;
+    s->encoded = false;
     s->d_counts = counts;
     s->d_offsets = offsets;
     s->d_controls = controls;
@@ -269,35 +309,12 @@ int ehmm_set_data_device(ehmm_session *s, int N, const int32_t *counts, const do
 int ehmm_set_groups(ehmm_session *s, const int32_t *group, int64_t G, const double *u_chip, const double *u_offsets,
                     const double *u_controls, const uint8_t *u_dsg) {
     EHMM_TRY(check_session(s));
-    EHMM_REQUIRE(s->N > 0, EHMM_ERR_STATE, "set_groups: call ehmm_set_data first");
+    EHMM_REQUIRE(s->N > 0 && !s->encoded, EHMM_ERR_STATE, "set_groups: call ehmm_set_data first");
     EHMM_REQUIRE(group && G >= 1 && u_chip && u_offsets, EHMM_ERR_ARG, "set_groups: group, G, ChIP and offsets required");
     const size_t n = (size_t)s->M * s->N;
     EHMM_TRY(s->group.reserve(n * sizeof(int32_t)));
     EHMM_CK(cudaMemcpyAsync(s->group.p, group, n * sizeof(int32_t), cudaMemcpyHostToDevice, s->stream));
-    // dtUnique columns are stored with a leading unused slot so that the 1-based group id indexes them
-    const size_t gb = (size_t)(G + 1) * sizeof(double);
-    EHMM_TRY(s->u_chip.reserve(gb));
-    EHMM_TRY(s->u_off.reserve(gb));
-    EHMM_CK(cudaMemsetAsync(s->u_chip.p, 0, sizeof(double), s->stream));
-    EHMM_CK(cudaMemsetAsync(s->u_off.p, 0, sizeof(double), s->stream));
-    EHMM_CK(cudaMemcpyAsync(s->u_chip.as<double>() + 1, u_chip, gb - sizeof(double), cudaMemcpyHostToDevice, s->stream));
-    EHMM_CK(cudaMemcpyAsync(s->u_off.as<double>() + 1, u_offsets, gb - sizeof(double), cudaMemcpyHostToDevice, s->stream));
-    if (u_controls) {
-        EHMM_TRY(s->u_ctrl.reserve(gb));
-        EHMM_CK(cudaMemsetAsync(s->u_ctrl.p, 0, sizeof(double), s->stream));
-        EHMM_CK(cudaMemcpyAsync(s->u_ctrl.as<double>() + 1, u_controls, gb - sizeof(double), cudaMemcpyHostToDevice, s->stream));
-    } else {
-        s->u_ctrl.release();
-    }
-    if (u_dsg) {
-        EHMM_REQUIRE(s->B > 0, EHMM_ERR_STATE, "set_groups: Dsg.Mix columns given before ehmm_set_design");
-        // host layout G x B column-major -> device (G+1) x B column-major
-        EHMM_TRY(s->u_dsg.reserve((size_t)(G + 1) * s->B));
-        EHMM_CK(cudaMemsetAsync(s->u_dsg.p, 0, (size_t)(G + 1) * s->B, s->stream));
-        for (int b = 0; b < s->B; b++)
-            EHMM_CK(cudaMemcpyAsync(s->u_dsg.as<uint8_t>() + (size_t)b * (G + 1) + 1, u_dsg + (size_t)b * G, (size_t)G,
-                                    cudaMemcpyHostToDevice, s->stream));
-    }
+    EHMM_TRY(upload_unique(s, G, u_chip, u_offsets, u_controls, u_dsg));
     // validate the ids and find out whether dtUnique matches the data (enables the gather path)
     EHMM_TRY(s->misc.reserve(64));
     int *bad = s->misc.as<int>();
@@ -311,6 +328,55 @@ int ehmm_set_groups(ehmm_session *s, const int32_t *group, int64_t G, const doub
     EHMM_CK(cudaStreamSynchronize(s->stream));
     EHMM_REQUIRE(!(hb & 2), EHMM_ERR_ARG, "set_groups: group ids must lie in [1, G]");
     s->groups_consistent = (hb == 0) && (!s->d_controls || u_controls);
+    s->G = G;
+    s->rc_columns = 0;
+    return EHMM_OK;
+}
+
+int ehmm_set_design_n(ehmm_session *s, int N, int B, const uint8_t *design) {
+    EHMM_TRY(check_session(s));
+    EHMM_REQUIRE(N >= 1 && N <= 64 && B >= 1 && B <= EHMM_MAX_B && design, EHMM_ERR_ARG, "set_design: bad N/B");
+    memcpy(s->design, design, (size_t)B * N);
+    s->N = N;
+    s->B = B;
+    s->have_design = true;
+    return EHMM_OK;
+}
+
+int ehmm_set_data_encoded(ehmm_session *s, int N, const int32_t *group, int64_t G, const double *u_chip,
+                          const double *u_offsets, const double *u_controls, const uint8_t *u_dsg) {
+    EHMM_TRY(check_session(s));
+    EHMM_REQUIRE(N >= 1 && group && G >= 1 && u_chip && u_offsets, EHMM_ERR_ARG, "set_data_encoded: bad arguments");
+    EHMM_REQUIRE((size_t)(G + 1) * 16 <= ((size_t)64 << 20), EHMM_ERR_ARG,
+                 "set_data_encoded: %lld groups exceed the dictionary limit; use ehmm_set_data", (long long)G);
+    double mx = 0;
+    for (int64_t g = 0; g < G; g++) {
+        EHMM_REQUIRE(u_chip[g] >= 0 && u_chip[g] == floor(u_chip[g]) && u_chip[g] < 2147483647.0, EHMM_ERR_ARG,
+                     "set_data_encoded: dtUnique ChIP[%lld] = %g is not a count", (long long)g, u_chip[g]);
+        if (u_chip[g] > mx) mx = u_chip[g];
+    }
+    s->N = N;
+    s->d_counts = nullptr;
+    s->d_offsets = nullptr;
+    s->d_controls = nullptr;
+    s->encoded = true;
+    s->encoded_ctrl = u_controls != nullptr;
+    s->count_max = (int64_t)mx;
+    const size_t n = (size_t)s->M * N;
+    EHMM_TRY(s->group.reserve(n * sizeof(int32_t)));
+    EHMM_CK(cudaMemcpyAsync(s->group.p, group, n * sizeof(int32_t), cudaMemcpyHostToDevice, s->stream));
+    EHMM_TRY(upload_unique(s, G, u_chip, u_offsets, u_controls, u_dsg));
+    EHMM_TRY(s->misc.reserve(64));
+    int *bad = s->misc.as<int>();
+    EHMM_CK(cudaMemsetAsync(bad, 0, sizeof(int), s->stream));
+    PROF(s, KID_MISC), group_range_kernel<<<148 * 8, 256, 0, s->stream>>>((int64_t)n, s->group.as<int32_t>(), G, bad);
+    EHMM_CK(cudaGetLastError());
+    EHMM_CK(cudaMemcpyAsync(s->h_pinned + 300, bad, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    EHMM_CK(cudaStreamSynchronize(s->stream));
+    int hb;
+    memcpy(&hb, s->h_pinned + 300, sizeof(int));
+    EHMM_REQUIRE(hb == 0, EHMM_ERR_ARG, "set_data_encoded: group ids must lie in [1, G]");
+    s->groups_consistent = true;
     s->G = G;
     s->rc_columns = 0;
     return EHMM_OK;

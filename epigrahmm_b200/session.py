@@ -76,6 +76,21 @@ class Session:
                                        C.c_void_p(controls_ptr) if controls_ptr else None))
         self.N = int(N)
 
+    def set_data_encoded(self, group, u_chip, u_offsets, u_controls=None, u_dsg=None, design=None):
+        """upload the table as dt$Group + dtUnique only (the counts/offsets matrices stay on the host)"""
+        g = _cm(group, np.int32)
+        g = g.reshape(self.M, -1, order="F")
+        N = g.shape[1]
+        if design is not None:
+            d = np.ascontiguousarray(design, dtype=np.uint8)
+            check(lib.ehmm_set_design_n(self._h, N, d.shape[0], bptr(d)))
+            self.B = d.shape[0]
+        uc, uo = _f64(u_chip), _f64(u_offsets)
+        uctrl = None if u_controls is None else _f64(u_controls)
+        udsg = None if u_dsg is None else np.asfortranarray(u_dsg, dtype=np.uint8)
+        check(lib.ehmm_set_data_encoded(self._h, N, iptr(g), uc.size, dptr(uc), dptr(uo), dptr(uctrl), bptr(udsg)))
+        self.N, self.G = N, uc.size
+
     def set_design(self, design):
         d = np.ascontiguousarray(design, dtype=np.uint8)
         assert d.ndim == 2 and d.shape[1] == self.N, "design must be B x N"

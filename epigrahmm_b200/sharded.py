@@ -166,11 +166,12 @@ class ShardedSession:
         ops = self.comm.all_gather(op)
         fwd, bwd = combine_carries(ops, self.rank, np.append(np.asarray(pi, dtype=np.float64), 0.0), K)
         tail = self.local.expstep_apply(fwd, bwd)          # forward vector after this block
-        stats = self.comm.all_reduce_sum(self.local.estep_stats())
-        row0 = self.comm.broadcast(self.local.fetch_logprob1_row0(), 0)
         ll_local = float(tail[K] + np.log(np.sum(tail[:K])))
-        ll = float(self.comm.broadcast(np.array([ll_local]), self.world - 1)[0])
-        self.local.estep_set_stats(stats, row0, ll)
+        # one exchange: statistics (summed), logProb1[0,] (first block's), log-likelihood (last block's)
+        packed = self.comm.all_gather(np.concatenate([self.local.estep_stats(), self.local.fetch_logprob1_row0(),
+                                                      [ll_local]]))
+        ns = K * K + 1
+        self.local.estep_set_stats(packed[:, :ns].sum(axis=0), packed[0, ns:ns + K], float(packed[-1, -1]))
 
     # rejection control -----------------------------------------------------------------------
     def _rc(self, p, differential):

@@ -68,6 +68,12 @@ int ehmm_set_data_device(ehmm_session *s, int N, const int32_t *counts, const do
  * [, Dsg.Mix 0/1 as G x B column-major] (R/base-core.R:99-104,190-198). */
 int ehmm_set_groups(ehmm_session *s, const int32_t *group, int64_t G, const double *u_chip, const double *u_offsets,
                     const double *u_controls, const uint8_t *u_dsg);
+/* Dictionary-encoded form of the same table: only dt$Group and dtUnique are uploaded (4 B per cell
+ * instead of 12-20 B); counts/offsets are implied by dtUnique[group].  Replaces ehmm_set_data +
+ * ehmm_set_groups.  For the differential model call ehmm_set_design_n(s, N, B, design) first. */
+int ehmm_set_data_encoded(ehmm_session *s, int N, const int32_t *group, int64_t G, const double *u_chip,
+                          const double *u_offsets, const double *u_controls, const uint8_t *u_dsg);
+int ehmm_set_design_n(ehmm_session *s, int N, int B, const uint8_t *design);
 /* design[b*N + i] = Dsg.Mix_b of sample i (generateMixtureIntercepts, R/base-utils.R:242-264). */
 int ehmm_set_design(ehmm_session *s, int B, const uint8_t *design);
 

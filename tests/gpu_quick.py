@@ -23,6 +23,10 @@ for K in (2, 3):
         e1.record(st)
     s.sync()
     ms = e0.elapsed_time(e1) / 10
+    s.profile(True)
+    for _ in range(5):
+        s.expstep(th["pi"], th["gamma"])
+    print({k: round(v[1] / 5, 4) for k, v in s.profile_read().items() if v[0]})
     byt = M * (48 * K + 8 * K * K)
     print("K=%d M=%d expStep %.3f ms  %.1f GB/s (algorithmic %d B/bin)  ll=%.6f" % (K, M, ms, byt / ms / 1e6, 48 * K + 8 * K * K, s.loglik()))
     s.close()

@@ -243,3 +243,36 @@ def test_dictionary_encoded_emission_is_bit_identical(ehmm, model):
         c = s.fetch("logLikelihood")
         assert s.profile_read()["emis_gather"][0] == 0
     assert np.array_equal(a, b) and np.array_equal(a, c)
+
+
+@pytest.mark.parametrize("model", ["consensus", "differential"])
+def test_dictionary_encoded_upload(ehmm, model):
+    """ehmm_set_data_encoded (dt$Group + dtUnique only) gives the same emission as the full table"""
+    M = 20011
+    if model == "consensus":
+        d = synth.make_consensus(M, 3, seed=51, controls=True)
+        g = synth.make_groups(d["counts"], d["offsets"], d["controls"])
+        psi = [np.array([np.log(2.0), 0.3, 3.0]), np.array([np.log(12.0), 0.1, 4.0])]
+        with ehmm.Session("t_enc_a", M, 2) as a, ehmm.Session("t_enc_b", M, 2) as b:
+            a.set_data(d["counts"], d["offsets"], d["controls"])
+            a.loglik_consensus(psi, MINZERO)
+            b.set_data_encoded(g["group"], g["u_chip"], g["u_offsets"], g["u_controls"])
+            b.loglik_consensus(psi, MINZERO)
+            assert np.array_equal(a.fetch("logLikelihood"), b.fetch("logLikelihood"))
+            with pytest.raises(ehmm.EhmmError):
+                b.set_data_encoded(g["group"] + g["G"], g["u_chip"], g["u_offsets"], g["u_controls"])  # ids out of range
+    else:
+        d = synth.make_differential(M, 3, 2, seed=52)
+        g = synth.make_groups(d["counts"], d["offsets"], design=d["design"])
+        delta = np.full(d["B"], 1.0 / d["B"])
+        psi = synth.THETA_DIFFERENTIAL["psi"]
+        with ehmm.Session("t_enc_a", M, 3) as a, ehmm.Session("t_enc_b", M, 3) as b:
+            a.set_data(d["counts"], d["offsets"])
+            a.set_design(d["design"])
+            a.loglik_differential_hmm(delta, psi, MINZERO)
+            a.inner_expstep(delta, psi, MINZERO)
+            b.set_data_encoded(g["group"], g["u_chip"], g["u_offsets"], None, g["u_dsg"], design=d["design"])
+            b.loglik_differential_hmm(delta, psi, MINZERO)
+            b.inner_expstep(delta, psi, MINZERO)
+            assert np.array_equal(a.fetch("logLikelihood"), b.fetch("logLikelihood"))
+            assert np.array_equal(a.fetch("mixtureProb"), b.fetch("mixtureProb"))
