@@ -51,6 +51,7 @@ PROTOTYPES = {
     "ehmm_set_data_device": [_sess, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p],
     "ehmm_set_groups": [_sess, _ip, C.c_int64, _dp, _dp, _dp, _bp],
     "ehmm_set_data_encoded": [_sess, C.c_int, _ip, C.c_int64, _dp, _dp, _dp, _bp],
+    "ehmm_set_data_encoded16": [_sess, C.c_int, C.POINTER(C.c_uint16), C.c_int64, _dp, _dp, _dp, _bp],
     "ehmm_set_design_n": [_sess, C.c_int, C.c_int, _bp],
     "ehmm_set_design": [_sess, C.c_int, _bp],
     "ehmm_loglik_consensus": [_sess, _dp, _dp, C.c_int, C.c_double],
@@ -85,6 +86,7 @@ PROTOTYPES = {
     "ehmm_reweight": [C.c_int, _dp, C.c_int64, C.c_double, _dp, C.c_int64, _lp],
     "ehmm_aggregate": [C.c_int, _dp, C.c_int64, _ip, C.c_int64, _dp],
     "ehmm_glm_nb": [_sess, C.c_int, _dp, C.c_int, _dp, _dp],
+    "ehmm_glm_nb_batch": [_sess, C.c_int, C.POINTER(C.c_int), _dp, C.c_int, _dp, _dp],
     "ehmm_glm_mix_nb": [_sess, _dp, C.c_double, _dp, _dp],
     "ehmm_profile_kernels": [],
     "ehmm_profile_name": [C.c_int],

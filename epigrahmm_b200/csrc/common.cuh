@@ -137,7 +137,8 @@ struct ehmm_session {
     int rc_count_cols = 0;
 
     // ---- emission / GLM scratch ----
-    ehmm::DevBuf lgtab, glm_part, misc, gtab;
+    ehmm::DevBuf lgtab, glm_part, glm_ticket, misc, gtab;
+    bool glm_ticket_ready = false;
     bool encoded = false;       // data given as dt$Group + dtUnique only (no count / offset matrices)
     bool encoded_ctrl = false;
     bool groups_consistent = false;  // dtUnique[group] reproduces (counts, offsets[, controls]) cell by cell
@@ -222,6 +223,7 @@ int mt_advance(ehmm_session *s, int64_t n);
 int mt_prefetch(ehmm_session *s, int64_t max_draws);
 // glm.cu
 int glm_nb(ehmm_session *s, int column, const double *par, int P, double *value, double *grad);
+int glm_nb_batch(ehmm_session *s, int ncols, const int *columns, const double *pars, int P, double *values, double *grads);
 int glm_mix_nb(ehmm_session *s, const double *par, double minZero, double *value, double *grad);
 // viterbi.cu
 int viterbi(ehmm_session *s, const double *pi, const double *gamma, double *states_out);

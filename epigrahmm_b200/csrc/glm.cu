@@ -78,6 +78,78 @@ __global__ void __launch_bounds__(GLM_NT)
     block_store<4>(acc, part);
 }
 
+// Batched form: blockIdx.y selects the (column, parameter) pair, so the optimiser can evaluate all
+// states in one launch; the last block to finish (ticket counter) reduces the per-block partials in
+// a fixed order, so no second launch is needed and the result is deterministic.
+struct NBBatch {
+    NBPar par[EHMM_MAX_K];
+    int column[EHMM_MAX_K];
+};
+
+__global__ void __launch_bounds__(GLM_NT)
+    glm_nb_batch_kernel(int64_t G, const double *__restrict__ buckets, const double *__restrict__ y,
+                        const double *__restrict__ off, const double *__restrict__ ctrl, NBBatch B,
+                        double *__restrict__ part, unsigned *__restrict__ ticket, double *__restrict__ out) {
+    const int q = blockIdx.y;
+    const NBPar P = B.par[q];
+    const double *wt = buckets + (size_t)B.column[q] * (G + 1);
+    double acc[4] = {0, 0, 0, 0};
+    for (int64_t g = 1 + (int64_t)blockIdx.x * GLM_NT + threadIdx.x; g <= G; g += (int64_t)gridDim.x * GLM_NT) {
+        const double w = wt[g];
+        if (w == 0.0) continue;
+        const double yy = y[g], cv = P.has_ctrl ? ctrl[g] : 0.0;
+        const double eta = (P.has_ctrl ? (P.b0 + cv * P.b1) : P.b0) + off[g];
+        const double mu = exp(eta);
+        double l = nb_logpmf_direct(yy, eta, P.size, P.lsize, P.lgs);
+        if (isinf(l)) l = -690.77552789821368;
+        const double den = 1.0 + P.phi * mu;
+        const double r = (yy - mu) / den;
+        const double dphi = (log(den) + P.phi * (yy - mu) / den - digamma_pos(yy + P.size) + P.dg_size) / (P.phi * P.phi);
+        acc[0] += w * l;
+        acc[1] += w * r;
+        acc[2] += w * r * cv;
+        acc[3] += w * dphi;
+    }
+    double *mypart = part + (size_t)q * gridDim.x * 4;
+    {
+        __shared__ double sh[(GLM_NT / 32) * 4];
+        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) acc[i] += __shfl_down_sync(0xffffffffu, acc[i], d);
+            if (lane == 0) sh[w * 4 + i] = acc[i];
+        }
+        __syncthreads();
+        if (threadIdx.x < 4) {
+            double t = sh[threadIdx.x];
+            for (int i = 1; i < GLM_NT / 32; i++) t += sh[i * 4 + threadIdx.x];
+            mypart[(size_t)blockIdx.x * 4 + threadIdx.x] = t;
+        }
+    }
+    __shared__ bool is_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(ticket + q, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (is_last) {
+        __shared__ double red[GLM_NT];
+        for (int c = 0; c < 4; c++) {
+            double t = 0.0;
+            for (int i = threadIdx.x; i < (int)gridDim.x; i += GLM_NT) t += __ldcg(mypart + (size_t)i * 4 + c);
+            red[threadIdx.x] = t;
+            __syncthreads();
+            for (int d = GLM_NT / 2; d > 0; d >>= 1) {
+                if ((int)threadIdx.x < d) red[threadIdx.x] += red[threadIdx.x + d];
+                __syncthreads();
+            }
+            if (threadIdx.x == 0) out[q * 4 + c] = red[0];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) ticket[q] = 0u;
+    }
+}
+
 struct MixPar {
     double b, db, l, dl, minZero, thr;
     double size[2], lsize[2], lgs[2], dg[2];  // D = 0 / 1
@@ -162,33 +234,60 @@ int finish(ehmm_session *s, int nblk, int nout, double *host_out) {
 
 }  // namespace
 
+int glm_nb_batch(ehmm_session *s, int ncols, const int *columns, const double *pars, int P_, double *values,
+                 double *grads);
+
 int glm_nb(ehmm_session *s, int column, const double *par, int P_, double *value, double *grad) {
+    return glm_nb_batch(s, 1, &column, par, P_, value, grad);
+}
+
+int glm_nb_batch(ehmm_session *s, int ncols, const int *columns, const double *pars, int P_, double *values,
+                 double *grads) {
     EHMM_REQUIRE(P_ == 1 || P_ == 2, EHMM_ERR_ARG, "glmNB: P must be 1 (Intercept) or 2 (Intercept, controls)");
     EHMM_REQUIRE(P_ == 1 || s->u_ctrl.p, EHMM_ERR_STATE, "glmNB: dtUnique has no controls column");
-    const double phi = par[P_];
-    EHMM_REQUIRE(phi > 0 && isfinite(phi), EHMM_ERR_ARG, "glmNB: dispersion %g must be positive", phi);
-    NBPar P;
-    P.b0 = par[0];
-    P.b1 = P_ == 2 ? par[1] : 0.0;
-    P.phi = phi;
-    P.size = 1.0 / phi;
-    P.lsize = log(P.size);
-    P.lgs = lgamma(P.size);
-    P.dg_size = host_digamma(P.size);
-    P.has_ctrl = (P_ == 2);
-    EHMM_TRY(s->glm_part.reserve(sizeof(double) * ((size_t)148 * 4 * GLM_MAXOUT + GLM_MAXOUT)));
+    EHMM_REQUIRE(ncols >= 1 && ncols <= EHMM_MAX_K, EHMM_ERR_ARG, "glmNB batch: 1..%d evaluations", EHMM_MAX_K);
+    NBBatch B;
+    for (int q = 0; q < ncols; q++) {
+        const double *par = pars + (size_t)q * (P_ + 1);
+        EHMM_REQUIRE(columns[q] >= 0 && columns[q] < s->rc_columns, EHMM_ERR_STATE, "glmNB: rejection table %d not available", columns[q]);
+        EHMM_REQUIRE(par[P_] > 0 && isfinite(par[P_]), EHMM_ERR_ARG, "glmNB: dispersion %g must be positive", par[P_]);
+        NBPar &P = B.par[q];
+        P.b0 = par[0];
+        P.b1 = P_ == 2 ? par[1] : 0.0;
+        P.phi = par[P_];
+        P.size = 1.0 / P.phi;
+        P.lsize = log(P.size);
+        P.lgs = lgamma(P.size);
+        P.dg_size = host_digamma(P.size);
+        P.has_ctrl = (P_ == 2);
+        B.column[q] = columns[q];
+    }
     const int nblk = blocks_for(s->G);
-    PROF(s, KID_GLM), glm_nb_kernel<<<nblk, GLM_NT, 0, s->stream>>>(s->G, s->rc_buckets.as<double>() + (size_t)column * (s->G + 1),
-                                                 s->u_chip.as<double>(), s->u_off.as<double>(),
-                                                 s->u_ctrl.as<double>(), P, s->glm_part.as<double>());
+    const size_t need = sizeof(double) * ((size_t)EHMM_MAX_K * 148 * 4 * 4 + EHMM_MAX_K * 4) + 64;
+    if (s->glm_part.bytes < need || !s->glm_ticket_ready) {
+        EHMM_TRY(s->glm_part.reserve(need > sizeof(double) * ((size_t)148 * 4 * GLM_MAXOUT + GLM_MAXOUT) ? need : sizeof(double) * ((size_t)148 * 4 * GLM_MAXOUT + GLM_MAXOUT)));
+        EHMM_TRY(s->glm_ticket.reserve(64));
+        EHMM_CK(cudaMemsetAsync(s->glm_ticket.p, 0, 64, s->stream));
+        s->glm_ticket_ready = true;
+    }
+    double *part = s->glm_part.as<double>();
+    double *out = part + (size_t)EHMM_MAX_K * 148 * 4 * 4;
+    dim3 grid((unsigned)nblk, (unsigned)ncols);
+    PROF(s, KID_GLM), glm_nb_batch_kernel<<<grid, GLM_NT, 0, s->stream>>>(
+        s->G, s->rc_buckets.as<double>(), s->u_chip.as<double>(), s->u_off.as<double>(), s->u_ctrl.as<double>(), B, part,
+        s->glm_ticket.as<unsigned>(), out);
     EHMM_CK(cudaGetLastError());
-    double o[4];
-    EHMM_TRY(finish(s, nblk, 4, o));
-    *value = -o[0];
-    if (grad) {
-        grad[0] = -o[1];
-        if (P_ == 2) grad[1] = -o[2];
-        grad[P_] = -o[3];
+    EHMM_CK(cudaMemcpyAsync(s->h_pinned + 128, out, sizeof(double) * 4 * ncols, cudaMemcpyDeviceToHost, s->stream));
+    EHMM_CK(cudaStreamSynchronize(s->stream));
+    for (int q = 0; q < ncols; q++) {
+        const double *o = s->h_pinned + 128 + 4 * q;
+        values[q] = -o[0];
+        if (grads) {
+            double *g = grads + (size_t)q * (P_ + 1);
+            g[0] = -o[1];
+            if (P_ == 2) g[1] = -o[2];
+            g[P_] = -o[3];
+        }
     }
     return EHMM_OK;
 }

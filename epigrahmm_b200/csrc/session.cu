@@ -105,6 +105,11 @@ int upload_unique(ehmm_session *s, int64_t G, const double *u_chip, const double
     return EHMM_OK;
 }
 
+__global__ void widen_u16_kernel(int64_t n, const uint16_t *__restrict__ in, int32_t *__restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = in[i];
+}
+
 __global__ void group_range_kernel(int64_t n, const int32_t *__restrict__ group, int64_t G, int *__restrict__ bad) {
     int b = 0;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -238,7 +243,7 @@ int ehmm_session_close(ehmm_session *s) {
     DevBuf *bufs[] = {&s->counts_own, &s->offsets_own, &s->controls_own, &s->group, &s->u_chip, &s->u_off, &s->u_ctrl,
                       &s->u_dsg, &s->logf, &s->logFP, &s->logBP, &s->logProb1, &s->logProb2, &s->eta, &s->viterbi,
                       &s->tileops, &s->carries, &s->tilestats, &s->fbscal, &s->rc_w, &s->rc_flag, &s->rc_scan,
-                      &s->rc_buckets, &s->rc_unif, &s->rc_tmp, &s->mt_raw, &s->mt_raw2, &s->mt_windows, &s->gtab, &s->lgtab, &s->glm_part, &s->misc};
+                      &s->rc_buckets, &s->rc_unif, &s->rc_tmp, &s->mt_raw, &s->mt_raw2, &s->mt_windows, &s->gtab, &s->glm_ticket, &s->lgtab, &s->glm_part, &s->misc};
     for (DevBuf *b : bufs) b->release();
     for (cudaEvent_t e : s->prof_pool) cudaEventDestroy(e);
     if (s->h_pinned) cudaFreeHost(s->h_pinned);
@@ -343,10 +348,24 @@ int ehmm_set_design_n(ehmm_session *s, int N, int B, const uint8_t *design) {
     return EHMM_OK;
 }
 
+static int set_encoded(ehmm_session *s, int N, const int32_t *group, const uint16_t *group16, int64_t G,
+                       const double *u_chip, const double *u_offsets, const double *u_controls, const uint8_t *u_dsg);
+
 int ehmm_set_data_encoded(ehmm_session *s, int N, const int32_t *group, int64_t G, const double *u_chip,
                           const double *u_offsets, const double *u_controls, const uint8_t *u_dsg) {
+    return set_encoded(s, N, group, nullptr, G, u_chip, u_offsets, u_controls, u_dsg);
+}
+
+int ehmm_set_data_encoded16(ehmm_session *s, int N, const uint16_t *group, int64_t G, const double *u_chip,
+                            const double *u_offsets, const double *u_controls, const uint8_t *u_dsg) {
+    EHMM_REQUIRE(G <= 65535, EHMM_ERR_ARG, "set_data_encoded16: G = %lld does not fit 16 bits", (long long)G);
+    return set_encoded(s, N, nullptr, group, G, u_chip, u_offsets, u_controls, u_dsg);
+}
+
+static int set_encoded(ehmm_session *s, int N, const int32_t *group, const uint16_t *group16, int64_t G,
+                       const double *u_chip, const double *u_offsets, const double *u_controls, const uint8_t *u_dsg) {
     EHMM_TRY(check_session(s));
-    EHMM_REQUIRE(N >= 1 && group && G >= 1 && u_chip && u_offsets, EHMM_ERR_ARG, "set_data_encoded: bad arguments");
+    EHMM_REQUIRE(N >= 1 && (group || group16) && G >= 1 && u_chip && u_offsets, EHMM_ERR_ARG, "set_data_encoded: bad arguments");
     EHMM_REQUIRE((size_t)(G + 1) * 16 <= ((size_t)64 << 20), EHMM_ERR_ARG,
                  "set_data_encoded: %lld groups exceed the dictionary limit; use ehmm_set_data", (long long)G);
     double mx = 0;
@@ -364,7 +383,15 @@ int ehmm_set_data_encoded(ehmm_session *s, int N, const int32_t *group, int64_t 
     s->count_max = (int64_t)mx;
     const size_t n = (size_t)s->M * N;
     EHMM_TRY(s->group.reserve(n * sizeof(int32_t)));
-    EHMM_CK(cudaMemcpyAsync(s->group.p, group, n * sizeof(int32_t), cudaMemcpyHostToDevice, s->stream));
+    if (group) {
+        EHMM_CK(cudaMemcpyAsync(s->group.p, group, n * sizeof(int32_t), cudaMemcpyHostToDevice, s->stream));
+    } else {
+        EHMM_TRY(s->rc_tmp.reserve(n * sizeof(uint16_t)));
+        EHMM_CK(cudaMemcpyAsync(s->rc_tmp.p, group16, n * sizeof(uint16_t), cudaMemcpyHostToDevice, s->stream));
+        PROF(s, KID_MISC), widen_u16_kernel<<<148 * 8, 256, 0, s->stream>>>((int64_t)n, s->rc_tmp.as<uint16_t>(),
+                                                                       s->group.as<int32_t>());
+        EHMM_CK(cudaGetLastError());
+    }
     EHMM_TRY(upload_unique(s, G, u_chip, u_offsets, u_controls, u_dsg));
     EHMM_TRY(s->misc.reserve(64));
     int *bad = s->misc.as<int>();
@@ -673,6 +700,12 @@ int ehmm_glm_nb(ehmm_session *s, int column, const double *par, int P, double *v
     EHMM_REQUIRE(par && value, EHMM_ERR_ARG, "null pointer");
     EHMM_REQUIRE(column >= 0 && column < s->rc_columns, EHMM_ERR_STATE, "glmNB: rejection table %d not available", column);
     return glm_nb(s, column, par, P, value, grad);
+}
+
+int ehmm_glm_nb_batch(ehmm_session *s, int n, const int *columns, const double *pars, int P, double *values, double *grads) {
+    EHMM_TRY(check_session(s));
+    EHMM_REQUIRE(columns && pars && values, EHMM_ERR_ARG, "null pointer");
+    return glm_nb_batch(s, n, columns, pars, P, values, grads);
 }
 
 int ehmm_glm_mix_nb(ehmm_session *s, const double *par, double minZero, double *value, double *grad) {

@@ -110,54 +110,72 @@ def _lbfgsb_minimize(fun, x0, lower, upper):
     return res.x, {0: 0, 1: 1}.get(res.status, 52)
 
 
-def _lbfgsb_setulb(fun, x0, lower, upper):
-    """The same optimiser core driven directly (scipy's reverse-communication routine `setulb`),
-    without minimize()'s per-call Python scaffolding: identical iterates, ~10x less host time.
-    The EM loop calls this K times per iteration, so the scaffolding would otherwise be a quarter
-    of an iteration on B200."""
-    from scipy.optimize import _lbfgsb
-    m, n = 5, len(x0)
-    lower, upper = np.asarray(lower, dtype=np.float64), np.asarray(upper, dtype=np.float64)
-    idt = _lbfgsb_int_dtype()
-    nbd = np.zeros(n, dtype=idt)
-    low, upp = np.zeros(n), np.zeros(n)
-    for i in range(n):
-        lo_f, hi_f = np.isfinite(lower[i]), np.isfinite(upper[i])
-        if lo_f:
-            low[i] = lower[i]
-        if hi_f:
-            upp[i] = upper[i]
-        nbd[i] = {(False, False): 0, (True, False): 1, (True, True): 2, (False, True): 3}[(bool(lo_f), bool(hi_f))]
-    x = np.clip(np.array(x0, dtype=np.float64), lower, upper)
-    f = np.array(0.0, dtype=np.float64)
-    g = np.zeros(n, dtype=np.float64)
-    wa = np.zeros(2 * m * n + 5 * n + 11 * m * m + 8 * m, np.float64)
-    iwa = np.zeros(3 * n, dtype=idt)
-    task, ln_task, lsave = np.zeros(2, dtype=idt), np.zeros(2, dtype=idt), np.zeros(4, dtype=idt)
-    isave, dsave = np.zeros(44, dtype=idt), np.zeros(29, dtype=np.float64)
-    nit = nfev = 0
-    while True:
-        _lbfgsb.setulb(m, x, low, upp, nbd, f, g, 1e7, 0.0, wa, iwa, task, lsave, isave, dsave, 20, ln_task)
-        if task[0] == 3:
-            fv, gv = fun(x.copy())
-            nfev += 1
-            f = np.array(fv, dtype=np.float64)
-            g = np.asarray(gv, dtype=np.float64)
-        elif task[0] == 1:
-            nit += 1
-            if nit >= 100:
-                task[0], task[1] = 5, 504
-            elif nfev > 15000:
-                task[0], task[1] = 5, 502
-        else:
+class _Setulb:
+    """One L-BFGS-B instance driven through scipy's reverse-communication routine `setulb`
+    (the optimiser core of scipy.optimize.minimize, without its per-call Python scaffolding:
+    identical iterates, ~4x less host time).  request() runs the routine until it needs f and g at a
+    point (returned) or has finished (None); feed() supplies them."""
+
+    def __init__(self, x0, lower, upper):
+        from scipy.optimize import _lbfgsb
+        self._lib = _lbfgsb
+        m, n = 5, len(x0)
+        lower, upper = np.asarray(lower, dtype=np.float64), np.asarray(upper, dtype=np.float64)
+        idt = _lbfgsb_int_dtype()
+        self.nbd = np.zeros(n, dtype=idt)
+        self.low, self.upp = np.zeros(n), np.zeros(n)
+        for i in range(n):
+            lo_f, hi_f = bool(np.isfinite(lower[i])), bool(np.isfinite(upper[i]))
+            if lo_f:
+                self.low[i] = lower[i]
+            if hi_f:
+                self.upp[i] = upper[i]
+            self.nbd[i] = {(False, False): 0, (True, False): 1, (True, True): 2, (False, True): 3}[(lo_f, hi_f)]
+        self.x = np.clip(np.array(x0, dtype=np.float64), lower, upper)
+        self.f = np.array(0.0, dtype=np.float64)
+        self.g = np.zeros(n, dtype=np.float64)
+        self.wa = np.zeros(2 * m * n + 5 * n + 11 * m * m + 8 * m, np.float64)
+        self.iwa = np.zeros(3 * n, dtype=idt)
+        self.task, self.ln_task, self.lsave = np.zeros(2, dtype=idt), np.zeros(2, dtype=idt), np.zeros(4, dtype=idt)
+        self.isave, self.dsave = np.zeros(44, dtype=idt), np.zeros(29, dtype=np.float64)
+        self.nit = self.nfev = 0
+        self.code = None
+
+    def request(self):
+        while True:
+            self._lib.setulb(5, self.x, self.low, self.upp, self.nbd, self.f, self.g, 1e7, 0.0, self.wa, self.iwa,
+                             self.task, self.lsave, self.isave, self.dsave, 20, self.ln_task)
+            if self.task[0] == 3:
+                return self.x.copy()
+            if self.task[0] == 1:
+                self.nit += 1
+                if self.nit >= 100:
+                    self.task[0], self.task[1] = 5, 504
+                elif self.nfev > 15000:
+                    self.task[0], self.task[1] = 5, 502
+                continue
             break
-    if task[0] == 4:
-        code = 0
-    elif nit >= 100 or nfev > 15000:
-        code = 1
-    else:
-        code = 52
-    return x, code
+        if self.task[0] == 4:
+            self.code = 0
+        elif self.nit >= 100 or self.nfev > 15000:
+            self.code = 1
+        else:
+            self.code = 52
+        return None
+
+    def feed(self, fv, gv):
+        self.nfev += 1
+        self.f = np.array(fv, dtype=np.float64)
+        self.g = np.asarray(gv, dtype=np.float64).copy()
+
+
+def _lbfgsb_setulb(fun, x0, lower, upper):
+    st = _Setulb(x0, lower, upper)
+    while True:
+        x = st.request()
+        if x is None:
+            return st.x, st.code
+        st.feed(*fun(x))
 
 
 def _lbfgsb_int_dtype():
@@ -206,6 +224,55 @@ def optimNB(par, backend, column, control):
     except Exception:  # tryCatch(error=): keep the starting value, convergence 99
         x, conv = start, 99
     return dict(par=invertDispersion(x), convergence=conv)
+
+
+def optimNB_all(pars, backend, control):
+    """optimNB for every state (R/base-EM.R:131-141 runs them one after the other with lapply).
+    The K problems are independent, so when the backend can evaluate several (state, parameter)
+    pairs in one launch (glm_nb_batch) their L-BFGS-B instances advance in lock-step: each one sees
+    exactly the evaluations it would see alone, and the host waits for K times fewer launches."""
+    if not (hasattr(backend, "glm_nb_batch") and _fast_lbfgsb_available()):
+        return [optimNB(p, backend, k, control) for k, p in enumerate(pars)]
+    starts = [invertDispersion(p) for p in pars]
+    P = len(starts[0]) - 1
+    lower = np.concatenate([np.full(P, -np.inf), [1.0 / control["maxDisp"]]])
+    upper = np.full(P + 1, np.inf)
+    out = [None] * len(pars)
+    states, req = {}, {}
+    for k, x0 in enumerate(starts):
+        try:
+            states[k] = _Setulb(x0, lower, upper)
+            req[k] = states[k].request()
+        except Exception:
+            out[k] = dict(par=invertDispersion(x0), convergence=99)
+    while True:
+        ks = [k for k in states if out[k] is None and req[k] is not None]
+        for k in [k for k in states if out[k] is None and req[k] is None]:
+            out[k] = dict(par=invertDispersion(states[k].x), convergence=states[k].code)
+        if not ks:
+            break
+        try:
+            vals, grads = backend.glm_nb_batch(ks, np.stack([req[k] for k in ks]))
+        except Exception:
+            for k in ks:
+                out[k] = dict(par=invertDispersion(starts[k]), convergence=99)
+            continue
+        for i, k in enumerate(ks):
+            if not np.isfinite(vals[i]):  # optim(): "L-BFGS-B needs finite values of 'fn'" -> tryCatch(error=)
+                out[k] = dict(par=invertDispersion(starts[k]), convergence=99)
+                continue
+            try:
+                states[k].feed(vals[i], grads[i])
+                req[k] = states[k].request()
+            except Exception:
+                out[k] = dict(par=invertDispersion(starts[k]), convergence=99)
+    return out
+
+
+def _fast_lbfgsb_available():
+    if _FAST_LBFGSB is None:
+        _lbfgsb(lambda x: (float(((x - 1.0) ** 2).sum()), 2.0 * (x - 1.0)), np.array([0.5]), [-np.inf], [np.inf])
+    return bool(_FAST_LBFGSB)
 
 
 def optimDifferential(par, backend, control):
@@ -260,7 +327,7 @@ def emConsensus(theta_old, backend, N, control, dist="nb", callback=None):
         backend.expstep(theta_old["pi"], theta_old["gamma"])
         theta_new.update(backend.maxstepprob())
         backend.rc_consensus(_rejection_cut(cur["iteration"], control))
-        optimMLE = [optimNB(theta_old["psi"][k], backend, k, control) for k in range(2)]
+        optimMLE = optimNB_all(theta_old["psi"], backend, control)
         theta_new["psi"] = [o["par"] for o in optimMLE]
         bic = backend.bic(numPar, N)
         q = backend.qfunction(theta_old["pi"], theta_old["gamma"])
@@ -286,7 +353,7 @@ def emInitialization(theta_old, backend, control, callback=None):
         backend.expstep(theta_old["pi"], theta_old["gamma"])
         theta_new.update(backend.maxstepprob())
         backend.rc_consensus(_rejection_cut(cur["iteration"], control))
-        optimMLE = [optimNB(theta_old["psi"][k], backend, k, control) for k in range(2)]
+        optimMLE = optimNB_all(theta_old["psi"], backend, control)
         theta_new["psi"] = [o["par"] for o in optimMLE]
         # (the reference updates count/convergence/error before bic/q here; same values result)
         bic = backend.bic(numPar, 1)

@@ -78,7 +78,9 @@ class Session:
 
     def set_data_encoded(self, group, u_chip, u_offsets, u_controls=None, u_dsg=None, design=None):
         """upload the table as dt$Group + dtUnique only (the counts/offsets matrices stay on the host)"""
-        g = _cm(group, np.int32)
+        group = np.asarray(group)
+        narrow = group.dtype == np.uint16      # 16-bit ids: half the upload, widened on the device
+        g = _cm(group, np.uint16 if narrow else np.int32)
         g = g.reshape(self.M, -1, order="F")
         N = g.shape[1]
         if design is not None:
@@ -88,7 +90,11 @@ class Session:
         uc, uo = _f64(u_chip), _f64(u_offsets)
         uctrl = None if u_controls is None else _f64(u_controls)
         udsg = None if u_dsg is None else np.asfortranarray(u_dsg, dtype=np.uint8)
-        check(lib.ehmm_set_data_encoded(self._h, N, iptr(g), uc.size, dptr(uc), dptr(uo), dptr(uctrl), bptr(udsg)))
+        if narrow:
+            check(lib.ehmm_set_data_encoded16(self._h, N, g.ctypes.data_as(C.POINTER(C.c_uint16)), uc.size, dptr(uc),
+                                              dptr(uo), dptr(uctrl), bptr(udsg)))
+        else:
+            check(lib.ehmm_set_data_encoded(self._h, N, iptr(g), uc.size, dptr(uc), dptr(uo), dptr(uctrl), bptr(udsg)))
         self.N, self.G = N, uc.size
 
     def set_design(self, design):
@@ -265,6 +271,15 @@ class Session:
         g = np.empty(par.size) if grad else None
         check(lib.ehmm_glm_nb(self._h, int(column), dptr(par), par.size - 1, C.byref(v), dptr(g)))
         return v.value, g
+
+    def glm_nb_batch(self, columns, pars):
+        """value and gradient for several (column, par) pairs in one launch"""
+        pars = np.ascontiguousarray(pars, dtype=np.float64)
+        n, P1 = pars.shape
+        cols = np.ascontiguousarray(columns, dtype=np.int32)
+        v, g = np.empty(n), np.empty((n, P1))
+        check(lib.ehmm_glm_nb_batch(self._h, n, cols.ctypes.data_as(C.POINTER(C.c_int)), dptr(pars), P1 - 1, dptr(v), dptr(g)))
+        return v, g
 
     def glm_mix_nb(self, par, minZero, grad=True):
         par = _f64(par)

@@ -73,6 +73,9 @@ int ehmm_set_groups(ehmm_session *s, const int32_t *group, int64_t G, const doub
  * ehmm_set_groups.  For the differential model call ehmm_set_design_n(s, N, B, design) first. */
 int ehmm_set_data_encoded(ehmm_session *s, int N, const int32_t *group, int64_t G, const double *u_chip,
                           const double *u_offsets, const double *u_controls, const uint8_t *u_dsg);
+/* same with 16-bit group ids (G <= 65535): halves the upload again; widened to int32 on the device */
+int ehmm_set_data_encoded16(ehmm_session *s, int N, const uint16_t *group, int64_t G, const double *u_chip,
+                            const double *u_offsets, const double *u_controls, const uint8_t *u_dsg);
 int ehmm_set_design_n(ehmm_session *s, int N, int B, const uint8_t *design);
 /* design[b*N + i] = Dsg.Mix_b of sample i (generateMixtureIntercepts, R/base-utils.R:242-264). */
 int ehmm_set_design(ehmm_session *s, int B, const uint8_t *design);
@@ -154,6 +157,10 @@ int ehmm_aggregate(int device, const double *x, int64_t n, const int32_t *f, int
 /* glmNB / derivNB, R/base-optim.R:109-130, over table `column` joined with dtUnique.
  * par = (beta0[, beta_ctrl], phi); value and grad (P + 1) are the NEGATIVE log-lik as in R. */
 int ehmm_glm_nb(ehmm_session *s, int column, const double *par, int P, double *value, double *grad);
+/* n evaluations in one launch (the per-state optimisations of R/base-EM.R:131-141 are independent,
+ * so their L-BFGS-B instances can advance in lock-step): columns[q], pars[q*(P+1) ..] -> values[q],
+ * grads[q*(P+1) ..]. */
+int ehmm_glm_nb_batch(ehmm_session *s, int n, const int *columns, const double *pars, int P, double *values, double *grads);
 /* glmMixNB / derivMixNB, R/base-optim.R:187-255, over all B+2 tables. par = (b, db, l, dl). */
 int ehmm_glm_mix_nb(ehmm_session *s, const double *par, double minZero, double *value, double *grad);
 

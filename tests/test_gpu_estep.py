@@ -259,6 +259,10 @@ def test_dictionary_encoded_upload(ehmm, model):
             b.set_data_encoded(g["group"], g["u_chip"], g["u_offsets"], g["u_controls"])
             b.loglik_consensus(psi, MINZERO)
             assert np.array_equal(a.fetch("logLikelihood"), b.fetch("logLikelihood"))
+            assert g["G"] < 65536
+            b.set_data_encoded(g["group"].astype(np.uint16), g["u_chip"], g["u_offsets"], g["u_controls"])  # 16-bit ids
+            b.loglik_consensus(psi, MINZERO)
+            assert np.array_equal(a.fetch("logLikelihood"), b.fetch("logLikelihood"))
             with pytest.raises(ehmm.EhmmError):
                 b.set_data_encoded(g["group"] + g["G"], g["u_chip"], g["u_offsets"], g["u_controls"])  # ids out of range
     else:
