@@ -137,7 +137,8 @@ struct ehmm_session {
     int rc_count_cols = 0;
 
     // ---- emission / GLM scratch ----
-    ehmm::DevBuf lgtab, glm_part, glm_ticket, misc, gtab;
+    ehmm::DevBuf lgtab, glm_part, glm_ticket, misc, gtab, inner_part;
+    int inner_part_blocks = 0;  // > 0: inner_part holds innerMaxStepProb partial sums for the current eta / logProb1
     bool glm_ticket_ready = false;
     bool encoded = false;       // data given as dt$Group + dtUnique only (no count / offset matrices)
     bool encoded_ctrl = false;

@@ -206,25 +206,57 @@ __global__ void __launch_bounds__(EM_NT)
     }
 }
 
-// innerExpStep, R/base-EM.R:302-314: eta[j,b] = exp(ll_b)/sum_b exp(ll_b) with exp(ll_b)==0 -> minZero
-template <int NMAX>
+// innerExpStep, R/base-EM.R:302-314: eta[j,b] = exp(ll_b)/sum_b exp(ll_b) with exp(ll_b)==0 -> minZero.
+// Optional fusion of innerMaxStepProb's sums (src/innerMaxStepProb.cpp:33-35): with the posterior of
+// the differential state at hand, sum_j P1[j,1]*eta[j,b] and sum_j P1[j,1] need no extra pass
+// (part[blk*(B+1) + b], reduced by colsum_kernel).
+template <int NMAX, int BMAX>
 __global__ void __launch_bounds__(EM_NT)
     emis_inner_kernel(int64_t M, int N, const int32_t *__restrict__ y, const double *__restrict__ off,
                       const __grid_constant__ EmisParams P, const __grid_constant__ MixParams X,
-                      const double *__restrict__ tab, double *__restrict__ eta) {
+                      const double *__restrict__ tab, double *__restrict__ eta, const double *__restrict__ lp1_col1,
+                      double *__restrict__ part) {
+    double acc[BMAX + 1];
+#pragma unroll
+    for (int b = 0; b <= BMAX; b++) acc[b] = 0.0;
     for (int64_t j = (int64_t)blockIdx.x * EM_NT + threadIdx.x; j < M; j += (int64_t)gridDim.x * EM_NT) {
         double LL0, LL2, d[NMAX];
         diff_cells<NMAX>(j, M, N, y, off, P, tab, LL0, LL2, d);
-        double s = 0.0;
-        for (int b = 0; b < X.B; b++) {
-            double v = exp(mix_ll<NMAX>(b, LL0, d, X));
-            if (v == 0.0) v = P.minZero;
-            eta[j + (int64_t)b * M] = v;
-            s += v;
+        double v[BMAX], s = 0.0;
+#pragma unroll
+        for (int b = 0; b < BMAX; b++) {
+            if (b < X.B) {
+                v[b] = exp(mix_ll<NMAX>(b, LL0, d, X));
+                if (v[b] == 0.0) v[b] = P.minZero;
+                s += v[b];
+            }
         }
-        for (int b = 0; b < X.B; b++) {
-            // own write, served from L1/L2; division as in the reference (exp(ll)/sumExpLL)
-            eta[j + (int64_t)b * M] = eta[j + (int64_t)b * M] / s;
+        const double p1 = lp1_col1 ? exp(__ldg(lp1_col1 + j)) : 0.0;
+        acc[BMAX] += p1;
+#pragma unroll
+        for (int b = 0; b < BMAX; b++) {
+            if (b < X.B) {
+                const double e = v[b] / s;  // division as in the reference (exp(ll)/sumExpLL)
+                eta[j + (int64_t)b * M] = e;
+                acc[b] = fma(p1, e, acc[b]);
+            }
+        }
+    }
+    if (lp1_col1) {
+        __shared__ double sh[(EM_NT / 32) * (BMAX + 1)];
+        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+        for (int b = 0; b <= BMAX; b++) {
+#pragma unroll
+            for (int dd = 16; dd > 0; dd >>= 1) acc[b] += __shfl_down_sync(0xffffffffu, acc[b], dd);
+            if (lane == 0) sh[w * (BMAX + 1) + b] = acc[b];
+        }
+        __syncthreads();
+        for (int b = threadIdx.x; b <= X.B; b += EM_NT) {
+            const int src = (b == X.B) ? BMAX : b;
+            double t = sh[src];
+            for (int i = 1; i < EM_NT / 32; i++) t += sh[i * (BMAX + 1) + src];
+            part[(int64_t)blockIdx.x * (X.B + 1) + b] = t;
         }
     }
 }
@@ -450,12 +482,27 @@ int emis_inner_estep(ehmm_session *s, const double *delta, const double *psi, do
     const int32_t *src_y = s->d_counts;
     const double *src_off = s->d_offsets, *src_tab = s->lgtab.as<double>();
     EHMM_TRY(diff_source(s, P, src_y, src_off, src_tab));
-    if (s->N <= 16)
-        PROF(s, KID_EMIS_INNER), emis_inner_kernel<16><<<g, EM_NT, 0, s->stream>>>(s->M, s->N, src_y, src_off, P, X,
-                                                         src_tab, s->eta.as<double>());
-    else
-        PROF(s, KID_EMIS_INNER), emis_inner_kernel<64><<<g, EM_NT, 0, s->stream>>>(s->M, s->N, src_y, src_off, P, X,
-                                                         src_tab, s->eta.as<double>());
+    // fuse innerMaxStepProb's sums when the posteriors of the current E-step are in place
+    const bool fuse = has(s, DS_P1) && s->K == 3;
+    const double *lp1c = fuse ? s->logProb1.as<double>() + s->M : nullptr;
+    EHMM_TRY(s->inner_part.reserve(sizeof(double) * ((size_t)g * (s->B + 1) + s->B + 1)));
+    double *part = s->inner_part.as<double>();
+#define EHMM_INNER(NM, BM)                                                                                          \
+    PROF(s, KID_EMIS_INNER), emis_inner_kernel<NM, BM><<<g, EM_NT, 0, s->stream>>>(s->M, s->N, src_y, src_off, P, X, \
+                                                                                   src_tab, s->eta.as<double>(), lp1c, part)
+    if (s->N <= 16) {
+        if (s->B <= 8) EHMM_INNER(16, 8);
+        else if (s->B <= 16) EHMM_INNER(16, 16);
+        else if (s->B <= 32) EHMM_INNER(16, 32);
+        else EHMM_INNER(16, 62);
+    } else {
+        if (s->B <= 8) EHMM_INNER(64, 8);
+        else if (s->B <= 16) EHMM_INNER(64, 16);
+        else if (s->B <= 32) EHMM_INNER(64, 32);
+        else EHMM_INNER(64, 62);
+    }
+#undef EHMM_INNER
+    s->inner_part_blocks = fuse ? g : 0;
     EHMM_CK(cudaGetLastError());
     s->valid |= DS_ETA;
     return EHMM_OK;
@@ -466,11 +513,19 @@ int inner_mstep_sums(ehmm_session *s, double *sums) {
     EHMM_REQUIRE(has(s, DS_ETA | DS_P1), EHMM_ERR_STATE, "innerMaxStepProb needs mixtureProb and logProb1");
     EHMM_REQUIRE(s->K == 3, EHMM_ERR_ARG, "innerMaxStepProb needs K=3");
     const int B = s->B;
-    const int nblk = 148 * 4;
-    EHMM_TRY(s->misc.reserve(sizeof(double) * ((size_t)nblk * (B + 1) + B + 1)));
-    double *part = s->misc.as<double>(), *out = part + (size_t)nblk * (B + 1);
-    PROF(s, KID_INNER_MSTEP), inner_mstep_kernel<<<nblk, 256, 0, s->stream>>>(s->M, B, s->logProb1.as<double>() + s->M, s->eta.as<double>(), part);
-    EHMM_CK(cudaGetLastError());
+    int nblk = 148 * 4;
+    double *part, *out;
+    if (s->inner_part_blocks > 0) {  // sums were accumulated by the innerExpStep kernel
+        nblk = s->inner_part_blocks;
+        part = s->inner_part.as<double>();
+        out = part + (size_t)nblk * (B + 1);
+    } else {
+        EHMM_TRY(s->misc.reserve(sizeof(double) * ((size_t)nblk * (B + 1) + B + 1)));
+        part = s->misc.as<double>();
+        out = part + (size_t)nblk * (B + 1);
+        PROF(s, KID_INNER_MSTEP), inner_mstep_kernel<<<nblk, 256, 0, s->stream>>>(s->M, B, s->logProb1.as<double>() + s->M, s->eta.as<double>(), part);
+        EHMM_CK(cudaGetLastError());
+    }
     PROF(s, KID_MISC), colsum_kernel<<<1, 256, 0, s->stream>>>(part, nblk, B + 1, out);
     EHMM_CK(cudaGetLastError());
     EHMM_CK(cudaMemcpyAsync(s->h_pinned + 64, out, sizeof(double) * (B + 1), cudaMemcpyDeviceToHost, s->stream));

@@ -117,50 +117,69 @@ template <> __device__ __forceinline__ double get_unif<uint32_t>(const uint32_t 
 
 // nrep = 1 for the consensus model (only f[0..M-1] is read, Q6 in SURVEY.md); nrep = N for the
 // differential model (repmat(w, N, 1) against the M*N group ids).
-// Each thread owns RC_STRIPS consecutive bins, so ranks inside the block come from one warp scan
-// and one block barrier; the weight loads of a warp still cover one contiguous 2 KB span.
+// Each thread owns RC_STRIPS consecutive bins, so ranks inside a tile come from one warp scan and
+// one block barrier; the weight loads of a warp still cover one contiguous 2 KB span.
+// Group ids are numbered by first appearance (data.table .GRP), so small ids are the frequent
+// (count, offset) combinations: ids < RC_HOT accumulate in a shared-memory histogram of a persistent
+// CTA (flushed once at the end) and only the long tail goes to global atomics.
+constexpr int RC_HOT = 4096;
+
 template <typename UT>
 __global__ void __launch_bounds__(RC_NT)
     rc_apply_kernel(RCSrc S, double p, int64_t nblk, const int64_t *__restrict__ offsets, const UT *__restrict__ unif,
                     const int32_t *__restrict__ group, int nrep, int64_t G, double *__restrict__ buckets,
                     double *__restrict__ wout) {
+    __shared__ double hot[RC_HOT];
     __shared__ int sh[RC_NT / 32];
     const int c = blockIdx.y;
-    const int64_t j0 = (int64_t)blockIdx.x * RC_TB + (int64_t)threadIdx.x * RC_STRIPS;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     double *bk = buckets + (int64_t)c * (G + 1);
-    double x[RC_STRIPS];
-    unsigned flags = 0;
-#pragma unroll
-    for (int r = 0; r < RC_STRIPS; r++) {
-        const int64_t j = j0 + r;
-        x[r] = (j < S.M) ? rc_weight(S, c, j) : 2.0;  // 2.0: never below p <= 1, never stored
-        if (x[r] < p && x[r] / p != 0.0) flags |= 1u << r;
-    }
-    const int cnt = __popc(flags);
-    int incl = cnt;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl += t;
-    }
-    if (lane == 31) sh[w] = incl;
+    for (int i = threadIdx.x; i < RC_HOT; i += RC_NT) hot[i] = 0.0;
     __syncthreads();
-    int before = incl - cnt;
-    for (int i = 0; i < w; i++) before += sh[i];
-    int64_t u = offsets[(int64_t)c * nblk + blockIdx.x] + before;
+    for (int64_t blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+        const int64_t j0 = blk * RC_TB + (int64_t)threadIdx.x * RC_STRIPS;
+        double x[RC_STRIPS];
+        unsigned flags = 0;
 #pragma unroll
-    for (int r = 0; r < RC_STRIPS; r++) {
-        const int64_t j = j0 + r;
-        if (j < S.M) {
-            double wt = x[r];
-            if (wt < p) wt = ((flags >> r) & 1u) ? rbinom1(wt / p, get_unif<UT>(unif, u++)) * p : 0.0;
-            if (wout) wout[(int64_t)c * S.M + j] = wt;
-            if (wt != 0.0) {
-                for (int i = 0; i < nrep; i++) atomicAdd(bk + __ldg(group + j + (int64_t)i * S.M), wt);
+        for (int r = 0; r < RC_STRIPS; r++) {
+            const int64_t j = j0 + r;
+            x[r] = (j < S.M) ? rc_weight(S, c, j) : 2.0;  // 2.0: never below p <= 1, never stored
+            if (x[r] < p && x[r] / p != 0.0) flags |= 1u << r;
+        }
+        const int cnt = __popc(flags);
+        int incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        if (lane == 31) sh[w] = incl;
+        __syncthreads();
+        int before = incl - cnt;
+        for (int i = 0; i < w; i++) before += sh[i];
+        int64_t u = offsets[(int64_t)c * nblk + blk] + before;
+#pragma unroll
+        for (int r = 0; r < RC_STRIPS; r++) {
+            const int64_t j = j0 + r;
+            if (j < S.M) {
+                double wt = x[r];
+                if (wt < p) wt = ((flags >> r) & 1u) ? rbinom1(wt / p, get_unif<UT>(unif, u++)) * p : 0.0;
+                if (wout) wout[(int64_t)c * S.M + j] = wt;
+                if (wt != 0.0) {
+                    for (int i = 0; i < nrep; i++) {
+                        const int g = __ldg(group + j + (int64_t)i * S.M);
+                        if (g < RC_HOT) atomicAdd(&hot[g], wt);
+                        else atomicAdd(bk + g, wt);
+                    }
+                }
             }
         }
+        __syncthreads();  // sh[] is reused by the next tile
     }
+    __syncthreads();
+    const int lim = (int)min((int64_t)RC_HOT, G + 1);
+    for (int i = threadIdx.x; i < lim; i += RC_NT)
+        if (hot[i] != 0.0) atomicAdd(bk + i, hot[i]);
 }
 
 __global__ void aggregate_kernel(const double *__restrict__ x, int64_t n, const int32_t *__restrict__ f,
@@ -222,6 +241,14 @@ __global__ void __launch_bounds__(RC_NT) rw_apply_kernel(double *__restrict__ x,
     }
 }
 
+// persistent CTAs: about four per SM in total (32 KB of shared memory each), split over the columns
+dim3 apply_grid(int64_t nblk, int columns) {
+    int64_t per = (148 * 4 + columns - 1) / columns;
+    if (per > nblk) per = nblk;
+    if (per < 1) per = 1;
+    return dim3((unsigned)per, (unsigned)columns);
+}
+
 int run_rc(ehmm_session *s, const RCSrc &S, double p, int nrep, const double *uniforms, int64_t n_uniforms,
            int64_t *consumed) {
     const int64_t nblk = (s->M + RC_TB - 1) / RC_TB;
@@ -252,7 +279,7 @@ int run_rc(ehmm_session *s, const RCSrc &S, double p, int nrep, const double *un
         EHMM_TRY(s->rc_unif.reserve(sizeof(double) * (size_t)(total > 0 ? total : 1)));
         if (total > 0)
             EHMM_CK(cudaMemcpyAsync(s->rc_unif.p, uniforms, sizeof(double) * total, cudaMemcpyHostToDevice, s->stream));
-        PROF(s, KID_RC_APPLY), rc_apply_kernel<double><<<grid, RC_NT, 0, s->stream>>>(S, p, nblk, s->rc_scan.as<int64_t>(),
+        PROF(s, KID_RC_APPLY), rc_apply_kernel<double><<<apply_grid(nblk, S.columns), RC_NT, 0, s->stream>>>(S, p, nblk, s->rc_scan.as<int64_t>(),
                                                                s->rc_unif.as<double>(), grp, nrep, s->G,
                                                                s->rc_buckets.as<double>(), nullptr);
     } else {
@@ -271,7 +298,7 @@ int run_rc(ehmm_session *s, const RCSrc &S, double p, int nrep, const double *un
             EHMM_CK(cudaMemcpyAsync(s->h_pinned + 512, s->mt_raw.p, sizeof(uint32_t) * 625, cudaMemcpyDeviceToHost, s->stream));
             state_back = true;
         }
-        PROF(s, KID_RC_APPLY), rc_apply_kernel<uint32_t><<<grid, RC_NT, 0, s->stream>>>(S, p, nblk, s->rc_scan.as<int64_t>(),
+        PROF(s, KID_RC_APPLY), rc_apply_kernel<uint32_t><<<apply_grid(nblk, S.columns), RC_NT, 0, s->stream>>>(S, p, nblk, s->rc_scan.as<int64_t>(),
                                                                  s->rc_unif.as<uint32_t>(), grp, nrep, s->G,
                                                                  s->rc_buckets.as<double>(), nullptr);
     }
@@ -348,7 +375,7 @@ int rc_apply_block(ehmm_session *s, const RCSrc &S, double p, int nrep, const in
         state_back = true;
     }
     dim3 grid((unsigned)nblk, (unsigned)S.columns);
-    PROF(s, KID_RC_APPLY), rc_apply_kernel<uint32_t><<<grid, RC_NT, 0, s->stream>>>(
+    PROF(s, KID_RC_APPLY), rc_apply_kernel<uint32_t><<<apply_grid(nblk, S.columns), RC_NT, 0, s->stream>>>(
         S, p, nblk, s->rc_scan.as<int64_t>(), s->rc_unif.as<uint32_t>(), s->group.as<int32_t>(), nrep, s->G,
         s->rc_buckets.as<double>(), nullptr);
     EHMM_CK(cudaGetLastError());

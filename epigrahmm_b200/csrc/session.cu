@@ -243,7 +243,7 @@ int ehmm_session_close(ehmm_session *s) {
     DevBuf *bufs[] = {&s->counts_own, &s->offsets_own, &s->controls_own, &s->group, &s->u_chip, &s->u_off, &s->u_ctrl,
                       &s->u_dsg, &s->logf, &s->logFP, &s->logBP, &s->logProb1, &s->logProb2, &s->eta, &s->viterbi,
                       &s->tileops, &s->carries, &s->tilestats, &s->fbscal, &s->rc_w, &s->rc_flag, &s->rc_scan,
-                      &s->rc_buckets, &s->rc_unif, &s->rc_tmp, &s->mt_raw, &s->mt_raw2, &s->mt_windows, &s->gtab, &s->glm_ticket, &s->lgtab, &s->glm_part, &s->misc};
+                      &s->rc_buckets, &s->rc_unif, &s->rc_tmp, &s->mt_raw, &s->mt_raw2, &s->mt_windows, &s->gtab, &s->glm_ticket, &s->inner_part, &s->lgtab, &s->glm_part, &s->misc};
     for (DevBuf *b : bufs) b->release();
     for (cudaEvent_t e : s->prof_pool) cudaEventDestroy(e);
     if (s->h_pinned) cudaFreeHost(s->h_pinned);
@@ -452,6 +452,7 @@ int ehmm_expstep(ehmm_session *s, const double *pi, const double *gamma, const d
     EHMM_TRY(fb_expstep(s, d_logf));
     s->valid |= DS_ESTEP;
     s->stats_stale = false;
+    s->inner_part_blocks = 0;
     return EHMM_OK;
 }
 
@@ -462,6 +463,7 @@ int ehmm_expstep_device(ehmm_session *s, const double *pi, const double *gamma, 
     EHMM_TRY(fb_expstep(s, logf_device));
     s->valid |= DS_ESTEP;
     s->stats_stale = false;
+    s->inner_part_blocks = 0;
     return EHMM_OK;
 }
 
@@ -484,6 +486,7 @@ int ehmm_expstep_apply(ehmm_session *s, const double *fwd_carry, const double *b
     s->reduce_pending = false;
     s->valid |= DS_ESTEP;
     s->stats_stale = false;
+    s->inner_part_blocks = 0;
     return EHMM_OK;
 }
 
@@ -788,6 +791,7 @@ int ehmm_store(ehmm_session *s, const char *name, const double *src, int64_t row
     EHMM_CK(cudaMemcpyAsync(d.buf->p, src, sizeof(double) * rows * cols, cudaMemcpyHostToDevice, s->stream));
     EHMM_CK(cudaStreamSynchronize(s->stream));
     s->valid |= d.bit;
+    s->inner_part_blocks = 0;
     if (d.bit & (DS_ESTEP | DS_LOGF)) {
         // a dataset was replaced from the host: the fused statistics no longer describe it
         s->stats_on_host = false;
