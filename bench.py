@@ -151,6 +151,7 @@ ALGO_BYTES = {  # algorithmic bytes per bin of each streaming kernel (DESIGN.md 
     "fb_apply": 32 * K + 8 * K * K,          # logf in; logFP, logBP, logProb1, logProb2 out
     "fb_reduce": 8 * K,                      # logf in
     "emis_consensus": 12 * N_SAMPLES + 8 * K,  # int32 counts + fp64 offsets in; logf out
+    "emis_gather": 4 * N_SAMPLES + 8 * K,    # dictionary-encoded emission: int32 group ids in; logf out
     "rc_count": 8 * K,                       # logProb1 in
     "rc_apply": 8 * K + 4,                   # logProb1 + group id in (uniforms / buckets are O(flagged))
 }
@@ -311,8 +312,15 @@ def main():
         per_launch = ALGO_BYTES[dom[0]] * M
         dur_ms = dom[1][1] / dom[1][0]
         ach = per_launch / (dur_ms * 1e-3) / 1e9
+        traffic = None
+        try:  # DRAM bytes per launch of the same kernel from the committed ncu --set full capture
+            tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+            if tj.get("bins") == M:
+                traffic = tj["traffic_bytes_per_launch"].get(dom[0])
+        except Exception:
+            pass
         roof = {"bound": "hbm", "kernel": dom[0], "achieved": ach, "peak": peak_gbs, "unit": "GB/s",
-                "frac": ach / peak_gbs, "traffic": None, "peak_source": "measured (MEASURED_PEAKS.json)" if pk else "fallback",
+                "frac": ach / peak_gbs, "traffic": traffic, "peak_source": "measured (MEASURED_PEAKS.json)" if pk else "fallback",
                 "algorithmic_bytes_per_launch": per_launch, "avg_launch_ms": dur_ms,
                 "share_of_step": dom[1][1] / ms}
     kernels = {}

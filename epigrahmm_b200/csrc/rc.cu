@@ -304,7 +304,13 @@ int run_rc(ehmm_session *s, const RCSrc &S, double p, int nrep, const double *un
     }
     EHMM_CK(cudaGetLastError());
     // the next call's sub-stream windows depend only on the RNG state: prepare them on the side stream
-    if (!uniforms && total > 0) EHMM_TRY(mt_prefetch(s, (int64_t)S.columns * s->M));
+    // (sized from this call's consumption with 25% headroom; a larger need falls back to preparing
+    // the windows on the main stream)
+    if (!uniforms && total > 0) {
+        int64_t est = total + total / 4 + 2 * 131072;
+        if (est > (int64_t)S.columns * s->M) est = (int64_t)S.columns * s->M;
+        EHMM_TRY(mt_prefetch(s, est));
+    }
     EHMM_CK(cudaStreamSynchronize(s->stream));
     if (state_back) memcpy(s->rng_state, s->h_pinned + 512, sizeof(uint32_t) * 625);
     s->rc_columns = S.columns;
