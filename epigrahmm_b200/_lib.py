@@ -50,6 +50,8 @@ PROTOTYPES = {
     "ehmm_set_data": [_sess, C.c_int, _ip, _dp, _dp],
     "ehmm_set_data_device": [_sess, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p],
     "ehmm_set_groups": [_sess, _ip, C.c_int64, _dp, _dp, _dp, _bp],
+    "ehmm_build_groups": [_sess, _lp],
+    "ehmm_groups_fetch": [_sess, _ip, _dp, _dp, _dp, _bp],
     "ehmm_set_data_encoded": [_sess, C.c_int, _ip, C.c_int64, _dp, _dp, _dp, _bp],
     "ehmm_set_data_encoded16": [_sess, C.c_int, C.POINTER(C.c_uint16), C.c_int64, _dp, _dp, _dp, _bp],
     "ehmm_set_design_n": [_sess, C.c_int, C.c_int, _bp],

@@ -14,7 +14,6 @@ import numpy as np
 
 from . import em
 from .session import Session
-from .synth import make_groups
 
 
 def _pattern_table(n_cond):
@@ -58,8 +57,7 @@ def initializer(counts, offsets, control, device=0, key="initializer"):
         with Session("%s.%d" % (key, i), M, 2, device) as s:
             c, o = counts[:, [i]], np.asarray(offsets)[:, [i]]
             s.set_data(c, o)
-            g = make_groups(c, o)
-            s.set_groups(g["group"], g["u_chip"], g["u_offsets"])
+            s.build_groups()          # dt$Group / dtUnique on the device (R/base-core.R:30-35)
             s.rng_set_state(_stream().state)
             peaks[:, i], _ = em.initializerHMM(c, o, s, control)
             _stream().state[:] = s.rng_get_state()
@@ -79,8 +77,7 @@ def consensusHMM(counts, offsets, peaks, condition, control, controls=None, devi
     ctrl = None if controls is None else np.log1p(np.asarray(controls, dtype=np.float64))
     s = session or Session(key or "epigraHMM.h5", M, 2, device)
     s.set_data(counts, offsets, ctrl)
-    g = make_groups(counts, offsets, ctrl)
-    s.set_groups(g["group"], g["u_chip"], g["u_offsets"], g["u_controls"])
+    s.build_groups()                  # R/base-core.R:184-198 on the device
     psi = estimateCoefficients(z, counts, offsets, control, "consensus")
     if ctrl is not None:
         psi = [np.array([p[0], 0.0, p[1]]) for p in psi]
@@ -115,8 +112,7 @@ def differentialHMM(counts, offsets, peaks, condition, control, device=0, key=No
     s = session or Session(key or "epigraHMM.h5", M, 3, device)
     s.set_data(counts, offsets)
     s.set_design(design)
-    g = make_groups(counts, offsets, design=design)
-    s.set_groups(g["group"], g["u_chip"], g["u_offsets"], None, g["u_dsg"])
+    s.build_groups()                  # R/base-core.R:97-104 on the device
     zmin, zmax = z.min(), z.max()
     chain = np.where(z == zmin, 0, np.where(z == zmax, 2, 1))
     diff = z[(z != 1) & (z != zmax)]

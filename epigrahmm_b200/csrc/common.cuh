@@ -217,6 +217,9 @@ int rc_table_rows(ehmm_session *s, int column, int64_t *rows);
 int rc_table_fetch(ehmm_session *s, int column, double *sums, double *ids);
 int rc_reweight(int device, double *x, int64_t n, double p, const double *uniforms, int64_t n_uniforms, int64_t *consumed);
 int rc_aggregate(int device, const double *x, int64_t n, const int32_t *f, int64_t G, double *buckets);
+// groups.cu
+int build_groups(ehmm_session *s, int64_t *G_out);
+int groups_fetch(ehmm_session *s, int32_t *group, double *u_chip, double *u_off, double *u_ctrl, uint8_t *u_dsg);
 // mtjump.cu
 int mt_generate(ehmm_session *s, int64_t n, uint32_t *out);
 int mt_generate_range(ehmm_session *s, int64_t lo_rel, int64_t n, uint32_t *out);

@@ -338,6 +338,17 @@ int ehmm_set_groups(ehmm_session *s, const int32_t *group, int64_t G, const doub
     return EHMM_OK;
 }
 
+int ehmm_build_groups(ehmm_session *s, int64_t *G) {
+    EHMM_TRY(check_session(s));
+    return build_groups(s, G);
+}
+
+int ehmm_groups_fetch(ehmm_session *s, int32_t *group, double *u_chip, double *u_offsets, double *u_controls,
+                      uint8_t *u_dsg) {
+    EHMM_TRY(check_session(s));
+    return groups_fetch(s, group, u_chip, u_offsets, u_controls, u_dsg);
+}
+
 int ehmm_set_design_n(ehmm_session *s, int N, int B, const uint8_t *design) {
     EHMM_TRY(check_session(s));
     EHMM_REQUIRE(N >= 1 && N <= 64 && B >= 1 && B <= EHMM_MAX_B && design, EHMM_ERR_ARG, "set_design: bad N/B");

@@ -76,6 +76,35 @@ class Session:
                                        C.c_void_p(controls_ptr) if controls_ptr else None))
         self.N = int(N)
 
+    def build_groups(self) -> int:
+        """dt$Group + dtUnique on the device (after set_data / set_design); returns G"""
+        G = C.c_int64()
+        check(lib.ehmm_build_groups(self._h, C.byref(G)))
+        self.G = G.value
+        return self.G
+
+    def groups_fetch(self, with_group=True):
+        """dict(group, u_chip, u_offsets, u_controls, u_dsg) as synth.make_groups returns them"""
+        G = self.G
+        grp = np.empty((self.M, self.N), dtype=np.int32, order="F") if with_group else None
+        uc, uo = np.empty(G), np.empty(G)
+        out = dict(G=G, group=grp, u_chip=uc, u_offsets=uo, u_controls=None, u_dsg=None)
+        check(lib.ehmm_groups_fetch(self._h, iptr(grp), dptr(uc), dptr(uo), None, None))
+        try:
+            uctrl = np.empty(G)
+            check(lib.ehmm_groups_fetch(self._h, None, None, None, dptr(uctrl), None))
+            out["u_controls"] = uctrl
+        except _lib.EhmmError:
+            pass
+        if self.B:
+            try:
+                ud = np.empty((G, self.B), dtype=np.uint8, order="F")
+                check(lib.ehmm_groups_fetch(self._h, None, None, None, None, bptr(ud)))
+                out["u_dsg"] = ud
+            except _lib.EhmmError:
+                pass
+        return out
+
     def set_data_encoded(self, group, u_chip, u_offsets, u_controls=None, u_dsg=None, design=None):
         """upload the table as dt$Group + dtUnique only (the counts/offsets matrices stay on the host)"""
         group = np.asarray(group)

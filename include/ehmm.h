@@ -68,6 +68,13 @@ int ehmm_set_data_device(ehmm_session *s, int N, const int32_t *counts, const do
  * [, Dsg.Mix 0/1 as G x B column-major] (R/base-core.R:99-104,190-198). */
 int ehmm_set_groups(ehmm_session *s, const int32_t *group, int64_t G, const double *u_chip, const double *u_offsets,
                     const double *u_controls, const uint8_t *u_dsg);
+/* Build dt$Group and dtUnique on the device from the uploaded table (and design), numbered by first
+ * appearance in the column-major long table like data.table's .GRP (R/base-core.R:97-104,184-198).
+ * Replaces the host-side grouping + ehmm_set_groups.  ehmm_groups_fetch copies them out (any pointer
+ * may be NULL; u_dsg is G x B column-major). */
+int ehmm_build_groups(ehmm_session *s, int64_t *G);
+int ehmm_groups_fetch(ehmm_session *s, int32_t *group, double *u_chip, double *u_offsets, double *u_controls,
+                      uint8_t *u_dsg);
 /* Dictionary-encoded form of the same table: only dt$Group and dtUnique are uploaded (4 B per cell
  * instead of 12-20 B); counts/offsets are implied by dtUnique[group].  Replaces ehmm_set_data +
  * ehmm_set_groups.  For the differential model call ehmm_set_design_n(s, N, B, design) first. */

@@ -225,3 +225,39 @@ def test_rc_device_rng_parallel_substreams(ehmm, oracle):
             assert np.array_equal(s.rng_get_state(), rng.state())
             for k in range(2):
                 assert np.allclose(s.rc_buckets(k), ref[k], rtol=1e-12, atol=0)
+
+
+@pytest.mark.parametrize("model", ["consensus", "consensus_ctrl", "differential"])
+def test_build_groups_on_device_matches_grp(ehmm, model):
+    """ehmm_build_groups == data.table's .GRP numbering (host reference: synth.make_groups)"""
+    M = 50021
+    if model == "differential":
+        d = synth.make_differential(M, 3, 2, seed=81)
+        ref = synth.make_groups(d["counts"], d["offsets"], design=d["design"])
+        K = 3
+    else:
+        d = synth.make_consensus(M, 3, seed=82, controls=(model == "consensus_ctrl"))
+        d["offsets"][7, 1] = -0.0     # -0.0 and +0.0 belong to one group
+        d["offsets"][9, 1] = 0.0
+        ref = synth.make_groups(d["counts"], d["offsets"], d["controls"])
+        K = 2
+    with ehmm.Session("t_grp", M, K) as s:
+        s.set_data(d["counts"], d["offsets"], d.get("controls"))
+        if model == "differential":
+            s.set_design(d["design"])
+        G = s.build_groups()
+        got = s.groups_fetch()
+        assert G == ref["G"]
+        assert np.array_equal(got["group"], ref["group"])
+        assert np.array_equal(got["u_chip"], ref["u_chip"]) and np.array_equal(got["u_offsets"], ref["u_offsets"])
+        if model == "consensus_ctrl":
+            assert np.array_equal(got["u_controls"], ref["u_controls"])
+        if model == "differential":
+            assert np.array_equal(got["u_dsg"], ref["u_dsg"])
+        # the device-built dictionary drives the gather emission and the rejection control
+        if K == 2:
+            psi = [np.array([np.log(2.0), 0.3, 3.0]), np.array([np.log(12.0), 0.1, 4.0])] if model == "consensus_ctrl" \
+                else synth.THETA_CONSENSUS["psi"]
+            s.profile(True)
+            s.loglik_consensus(psi, MINZERO)
+            assert s.profile_read()["emis_gather"][0] == 1
