@@ -69,6 +69,8 @@ PROTOTYPES = {
     "ehmm_inner_maxstepprob": [_sess, _dp],
     "ehmm_marginal_probability": [_sess, _dp],
     "ehmm_viterbi": [_sess, _dp, _dp, _dp],
+    "ehmm_viterbi_forward": [_sess, _dp, _dp, _dp, _dp],
+    "ehmm_viterbi_backtrace": [_sess, C.c_int, C.POINTER(C.c_int), _dp],
     "ehmm_expstep_reduce": [_sess, _dp, _dp, _dp, _dp],
     "ehmm_expstep_apply": [_sess, _dp, _dp, _dp],
     "ehmm_estep_stats": [_sess, _dp],

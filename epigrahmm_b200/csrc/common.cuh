@@ -108,7 +108,8 @@ struct ehmm_session {
     bool have_design = false;
 
     // ---- datasets ----
-    ehmm::DevBuf logf, logFP, logBP, logProb1, logProb2, eta, viterbi;
+    ehmm::DevBuf logf, logFP, logBP, logProb1, logProb2, eta, viterbi, vit_bp;
+    bool vit_forward_done = false;
     unsigned valid = 0;        // DS_* bits: which datasets hold data
     bool stats_stale = false;  // datasets were replaced from the host; statistics must be recomputed
 
@@ -231,5 +232,7 @@ int glm_nb_batch(ehmm_session *s, int ncols, const int *columns, const double *p
 int glm_mix_nb(ehmm_session *s, const double *par, double minZero, double *value, double *grad);
 // viterbi.cu
 int viterbi(ehmm_session *s, const double *pi, const double *gamma, double *states_out);
+int viterbi_forward(ehmm_session *s, const double *pi, const double *gamma, const double *v_in, double *v_out);
+int viterbi_backtrace(ehmm_session *s, int state_last, int *state_prev, double *states_out);
 
 }  // namespace ehmm

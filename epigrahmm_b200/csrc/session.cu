@@ -241,7 +241,7 @@ int ehmm_session_close(ehmm_session *s) {
         if (it != g_sessions.end() && it->second == s) g_sessions.erase(it);
     }
     DevBuf *bufs[] = {&s->counts_own, &s->offsets_own, &s->controls_own, &s->group, &s->u_chip, &s->u_off, &s->u_ctrl,
-                      &s->u_dsg, &s->logf, &s->logFP, &s->logBP, &s->logProb1, &s->logProb2, &s->eta, &s->viterbi,
+                      &s->u_dsg, &s->logf, &s->logFP, &s->logBP, &s->logProb1, &s->logProb2, &s->eta, &s->viterbi, &s->vit_bp,
                       &s->tileops, &s->carries, &s->tilestats, &s->fbscal, &s->rc_w, &s->rc_flag, &s->rc_scan,
                       &s->rc_buckets, &s->rc_unif, &s->rc_tmp, &s->mt_raw, &s->mt_raw2, &s->mt_windows, &s->gtab, &s->glm_ticket, &s->inner_part, &s->lgtab, &s->glm_part, &s->misc};
     for (DevBuf *b : bufs) b->release();
@@ -618,6 +618,18 @@ int ehmm_viterbi(ehmm_session *s, const double *pi, const double *gamma, double 
     EHMM_REQUIRE(has(s, DS_FP), EHMM_ERR_STATE, "computeViterbiSequence: no logFP dataset (expStep has not run)");
     EHMM_REQUIRE(pi && gamma, EHMM_ERR_ARG, "null pointer");
     return viterbi(s, pi, gamma, states_out);
+}
+
+int ehmm_viterbi_forward(ehmm_session *s, const double *pi, const double *gamma, const double *v_in, double *v_out) {
+    EHMM_TRY(check_session(s));
+    EHMM_REQUIRE(has(s, DS_FP), EHMM_ERR_STATE, "computeViterbiSequence: no logFP dataset (expStep has not run)");
+    EHMM_REQUIRE(pi && gamma && v_out, EHMM_ERR_ARG, "null pointer");
+    return viterbi_forward(s, pi, gamma, v_in, v_out);
+}
+
+int ehmm_viterbi_backtrace(ehmm_session *s, int state_last, int *state_prev, double *states_out) {
+    EHMM_TRY(check_session(s));
+    return viterbi_backtrace(s, state_last, state_prev, states_out);
 }
 
 int ehmm_rng_set_state(ehmm_session *s, const uint32_t *state625) {

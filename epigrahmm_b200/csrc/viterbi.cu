@@ -20,6 +20,8 @@ constexpr int VT_TILE = 2048;  // bins per shared-memory tile
 struct VitPar {
     double lpi[EHMM_MAX_K];
     double lg[EHMM_MAX_K * EHMM_MAX_K];  // lg[i*K+k] = log gamma(i,k)
+    double vin[EHMM_MAX_K];              // LOGV of the bin in front of this block (bin blocks only)
+    int has_vin;                         // 0: this block starts the chain
 };
 
 template <int K>
@@ -32,6 +34,8 @@ __global__ void __launch_bounds__(VT_NT)
     const int tid = threadIdx.x;
     const int64_t nT = (M + VT_TILE - 1) / VT_TILE;
     double V[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) V[k] = P.vin[k];
     // prefetch tile 0
     {
         const int n0 = (int)min((int64_t)VT_TILE, M);
@@ -48,7 +52,7 @@ __global__ void __launch_bounds__(VT_NT)
         double *nxt = tile[(t + 1) & 1];
         if (tid == 0) {
             for (int b = 0; b < n; b++) {
-                if (s0 + b == 0) {
+                if (s0 + b == 0 && !P.has_vin) {
 #pragma unroll
                     for (int k = 0; k < K; k++) V[k] = __dadd_rn(P.lpi[k], cur[k * VT_TILE]);
                     sbp[0] = 0;
@@ -92,10 +96,12 @@ __global__ void __launch_bounds__(VT_NT)
 }
 
 // backtrace: S[M-1] = argmax V[M-1,:] (first maximum), S[j] = psi[j+1][S[j+1]]
+// carry_in: state of this block's last bin when a later block decided it, -1 at the chain's end
+// (then argmax of V).  carry[0] receives the state of the bin in front of the block.
 template <int K>
 __global__ void __launch_bounds__(VT_NT) viterbi_backtrace_kernel(const uint8_t *__restrict__ bp, int64_t M,
-                                                                  const double *__restrict__ vlast,
-                                                                  double *__restrict__ states) {
+                                                                  const double *__restrict__ vlast, int carry_in,
+                                                                  double *__restrict__ states, int *__restrict__ carry_out) {
     __shared__ uint8_t sbp[VT_TILE + 1];
     __shared__ uint8_t sst[VT_TILE];
     __shared__ int carry;
@@ -105,7 +111,7 @@ __global__ void __launch_bounds__(VT_NT) viterbi_backtrace_kernel(const uint8_t 
         int best = 0;
         for (int k = 1; k < K; k++)
             if (vlast[k] > vlast[best]) best = k;
-        carry = best;  // state of bin M-1
+        carry = (carry_in >= 0) ? carry_in : best;  // state of bin M-1
     }
     __syncthreads();
     for (int64_t t = nT - 1; t >= 0; t--) {
@@ -128,47 +134,88 @@ __global__ void __launch_bounds__(VT_NT) viterbi_backtrace_kernel(const uint8_t 
         for (int b = tid; b < n; b += VT_NT) states[s0 + b] = (double)sst[b];
         __syncthreads();
     }
+    // psi of the block's first bin applied to its state: the state of the bin in front of the block
+    if (tid == 0) carry_out[0] = (bp[0] >> (2 * carry)) & 3;
 }
 
-template <int K> int run(ehmm_session *s, const VitPar &P, double *states_out) {
+template <int K> int forward(ehmm_session *s, const VitPar &P) {
     const int64_t M = s->M;
     EHMM_TRY(s->viterbi.reserve(sizeof(double) * M));
-    EHMM_TRY(s->rc_tmp.reserve((size_t)M + 64));
-    uint8_t *bp = s->rc_tmp.as<uint8_t>();
+    EHMM_TRY(s->vit_bp.reserve((size_t)M + 64));
     EHMM_TRY(s->misc.reserve(256));
-    double *vlast = s->misc.as<double>();
     const size_t smem = sizeof(double) * 2 * K * VT_TILE + VT_TILE;
     static bool attr[EHMM_MAX_K + 1] = {false};
     if (!attr[K]) {
         EHMM_CK(cudaFuncSetAttribute(viterbi_forward_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr[K] = true;
     }
-    PROF(s, KID_VIT_FWD), viterbi_forward_kernel<K><<<1, VT_NT, smem, s->stream>>>(s->logFP.as<double>(), M, P, bp, vlast);
+    PROF(s, KID_VIT_FWD), viterbi_forward_kernel<K><<<1, VT_NT, smem, s->stream>>>(s->logFP.as<double>(), M, P,
+                                                                              s->vit_bp.as<uint8_t>(), s->misc.as<double>());
     EHMM_CK(cudaGetLastError());
-    PROF(s, KID_VIT_BWD), viterbi_backtrace_kernel<K><<<1, VT_NT, 0, s->stream>>>(bp, M, vlast, s->viterbi.as<double>());
+    return EHMM_OK;
+}
+
+template <int K> int backtrace(ehmm_session *s, int carry_in, int *carry_out, double *states_out) {
+    const int64_t M = s->M;
+    int *dcarry = reinterpret_cast<int *>(s->misc.as<double>() + 16);
+    PROF(s, KID_VIT_BWD), viterbi_backtrace_kernel<K><<<1, VT_NT, 0, s->stream>>>(
+        s->vit_bp.as<uint8_t>(), M, s->misc.as<double>(), carry_in, s->viterbi.as<double>(), dcarry);
     EHMM_CK(cudaGetLastError());
     if (states_out)
         EHMM_CK(cudaMemcpyAsync(states_out, s->viterbi.p, sizeof(double) * M, cudaMemcpyDeviceToHost, s->stream));
+    int hc = 0;
+    EHMM_CK(cudaMemcpyAsync(&hc, dcarry, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
     EHMM_CK(cudaStreamSynchronize(s->stream));
+    if (carry_out) *carry_out = hc;
     s->valid |= DS_VIT;
     return EHMM_OK;
+}
+
+void fill(VitPar &P, int K, const double *pi, const double *gamma, const double *vin) {
+    // host libm log(), i.e. the very values the reference's log(pi.t()) / log(gamma.col(k)) produce
+    for (int k = 0; k < K; k++) P.lpi[k] = log(pi[k]);
+    for (int i = 0; i < K; i++)
+        for (int k = 0; k < K; k++) P.lg[i * K + k] = log(gamma[i + k * K]);
+    P.has_vin = vin != nullptr;
+    for (int k = 0; k < K; k++) P.vin[k] = vin ? vin[k] : 0.0;
 }
 
 }  // namespace
 
 int viterbi(ehmm_session *s, const double *pi, const double *gamma, double *states_out) {
     EHMM_REQUIRE(s->m0 == 0 && s->Mtot == s->M, EHMM_ERR_STATE,
-                 "computeViterbiSequence runs on the whole chain; gather logFP to one session first");
+                 "computeViterbiSequence on a bin block: use ehmm_viterbi_forward / ehmm_viterbi_backtrace");
     VitPar P = {};
-    const int K = s->K;
-    // host libm log(), i.e. the very values the reference's log(pi.t()) / log(gamma.col(k)) produce
-    for (int k = 0; k < K; k++) P.lpi[k] = log(pi[k]);
-    for (int i = 0; i < K; i++)
-        for (int k = 0; k < K; k++) P.lg[i * K + k] = log(gamma[i + k * K]);
-    if (K == 2) return run<2>(s, P, states_out);
-    if (K == 3) return run<3>(s, P, states_out);
-    set_error("viterbi: K=%d unsupported", K);
+    fill(P, s->K, pi, gamma, nullptr);
+    if (s->K == 2) { EHMM_TRY(forward<2>(s, P)); return backtrace<2>(s, -1, nullptr, states_out); }
+    if (s->K == 3) { EHMM_TRY(forward<3>(s, P)); return backtrace<3>(s, -1, nullptr, states_out); }
+    set_error("viterbi: K=%d unsupported", s->K);
     return EHMM_ERR_ARG;
+}
+
+// bin-block form: the (max,+) recursion is serial over the chain, so blocks run one after the other;
+// v_in = LOGV of the bin in front of this block (NULL for the first block), v_out = LOGV of its last bin
+int viterbi_forward(ehmm_session *s, const double *pi, const double *gamma, const double *v_in, double *v_out) {
+    EHMM_REQUIRE((s->m0 == 0) == (v_in == nullptr), EHMM_ERR_ARG, "viterbi_forward: v_in is required exactly for blocks with m0 > 0");
+    VitPar P = {};
+    fill(P, s->K, pi, gamma, v_in);
+    if (s->K == 2) EHMM_TRY(forward<2>(s, P));
+    else if (s->K == 3) EHMM_TRY(forward<3>(s, P));
+    else { set_error("viterbi: K=%d unsupported", s->K); return EHMM_ERR_ARG; }
+    EHMM_CK(cudaMemcpyAsync(s->h_pinned + 320, s->misc.p, sizeof(double) * s->K, cudaMemcpyDeviceToHost, s->stream));
+    EHMM_CK(cudaStreamSynchronize(s->stream));
+    for (int k = 0; k < s->K; k++) v_out[k] = s->h_pinned[320 + k];
+    s->vit_forward_done = true;
+    return EHMM_OK;
+}
+
+// state_last: state of this block's last bin as decided by the next block, -1 for the chain's end;
+// state_prev: state of the bin in front of this block (to hand to the previous block)
+int viterbi_backtrace(ehmm_session *s, int state_last, int *state_prev, double *states_out) {
+    EHMM_REQUIRE(s->vit_forward_done, EHMM_ERR_STATE, "viterbi_backtrace without viterbi_forward");
+    EHMM_REQUIRE(state_last >= -1 && state_last < s->K, EHMM_ERR_ARG, "bad state %d", state_last);
+    if (s->K == 2) return backtrace<2>(s, state_last, state_prev, states_out);
+    return backtrace<3>(s, state_last, state_prev, states_out);
 }
 
 }  // namespace ehmm

@@ -232,6 +232,18 @@ class Session:
         check(lib.ehmm_viterbi(self._h, dptr(_f64(pi)), dptr(_cm(gamma)), dptr(out)))
         return out
 
+    def viterbi_forward(self, pi, gamma, v_in=None):
+        v_out = np.empty(self.K)
+        check(lib.ehmm_viterbi_forward(self._h, dptr(_f64(pi)), dptr(_cm(gamma)), dptr(None if v_in is None else _f64(v_in)),
+                                       dptr(v_out)))
+        return v_out
+
+    def viterbi_backtrace(self, state_last=-1, fetch=True):
+        out = np.empty(self.M) if fetch else None
+        prev = C.c_int()
+        check(lib.ehmm_viterbi_backtrace(self._h, int(state_last), C.byref(prev), dptr(out)))
+        return out, prev.value
+
     # -- rejection control -----------------------------------------------------------------
     def rng_set_state(self, state625):
         st = np.ascontiguousarray(state625, dtype=np.uint32)

@@ -228,4 +228,17 @@ class ShardedSession:
         return s[:-1] / s[-1]
 
     def viterbi(self, pi, gamma, fetch=True):
-        raise NotImplementedError("Viterbi runs on the whole chain: gather logFP into one Session")
+        """computeViterbiSequence over the blocks: the recursion is serial, so the ranks take turns
+        (K doubles forwards, one state backwards).  Returns this rank's block of the path."""
+        v = None
+        for r in range(self.world):
+            mine = self.local.viterbi_forward(pi, gamma, v) if r == self.rank else np.zeros(self.K)
+            v = self.comm.broadcast(mine, r)
+        state, out = -1, None
+        for r in range(self.world - 1, -1, -1):
+            if r == self.rank:
+                out, prev = self.local.viterbi_backtrace(state, fetch)
+            else:
+                prev = 0
+            state = int(self.comm.broadcast(np.array([float(prev)]), r)[0])
+        return out

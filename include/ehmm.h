@@ -120,6 +120,14 @@ int ehmm_marginal_probability(ehmm_session *s, double *out);
 /* computeViterbiSequence, src/computeViterbiSequence.cpp:12-54 (states_out: M doubles or NULL). */
 int ehmm_viterbi(ehmm_session *s, const double *pi, const double *gamma, double *states_out);
 
+/* Bin-block form of computeViterbiSequence: the (max,+) recursion is serial over the chain, so the
+ * blocks run one after the other handing on K doubles (forward) and one state (backtrace).
+ * v_in: LOGV of the bin in front of this block (NULL for the block that starts the chain);
+ * state_last: state of this block's last bin decided by the next block (-1 at the chain's end);
+ * state_prev: state of the bin in front of this block. */
+int ehmm_viterbi_forward(ehmm_session *s, const double *pi, const double *gamma, const double *v_in, double *v_out);
+int ehmm_viterbi_backtrace(ehmm_session *s, int state_last, int *state_prev, double *states_out);
+
 /* Sharded E-step (bin blocks across GPUs): phase 1 reduces this block to one
  * scaled K x K operator (op: K*K + 1 doubles = mantissa matrix row-major + log scale);
  * phase 2 applies the carries the host computed from all blocks' operators

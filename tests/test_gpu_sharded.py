@@ -79,6 +79,16 @@ def test_blocks_on_one_gpu(ehmm, oracle, K, cuts):
         m0, m1 = whole.maxstepprob(), blocks[-1].maxstepprob()
         assert np.allclose(m0["pi"], m1["pi"], rtol=1e-11) and np.allclose(m0["gamma"], m1["gamma"], rtol=1e-11)
         assert abs(whole.bic(5, 2) - blocks[0].bic(5, 2)) <= 1e-12 * abs(whole.bic(5, 2))
+        # Viterbi handed from block to block equals the whole-chain path bit for bit
+        want = whole.viterbi(th["pi"], th["gamma"])
+        v = None
+        for b in blocks:
+            v = b.viterbi_forward(th["pi"], th["gamma"], v)
+        state, parts = -1, []
+        for b in reversed(blocks):
+            path, state = b.viterbi_backtrace(state)
+            parts.append(path)
+        assert np.array_equal(np.concatenate(parts[::-1]), want)
         # rejection control with the global draw order
         diff = K == 3
         for p in (0.05, 0.9):
@@ -126,9 +136,11 @@ def _nccl_worker(rank, world, initfile, outdir):
     th = synth.THETA_CONSENSUS
     theta = dict(pi=th["pi"], gamma=th["gamma"], psi=[np.array([0.5, 2.0]), np.array([2.0, 2.0])])
     fit = em.emConsensus(theta, s, N, em.controlEM(maxIterEM=3))
+    th_new = fit["theta_new"]
+    vit = s.viterbi(th_new["pi"], th_new["gamma"])
     np.savez(os.path.join(outdir, "r%d.npz" % rank), par=em.unlist(fit["theta_new"]),
              bic=fit["controlHist"][-2]["bic"], q=fit["controlHist"][-2]["q"], L1=s.fetch("logProb1"),
-             state=s.rng_get_state())
+             state=s.rng_get_state(), vit=vit)
     s.close()
     dist.destroy_process_group()
 
@@ -155,6 +167,7 @@ def test_two_gpus_nccl(ehmm):
         fit = em.emConsensus(theta, s, N, em.controlEM(maxIterEM=3))
         L1 = s.fetch("logProb1")
         st = s.rng_get_state()
+        vit = s.viterbi(fit["theta_new"]["pi"], fit["theta_new"]["gamma"])
     par = em.unlist(fit["theta_new"])
     for i in range(2):
         assert np.max(np.abs(r[i]["par"] - par) / np.abs(par)) <= 1e-9
@@ -162,3 +175,5 @@ def test_two_gpus_nccl(ehmm):
         assert np.array_equal(r[i]["state"], st)
     got = np.vstack([r[0]["L1"], r[1]["L1"]])
     assert np.max(np.abs(np.exp(got) - np.exp(L1))) <= 1e-8
+    # the sharded Viterbi path (logFP differs from the single-GPU run in the last bits only)
+    assert np.mean(np.concatenate([r[0]["vit"], r[1]["vit"]]) != vit) <= 1e-4
