@@ -114,7 +114,7 @@ struct ehmm_session {
     bool stats_stale = false;  // datasets were replaced from the host; statistics must be recomputed
 
     // ---- forward-backward scratch ----
-    ehmm::DevBuf tileops, carries, tilestats, fbscal;  // fbscal: [ll, stats..., total op...]
+    ehmm::DevBuf tileops, carries, tilestats, fbscal, rangeops, rangecarry;  // fbscal: [ll, stats..., total op...]
     double h_pi[EHMM_MAX_K] = {0};
     double h_gamma[EHMM_MAX_K * EHMM_MAX_K] = {0};  // column-major as given
     double h_stats[ehmm::FB_MAX_STATS] = {0};       // K*K joint sums, then sum(P1*logf)

@@ -21,7 +21,14 @@ namespace ehmm {
 
 namespace {
 
-constexpr double LN2 = 0.693147180559945309417232121458;
+// 64-bit literals that are not encodable as instruction immediates are materialised with two moves
+// per use; kept in constant memory they are operands (or loaded once per thread).
+__constant__ double kC[10] = {
+    6.666666666666735130e-01, 3.999999999940941908e-01, 2.857142874366239149e-01, 2.222219843214978396e-01,
+    1.818357216161805012e-01, 1.531383769920937332e-01, 1.479819860511658591e-01,  // fdlibm Lg1..Lg7
+    6.93147180369123816490e-01, 1.90821492927058770002e-10,                          // ln2_hi, ln2_lo
+    0.693147180559945309417232121458};                                               // ln 2
+#define LN2 (kC[9])
 constexpr double TINY_LIN = 1e-290;  // below this a stored linear forward value is recomputed in log space
 
 template <int K> struct Op {
@@ -44,7 +51,7 @@ struct FBParams {
 template <int K> struct FBCfg;
 template <> struct FBCfg<2> { static constexpr int NT = 256, L = 5; };
 template <> struct FBCfg<3> { static constexpr int NT = 192, L = 5; };
-constexpr int CARRY_NT = 1024;
+template <int K> struct CarryCfg { static constexpr int NT = (K <= 2) ? 1024 : 512; };  // K = 3 needs > 64 registers
 
 // 2^-e for the binary exponent e encoded in the high word `hi` of a non-negative double
 // (normal numbers only; e = 0 for zero / subnormal / inf / nan)
@@ -76,11 +83,10 @@ __device__ __forceinline__ double log_pos(double x) {
     const double f = __hiloint2double(hi, lo) - 1.0;
     const double s = f * rcp_fast(2.0 + f);
     const double z = s * s, w = z * z;
-    const double t1 = w * fma(w, fma(w, 1.531383769920937332e-01, 2.222219843214978396e-01), 3.999999999940941908e-01);
-    const double t2 = z * fma(w, fma(w, fma(w, 1.479819860511658591e-01, 1.818357216161805012e-01),
-                                     2.857142874366239149e-01), 6.666666666666735130e-01);
+    const double t1 = w * fma(w, fma(w, kC[5], kC[3]), kC[1]);
+    const double t2 = z * fma(w, fma(w, fma(w, kC[6], kC[4]), kC[2]), kC[0]);
     const double R = t2 + t1, hfsq = 0.5 * f * f, dk = (double)e;
-    return dk * 6.93147180369123816490e-01 - ((hfsq - (s * (hfsq + R) + dk * 1.90821492927058770002e-10)) - f);
+    return dk * kC[7] - ((hfsq - (s * (hfsq + R) + dk * kC[8])) - f);
 }
 
 template <int K> __device__ __forceinline__ void op_identity(Op<K> &X) {
@@ -300,10 +306,11 @@ __global__ void __launch_bounds__(NT) fb_reduce_kernel(const double *__restrict_
 // mode 1: carries[t] = { A_t[K], lfT, B_t[K], lbT } for every tile, scal[0] = log-likelihood,
 //         scal[K*K+2 .. ] = forward vector after the last tile (K + 1 doubles)
 template <int K>
-__global__ void __launch_bounds__(CARRY_NT) fb_carry_kernel(const double *__restrict__ tileops, int64_t nT, int mode,
+__global__ void __launch_bounds__(CarryCfg<K>::NT) fb_carry_kernel(const double *__restrict__ tileops, int64_t nT, int mode,
                                                             const __grid_constant__ CarryIn cin,
                                                             double *__restrict__ carries, double *__restrict__ scal) {
     const double *startvec = cin.start, *endvec = cin.end;
+    constexpr int CARRY_NT = CarryCfg<K>::NT;
     constexpr int OPN = K * K + 1, NW = CARRY_NT / 32;
     __shared__ double sWarp[NW * OPN];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -380,6 +387,84 @@ __global__ void __launch_bounds__(CARRY_NT) fb_carry_kernel(const double *__rest
         for (int k = 0; k < K; k++) scal[OPN + 2 + K + k] = u.v[k];
         scal[OPN + 2 + 2 * K] = u.ls;
     }
+}
+
+// ---- two-level carry scan ------------------------------------------------------------------------
+// The tile operators (nT ~ 1e4 .. 6e4) are scanned in two levels so that no single CTA has to pull
+// them through one SM's load/store unit: R ranges of q consecutive tiles are reduced in parallel
+// (fb_range_reduce_kernel), fb_carry_kernel scans the R range operators, and
+// fb_range_apply_kernel expands the range carries to per-tile carries.
+constexpr int RANGE_NT = 128;
+
+template <int K>
+__global__ void __launch_bounds__(RANGE_NT) fb_range_reduce_kernel(const double *__restrict__ tileops, int64_t nT, int q,
+                                                                   double *__restrict__ rangeops) {
+    constexpr int OPN = K * K + 1, NW = RANGE_NT / 32;
+    extern __shared__ double sOps[];
+    __shared__ double sWarp[NW * OPN];
+    const int64_t t0 = (int64_t)blockIdx.x * q;
+    const int n = (int)max((int64_t)0, min((int64_t)q, nT - t0));
+    for (int i = threadIdx.x; i < n * OPN; i += RANGE_NT) sOps[i] = tileops[t0 * OPN + i];
+    __syncthreads();
+    const int per = (n + RANGE_NT - 1) / RANGE_NT;
+    const int a = min(n, (int)threadIdx.x * per), b = min(n, a + per);
+    Op<K> X;
+    op_identity(X);
+    for (int t = a; t < b; t++) X = op_mul<K>(X, op_load<K>(sOps + t * OPN));
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        Op<K> O = op_shfl_down<K>(X, d);
+        if (lane + d < 32) X = op_mul<K>(X, O);
+    }
+    if (lane == 0) op_store<K>(sWarp + w * OPN, X);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        Op<K> T = op_load<K>(sWarp);
+        for (int i = 1; i < NW; i++) T = op_mul<K>(T, op_load<K>(sWarp + i * OPN));
+        op_store<K>(rangeops + (int64_t)blockIdx.x * OPN, T);
+    }
+}
+
+// carries[t] = { A_t[K], lfT, B_t[K], lbT } from the carries of the range the tile belongs to
+template <int K>
+__global__ void __launch_bounds__(64) fb_range_apply_kernel(const double *__restrict__ tileops, int64_t nT, int q,
+                                                            const double *__restrict__ rangecarry,
+                                                            double *__restrict__ carries) {
+    constexpr int OPN = K * K + 1, CN = 2 * K + 2;
+    extern __shared__ double sm[];
+    double *sOps = sm;              // q * OPN
+    double *sOut = sm + q * OPN;    // q * CN
+    const int64_t t0 = (int64_t)blockIdx.x * q;
+    const int n = (int)max((int64_t)0, min((int64_t)q, nT - t0));
+    for (int i = threadIdx.x; i < n * OPN; i += 64) sOps[i] = tileops[t0 * OPN + i];
+    __syncthreads();
+    const double *rc = rangecarry + (int64_t)blockIdx.x * CN;
+    if (threadIdx.x == 0) {  // forward, sequential over the range
+        Vec<K> v;
+#pragma unroll
+        for (int k = 0; k < K; k++) v.v[k] = rc[k];
+        v.ls = rc[K];
+        for (int t = 0; t < n; t++) {
+#pragma unroll
+            for (int k = 0; k < K; k++) sOut[t * CN + k] = v.v[k];
+            sOut[t * CN + K] = v.ls;
+            v = vec_mul_op<K>(v, op_load<K>(sOps + t * OPN));
+        }
+    } else if (threadIdx.x == 32) {  // backward, on another warp
+        Vec<K> u;
+#pragma unroll
+        for (int k = 0; k < K; k++) u.v[k] = rc[K + 1 + k];
+        u.ls = rc[2 * K + 1];
+        for (int t = n - 1; t >= 0; t--) {
+#pragma unroll
+            for (int k = 0; k < K; k++) sOut[t * CN + K + 1 + k] = u.v[k];
+            sOut[t * CN + 2 * K + 1] = u.ls;
+            u = op_mul_vec<K>(op_load<K>(sOps + t * OPN), u);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n * CN; i += 64) carries[t0 * CN + i] = sOut[i];
 }
 
 // ---- kernel C: tile -> all outputs + statistics -------------------------------------------------
@@ -609,7 +694,7 @@ __global__ void __launch_bounds__(NT)
     if (tid < NS) {
         double s = sWarp[tid];
         for (int i = 1; i < NW; i++) s += sWarp[i * NS + tid];
-        tilestats[(int64_t)blockIdx.x * NS + tid] = s;
+        tilestats[(int64_t)tid * gridDim.x + blockIdx.x] = s;  // [statistic][tile]: coalesced for fb_stats_kernel
     }
 }
 
@@ -637,22 +722,21 @@ __global__ void fb_boundary_fix_kernel(int64_t M, int64_t nT, int TB, const __gr
     }
 }
 
-// deterministic sum of the per-tile statistics: out[i] = sum_t tilestats[t*NS + i]
+// deterministic sum of the per-tile statistics: out[i] = sum_t tilestats[i*nT + t]; one CTA per statistic
 __global__ void __launch_bounds__(256) fb_stats_kernel(const double *__restrict__ tilestats, int64_t nT, int NS,
                                                        double *__restrict__ out) {
     __shared__ double sh[256];
-    for (int i = 0; i < NS; i++) {
-        double s = 0.0;
-        for (int64_t t = threadIdx.x; t < nT; t += 256) s += tilestats[t * NS + i];
-        sh[threadIdx.x] = s;
-        __syncthreads();
-        for (int d = 128; d > 0; d >>= 1) {
-            if ((int)threadIdx.x < d) sh[threadIdx.x] += sh[threadIdx.x + d];
-            __syncthreads();
-        }
-        if (threadIdx.x == 0) out[i] = sh[0];
+    const int i = blockIdx.x;
+    double s = 0.0;
+    for (int64_t t = threadIdx.x; t < nT; t += 256) s += tilestats[(int64_t)i * nT + t];
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int d = 128; d > 0; d >>= 1) {
+        if ((int)threadIdx.x < d) sh[threadIdx.x] += sh[threadIdx.x + d];
         __syncthreads();
     }
+    if (threadIdx.x == 0) out[i] = sh[0];
+    (void)NS;
 }
 
 // statistics straight from the datasets (used when logProb1/logProb2 were stored from the host,
@@ -688,7 +772,7 @@ __global__ void __launch_bounds__(256)
     if (threadIdx.x < NS) {
         double t = sh[threadIdx.x];
         for (int i = 1; i < 8; i++) t += sh[i * NS + threadIdx.x];
-        part[(int64_t)blockIdx.x * NS + threadIdx.x] = t;
+        part[(int64_t)threadIdx.x * gridDim.x + blockIdx.x] = t;
     }
 }
 
@@ -722,12 +806,27 @@ template <int K> int64_t num_tiles(int64_t M) {
     return (M + TB - 1) / TB;
 }
 
+constexpr int MAX_RANGES = 592;  // 4 per SM
+constexpr int MAX_Q = 1024;      // tiles per range staged in shared memory
+
+// R ranges of q tiles each
+inline void range_split(int64_t nT, int &R, int &q) {
+    int64_t r = nT < 296 ? nT : 296;
+    int64_t qq = (nT + r - 1) / r;
+    if (qq > MAX_Q) { qq = MAX_Q; }
+    r = (nT + qq - 1) / qq;
+    R = (int)r;
+    q = (int)qq;
+}
+
 template <int K> int ensure_scratch(ehmm_session *s) {
     const int64_t nT = num_tiles<K>(s->M);
     EHMM_TRY(s->tileops.reserve(sizeof(double) * nT * (K * K + 1)));
     EHMM_TRY(s->carries.reserve(sizeof(double) * nT * (2 * K + 2)));
     EHMM_TRY(s->tilestats.reserve(sizeof(double) * nT * (K * K + 1)));
     EHMM_TRY(s->fbscal.reserve(sizeof(double) * scal_len<K>()));
+    EHMM_TRY(s->rangeops.reserve(sizeof(double) * MAX_RANGES * (K * K + 1)));
+    EHMM_TRY(s->rangecarry.reserve(sizeof(double) * MAX_RANGES * (2 * K + 2)));
     EHMM_TRY(s->logFP.reserve(sizeof(double) * s->M * K));
     EHMM_TRY(s->logBP.reserve(sizeof(double) * s->M * K));
     EHMM_TRY(s->logProb1.reserve(sizeof(double) * s->M * K));
@@ -739,6 +838,11 @@ template <int K> int ensure_scratch(ehmm_session *s) {
                                      (int)reduce_smem<K>()));
         EHMM_CK(cudaFuncSetAttribute(fb_apply_kernel<K, C::NT, C::L>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)apply_smem<K>()));
+        // the range kernels stage up to MAX_Q tile operators in shared memory
+        EHMM_CK(cudaFuncSetAttribute(fb_range_reduce_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)(sizeof(double) * MAX_Q * (K * K + 1))));
+        EHMM_CK(cudaFuncSetAttribute(fb_range_apply_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)(sizeof(double) * MAX_Q * (K * K + 1 + 2 * K + 2))));
         attr_done[K] = true;
     }
     return EHMM_OK;
@@ -753,9 +857,15 @@ template <int K> int launch_reduce(ehmm_session *s, const double *d_logf, int mo
     PROF(s, KID_FB_REDUCE), fb_reduce_kernel<K, C::NT, C::L><<<(unsigned)nT, C::NT, reduce_smem<K>(), s->stream>>>(
         d_logf, s->M, first, P, s->tileops.as<double>());
     EHMM_CK(cudaGetLastError());
+    int R, q;
+    range_split(nT, R, q);
+    EHMM_REQUIRE(R <= MAX_RANGES, EHMM_ERR_ARG, "expStep: %lld tiles exceed the carry scan's capacity", (long long)nT);
+    PROF(s, KID_FB_CARRY), fb_range_reduce_kernel<K><<<R, RANGE_NT, sizeof(double) * q * (K * K + 1), s->stream>>>(
+        s->tileops.as<double>(), nT, q, s->rangeops.as<double>());
+    EHMM_CK(cudaGetLastError());
     if (mode0_total) {
         CarryIn cin = {};
-        PROF(s, KID_FB_CARRY), fb_carry_kernel<K><<<1, CARRY_NT, 0, s->stream>>>(s->tileops.as<double>(), nT, 0, cin, nullptr,
+        PROF(s, KID_FB_CARRY), fb_carry_kernel<K><<<1, CarryCfg<K>::NT, 0, s->stream>>>(s->rangeops.as<double>(), R, 0, cin, nullptr,
                                                          s->fbscal.as<double>());
         EHMM_CK(cudaGetLastError());
     }
@@ -769,8 +879,13 @@ template <int K> int launch_apply(ehmm_session *s, const double *d_logf, const C
     const int64_t nT = num_tiles<K>(s->M);
     const int first = (s->m0 == 0) ? 1 : 0;
     double *scal = s->fbscal.as<double>();
-    PROF(s, KID_FB_CARRY), fb_carry_kernel<K><<<1, CARRY_NT, 0, s->stream>>>(s->tileops.as<double>(), nT, 1, cin, s->carries.as<double>(),
-                                                     scal);
+    int R, q;
+    range_split(nT, R, q);
+    PROF(s, KID_FB_CARRY), fb_carry_kernel<K><<<1, CarryCfg<K>::NT, 0, s->stream>>>(s->rangeops.as<double>(), R, 1, cin,
+                                                                          s->rangecarry.as<double>(), scal);
+    EHMM_CK(cudaGetLastError());
+    PROF(s, KID_FB_CARRY), fb_range_apply_kernel<K><<<R, 64, sizeof(double) * q * (K * K + 1 + 2 * K + 2), s->stream>>>(
+        s->tileops.as<double>(), nT, q, s->rangecarry.as<double>(), s->carries.as<double>());
     EHMM_CK(cudaGetLastError());
     PROF(s, KID_FB_APPLY), fb_apply_kernel<K, C::NT, C::L><<<(unsigned)nT, C::NT, apply_smem<K>(), s->stream>>>(
         d_logf, s->M, first, P, s->carries.as<double>(), s->logFP.as<double>(), s->logBP.as<double>(),
@@ -782,7 +897,7 @@ template <int K> int launch_apply(ehmm_session *s, const double *d_logf, const C
             s->logProb2.as<double>());
         EHMM_CK(cudaGetLastError());
     }
-    PROF(s, KID_FB_STATS), fb_stats_kernel<<<1, 256, 0, s->stream>>>(s->tilestats.as<double>(), nT, K * K + 1, scal + scal_stats_off<K>());
+    PROF(s, KID_FB_STATS), fb_stats_kernel<<<K * K + 1, 256, 0, s->stream>>>(s->tilestats.as<double>(), nT, K * K + 1, scal + scal_stats_off<K>());
     EHMM_CK(cudaGetLastError());
     return EHMM_OK;
 }
@@ -834,7 +949,7 @@ template <int K> int fetch_stats_impl(ehmm_session *s) {
                 s->M, has(s, DS_LOGF) ? s->logf.as<double>() : nullptr, s->logProb1.as<double>(),
                 s->logProb2.as<double>(), s->tilestats.as<double>());
             EHMM_CK(cudaGetLastError());
-            PROF(s, KID_FB_STATS), fb_stats_kernel<<<1, 256, 0, s->stream>>>(s->tilestats.as<double>(), nblk, NS,
+            PROF(s, KID_FB_STATS), fb_stats_kernel<<<NS, 256, 0, s->stream>>>(s->tilestats.as<double>(), nblk, NS,
                                                      s->fbscal.as<double>() + scal_stats_off<K>());
             EHMM_CK(cudaGetLastError());
             EHMM_CK(cudaMemcpyAsync(hp + 1, s->fbscal.as<double>() + scal_stats_off<K>(), sizeof(double) * NS,

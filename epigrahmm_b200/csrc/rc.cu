@@ -73,27 +73,51 @@ __global__ void __launch_bounds__(RC_NT) rc_count_kernel(RCSrc S, double p, int6
     }
 }
 
-// exclusive scan of n ints into int64 offsets; offsets[n] = total.  One CTA.
+// exclusive scan of n ints into int64 offsets; offsets[n] = total.  One CTA; each thread owns 16
+// consecutive counts per round (warp-shuffle scan of the thread sums, then the warp sums).
 __global__ void __launch_bounds__(1024) rc_scan_kernel(const int *__restrict__ counts, int64_t n,
                                                        int64_t *__restrict__ offsets) {
-    __shared__ int64_t sh[1024];
+    constexpr int IT = 16;
+    __shared__ int64_t swarp[32];
     __shared__ int64_t carry;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     if (threadIdx.x == 0) carry = 0;
     __syncthreads();
-    for (int64_t base = 0; base < n; base += 1024) {
-        const int64_t i = base + threadIdx.x;
-        const int64_t v = (i < n) ? counts[i] : 0;
-        sh[threadIdx.x] = v;
-        __syncthreads();
-        for (int d = 1; d < 1024; d <<= 1) {
-            int64_t t = (threadIdx.x >= d) ? sh[threadIdx.x - d] : 0;
-            __syncthreads();
-            sh[threadIdx.x] += t;
-            __syncthreads();
+    for (int64_t base = 0; base < n; base += 1024 * IT) {
+        const int64_t i0 = base + (int64_t)threadIdx.x * IT;
+        int v[IT];
+        int64_t tsum = 0;
+#pragma unroll
+        for (int k = 0; k < IT; k++) {
+            v[k] = (i0 + k < n) ? counts[i0 + k] : 0;
+            tsum += v[k];
         }
-        if (i < n) offsets[i] = carry + sh[threadIdx.x] - v;
+        int64_t incl = tsum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int64_t t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        if (lane == 31) swarp[w] = incl;
         __syncthreads();
-        if (threadIdx.x == 1023) carry += sh[1023];
+        if (w == 0) {
+            int64_t x = swarp[lane];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int64_t t = __shfl_up_sync(0xffffffffu, x, d);
+                if (lane >= d) x += t;
+            }
+            swarp[lane] = x;  // inclusive sums of the warps
+        }
+        __syncthreads();
+        int64_t run = carry + (w > 0 ? swarp[w - 1] : 0) + (incl - tsum);
+#pragma unroll
+        for (int k = 0; k < IT; k++) {
+            if (i0 + k < n) offsets[i0 + k] = run;
+            run += v[k];
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) carry += swarp[31];
         __syncthreads();
     }
     if (threadIdx.x == 0) offsets[n] = carry;
