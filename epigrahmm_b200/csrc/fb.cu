@@ -16,6 +16,7 @@
 //                      (reads 8K, writes 24K + 8K^2 B/bin)
 // followed by a deterministic reduction of the per-tile statistics.
 #include "common.cuh"
+#include "logtab.h"
 
 namespace ehmm {
 
@@ -23,13 +24,13 @@ namespace {
 
 // 64-bit literals that are not encodable as instruction immediates are materialised with two moves
 // per use; kept in constant memory they are operands (or loaded once per thread).
-__constant__ double kC[10] = {
+__constant__ double kC[14] = {
     6.666666666666735130e-01, 3.999999999940941908e-01, 2.857142874366239149e-01, 2.222219843214978396e-01,
     1.818357216161805012e-01, 1.531383769920937332e-01, 1.479819860511658591e-01,  // fdlibm Lg1..Lg7
     6.93147180369123816490e-01, 1.90821492927058770002e-10,                          // ln2_hi, ln2_lo
-    0.693147180559945309417232121458};                                               // ln 2
+    0.693147180559945309417232121458,                                                // ln 2
+    1.0 / 3.0, 1.0 / 5.0, -1.0 / 6.0, 1.0 / 7.0};                                    // log1p series (log_norm)
 #define LN2 (kC[9])
-constexpr double TINY_LIN = 1e-290;  // below this a stored linear forward value is recomputed in log space
 
 template <int K> struct Op {
     double m[K * K];  // row-major mantissa, m[i*K+l]
@@ -49,8 +50,10 @@ struct FBParams {
 };
 
 template <int K> struct FBCfg;
-template <> struct FBCfg<2> { static constexpr int NT = 256, L = 5; };
-template <> struct FBCfg<3> { static constexpr int NT = 192, L = 5; };
+// L odd keeps the chunk-strided shared-memory accesses conflict-free (L = 6 measured 8 % slower);
+// APPLY_CTAS = resident apply CTAs per SM the register budget is set for (4 spills and is slower)
+template <> struct FBCfg<2> { static constexpr int NT = 256, L = 5, APPLY_CTAS = 3; };
+template <> struct FBCfg<3> { static constexpr int NT = 192, L = 5, APPLY_CTAS = 3; };
 template <int K> struct CarryCfg { static constexpr int NT = (K <= 2) ? 1024 : 512; };  // K = 3 needs > 64 registers
 
 // 2^-e for the binary exponent e encoded in the high word `hi` of a non-negative double
@@ -71,22 +74,55 @@ __device__ __forceinline__ double rcp_fast(double x) {
     return fma(r, e, r);
 }
 
-// log(x) for positive normal x (the fdlibm e_log.c kernel, < 1 ulp), without the library
-// version's special-case paths; anything else falls back to log().
-__device__ __forceinline__ double log_pos(double x) {
-    int hi = __double2hiint(x);
-    const int lo = __double2loint(x);
-    if ((unsigned)(hi - 0x00100000) >= 0x7fe00000u) return log(x);
-    int e = (hi >> 20) - 1023;
-    hi = (hi & 0x000fffff) | 0x3ff00000;
-    if (hi > 0x3ff6a09e) { hi -= 0x00100000; e += 1; }  // mantissa above sqrt(2): halve it
-    const double f = __hiloint2double(hi, lo) - 1.0;
-    const double s = f * rcp_fast(2.0 + f);
-    const double z = s * s, w = z * z;
-    const double t1 = w * fma(w, fma(w, kC[5], kC[3]), kC[1]);
-    const double t2 = z * fma(w, fma(w, fma(w, kC[6], kC[4]), kC[2]), kC[0]);
-    const double R = t2 + t1, hfsq = 0.5 * f * f, dk = (double)e;
-    return dk * kC[7] - ((hfsq - (s * (hfsq + R) + dk * kC[8])) - f);
+// log(x) for positive normal x from a 128-interval table (tools/gen_logtab.py): the mantissa is
+// rotated into [sqrt(2)/2, sqrt(2)) as above, x = 2^e * c_i * (1 + r) with |r| <= 2^-8, and
+// log1p(r) is its series to r^7 (remainder < 2^-67).  11 fp64 instructions instead of ~28; error
+// below 2 ulp.  sT is the table staged in shared memory.
+__device__ __forceinline__ bool normal_pos(double x) {
+    return (unsigned)(__double2hiint(x) - 0x00100000) < 0x7fe00000u;
+}
+constexpr int HI_TINY = 0x03c00000;  // high word of 2^-963 ~ 1.3e-290: below it the linear forward value is rebuilt in log space
+__device__ __forceinline__ bool not_tiny(double x) {
+    return (unsigned)(__double2hiint(x) - HI_TINY) < (unsigned)(0x7ff00000 - HI_TINY);
+}
+// x must be a positive normal number (normal_pos)
+__device__ __forceinline__ double log_norm(double x, const double2 *sT) {
+    const int h2 = __double2hiint(x) + 0x95f62;  // 0x3ff00000 - 0x3fe6a09e
+    const int e = (h2 >> 20) - 1023;
+    const double2 t = sT[(h2 >> 13) & 127];
+    const double m = __hiloint2double((h2 & 0x000fffff) + 0x3fe6a09e, __double2loint(x));
+    const double r = fma(m, t.x, -1.0);
+    double q = fma(r, kC[13], kC[12]);
+    q = fma(r, q, kC[11]);
+    q = fma(r, q, -0.25);
+    q = fma(r, q, kC[10]);
+    q = fma(r, q, -0.5);
+    return fma((double)e, LN2, t.y) + fma(r * r, q, r);
+}
+
+// e_k = exp(f_k - max_l f_l): the entry of the maximum is exp(0) = 1 exactly, so K - 1 exponentials
+template <int K> __device__ __forceinline__ void shifted_exp(const double (&f)[K], double &m, double (&e)[K]) {
+    if constexpr (K == 2) {
+        const double d = f[0] - f[1], x = exp(-fabs(d));
+        m = fmax(f[0], f[1]);
+        e[0] = (d >= 0.0) ? 1.0 : x;
+        e[1] = (d >= 0.0) ? x : 1.0;
+        if (d != d) { e[0] = x; e[1] = x; }  // -inf - -inf: NaN, as exp(f - m) would give
+    } else if constexpr (K == 3) {
+        const int am = (f[0] >= f[1] && f[0] >= f[2]) ? 0 : (f[1] >= f[2] ? 1 : 2);
+        m = (am == 0) ? f[0] : (am == 1 ? f[1] : f[2]);
+        const double a = (am == 0) ? f[1] : f[0], b = (am == 2) ? f[1] : f[2];  // the two others, in order
+        const double ea = exp(a - m), eb = exp(b - m);
+        e[0] = (am == 0) ? 1.0 : ea;
+        e[1] = (am == 1) ? 1.0 : (am == 0 ? ea : eb);
+        e[2] = (am == 2) ? 1.0 : eb;
+    } else {
+        m = f[0];
+#pragma unroll
+        for (int k = 1; k < K; k++) m = fmax(m, f[k]);
+#pragma unroll
+        for (int k = 0; k < K; k++) e[k] = exp(f[k] - m);
+    }
 }
 
 template <int K> __device__ __forceinline__ void op_identity(Op<K> &X) {
@@ -208,14 +244,13 @@ __device__ __forceinline__ void load_tile(const double *__restrict__ logf, int64
 #pragma unroll
     for (int r = 0; r < L; r++) {
         int b = r * NT + threadIdx.x;
-        double m = f[r][0];
-#pragma unroll
-        for (int k = 1; k < K; k++) m = fmax(m, f[r][k]);
+        double m, e[K];
+        shifted_exp<K>(f[r], m, e);
         sM[b] = m;
 #pragma unroll
         for (int k = 0; k < K; k++) {
             if (KEEP_F) sF[k * TB + b] = f[r][k];
-            sE[k * TB + b] = exp(f[r][k] - m);
+            sE[k * TB + b] = e[k];
         }
     }
 }
@@ -469,28 +504,28 @@ __global__ void __launch_bounds__(64) fb_range_apply_kernel(const double *__rest
 
 // ---- kernel C: tile -> all outputs + statistics -------------------------------------------------
 template <int K, int NT, int L>
-__global__ void __launch_bounds__(NT)
+__global__ void __launch_bounds__(NT, FBCfg<K>::APPLY_CTAS)
     fb_apply_kernel(const double *__restrict__ logf, int64_t M, int first_is_start, const __grid_constant__ FBParams P,
                     const double *__restrict__ carries, double *__restrict__ logFP, double *__restrict__ logBP,
                     double *__restrict__ logProb1, double *__restrict__ logProb2, double *__restrict__ tilestats) {
     constexpr int TB = NT * L, NW = NT / 32, OPN = K * K + 1, NS = K * K + 1;
     extern __shared__ double smem[];
-    double *sF = smem;             // K*TB  logf
-    double *sM = sF + K * TB;      // TB    per-bin max
+    double2 *sT = reinterpret_cast<double2 *>(smem);  // 128 entries of the log table
+    double *sM = smem + 256;       // TB    per-bin max
     double *sA = sM + TB;          // K*TB  e_j, then alpha~_j (post-emission, chunk scale)
     double *sB = sA + K * TB;      // K*TB  beta~_j
-    double *sScF = sB + K * TB;    // TB    tile-local log scale of alpha~_j
-    double *sScB = sScF + TB;      // TB    tile-local log scale of beta~_j
-    double *sX = sScB + TB;        // 2*NT*K  lf exchange between neighbouring bins
-    double *sLast = sX + 2 * NT * K;  // L*K
-    double *sWarp = sLast + L * K;    // NW*OPN, later NW*NS for the statistics
+    double *sScF = sM;             // the forward pass replaces m_j by the tile-local log scale of alpha~_j
+    double *sU = sB + K * TB;      // NT    per chunk: log scale of beta~ behind it + forward scale at its end
+    double *sRow = sU + NT;        // (TB/32)*K  log alpha~ of the bin before every 32-bin row
+    double *sWarp = sRow + (TB / 32) * K;  // NW*OPN, later NW*NS for the statistics
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int64_t s0 = (int64_t)blockIdx.x * TB;
     const int nvalid = (int)min((int64_t)TB, M - s0);
     const bool special0 = first_is_start && blockIdx.x == 0;
     const double *cr = carries + (int64_t)blockIdx.x * (2 * K + 2);
 
-    load_tile<K, NT, L, true>(logf, M, s0, nvalid, sF, sM, sA);
+    if (tid < 128) sT[tid] = kLogTab[tid];
+    load_tile<K, NT, L, false>(logf, M, s0, nvalid, nullptr, sM, sA);
     __syncthreads();
     {
         Op<K> X = chunk_product<K, L, TB>(sA, sM, tid, nvalid, special0, P);
@@ -532,7 +567,6 @@ __global__ void __launch_bounds__(NT)
                     double wv[K];
 #pragma unroll
                     for (int k = 0; k < K; k++) { sB[k * TB + b] = u[k]; wv[k] = sA[k * TB + b] * u[k]; }
-                    sScB[b] = s;
 #pragma unroll
                     for (int r = 0; r < K; r++) {
                         double acc = P.g[r * K] * wv[0];
@@ -572,30 +606,65 @@ __global__ void __launch_bounds__(NT)
                     sScF[b] = s;
                 }
             }
+            // scale of beta~_b = ub.ls + (sum of m over the later bins of the chunk) = sU - sScF[b]
+            sU[tid] = ub.ls + s;
         }
     }
     __syncthreads();
 
-    // ---- epilogue: striped over bins, everything coalesced ----
+    // ---- epilogue: striped over bins, everything coalesced, no block-level synchronisation ----
     const double lfT = cr[K], lbT = cr[2 * K + 1];
     double acc[NS];
 #pragma unroll
     for (int i = 0; i < NS; i++) acc[i] = 0.0;
     const double lKK = -log((double)(K * K));
+    // log alpha~ of tile-local bin bb in the scale sScF[bb] from the log-domain recursion: used where
+    // the linear value underflowed (an emission below exp(-667) relative to the bin's largest)
+    auto slow_lf = [&](int bb, int k) -> double {
+        double ap[K], scp = 0.0, av;
+        if (bb > 0) {
+#pragma unroll
+            for (int i = 0; i < K; i++) ap[i] = sA[i * TB + bb - 1];
+            scp = sScF[bb - 1];
+        } else {
+#pragma unroll
+            for (int i = 0; i < K; i++) ap[i] = cr[i];
+        }
+        if (special0 && bb == 0) {
+            av = ap[k];
+        } else {
+            av = ap[0] * P.g[k];
+#pragma unroll
+            for (int i = 1; i < K; i++) av = fma(ap[i], P.g[i * K + k], av);
+        }
+        return log(av) + __ldg(logf + (int64_t)k * M + s0 + bb) + (scp - sScF[bb]);
+    };
+    // lane 0 of every 32-bin row needs log alpha~ of the bin before the row (another warp's bin)
+    for (int idx = tid; idx < (TB / 32) * K; idx += NT) {
+        const int row = idx / K, k = idx - row * K, bb = 32 * row - 1;
+        double v = 0.0;
+        if (row == 0) {
+            v = log(fmax(cr[k], 4.9406564584124654e-324));
+        } else if (bb < nvalid) {
+            const double x = sA[k * TB + bb];
+            v = not_tiny(x) ? log_norm(x, sT) : slow_lf(bb, k);
+        }
+        sRow[idx] = v;
+    }
+    __syncthreads();
 #pragma unroll 1
     for (int r = 0; r < L; r++) {
         const int b = r * NT + tid;
         const bool valid = b < nvalid;
         const int64_t j = s0 + b;
         const bool isfirst = special0 && b == 0;
-        double al[K], be[K], f[K], alp[K], lf[K], lb[K];
-        double scf = 0, scfp = 0, scb = 0, m = 0;
+        double al[K], be[K], f[K], alp[K], lf[K], lb[K], lZ;
+        double scf = 0, scfp = 0, scb = 0;
         if (valid) {
 #pragma unroll
-            for (int k = 0; k < K; k++) { al[k] = sA[k * TB + b]; be[k] = sB[k * TB + b]; f[k] = sF[k * TB + b]; }
+            for (int k = 0; k < K; k++) { al[k] = sA[k * TB + b]; be[k] = sB[k * TB + b]; f[k] = __ldg(logf + (int64_t)k * M + j); }
             scf = sScF[b];
-            scb = sScB[b];
-            m = sM[b];
+            scb = sU[b / L] - scf;
             if (b > 0) {
 #pragma unroll
                 for (int k = 0; k < K; k++) alp[k] = sA[k * TB + b - 1];
@@ -603,7 +672,6 @@ __global__ void __launch_bounds__(NT)
             } else {
 #pragma unroll
                 for (int k = 0; k < K; k++) alp[k] = cr[k];
-                scfp = 0.0;
             }
         } else {
 #pragma unroll
@@ -625,32 +693,33 @@ __global__ void __launch_bounds__(NT)
         }
         double Z = 0.0;
 #pragma unroll
-        for (int k = 0; k < K; k++) {
-            lf[k] = (al[k] >= TINY_LIN) ? log_pos(al[k]) : (log(a[k]) + f[k] + (scfp - scf));
-            lb[k] = log_pos(be[k]);
-            Z = fma(al[k], be[k], Z);
-        }
-        sX[(r & 1) * NT * K + tid * K + 0] = lf[0];
+        for (int k = 0; k < K; k++) Z = fma(al[k], be[k], Z);
+        // one test for the whole bin: every logarithm has a positive normal argument (the rule)
+        bool fast = normal_pos(Z);
 #pragma unroll
-        for (int k = 1; k < K; k++) sX[(r & 1) * NT * K + tid * K + k] = lf[k];
-        if (tid == NT - 1) {
+        for (int k = 0; k < K; k++) fast = fast && not_tiny(al[k]) && normal_pos(be[k]);
+        if (fast) {
 #pragma unroll
-            for (int k = 0; k < K; k++) sLast[r * K + k] = lf[k];
-        }
-        __syncthreads();
-        double lfp[K];
-        if (tid > 0) {
-#pragma unroll
-            for (int k = 0; k < K; k++) lfp[k] = sX[(r & 1) * NT * K + (tid - 1) * K + k];
-        } else if (r > 0) {
-#pragma unroll
-            for (int k = 0; k < K; k++) lfp[k] = sLast[(r - 1) * K + k];
+            for (int k = 0; k < K; k++) { lf[k] = log_norm(al[k], sT); lb[k] = log_norm(be[k], sT); }
+            lZ = log_norm(Z, sT);
         } else {
 #pragma unroll
-            for (int k = 0; k < K; k++) lfp[k] = log(fmax(alp[k], 4.9406564584124654e-324));
+            for (int k = 0; k < K; k++) {
+                lf[k] = not_tiny(al[k]) ? log(al[k]) : (log(a[k]) + f[k] + (scfp - scf));
+                lb[k] = log(be[k]);
+            }
+            lZ = log(Z);
+        }
+        // log alpha~ of the previous bin: the neighbouring lane has just computed it
+        double lfp[K];
+#pragma unroll
+        for (int k = 0; k < K; k++) lfp[k] = __shfl_up_sync(0xffffffffu, lf[k], 1);
+        if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < K; k++) lfp[k] = sRow[(b >> 5) * K + k];
         }
         if (valid) {
-            const double lZ = log_pos(Z), rZ = rcp_fast(Z);
+            const double rZ = rcp_fast(Z);
             double lp1[K], p1[K];
 #pragma unroll
             for (int k = 0; k < K; k++) {
@@ -671,8 +740,9 @@ __global__ void __launch_bounds__(NT)
                     const double ra = p1[l] * rcp_fast(a[l]);
 #pragma unroll
                     for (int i = 0; i < K; i++) {
+                        // (not clamped: may exceed 0 by the rounding of the O(1e4) scale terms, ~1e-12)
                         logProb2[(int64_t)(i * K + l) * M + j] =
-                            fmin(lp1[l] + ((((lfp[i] + d) + P.lg[i * K + l]) + f[l]) - lf[l]), 0.0);
+                            lp1[l] + ((((lfp[i] + d) + P.lg[i * K + l]) + f[l]) - lf[l]);
                         acc[i * K + l] = fma(alp[i] * P.g[i * K + l], ra, acc[i * K + l]);
                     }
                 }
@@ -712,7 +782,7 @@ __global__ void fb_boundary_fix_kernel(int64_t M, int64_t nT, int TB, const __gr
     const int64_t j = t * TB;
 #pragma unroll
     for (int i = 0; i < K; i++) {
-        if (cr[i] < TINY_LIN) {
+        if (!not_tiny(cr[i])) {
 #pragma unroll
             for (int l = 0; l < K; l++)
                 logProb2[(int64_t)(i * K + l) * M + j] =
@@ -783,7 +853,7 @@ template <int K> size_t reduce_smem() {
 template <int K> size_t apply_smem() {
     using C = FBCfg<K>;
     size_t TB = (size_t)C::NT * C::L;
-    return sizeof(double) * ((3 * K + 3) * TB + 2 * C::NT * K + C::L * K + (C::NT / 32) * (K * K + 1));
+    return sizeof(double) * (256 + (2 * K + 1) * TB + C::NT + (TB / 32) * K + (C::NT / 32) * (K * K + 1));
 }
 
 void fill_params(const ehmm_session *s, FBParams &P) {
