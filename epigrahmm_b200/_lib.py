@@ -1,7 +1,7 @@
 """ctypes binding of libehmm_b200.so (the C ABI declared in include/ehmm.h).
 
 There is no fallback: if the shared library is missing or fails to load, importing
-this module raises.  Build it with ``python -m epigrahmm_b200.build``.
+this module raises.  Build it with ``python epigrahmm_b200/build.py``.
 """
 from __future__ import annotations
 
@@ -24,7 +24,7 @@ class EhmmError(RuntimeError):
 
 if not os.path.exists(SO_PATH):
     raise ImportError(
-        "%s not found: the CUDA library has not been built (python -m epigrahmm_b200.build). "
+        "%s not found: the CUDA library has not been built (python epigrahmm_b200/build.py). "
         "epigrahmm_b200 has no CPU fallback." % SO_PATH)
 
 lib = C.CDLL(SO_PATH)
@@ -73,6 +73,7 @@ PROTOTYPES = {
     "ehmm_viterbi_backtrace": [_sess, C.c_int, C.POINTER(C.c_int), _dp],
     "ehmm_expstep_reduce": [_sess, _dp, _dp, _dp, _dp],
     "ehmm_expstep_apply": [_sess, _dp, _dp, _dp],
+    "ehmm_expstep_apply_ops": [_sess, _dp, C.c_int, C.c_int],
     "ehmm_estep_stats": [_sess, _dp],
     "ehmm_estep_row0": [_sess, _dp],
     "ehmm_estep_set_stats": [_sess, _dp, _dp, C.c_double],
@@ -100,6 +101,9 @@ PROTOTYPES = {
     "ehmm_fetch": [_sess, C.c_char_p, _dp, C.c_int64],
     "ehmm_device_ptr": [_sess, C.c_char_p, C.POINTER(C.c_void_p)],
     "ehmm_store": [_sess, C.c_char_p, _dp, C.c_int64, C.c_int64],
+    "ehmm_comm_open": [C.c_char_p, C.c_int, C.c_int, C.c_int64, C.c_double, C.POINTER(C.c_void_p)],
+    "ehmm_comm_allgather": [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p],
+    "ehmm_comm_close": [C.c_void_p],
 }
 _RESTYPE = {"ehmm_last_error": C.c_char_p, "ehmm_profile_name": C.c_char_p}
 

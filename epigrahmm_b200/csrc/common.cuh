@@ -131,6 +131,7 @@ struct ehmm_session {
     int64_t mtj_valid = 0;       // sub-stream windows valid for the state in mt_raw
     bool mtj_pending = false;    // ... being computed on stream2 (event ev)
     bool rng_dev_valid = false;  // mt_raw holds rng_state
+    bool rng_pending = false;    // the state after the last draw is on its way to h_pinned + 512 (rng_state[0] is already current)
     int rc_columns = 0;
     int rc_N = 0;
     int64_t rc_colcount[64] = {0};  // sharded form: flagged counts of this block per column
@@ -201,6 +202,10 @@ int fb_expstep(ehmm_session *s, const double *d_logf);
 int fb_reduce(ehmm_session *s, const double *d_logf, double *op_host);
 int fb_apply(ehmm_session *s, const double *fwd_carry, const double *bwd_carry, double *fwd_out);
 int fb_fetch_stats(ehmm_session *s);
+// RNG state on the host: a draw only books the new position (rng_note_advance) and queues the copy
+// of the 624 words; whoever needs the words waits for it here.
+void rng_note_advance(ehmm_session *s, int64_t n);
+int rng_sync_host(ehmm_session *s);
 inline bool has(const ehmm_session *s, unsigned bits) { return (s->valid & bits) == bits; }
 // emission.cu
 int emis_consensus(ehmm_session *s, const double *th1, const double *th2, int P, double minZero);

@@ -320,6 +320,7 @@ int run_rc(ehmm_session *s, const RCSrc &S, double p, int nrep, const double *un
             }
             EHMM_TRY(mt_generate(s, total, s->rc_unif.as<uint32_t>()));
             EHMM_CK(cudaMemcpyAsync(s->h_pinned + 512, s->mt_raw.p, sizeof(uint32_t) * 625, cudaMemcpyDeviceToHost, s->stream));
+            rng_note_advance(s, total);
             state_back = true;
         }
         PROF(s, KID_RC_APPLY), rc_apply_kernel<uint32_t><<<apply_grid(nblk, S.columns), RC_NT, 0, s->stream>>>(S, p, nblk, s->rc_scan.as<int64_t>(),
@@ -335,8 +336,7 @@ int run_rc(ehmm_session *s, const RCSrc &S, double p, int nrep, const double *un
         if (est > (int64_t)S.columns * s->M) est = (int64_t)S.columns * s->M;
         EHMM_TRY(mt_prefetch(s, est));
     }
-    EHMM_CK(cudaStreamSynchronize(s->stream));
-    if (state_back) memcpy(s->rng_state, s->h_pinned + 512, sizeof(uint32_t) * 625);
+    (void)state_back;  // the host does not wait for the tables: the next reader of the stream does
     s->rc_columns = S.columns;
     s->rc_N = nrep;
     if (consumed) *consumed = total;
@@ -402,6 +402,7 @@ int rc_apply_block(ehmm_session *s, const RCSrc &S, double p, int nrep, const in
         }
         EHMM_TRY(mt_advance(s, total));
         EHMM_CK(cudaMemcpyAsync(s->h_pinned + 512, s->mt_raw.p, sizeof(uint32_t) * 625, cudaMemcpyDeviceToHost, s->stream));
+        rng_note_advance(s, total);
         state_back = true;
     }
     dim3 grid((unsigned)nblk, (unsigned)S.columns);
@@ -410,13 +411,33 @@ int rc_apply_block(ehmm_session *s, const RCSrc &S, double p, int nrep, const in
         s->rc_buckets.as<double>(), nullptr);
     EHMM_CK(cudaGetLastError());
     if (total > 0) EHMM_TRY(mt_prefetch(s, total + 624));
-    EHMM_CK(cudaStreamSynchronize(s->stream));
-    if (state_back) memcpy(s->rng_state, s->h_pinned + 512, sizeof(uint32_t) * 625);
+    (void)state_back;
     s->rc_columns = S.columns;
     s->rc_N = nrep;
     s->rc_count_cols = 0;
     return EHMM_OK;
 }
+
+}  // namespace
+
+void rng_note_advance(ehmm_session *s, int64_t n) {
+    const int64_t E = (int64_t)s->rng_state[0] + n;  // R: mti counts the words used of the current block of 624
+    s->rng_state[0] = (uint32_t)(E <= 624 ? E : (E - 1) % 624 + 1);
+    s->rng_pending = true;
+}
+
+int rng_sync_host(ehmm_session *s) {
+    if (!s->rng_pending) return EHMM_OK;
+    EHMM_CK(cudaStreamSynchronize(s->stream));
+    const uint32_t *h = reinterpret_cast<const uint32_t *>(s->h_pinned + 512);
+    EHMM_REQUIRE(h[0] == s->rng_state[0], EHMM_ERR_RNG, "RNG position on the device (%u) differs from the booked one (%u)", h[0],
+                 s->rng_state[0]);
+    memcpy(s->rng_state, h, sizeof(uint32_t) * 625);
+    s->rng_pending = false;
+    return EHMM_OK;
+}
+
+namespace {
 
 struct TmpDev {
     void *p = nullptr;

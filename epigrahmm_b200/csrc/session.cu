@@ -501,6 +501,63 @@ int ehmm_expstep_apply(ehmm_session *s, const double *fwd_carry, const double *b
     return EHMM_OK;
 }
 
+namespace {
+// exact power-of-two renormalisation of a small non-negative vector with a natural-log scale
+void renorm_host(double *m, int n, double &ls) {
+    double mx = m[0];
+    for (int i = 1; i < n; i++) mx = m[i] > mx ? m[i] : mx;
+    if (!(mx > 0.0) || !std::isfinite(mx)) return;
+    int e;
+    frexp(mx, &e);
+    e -= 1;  // floor(log2(mx))
+    const double sc = ldexp(1.0, -e);
+    for (int i = 0; i < n; i++) m[i] *= sc;
+    ls += e * 0.693147180559945309417232121458;
+}
+}  // namespace
+
+// The sharded E-step's second half with the carries composed here: ops_all holds the P block
+// operators (K*K row-major mantissa + log scale each) gathered from all ranks; this block's forward
+// carry is pi * prod(ops[:rank]), its backward carry prod(ops[rank+1:]) * 1.
+int ehmm_expstep_apply_ops(ehmm_session *s, const double *ops_all, int P, int rank) {
+    EHMM_TRY(check_session(s));
+    EHMM_REQUIRE(s->reduce_pending, EHMM_ERR_STATE, "expstep_apply_ops without expstep_reduce");
+    EHMM_REQUIRE(ops_all && P >= 1 && rank >= 0 && rank < P, EHMM_ERR_ARG, "bad operator list");
+    const int K = s->K, ON = K * K + 1;
+    double fwd[EHMM_MAX_K + 1], bwd[EHMM_MAX_K + 1], t[EHMM_MAX_K];
+    for (int k = 0; k < K; k++) { fwd[k] = s->h_pi[k]; bwd[k] = 1.0; }
+    fwd[K] = 0.0;
+    bwd[K] = 0.0;
+    for (int r = 0; r < rank; r++) {
+        const double *A = ops_all + (size_t)r * ON;
+        for (int l = 0; l < K; l++) {
+            double acc = 0.0;
+            for (int i = 0; i < K; i++) acc += fwd[i] * A[i * K + l];
+            t[l] = acc;
+        }
+        for (int l = 0; l < K; l++) fwd[l] = t[l];
+        fwd[K] += A[K * K];
+        renorm_host(fwd, K, fwd[K]);
+    }
+    for (int r = P - 1; r > rank; r--) {
+        const double *A = ops_all + (size_t)r * ON;
+        for (int i = 0; i < K; i++) {
+            double acc = 0.0;
+            for (int l = 0; l < K; l++) acc += A[i * K + l] * bwd[l];
+            t[i] = acc;
+        }
+        for (int i = 0; i < K; i++) bwd[i] = t[i];
+        bwd[K] += A[K * K];
+        renorm_host(bwd, K, bwd[K]);
+    }
+    EHMM_TRY(fb_apply(s, fwd, bwd, nullptr));
+    s->reduce_pending = false;
+    s->valid |= DS_ESTEP;
+    s->stats_stale = false;
+    s->inner_part_blocks = 0;
+    return EHMM_OK;
+}
+
 int ehmm_estep_stats(ehmm_session *s, double *stats) {
     EHMM_TRY(check_session(s));
     EHMM_REQUIRE(has(s, DS_P1 | DS_P2) && stats, EHMM_ERR_STATE, "estep_stats: expStep has not run");
@@ -638,11 +695,13 @@ int ehmm_rng_set_state(ehmm_session *s, const uint32_t *state625) {
     memcpy(s->rng_state, state625, sizeof(uint32_t) * 625);
     s->rng_set = true;
     s->rng_dev_valid = false;
+    s->rng_pending = false;
     return EHMM_OK;
 }
 
 int ehmm_rng_get_state(ehmm_session *s, uint32_t *state625) {
     EHMM_REQUIRE(s && state625, EHMM_ERR_ARG, "null pointer");
+    EHMM_TRY(rng_sync_host(s));
     memcpy(state625, s->rng_state, sizeof(uint32_t) * 625);
     return EHMM_OK;
 }

@@ -183,6 +183,10 @@ class Session:
         check(lib.ehmm_expstep_apply(self._h, dptr(fwd), dptr(bwd), dptr(out)))
         return out
 
+    def expstep_apply_ops(self, ops, rank):
+        ops = _f64(ops)
+        check(lib.ehmm_expstep_apply_ops(self._h, dptr(ops), int(ops.shape[0]), int(rank)))
+
     def estep_stats(self):
         st = np.empty(self.K * self.K + 1)
         check(lib.ehmm_estep_stats(self._h, dptr(st)))

@@ -19,6 +19,8 @@ Everything exchanged is a few hundred bytes except the bucket vectors (columns x
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 
 from .session import Session
@@ -108,15 +110,66 @@ class TorchComm:
     def broadcast(self, a, src):
         return self.all_gather(a)[src]
 
-    def all_reduce_device(self, ptr, n):
-        """in-place sum of n doubles at device pointer ptr (NCCL over NVLink)"""
+    def all_reduce_device(self, ptr, n, stream=None):
+        """in-place sum of n doubles at device pointer ptr (NCCL over NVLink).  With `stream` (the
+        session's cudaStream_t) the collective is ordered on that stream -- after the kernels that
+        produced the data and before the ones that read it -- and the host does not wait."""
         key = ("dev", ptr, n)
         if key not in self._bufs:
             class _Buf:
                 __cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 3}
             self._bufs[key] = self.torch.as_tensor(_Buf(), device=self.device)
-        self.dist.all_reduce(self._bufs[key])
-        self.torch.cuda.current_stream().synchronize()
+        if stream is None:
+            self.dist.all_reduce(self._bufs[key])
+            self.torch.cuda.current_stream().synchronize()
+            return
+        if ("stream", stream) not in self._bufs:
+            self._bufs[("stream", stream)] = self.torch.cuda.ExternalStream(stream)
+        with self.torch.cuda.stream(self._bufs[("stream", stream)]):
+            self.dist.all_reduce(self._bufs[key])
+
+
+class ShmComm(TorchComm):
+    """TorchComm whose small host all-gathers go through the library's shared-memory exchange
+    (ehmm_comm_*, one node) instead of a collective: the vectors are a few hundred bytes and both
+    ends are host code, so a device collective would add two PCIe copies and a stream
+    synchronisation each.  Large or oddly typed arrays and the in-HBM all-reduce stay on torch."""
+    SLOT = 1 << 16
+
+    def __init__(self, dist, device=None, timeout_s=120.0):
+        super().__init__(dist, device)
+        import ctypes as C
+        import secrets
+        from . import _lib
+        self._lib, self._C = _lib, C
+        # a name unique to this job, chosen by rank 0
+        tok = [("/ehmm-%d-%s" % (os.getpid(), secrets.token_hex(6))) if self.rank == 0 else None]
+        dist.broadcast_object_list(tok, src=0)
+        h = C.c_void_p()
+        _lib.check(_lib.lib.ehmm_comm_open(tok[0].encode(), self.rank, self.world, self.SLOT, float(timeout_s), C.byref(h)))
+        self._h = h
+
+    def all_gather(self, a):
+        a = np.ascontiguousarray(a)
+        if a.nbytes > self.SLOT or a.dtype.hasobject:
+            return self._all_gather_general(a)
+        out = np.empty((self.world,) + a.shape, dtype=a.dtype)
+        self._lib.check(self._lib.lib.ehmm_comm_allgather(self._h, a.ctypes.data, a.nbytes, out.ctypes.data))
+        return out
+
+    def close(self):
+        if self._h is not None:
+            self._lib.lib.ehmm_comm_close(self._h)
+            self._h = None
+
+
+def make_comm(dist, device=None):
+    """the exchange for ranks of one node (the bench / driver contract); set EHMM_COMM=torch to keep
+    every exchange on torch.distributed (ranks on several nodes)"""
+    import os
+    if os.environ.get("EHMM_COMM", "shm") == "torch":
+        return TorchComm(dist, device)
+    return ShmComm(dist, device)
 
 
 def global_groups(counts, offsets, comm, m0, Mtot, controls=None, design=None):
@@ -172,7 +225,7 @@ class ShardedSession:
     """Session-compatible backend for epigrahmm_b200.em over one bin block per rank."""
 
     def __init__(self, key, M, K, device, dist, local=None, comm=None):
-        self.comm = comm or TorchComm(dist, device="cuda:%d" % device)
+        self.comm = comm or make_comm(dist, device="cuda:%d" % device)
         self.rank, self.world = self.comm.rank, self.comm.world
         sizes = self.comm.all_gather(np.array([M], dtype=np.int64)).ravel()
         self.Mtot, self.m0 = int(sizes.sum()), int(sizes[:self.rank].sum())
@@ -192,12 +245,17 @@ class ShardedSession:
         K = self.K
         op = self.local.expstep_reduce(pi, gamma, logf)
         ops = self.comm.all_gather(op)
-        fwd, bwd = combine_carries(ops, self.rank, np.append(np.asarray(pi, dtype=np.float64), 0.0), K)
-        tail = self.local.expstep_apply(fwd, bwd)          # forward vector after this block
-        ll_local = float(tail[K] + np.log(np.sum(tail[:K])))
+        if hasattr(self.local, "expstep_apply_ops"):       # carries composed inside the library, no wait
+            self.local.expstep_apply_ops(ops, self.rank)
+            stats = self.local.estep_stats()               # the E-step's one synchronisation
+            ll_local = self.local.loglik()                 # forward mass after this block (the last block's is the chain's)
+        else:                                              # host-resident backend (CPU tests)
+            fwd, bwd = combine_carries(ops, self.rank, np.append(np.asarray(pi, dtype=np.float64), 0.0), K)
+            tail = self.local.expstep_apply(fwd, bwd)      # forward vector after this block
+            ll_local = float(tail[K] + np.log(np.sum(tail[:K])))
+            stats = self.local.estep_stats()
         # one exchange: statistics (summed), logProb1[0,] (first block's), log-likelihood (last block's)
-        packed = self.comm.all_gather(np.concatenate([self.local.estep_stats(), self.local.fetch_logprob1_row0(),
-                                                      [ll_local]]))
+        packed = self.comm.all_gather(np.concatenate([stats, self.local.fetch_logprob1_row0(), [ll_local]]))
         ns = K * K + 1
         self.local.estep_set_stats(packed[:, :ns].sum(axis=0), packed[0, ns:ns + K], float(packed[-1, -1]))
 
@@ -210,7 +268,7 @@ class ShardedSession:
             self.local.rc_buckets_set(self.comm.all_reduce_sum(self.local.rc_buckets_host()))
         else:
             ptr, n = self.local.rc_buckets_device()
-            self.comm.all_reduce_device(ptr, n)
+            self.comm.all_reduce_device(ptr, n, stream=self.local.stream)
         return total
 
     def rc_consensus(self, p, uniforms=None):

@@ -134,6 +134,10 @@ int ehmm_viterbi_backtrace(ehmm_session *s, int state_last, int *state_prev, dou
  * (fwd/bwd: K + 1 doubles = vector + log scale). */
 int ehmm_expstep_reduce(ehmm_session *s, const double *pi, const double *gamma, const double *logf, double *op);
 int ehmm_expstep_apply(ehmm_session *s, const double *fwd_carry, const double *bwd_carry, double *fwd_out);
+/* phase 2 with the carries composed by the library: ops_all = the P operators gathered in rank
+ * order (P * (K*K + 1) doubles); forward carry = pi * prod(ops[:rank]), backward carry =
+ * prod(ops[rank+1:]) * 1.  Does not synchronise; ehmm_estep_stats / ehmm_loglik_value do. */
+int ehmm_expstep_apply_ops(ehmm_session *s, const double *ops_all, int P, int rank);
 /* raw sufficient statistics of the last expStep: K*K joint sums (j >= 1) then sum(P1 * logf). */
 int ehmm_estep_stats(ehmm_session *s, double *stats);
 /* logProb1[0,] of this block (K doubles): maxStepProb's pi comes from the first block's row. */
@@ -196,6 +200,18 @@ int ehmm_fetch(ehmm_session *s, const char *name, double *dst, int64_t n);
 int ehmm_device_ptr(ehmm_session *s, const char *name, void **ptr);
 /* load a dataset from the host (lets each exported function be called on its own inputs). */
 int ehmm_store(ehmm_session *s, const char *name, const double *src, int64_t rows, int64_t cols);
+
+/* ---- exchange of small host vectors between the ranks of one node -------------------------- */
+/* The bin-block sharded fit exchanges K x K block operators, sufficient statistics
+ * and flagged counts: hundreds of bytes, produced and consumed on the host.  These go through a
+ * POSIX shared-memory segment (name: "/..." unique per job, agreed through the launcher) instead of
+ * a device collective; NCCL carries the rejection tables (ehmm_rc_buckets_device).  Collective:
+ * every rank of the job calls open / allgather in the same order. */
+typedef struct ehmm_comm ehmm_comm;
+int ehmm_comm_open(const char *name, int rank, int world, int64_t slot_bytes, double timeout_s, ehmm_comm **out);
+/* in: nbytes (<= slot_bytes) from this rank; out: world * nbytes in rank order */
+int ehmm_comm_allgather(ehmm_comm *c, const void *in, int64_t nbytes, void *out);
+int ehmm_comm_close(ehmm_comm *c);
 
 #ifdef __cplusplus
 }

@@ -216,3 +216,40 @@ def test_rc_offsets_and_carries():
         for q in range(P - 1, r, -1):
             u, lu = ops[q, :9].reshape(3, 3) @ u, lu + ops[q, 9]
         assert np.allclose(np.log(bwd[:K]) + bwd[K], np.log(u) + lu, rtol=1e-12)
+
+
+def _comm_worker(rank, world, initfile, outdir):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from epigrahmm_b200 import sharded
+    dist.init_process_group("gloo", init_method="file://" + initfile, rank=rank, world_size=world)
+    ok = True
+    for kind in ("shm", "torch"):
+        os.environ["EHMM_COMM"] = kind
+        comm = sharded.make_comm(dist)
+        assert isinstance(comm, sharded.ShmComm) == (kind == "shm")
+        for it in range(300):                      # many epochs: both banks, ranks drifting apart
+            n = 1 + (it * 7) % 50
+            a = np.arange(n, dtype=np.float64) * (rank + 1) + it
+            got = comm.all_gather(a)
+            ok &= got.shape == (world, n) and all(np.array_equal(got[r], np.arange(n) * (r + 1.0) + it) for r in range(world))
+            if it % 3 == rank:                     # uneven pacing
+                _ = np.linalg.norm(np.ones(2000))
+        cnt = comm.all_gather(np.array([rank, 10 * rank], dtype=np.int64))
+        ok &= cnt.dtype == np.int64 and np.array_equal(cnt, [[r, 10 * r] for r in range(world)])
+        ok &= np.array_equal(comm.all_reduce_sum(np.array([1.0, rank])), [world, sum(range(world))])
+        ok &= np.array_equal(comm.broadcast(np.array([float(rank)]), world - 1), [world - 1.0])
+        big = comm.all_gather(np.full(20000, float(rank)))      # larger than a slot: the torch path
+        ok &= big.shape == (world, 20000) and all(np.all(big[r] == r) for r in range(world))
+        if kind == "shm":
+            comm.close()
+    open(os.path.join(outdir, "ok%d" % rank), "w").write(str(bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_shared_memory_exchange_three_ranks():
+    """ehmm_comm_* (the host exchange of the sharded fit) against torch.distributed, world size 3"""
+    import torch.multiprocessing as mp
+    with tempfile.TemporaryDirectory() as td:
+        mp.spawn(_comm_worker, args=(3, os.path.join(td, "init"), td), nprocs=3, join=True)
+        assert [open(os.path.join(td, "ok%d" % r)).read() for r in range(3)] == ["True"] * 3
