@@ -24,7 +24,8 @@ constexpr int64_t JW = (int64_t)1 << LOG2J;  // words per sub-stream
 constexpr int LEVELS = 15;                   // up to 2^15 sub-streams = 4.3e9 draws per call
 constexpr int MT_N = 624, MT_M = 397, MT_D = MT_N - MT_M;  // 227
 constexpr int EXPW = mtpoly::DEG + MT_N - 1;               // words a jump needs (20560)
-constexpr int JUMP_NT = 320;
+constexpr int JUMP_NT = 640;                                // one output word per thread (624 used)
+constexpr int JUMP_SPLIT = 8;                              // CTAs per window, each takes a slice of the coefficient list
 constexpr int ZERO_IDX = EXPW + 8;                         // index whose word is 0 for every output lane
 constexpr int BUFW = ZERO_IDX + MT_N + 8;                  // expanded words + zeroed tail
 constexpr int MAX_IDX = 20480;                             // index-list capacity per level (uint16)
@@ -48,41 +49,40 @@ __global__ void mt_base_kernel(const uint32_t *__restrict__ state, uint32_t *__r
         S[i] = (i < MT_N - 1) ? state[1 + i + 1] : (state[1 + MT_M] ^ twist(state[1], state[2]));
 }
 
-// S[(base + c)] = jump(S[c]) by the polynomial whose set coefficients are listed in `idx`
-// (nidx entries, padded to a multiple of 8 with ZERO_IDX, which addresses a zeroed region)
+// S[(base + c)] ^= partial jump(S[c]) by the polynomial whose set coefficients are listed in `idx`
+// (nidx entries, padded to a multiple of 8 with ZERO_IDX, which addresses a zeroed region).  The
+// coefficient list is split over gridDim.y CTAs (a window is latency-bound in one CTA and the
+// doubling rounds are serial); the destination windows are zeroed beforehand and accumulate by XOR.
 __global__ void __launch_bounds__(JUMP_NT) mt_jump_kernel(const uint16_t *__restrict__ idx, int nidx,
                                                           uint32_t *__restrict__ S, int base) {
     extern __shared__ uint32_t sm[];
     uint32_t *buf = sm;                                                   // EXPW words + zero pad
-    uint16_t *sidx = reinterpret_cast<uint16_t *>(sm + BUFW);             // nidx entries
+    uint16_t *sidx = reinterpret_cast<uint16_t *>(sm + BUFW);             // this CTA's slice of the list
     const int tid = threadIdx.x;
     const uint32_t *src = S + (size_t)blockIdx.x * MT_N;
     uint32_t *dst = S + (size_t)(base + blockIdx.x) * MT_N;
+    const int per = ((nidx / 8 + gridDim.y - 1) / gridDim.y) * 8;         // entries per slice (multiple of 8)
+    const int q0 = min(nidx, (int)blockIdx.y * per), q1 = min(nidx, q0 + per);
     for (int i = tid; i < MT_N; i += JUMP_NT) buf[i] = src[i];
     for (int i = EXPW + tid; i < BUFW; i += JUMP_NT) buf[i] = 0u;
-    for (int i = tid; i < nidx / 2; i += JUMP_NT)
-        reinterpret_cast<uint32_t *>(sidx)[i] = reinterpret_cast<const uint32_t *>(idx)[i];
+    for (int i = tid; i < (q1 - q0) / 2; i += JUMP_NT)
+        reinterpret_cast<uint32_t *>(sidx)[i] = reinterpret_cast<const uint32_t *>(idx + q0)[i];
     __syncthreads();
     for (int b0 = MT_N; b0 < EXPW; b0 += MT_D) {
         const int i = b0 + tid;
         if (tid < MT_D && i < EXPW) buf[i] = buf[i - MT_D] ^ twist(buf[i - MT_N], buf[i - MT_N + 1]);
         __syncthreads();
     }
-    if (tid < MT_N / 2) {
-        uint32_t a0 = 0, a1 = 0;
-        const uint32_t *b0p = buf + tid, *b1p = buf + tid + MT_N / 2;
-        for (int q = 0; q < nidx; q += 8) {
+    if (tid < MT_N) {
+        uint32_t a0 = 0;
+        const uint32_t *bp = buf + tid;
+        for (int q = 0; q < q1 - q0; q += 8) {
             const uint4 pk = *reinterpret_cast<const uint4 *>(sidx + q);  // 8 indices, broadcast
             const unsigned w[4] = {pk.x, pk.y, pk.z, pk.w};
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const unsigned i0 = w[j] & 0xffffu, i1 = w[j] >> 16;
-                a0 ^= b0p[i0] ^ b0p[i1];
-                a1 ^= b1p[i0] ^ b1p[i1];
-            }
+            for (int j = 0; j < 4; j++) a0 ^= bp[w[j] & 0xffffu] ^ bp[w[j] >> 16];
         }
-        dst[tid] = a0;
-        dst[tid + MT_N / 2] = a1;
+        if (a0) atomicXor(dst + tid, a0);
     }
 }
 
@@ -201,7 +201,9 @@ int mt_prepare(ehmm_session *s, cudaStream_t st, int64_t max_draws) {
     for (int k = 0; ((int64_t)1 << k) < P; k++) {
         const int64_t base = (int64_t)1 << k;
         const int64_t cnt = (P - base < base) ? (P - base) : base;
-        mt_jump_kernel<<<(unsigned)cnt, JUMP_NT, JUMP_SMEM, st>>>(idx + (size_t)k * MAX_IDX, g_nidx[k], S, (int)base);
+        EHMM_CK(cudaMemsetAsync(S + (size_t)base * MT_N, 0, sizeof(uint32_t) * MT_N * (size_t)cnt, st));
+        mt_jump_kernel<<<dim3((unsigned)cnt, JUMP_SPLIT), JUMP_NT, JUMP_SMEM, st>>>(idx + (size_t)k * MAX_IDX, g_nidx[k], S,
+                                                                                  (int)base);
         EHMM_CK(cudaGetLastError());
         s->launches[KID_MT]++;
     }
