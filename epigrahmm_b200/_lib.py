@@ -57,6 +57,7 @@ PROTOTYPES = {
     "ehmm_set_design_n": [_sess, C.c_int, C.c_int, _bp],
     "ehmm_set_design": [_sess, C.c_int, _bp],
     "ehmm_loglik_consensus": [_sess, _dp, _dp, C.c_int, C.c_double],
+    "ehmm_loglik_consensus_zinb": [_sess, _dp, _dp, C.c_int, C.c_double],
     "ehmm_loglik_init": [_sess, _dp, _dp],
     "ehmm_loglik_differential_hmm": [_sess, _dp, _dp, C.c_double],
     "ehmm_inner_expstep": [_sess, _dp, _dp, C.c_double],
@@ -91,6 +92,7 @@ PROTOTYPES = {
     "ehmm_reweight": [C.c_int, _dp, C.c_int64, C.c_double, _dp, C.c_int64, _lp],
     "ehmm_aggregate": [C.c_int, _dp, C.c_int64, _ip, C.c_int64, _dp],
     "ehmm_glm_nb": [_sess, C.c_int, _dp, C.c_int, _dp, _dp],
+    "ehmm_glm_zinb": [_sess, C.c_int, _dp, C.c_int, C.c_double, _dp, _dp],
     "ehmm_glm_nb_batch": [_sess, C.c_int, C.POINTER(C.c_int), _dp, C.c_int, _dp, _dp],
     "ehmm_glm_mix_nb": [_sess, _dp, C.c_double, _dp, _dp],
     "ehmm_profile_kernels": [],

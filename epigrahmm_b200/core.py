@@ -32,19 +32,25 @@ def enumeratePatterns(peaks, condition):
     return group, ref
 
 
-def estimateCoefficients(z, counts, offsets, control, type_):
-    """R/base-utils.R:282-320 (dist = 'nb')"""
+def estimateCoefficients(z, counts, offsets, control, type_, dist="nb"):
+    """R/base-utils.R:282-320"""
     r = (np.asarray(counts, dtype=np.float64) + 1.0) / np.exp(offsets)
     par = []
     for x in (z.min(), z.max()):
         v = r[z == x].ravel()
         mu, s2 = v.mean(), v.var(ddof=1)
         disp = control["maxDisp"] if s2 <= mu else min(mu ** 2 / (s2 - mu), control["maxDisp"])
-        par.append((mu, disp))
+        zip_ = max(0.01, (s2 - mu) / (s2 + mu ** 2 - mu))
+        par.append((mu, disp, zip_))
     if type_ == "differential":
-        p1 = np.log(np.array(par[0]))
-        return [p1, np.log(np.array(par[1])) - p1]
-    return [np.array([math.log(par[0][0]), par[0][1]]), np.array([math.log(par[1][0]), par[1][1]])]
+        if dist != "nb":
+            raise NotImplementedError("the differential model with dist='zinb' is not on the accelerated path yet")
+        p1 = np.log(np.array(par[0][:2]))
+        return [p1, np.log(np.array(par[1][:2])) - p1]
+    first = [math.log(par[0][0]), par[0][1]]
+    if dist == "zinb":
+        first = [math.log(par[0][2])] + first
+    return [np.array(first), np.array([math.log(par[1][0]), par[1][1]])]
 
 
 def initializer(counts, offsets, control, device=0, key="initializer"):
@@ -69,8 +75,8 @@ def _stream():
     return rng.GLOBAL
 
 
-def consensusHMM(counts, offsets, peaks, condition, control, controls=None, device=0, key=None, session=None):
-    """R/base-core.R:163-228 (dist = 'nb').  Returns dict(session, theta, history)."""
+def consensusHMM(counts, offsets, peaks, condition, control, controls=None, device=0, key=None, session=None, dist="nb"):
+    """R/base-core.R:163-228.  Returns dict(session, theta, history)."""
     counts = np.asarray(counts)
     M, N = counts.shape
     z, _ = enumeratePatterns(np.asarray(peaks), condition)
@@ -78,12 +84,12 @@ def consensusHMM(counts, offsets, peaks, condition, control, controls=None, devi
     s = session or Session(key or "epigraHMM.h5", M, 2, device)
     s.set_data(counts, offsets, ctrl)
     s.build_groups()                  # R/base-core.R:184-198 on the device
-    psi = estimateCoefficients(z, counts, offsets, control, "consensus")
-    if ctrl is not None:
-        psi = [np.array([p[0], 0.0, p[1]]) for p in psi]
+    psi = estimateCoefficients(z, counts, offsets, control, "consensus", dist)
+    if ctrl is not None:   # a zero coefficient after every intercept (R/base-utils.R:305-316, ifControls)
+        psi = [np.concatenate([np.ravel([[v, 0.0] for v in p[:-1]]), p[-1:]]) for p in psi]
     theta = dict(pi=np.array([0.999, 0.001]), gamma=em.estimateTransitionProb(z, 2), psi=psi)
     s.rng_set_state(_stream().state)
-    fit = em.emConsensus(theta, s, N, control)
+    fit = em.emConsensus(theta, s, N, control, dist=dist)
     _stream().state[:] = s.rng_get_state()
     th = fit["theta_new"]
     s.viterbi(th["pi"], th["gamma"], fetch=False)
@@ -131,10 +137,12 @@ def differentialHMM(counts, offsets, peaks, condition, control, device=0, key=No
 
 def epigraHMM(counts, offsets, peaks, condition, control, type="consensus", dist="nb", **kw):
     """epigraHMM() (R/epigraHMM.R:39-90) on arrays."""
-    if dist != "nb":
-        raise NotImplementedError("dist='zinb' is not on the accelerated path yet")
+    if dist not in ("nb", "zinb"):
+        raise ValueError("dist must be 'nb' or 'zinb'")
     if type == "consensus":
-        return consensusHMM(counts, offsets, peaks, condition, control, **kw)
+        return consensusHMM(counts, offsets, peaks, condition, control, dist=dist, **kw)
     if type == "differential":
+        if dist != "nb":
+            raise NotImplementedError("the differential model with dist='zinb' is not on the accelerated path yet")
         return differentialHMM(counts, offsets, peaks, condition, control, **kw)
     raise ValueError("type must be 'consensus' or 'differential'")

@@ -208,7 +208,7 @@ void rng_note_advance(ehmm_session *s, int64_t n);
 int rng_sync_host(ehmm_session *s);
 inline bool has(const ehmm_session *s, unsigned bits) { return (s->valid & bits) == bits; }
 // emission.cu
-int emis_consensus(ehmm_session *s, const double *th1, const double *th2, int P, double minZero);
+int emis_consensus(ehmm_session *s, const double *th1, const double *th2, int P, double minZero, const double *zi = nullptr);
 int emis_init(ehmm_session *s, const double *psi1, const double *psi2);
 int emis_differential_hmm(ehmm_session *s, const double *delta, const double *psi, double minZero);
 int emis_inner_estep(ehmm_session *s, const double *delta, const double *psi, double minZero);
@@ -233,6 +233,7 @@ int mt_advance(ehmm_session *s, int64_t n);
 int mt_prefetch(ehmm_session *s, int64_t max_draws);
 // glm.cu
 int glm_nb(ehmm_session *s, int column, const double *par, int P, double *value, double *grad);
+int glm_zinb(ehmm_session *s, int column, const double *par, int P, double minZero, double *value, double *grad);
 int glm_nb_batch(ehmm_session *s, int ncols, const int *columns, const double *pars, int P, double *values, double *grads);
 int glm_mix_nb(ehmm_session *s, const double *par, double minZero, double *value, double *grad);
 // viterbi.cu

@@ -23,6 +23,7 @@ struct EmisParams {
     double lsize[MAX_DENS];  // log(size)
     double lgs[MAX_DENS];    // lgamma(size)
     double minZero, lminZero, thr;
+    double z0, z1;           // zero-inflation predictor of density 0 (ZINB background): z0 [+ z1*ctrl] + offset
     int tabn;
 };
 
@@ -56,8 +57,17 @@ __device__ __forceinline__ double plus_min_zero(double l, const EmisParams &P) {
     return (l > P.thr) ? l : log(exp(l) + P.minZero);
 }
 
-// loglikConsensusHMM (NB): LL[j,k] = sum_i log(NB(y_ji; mu=exp(th_k0 [+ th_k1*ctrl_ji] + o_ji), size_k) + minZero)
-template <bool CTRL, bool PLUS_MZ>
+// zero-inflated background cell (R/base-loglikelihood.R:124-133): l01 = log(dnbinom(x) + minZero);
+// for x = 0 the reference's ll00 is the same number
+__device__ __forceinline__ double zinb_cell(int x, double l01, double xbeta) {
+    const double zip = 1.0 / (1.0 + exp(-xbeta));
+    const double l1mz = log(1.0 - zip);
+    return (x == 0) ? log(zip + exp(l1mz + l01)) : (l1mz + l01);
+}
+
+// loglikConsensusHMM: LL[j,k] = sum_i log(NB(y_ji; mu=exp(th_k0 [+ th_k1*ctrl_ji] + o_ji), size_k) + minZero);
+// ZI: the background state is zero-inflated (dist = 'zinb')
+template <bool CTRL, bool PLUS_MZ, bool ZI = false>
 __global__ void __launch_bounds__(EM_NT)
     emis_consensus_kernel(int64_t M, int N, const int32_t *__restrict__ y, const double *__restrict__ off,
                           const double *__restrict__ ctrl, const __grid_constant__ EmisParams P,
@@ -79,6 +89,7 @@ __global__ void __launch_bounds__(EM_NT)
             }
             double l0 = nb_logpmf(x, e0, 0, P, tab), l1 = nb_logpmf(x, e1, 1, P, tab);
             if (PLUS_MZ) { l0 = plus_min_zero(l0, P); l1 = plus_min_zero(l1, P); }
+            if (ZI) l0 = zinb_cell(x, l0, (CTRL ? (P.z0 + P.z1 * __ldg(ctrl + c)) : P.z0) + o);
             a0 += l0;
             a1 += l1;
         }
@@ -93,7 +104,7 @@ __global__ void __launch_bounds__(EM_NT)
 // once per group into a table and each bin gathers them: 4N B/bin of ids instead of 12N B/bin of
 // counts+offsets, and no transcendental work in the M*N stream.  Values are bit-identical to the
 // per-cell kernels (same function of the same inputs, same summation order).
-template <bool CTRL, bool PLUS_MZ>
+template <bool CTRL, bool PLUS_MZ, bool ZI = false>
 __global__ void __launch_bounds__(EM_NT)
     group_table_consensus_kernel(int64_t G, const double *__restrict__ uy, const double *__restrict__ uoff,
                                  const double *__restrict__ uctrl, const __grid_constant__ EmisParams P,
@@ -114,6 +125,7 @@ __global__ void __launch_bounds__(EM_NT)
     }
     double l0 = nb_logpmf(x, e0, 0, P, tab), l1 = nb_logpmf(x, e1, 1, P, tab);
     if (PLUS_MZ) { l0 = plus_min_zero(l0, P); l1 = plus_min_zero(l1, P); }
+    if (ZI) l0 = zinb_cell(x, l0, (CTRL ? (P.z0 + P.z1 * uctrl[g]) : P.z0) + o);
     E[g] = make_double2(l0, l1);
 }
 
@@ -377,7 +389,31 @@ void fill_diff(EmisParams &P, const double *psi) {
 
 }  // namespace
 
-int emis_consensus(ehmm_session *s, const double *th1, const double *th2, int P_, double minZero) {
+namespace {
+template <bool CTRL, bool ZI> int launch_consensus(ehmm_session *s, const EmisParams &P) {
+    const int g = grid_for(s->M);
+    if (use_groups(s, 2)) {
+        EHMM_TRY(s->gtab.reserve(sizeof(double2) * (size_t)(s->G + 1)));
+        const unsigned gb = (unsigned)((s->G + 1 + EM_NT - 1) / EM_NT);
+        PROF(s, KID_EMIS_TAB), group_table_consensus_kernel<CTRL, true, ZI><<<gb, EM_NT, 0, s->stream>>>(
+            s->G, s->u_chip.as<double>(), s->u_off.as<double>(), CTRL ? s->u_ctrl.as<double>() : nullptr, P,
+            s->lgtab.as<double>(), s->gtab.as<double2>());
+        EHMM_CK(cudaGetLastError());
+        PROF(s, KID_EMIS_GATHER), gather_consensus_kernel<<<g, EM_NT, 0, s->stream>>>(
+            s->M, s->N, s->group.as<int32_t>(), s->gtab.as<double2>(), s->logf.as<double>());
+        EHMM_CK(cudaGetLastError());
+        return EHMM_OK;
+    }
+    PROF(s, KID_EMIS_CONSENSUS), emis_consensus_kernel<CTRL, true, ZI><<<g, EM_NT, 0, s->stream>>>(
+        s->M, s->N, s->d_counts, s->d_offsets, CTRL ? s->d_controls : nullptr, P, s->lgtab.as<double>(), s->logf.as<double>());
+    EHMM_CK(cudaGetLastError());
+    return EHMM_OK;
+}
+}  // namespace
+
+// zi == nullptr: NB (th1 = (beta0[, beta_ctrl], size)); else zi = (lambda0[, lambda_ctrl]) of the
+// zero-inflated background (R/base-loglikelihood.R:123-141)
+int emis_consensus(ehmm_session *s, const double *th1, const double *th2, int P_, double minZero, const double *zi) {
     EHMM_TRY(require_data(s, "loglikConsensusHMM"));
     EHMM_REQUIRE(s->K == 2, EHMM_ERR_ARG, "loglikConsensusHMM needs a K=2 session (K=%d)", s->K);
     EHMM_REQUIRE(P_ == 2 || P_ == 3, EHMM_ERR_ARG, "P must be 2 (beta0,size) or 3 (beta0,beta_ctrl,size)");
@@ -385,35 +421,14 @@ int emis_consensus(ehmm_session *s, const double *th1, const double *th2, int P_
     EmisParams P = {};
     fill_density(P, 0, th1[0], P_ == 3 ? th1[1] : 0.0, th1[P_ - 1]);
     fill_density(P, 1, th2[0], P_ == 3 ? th2[1] : 0.0, th2[P_ - 1]);
+    if (zi) {
+        P.z0 = zi[0];
+        P.z1 = P_ == 3 ? zi[1] : 0.0;
+    }
     EHMM_TRY(prepare_tab(s, P, 2, minZero));
     EHMM_TRY(s->logf.reserve(sizeof(double) * s->M * 2));
-    const int g = grid_for(s->M);
-    if (use_groups(s, 2)) {
-        EHMM_TRY(s->gtab.reserve(sizeof(double2) * (size_t)(s->G + 1)));
-        const unsigned gb = (unsigned)((s->G + 1 + EM_NT - 1) / EM_NT);
-        if (P_ == 3)
-            PROF(s, KID_EMIS_TAB), group_table_consensus_kernel<true, true><<<gb, EM_NT, 0, s->stream>>>(
-                s->G, s->u_chip.as<double>(), s->u_off.as<double>(), s->u_ctrl.as<double>(), P, s->lgtab.as<double>(),
-                s->gtab.as<double2>());
-        else
-            PROF(s, KID_EMIS_TAB), group_table_consensus_kernel<false, true><<<gb, EM_NT, 0, s->stream>>>(
-                s->G, s->u_chip.as<double>(), s->u_off.as<double>(), nullptr, P, s->lgtab.as<double>(),
-                s->gtab.as<double2>());
-        EHMM_CK(cudaGetLastError());
-        PROF(s, KID_EMIS_GATHER), gather_consensus_kernel<<<g, EM_NT, 0, s->stream>>>(
-            s->M, s->N, s->group.as<int32_t>(), s->gtab.as<double2>(), s->logf.as<double>());
-        EHMM_CK(cudaGetLastError());
-        s->valid |= DS_LOGF;
-        return EHMM_OK;
-    }
-    if (P_ == 3)
-        PROF(s, KID_EMIS_CONSENSUS), emis_consensus_kernel<true, true><<<g, EM_NT, 0, s->stream>>>(s->M, s->N, s->d_counts, s->d_offsets,
-                                                                     s->d_controls, P, s->lgtab.as<double>(),
-                                                                     s->logf.as<double>());
-    else
-        PROF(s, KID_EMIS_CONSENSUS), emis_consensus_kernel<false, true><<<g, EM_NT, 0, s->stream>>>(s->M, s->N, s->d_counts, s->d_offsets, nullptr,
-                                                                      P, s->lgtab.as<double>(), s->logf.as<double>());
-    EHMM_CK(cudaGetLastError());
+    if (P_ == 3) EHMM_TRY(zi ? (launch_consensus<true, true>(s, P)) : (launch_consensus<true, false>(s, P)));
+    else EHMM_TRY(zi ? (launch_consensus<false, true>(s, P)) : (launch_consensus<false, false>(s, P)));
     s->valid |= DS_LOGF;
     return EHMM_OK;
 }

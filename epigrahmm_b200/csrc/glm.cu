@@ -150,6 +150,52 @@ __global__ void __launch_bounds__(GLM_NT)
     }
 }
 
+// glmZINB / derivZINB (R/base-optim.R:136-181) over the background state's rejection table.
+struct ZinbPar {
+    double b0, b1, l0, l1, phi, size, lsize, lgs, dg_size, minZero, thr;
+    int has_ctrl;
+};
+
+// out: [0] = sum w*l, [1] = sum d/dbeta0, [2] = sum d/dbeta_ctrl, [3] = sum d/dphi, [4] = sum d/dlambda0, [5] = d/dlambda_ctrl
+__global__ void __launch_bounds__(GLM_NT)
+    glm_zinb_kernel(int64_t G, const double *__restrict__ wt, const double *__restrict__ y, const double *__restrict__ off,
+                    const double *__restrict__ ctrl, ZinbPar P, double *__restrict__ part) {
+    double acc[6] = {0, 0, 0, 0, 0, 0};
+    const double iphi2 = 1.0 / (P.phi * P.phi);
+    for (int64_t g = 1 + (int64_t)blockIdx.x * GLM_NT + threadIdx.x; g <= G; g += (int64_t)gridDim.x * GLM_NT) {
+        const double w = wt[g];
+        if (w == 0.0) continue;
+        const double yy = y[g], cv = P.has_ctrl ? ctrl[g] : 0.0, o = off[g];
+        const double eta = (P.has_ctrl ? (P.b0 + cv * P.b1) : P.b0) + o;
+        const double mu = exp(eta);
+        const double z = 1.0 / (1.0 + exp(-((P.has_ctrl ? (P.l0 + cv * P.l1) : P.l0) + o)));
+        const double l1mz = log(1.0 - z), aux = 1.0 + P.phi * mu, laux = log(aux);
+        double d = nb_logpmf_direct(yy, eta, P.size, P.lsize, P.lgs);  // log dnbinom(y); y = 0 gives the reference's d0
+        if (!(d > P.thr)) d = log(exp(d) + P.minZero);
+        double lval, db, dp, dl;
+        if (yy == 0.0) {
+            const double P0 = z + exp(l1mz + d), c = (w / P0) * (1.0 - z);
+            lval = log(P0);
+            db = c * (-mu * pow(aux, -(P.size + 1.0)));
+            dp = c * pow(aux, -P.size) * (laux * iphi2 - mu / (P.phi * aux));
+            dl = (w / P0) * (1.0 - exp(d)) * z * (1.0 - z);
+        } else {
+            const double P1 = exp(l1mz + d), ed = exp(d), c = (w / P1) * (1.0 - z) * ed;
+            lval = l1mz + d;
+            db = c * (yy - mu) / aux;
+            dp = c * (laux * iphi2 - mu * (yy + P.size) / aux - digamma_pos(yy + P.size) * iphi2 + P.dg_size * iphi2 + yy / P.phi);
+            dl = (w / P1) * (-ed) * z * (1.0 - z);
+        }
+        acc[0] += w * lval;
+        acc[1] += db;
+        acc[2] += db * cv;
+        acc[3] += dp;
+        acc[4] += dl;
+        acc[5] += dl * cv;
+    }
+    block_store<6>(acc, part);
+}
+
 struct MixPar {
     double b, db, l, dl, minZero, thr;
     double size[2], lsize[2], lgs[2], dg[2];  // D = 0 / 1
@@ -288,6 +334,45 @@ int glm_nb_batch(ehmm_session *s, int ncols, const int *columns, const double *p
             if (P_ == 2) g[1] = -o[2];
             g[P_] = -o[3];
         }
+    }
+    return EHMM_OK;
+}
+
+// par = (beta[P], phi, lambda[P]), P = 1 (Intercept) or 2 (Intercept, controls)
+int glm_zinb(ehmm_session *s, int column, const double *par, int P_, double minZero, double *value, double *grad) {
+    EHMM_REQUIRE(P_ == 1 || P_ == 2, EHMM_ERR_ARG, "glmZINB: P must be 1 (Intercept) or 2 (Intercept, controls)");
+    EHMM_REQUIRE(P_ == 1 || s->u_ctrl.p, EHMM_ERR_STATE, "glmZINB: dtUnique has no controls column");
+    EHMM_REQUIRE(column >= 0 && column < s->rc_columns, EHMM_ERR_STATE, "glmZINB: rejection table %d not available", column);
+    EHMM_REQUIRE(par[P_] > 0 && isfinite(par[P_]), EHMM_ERR_ARG, "glmZINB: dispersion %g must be positive", par[P_]);
+    ZinbPar P;
+    P.b0 = par[0];
+    P.b1 = P_ == 2 ? par[1] : 0.0;
+    P.phi = par[P_];
+    P.l0 = par[P_ + 1];
+    P.l1 = P_ == 2 ? par[P_ + 2] : 0.0;
+    P.size = 1.0 / P.phi;
+    P.lsize = log(P.size);
+    P.lgs = lgamma(P.size);
+    P.dg_size = host_digamma(P.size);
+    P.minZero = minZero;
+    P.thr = log(minZero) + 40.0;
+    P.has_ctrl = (P_ == 2);
+    EHMM_TRY(s->glm_part.reserve(sizeof(double) * ((size_t)EHMM_MAX_K * 148 * 4 * 4 + EHMM_MAX_K * 4) + 64 +
+                                 sizeof(double) * ((size_t)148 * 4 * GLM_MAXOUT + GLM_MAXOUT)));
+    const int nblk = blocks_for(s->G);
+    PROF(s, KID_GLM), glm_zinb_kernel<<<nblk, GLM_NT, 0, s->stream>>>(
+        s->G, s->rc_buckets.as<double>() + (size_t)column * (s->G + 1), s->u_chip.as<double>(), s->u_off.as<double>(),
+        s->u_ctrl.as<double>(), P, s->glm_part.as<double>());
+    EHMM_CK(cudaGetLastError());
+    double o[6];
+    EHMM_TRY(finish(s, nblk, 6, o));
+    *value = -o[0];
+    if (grad) {
+        grad[0] = -o[1];
+        if (P_ == 2) grad[1] = -o[2];
+        grad[P_] = -o[3];
+        grad[P_ + 1] = -o[4];
+        if (P_ == 2) grad[P_ + 2] = -o[5];
     }
     return EHMM_OK;
 }

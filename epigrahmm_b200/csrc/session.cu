@@ -437,6 +437,14 @@ int ehmm_loglik_consensus(ehmm_session *s, const double *theta1, const double *t
     return emis_consensus(s, theta1, theta2, P, minZero);
 }
 
+int ehmm_loglik_consensus_zinb(ehmm_session *s, const double *theta1, const double *theta2, int Q, double minZero) {
+    EHMM_TRY(check_session(s));
+    EHMM_REQUIRE(theta1 && theta2, EHMM_ERR_ARG, "null parameters");
+    EHMM_REQUIRE(Q == 3 || Q == 5, EHMM_ERR_ARG, "theta1 must hold 3 (lambda, beta, size) or 5 (with controls) entries");
+    const int nl = (Q - 1) / 2;  // zero-inflation coefficients come first, then the NB part
+    return emis_consensus(s, theta1 + nl, theta2, Q - nl, minZero, theta1);
+}
+
 int ehmm_loglik_init(ehmm_session *s, const double *psi1, const double *psi2) {
     EHMM_TRY(check_session(s));
     EHMM_REQUIRE(psi1 && psi2, EHMM_ERR_ARG, "null parameters");
@@ -785,6 +793,12 @@ int ehmm_glm_nb(ehmm_session *s, int column, const double *par, int P, double *v
     EHMM_REQUIRE(par && value, EHMM_ERR_ARG, "null pointer");
     EHMM_REQUIRE(column >= 0 && column < s->rc_columns, EHMM_ERR_STATE, "glmNB: rejection table %d not available", column);
     return glm_nb(s, column, par, P, value, grad);
+}
+
+int ehmm_glm_zinb(ehmm_session *s, int column, const double *par, int P, double minZero, double *value, double *grad) {
+    EHMM_TRY(check_session(s));
+    EHMM_REQUIRE(par && value, EHMM_ERR_ARG, "null pointer");
+    return glm_zinb(s, column, par, P, minZero, value, grad);
 }
 
 int ehmm_glm_nb_batch(ehmm_session *s, int n, const int *columns, const double *pars, int P, double *values, double *grads) {

@@ -97,9 +97,21 @@ def getError(controlHist, parHist, control) -> np.ndarray:
         return np.array([np.max(np.abs((new - old) / old)), np.max(np.abs(new - old)), abs((q_new - q_old) / q_old)])
 
 
-def invertDispersion(par):
+def invertDispersion(par, model="nb"):
+    """R/base-utils.R:170-181.  'nb': (beta..., size) <-> (beta..., 1/size), an involution.  'zinb': the model's
+    (lambda[P], beta[P], size) -> the optimiser's (beta[P], 1/size, lambda[P])."""
     par = np.asarray(par, dtype=np.float64)
-    return np.concatenate([par[:-1], [1.0 / par[-1]]])
+    if model == "nb":
+        return np.concatenate([par[:-1], [1.0 / par[-1]]])
+    P = (par.size - 1) // 2
+    return np.concatenate([par[P:2 * P], [1.0 / par[2 * P]], par[:P]])
+
+
+def _zinb_from_optim(x):
+    """optimNB's back-transformation for dist = 'zinb' (R/base-optim.R:43-47)"""
+    x = np.asarray(x, dtype=np.float64)
+    P = (x.size - 1) // 2
+    return np.concatenate([x[P + 1:], x[:P], [1.0 / x[P]]])
 
 
 def _lbfgsb_minimize(fun, x0, lower, upper):
@@ -226,11 +238,27 @@ def optimNB(par, backend, column, control):
     return dict(par=invertDispersion(x), convergence=conv)
 
 
-def optimNB_all(pars, backend, control):
+def optimZINB(par, backend, column, control):
+    """R/base-optim.R:28-48 (dist='zinb'): par = (lambda[P], beta[P], size) -> optimise (beta, phi, lambda)."""
+    par = np.asarray(par, dtype=np.float64)
+    start = invertDispersion(par, "zinb")
+    P = (par.size - 1) // 2
+    try:
+        lower = np.concatenate([np.full(P, -np.inf), [1.0 / control["maxDisp"]], np.full(P, -np.inf)])
+        x, conv = _lbfgsb(lambda x: backend.glm_zinb(column, x, control["minZero"]), start, lower, np.full(2 * P + 1, np.inf))
+    except Exception:
+        x, conv = start, 99
+    return dict(par=_zinb_from_optim(x), convergence=conv)
+
+
+def optimNB_all(pars, backend, control, dist="nb"):
     """optimNB for every state (R/base-EM.R:131-141 runs them one after the other with lapply).
+    With dist = 'zinb' the first state is the zero-inflated one (l.140) and is optimised on its own.
     The K problems are independent, so when the backend can evaluate several (state, parameter)
     pairs in one launch (glm_nb_batch) their L-BFGS-B instances advance in lock-step: each one sees
     exactly the evaluations it would see alone, and the host waits for K times fewer launches."""
+    if dist == "zinb":
+        return [optimZINB(pars[0], backend, 0, control)] + [optimNB(p, backend, k, control) for k, p in enumerate(pars) if k > 0]
     if not (hasattr(backend, "glm_nb_batch") and _fast_lbfgsb_available()):
         return [optimNB(p, backend, k, control) for k, p in enumerate(pars)]
     starts = [invertDispersion(p) for p in pars]
@@ -312,9 +340,11 @@ def _continue(controlHist, control):
 
 
 def emConsensus(theta_old, backend, N, control, dist="nb", callback=None):
-    """R/base-EM.R:98-178.  theta = dict(pi, gamma, psi=[theta1, theta2]); psi_k = (beta0[, beta_ctrl], size)."""
-    if dist != "nb":
-        raise NotImplementedError("dist='zinb' is not on the accelerated path yet")
+    """R/base-EM.R:98-178.  theta = dict(pi, gamma, psi=[theta1, theta2]); psi_k = (beta0[, beta_ctrl], size);
+    with dist = 'zinb' theta1 = (lambda0[, lambda_ctrl], beta0[, beta_ctrl], size)."""
+    if dist not in ("nb", "zinb"):
+        raise ValueError("dist must be 'nb' or 'zinb'")
+    loglik = backend.loglik_consensus if dist == "nb" else backend.loglik_consensus_zinb
     controlHist, parHist = [controlList()], []
     theta_old = copy.deepcopy(theta_old)
     theta_new = copy.deepcopy(theta_old)
@@ -323,11 +353,11 @@ def emConsensus(theta_old, backend, N, control, dist="nb", callback=None):
     while _continue(controlHist, control):
         cur = controlHist[-1]
         cur["iteration"] += 1
-        backend.loglik_consensus(theta_old["psi"], control["minZero"])
+        loglik(theta_old["psi"], control["minZero"])
         backend.expstep(theta_old["pi"], theta_old["gamma"])
         theta_new.update(backend.maxstepprob())
         backend.rc_consensus(_rejection_cut(cur["iteration"], control))
-        optimMLE = optimNB_all(theta_old["psi"], backend, control)
+        optimMLE = optimNB_all(theta_old["psi"], backend, control, dist)
         theta_new["psi"] = [o["par"] for o in optimMLE]
         bic = backend.bic(numPar, N)
         q = backend.qfunction(theta_old["pi"], theta_old["gamma"])

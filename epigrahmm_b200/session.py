@@ -146,6 +146,11 @@ class Session:
         t1, t2 = _f64(psi[0]), _f64(psi[1])
         check(lib.ehmm_loglik_consensus(self._h, dptr(t1), dptr(t2), t1.size, float(minZero)))
 
+    def loglik_consensus_zinb(self, psi, minZero):
+        """dist = 'zinb': psi[0] = (lambda0[, lambda_ctrl], beta0[, beta_ctrl], size), psi[1] as for 'nb'"""
+        t1, t2 = _f64(psi[0]), _f64(psi[1])
+        check(lib.ehmm_loglik_consensus_zinb(self._h, dptr(t1), dptr(t2), t1.size, float(minZero)))
+
     def loglik_init(self, psi):
         t1, t2 = _f64(psi[0]), _f64(psi[1])
         check(lib.ehmm_loglik_init(self._h, dptr(t1), dptr(t2)))
@@ -315,6 +320,14 @@ class Session:
         v = C.c_double()
         g = np.empty(par.size) if grad else None
         check(lib.ehmm_glm_nb(self._h, int(column), dptr(par), par.size - 1, C.byref(v), dptr(g)))
+        return v.value, g
+
+    def glm_zinb(self, column, par, minZero, grad=True):
+        """glmZINB/derivZINB: par = (beta[P], phi, lambda[P])"""
+        par = _f64(par)
+        v = C.c_double()
+        g = np.empty(par.size) if grad else None
+        check(lib.ehmm_glm_zinb(self._h, int(column), dptr(par), (par.size - 1) // 2, float(minZero), C.byref(v), dptr(g)))
         return v.value, g
 
     def glm_nb_batch(self, columns, pars):

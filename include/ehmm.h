@@ -90,6 +90,10 @@ int ehmm_set_design(ehmm_session *s, int B, const uint8_t *design);
 /* ---- emission log-likelihoods -> dataset logLikelihood (device) ------------------ */
 /* loglikConsensusHMM NB branch, R/base-loglikelihood.R:104-122. P = 2 or 3 parameters per state. */
 int ehmm_loglik_consensus(ehmm_session *s, const double *theta1, const double *theta2, int P, double minZero);
+/* dist = 'zinb' (R/base-loglikelihood.R:123-141): the background state is zero-inflated,
+ * theta1 = (lambda0[, lambda_ctrl], beta0[, beta_ctrl], size) with Q = 3 or 5 entries (the offsets
+ * enter the zero-inflation predictor too, l.125); theta2 = (beta0[, beta_ctrl], size) as above. */
+int ehmm_loglik_consensus_zinb(ehmm_session *s, const double *theta1, const double *theta2, int Q, double minZero);
 /* emInitialization emission, R/base-EM.R:24-30 (N = 1, dnbinom(log=TRUE)). */
 int ehmm_loglik_init(ehmm_session *s, const double *psi1, const double *psi2);
 /* loglikDifferentialHMM NB branch, R/base-loglikelihood.R:45-71,96. psi = (b, l, db, dl). */
@@ -176,6 +180,9 @@ int ehmm_aggregate(int device, const double *x, int64_t n, const int32_t *f, int
 /* glmNB / derivNB, R/base-optim.R:109-130, over table `column` joined with dtUnique.
  * par = (beta0[, beta_ctrl], phi); value and grad (P + 1) are the NEGATIVE log-lik as in R. */
 int ehmm_glm_nb(ehmm_session *s, int column, const double *par, int P, double *value, double *grad);
+/* glmZINB / derivZINB (R/base-optim.R:136-181) over rejection table `column`:
+ * par = (beta[P], phi, lambda[P]), grad has 2P + 1 entries in the same order. */
+int ehmm_glm_zinb(ehmm_session *s, int column, const double *par, int P, double minZero, double *value, double *grad);
 /* n evaluations in one launch (the per-state optimisations of R/base-EM.R:131-141 are independent,
  * so their L-BFGS-B instances can advance in lock-step): columns[q], pars[q*(P+1) ..] -> values[q],
  * grads[q*(P+1) ..]. */

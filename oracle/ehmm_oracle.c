@@ -523,6 +523,41 @@ EO_API void eo_loglik_consensus(int64_t M, int N, const int32_t *y, const double
     }
 }
 
+/* loglikConsensusHMM, ZINB branch: R/base-loglikelihood.R:123-141.  The background state is
+ * zero-inflated: th1 = (lambda0[, lambda_ctrl], beta0[, beta_ctrl], size), Q = 3 or 5 entries;
+ * the enrichment state is the NB of the other branch, th2 = (beta0[, beta_ctrl], size).
+ * Note that the offsets enter the zero-inflation predictor as well (l.125). */
+EO_API void eo_loglik_consensus_zinb(int64_t M, int N, const int32_t *y, const double *off, const double *ctrl,
+                                     const double *th1, const double *th2, int Q, double minZero, double *LL) {
+    const int useC = (Q == 5);
+    for (int64_t j = 0; j < M; j++) {
+        long double acc = 0;
+        for (int i = 0; i < N; i++) {
+            int64_t c = j + (int64_t)i * M;
+            double xbeta = (useC ? th1[0] + th1[1] * ctrl[c] : th1[0]) + off[c];
+            double mu = exp((useC ? th1[2] + th1[3] * ctrl[c] : th1[1]) + off[c]);
+            double size = useC ? th1[4] : th1[2];
+            double ll00 = log(eo_dnbinom_mu(0.0, size, mu, 0) + minZero);
+            double ll01 = log(eo_dnbinom_mu((double)y[c], size, mu, 0) + minZero);
+            double zip = 1 / (1 + exp(-xbeta));
+            double yvec0 = (y[c] == 0) ? 1.0 : 0.0;
+            acc += yvec0 * log(zip + exp(log(1 - zip) + ll00)) + (1 - yvec0) * (log(1 - zip) + ll01);
+        }
+        LL[j] = (double)acc;
+    }
+    int P = useC ? 3 : 2;
+    double size2 = th2[P - 1];
+    for (int64_t j = 0; j < M; j++) {
+        long double acc = 0;
+        for (int i = 0; i < N; i++) {
+            int64_t c = j + (int64_t)i * M;
+            double mu = exp((useC ? th2[0] + th2[1] * ctrl[c] : th2[0]) + off[c]);
+            acc += log(eo_dnbinom_mu((double)y[c], size2, mu, 0) + minZero);
+        }
+        LL[j + M] = (double)acc;
+    }
+}
+
 /* emInitialization emission: R/base-EM.R:24-30 (N = 1, dnbinom(log=TRUE), psi_k=(beta,size)) */
 EO_API void eo_loglik_init(int64_t M, const int32_t *y, const double *off, const double *psi1,
                            const double *psi2, double *LL) {
@@ -615,6 +650,52 @@ EO_API double eo_glm_nb(int64_t G, int P, const double *par, const double *y, co
     }
     if (grad) {
         for (int c = 0; c < P; c++) grad[c] = -(double)gb[c];
+        grad[P] = -(double)gphi;
+    }
+    return -(double)f;
+}
+
+/* glmZINB / derivZINB: R/base-optim.R:136-181.  x: G x P column-major; par = (beta[P], phi,
+ * lambda[P]); returns the value, grad (2P + 1 entries) when non-NULL. */
+EO_API double eo_glm_zinb(int64_t G, int P, const double *par, const double *y, const double *x,
+                          const double *offset, const double *w, double minZero, double *grad) {
+    double phi = par[P];
+    long double f = 0, gphi = 0, gb[8] = {0}, gl[8] = {0};
+    for (int64_t g = 0; g < G; g++) {
+        double eb = 0, el = 0;
+        for (int c = 0; c < P; c++) {
+            eb += x[g + (int64_t)c * G] * par[c];
+            el += x[g + (int64_t)c * G] * par[P + 1 + c];
+        }
+        double mu = exp(eb + offset[g]);
+        double z = 1 / (1 + exp(-(el + offset[g])));
+        double y0 = (y[g] == 0) ? 1.0 : 0.0;
+        double d0 = log(eo_dnbinom_mu(0.0, 1 / phi, mu, 0) + minZero);
+        double d1 = log(eo_dnbinom_mu(y[g], 1 / phi, mu, 0) + minZero);
+        double l0 = log(z + exp(log(1 - z) + d0));
+        double l1 = log(1 - z) + d1;
+        f += w[g] * (y0 * l0 + (1 - y0) * l1);
+        if (grad) {
+            double P0 = z + exp(log(1 - z) + d0);
+            double P1 = exp(log(1 - z) + d1);
+            double aux = 1 + phi * mu;
+            double db1 = y0 * (w[g] / P0) * (1 - z) * (-mu * pow(1 + phi * mu, -(1 / phi + 1)));
+            double db2 = (1 - y0) * (w[g] / P1) * (1 - z) * exp(d1) * (y[g] - mu) / (1 + phi * mu);
+            double dp1 = y0 * (w[g] / P0) * (1 - z) * pow(aux, -1 / phi) * (log(aux) / (phi * phi) - mu / (phi * aux));
+            double dp2 = (1 - y0) * (w[g] / P1) * (1 - z) * exp(d1) *
+                         (log(aux) / (phi * phi) - mu * (y[g] + 1 / phi) / aux - eo_digamma(y[g] + 1 / phi) / (phi * phi) +
+                          eo_digamma(1 / phi) / (phi * phi) + y[g] / phi);
+            double dl1 = y0 * (w[g] / P0) * (1 - exp(d0)) * z * (1 - z);
+            double dl2 = (1 - y0) * (w[g] / P1) * (-exp(d1)) * z * (1 - z);
+            for (int c = 0; c < P; c++) {
+                gb[c] += (db1 + db2) * x[g + (int64_t)c * G];
+                gl[c] += (dl1 + dl2) * x[g + (int64_t)c * G];
+            }
+            gphi += dp1 + dp2;
+        }
+    }
+    if (grad) {
+        for (int c = 0; c < P; c++) { grad[c] = -(double)gb[c]; grad[P + 1 + c] = -(double)gl[c]; }
         grad[P] = -(double)gphi;
     }
     return -(double)f;

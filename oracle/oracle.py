@@ -41,6 +41,7 @@ def lib():
         _lib.eo_qfunction.restype = C.c_double
         _lib.eo_bic.restype = C.c_double
         _lib.eo_glm_nb.restype = C.c_double
+        _lib.eo_glm_zinb.restype = C.c_double
         _lib.eo_glm_mix_nb.restype = C.c_double
         for n in ("eo_reweight", "eo_reweight_buf", "eo_aggregate_compact", "eo_consensus_rc", "eo_differential_rc"):
             getattr(_lib, n).restype = C.c_int64
@@ -237,6 +238,20 @@ def loglikConsensusHMM(y, offsets, psi, minZero, controls=None):
     return LL
 
 
+def loglikConsensusHMMzinb(y, offsets, psi, minZero, controls=None):
+    """R/base-loglikelihood.R:123-141 (dist = 'zinb').  psi[0] = (lambda0[, lambda_ctrl], beta0[, beta_ctrl],
+    size) for the zero-inflated background, psi[1] = (beta0[, beta_ctrl], size)."""
+    y, off = _i32cm(y), _colmajor(offsets)
+    M, N = y.shape
+    ctrl = None if controls is None else _colmajor(controls)
+    th1, th2 = _f64(psi[0]), _f64(psi[1])
+    assert th1.size == (3 if ctrl is None else 5) and th2.size == (2 if ctrl is None else 3)
+    LL = np.empty((M, 2), order="F")
+    lib().eo_loglik_consensus_zinb(C.c_int64(M), N, _p(y, C.c_int32), _p(off), _p(ctrl), _p(th1), _p(th2),
+                                   int(th1.size), C.c_double(minZero), _p(LL))
+    return LL
+
+
 def loglikInit(y, offsets, psi):
     """R/base-EM.R:24-30 (single sample, dnbinom(log=TRUE))."""
     y, off = _i32cm(np.asarray(y).reshape(-1, 1)), _colmajor(np.asarray(offsets).reshape(-1, 1))
@@ -287,6 +302,16 @@ def glmNB(par, y, x, offset, weights, grad=True):
     g = np.empty(P + 1)
     v = lib().eo_glm_nb(C.c_int64(G), P, _p(_f64(par)), _p(_f64(y)), _p(x), _p(_f64(offset)), _p(_f64(weights)),
                         _p(g) if grad else None)
+    return v, g
+
+
+def glmZINB(par, y, x, offset, weights, minZero, grad=True):
+    """R/base-optim.R:136-181 -> (value, gradient); par = (beta[P], phi, lambda[P])."""
+    x = _colmajor(np.asarray(x, float).reshape(len(y), -1) if len(y) else np.zeros((0, 1)))
+    G, P = x.shape
+    g = np.empty(2 * P + 1)
+    v = lib().eo_glm_zinb(C.c_int64(G), P, _p(_f64(par)), _p(_f64(y)), _p(x), _p(_f64(offset)), _p(_f64(weights)),
+                          C.c_double(minZero), _p(g) if grad else None)
     return v, g
 
 

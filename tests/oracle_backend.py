@@ -26,6 +26,9 @@ class OracleBackend:
     def loglik_consensus(self, psi, minZero):
         self.h["logLikelihood"] = O.loglikConsensusHMM(self.counts, self.offsets, psi, minZero, self.controls)
 
+    def loglik_consensus_zinb(self, psi, minZero):
+        self.h["logLikelihood"] = O.loglikConsensusHMMzinb(self.counts, self.offsets, psi, minZero, self.controls)
+
     def loglik_init(self, psi):
         self.h["logLikelihood"] = O.loglikInit(self.counts[:, 0], self.offsets[:, 0], psi)
 
@@ -85,6 +88,13 @@ class OracleBackend:
         if self.g.get("u_controls") is not None:
             x = np.column_stack([x[:, 0], self.g["u_controls"][ids - 1]])
         return O.glmNB(par, self.g["u_chip"][ids - 1], x, self.g["u_offsets"][ids - 1], self.rc[column][ids], grad)
+
+    def glm_zinb(self, column, par, minZero, grad=True):
+        ids = np.nonzero(self.rc[column])[0]
+        x = np.ones((ids.size, 1))
+        if self.g.get("u_controls") is not None:
+            x = np.column_stack([x[:, 0], self.g["u_controls"][ids - 1]])
+        return O.glmZINB(par, self.g["u_chip"][ids - 1], x, self.g["u_offsets"][ids - 1], self.rc[column][ids], minZero, grad)
 
     def glm_mix_nb(self, par, minZero, grad=True):
         B = self.B

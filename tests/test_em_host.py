@@ -128,3 +128,36 @@ def test_optim_differential_reference_test(oracle):
     assert abs(opt["par"][0] - 1.0) < 1e-4 and abs(opt["par"][1] - np.log(ctl["maxDisp"])) < 1e-4
     assert abs(opt["par"][2]) < 1e-4 and opt["par"][3] > 0
     del grp
+
+
+def test_zinb_parameter_maps_and_em_on_oracle_backend(oracle):
+    """invertDispersion(model='zinb') / optimNB's back-transformation (R/base-utils.R:174-180,
+    R/base-optim.R:43-47), estimateCoefficients(dist='zinb') and a short emConsensus(dist='zinb') over the
+    oracle backend: the structural zeros are picked up by the zero-inflation intercept."""
+    from oracle_backend import OracleBackend
+    from epigrahmm_b200 import core, em, synth
+    p3, p5 = np.array([-1.0, 0.7, 3.0]), np.array([-1.0, 0.2, 0.7, -0.1, 3.0])
+    assert np.allclose(em.invertDispersion(p3, "zinb"), [0.7, 1 / 3.0, -1.0])
+    assert np.allclose(em.invertDispersion(p5, "zinb"), [0.7, -0.1, 1 / 3.0, -1.0, 0.2])
+    assert np.allclose(em._zinb_from_optim(em.invertDispersion(p3, "zinb")), p3)
+    assert np.allclose(em._zinb_from_optim(em.invertDispersion(p5, "zinb")), p5)
+    M, N = 6007, 2
+    d = synth.make_consensus(M, N, seed=77)
+    rng = np.random.default_rng(78)
+    counts = d["counts"].copy()
+    counts[(rng.random(counts.shape) < 0.3) & (d["z"][:, None] == 0)] = 0
+    counts = np.asfortranarray(counts)
+    z = 1 + (d["z"] == 1)
+    ctl = em.controlEM(maxIterEM=5)
+    psi = core.estimateCoefficients(z, counts, d["offsets"], ctl, "consensus", "zinb")
+    assert psi[0].size == 3 and psi[1].size == 2 and psi[0][0] <= 0.0       # log(zip), zip in [0.01, 1]
+    theta = dict(pi=np.array([0.999, 0.001]), gamma=em.estimateTransitionProb(z, 2), psi=psi)
+    be = OracleBackend(counts, d["offsets"], 2, groups=synth.make_groups(counts, d["offsets"]), rng=oracle.RNG.set_seed(5))
+    fit = em.emConsensus(theta, be, N, ctl, dist="zinb")
+    th = fit["theta_new"]
+    assert len(fit["parHist"]) == 5 and th["psi"][0].size == 3
+    assert all(np.all(np.isfinite(em.unlist(p))) for p in fit["parHist"])
+    zi = 1 / (1 + np.exp(-th["psi"][0][0]))
+    assert 0.15 < zi < 0.45, zi
+    bics = [h["bic"] for h in fit["controlHist"][:-1]]
+    assert bics[-1] < bics[0]

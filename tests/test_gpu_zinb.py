@@ -1,0 +1,115 @@
+"""dist = 'zinb' (SURVEY.md section 8f rank 3): zero-inflated background state of the consensus
+model -- emission (R/base-loglikelihood.R:123-141), glmZINB/derivZINB (R/base-optim.R:136-181) and
+the EM trajectory with optimNB(dist = 'zinb') for state 1 (R/base-EM.R:140), GPU vs oracle."""
+import numpy as np
+import pytest
+
+from oracle_backend import OracleBackend
+
+from epigrahmm_b200 import core, em, synth
+
+pytestmark = pytest.mark.gpu
+MINZERO = 2.2250738585072014e-308
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300)))
+
+
+def _zinb_data(M, N, seed, inflate=0.25, controls=False):
+    d = synth.make_consensus(M, N, seed=seed)
+    rng = np.random.default_rng(seed + 1)
+    counts = d["counts"].copy()
+    drop = (rng.random(counts.shape) < inflate) & (d["z"][:, None] == 0)   # structural zeros in the background
+    counts[drop] = 0
+    d["counts"] = np.asfortranarray(counts)
+    d["controls"] = np.asfortranarray(np.log1p(rng.poisson(3.0, counts.shape).astype(float))) if controls else None
+    return d
+
+
+@pytest.mark.parametrize("controls", [False, True])
+def test_zinb_emission_matches_oracle_on_both_paths(ehmm, oracle, controls):
+    M, N = 20011, 3
+    d = _zinb_data(M, N, 31, controls=controls)
+    psi = [np.array([-0.8, 0.3, 0.7, -0.1, 3.0]), np.array([2.4, 0.05, 4.0])] if controls else \
+        [np.array([-0.8, 0.7, 3.0]), np.array([2.4, 4.0])]
+    ref = oracle.loglikConsensusHMMzinb(d["counts"], d["offsets"], psi, MINZERO, d["controls"])
+    with ehmm.Session("zinb-e", M, 2) as s:
+        s.set_data(d["counts"], d["offsets"], d["controls"])
+        s.loglik_consensus_zinb(psi, MINZERO)                  # per-cell kernel
+        cell = s.fetch("logLikelihood")
+        assert _rel(cell, ref) <= 1e-12
+        s.build_groups()
+        s.loglik_consensus_zinb(psi, MINZERO)                  # dictionary-encoded path
+        assert np.array_equal(s.fetch("logLikelihood"), cell)
+        # an extreme zero-inflation predictor and a tiny size stay finite (minZero keeps the logs alive)
+        hard = [psi[0].copy(), psi[1]]
+        hard[0][0] = 30.0
+        s.loglik_consensus_zinb(hard, MINZERO)
+        got = s.fetch("logLikelihood")
+        want = oracle.loglikConsensusHMMzinb(d["counts"], d["offsets"], hard, MINZERO, d["controls"])
+        assert np.all(np.isfinite(got)) and _rel(got, want) <= 1e-9
+
+
+@pytest.mark.parametrize("controls", [False, True])
+def test_glm_zinb_value_and_gradient(ehmm, oracle, controls):
+    M, N = 30011, 2
+    d = _zinb_data(M, N, 47, controls=controls)
+    g = synth.make_groups(d["counts"], d["offsets"], controls=d["controls"])
+    th = synth.THETA_CONSENSUS
+    be = OracleBackend(d["counts"], d["offsets"], 2, controls=d["controls"], groups=g, rng=oracle.RNG.set_seed(3))
+    psi_nb = [np.array([0.7, 0.0, 3.0]), np.array([2.4, 0.0, 4.0])] if controls else th["psi"]
+    be.loglik_consensus(psi_nb, MINZERO)
+    be.expstep(th["pi"], th["gamma"])
+    be.rc_consensus(0.05)
+    with ehmm.Session("zinb-g", M, 2) as s:
+        s.set_data(d["counts"], d["offsets"], d["controls"])
+        s.set_groups(g["group"], g["u_chip"], g["u_offsets"], g.get("u_controls"))
+        s.store("logProb1", be.fetch("logProb1"))
+        s.rng_set_state(oracle.RNG.set_seed(3).state())
+        s.rc_consensus(0.05)
+        pars = [np.array([0.6, 0.05, 0.4, -0.7, 0.1]), np.array([1.5, -0.2, 2.0, 1.0, -0.3])] if controls else \
+            [np.array([0.6, 0.4, -0.7]), np.array([1.5, 2.0, 1.0]), np.array([0.1, 0.001, -6.0])]
+        for par in pars:
+            v, gr = s.glm_zinb(0, par, MINZERO)
+            vo, go = be.glm_zinb(0, par, MINZERO)
+            assert abs(v - vo) <= 1e-11 * abs(vo), (par, v, vo)
+            assert np.max(np.abs(gr - go)) <= 1e-9 * max(1.0, np.max(np.abs(go))), (par, gr, go)
+
+
+def test_em_trajectory_zinb(ehmm, oracle):
+    """same driver, backend swapped (T2) with dist = 'zinb'; gates as in tests/test_gpu_em.py"""
+    M, N = 20011, 2
+    d = _zinb_data(M, N, 53)
+    g = synth.make_groups(d["counts"], d["offsets"])
+    z = 1 + (d["z"] == 1)
+    ctl = em.controlEM(maxIterEM=6)
+    theta = dict(pi=np.array([0.999, 0.001]), gamma=em.estimateTransitionProb(z, 2),
+                 psi=core.estimateCoefficients(z, d["counts"], d["offsets"], ctl, "consensus", "zinb"))
+    assert theta["psi"][0].size == 3 and theta["psi"][1].size == 2
+    rng = oracle.RNG.set_seed(99)
+    be = OracleBackend(d["counts"], d["offsets"], 2, groups=g, rng=rng)
+    fo = em.emConsensus(theta, be, N, ctl, dist="zinb")
+    with ehmm.Session("zinb-em", M, 2) as s:
+        s.set_data(d["counts"], d["offsets"])
+        assert s.build_groups() == g["G"]
+        s.rng_set_state(oracle.RNG.set_seed(99).state())
+        fg = em.emConsensus(theta, s, N, ctl, dist="zinb")
+        assert len(fg["parHist"]) == len(fo["parHist"])
+        worst, tight = 0.0, 0
+        for it, (pg, po) in enumerate(zip(fg["parHist"], fo["parHist"])):
+            r = _rel(em.unlist(pg), em.unlist(po))
+            worst, tight = max(worst, r), tight + (r <= 1e-9)
+            assert r <= 1e-6, (it + 1, r)
+            assert _rel(fg["controlHist"][it]["bic"], fo["controlHist"][it]["bic"]) <= max(1e-9, 10 * worst)
+        assert tight >= len(fg["parHist"]) // 2
+        print("zinb trajectory: worst relative parameter difference %.3g" % worst)
+        th = fg["theta_new"]
+        # the fit sees the structural zeros: the zero-inflation probability at offset 0 is well above the floor
+        zi = 1.0 / (1.0 + np.exp(-th["psi"][0][0]))
+        assert 0.1 < zi < 0.5, zi
+        if worst <= 1e-9:
+            assert np.array_equal(s.rng_get_state(), rng.state())
+            to = fo["theta_new"]
+            assert np.array_equal(s.viterbi(th["pi"], th["gamma"]), be.viterbi(to["pi"], to["gamma"]))

@@ -176,3 +176,65 @@ def test_helas3_fixture():
     a = np.load(os.path.join(GOLD, "helas3_counts.npz"))["counts"]
     assert a.shape == (9994, 6) and a.dtype == np.int32
     assert a.sum(0).tolist() == [104862, 75257, 86302, 59193, 91121, 85604] and a.max() == 191
+
+
+# ---- dist = 'zinb'  ---------------------------------------------------------
+
+def test_zinb_emission_against_scipy_twin(oracle):
+    """R/base-loglikelihood.R:123-141 written out with scipy's nbinom (independent arithmetic)"""
+    from scipy.stats import nbinom
+    rng = np.random.default_rng(11)
+    M, N = 300, 3
+    y = rng.negative_binomial(3, 0.4, (M, N)).astype(np.int32)
+    y[rng.random((M, N)) < 0.3] = 0
+    off = np.round(rng.normal(0, 0.1, (M, N)), 3)
+    ctrl = np.log1p(rng.poisson(3.0, (M, N)).astype(float))
+    mz = 2.2250738585072014e-308
+
+    def dnb(x, mu, size):
+        return nbinom.pmf(x, size, size / (size + mu))
+    for useC in (False, True):
+        psi = [np.array([-1.0, 0.2, 0.7, -0.1, 3.0]), np.array([2.0, 0.05, 4.0])] if useC else \
+            [np.array([-1.0, 0.7, 3.0]), np.array([2.0, 4.0])]
+        LL = oracle.loglikConsensusHMMzinb(np.asfortranarray(y), np.asfortranarray(off), psi, mz,
+                                           np.asfortranarray(ctrl) if useC else None)
+        if useC:
+            xb, mu1, s1 = psi[0][0] + psi[0][1] * ctrl + off, np.exp(psi[0][2] + psi[0][3] * ctrl + off), psi[0][4]
+            mu2, s2 = np.exp(psi[1][0] + psi[1][1] * ctrl + off), psi[1][2]
+        else:
+            xb, mu1, s1 = psi[0][0] + off, np.exp(psi[0][1] + off), psi[0][2]
+            mu2, s2 = np.exp(psi[1][0] + off), psi[1][1]
+        zp = 1 / (1 + np.exp(-xb))
+        cell = np.where(y == 0, np.log(zp + (1 - zp) * (dnb(0, mu1, s1) + mz)), np.log(1 - zp) + np.log(dnb(y, mu1, s1) + mz))
+        assert np.max(np.abs(LL[:, 0] - cell.sum(1))) <= 1e-11
+        assert np.max(np.abs(LL[:, 1] - np.log(dnb(y, mu2, s2) + mz).sum(1))) <= 1e-11
+
+
+def test_glm_zinb_gradient_and_nb_limit(oracle):
+    """derivZINB is the gradient of glmZINB (central differences); with lambda -> -inf the value is glmNB's
+    (up to the minZero floor, which both apply inside the log)"""
+    rng = np.random.default_rng(12)
+    G = 400
+    y = rng.negative_binomial(2, 0.3, G).astype(float)
+    y[rng.random(G) < 0.3] = 0
+    o, w = np.round(rng.normal(0, 0.1, G), 3), rng.random(G)
+    ctrl = np.log1p(rng.poisson(3.0, G).astype(float))
+    mz = 2.2250738585072014e-308
+    for x, par in ((np.ones((G, 1)), np.array([0.8, 0.4, -0.5])),
+                   (np.column_stack([np.ones(G), ctrl]), np.array([0.8, -0.1, 0.4, -0.5, 0.2]))):
+        v, g = oracle.glmZINB(par, y, x, o, w, mz)
+        num = np.zeros(par.size)
+        for i in range(par.size):
+            h = 1e-6
+            a, b = par.copy(), par.copy()
+            a[i] += h
+            b[i] -= h
+            num[i] = (oracle.glmZINB(a, y, x, o, w, mz, grad=False)[0] - oracle.glmZINB(b, y, x, o, w, mz, grad=False)[0]) / (2 * h)
+        assert np.max(np.abs(g - num)) <= 1e-5 * max(1.0, np.max(np.abs(num)))
+        P = x.shape[1]
+        nozi = par.copy()
+        nozi[P + 1] = -40.0
+        nozi[P + 2:] = 0.0
+        vz = oracle.glmZINB(nozi, y, x, o, w, mz, grad=False)[0]
+        vn = oracle.glmNB(par[:P + 1], y, x, o, w, grad=False)[0]
+        assert abs(vz - vn) <= 1e-9 * abs(vn)
