@@ -60,7 +60,9 @@ PROTOTYPES = {
     "ehmm_loglik_consensus_zinb": [_sess, _dp, _dp, C.c_int, C.c_double],
     "ehmm_loglik_init": [_sess, _dp, _dp],
     "ehmm_loglik_differential_hmm": [_sess, _dp, _dp, C.c_double],
+    "ehmm_loglik_differential_hmm_zinb": [_sess, _dp, _dp, C.c_double],
     "ehmm_inner_expstep": [_sess, _dp, _dp, C.c_double],
+    "ehmm_inner_expstep_zinb": [_sess, _dp, _dp, C.c_double],
     "ehmm_expstep": [_sess, _dp, _dp, _dp],
     "ehmm_expstep_device": [_sess, _dp, _dp, C.c_void_p],
     "ehmm_loglik_value": [_sess, _dp],
@@ -95,6 +97,7 @@ PROTOTYPES = {
     "ehmm_glm_zinb": [_sess, C.c_int, _dp, C.c_int, C.c_double, _dp, _dp],
     "ehmm_glm_nb_batch": [_sess, C.c_int, C.POINTER(C.c_int), _dp, C.c_int, _dp, _dp],
     "ehmm_glm_mix_nb": [_sess, _dp, C.c_double, _dp, _dp],
+    "ehmm_glm_mix_zinb": [_sess, _dp, C.c_double, _dp, _dp],
     "ehmm_profile_kernels": [],
     "ehmm_profile_name": [C.c_int],
     "ehmm_profile": [_sess, C.c_int],

@@ -43,10 +43,9 @@ def estimateCoefficients(z, counts, offsets, control, type_, dist="nb"):
         zip_ = max(0.01, (s2 - mu) / (s2 + mu ** 2 - mu))
         par.append((mu, disp, zip_))
     if type_ == "differential":
-        if dist != "nb":
-            raise NotImplementedError("the differential model with dist='zinb' is not on the accelerated path yet")
         p1 = np.log(np.array(par[0][:2]))
-        return [p1, np.log(np.array(par[1][:2])) - p1]
+        p2 = np.log(np.array(par[1][:2])) - p1
+        return [p1, p2] if dist == "nb" else [np.concatenate([[math.log(par[0][2])], p1]), p2]
     first = [math.log(par[0][0]), par[0][1]]
     if dist == "zinb":
         first = [math.log(par[0][2])] + first
@@ -96,8 +95,8 @@ def consensusHMM(counts, offsets, peaks, condition, control, controls=None, devi
     return dict(session=s, theta=th, history=fit)
 
 
-def differentialHMM(counts, offsets, peaks, condition, control, device=0, key=None, session=None):
-    """R/base-core.R:69-157 (dist = 'nb', control$pattern = NULL -> all 2^G - 2 patterns)."""
+def differentialHMM(counts, offsets, peaks, condition, control, device=0, key=None, session=None, dist="nb"):
+    """R/base-core.R:69-157 (control$pattern = NULL -> all 2^G - 2 patterns)."""
     counts = np.asarray(counts)
     M, N = counts.shape
     cond = list(dict.fromkeys(condition))
@@ -125,9 +124,9 @@ def differentialHMM(counts, offsets, peaks, condition, control, device=0, key=No
     sub = diff[np.isin(diff, zseq)]
     delta = np.array([(sub == zq).sum() / max(sub.size, 1) for zq in zseq], dtype=np.float64)
     theta = dict(pi=np.array([0.999, 0.0005, 0.0005]), gamma=em.estimateTransitionProb(chain, 3), delta=delta,
-                 psi=estimateCoefficients(z, counts, offsets, control, "differential"))
+                 psi=estimateCoefficients(z, counts, offsets, control, "differential", dist))
     s.rng_set_state(_stream().state)
-    fit = em.outerEMDifferential(theta, s, N, control)
+    fit = em.outerEMDifferential(theta, s, N, control, dist=dist)
     _stream().state[:] = s.rng_get_state()
     th = fit["theta_new"]
     s.viterbi(th["pi"], th["gamma"], fetch=False)
@@ -142,7 +141,5 @@ def epigraHMM(counts, offsets, peaks, condition, control, type="consensus", dist
     if type == "consensus":
         return consensusHMM(counts, offsets, peaks, condition, control, dist=dist, **kw)
     if type == "differential":
-        if dist != "nb":
-            raise NotImplementedError("the differential model with dist='zinb' is not on the accelerated path yet")
-        return differentialHMM(counts, offsets, peaks, condition, control, **kw)
+        return differentialHMM(counts, offsets, peaks, condition, control, dist=dist, **kw)
     raise ValueError("type must be 'consensus' or 'differential'")

@@ -210,8 +210,8 @@ inline bool has(const ehmm_session *s, unsigned bits) { return (s->valid & bits)
 // emission.cu
 int emis_consensus(ehmm_session *s, const double *th1, const double *th2, int P, double minZero, const double *zi = nullptr);
 int emis_init(ehmm_session *s, const double *psi1, const double *psi2);
-int emis_differential_hmm(ehmm_session *s, const double *delta, const double *psi, double minZero);
-int emis_inner_estep(ehmm_session *s, const double *delta, const double *psi, double minZero);
+int emis_differential_hmm(ehmm_session *s, const double *delta, const double *psi, double minZero, int zinb = 0);
+int emis_inner_estep(ehmm_session *s, const double *delta, const double *psi, double minZero, int zinb = 0);
 int inner_maxstepprob(ehmm_session *s, double *delta_out);
 int inner_mstep_sums(ehmm_session *s, double *sums);
 // rc.cu
@@ -236,6 +236,7 @@ int glm_nb(ehmm_session *s, int column, const double *par, int P, double *value,
 int glm_zinb(ehmm_session *s, int column, const double *par, int P, double minZero, double *value, double *grad);
 int glm_nb_batch(ehmm_session *s, int ncols, const int *columns, const double *pars, int P, double *values, double *grads);
 int glm_mix_nb(ehmm_session *s, const double *par, double minZero, double *value, double *grad);
+int glm_mix_zinb(ehmm_session *s, const double *par, double minZero, double *value, double *grad);
 // viterbi.cu
 int viterbi(ehmm_session *s, const double *pi, const double *gamma, double *states_out);
 int viterbi_forward(ehmm_session *s, const double *pi, const double *gamma, const double *v_in, double *v_out);

@@ -24,6 +24,8 @@ struct EmisParams {
     double lgs[MAX_DENS];    // lgamma(size)
     double minZero, lminZero, thr;
     double z0, z1;           // zero-inflation predictor of density 0 (ZINB background): z0 [+ z1*ctrl] + offset
+    double zip;              // differential model with dist = 'zinb': constant zero-inflation probability of density 0
+    int zi_diff;             // ... and the flag that switches it on
     int tabn;
 };
 
@@ -63,6 +65,11 @@ __device__ __forceinline__ double zinb_cell(int x, double l01, double xbeta) {
     const double zip = 1.0 / (1.0 + exp(-xbeta));
     const double l1mz = log(1.0 - zip);
     return (x == 0) ? log(zip + exp(l1mz + l01)) : (l1mz + l01);
+}
+
+// dzinb(log = TRUE), R/base-loglikelihood.R:152-158, from the NB log-density l of the same cell
+__device__ __forceinline__ double dzinb_log(int x, double l, const EmisParams &P) {
+    return log((x == 0 ? P.zip : 0.0) + (1.0 - P.zip) * (exp(l) + P.minZero));
 }
 
 // loglikConsensusHMM: LL[j,k] = sum_i log(NB(y_ji; mu=exp(th_k0 [+ th_k1*ctrl_ji] + o_ji), size_k) + minZero);
@@ -154,7 +161,9 @@ __global__ void __launch_bounds__(EM_NT)
     if (g == 0) { E[0] = make_double2(0.0, 0.0); return; }
     const int x = (int)uy[g];
     const double o = uoff[g];
-    E[g] = make_double2(nb_logpmf(x, P.b0[0] + o, 0, P, tab), nb_logpmf(x, P.b0[1] + o, 1, P, tab));
+    double l0 = nb_logpmf(x, P.b0[0] + o, 0, P, tab);
+    if (P.zi_diff) l0 = dzinb_log(x, l0, P);
+    E[g] = make_double2(l0, nb_logpmf(x, P.b0[1] + o, 1, P, tab));
 }
 
 // per-bin pieces of the differential model: LL0 = sum_i l0_i, LL2 = sum_i l1_i, d_i = l1_i - l0_i
@@ -180,6 +189,7 @@ __device__ __forceinline__ void diff_cells(int64_t j, int64_t M, int N, const in
                 const int x = __ldg(y + c);
                 const double o = __ldg(off + c);
                 l0 = nb_logpmf(x, P.b0[0] + o, 0, P, tab);
+                if (P.zi_diff) l0 = dzinb_log(x, l0, P);
                 l1 = nb_logpmf(x, P.b0[1] + o, 1, P, tab);
             }
             LL0 += l0;
@@ -381,8 +391,15 @@ int diff_source(ehmm_session *s, const EmisParams &P, const int32_t *&y, const d
     return EHMM_OK;
 }
 
-void fill_diff(EmisParams &P, const double *psi) {
-    // psi = (b_bg, l_bg, db, dl): mu_D = exp(psi1 + psi3*D + o), size_D = exp(psi2 + psi4*D)
+void fill_diff(EmisParams &P, const double *psi, int zinb) {
+    // nb:   psi = (b_bg, l_bg, db, dl): mu_D = exp(psi1 + psi3*D + o), size_D = exp(psi2 + psi4*D)
+    // zinb: psi = (lambda, b_bg, l_bg, db, dl), the D = 0 density zero-inflated with zip = logistic(lambda)
+    //       (R/base-loglikelihood.R:23-36,72-95)
+    if (zinb) {
+        P.zi_diff = 1;
+        P.zip = exp(psi[0]) / (1.0 + exp(psi[0]));
+        psi += 1;
+    }
     fill_density(P, 0, psi[0], 0.0, exp(psi[1]));
     fill_density(P, 1, psi[0] + psi[2], 0.0, exp(psi[1] + psi[3]));
 }
@@ -461,12 +478,12 @@ int emis_init(ehmm_session *s, const double *psi1, const double *psi2) {
     return EHMM_OK;
 }
 
-int emis_differential_hmm(ehmm_session *s, const double *delta, const double *psi, double minZero) {
+int emis_differential_hmm(ehmm_session *s, const double *delta, const double *psi, double minZero, int zinb) {
     EHMM_TRY(require_data(s, "loglikDifferentialHMM"));
     EHMM_REQUIRE(s->K == 3, EHMM_ERR_ARG, "loglikDifferentialHMM needs a K=3 session (K=%d)", s->K);
     EmisParams P = {};
     MixParams X = {};
-    fill_diff(P, psi);
+    fill_diff(P, psi, zinb);
     EHMM_TRY(fill_mix(s, X, delta));
     EHMM_TRY(prepare_tab(s, P, 2, minZero));
     EHMM_TRY(s->logf.reserve(sizeof(double) * s->M * 3));
@@ -485,11 +502,11 @@ int emis_differential_hmm(ehmm_session *s, const double *delta, const double *ps
     return EHMM_OK;
 }
 
-int emis_inner_estep(ehmm_session *s, const double *delta, const double *psi, double minZero) {
+int emis_inner_estep(ehmm_session *s, const double *delta, const double *psi, double minZero, int zinb) {
     EHMM_TRY(require_data(s, "innerExpStep"));
     EmisParams P = {};
     MixParams X = {};
-    fill_diff(P, psi);
+    fill_diff(P, psi, zinb);
     EHMM_TRY(fill_mix(s, X, delta));
     EHMM_TRY(prepare_tab(s, P, 2, minZero));
     EHMM_TRY(s->eta.reserve(sizeof(double) * s->M * s->B));

@@ -234,6 +234,58 @@ __global__ void __launch_bounds__(GLM_NT)
     block_store<5>(acc, part);
 }
 
+// glmMixZINB / derivMixZINB (R/base-optim.R:261-362): rows of column 0 (background) and mixture rows
+// with Dsg.Mix = 0 are zero-inflated NB with (zip, mu_z, size_z); rows of the last column and
+// mixture rows with Dsg.Mix = 1 are NB with (mu_n, size_n).
+struct MixZPar {
+    double lam, zip, bz, bn, minZero, thr;
+    double size[2], lsize[2], lgs[2], dg[2];  // 0: zero-inflated background, 1: enrichment
+};
+
+// out: [0] = value, [1..5] = gradient wrt (lambda, b_z, l_z, b_n, l_n)
+__global__ void __launch_bounds__(GLM_NT)
+    glm_mix_zinb_kernel(int64_t G, int ncol, const double *__restrict__ buckets, const double *__restrict__ y,
+                        const double *__restrict__ off, const uint8_t *__restrict__ dsg, MixZPar P, double *__restrict__ part) {
+    double acc[6] = {0, 0, 0, 0, 0, 0};
+    const int64_t total = (int64_t)ncol * (G + 1);
+    for (int64_t idx = (int64_t)blockIdx.x * GLM_NT + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * GLM_NT) {
+        const double w = buckets[idx];
+        if (w == 0.0) continue;
+        const int c = (int)(idx / (G + 1));
+        const int64_t g = idx - (int64_t)c * (G + 1);
+        int D;
+        if (c == 0) D = 0;
+        else if (c == ncol - 1) D = 1;
+        else D = dsg[g + (int64_t)(c - 1) * (G + 1)];
+        const double yy = y[g], o = off[g];
+        const double ph = P.size[D], eta = (D ? P.bn : P.bz) + o, mu = exp(eta);
+        const double lpmf = nb_logpmf_direct(yy, eta, ph, P.lsize[D], P.lgs[D]);
+        if (D) {  // log(dnbinom + minZero) and the NB score
+            const double lv = (lpmf > P.thr) ? lpmf : log(exp(lpmf) + P.minZero);
+            acc[0] += -w * lv;
+            acc[4] += -w * (yy / mu - ((yy + ph) / (mu + ph))) * mu;
+            acc[5] += -w * (digamma_pos(yy + ph) - P.dg[1] + 1.0 + P.lsize[1] - (yy + ph) / (mu + ph) - log(mu + ph)) * ph;
+        } else {
+            const double zip = P.zip;
+            if (yy == 0.0) {
+                const double d0 = exp(lpmf);                          // dnbinom(0) = (ph/(mu+ph))^ph
+                const double dz = zip + (1.0 - zip) * (d0 + P.minZero);  // dzinb(0, log = FALSE)
+                const double q = ph / (mu + ph);
+                acc[0] += -w * log(dz);
+                acc[1] += -w * (((1.0 - d0) / dz) * zip * (1.0 - zip));
+                acc[2] += -w * ((-(1.0 - zip) * pow(q, ph + 1.0) / dz) * mu);
+                acc[3] += -w * ((1.0 - zip) * pow(q, ph) * (log(q) + mu / (mu + ph)) * (1.0 / dz) * ph);
+            } else {
+                acc[0] += -w * log((1.0 - zip) * (exp(lpmf) + P.minZero));
+                acc[1] += -w * (-zip);
+                acc[2] += -w * ((yy / mu - (yy + ph) / (mu + ph)) * mu);
+                acc[3] += -w * ((digamma_pos(yy + ph) - P.dg[0] + 1.0 + P.lsize[0] - (yy + ph) / (mu + ph) - log(mu + ph)) * ph);
+            }
+        }
+    }
+    block_store<6>(acc, part);
+}
+
 __global__ void __launch_bounds__(256) glm_final_kernel(const double *__restrict__ part, int nblk, int ncol,
                                                         double *__restrict__ out) {
     __shared__ double sh[256];
@@ -406,6 +458,38 @@ int glm_mix_nb(ehmm_session *s, const double *par, double minZero, double *value
     *value = o[0];
     if (grad)
         for (int i = 0; i < 4; i++) grad[i] = o[1 + i];
+    return EHMM_OK;
+}
+
+// par = (lambda, b_bg, l_bg, b_enr, l_enr) -- optimDifferential's "newpar" (R/base-optim.R:80-82)
+int glm_mix_zinb(ehmm_session *s, const double *par, double minZero, double *value, double *grad) {
+    EHMM_REQUIRE(s->u_dsg.p, EHMM_ERR_STATE, "glmMixZINB: dtUnique has no Dsg.Mix columns (ehmm_set_groups)");
+    MixZPar P;
+    P.lam = par[0];
+    P.zip = exp(par[0]) / (1.0 + exp(par[0]));
+    P.bz = par[1];
+    P.bn = par[3];
+    P.minZero = minZero;
+    P.thr = log(minZero) + 40.0;
+    for (int D = 0; D < 2; D++) {
+        P.size[D] = exp(D ? par[4] : par[2]);
+        P.lsize[D] = log(P.size[D]);
+        P.lgs[D] = lgamma(P.size[D]);
+        P.dg[D] = host_digamma(P.size[D]);
+    }
+    EHMM_TRY(s->glm_part.reserve(sizeof(double) * ((size_t)EHMM_MAX_K * 148 * 4 * 4 + EHMM_MAX_K * 4) + 64 +
+                                 sizeof(double) * ((size_t)148 * 4 * GLM_MAXOUT + GLM_MAXOUT)));
+    const int ncol = s->B + 2;
+    const int nblk = blocks_for((int64_t)ncol * (s->G + 1));
+    PROF(s, KID_GLM), glm_mix_zinb_kernel<<<nblk, GLM_NT, 0, s->stream>>>(
+        s->G, ncol, s->rc_buckets.as<double>(), s->u_chip.as<double>(), s->u_off.as<double>(), s->u_dsg.as<uint8_t>(), P,
+        s->glm_part.as<double>());
+    EHMM_CK(cudaGetLastError());
+    double o[6];
+    EHMM_TRY(finish(s, nblk, 6, o));
+    *value = o[0];
+    if (grad)
+        for (int i = 0; i < 5; i++) grad[i] = o[1 + i];
     return EHMM_OK;
 }
 

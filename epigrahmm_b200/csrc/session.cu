@@ -451,6 +451,12 @@ int ehmm_loglik_init(ehmm_session *s, const double *psi1, const double *psi2) {
     return emis_init(s, psi1, psi2);
 }
 
+int ehmm_loglik_differential_hmm_zinb(ehmm_session *s, const double *delta, const double *psi, double minZero) {
+    EHMM_TRY(check_session(s));
+    EHMM_REQUIRE(delta && psi, EHMM_ERR_ARG, "null parameters");
+    return emis_differential_hmm(s, delta, psi, minZero, 1);
+}
+
 int ehmm_loglik_differential_hmm(ehmm_session *s, const double *delta, const double *psi, double minZero) {
     EHMM_TRY(check_session(s));
     EHMM_REQUIRE(delta && psi, EHMM_ERR_ARG, "null parameters");
@@ -461,6 +467,12 @@ int ehmm_inner_expstep(ehmm_session *s, const double *delta, const double *psi, 
     EHMM_TRY(check_session(s));
     EHMM_REQUIRE(delta && psi, EHMM_ERR_ARG, "null parameters");
     return emis_inner_estep(s, delta, psi, minZero);
+}
+
+int ehmm_inner_expstep_zinb(ehmm_session *s, const double *delta, const double *psi, double minZero) {
+    EHMM_TRY(check_session(s));
+    EHMM_REQUIRE(delta && psi, EHMM_ERR_ARG, "null parameters");
+    return emis_inner_estep(s, delta, psi, minZero, 1);
 }
 
 int ehmm_expstep(ehmm_session *s, const double *pi, const double *gamma, const double *logf) {
@@ -812,6 +824,13 @@ int ehmm_glm_mix_nb(ehmm_session *s, const double *par, double minZero, double *
     EHMM_REQUIRE(par && value, EHMM_ERR_ARG, "null pointer");
     EHMM_REQUIRE(s->rc_columns == s->B + 2 && s->B > 0, EHMM_ERR_STATE, "glmMixNB: differential rejection tables not available");
     return glm_mix_nb(s, par, minZero, value, grad);
+}
+
+int ehmm_glm_mix_zinb(ehmm_session *s, const double *par, double minZero, double *value, double *grad) {
+    EHMM_TRY(check_session(s));
+    EHMM_REQUIRE(par && value, EHMM_ERR_ARG, "null pointer");
+    EHMM_REQUIRE(s->rc_columns == s->B + 2 && s->B > 0, EHMM_ERR_STATE, "glmMixZINB: differential rejection tables not available");
+    return glm_mix_zinb(s, par, minZero, value, grad);
 }
 
 int ehmm_profile_kernels(void) { return KID_COUNT; }

@@ -316,6 +316,21 @@ def optimDifferential(par, backend, control):
     return dict(par=np.asarray(x)[perm], convergence=conv)
 
 
+def optimDifferentialZINB(par, backend, control):
+    """R/base-optim.R:80-101 (dist='zinb'): par = unlist(psi) = (lambda, b, l, db, dl); the optimiser sees
+    (lambda, b, l, b + db, l + dl)."""
+    par = np.asarray(par, dtype=np.float64)
+    newpar = np.array([par[0], par[1], par[2], par[1] + par[3], par[2] + par[4]])
+    try:
+        lower = np.full(5, math.log(control["minZero"]))
+        upper = np.array([np.inf, np.inf, math.log(control["maxDisp"]), np.inf, math.log(control["maxDisp"])])
+        x, conv = _lbfgsb(lambda x: backend.glm_mix_zinb(x, control["minZero"]), newpar, lower, upper)
+    except Exception:
+        x, conv = par, 99  # the reference back-transforms the untouched par as well (R/base-optim.R:98-100)
+    x = np.asarray(x)
+    return dict(par=np.array([x[0], x[1], x[2], x[3] - x[1], x[4] - x[2]]), convergence=conv)
+
+
 def _rejection_cut(iteration, control):
     rejectionCut = max(0.9 ** iteration, control["probCut"])
     return (control["probCut"] > 0) * rejectionCut
@@ -396,19 +411,21 @@ def emInitialization(theta_old, backend, control, callback=None):
     return dict(theta_new=theta_new, controlHist=controlHist, parHist=parHist)
 
 
-def innerEMDifferential(theta_old, backend, probCut, control):
-    """R/base-EM.R:184-228.  psi = [(b, l), (db, dl)]."""
+def innerEMDifferential(theta_old, backend, probCut, control, dist="nb"):
+    """R/base-EM.R:184-228.  psi = [(b, l), (db, dl)]; with dist = 'zinb' [(lambda, b, l), (db, dl)]."""
+    inner_expstep = backend.inner_expstep if dist == "nb" else backend.inner_expstep_zinb
+    nfirst = 2 if dist == "nb" else 3
     count, error = 0, 1.0
     tmp_old = copy.deepcopy(theta_old)
     tmp_new = copy.deepcopy(theta_old)
     optimMLE = None
     while count < control["maxIterInnerEM"] and error > control["epsilonInnerEM"]:
         psi_flat = np.concatenate([np.ravel(p) for p in tmp_old["psi"]])
-        backend.inner_expstep(tmp_old["delta"], psi_flat, control["minZero"])
+        inner_expstep(tmp_old["delta"], psi_flat, control["minZero"])
         tmp_new["delta"] = backend.inner_maxstepprob()
         backend.rc_differential(probCut)
-        optimMLE = optimDifferential(psi_flat, backend, control)
-        tmp_new["psi"] = [optimMLE["par"][0:2].copy(), optimMLE["par"][2:4].copy()]
+        optimMLE = (optimDifferential if dist == "nb" else optimDifferentialZINB)(psi_flat, backend, control)
+        tmp_new["psi"] = [optimMLE["par"][:nfirst].copy(), optimMLE["par"][nfirst:].copy()]
         new = np.concatenate([tmp_new["delta"], np.concatenate(tmp_new["psi"])])
         old = np.concatenate([np.ravel(tmp_old["delta"]), psi_flat])
         with np.errstate(divide="ignore", invalid="ignore"):
@@ -420,8 +437,9 @@ def innerEMDifferential(theta_old, backend, probCut, control):
 
 def outerEMDifferential(theta_old, backend, N, control, dist="nb", callback=None):
     """R/base-EM.R:234-296.  theta = dict(pi, gamma, delta, psi=[(b, l), (db, dl)])."""
-    if dist != "nb":
-        raise NotImplementedError("dist='zinb' is not on the accelerated path yet")
+    if dist not in ("nb", "zinb"):
+        raise ValueError("dist must be 'nb' or 'zinb'")
+    loglik = backend.loglik_differential_hmm if dist == "nb" else backend.loglik_differential_hmm_zinb
     controlHist, parHist = [controlList()], []
     theta_old = copy.deepcopy(theta_old)
     theta_new = copy.deepcopy(theta_old)
@@ -432,10 +450,10 @@ def outerEMDifferential(theta_old, backend, N, control, dist="nb", callback=None
         cur = controlHist[-1]
         cur["iteration"] += 1
         psi_flat = np.concatenate([np.ravel(p) for p in theta_old["psi"]])
-        backend.loglik_differential_hmm(theta_old["delta"], psi_flat, control["minZero"])
+        loglik(theta_old["delta"], psi_flat, control["minZero"])
         backend.expstep(theta_old["pi"], theta_old["gamma"])
         theta_new.update(backend.maxstepprob())
-        inner = innerEMDifferential(theta_old, backend, _rejection_cut(cur["iteration"], control), control)
+        inner = innerEMDifferential(theta_old, backend, _rejection_cut(cur["iteration"], control), control, dist)
         theta_new["delta"] = inner["theta_new"]["delta"]
         theta_new["psi"] = inner["theta_new"]["psi"]
         bic = backend.bic(numPar, N)

@@ -159,6 +159,15 @@ class Session:
         d, p = _f64(delta), _f64(np.concatenate([np.ravel(x) for x in psi]) if isinstance(psi, (list, tuple)) else psi)
         check(lib.ehmm_loglik_differential_hmm(self._h, dptr(d), dptr(p), float(minZero)))
 
+    def loglik_differential_hmm_zinb(self, delta, psi, minZero):
+        """dist = 'zinb': psi = (lambda, b_bg, l_bg, db, dl)"""
+        d, p = _f64(delta), _f64(np.concatenate([np.ravel(x) for x in psi]) if isinstance(psi, (list, tuple)) else psi)
+        check(lib.ehmm_loglik_differential_hmm_zinb(self._h, dptr(d), dptr(p), float(minZero)))
+
+    def inner_expstep_zinb(self, delta, psi, minZero):
+        d, p = _f64(delta), _f64(np.concatenate([np.ravel(x) for x in psi]) if isinstance(psi, (list, tuple)) else psi)
+        check(lib.ehmm_inner_expstep_zinb(self._h, dptr(d), dptr(p), float(minZero)))
+
     def inner_expstep(self, delta, psi, minZero):
         d, p = _f64(delta), _f64(np.concatenate([np.ravel(x) for x in psi]) if isinstance(psi, (list, tuple)) else psi)
         check(lib.ehmm_inner_expstep(self._h, dptr(d), dptr(p), float(minZero)))
@@ -344,6 +353,14 @@ class Session:
         v = C.c_double()
         g = np.empty(4) if grad else None
         check(lib.ehmm_glm_mix_nb(self._h, dptr(par), float(minZero), C.byref(v), dptr(g)))
+        return v.value, g
+
+    def glm_mix_zinb(self, par, minZero, grad=True):
+        """glmMixZINB/derivMixZINB: par = (lambda, b_bg, l_bg, b_enr, l_enr)"""
+        par = _f64(par)
+        v = C.c_double()
+        g = np.empty(5) if grad else None
+        check(lib.ehmm_glm_mix_zinb(self._h, dptr(par), float(minZero), C.byref(v), dptr(g)))
         return v.value, g
 
     # -- launch accounting -----------------------------------------------------------------

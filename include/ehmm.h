@@ -98,8 +98,12 @@ int ehmm_loglik_consensus_zinb(ehmm_session *s, const double *theta1, const doub
 int ehmm_loglik_init(ehmm_session *s, const double *psi1, const double *psi2);
 /* loglikDifferentialHMM NB branch, R/base-loglikelihood.R:45-71,96. psi = (b, l, db, dl). */
 int ehmm_loglik_differential_hmm(ehmm_session *s, const double *delta, const double *psi, double minZero);
+/* dist = 'zinb' (R/base-loglikelihood.R:23-36,72-96): psi = (lambda, b_bg, l_bg, db, dl); the
+ * D = 0 density is zero-inflated with zip = exp(lambda) / (1 + exp(lambda)). */
+int ehmm_loglik_differential_hmm_zinb(ehmm_session *s, const double *delta, const double *psi, double minZero);
 /* innerExpStep, R/base-EM.R:302-314 -> dataset mixtureProb. */
 int ehmm_inner_expstep(ehmm_session *s, const double *delta, const double *psi, double minZero);
+int ehmm_inner_expstep_zinb(ehmm_session *s, const double *delta, const double *psi, double minZero);
 
 /* ---- E-step / M-step (src/*.cpp) ---------------------------------------------------- */
 /* expStep, src/expStep.cpp:45-123. logf: host M x K matrix, or NULL to use the
@@ -189,6 +193,9 @@ int ehmm_glm_zinb(ehmm_session *s, int column, const double *par, int P, double 
 int ehmm_glm_nb_batch(ehmm_session *s, int n, const int *columns, const double *pars, int P, double *values, double *grads);
 /* glmMixNB / derivMixNB, R/base-optim.R:187-255, over all B+2 tables. par = (b, db, l, dl). */
 int ehmm_glm_mix_nb(ehmm_session *s, const double *par, double minZero, double *value, double *grad);
+/* glmMixZINB / derivMixZINB (R/base-optim.R:261-362): par = (lambda, b_bg, l_bg, b_enr, l_enr),
+ * grad has 5 entries. */
+int ehmm_glm_mix_zinb(ehmm_session *s, const double *par, double minZero, double *value, double *grad);
 
 /* ---- launch accounting and per-kernel timing --------------------------------------------- */
 /* Number of distinct kernels the library tracks and their names (index = kernel id). */

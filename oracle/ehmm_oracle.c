@@ -624,6 +624,118 @@ EO_API void eo_inner_estep(int64_t M, int N, int B, const int32_t *y, const doub
     }
 }
 
+/* ---- dist = 'zinb', differential model: psi = (lambda, b_bg, l_bg, db, dl) ---------------- */
+/* dzinb: R/base-loglikelihood.R:152-158 */
+static double eo_dzinb(double x, double size, double mu, double zip, int lg, double minZero) {
+    double v = zip * (x == 0 ? 1.0 : 0.0) + (1 - zip) * (eo_dnbinom_mu(x, size, mu, 0) + minZero);
+    return lg ? log(v) : v;
+}
+
+/* loglikDifferential, ZINB: R/base-loglikelihood.R:23-36 (the masks multiply, as in R) */
+EO_API void eo_loglik_differential_zinb(int64_t M, int N, int B, const int32_t *y, const double *off,
+                                        const uint8_t *design, const double *delta, const double *psi,
+                                        double minZero, double *ll) {
+    double zip = exp(psi[0]) / (1 + exp(psi[0]));
+    for (int b = 0; b < B; b++) {
+        double ld = log(delta[b]);
+        for (int64_t j = 0; j < M; j++) {
+            long double acc = 0;
+            for (int i = 0; i < N; i++) {
+                int64_t c = j + (int64_t)i * M;
+                double D = design[b * N + i];
+                double nb = eo_dnbinom_mu((double)y[c], exp(psi[2] + psi[4]), exp(psi[1] + psi[3] + off[c]), 1);
+                double zi = eo_dzinb((double)y[c], exp(psi[2]), exp(psi[1] + off[c]), zip, 1, minZero);
+                acc += (D == 1) * nb + (D == 0) * zi;
+            }
+            ll[j + (int64_t)b * M] = ld + (double)acc;
+        }
+    }
+}
+
+/* loglikDifferentialHMM, ZINB: R/base-loglikelihood.R:72-96 */
+EO_API void eo_loglik_differential_hmm_zinb(int64_t M, int N, int B, const int32_t *y, const double *off,
+                                            const uint8_t *design, const double *delta, const double *psi,
+                                            double minZero, double *LL) {
+    double *ll = (double *)malloc(sizeof(double) * (size_t)(M * B));
+    eo_loglik_differential_zinb(M, N, B, y, off, design, delta, psi, minZero, ll);
+    double zip = exp(psi[0]) / (1 + exp(psi[0]));
+    for (int64_t j = 0; j < M; j++) {
+        long double a0 = 0, a2 = 0;
+        for (int i = 0; i < N; i++) {
+            int64_t c = j + (int64_t)i * M;
+            a0 += eo_dzinb((double)y[c], exp(psi[2]), exp(psi[1] + off[c]), zip, 1, minZero);
+            a2 += eo_dnbinom_mu((double)y[c], exp(psi[2] + psi[4]), exp(psi[1] + psi[3] + off[c]), 1);
+        }
+        double s = exp(ll[j]);
+        for (int b = 1; b < B; b++) s = s + exp(ll[j + (int64_t)b * M]);
+        double v[3] = {(double)a0, log(s), (double)a2};
+        for (int k = 0; k < 3; k++) LL[j + k * M] = isinf(v[k]) ? log(minZero) : v[k];
+    }
+    free(ll);
+}
+
+/* innerExpStep with dist = 'zinb': R/base-EM.R:302-314 */
+EO_API void eo_inner_estep_zinb(int64_t M, int N, int B, const int32_t *y, const double *off, const uint8_t *design,
+                                const double *delta, const double *psi, double minZero, double *eta) {
+    eo_loglik_differential_zinb(M, N, B, y, off, design, delta, psi, minZero, eta);
+    double lmz = log(minZero);
+    for (int64_t j = 0; j < M; j++) {
+        double s = 0;
+        for (int b = 0; b < B; b++) {
+            double v = eta[j + (int64_t)b * M];
+            if (exp(v) == 0) v = lmz;
+            v = exp(v);
+            eta[j + (int64_t)b * M] = v;
+            s = (b == 0) ? v : s + v;
+        }
+        for (int b = 0; b < B; b++) eta[j + (int64_t)b * M] /= s;
+    }
+}
+
+/* glmMixZINB / derivMixZINB: R/base-optim.R:261-362.  Same long table as eo_glm_mix_nb;
+ * par = (lambda, b_bg, l_bg, b_enr, l_enr) (all five free: optimDifferential passes b_bg + db). */
+EO_API double eo_glm_mix_zinb(int64_t n, int B, int maxid, const double *par, const int32_t *id,
+                              const double *w, const double *y, const double *off, const uint8_t *dsg,
+                              double minZero, double *grad) {
+    long double f = 0, g5[5] = {0, 0, 0, 0, 0};
+    (void)B;
+    double zip = exp(par[0]) / (1 + exp(par[0]));
+    double phz = exp(par[2]), phn = exp(par[4]);
+    for (int64_t r = 0; r < n; r++) {
+        double D; /* 1: NB (enriched) row, 0: ZINB (background) row */
+        if (id[r] == 1) D = 0;
+        else if (id[r] == maxid) D = 1;
+        else D = dsg[r + (int64_t)(id[r] - 2) * n];
+        double muz = exp(par[1] + off[r]), mun = exp(par[3] + off[r]);
+        double lnb = log(eo_dnbinom_mu(y[r], phn, mun, 0) + minZero);
+        double lzi = eo_dzinb(y[r], phz, muz, zip, 1, minZero);
+        if (id[r] == 1) f += -w[r] * lzi;
+        else if (id[r] == maxid) f += -w[r] * lnb;
+        else f += -w[r] * ((D == 1) * lnb + (D == 0) * lzi);
+        if (grad) {
+            double y0 = (y[r] == 0) ? 1.0 : 0.0, yn = 1 - y0;
+            if (id[r] != maxid) { /* ZINB part (masked by Dsg.Mix == 0 on mixture rows) */
+                double mk = (id[r] == 1) ? 1.0 : (D == 0);
+                double dz = eo_dzinb(0.0, phz, muz, zip, 0, minZero);
+                double g1 = -w[r] * mk * (y0 * (((1 - eo_dnbinom_mu(0.0, phz, muz, 0)) / dz) * zip * (1 - zip)) + yn * (-zip));
+                double g2 = -w[r] * mk * (y0 * ((-(1 - zip) * pow(phz / (muz + phz), phz + 1) / dz) * muz) +
+                                          yn * ((y[r] / muz - (y[r] + phz) / (muz + phz)) * muz));
+                double g3 = -w[r] * mk * (y0 * ((1 - zip) * pow(phz / (muz + phz), phz) * (log(phz / (muz + phz)) + muz / (muz + phz)) * (1 / dz) * phz) +
+                                          yn * ((eo_digamma(y[r] + phz) - eo_digamma(phz) + 1 + log(phz) - (y[r] + phz) / (muz + phz) - log(muz + phz)) * phz));
+                g5[0] += g1; g5[1] += g2; g5[2] += g3;
+            }
+            if (id[r] != 1) { /* NB part (masked by Dsg.Mix == 1 on mixture rows) */
+                double mk = (id[r] == maxid) ? 1.0 : (D == 1);
+                double g4 = -w[r] * mk * (y[r] / mun - ((y[r] + phn) / (mun + phn))) * mun;
+                double g5v = -w[r] * mk * (eo_digamma(y[r] + phn) - eo_digamma(phn) + 1 + log(phn) - (y[r] + phn) / (mun + phn) - log(mun + phn)) * phn;
+                g5[3] += g4; g5[4] += g5v;
+            }
+        }
+    }
+    if (grad) for (int i = 0; i < 5; i++) grad[i] = (double)g5[i];
+    return (double)f;
+}
+
 /* ------------------------------------------------------------------------ */
 /* NB-GLM objective / gradient (R/base-optim.R).  sum()/colSums() use long   */
 /* double accumulation as R does.                                            */

@@ -42,6 +42,7 @@ def lib():
         _lib.eo_bic.restype = C.c_double
         _lib.eo_glm_nb.restype = C.c_double
         _lib.eo_glm_zinb.restype = C.c_double
+        _lib.eo_glm_mix_zinb.restype = C.c_double
         _lib.eo_glm_mix_nb.restype = C.c_double
         for n in ("eo_reweight", "eo_reweight_buf", "eo_aggregate_compact", "eo_consensus_rc", "eo_differential_rc"):
             getattr(_lib, n).restype = C.c_int64
@@ -293,6 +294,50 @@ def innerExpStep(y, offsets, design, delta, psi, minZero):
     lib().eo_inner_estep(C.c_int64(M), N, B, _p(y, C.c_int32), _p(off), _p(d, C.c_uint8),
                          _p(_f64(delta)), _p(_f64(psi)), C.c_double(minZero), _p(eta))
     return eta
+
+
+def loglikDifferentialZINB(y, offsets, design, delta, psi, minZero):
+    """R/base-loglikelihood.R:23-36; psi = (lambda, b_bg, l_bg, db, dl)"""
+    y, off, d = _i32cm(y), _colmajor(offsets), _design(design)
+    M, N = y.shape
+    B = d.shape[0]
+    ll = np.empty((M, B), order="F")
+    lib().eo_loglik_differential_zinb(C.c_int64(M), N, B, _p(y, C.c_int32), _p(off), _p(d, C.c_uint8),
+                                      _p(_f64(delta)), _p(_f64(psi)), C.c_double(minZero), _p(ll))
+    return ll
+
+
+def loglikDifferentialHMMzinb(y, offsets, design, delta, psi, minZero):
+    """R/base-loglikelihood.R:72-96"""
+    y, off, d = _i32cm(y), _colmajor(offsets), _design(design)
+    M, N = y.shape
+    B = d.shape[0]
+    LL = np.empty((M, 3), order="F")
+    lib().eo_loglik_differential_hmm_zinb(C.c_int64(M), N, B, _p(y, C.c_int32), _p(off), _p(d, C.c_uint8),
+                                          _p(_f64(delta)), _p(_f64(psi)), C.c_double(minZero), _p(LL))
+    return LL
+
+
+def innerExpStepZINB(y, offsets, design, delta, psi, minZero):
+    y, off, d = _i32cm(y), _colmajor(offsets), _design(design)
+    M, N = y.shape
+    B = d.shape[0]
+    eta = np.empty((M, B), order="F")
+    lib().eo_inner_estep_zinb(C.c_int64(M), N, B, _p(y, C.c_int32), _p(off), _p(d, C.c_uint8),
+                              _p(_f64(delta)), _p(_f64(psi)), C.c_double(minZero), _p(eta))
+    return eta
+
+
+def glmMixZINB(par, id, weights, y, offsets, dsg, maxid, minZero, grad=True):
+    """R/base-optim.R:261-362 -> (value, gradient); par = (lambda, b_bg, l_bg, b_enr, l_enr)."""
+    dsg = np.asfortranarray(dsg, dtype=np.uint8)
+    n, B = dsg.shape
+    g = np.empty(5)
+    idv = np.ascontiguousarray(id, dtype=np.int32)
+    v = lib().eo_glm_mix_zinb(C.c_int64(n), B, int(maxid), _p(_f64(par)), _p(idv, C.c_int32), _p(_f64(weights)),
+                              _p(_f64(y)), _p(_f64(offsets)), _p(dsg, C.c_uint8), C.c_double(minZero),
+                              _p(g) if grad else None)
+    return v, g
 
 
 def glmNB(par, y, x, offset, weights, grad=True):

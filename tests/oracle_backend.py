@@ -35,6 +35,12 @@ class OracleBackend:
     def loglik_differential_hmm(self, delta, psi, minZero):
         self.h["logLikelihood"] = O.loglikDifferentialHMM(self.counts, self.offsets, self.design, delta, psi, minZero)
 
+    def loglik_differential_hmm_zinb(self, delta, psi, minZero):
+        self.h["logLikelihood"] = O.loglikDifferentialHMMzinb(self.counts, self.offsets, self.design, delta, psi, minZero)
+
+    def inner_expstep_zinb(self, delta, psi, minZero):
+        self.h["mixtureProb"] = O.innerExpStepZINB(self.counts, self.offsets, self.design, delta, psi, minZero)
+
     def inner_expstep(self, delta, psi, minZero):
         self.h["mixtureProb"] = O.innerExpStep(self.counts, self.offsets, self.design, delta, psi, minZero)
 
@@ -96,11 +102,20 @@ class OracleBackend:
             x = np.column_stack([x[:, 0], self.g["u_controls"][ids - 1]])
         return O.glmZINB(par, self.g["u_chip"][ids - 1], x, self.g["u_offsets"][ids - 1], self.rc[column][ids], minZero, grad)
 
-    def glm_mix_nb(self, par, minZero, grad=True):
+    def _mix_rows(self):
         B = self.B
         rows = [(c + 1, np.nonzero(self.rc[c])[0]) for c in range(B + 2)]
         id_ = np.concatenate([np.full(ix.size, c) for c, ix in rows])
         gi = np.concatenate([ix for _, ix in rows])
         w = np.concatenate([self.rc[c - 1][ix] for c, ix in rows])
+        return id_, gi, w
+
+    def glm_mix_nb(self, par, minZero, grad=True):
+        id_, gi, w = self._mix_rows()
         return O.glmMixNB(par, id_, w, self.g["u_chip"][gi - 1], self.g["u_offsets"][gi - 1], self.g["u_dsg"][gi - 1],
-                          B + 2, minZero, grad)
+                          self.B + 2, minZero, grad)
+
+    def glm_mix_zinb(self, par, minZero, grad=True):
+        id_, gi, w = self._mix_rows()
+        return O.glmMixZINB(par, id_, w, self.g["u_chip"][gi - 1], self.g["u_offsets"][gi - 1], self.g["u_dsg"][gi - 1],
+                            self.B + 2, minZero, grad)

@@ -113,3 +113,93 @@ def test_em_trajectory_zinb(ehmm, oracle):
             assert np.array_equal(s.rng_get_state(), rng.state())
             to = fo["theta_new"]
             assert np.array_equal(s.viterbi(th["pi"], th["gamma"]), be.viterbi(to["pi"], to["gamma"]))
+
+
+# ---- differential model with dist = 'zinb' -------------------------------------------------------
+
+def _zinb_diff_data(M, n_cond, n_rep, seed, inflate=0.25):
+    d = synth.make_differential(M, n_cond, n_rep, seed=seed)
+    rng = np.random.default_rng(seed + 1)
+    counts = d["counts"].copy()
+    counts[(rng.random(counts.shape) < inflate) & (d["z"][:, None] == 0)] = 0
+    d["counts"] = np.asfortranarray(counts)
+    return d
+
+
+PSI_Z = np.array([-1.0, np.log(2.0), np.log(3.0), np.log(6.0), np.log(4.0 / 3.0)])   # (lambda, b, l, db, dl)
+
+
+def test_differential_zinb_emission_and_mixture_posteriors(ehmm, oracle):
+    M, nc, nr = 9001, 3, 2
+    d = _zinb_diff_data(M, nc, nr, 61)
+    B = d["B"]
+    delta = np.linspace(1, 2, B)
+    delta /= delta.sum()
+    LLo = oracle.loglikDifferentialHMMzinb(d["counts"], d["offsets"], d["design"], delta, PSI_Z, MINZERO)
+    eta_o = oracle.innerExpStepZINB(d["counts"], d["offsets"], d["design"], delta, PSI_Z, MINZERO)
+    with ehmm.Session("zinb-d", M, 3) as s:
+        s.set_data(d["counts"], d["offsets"])
+        s.set_design(d["design"])
+        for grouped in (False, True):
+            if grouped:
+                s.build_groups()
+            s.loglik_differential_hmm_zinb(delta, PSI_Z, MINZERO)
+            assert _rel(s.fetch("logLikelihood"), LLo) <= 1e-10, grouped
+            s.inner_expstep_zinb(delta, PSI_Z, MINZERO)
+            assert np.max(np.abs(s.fetch("mixtureProb") - eta_o)) <= 1e-9, grouped
+
+
+def test_glm_mix_zinb_value_and_gradient(ehmm, oracle):
+    M, nc, nr = 9001, 3, 2
+    d = _zinb_diff_data(M, nc, nr, 67)
+    g = synth.make_groups(d["counts"], d["offsets"], design=d["design"])
+    th = synth.THETA_DIFFERENTIAL
+    B = d["B"]
+    delta = np.full(B, 1.0 / B)
+    be = OracleBackend(d["counts"], d["offsets"], 3, design=d["design"], groups=g, rng=oracle.RNG.set_seed(4))
+    be.loglik_differential_hmm_zinb(delta, PSI_Z, MINZERO)
+    be.expstep(th["pi"], th["gamma"])
+    be.inner_expstep_zinb(delta, PSI_Z, MINZERO)
+    be.rc_differential(0.05)
+    with ehmm.Session("zinb-dg", M, 3) as s:
+        s.set_data(d["counts"], d["offsets"])
+        s.set_design(d["design"])
+        s.set_groups(g["group"], g["u_chip"], g["u_offsets"], None, g["u_dsg"])
+        s.store("logProb1", be.fetch("logProb1"))
+        s.store("mixtureProb", be.fetch("mixtureProb"))
+        s.rng_set_state(oracle.RNG.set_seed(4).state())
+        s.rc_differential(0.05)
+        for par in (np.array([-1.0, 0.7, 1.1, 2.5, 1.4]), np.array([0.5, 0.2, 0.1, 1.9, 2.0]), np.array([-4.0, 1.0, 3.0, 2.0, 0.5])):
+            v, gr = s.glm_mix_zinb(par, MINZERO)
+            vo, go = be.glm_mix_zinb(par, MINZERO)
+            assert abs(v - vo) <= 1e-11 * abs(vo), (par, v, vo)
+            assert np.max(np.abs(gr - go)) <= 1e-9 * max(1.0, np.max(np.abs(go))), (par, gr, go)
+
+
+def test_em_trajectory_differential_zinb(ehmm, oracle):
+    M, nc, nr = 8009, 2, 2
+    d = _zinb_diff_data(M, nc, nr, 71)
+    g = synth.make_groups(d["counts"], d["offsets"], design=d["design"])
+    N, B = nc * nr, d["B"]
+    th = synth.THETA_DIFFERENTIAL
+    theta = dict(pi=th["pi"], gamma=th["gamma"], delta=np.full(B, 1.0 / B), psi=[PSI_Z[:3].copy(), PSI_Z[3:].copy()])
+    ctl = em.controlEM(maxIterEM=3)
+    rng = oracle.RNG.set_seed(8)
+    be = OracleBackend(d["counts"], d["offsets"], 3, design=d["design"], groups=g, rng=rng)
+    fo = em.outerEMDifferential(theta, be, N, ctl, dist="zinb")
+    with ehmm.Session("zinb-dem", M, 3) as s:
+        s.set_data(d["counts"], d["offsets"])
+        s.set_design(d["design"])
+        assert s.build_groups() == g["G"]
+        s.rng_set_state(oracle.RNG.set_seed(8).state())
+        fg = em.outerEMDifferential(theta, s, N, ctl, dist="zinb")
+        worst, tight = 0.0, 0
+        for pg, po in zip(fg["parHist"], fo["parHist"]):
+            r = _rel(em.unlist(pg), em.unlist(po))
+            worst, tight = max(worst, r), tight + (r <= 1e-9)
+            assert r <= 1e-6
+        assert tight >= len(fg["parHist"]) // 2
+        print("differential zinb trajectory: worst relative parameter difference %.3g" % worst)
+        assert fg["theta_new"]["psi"][0].size == 3 and fg["theta_new"]["psi"][1].size == 2
+        zi = 1.0 / (1.0 + np.exp(-fg["theta_new"]["psi"][0][0]))
+        assert 0.1 < zi < 0.5, zi

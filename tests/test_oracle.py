@@ -238,3 +238,48 @@ def test_glm_zinb_gradient_and_nb_limit(oracle):
         vz = oracle.glmZINB(nozi, y, x, o, w, mz, grad=False)[0]
         vn = oracle.glmNB(par[:P + 1], y, x, o, w, grad=False)[0]
         assert abs(vz - vn) <= 1e-9 * abs(vn)
+
+
+def test_differential_zinb_oracle_against_twin_and_differences(oracle):
+    """loglikDifferential(HMM) with dist='zinb' against a scipy twin; derivMixZINB against central differences"""
+    from scipy.stats import nbinom
+    rng = np.random.default_rng(21)
+    M, N, B = 200, 4, 2
+    design = np.array([[1, 1, 0, 0], [0, 0, 1, 1]], dtype=np.uint8)
+    y = rng.negative_binomial(3, 0.4, (M, N)).astype(np.int32)
+    y[rng.random((M, N)) < 0.3] = 0
+    off = np.round(rng.normal(0, 0.1, (M, N)), 3)
+    psi = np.array([-1.0, 0.7, 1.1, 1.3, 0.3])
+    delta = np.array([0.4, 0.6])
+    mz = 2.2250738585072014e-308
+    zp = np.exp(psi[0]) / (1 + np.exp(psi[0]))
+
+    def dnb(x, mu, size):
+        return nbinom.pmf(x, size, size / (size + mu))
+    lz = np.log(zp * (y == 0) + (1 - zp) * (dnb(y, np.exp(psi[1] + off), np.exp(psi[2])) + mz))
+    ln = nbinom.logpmf(y, np.exp(psi[2] + psi[4]), np.exp(psi[2] + psi[4]) / (np.exp(psi[2] + psi[4]) + np.exp(psi[1] + psi[3] + off)))
+    ll = np.stack([np.log(delta[b]) + np.where(design[b][None, :] == 1, ln, lz).sum(1) for b in range(B)], axis=1)
+    got = oracle.loglikDifferentialZINB(np.asfortranarray(y), np.asfortranarray(off), design, delta, psi, mz)
+    assert np.max(np.abs(got - ll)) <= 1e-10
+    LL = oracle.loglikDifferentialHMMzinb(np.asfortranarray(y), np.asfortranarray(off), design, delta, psi, mz)
+    assert np.max(np.abs(LL[:, 0] - lz.sum(1))) <= 1e-10 and np.max(np.abs(LL[:, 2] - ln.sum(1))) <= 1e-10
+    assert np.max(np.abs(LL[:, 1] - np.log(np.exp(ll).sum(1)))) <= 1e-10
+    eta = oracle.innerExpStepZINB(np.asfortranarray(y), np.asfortranarray(off), design, delta, psi, mz)
+    assert np.max(np.abs(eta - np.exp(ll) / np.exp(ll).sum(1, keepdims=True))) <= 1e-12
+    # objective / gradient over a long table
+    n = 300
+    idv = rng.integers(1, B + 3, n).astype(np.int32)
+    yy = rng.negative_binomial(2, 0.3, n).astype(float)
+    yy[rng.random(n) < 0.3] = 0
+    o, w = np.round(rng.normal(0, 0.1, n), 3), rng.random(n)
+    dsg = rng.integers(0, 2, (n, B)).astype(np.uint8)
+    par = np.array([-0.7, 0.6, 1.0, 2.2, 1.3])
+    v, g = oracle.glmMixZINB(par, idv, w, yy, o, dsg, B + 2, mz)
+    num = np.zeros(5)
+    for i in range(5):
+        a, b = par.copy(), par.copy()
+        a[i] += 1e-6
+        b[i] -= 1e-6
+        num[i] = (oracle.glmMixZINB(a, idv, w, yy, o, dsg, B + 2, mz, grad=False)[0] -
+                  oracle.glmMixZINB(b, idv, w, yy, o, dsg, B + 2, mz, grad=False)[0]) / 2e-6
+    assert np.max(np.abs(g - num)) <= 1e-5 * max(1.0, np.max(np.abs(num)))
