@@ -134,6 +134,37 @@ def differentialHMM(counts, offsets, peaks, condition, control, device=0, key=No
     return dict(session=s, theta=th, history=fit, mixturePatterns=patterns, design=design)
 
 
+def _components(fit):
+    """metadata(object)$components (R/base-core.R:145-151): per mixture component the 1-based conditions it
+    marks as enriched and its posterior proportion (the last delta)."""
+    enr = [[i + 1 for i, ch in enumerate(p) if ch == "E"] for p in fit["mixturePatterns"]]
+    return enr, np.asarray(fit["theta"]["delta"], dtype=np.float64)
+
+
+def prunePatterns(counts, offsets, peaks, condition, control, dist="nb", **kw):
+    """prunePatterns() (R/base-utils.R:398-447): fit the full differential model, then drop the rarest
+    combinatorial pattern and refit while any posterior proportion is below control$pruningThreshold.
+    Returns the last fit with `pruned` = the patterns removed, in order, and `fullBIC`."""
+    threshold = control["pruningThreshold"]
+    if threshold is None:
+        raise ValueError("control['pruningThreshold'] is NULL")
+    control = dict(control, pruningThreshold=None)
+    fit = differentialHMM(counts, offsets, peaks, condition, control, dist=dist, **kw)
+    full_bic = fit["history"]["controlHist"][-2]["bic"]
+    pruned = []
+    enr, post = _components(fit)
+    while np.any(post < threshold):
+        fit["session"].close()                       # unlink(metadata(fitFull)$output)
+        idx = int(np.argmin(post))                   # which.min: the first of the rarest
+        pruned.append(enr[idx])
+        control = dict(control, pattern=[e for i, e in enumerate(enr) if i != idx])
+        fit = differentialHMM(counts, offsets, peaks, condition, control, dist=dist, **kw)
+        enr, post = _components(fit)
+    fit["pruned"], fit["fullBIC"] = pruned, full_bic
+    fit["control"] = dict(control, pruningThreshold=threshold)
+    return fit
+
+
 def epigraHMM(counts, offsets, peaks, condition, control, type="consensus", dist="nb", **kw):
     """epigraHMM() (R/epigraHMM.R:39-90) on arrays."""
     if dist not in ("nb", "zinb"):
@@ -141,5 +172,7 @@ def epigraHMM(counts, offsets, peaks, condition, control, type="consensus", dist
     if type == "consensus":
         return consensusHMM(counts, offsets, peaks, condition, control, dist=dist, **kw)
     if type == "differential":
+        if control.get("pruningThreshold") is not None:   # R/epigraHMM.R:82-84
+            return prunePatterns(counts, offsets, peaks, condition, control, dist=dist, **kw)
         return differentialHMM(counts, offsets, peaks, condition, control, dist=dist, **kw)
     raise ValueError("type must be 'consensus' or 'differential'")

@@ -305,3 +305,39 @@ def test_full_flow_like_reference_callpeaks(ehmm):
             assert (truth & ~call).sum() / truth.sum() <= 0.05
     finally:
         s.close()
+
+
+def test_prune_patterns_removes_absent_combinations(ehmm):
+    """prunePatterns (R/base-utils.R:398-447; epigraHMM() routes to it when control$pruningThreshold is set,
+    R/epigraHMM.R:82-84): three conditions, but the differential windows only ever show 'A alone' or
+    'B and C together'.  Every other combinatorial pattern must be pruned, one refit per removal."""
+    from epigrahmm_b200 import core, rng, synth
+    M, n_cond, n_rep = 30011, 3, 2
+    gen = np.random.default_rng(5)
+    z = synth.markov_chain(M, synth.GAMMA3, gen)
+    pats = synth.enumerate_patterns(n_cond)                  # rows ordered as the reference's table
+    keep = [i for i, p in enumerate(pats.tolist()) if p in ([1, 0, 0], [0, 1, 1])]
+    assert len(keep) == 2
+    comp = np.asarray(keep)[gen.integers(0, 2, M)]
+    cond_of = np.repeat(np.arange(n_cond), n_rep)
+    enriched = np.where((z == 2)[:, None], 1, np.where((z == 1)[:, None], pats[comp][:, cond_of], 0))
+    mu, size = np.where(enriched == 1, 12.0, 2.0), np.where(enriched == 1, 4.0, 3.0)
+    offsets = np.asfortranarray(np.round(gen.normal(0.0, 0.1, (M, n_cond * n_rep)), 3))
+    counts = np.asfortranarray(gen.poisson(gen.gamma(shape=size, scale=mu / size * np.exp(offsets))).astype(np.int32))
+    condition = ["A", "A", "B", "B", "C", "C"]
+    rng.set_seed(210423)
+    peaks = (enriched == 1).astype(float)                    # initial peak calls (the initializer is tested elsewhere)
+    ctl = em.controlEM(maxIterEM=8, pruningThreshold=0.05)
+    fit = core.epigraHMM(counts, offsets, peaks, condition, ctl, type="differential", key="/tmp/prune.h5")
+    try:
+        assert sorted(fit["mixturePatterns"]) == ["BEE", "EBB"]
+        assert len(fit["pruned"]) == 4 and [1] not in fit["pruned"] and [2, 3] not in fit["pruned"]
+        assert np.all(fit["theta"]["delta"] >= 0.05) and abs(fit["theta"]["delta"].sum() - 1) < 1e-9
+        assert fit["design"].shape == (2, 6)
+        bic = fit["history"]["controlHist"][-2]["bic"]
+        assert np.isfinite(bic) and np.isfinite(fit["fullBIC"])
+        assert fit["control"]["pruningThreshold"] == 0.05 and len(fit["control"]["pattern"]) == 2
+        v = fit["session"].fetch("viterbi").ravel()
+        assert np.mean((v == 1) == (z == 1)) > 0.9
+    finally:
+        fit["session"].close()
