@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(EM_NT)
 // per-bin pieces of the differential model: LL0 = sum_i l0_i, LL2 = sum_i l1_i, d_i = l1_i - l0_i
 // (y == nullptr selects the dictionary-encoded source: `off` then points at the group table and
 // `tab` at the int32 group ids)
-template <int NMAX>
+template <int NMAX, bool GROUPED>
 __device__ __forceinline__ void diff_cells(int64_t j, int64_t M, int N, const int32_t *__restrict__ y,
                                            const double *__restrict__ off, const EmisParams &P,
                                            const double *__restrict__ tab, double &LL0, double &LL2, double *d) {
@@ -180,7 +180,7 @@ __device__ __forceinline__ void diff_cells(int64_t j, int64_t M, int N, const in
         if (i < N) {
             const int64_t c = j + (int64_t)i * M;
             double l0, l1;
-            if (y == nullptr) {
+            if (GROUPED) {
                 const double2 e = __ldg(reinterpret_cast<const double2 *>(off) +
                                         __ldg(reinterpret_cast<const int32_t *>(tab) + c));
                 l0 = e.x;
@@ -210,15 +210,16 @@ __device__ __forceinline__ double mix_ll(int b, double LL0, const double *d, con
     return X.ldelta[b] + (LL0 + s);
 }
 
-// loglikDifferentialHMM (NB), R/base-loglikelihood.R:45-71,96
-template <int NMAX>
+// loglikDifferentialHMM, R/base-loglikelihood.R:45-96.  GROUPED: the dictionary-encoded source (the
+// kernel then holds no density code at all, which keeps it small enough for the instruction cache)
+template <int NMAX, bool GROUPED>
 __global__ void __launch_bounds__(EM_NT)
     emis_diff_hmm_kernel(int64_t M, int N, const int32_t *__restrict__ y, const double *__restrict__ off,
                          const __grid_constant__ EmisParams P, const __grid_constant__ MixParams X,
                          const double *__restrict__ tab, double *__restrict__ LL) {
     for (int64_t j = (int64_t)blockIdx.x * EM_NT + threadIdx.x; j < M; j += (int64_t)gridDim.x * EM_NT) {
         double LL0, LL2, d[NMAX];
-        diff_cells<NMAX>(j, M, N, y, off, P, tab, LL0, LL2, d);
+        diff_cells<NMAX, GROUPED>(j, M, N, y, off, P, tab, LL0, LL2, d);
         double s = 0.0;
         for (int b = 0; b < X.B; b++) s += exp(mix_ll<NMAX>(b, LL0, d, X));  // not max-shifted, as in the reference
         double LL1 = log(s);
@@ -232,7 +233,7 @@ __global__ void __launch_bounds__(EM_NT)
 // Optional fusion of innerMaxStepProb's sums (src/innerMaxStepProb.cpp:33-35): with the posterior of
 // the differential state at hand, sum_j P1[j,1]*eta[j,b] and sum_j P1[j,1] need no extra pass
 // (part[blk*(B+1) + b], reduced by colsum_kernel).
-template <int NMAX, int BMAX>
+template <int NMAX, int BMAX, bool GROUPED>
 __global__ void __launch_bounds__(EM_NT)
     emis_inner_kernel(int64_t M, int N, const int32_t *__restrict__ y, const double *__restrict__ off,
                       const __grid_constant__ EmisParams P, const __grid_constant__ MixParams X,
@@ -243,7 +244,7 @@ __global__ void __launch_bounds__(EM_NT)
     for (int b = 0; b <= BMAX; b++) acc[b] = 0.0;
     for (int64_t j = (int64_t)blockIdx.x * EM_NT + threadIdx.x; j < M; j += (int64_t)gridDim.x * EM_NT) {
         double LL0, LL2, d[NMAX];
-        diff_cells<NMAX>(j, M, N, y, off, P, tab, LL0, LL2, d);
+        diff_cells<NMAX, GROUPED>(j, M, N, y, off, P, tab, LL0, LL2, d);
         double v[BMAX], s = 0.0;
 #pragma unroll
         for (int b = 0; b < BMAX; b++) {
@@ -491,12 +492,20 @@ int emis_differential_hmm(ehmm_session *s, const double *delta, const double *ps
     const int32_t *src_y = s->d_counts;
     const double *src_off = s->d_offsets, *src_tab = s->lgtab.as<double>();
     EHMM_TRY(diff_source(s, P, src_y, src_off, src_tab));
-    if (s->N <= 16)
-        PROF(s, KID_EMIS_DIFF), emis_diff_hmm_kernel<16><<<g, EM_NT, 0, s->stream>>>(s->M, s->N, src_y, src_off, P, X,
-                                                            src_tab, s->logf.as<double>());
-    else
-        PROF(s, KID_EMIS_DIFF), emis_diff_hmm_kernel<64><<<g, EM_NT, 0, s->stream>>>(s->M, s->N, src_y, src_off, P, X,
-                                                            src_tab, s->logf.as<double>());
+    const bool grouped = (src_y == nullptr);
+#define EHMM_DIFF(NM, GR)                                                                                             \
+    PROF(s, KID_EMIS_DIFF), emis_diff_hmm_kernel<NM, GR><<<g, EM_NT, 0, s->stream>>>(s->M, s->N, src_y, src_off, P, X, \
+                                                                                     src_tab, s->logf.as<double>())
+    if (grouped) {  // tight unroll bounds for the shapes of BASELINE configs 3-5 (N = 6 / 10 / 12)
+        if (s->N <= 6) EHMM_DIFF(6, true);
+        else if (s->N <= 12) EHMM_DIFF(12, true);
+        else if (s->N <= 16) EHMM_DIFF(16, true);
+        else EHMM_DIFF(64, true);
+    } else {
+        if (s->N <= 16) EHMM_DIFF(16, false);
+        else EHMM_DIFF(64, false);
+    }
+#undef EHMM_DIFF
     EHMM_CK(cudaGetLastError());
     s->valid |= DS_LOGF;
     return EHMM_OK;
@@ -519,20 +528,36 @@ int emis_inner_estep(ehmm_session *s, const double *delta, const double *psi, do
     const double *lp1c = fuse ? s->logProb1.as<double>() + s->M : nullptr;
     EHMM_TRY(s->inner_part.reserve(sizeof(double) * ((size_t)g * (s->B + 1) + s->B + 1)));
     double *part = s->inner_part.as<double>();
-#define EHMM_INNER(NM, BM)                                                                                          \
-    PROF(s, KID_EMIS_INNER), emis_inner_kernel<NM, BM><<<g, EM_NT, 0, s->stream>>>(s->M, s->N, src_y, src_off, P, X, \
-                                                                                   src_tab, s->eta.as<double>(), lp1c, part)
-    if (s->N <= 16) {
-        if (s->B <= 8) EHMM_INNER(16, 8);
-        else if (s->B <= 16) EHMM_INNER(16, 16);
-        else if (s->B <= 32) EHMM_INNER(16, 32);
-        else EHMM_INNER(16, 62);
+    const bool grouped = (src_y == nullptr);
+#define EHMM_INNER(NM, BM, GR)                                                                                        \
+    PROF(s, KID_EMIS_INNER), emis_inner_kernel<NM, BM, GR><<<g, EM_NT, 0, s->stream>>>(s->M, s->N, src_y, src_off, P, X, \
+                                                                                       src_tab, s->eta.as<double>(), lp1c, part)
+    // the loops over samples and components are unrolled to the template bounds: tight bounds for the
+    // dictionary-encoded source (B = 6 / 30 / 14 in BASELINE configs 3-5), wide ones for the per-cell fallback
+#define EHMM_INNER_B(NM)                               \
+    do {                                               \
+        if (s->B <= 6) EHMM_INNER(NM, 6, true);        \
+        else if (s->B <= 14) EHMM_INNER(NM, 14, true); \
+        else if (s->B <= 30) EHMM_INNER(NM, 30, true); \
+        else EHMM_INNER(NM, 62, true);                 \
+    } while (0)
+    if (grouped) {
+        if (s->N <= 6) EHMM_INNER_B(6);
+        else if (s->N <= 12) EHMM_INNER_B(12);
+        else if (s->N <= 16) EHMM_INNER_B(16);
+        else EHMM_INNER_B(64);
+    } else if (s->N <= 16) {
+        if (s->B <= 8) EHMM_INNER(16, 8, false);
+        else if (s->B <= 16) EHMM_INNER(16, 16, false);
+        else if (s->B <= 32) EHMM_INNER(16, 32, false);
+        else EHMM_INNER(16, 62, false);
     } else {
-        if (s->B <= 8) EHMM_INNER(64, 8);
-        else if (s->B <= 16) EHMM_INNER(64, 16);
-        else if (s->B <= 32) EHMM_INNER(64, 32);
-        else EHMM_INNER(64, 62);
+        if (s->B <= 8) EHMM_INNER(64, 8, false);
+        else if (s->B <= 16) EHMM_INNER(64, 16, false);
+        else if (s->B <= 32) EHMM_INNER(64, 32, false);
+        else EHMM_INNER(64, 62, false);
     }
+#undef EHMM_INNER_B
 #undef EHMM_INNER
     s->inner_part_blocks = fuse ? g : 0;
     EHMM_CK(cudaGetLastError());
