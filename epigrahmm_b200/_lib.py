@@ -54,6 +54,7 @@ PROTOTYPES = {
     "ehmm_groups_fetch": [_sess, _ip, _dp, _dp, _dp, _bp],
     "ehmm_set_data_encoded": [_sess, C.c_int, _ip, C.c_int64, _dp, _dp, _dp, _bp],
     "ehmm_set_data_encoded16": [_sess, C.c_int, C.POINTER(C.c_uint16), C.c_int64, _dp, _dp, _dp, _bp],
+    "ehmm_prefetch_groups": [_sess, C.c_int, C.c_void_p, C.c_int],
     "ehmm_set_design_n": [_sess, C.c_int, C.c_int, _bp],
     "ehmm_set_design": [_sess, C.c_int, _bp],
     "ehmm_loglik_consensus": [_sess, _dp, _dp, C.c_int, C.c_double],

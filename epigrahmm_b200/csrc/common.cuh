@@ -91,6 +91,15 @@ struct ehmm_session {
     int64_t Mtot = 0;   // bins in the global chain
     cudaStream_t stream = nullptr;
     cudaStream_t stream2 = nullptr;  // side stream (uniform generation)
+    // staged upload of the next table's Group column (ehmm_prefetch_groups): copy stream, two staging
+    // buffers used in turn, "copied" / "consumed" events per buffer
+    cudaStream_t stream_up = nullptr;
+    cudaEvent_t ev_up[2] = {nullptr, nullptr}, ev_used[2] = {nullptr, nullptr};
+    ehmm::DevBuf stage[2];
+    const void *staged_src[2] = {nullptr, nullptr};
+    size_t staged_bytes[2] = {0, 0};
+    bool stage_used_pending[2] = {false, false};
+    int stage_next = 0;
     cudaEvent_t ev = nullptr, ev2 = nullptr;
 
     // ---- data (dt) ----

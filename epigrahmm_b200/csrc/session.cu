@@ -203,6 +203,11 @@ int ehmm_session_open(const char *key, int64_t M, int K, int device, ehmm_sessio
     s->K = K;
     EHMM_CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     EHMM_CK(cudaStreamCreateWithFlags(&s->stream2, cudaStreamNonBlocking));
+    EHMM_CK(cudaStreamCreateWithFlags(&s->stream_up, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+        EHMM_CK(cudaEventCreateWithFlags(&s->ev_up[i], cudaEventDisableTiming));
+        EHMM_CK(cudaEventCreateWithFlags(&s->ev_used[i], cudaEventDisableTiming));
+    }
     EHMM_CK(cudaEventCreateWithFlags(&s->ev, cudaEventDisableTiming));
     EHMM_CK(cudaEventCreateWithFlags(&s->ev2, cudaEventDisableTiming));
     EHMM_CK(cudaMallocHost(&s->h_pinned, sizeof(double) * 1024));
@@ -235,6 +240,7 @@ int ehmm_session_close(ehmm_session *s) {
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     if (s->stream2) cudaStreamSynchronize(s->stream2);
+    if (s->stream_up) cudaStreamSynchronize(s->stream_up);
     {
         std::unique_lock<std::mutex> lk(g_mu, std::try_to_lock);
         auto it = g_sessions.find(s->key);
@@ -245,6 +251,12 @@ int ehmm_session_close(ehmm_session *s) {
                       &s->tileops, &s->carries, &s->tilestats, &s->fbscal, &s->rangeops, &s->rangecarry, &s->rc_w, &s->rc_flag, &s->rc_scan,
                       &s->rc_buckets, &s->rc_unif, &s->rc_tmp, &s->mt_raw, &s->mt_raw2, &s->mt_windows, &s->gtab, &s->glm_ticket, &s->inner_part, &s->lgtab, &s->glm_part, &s->misc};
     for (DevBuf *b : bufs) b->release();
+    for (int i = 0; i < 2; i++) {
+        s->stage[i].release();
+        if (s->ev_up[i]) cudaEventDestroy(s->ev_up[i]);
+        if (s->ev_used[i]) cudaEventDestroy(s->ev_used[i]);
+    }
+    if (s->stream_up) cudaStreamDestroy(s->stream_up);
     for (cudaEvent_t e : s->prof_pool) cudaEventDestroy(e);
     if (s->h_pinned) cudaFreeHost(s->h_pinned);
     if (s->ev) cudaEventDestroy(s->ev);
@@ -373,6 +385,35 @@ int ehmm_set_data_encoded16(ehmm_session *s, int N, const uint16_t *group, int64
     return set_encoded(s, N, nullptr, group, G, u_chip, u_offsets, u_controls, u_dsg);
 }
 
+// Start copying a Group column (M*N ids of bytes_per_id = 2 or 4 bytes, pinned host memory for a truly
+// asynchronous copy) into a staging buffer on the session's copy stream and return at once.  The next
+// ehmm_set_data_encoded[16] call that is given the same host pointer takes the staged copy instead of
+// copying again, so the upload of table k+1 overlaps the EM iteration on table k.
+int ehmm_prefetch_groups(ehmm_session *s, int N, const void *group, int bytes_per_id) {
+    EHMM_TRY(check_session(s));
+    EHMM_REQUIRE(group && N >= 1 && (bytes_per_id == 2 || bytes_per_id == 4), EHMM_ERR_ARG, "prefetch_groups: bad arguments");
+    const int b = s->stage_next;
+    const size_t bytes = (size_t)s->M * N * bytes_per_id;
+    EHMM_TRY(s->stage[b].reserve(bytes));
+    if (s->stage_used_pending[b]) {  // the previous tenant of this buffer may still be read on the main stream
+        EHMM_CK(cudaStreamWaitEvent(s->stream_up, s->ev_used[b], 0));
+        s->stage_used_pending[b] = false;
+    }
+    EHMM_CK(cudaMemcpyAsync(s->stage[b].p, group, bytes, cudaMemcpyHostToDevice, s->stream_up));
+    EHMM_CK(cudaEventRecord(s->ev_up[b], s->stream_up));
+    s->staged_src[b] = group;
+    s->staged_bytes[b] = bytes;
+    s->stage_next = b ^ 1;
+    return EHMM_OK;
+}
+
+// staged copy of `src` (bytes long), or -1
+static int staged_slot(ehmm_session *s, const void *src, size_t bytes) {
+    for (int b = 0; b < 2; b++)
+        if (s->staged_src[b] == src && s->staged_bytes[b] == bytes) return b;
+    return -1;
+}
+
 static int set_encoded(ehmm_session *s, int N, const int32_t *group, const uint16_t *group16, int64_t G,
                        const double *u_chip, const double *u_offsets, const double *u_controls, const uint8_t *u_dsg) {
     EHMM_TRY(check_session(s));
@@ -394,7 +435,20 @@ static int set_encoded(ehmm_session *s, int N, const int32_t *group, const uint1
     s->count_max = (int64_t)mx;
     const size_t n = (size_t)s->M * N;
     EHMM_TRY(s->group.reserve(n * sizeof(int32_t)));
-    if (group) {
+    const int slot = group ? staged_slot(s, group, n * sizeof(int32_t)) : staged_slot(s, group16, n * sizeof(uint16_t));
+    if (slot >= 0) {  // prefetched (ehmm_prefetch_groups): wait for the copy on the device, not on the host
+        EHMM_CK(cudaStreamWaitEvent(s->stream, s->ev_up[slot], 0));
+        if (group) {
+            EHMM_CK(cudaMemcpyAsync(s->group.p, s->stage[slot].p, n * sizeof(int32_t), cudaMemcpyDeviceToDevice, s->stream));
+        } else {
+            PROF(s, KID_MISC), widen_u16_kernel<<<148 * 8, 256, 0, s->stream>>>((int64_t)n, s->stage[slot].as<uint16_t>(),
+                                                                           s->group.as<int32_t>());
+            EHMM_CK(cudaGetLastError());
+        }
+        EHMM_CK(cudaEventRecord(s->ev_used[slot], s->stream));
+        s->stage_used_pending[slot] = true;
+        s->staged_src[slot] = nullptr;  // a staged copy is consumed once
+    } else if (group) {
         EHMM_CK(cudaMemcpyAsync(s->group.p, group, n * sizeof(int32_t), cudaMemcpyHostToDevice, s->stream));
     } else {
         EHMM_TRY(s->rc_tmp.reserve(n * sizeof(uint16_t)));

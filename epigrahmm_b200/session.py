@@ -126,6 +126,13 @@ class Session:
             check(lib.ehmm_set_data_encoded(self._h, N, iptr(g), uc.size, dptr(uc), dptr(uo), dptr(uctrl), bptr(udsg)))
         self.N, self.G = N, uc.size
 
+    def prefetch_groups(self, group):
+        """start the upload of the NEXT table's Group column (pinned memory) on the copy stream; the next
+        set_data_encoded(group, ...) with the same array takes the staged copy"""
+        group = np.asarray(group)
+        g = _cm(group, np.uint16 if group.dtype == np.uint16 else np.int32)
+        check(lib.ehmm_prefetch_groups(self._h, g.size // self.M, g.ctypes.data, g.itemsize))
+
     def set_design(self, design):
         d = np.ascontiguousarray(design, dtype=np.uint8)
         assert d.ndim == 2 and d.shape[1] == self.N, "design must be B x N"

@@ -261,3 +261,39 @@ def test_build_groups_on_device_matches_grp(ehmm, model):
             s.profile(True)
             s.loglik_consensus(psi, MINZERO)
             assert s.profile_read()["emis_gather"][0] == 1
+
+
+def test_prefetched_group_upload_equals_direct(ehmm):
+    """ehmm_prefetch_groups: the staged copy is what set_data_encoded[16] installs, for both id widths,
+    over several rounds (two staging buffers in turn), and an unrelated pointer falls back to a direct copy"""
+    import torch
+    M, N = 40013, 3
+    d = synth.make_consensus(M, N, seed=91)
+    g = synth.make_groups(d["counts"], d["offsets"])
+    th = synth.THETA_CONSENSUS
+    with ehmm.Session("t_pref", M, 2) as s:
+        s.set_data(d["counts"], d["offsets"])
+        s.set_groups(g["group"], g["u_chip"], g["u_offsets"])
+        s.loglik_consensus(th["psi"], MINZERO)
+        want = s.fetch("logLikelihood")
+        for dtype in (np.uint16, np.int32):
+            if dtype == np.uint16 and g["G"] >= 65536:
+                continue
+            bufs = []
+            for k in range(3):                       # three different tables: the same ids, permuted bins
+                perm = np.random.default_rng(k).permutation(M)
+                t = torch.empty(M * N, dtype=torch.uint16 if dtype == np.uint16 else torch.int32).pin_memory()
+                a = t.numpy()
+                a[:] = g["group"][perm].astype(dtype).ravel(order="F")
+                bufs.append((t, a, perm))
+            s.prefetch_groups(bufs[0][1])
+            for k, (t, a, perm) in enumerate(bufs):
+                s.set_data_encoded(a, g["u_chip"], g["u_offsets"])
+                if k + 1 < len(bufs):
+                    s.prefetch_groups(bufs[k + 1][1])
+                s.loglik_consensus(th["psi"], MINZERO)
+                assert np.array_equal(s.fetch("logLikelihood"), want[perm]), (dtype, k)
+            # not prefetched: direct copy
+            s.set_data_encoded(g["group"].astype(dtype), g["u_chip"], g["u_offsets"])
+            s.loglik_consensus(th["psi"], MINZERO)
+            assert np.array_equal(s.fetch("logLikelihood"), want)
