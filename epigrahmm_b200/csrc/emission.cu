@@ -43,14 +43,19 @@ __global__ void lgtab_kernel(EmisParams P, int nd, double *__restrict__ tab) {
     tab[i] = (lgamma((double)x + P.size[d]) - P.lgs[d]) - lgamma((double)x + 1.0);
 }
 
+// counts beyond the per-call table (rare): kept out of line, lgamma is long and would otherwise be
+// inlined at every unrolled use of nb_logpmf
+__device__ __noinline__ double lg_tail(double x, double size, double lgs) {
+    return (lgamma(x + size) - lgs) - lgamma(x + 1.0);
+}
+
 __device__ __forceinline__ double nb_logpmf(int x, double eta, int d, const EmisParams &P,
                                             const double *__restrict__ tab) {
     const double t = eta - P.lsize[d];
     const double w = log1p(exp(-fabs(t)));
     const double sp = (t > 0.0) ? t + w : w;   // softplus(t)  = log(1 + mu/size)
     const double spm = (t > 0.0) ? w : w - t;  // softplus(-t) = log(1 + size/mu)
-    const double c = (x < P.tabn) ? __ldg(tab + d * P.tabn + x)
-                                  : (lgamma((double)x + P.size[d]) - P.lgs[d]) - lgamma((double)x + 1.0);
+    const double c = (x < P.tabn) ? __ldg(tab + d * P.tabn + x) : lg_tail((double)x, P.size[d], P.lgs[d]);
     return (c - P.size[d] * sp) - (double)x * spm;
 }
 
@@ -546,15 +551,11 @@ int emis_inner_estep(ehmm_session *s, const double *delta, const double *psi, do
         else if (s->N <= 12) EHMM_INNER_B(12);
         else if (s->N <= 16) EHMM_INNER_B(16);
         else EHMM_INNER_B(64);
-    } else if (s->N <= 16) {
-        if (s->B <= 8) EHMM_INNER(16, 8, false);
-        else if (s->B <= 16) EHMM_INNER(16, 16, false);
-        else if (s->B <= 32) EHMM_INNER(16, 32, false);
+    } else if (s->N <= 16) {  // per-cell fallback (no dictionary): few, wide instantiations keep the build short
+        if (s->B <= 16) EHMM_INNER(16, 16, false);
         else EHMM_INNER(16, 62, false);
     } else {
-        if (s->B <= 8) EHMM_INNER(64, 8, false);
-        else if (s->B <= 16) EHMM_INNER(64, 16, false);
-        else if (s->B <= 32) EHMM_INNER(64, 32, false);
+        if (s->B <= 16) EHMM_INNER(64, 16, false);
         else EHMM_INNER(64, 62, false);
     }
 #undef EHMM_INNER_B
