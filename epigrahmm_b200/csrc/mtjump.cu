@@ -148,7 +148,8 @@ std::mutex g_mu;
 std::vector<uint16_t> g_idx;    // LEVELS * MAX_IDX coefficient positions
 int g_nidx[LEVELS] = {0};
 std::map<int, uint16_t *> g_dev_idx;
-constexpr size_t JUMP_SMEM = sizeof(uint32_t) * BUFW + sizeof(uint16_t) * MAX_IDX;
+// expanded words + this CTA's slice of the coefficient list (84.8 KB + 5.1 KB: two CTAs per SM)
+constexpr size_t JUMP_SMEM = sizeof(uint32_t) * BUFW + sizeof(uint16_t) * (MAX_IDX / JUMP_SPLIT + 16);
 
 int device_polys(int device, const uint16_t **out) {
     std::lock_guard<std::mutex> lk(g_mu);
