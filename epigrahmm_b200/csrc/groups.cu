@@ -146,7 +146,9 @@ int build_groups(ehmm_session *s, int64_t *G_out) {
         DevBuf *b[5];
         ~Guard() { for (auto p : b) p->release(); }
     } guard{{&tags, &first, &list, &rank, &misc2}};
-    EHMM_TRY(misc2.reserve(64));
+    // flags / counter in the first 64 bytes, the design matrix behind them: sized once, because a
+    // growing reserve() reallocates and would drop the verification flag written in between
+    EHMM_TRY(misc2.reserve(64 + (size_t)EHMM_MAX_B * 64));
     std::vector<unsigned long long> h;
     unsigned long long cap = 1ULL << 22, G = 0;
     for (int attempt = 0;; attempt++) {
@@ -206,7 +208,6 @@ int build_groups(ehmm_session *s, int64_t *G_out) {
     EHMM_CK(cudaGetLastError());
     if (s->have_design) {
         EHMM_TRY(s->u_dsg.reserve((size_t)(G + 1) * s->B));
-        EHMM_TRY(misc2.reserve(64 + (size_t)s->B * s->N));
         EHMM_CK(cudaMemcpyAsync(misc2.as<uint8_t>() + 64, s->design, (size_t)s->B * s->N, cudaMemcpyHostToDevice, s->stream));
         const int64_t tot = (int64_t)(G + 1) * s->B;
         PROF(s, KID_MISC), grp_dsg_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s->stream>>>(

@@ -128,21 +128,23 @@ class _Setulb:
     identical iterates, ~4x less host time).  request() runs the routine until it needs f and g at a
     point (returned) or has finished (None); feed() supplies them."""
 
-    def __init__(self, x0, lower, upper):
-        from scipy.optimize import _lbfgsb
-        self._lib = _lbfgsb
-        m, n = 5, len(x0)
+    _lib = None
+
+    @staticmethod
+    def bounds(lower, upper):
+        """(nbd, low, upp, lower, upper) in setulb's form; shared by instances with the same bounds"""
         lower, upper = np.asarray(lower, dtype=np.float64), np.asarray(upper, dtype=np.float64)
-        idt = _lbfgsb_int_dtype()
-        self.nbd = np.zeros(n, dtype=idt)
-        self.low, self.upp = np.zeros(n), np.zeros(n)
-        for i in range(n):
-            lo_f, hi_f = bool(np.isfinite(lower[i])), bool(np.isfinite(upper[i]))
-            if lo_f:
-                self.low[i] = lower[i]
-            if hi_f:
-                self.upp[i] = upper[i]
-            self.nbd[i] = {(False, False): 0, (True, False): 1, (True, True): 2, (False, True): 3}[(lo_f, hi_f)]
+        lo_f, hi_f = np.isfinite(lower), np.isfinite(upper)
+        nbd = np.where(lo_f & hi_f, 2, np.where(lo_f, 1, np.where(hi_f, 3, 0))).astype(_lbfgsb_int_dtype())
+        return nbd, np.where(lo_f, lower, 0.0), np.where(hi_f, upper, 0.0), lower, upper
+
+    def __init__(self, x0, lower=None, upper=None, bounds=None):
+        if _Setulb._lib is None:
+            from scipy.optimize import _lbfgsb
+            _Setulb._lib = _lbfgsb
+        m, n = 5, len(x0)
+        self.nbd, self.low, self.upp, lower, upper = bounds if bounds is not None else _Setulb.bounds(lower, upper)
+        idt = self.nbd.dtype
         self.x = np.clip(np.array(x0, dtype=np.float64), lower, upper)
         self.f = np.array(0.0, dtype=np.float64)
         self.g = np.zeros(n, dtype=np.float64)
@@ -154,20 +156,23 @@ class _Setulb:
         self.code = None
 
     def request(self):
+        """-> the point (a view of the internal x: copy it before the next call) or None when finished"""
+        setulb, task = self._lib.setulb, self.task
         while True:
-            self._lib.setulb(5, self.x, self.low, self.upp, self.nbd, self.f, self.g, 1e7, 0.0, self.wa, self.iwa,
-                             self.task, self.lsave, self.isave, self.dsave, 20, self.ln_task)
-            if self.task[0] == 3:
-                return self.x.copy()
-            if self.task[0] == 1:
+            setulb(5, self.x, self.low, self.upp, self.nbd, self.f, self.g, 1e7, 0.0, self.wa, self.iwa,
+                   task, self.lsave, self.isave, self.dsave, 20, self.ln_task)
+            t = task[0]
+            if t == 3:
+                return self.x
+            if t == 1:
                 self.nit += 1
                 if self.nit >= 100:
-                    self.task[0], self.task[1] = 5, 504
+                    task[0], task[1] = 5, 504
                 elif self.nfev > 15000:
-                    self.task[0], self.task[1] = 5, 502
+                    task[0], task[1] = 5, 502
                 continue
             break
-        if self.task[0] == 4:
+        if t == 4:
             self.code = 0
         elif self.nit >= 100 or self.nfev > 15000:
             self.code = 1
@@ -177,8 +182,8 @@ class _Setulb:
 
     def feed(self, fv, gv):
         self.nfev += 1
-        self.f = np.array(fv, dtype=np.float64)
-        self.g = np.asarray(gv, dtype=np.float64).copy()
+        self.f[...] = fv
+        self.g[:] = gv
 
 
 def _lbfgsb_setulb(fun, x0, lower, upper):
@@ -187,7 +192,7 @@ def _lbfgsb_setulb(fun, x0, lower, upper):
         x = st.request()
         if x is None:
             return st.x, st.code
-        st.feed(*fun(x))
+        st.feed(*fun(x.copy()))
 
 
 def _lbfgsb_int_dtype():
@@ -267,31 +272,39 @@ def optimNB_all(pars, backend, control, dist="nb"):
     upper = np.full(P + 1, np.inf)
     out = [None] * len(pars)
     states, req = {}, {}
+    bounds = _Setulb.bounds(lower, upper)
     for k, x0 in enumerate(starts):
         try:
-            states[k] = _Setulb(x0, lower, upper)
+            states[k] = _Setulb(x0, bounds=bounds)
             req[k] = states[k].request()
         except Exception:
             out[k] = dict(par=invertDispersion(x0), convergence=99)
+    X = np.empty((len(pars), P + 1))   # the batch of points of one round (request() returns views)
     while True:
-        ks = [k for k in states if out[k] is None and req[k] is not None]
-        for k in [k for k in states if out[k] is None and req[k] is None]:
-            out[k] = dict(par=invertDispersion(states[k].x), convergence=states[k].code)
+        ks = []
+        for k, st in states.items():
+            if out[k] is None:
+                if req[k] is None:
+                    out[k] = dict(par=invertDispersion(st.x), convergence=st.code)
+                else:
+                    X[len(ks)] = req[k]
+                    ks.append(k)
         if not ks:
             break
         try:
-            vals, grads = backend.glm_nb_batch(ks, np.stack([req[k] for k in ks]))
+            vals, grads = backend.glm_nb_batch(ks, X[:len(ks)])
         except Exception:
             for k in ks:
                 out[k] = dict(par=invertDispersion(starts[k]), convergence=99)
             continue
         for i, k in enumerate(ks):
-            if not np.isfinite(vals[i]):  # optim(): "L-BFGS-B needs finite values of 'fn'" -> tryCatch(error=)
+            if not math.isfinite(vals[i]):  # optim(): "L-BFGS-B needs finite values of 'fn'" -> tryCatch(error=)
                 out[k] = dict(par=invertDispersion(starts[k]), convergence=99)
                 continue
             try:
-                states[k].feed(vals[i], grads[i])
-                req[k] = states[k].request()
+                st = states[k]
+                st.feed(vals[i], grads[i])
+                req[k] = st.request()
             except Exception:
                 out[k] = dict(par=invertDispersion(starts[k]), convergence=99)
     return out

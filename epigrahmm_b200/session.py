@@ -31,6 +31,7 @@ class Session:
         self.N = 0
         self.B = 0
         self.G = 0
+        self._glm_cache = {}
 
     # -- lifetime --------------------------------------------------------------------------
     def close(self):
@@ -350,10 +351,17 @@ class Session:
         """value and gradient for several (column, par) pairs in one launch"""
         pars = np.ascontiguousarray(pars, dtype=np.float64)
         n, P1 = pars.shape
-        cols = np.ascontiguousarray(columns, dtype=np.int32)
-        v, g = np.empty(n), np.empty((n, P1))
-        check(lib.ehmm_glm_nb_batch(self._h, n, cols.ctypes.data_as(C.POINTER(C.c_int)), dptr(pars), P1 - 1, dptr(v), dptr(g)))
-        return v, g
+        key = (tuple(columns), P1)
+        c = self._glm_cache.get(key)
+        if c is None:   # the optimiser calls this in a tight loop: keep the small arrays and their pointers
+            cols = np.ascontiguousarray(columns, dtype=np.int32)
+            v, g = np.empty(n), np.empty((n, P1))
+            c = self._glm_cache[key] = (cols, v, g, cols.ctypes.data_as(C.POINTER(C.c_int)), dptr(v), dptr(g))
+        cols, v, g, pc, pv, pg = c
+        rc = lib.ehmm_glm_nb_batch(self._h, n, pc, dptr(pars), P1 - 1, pv, pg)
+        if rc:
+            check(rc)
+        return v.copy(), g.copy()
 
     def glm_mix_nb(self, par, minZero, grad=True):
         par = _f64(par)
