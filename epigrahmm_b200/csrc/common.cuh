@@ -139,6 +139,9 @@ struct ehmm_session {
     ehmm::DevBuf rc_w, rc_flag, rc_scan, rc_buckets, rc_unif, rc_tmp, mt_raw, mt_raw2, mt_windows;
     int64_t mtj_valid = 0;       // sub-stream windows valid for the state in mt_raw
     bool mtj_pending = false;    // ... being computed on stream2 (event ev)
+    bool mtj_base = false;       // window 0 is in place
+    int64_t mtj_iv[8][2] = {{0}};  // further valid runs of windows [lo, hi] (sharded fits prepare only their slice)
+    int mtj_niv = 0;
     bool rng_dev_valid = false;  // mt_raw holds rng_state
     bool rng_pending = false;    // the state after the last draw is on its way to h_pinned + 512 (rng_state[0] is already current)
     int rc_columns = 0;
@@ -239,7 +242,9 @@ int groups_fetch(ehmm_session *s, int32_t *group, double *u_chip, double *u_off,
 int mt_generate(ehmm_session *s, int64_t n, uint32_t *out);
 int mt_generate_range(ehmm_session *s, int64_t lo_rel, int64_t n, uint32_t *out);
 int mt_advance(ehmm_session *s, int64_t n);
+int mt_advance_side(ehmm_session *s, int64_t n, void *h_state);
 int mt_prefetch(ehmm_session *s, int64_t max_draws);
+int mt_prefetch_ranges(ehmm_session *s, int nr, const int64_t *lo, const int64_t *n, int64_t total, int margin);
 // glm.cu
 int glm_nb(ehmm_session *s, int column, const double *par, int P, double *value, double *grad);
 int glm_zinb(ehmm_session *s, int column, const double *par, int P, double minZero, double *value, double *grad);

@@ -49,18 +49,18 @@ __global__ void mt_base_kernel(const uint32_t *__restrict__ state, uint32_t *__r
         S[i] = (i < MT_N - 1) ? state[1 + i + 1] : (state[1 + MT_M] ^ twist(state[1], state[2]));
 }
 
-// S[(base + c)] ^= partial jump(S[c]) by the polynomial whose set coefficients are listed in `idx`
+// dst[c] ^= partial jump(src[c]) by the polynomial whose set coefficients are listed in `idx`
 // (nidx entries, padded to a multiple of 8 with ZERO_IDX, which addresses a zeroed region).  The
 // coefficient list is split over gridDim.y CTAs (a window is latency-bound in one CTA and the
 // doubling rounds are serial); the destination windows are zeroed beforehand and accumulate by XOR.
 __global__ void __launch_bounds__(JUMP_NT) mt_jump_kernel(const uint16_t *__restrict__ idx, int nidx,
-                                                          uint32_t *__restrict__ S, int base) {
+                                                          const uint32_t *__restrict__ srcw, uint32_t *__restrict__ dstw) {
     extern __shared__ uint32_t sm[];
     uint32_t *buf = sm;                                                   // EXPW words + zero pad
     uint16_t *sidx = reinterpret_cast<uint16_t *>(sm + BUFW);             // this CTA's slice of the list
     const int tid = threadIdx.x;
-    const uint32_t *src = S + (size_t)blockIdx.x * MT_N;
-    uint32_t *dst = S + (size_t)(base + blockIdx.x) * MT_N;
+    const uint32_t *src = srcw + (size_t)blockIdx.x * MT_N;  // window blockIdx.x of the source run
+    uint32_t *dst = dstw + (size_t)blockIdx.x * MT_N;        // ... jumps to window blockIdx.x of the destination run
     const int per = ((nidx / 8 + gridDim.y - 1) / gridDim.y) * 8;         // entries per slice (multiple of 8)
     const int q0 = min(nidx, (int)blockIdx.y * per), q1 = min(nidx, q0 + per);
     for (int i = tid; i < MT_N; i += JUMP_NT) buf[i] = src[i];
@@ -187,39 +187,130 @@ int64_t substreams_for(int64_t pos, int64_t n) {  // sub-streams touched by draw
 
 }  // namespace
 
+namespace {
+
+int launch_jump(ehmm_session *s, cudaStream_t st, const uint16_t *idx, int k, const uint32_t *src, uint32_t *dst, int64_t cnt) {
+    EHMM_CK(cudaMemsetAsync(dst, 0, sizeof(uint32_t) * MT_N * (size_t)cnt, st));
+    mt_jump_kernel<<<dim3((unsigned)cnt, JUMP_SPLIT), JUMP_NT, JUMP_SMEM, st>>>(idx + (size_t)k * MAX_IDX, g_nidx[k], src, dst);
+    EHMM_CK(cudaGetLastError());
+    s->launches[KID_MT]++;
+    return EHMM_OK;
+}
+
+// window buffer for sub-streams [0, P) plus two scratch windows; growing it invalidates what it held
+int reserve_windows(ehmm_session *s, int64_t P) {
+    const size_t need = sizeof(uint32_t) * MT_N * (size_t)(P + 2);
+    if (s->mt_windows.bytes < need) {
+        if (s->mtj_pending) {  // kernels on the side stream may still write the old buffer
+            EHMM_CK(cudaStreamSynchronize(s->stream2));
+            s->mtj_pending = false;
+        }
+        EHMM_TRY(s->mt_windows.reserve(need + need / 2));
+        s->mtj_valid = 0;
+        s->mtj_niv = 0;
+        s->mtj_base = false;
+    }
+    return EHMM_OK;
+}
+
+int base_window(ehmm_session *s, cudaStream_t st) {
+    if (s->mtj_base) return EHMM_OK;
+    mt_base_kernel<<<1, 256, 0, st>>>(s->mt_raw.as<uint32_t>(), s->mt_windows.as<uint32_t>());
+    EHMM_CK(cudaGetLastError());
+    s->launches[KID_MT]++;
+    s->mtj_base = true;
+    return EHMM_OK;
+}
+
+bool windows_cover(const ehmm_session *s, int64_t lo, int64_t hi) {
+    if (lo > hi) return true;
+    if (hi < s->mtj_valid) return true;
+    for (int i = 0; i < s->mtj_niv; i++)
+        if (s->mtj_iv[i][0] <= lo && hi <= s->mtj_iv[i][1]) return true;
+    return false;
+}
+
+}  // namespace
+
 // Prepare the windows of sub-streams 1..P-1 for the stream whose state is in s->mt_raw (device).
 int mt_prepare(ehmm_session *s, cudaStream_t st, int64_t max_draws) {
     const int64_t P = substreams_for(624, max_draws);
-    if (P <= 1) { s->mtj_valid = 1; return EHMM_OK; }
+    if (P <= 1) { if (s->mtj_valid < 1) s->mtj_valid = 1; return EHMM_OK; }
     EHMM_REQUIRE(P <= ((int64_t)1 << LEVELS), EHMM_ERR_RNG, "too many uniforms in one call (%lld)", (long long)max_draws);
     const uint16_t *idx = nullptr;
     EHMM_TRY(device_polys(s->device, &idx));
-    EHMM_TRY(s->mt_windows.reserve(sizeof(uint32_t) * MT_N * (size_t)P));
+    EHMM_TRY(reserve_windows(s, P));
     uint32_t *S = s->mt_windows.as<uint32_t>();
-    mt_base_kernel<<<1, 256, 0, st>>>(s->mt_raw.as<uint32_t>(), S);
-    EHMM_CK(cudaGetLastError());
-    s->launches[KID_MT]++;
+    EHMM_TRY(base_window(s, st));
     for (int k = 0; ((int64_t)1 << k) < P; k++) {
         const int64_t base = (int64_t)1 << k;
         const int64_t cnt = (P - base < base) ? (P - base) : base;
-        EHMM_CK(cudaMemsetAsync(S + (size_t)base * MT_N, 0, sizeof(uint32_t) * MT_N * (size_t)cnt, st));
-        mt_jump_kernel<<<dim3((unsigned)cnt, JUMP_SPLIT), JUMP_NT, JUMP_SMEM, st>>>(idx + (size_t)k * MAX_IDX, g_nidx[k], S,
-                                                                                  (int)base);
-        EHMM_CK(cudaGetLastError());
-        s->launches[KID_MT]++;
+        EHMM_TRY(launch_jump(s, st, idx, k, S, S + (size_t)base * MT_N, cnt));
     }
     s->mtj_valid = P;
     return EHMM_OK;
 }
 
+// Windows of sub-streams [q_lo, q_hi] only (a bin block's slice of the stream in a sharded fit starts
+// far into it): window q_lo from window 0 by one jump per set bit of q_lo, then doubling inside the
+// range -- popcount(q_lo) + log2(length) launches and q_hi - q_lo + popcount(q_lo) window jumps instead
+// of q_hi.
+int mt_prepare_range(ehmm_session *s, cudaStream_t st, int64_t q_lo, int64_t q_hi) {
+    if (q_lo < 0) q_lo = 0;
+    if (q_hi < q_lo || windows_cover(s, q_lo, q_hi)) return EHMM_OK;
+    EHMM_REQUIRE(q_hi < ((int64_t)1 << LEVELS), EHMM_ERR_RNG, "draw position beyond 2^%d sub-streams", LEVELS);
+    const uint16_t *idx = nullptr;
+    EHMM_TRY(device_polys(s->device, &idx));
+    EHMM_TRY(reserve_windows(s, q_hi + 1));
+    uint32_t *S = s->mt_windows.as<uint32_t>();
+    const int64_t cap = (int64_t)(s->mt_windows.bytes / (sizeof(uint32_t) * MT_N));
+    uint32_t *scratch[2] = {S + (size_t)(cap - 2) * MT_N, S + (size_t)(cap - 1) * MT_N};
+    EHMM_TRY(base_window(s, st));
+    if (q_lo > 0) {
+        const uint32_t *cur = S;
+        int bits = 0, done = 0;
+        for (int k = 0; k < LEVELS; k++) bits += (q_lo >> k) & 1;
+        for (int k = 0; k < LEVELS; k++) {
+            if (!((q_lo >> k) & 1)) continue;
+            uint32_t *dst = (++done == bits) ? S + (size_t)q_lo * MT_N : scratch[done & 1];
+            EHMM_TRY(launch_jump(s, st, idx, k, cur, dst, 1));
+            cur = dst;
+        }
+    }
+    const int64_t len = q_hi - q_lo + 1;
+    uint32_t *R = S + (size_t)q_lo * MT_N;
+    for (int k = 0; ((int64_t)1 << k) < len; k++) {
+        const int64_t base = (int64_t)1 << k;
+        const int64_t cnt = (len - base < base) ? (len - base) : base;
+        EHMM_TRY(launch_jump(s, st, idx, k, R, R + (size_t)base * MT_N, cnt));
+    }
+    if (s->mtj_niv < 8) {
+        s->mtj_iv[s->mtj_niv][0] = q_lo;
+        s->mtj_iv[s->mtj_niv][1] = q_hi;
+        s->mtj_niv++;
+    }
+    return EHMM_OK;
+}
+
 static int64_t substream_of(int64_t a) { return a <= 0 ? 0 : (a - 1) / JW; }
 
-static int ensure_windows(ehmm_session *s, int64_t P) {
+static int wait_pending(ehmm_session *s) {
     if (s->mtj_pending) {  // windows being prepared on the side stream
         EHMM_CK(cudaStreamWaitEvent(s->stream, s->ev, 0));
         s->mtj_pending = false;
     }
+    return EHMM_OK;
+}
+
+static int ensure_windows(ehmm_session *s, int64_t P) {
+    EHMM_TRY(wait_pending(s));
     if (P > 1 && s->mtj_valid < P) EHMM_TRY(mt_prepare(s, s->stream, (P - 1) * JW + 2));
+    return EHMM_OK;
+}
+
+static int ensure_range(ehmm_session *s, int64_t q_lo, int64_t q_hi) {
+    EHMM_TRY(wait_pending(s));
+    if (q_hi >= 1 && !windows_cover(s, q_lo, q_hi)) EHMM_TRY(mt_prepare_range(s, s->stream, q_lo, q_hi));
     return EHMM_OK;
 }
 
@@ -237,6 +328,8 @@ int mt_generate(ehmm_session *s, int64_t n, uint32_t *out) {
     EHMM_CK(cudaGetLastError());
     std::swap(s->mt_raw, s->mt_raw2);
     s->mtj_valid = 0;
+    s->mtj_niv = 0;
+    s->mtj_base = false;
     return EHMM_OK;
 }
 
@@ -245,7 +338,7 @@ int mt_generate_range(ehmm_session *s, int64_t lo_rel, int64_t n, uint32_t *out)
     if (n <= 0) return EHMM_OK;
     const int64_t pos = s->rng_state[0];
     const int64_t s0 = substream_of(pos + lo_rel), s1 = substream_of(pos + lo_rel + n - 1);
-    EHMM_TRY(ensure_windows(s, s1 + 1));
+    EHMM_TRY(ensure_range(s, s0, s1));
     PROF(s, KID_MT), mt_generate_kernel<<<(unsigned)(s1 - s0 + 1), GEN_NT, 0, s->stream>>>(
         s->mt_raw.as<uint32_t>(), s->mt_windows.as<uint32_t>(), (int)s0, lo_rel, lo_rel + n, out, -1, nullptr);
     EHMM_CK(cudaGetLastError());
@@ -259,12 +352,39 @@ int mt_advance(ehmm_session *s, int64_t n) {
     const int64_t E = pos + n, st_lo = ((E - 1) / 624) * 624;
     const int64_t s0 = substream_of(st_lo), s1 = substream_of(E - 1);
     EHMM_TRY(s->mt_raw2.reserve(sizeof(uint32_t) * 625));
-    EHMM_TRY(ensure_windows(s, s1 + 1));
+    EHMM_TRY(ensure_range(s, s0, s1));
     PROF(s, KID_MT), mt_generate_kernel<<<(unsigned)(s1 - s0 + 1), GEN_NT, 0, s->stream>>>(
         s->mt_raw.as<uint32_t>(), s->mt_windows.as<uint32_t>(), (int)s0, 0, 0, nullptr, n, s->mt_raw2.as<uint32_t>());
     EHMM_CK(cudaGetLastError());
     std::swap(s->mt_raw, s->mt_raw2);
     s->mtj_valid = 0;
+    s->mtj_niv = 0;
+    s->mtj_base = false;
+    return EHMM_OK;
+}
+
+// mt_advance on the side stream, followed by the copy of the new state to the pinned host buffer: the
+// single CTA that walks to the end of the last sub-stream (~0.1 ms) then overlaps the table kernels.
+// The main stream meets the side stream again at the next wait_pending (mt_prefetch_ranges records it).
+int mt_advance_side(ehmm_session *s, int64_t n, void *h_state) {
+    if (n <= 0) return EHMM_OK;
+    const int64_t pos = s->rng_state[0];
+    const int64_t E = pos + n, st_lo = ((E - 1) / 624) * 624;
+    const int64_t s0 = substream_of(st_lo), s1 = substream_of(E - 1);
+    EHMM_TRY(s->mt_raw2.reserve(sizeof(uint32_t) * 625));
+    EHMM_TRY(wait_pending(s));
+    EHMM_CK(cudaEventRecord(s->ev2, s->stream));
+    EHMM_CK(cudaStreamWaitEvent(s->stream2, s->ev2, 0));
+    if (s1 >= 1) EHMM_TRY(mt_prepare_range(s, s->stream2, s0, s1));
+    mt_generate_kernel<<<(unsigned)(s1 - s0 + 1), GEN_NT, 0, s->stream2>>>(
+        s->mt_raw.as<uint32_t>(), s->mt_windows.as<uint32_t>(), (int)s0, 0, 0, nullptr, n, s->mt_raw2.as<uint32_t>());
+    EHMM_CK(cudaGetLastError());
+    s->launches[KID_MT]++;
+    std::swap(s->mt_raw, s->mt_raw2);
+    s->mtj_valid = 0;
+    s->mtj_niv = 0;
+    s->mtj_base = false;
+    EHMM_CK(cudaMemcpyAsync(h_state, s->mt_raw.p, sizeof(uint32_t) * 625, cudaMemcpyDeviceToHost, s->stream2));
     return EHMM_OK;
 }
 
@@ -274,6 +394,26 @@ int mt_prefetch(ehmm_session *s, int64_t max_draws) {
     EHMM_CK(cudaEventRecord(s->ev2, s->stream));
     EHMM_CK(cudaStreamWaitEvent(s->stream2, s->ev2, 0));
     EHMM_TRY(mt_prepare(s, s->stream2, max_draws));
+    EHMM_CK(cudaEventRecord(s->ev, s->stream2));
+    s->mtj_pending = true;
+    return EHMM_OK;
+}
+
+// Sharded form: prepare only the windows the next call is expected to touch -- relative draw ranges
+// [lo[i], lo[i] + n[i]) with `margin` sub-streams either side, and the words around position `total`
+// (the state after the call) -- on the side stream.
+int mt_prefetch_ranges(ehmm_session *s, int nr, const int64_t *lo, const int64_t *n, int64_t total, int margin) {
+    EHMM_CK(cudaEventRecord(s->ev2, s->stream));
+    EHMM_CK(cudaStreamWaitEvent(s->stream2, s->ev2, 0));
+    const int64_t pos = s->rng_state[0];
+    for (int i = 0; i < nr; i++) {
+        if (n[i] <= 0) continue;
+        EHMM_TRY(mt_prepare_range(s, s->stream2, substream_of(pos + lo[i]) - margin, substream_of(pos + lo[i] + n[i] - 1) + margin));
+    }
+    if (total > 0) {
+        const int64_t E = pos + total, st_lo = ((E - 1) / MT_N) * MT_N;
+        EHMM_TRY(mt_prepare_range(s, s->stream2, substream_of(st_lo) - margin, substream_of(E - 1) + margin));
+    }
     EHMM_CK(cudaEventRecord(s->ev, s->stream2));
     s->mtj_pending = true;
     return EHMM_OK;

@@ -317,6 +317,8 @@ int run_rc(ehmm_session *s, const RCSrc &S, double p, int nrep, const double *un
                 EHMM_CK(cudaMemcpyAsync(s->mt_raw.p, s->h_pinned + 512, sizeof(uint32_t) * 625, cudaMemcpyHostToDevice, s->stream));
                 s->rng_dev_valid = true;
                 s->mtj_valid = 0;
+                s->mtj_niv = 0;
+                s->mtj_base = false;
             }
             EHMM_TRY(mt_generate(s, total, s->rc_unif.as<uint32_t>()));
             EHMM_CK(cudaMemcpyAsync(s->h_pinned + 512, s->mt_raw.p, sizeof(uint32_t) * 625, cudaMemcpyDeviceToHost, s->stream));
@@ -391,6 +393,8 @@ int rc_apply_block(ehmm_session *s, const RCSrc &S, double p, int nrep, const in
             EHMM_CK(cudaMemcpyAsync(s->mt_raw.p, s->h_pinned + 512, sizeof(uint32_t) * 625, cudaMemcpyHostToDevice, s->stream));
             s->rng_dev_valid = true;
             s->mtj_valid = 0;
+            s->mtj_niv = 0;
+            s->mtj_base = false;
         }
         int64_t at = 0;
         for (int c = 0; c < S.columns; c++) {
@@ -400,9 +404,6 @@ int rc_apply_block(ehmm_session *s, const RCSrc &S, double p, int nrep, const in
             EHMM_TRY(mt_generate_range(s, col_offsets[c], s->rc_colcount[c], s->rc_unif.as<uint32_t>() + at));
             at += s->rc_colcount[c];
         }
-        EHMM_TRY(mt_advance(s, total));
-        EHMM_CK(cudaMemcpyAsync(s->h_pinned + 512, s->mt_raw.p, sizeof(uint32_t) * 625, cudaMemcpyDeviceToHost, s->stream));
-        rng_note_advance(s, total);
         state_back = true;
     }
     dim3 grid((unsigned)nblk, (unsigned)S.columns);
@@ -410,7 +411,13 @@ int rc_apply_block(ehmm_session *s, const RCSrc &S, double p, int nrep, const in
         S, p, nblk, s->rc_scan.as<int64_t>(), s->rc_unif.as<uint32_t>(), s->group.as<int32_t>(), nrep, s->G,
         s->rc_buckets.as<double>(), nullptr);
     EHMM_CK(cudaGetLastError());
-    if (total > 0) EHMM_TRY(mt_prefetch(s, total + 624));
+    if (total > 0) {
+        // side stream: the stream's state after all ranks' draws, then the windows of the next call's
+        // slice, which sits where this one's did, give or take a few thousand draws
+        EHMM_TRY(mt_advance_side(s, total, s->h_pinned + 512));
+        rng_note_advance(s, total);
+        EHMM_TRY(mt_prefetch_ranges(s, S.columns, col_offsets, s->rc_colcount, total, 2));
+    }
     (void)state_back;
     s->rc_columns = S.columns;
     s->rc_N = nrep;
@@ -429,6 +436,7 @@ void rng_note_advance(ehmm_session *s, int64_t n) {
 int rng_sync_host(ehmm_session *s) {
     if (!s->rng_pending) return EHMM_OK;
     EHMM_CK(cudaStreamSynchronize(s->stream));
+    EHMM_CK(cudaStreamSynchronize(s->stream2));  // the sharded form copies the state on the side stream
     const uint32_t *h = reinterpret_cast<const uint32_t *>(s->h_pinned + 512);
     EHMM_REQUIRE(h[0] == s->rng_state[0], EHMM_ERR_RNG, "RNG position on the device (%u) differs from the booked one (%u)", h[0],
                  s->rng_state[0]);
