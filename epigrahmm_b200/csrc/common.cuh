@@ -136,7 +136,7 @@ struct ehmm_session {
     // ---- rejection control ----
     uint32_t rng_state[625] = {624};
     bool rng_set = false;
-    ehmm::DevBuf rc_w, rc_flag, rc_scan, rc_buckets, rc_unif, rc_tmp, mt_raw, mt_raw2, mt_windows;
+    ehmm::DevBuf rc_flag, rc_scan, rc_buckets, rc_unif, rc_tmp, mt_raw, mt_raw2, mt_windows;
     int64_t mtj_valid = 0;       // sub-stream windows valid for the state in mt_raw
     bool mtj_pending = false;    // ... being computed on stream2 (event ev)
     bool mtj_base = false;       // window 0 is in place

@@ -24,13 +24,9 @@ namespace {
 
 // 64-bit literals that are not encodable as instruction immediates are materialised with two moves
 // per use; kept in constant memory they are operands (or loaded once per thread).
-__constant__ double kC[14] = {
-    6.666666666666735130e-01, 3.999999999940941908e-01, 2.857142874366239149e-01, 2.222219843214978396e-01,
-    1.818357216161805012e-01, 1.531383769920937332e-01, 1.479819860511658591e-01,  // fdlibm Lg1..Lg7
-    6.93147180369123816490e-01, 1.90821492927058770002e-10,                          // ln2_hi, ln2_lo
-    0.693147180559945309417232121458,                                                // ln 2
-    1.0 / 3.0, 1.0 / 5.0, -1.0 / 6.0, 1.0 / 7.0};                                    // log1p series (log_norm)
-#define LN2 (kC[9])
+__constant__ double kC[5] = {0.693147180559945309417232121458,             // ln 2
+                             1.0 / 3.0, 1.0 / 5.0, -1.0 / 6.0, 1.0 / 7.0};  // log1p series (log_norm)
+#define LN2 (kC[0])
 
 template <int K> struct Op {
     double m[K * K];  // row-major mantissa, m[i*K+l]
@@ -92,10 +88,10 @@ __device__ __forceinline__ double log_norm(double x, const double2 *sT) {
     const double2 t = sT[(h2 >> 13) & 127];
     const double m = __hiloint2double((h2 & 0x000fffff) + 0x3fe6a09e, __double2loint(x));
     const double r = fma(m, t.x, -1.0);
-    double q = fma(r, kC[13], kC[12]);
-    q = fma(r, q, kC[11]);
+    double q = fma(r, kC[4], kC[3]);
+    q = fma(r, q, kC[2]);
     q = fma(r, q, -0.25);
-    q = fma(r, q, kC[10]);
+    q = fma(r, q, kC[1]);
     q = fma(r, q, -0.5);
     return fma((double)e, LN2, t.y) + fma(r * r, q, r);
 }
