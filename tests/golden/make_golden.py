@@ -3,6 +3,8 @@
   helas3_counts.npz   the 9 994 x 6 count matrix of the reference's bundled data/helas3.rda
                       (xz-compressed RDX3; read here without R by locating the INTSXP payload).
                       Needs /root/reference; column sums are checked against SURVEY.md section 8c.
+  golden_zinb.npz     the same for dist = 'zinb' (consensus and differential emission, mixture posteriors,
+                      glmZINB / glmMixZINB value and gradient).
   golden_small.npz    seeded small inputs (epigrahmm_b200.synth) and the CPU oracle's outputs for
                       every function on the hot path.  The reference holds no numeric golden vectors
                       and cannot be executed in this image (no R), so these pin the ORACLE: the CPU
@@ -82,8 +84,50 @@ def small():
     np.savez_compressed(os.path.join(HERE, "golden_small.npz"), **out)
 
 
+PSI_ZC = [np.array([-0.8, 0.7, 3.0]), np.array([2.4, 4.0])]                       # consensus: (lambda, beta, size), (beta, size)
+PSI_ZD = np.array([-1.0, np.log(2.0), np.log(3.0), np.log(6.0), np.log(4.0 / 3.0)])    # differential: (lambda, b, l, db, dl)
+PAR_GLM = np.array([0.6, 0.4, -0.7])                                                # glmZINB: (beta, phi, lambda)
+PAR_MIX = np.array([-1.0, 0.7, 1.1, 2.5, 1.4])                                      # glmMixZINB: (lambda, b_bg, l_bg, b_enr, l_enr)
+
+
+def zinb():
+    from oracle import oracle as O
+    from epigrahmm_b200 import synth
+    out = {}
+    d = synth.make_consensus(1200, 3, seed=20261011)
+    rng = np.random.default_rng(20261012)
+    counts = d["counts"].copy()
+    counts[(rng.random(counts.shape) < 0.25) & (d["z"][:, None] == 0)] = 0
+    counts = np.asfortranarray(counts)
+    g = synth.make_groups(counts, d["offsets"])
+    logf = O.loglikConsensusHMMzinb(counts, d["offsets"], PSI_ZC, MINZERO)
+    w = rng.random(g["G"])
+    v, gr = O.glmZINB(PAR_GLM, g["u_chip"], np.ones((g["G"], 1)), g["u_offsets"], w, MINZERO)
+    out.update(c_counts=counts, c_offsets=d["offsets"], c_logf=logf, c_u_chip=g["u_chip"], c_u_offsets=g["u_offsets"],
+               c_w=w, c_glm_v=v, c_glm_g=gr)
+    d = synth.make_differential(600, 3, 2, seed=20261013)
+    counts = d["counts"].copy()
+    counts[(rng.random(counts.shape) < 0.25) & (d["z"][:, None] == 0)] = 0
+    counts = np.asfortranarray(counts)
+    delta = np.linspace(1.0, 2.0, d["B"])
+    delta /= delta.sum()
+    LL = O.loglikDifferentialHMMzinb(counts, d["offsets"], d["design"], delta, PSI_ZD, MINZERO)
+    eta = O.innerExpStepZINB(counts, d["offsets"], d["design"], delta, PSI_ZD, MINZERO)
+    n = 500
+    idv = rng.integers(1, d["B"] + 3, n).astype(np.int32)
+    yy = rng.negative_binomial(2, 0.3, n).astype(float)
+    yy[rng.random(n) < 0.3] = 0
+    off, ww = np.round(rng.normal(0, 0.1, n), 3), rng.random(n)
+    dsg = rng.integers(0, 2, (n, d["B"])).astype(np.uint8)
+    mv, mg = O.glmMixZINB(PAR_MIX, idv, ww, yy, off, dsg, d["B"] + 2, MINZERO)
+    out.update(d_counts=counts, d_offsets=d["offsets"], d_design=d["design"], d_delta=delta, d_logf=LL, d_eta=eta,
+               m_id=idv, m_y=yy, m_off=off, m_w=ww, m_dsg=dsg, m_v=mv, m_g=mg)
+    np.savez_compressed(os.path.join(HERE, "golden_zinb.npz"), **out)
+
+
 if __name__ == "__main__":
     helas3()
     small()
+    zinb()
     for f in sorted(os.listdir(HERE)):
         print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -203,3 +203,44 @@ def test_em_trajectory_differential_zinb(ehmm, oracle):
         assert fg["theta_new"]["psi"][0].size == 3 and fg["theta_new"]["psi"][1].size == 2
         zi = 1.0 / (1.0 + np.exp(-fg["theta_new"]["psi"][0][0]))
         assert 0.1 < zi < 0.5, zi
+
+
+def test_cuda_path_against_committed_zinb_golden(ehmm):
+    """tests/golden/golden_zinb.npz: the CUDA path against the committed oracle outputs (no oracle call here)"""
+    import os
+    import sys
+    gold = os.path.join(os.path.dirname(__file__), "golden")
+    sys.path.insert(0, gold)
+    import make_golden as mg
+    g = np.load(os.path.join(gold, "golden_zinb.npz"))
+    M, N = g["c_counts"].shape
+    with ehmm.Session("gz-c", M, 2) as s:
+        s.set_data(g["c_counts"], g["c_offsets"])
+        s.loglik_consensus_zinb(mg.PSI_ZC, MINZERO)
+        assert _rel(s.fetch("logLikelihood"), g["c_logf"]) <= 1e-12
+        # glmZINB over the golden table: one group per row, weights as the "rejection table" of column 0
+        G = g["c_u_chip"].size
+        grp = np.ones((M, N), dtype=np.int32, order="F")
+        s.set_groups(grp, g["c_u_chip"], g["c_u_offsets"])
+        s.store("logProb1", np.log(np.full((M, 2), 0.5)))
+        s.rc_consensus(0.0)                                  # allocates the tables (p = 0: no thinning)
+        ptr, n = s.rc_buckets_device()
+        import torch
+        class _B:
+            __cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 3}
+        t = torch.as_tensor(_B(), device="cuda")
+        t.zero_()
+        t[1:G + 1] = torch.as_tensor(g["c_w"], device="cuda")
+        torch.cuda.synchronize()
+        v, gr = s.glm_zinb(0, mg.PAR_GLM, MINZERO)
+        assert abs(v - float(g["c_glm_v"])) <= 1e-11 * abs(float(g["c_glm_v"]))
+        assert np.max(np.abs(gr - g["c_glm_g"])) <= 1e-9 * max(1.0, np.max(np.abs(g["c_glm_g"])))
+    M, N = g["d_counts"].shape
+    with ehmm.Session("gz-d", M, 3) as s:
+        s.set_data(g["d_counts"], g["d_offsets"])
+        s.set_design(g["d_design"])
+        s.build_groups()
+        s.loglik_differential_hmm_zinb(g["d_delta"], mg.PSI_ZD, MINZERO)
+        assert _rel(s.fetch("logLikelihood"), g["d_logf"]) <= 1e-10
+        s.inner_expstep_zinb(g["d_delta"], mg.PSI_ZD, MINZERO)
+        assert np.max(np.abs(s.fetch("mixtureProb") - g["d_eta"])) <= 1e-9

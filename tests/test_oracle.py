@@ -2,6 +2,7 @@
 implementations of the third-party arithmetic, a numpy twin of the native recursions, and the
 committed golden vectors."""
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -283,3 +284,20 @@ def test_differential_zinb_oracle_against_twin_and_differences(oracle):
         num[i] = (oracle.glmMixZINB(a, idv, w, yy, o, dsg, B + 2, mz, grad=False)[0] -
                   oracle.glmMixZINB(b, idv, w, yy, o, dsg, B + 2, mz, grad=False)[0]) / 2e-6
     assert np.max(np.abs(g - num)) <= 1e-5 * max(1.0, np.max(np.abs(num)))
+
+
+def test_oracle_reproduces_zinb_golden(oracle):
+    """tests/golden/golden_zinb.npz (make_golden.py::zinb) pins the oracle's dist = 'zinb' functions"""
+    sys.path.insert(0, GOLD)
+    import make_golden as mg
+    g = np.load(os.path.join(GOLD, "golden_zinb.npz"))
+    assert np.array_equal(oracle.loglikConsensusHMMzinb(g["c_counts"], g["c_offsets"], mg.PSI_ZC, MINZERO), g["c_logf"])
+    v, gr = oracle.glmZINB(mg.PAR_GLM, g["c_u_chip"], np.ones((g["c_u_chip"].size, 1)), g["c_u_offsets"], g["c_w"], MINZERO)
+    assert v == float(g["c_glm_v"]) and np.array_equal(gr, g["c_glm_g"])
+    LL = oracle.loglikDifferentialHMMzinb(g["d_counts"], g["d_offsets"], g["d_design"], g["d_delta"], mg.PSI_ZD, MINZERO)
+    assert np.array_equal(LL, g["d_logf"])
+    eta = oracle.innerExpStepZINB(g["d_counts"], g["d_offsets"], g["d_design"], g["d_delta"], mg.PSI_ZD, MINZERO)
+    assert np.array_equal(eta, g["d_eta"])
+    B = g["d_design"].shape[0]
+    mv, mgr = oracle.glmMixZINB(mg.PAR_MIX, g["m_id"], g["m_w"], g["m_y"], g["m_off"], g["m_dsg"], B + 2, MINZERO)
+    assert mv == float(g["m_v"]) and np.array_equal(mgr, g["m_g"])
