@@ -162,3 +162,60 @@ def test_c2_full_size_properties(ehmm):
         assert set(np.unique(v)) <= {0.0, 1.0}
         assert np.mean((v == 1) == (x[:, 1] > 0.5)) > 0.98
         assert np.mean((v == 1) == (d["z"] == 1)) > 0.95
+
+
+def test_c3_full_size_properties(ehmm):
+    """BASELINE configs[2] at its full size (15 000 000 bins x 6 samples, K = 3, B = 6): size-independent
+    properties of the differential path -- the two emission sources agree, posteriors and mixture
+    posteriors are normalised, the fused inner M-step equals the sums over the datasets, the rejection
+    control consumes exactly one uniform per flagged (bin, column), Viterbi follows the truth."""
+    M, n_cond, n_rep = 15_000_000, 3, 2
+    d = synth.make_differential(M, n_cond, n_rep, seed=20261003)
+    B = d["B"]
+    th = synth.THETA_DIFFERENTIAL
+    delta = np.full(B, 1.0 / B)
+    psi = np.concatenate([th["psi"][:2], th["psi"][2:]])
+    with ehmm.Session("c3", M, 3) as s:
+        s.set_data(d["counts"], d["offsets"])
+        s.set_design(d["design"])
+        s.loglik_differential_hmm(delta, psi, MINZERO)        # per-cell source
+        direct = s.fetch("logLikelihood")
+        G = s.build_groups()
+        assert 1000 < G < 2_000_000
+        s.loglik_differential_hmm(delta, psi, MINZERO)        # dictionary-encoded source
+        logf = s.fetch("logLikelihood")
+        assert np.max(np.abs(direct - logf)) <= 1e-9 * np.max(np.abs(logf))
+        del direct
+        s.expstep(th["pi"], th["gamma"])
+        L1 = s.fetch("logProb1")
+        assert np.all(np.isfinite(L1)) and np.all(L1 <= 0)
+        P1 = np.exp(L1)
+        assert np.max(np.abs(P1.sum(1) - 1.0)) <= 1e-12
+        st = s.estep_stats()
+        assert abs(st[:9].sum() - (M - 1)) <= 1e-6 * M
+        assert abs(st[9] - np.sum(P1 * logf)) <= 1e-9 * abs(st[9])
+        del logf, L1
+        m = s.maxstepprob()
+        assert np.allclose(np.asarray(m["gamma"]).sum(1), 1.0) and abs(m["pi"].sum() - 1) < 1e-12
+        s.inner_expstep(delta, psi, MINZERO)
+        eta = s.fetch("mixtureProb")
+        assert eta.shape == (M, B) and np.max(np.abs(eta.sum(1) - 1.0)) <= 1e-12
+        dl = s.inner_maxstepprob()
+        want = (P1[:, 1:2] * eta).sum(0) / P1[:, 1].sum()
+        assert abs(dl.sum() - 1) <= 1e-12 and np.max(np.abs(dl - want)) <= 1e-9
+        # the differential windows were simulated with uniform patterns: the mixing proportions are near 1/B
+        assert np.max(np.abs(dl - 1.0 / B)) < 0.02
+        from epigrahmm_b200.rng import RState
+        s.rng_set_state(RState(11).state.copy())
+        n = s.rc_differential(0.05)
+        cols = [P1[:, 0]] + [P1[:, 1] * eta[:, b] for b in range(B)] + [P1[:, 2]]
+        flagged = sum(int(np.count_nonzero((x < 0.05) & (x / 0.05 != 0))) for x in cols)
+        assert n == flagged
+        b0 = s.rc_buckets(0)
+        assert b0[0] == 0 and np.all(b0 >= 0)
+        tot = s.rc_buckets(B + 1).sum()                      # thinning preserves the expected weight
+        assert abs(tot - 6 * P1[:, 2].sum()) <= 6 * (6 * np.sqrt(0.05 * P1[:, 2].sum()) + 1)
+        del eta, cols
+        v = s.viterbi(th["pi"], th["gamma"])
+        assert set(np.unique(v)) <= {0.0, 1.0, 2.0}
+        assert np.mean(v == d["z"]) > 0.9
