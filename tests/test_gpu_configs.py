@@ -164,13 +164,14 @@ def test_c2_full_size_properties(ehmm):
         assert np.mean((v == 1) == (d["z"] == 1)) > 0.95
 
 
-def test_c3_full_size_properties(ehmm):
-    """BASELINE configs[2] at its full size (15 000 000 bins x 6 samples, K = 3, B = 6): size-independent
-    properties of the differential path -- the two emission sources agree, posteriors and mixture
-    posteriors are normalised, the fused inner M-step equals the sums over the datasets, the rejection
-    control consumes exactly one uniform per flagged (bin, column), Viterbi follows the truth."""
-    M, n_cond, n_rep = 15_000_000, 3, 2
-    d = synth.make_differential(M, n_cond, n_rep, seed=20261003)
+@pytest.mark.parametrize("M,n_cond,n_rep", [(15_000_000, 3, 2), (6_000_000, 5, 2)], ids=["c3", "c4"])
+def test_c3_c4_full_size_properties(ehmm, M, n_cond, n_rep):
+    """BASELINE configs[2] and [3] at their full sizes (15 000 000 bins x 6 samples, B = 6; 6 000 000 bins x
+    10 samples, B = 30; K = 3): size-independent properties of the differential path -- the two emission
+    sources agree, posteriors and mixture posteriors are normalised, the fused inner M-step equals the
+    sums over the datasets, the rejection control consumes exactly one uniform per flagged (bin, column),
+    Viterbi follows the truth."""
+    d = synth.make_differential(M, n_cond, n_rep, seed=20261000 + n_cond)
     B = d["B"]
     th = synth.THETA_DIFFERENTIAL
     delta = np.full(B, 1.0 / B)
@@ -213,8 +214,9 @@ def test_c3_full_size_properties(ehmm):
         assert n == flagged
         b0 = s.rc_buckets(0)
         assert b0[0] == 0 and np.all(b0 >= 0)
+        N = n_cond * n_rep
         tot = s.rc_buckets(B + 1).sum()                      # thinning preserves the expected weight
-        assert abs(tot - 6 * P1[:, 2].sum()) <= 6 * (6 * np.sqrt(0.05 * P1[:, 2].sum()) + 1)
+        assert abs(tot - N * P1[:, 2].sum()) <= N * (6 * np.sqrt(0.05 * P1[:, 2].sum()) + 1)
         del eta, cols
         v = s.viterbi(th["pi"], th["gamma"])
         assert set(np.unique(v)) <= {0.0, 1.0, 2.0}
