@@ -253,3 +253,100 @@ def test_shared_memory_exchange_three_ranks():
     with tempfile.TemporaryDirectory() as td:
         mp.spawn(_comm_worker, args=(3, os.path.join(td, "init"), td), nprocs=3, join=True)
         assert [open(os.path.join(td, "ok%d" % r)).read() for r in range(3)] == ["True"] * 3
+
+
+class DiffBlockBackend(BlockBackend):
+    """the differential additions of a bin block: mixture emission, innerExpStep, the inner M-step sums
+    and the rejection control over the B + 2 columns (N group ids per bin)"""
+
+    def __init__(self, O, counts, offsets, design, rng_state):
+        super().__init__(O, counts, offsets, 3, rng_state)
+        self.design, self.B = design, design.shape[0]
+
+    def loglik_differential_hmm(self, delta, psi, minZero):
+        self.h["logLikelihood"] = self.O.loglikDifferentialHMM(self.counts, self.offsets, self.design, delta, psi, minZero)
+
+    def inner_expstep(self, delta, psi, minZero):
+        self.h["mixtureProb"] = self.O.innerExpStep(self.counts, self.offsets, self.design, delta, psi, minZero)
+
+    def inner_mstep_sums(self):
+        p = np.exp(self.h["logProb1"][:, 1])
+        return np.append((p[:, None] * self.h["mixtureProb"]).sum(0), p.sum())
+
+    def _cols(self):
+        P = np.exp(self.h["logProb1"])
+        return [P[:, 0]] + [P[:, 1] * self.h["mixtureProb"][:, b] for b in range(self.B)] + [P[:, 2]]
+
+    def rc_count(self, p, differential=False):
+        assert differential
+        return np.array([np.count_nonzero((x < p) & (x / p != 0)) for x in self._cols()], dtype=np.int64)
+
+    def rc_apply_at(self, p, offs, total, differential=False):
+        u = self.rng.runif(int(total))
+        G = self.g["G"]
+        self.buckets = np.zeros((self.B + 2, G + 1))
+        for c, x in enumerate(self._cols()):
+            w, n = self.O.reweight(x, p, uniforms=u[offs[c]:])
+            for i in range(self.N):
+                np.add.at(self.buckets[c], self.g["group"][:, i], w)
+
+
+def _diff_worker(rank, world, initfile, outdir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    from oracle import oracle as O
+    from epigrahmm_b200 import sharded, synth
+    dist.init_process_group("gloo", init_method="file://" + initfile, rank=rank, world_size=world)
+    M = 3001
+    d = synth.make_differential(M, 2, 2, seed=9)
+    cuts = [0, 900, 2100, M]                                   # three uneven blocks
+    lo, hi = cuts[rank], cuts[rank + 1]
+    counts, offsets = np.asfortranarray(d["counts"][lo:hi]), np.asfortranarray(d["offsets"][lo:hi])
+    be = DiffBlockBackend(O, counts, offsets, d["design"], O.RNG.set_seed(31).state())
+    s = sharded.ShardedSession("td", hi - lo, 3, 0, dist, local=be)
+    g = sharded.global_groups(counts, offsets, s.comm, s.m0, s.Mtot, design=d["design"])
+    be.set_groups(g)
+    th = synth.THETA_DIFFERENTIAL
+    delta = np.array([0.3, 0.7])
+    be.loglik_differential_hmm(delta, th["psi"], MINZERO)
+    s.expstep(th["pi"], th["gamma"])
+    be.inner_expstep(delta, th["psi"], MINZERO)
+    dl = s.inner_maxstepprob()
+    total = s.rc_differential(0.05)
+    np.savez(os.path.join(outdir, "d%d.npz" % rank), L1=be.h["logProb1"], eta=be.h["mixtureProb"], delta=dl,
+             buckets=be.buckets, total=total, state=be.rng.state(), group=g["group"], G=g["G"])
+    dist.destroy_process_group()
+
+
+def test_three_rank_differential_protocol(oracle):
+    """the differential side of the sharded protocol over three uneven bin blocks (gloo, CPU): delta from
+    all-reduced inner M-step sums, one global draw order over the B + 2 columns, summed rejection tables"""
+    import torch.multiprocessing as mp
+    from epigrahmm_b200 import synth
+    with tempfile.TemporaryDirectory() as td:
+        mp.spawn(_diff_worker, args=(3, os.path.join(td, "init"), td), nprocs=3, join=True)
+        r = [np.load(os.path.join(td, "d%d.npz" % i)) for i in range(3)]
+        M = 3001
+        d = synth.make_differential(M, 2, 2, seed=9)
+        g = synth.make_groups(d["counts"], d["offsets"], design=d["design"])
+        th = synth.THETA_DIFFERENTIAL
+        delta = np.array([0.3, 0.7])
+        logf = oracle.loglikDifferentialHMM(d["counts"], d["offsets"], d["design"], delta, th["psi"], MINZERO)
+        h = oracle.expStep(th["pi"], th["gamma"], logf)
+        h["mixtureProb"] = oracle.innerExpStep(d["counts"], d["offsets"], d["design"], delta, th["psi"], MINZERO)
+        L1 = np.vstack([x["L1"] for x in r])
+        assert np.max(np.abs(np.exp(L1) - np.exp(h["logProb1"]))) <= 1e-8
+        assert np.array_equal(np.vstack([x["group"] for x in r]), g["group"]) and int(r[0]["G"]) == g["G"]
+        want_delta = oracle.innerMaxStepProb(h)
+        for x in r:
+            assert np.max(np.abs(x["delta"] - want_delta)) <= 1e-8
+        # rejection control on the merged posteriors of the ranks, one process, one stream
+        hm = dict(h, logProb1=L1, mixtureProb=np.vstack([x["eta"] for x in r]))
+        rng = oracle.RNG.set_seed(31)
+        u = rng.runif(int(r[0]["total"]))
+        rc, n = oracle.differentialRejectionControlled(hm, g["group"], 0.05, 4, uniforms=u, dense=True)
+        assert n == int(r[0]["total"]) == int(r[2]["total"])
+        for x in r:
+            assert np.array_equal(x["state"], rng.state())
+            assert np.allclose(x["buckets"], rc, rtol=1e-8, atol=0) and np.array_equal(x["buckets"] != 0, rc != 0)
