@@ -86,7 +86,9 @@ int ehmm_set_data_encoded16(ehmm_session *s, int N, const uint16_t *group, int64
 /* Start copying the Group column of the NEXT table (M*N ids of 2 or 4 bytes, pinned host memory)
  * to a staging buffer on a copy stream and return at once; the next ehmm_set_data_encoded[16] call
  * given the same pointer uses the staged copy.  Lets the upload of table k+1 overlap the EM
- * iteration on table k (two staging buffers, used in turn). */
+ * iteration on table k (two staging buffers, used in turn).  The host buffer must stay unchanged
+ * until that call, and every prefetch must be followed by it: a staged copy is matched by address
+ * and consumed once. */
 int ehmm_prefetch_groups(ehmm_session *s, int N, const void *group, int bytes_per_id);
 int ehmm_set_design_n(ehmm_session *s, int N, int B, const uint8_t *design);
 /* design[b*N + i] = Dsg.Mix_b of sample i (generateMixtureIntercepts, R/base-utils.R:242-264). */
