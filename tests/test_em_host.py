@@ -161,3 +161,40 @@ def test_zinb_parameter_maps_and_em_on_oracle_backend(oracle):
     assert 0.15 < zi < 0.45, zi
     bics = [h["bic"] for h in fit["controlHist"][:-1]]
     assert bics[-1] < bics[0]
+
+
+def test_prune_patterns_loop_semantics(monkeypatch):
+    """prunePatterns (R/base-utils.R:398-447) with the fit stubbed out: the rarest pattern goes first
+    (which.min takes the first of ties), control$pattern lists the survivors as 1-based condition sets,
+    the loop ends when every posterior proportion reaches the threshold, pruningThreshold is restored"""
+    from epigrahmm_b200 import core, em
+    calls = []
+    post = {None: [0.40, 0.01, 0.30, 0.01, 0.20, 0.08],          # full model, 3 conditions -> 6 patterns
+            5: [0.41, 0.30, 0.01, 0.20, 0.08],
+            4: [0.42, 0.30, 0.20, 0.08]}
+    full = ["EBB", "BEB", "BBE", "EEB", "EBE", "BEE"]
+
+    class FakeSession:
+        closed = 0
+
+        def close(self):
+            FakeSession.closed += 1
+
+    def fake_fit(counts, offsets, peaks, condition, control, dist="nb", **kw):
+        pat = control.get("pattern")
+        calls.append(pat)
+        names = full if pat is None else ["".join("E" if c + 1 in p else "B" for c in range(3)) for p in pat]
+        key = None if pat is None else len(pat)
+        assert control["pruningThreshold"] is None
+        return dict(session=FakeSession(), theta=dict(delta=np.array(post[key])), mixturePatterns=names,
+                    history=dict(controlHist=[dict(bic=-123.0), dict(bic=-123.0)]))
+    monkeypatch.setattr(core, "differentialHMM", fake_fit)
+    ctl = em.controlEM(pruningThreshold=0.05)
+    fit = core.epigraHMM(None, None, None, ["A", "B", "C"], ctl, type="differential")
+    assert calls[0] is None
+    assert calls[1] == [[1], [3], [1, 2], [1, 3], [2, 3]]       # 'BEB' (the first of the two 0.01s) removed
+    assert calls[2] == [[1], [3], [1, 3], [2, 3]]               # then 'EEB'
+    assert len(calls) == 3 and fit["pruned"] == [[2], [1, 2]]
+    assert fit["mixturePatterns"] == ["EBB", "BBE", "EBE", "BEE"] and FakeSession.closed == 2
+    assert fit["control"]["pruningThreshold"] == 0.05 and ctl["pruningThreshold"] == 0.05
+    assert fit["fullBIC"] == -123.0
