@@ -522,6 +522,35 @@ def callPeaks(backend, method="viterbi"):
     return fdrControl(np.exp(backend.fetch("logProb1")[:, 1]), fdr=float(method))
 
 
+def callPatterns(backend, peaks, patterns, type="all", fdr=None, pattern=None, ranges=None):
+    """R/callPaterns.R:78-112 without the GRanges bookkeeping.  `peaks` (and `ranges`) are boolean masks
+    over the bins (the windows overlapping the peak / range set); `patterns` names the mixture
+    components (differentialHMM's mixturePatterns, or getPatterns' condition names).  Returns the bin
+    indices kept and, per type: 'all' / 'ranges' the M' x B posterior matrix, 'fdr' a boolean vector for
+    `pattern`, 'max' the name of the most probable pattern per window (which.max: first of ties)."""
+    post = backend.fetch("mixtureProb")
+    peaks = np.asarray(peaks, dtype=bool)
+    if peaks.shape != (post.shape[0],):
+        raise ValueError("peaks must flag every bin")
+    if len(patterns) != post.shape[1]:
+        raise ValueError("one name per mixture component")
+    idx = np.nonzero(peaks)[0]
+    post = post[idx]
+    if type == "all":
+        return idx, post
+    if type == "fdr":
+        if pattern not in list(patterns):
+            raise ValueError("unknown pattern %r" % (pattern,))
+        return idx, fdrControl(post[:, list(patterns).index(pattern)], fdr=fdr)
+    if type == "max":
+        names = np.asarray(list(patterns), dtype=object)
+        return idx, names[np.argmax(post, axis=1)]
+    if type == "ranges":
+        keep = np.asarray(ranges, dtype=bool)[idx]
+        return idx[keep], post[keep]
+    raise ValueError("type must be 'all', 'fdr', 'max' or 'ranges'")
+
+
 def initial_psi_single_sample(counts, offsets, maxDisp, z):
     """initializerHMM's moment estimates (R/base-core.R:41-49) for the two groups of z (1/2)."""
     r = (np.asarray(counts, dtype=np.float64) + 1.0) / np.exp(offsets)

@@ -198,3 +198,25 @@ def test_prune_patterns_loop_semantics(monkeypatch):
     assert fit["mixturePatterns"] == ["EBB", "BBE", "EBE", "BEE"] and FakeSession.closed == 2
     assert fit["control"]["pruningThreshold"] == 0.05 and ctl["pruningThreshold"] == 0.05
     assert fit["fullBIC"] == -123.0
+
+
+def test_call_patterns_types():
+    """callPatterns (R/callPaterns.R:78-112): 'all', 'fdr', 'max' (which.max: the first of ties) and 'ranges'"""
+    from epigrahmm_b200 import em
+
+    class B:
+        def fetch(self, name):
+            assert name == "mixtureProb"
+            return np.array([[0.7, 0.2, 0.1], [0.1, 0.1, 0.8], [0.4, 0.4, 0.2], [0.05, 0.9, 0.05], [0.98, 0.01, 0.01]])
+    peaks = np.array([True, False, True, True, True])
+    names = ["A", "B", "A-B"]
+    idx, all_ = em.callPatterns(B(), peaks, names)
+    assert idx.tolist() == [0, 2, 3, 4] and all_.shape == (4, 3)
+    idx, mx = em.callPatterns(B(), peaks, names, type="max")
+    assert mx.tolist() == ["A", "A", "B", "A"]
+    idx, f = em.callPatterns(B(), peaks, names, type="fdr", fdr=0.2, pattern="A")
+    assert f.tolist() == em.fdrControl(np.array([0.7, 0.4, 0.05, 0.98]), 0.2).tolist() and f.tolist() == [True, False, False, True]
+    idx, r = em.callPatterns(B(), peaks, names, type="ranges", ranges=np.array([False, True, True, False, True]))
+    assert idx.tolist() == [2, 4] and r.shape == (2, 3)
+    with pytest.raises(ValueError):
+        em.callPatterns(B(), peaks, names, type="fdr", fdr=0.2, pattern="C")
