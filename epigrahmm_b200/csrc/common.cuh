@@ -159,6 +159,10 @@ struct ehmm_session {
     bool groups_consistent = false;  // dtUnique[group] reproduces (counts, offsets[, controls]) cell by cell
     int64_t count_max = -1;
     double *h_pinned = nullptr;  // small pinned staging buffer (1024 doubles; [512..] = RNG state)
+    // mapped (zero-copy) result slot of the batched GLM kernel: the kernel's last block stores values and
+    // gradients here and then an epoch flag; the host polls the flag instead of copying and synchronising
+    double *h_glm = nullptr, *d_glm = nullptr;  // 64 doubles; [63] holds the flag (as unsigned)
+    unsigned glm_epoch = 0;
 
     // ---- launch counters and optional per-kernel CUDA-event timing ----
     int64_t launches[ehmm::KID_COUNT] = {0};

@@ -4,6 +4,8 @@
 // group id; a zero bucket contributes exactly 0, so summing over all G groups equals summing over
 // the reference's non-zero rows.  Block partial sums are reduced in a fixed order (deterministic).
 #include "common.cuh"
+#include <atomic>
+#include <chrono>
 
 namespace ehmm {
 
@@ -89,7 +91,8 @@ struct NBBatch {
 __global__ void __launch_bounds__(GLM_NT)
     glm_nb_batch_kernel(int64_t G, const double *__restrict__ buckets, const double *__restrict__ y,
                         const double *__restrict__ off, const double *__restrict__ ctrl, NBBatch B,
-                        double *__restrict__ part, unsigned *__restrict__ ticket, double *__restrict__ out) {
+                        double *__restrict__ part, unsigned *__restrict__ ticket, double *__restrict__ out,
+                        double *__restrict__ hout, unsigned epoch) {
     const int q = blockIdx.y;
     const NBPar P = B.par[q];
     const double *wt = buckets + (size_t)B.column[q] * (G + 1);
@@ -143,10 +146,22 @@ __global__ void __launch_bounds__(GLM_NT)
                 if ((int)threadIdx.x < d) red[threadIdx.x] += red[threadIdx.x + d];
                 __syncthreads();
             }
-            if (threadIdx.x == 0) out[q * 4 + c] = red[0];
+            if (threadIdx.x == 0) {
+                out[q * 4 + c] = red[0];
+                hout[q * 4 + c] = red[0];  // zero-copy: straight into the host's mapped result slot
+            }
             __syncthreads();
         }
-        if (threadIdx.x == 0) ticket[q] = 0u;
+        if (threadIdx.x == 0) {
+            ticket[q] = 0u;
+            // the evaluation whose last block finishes last publishes the epoch (after all results)
+            __threadfence_system();
+            if (atomicAdd(ticket + EHMM_MAX_K, 1u) == gridDim.y - 1) {
+                ticket[EHMM_MAX_K] = 0u;
+                __threadfence_system();
+                *reinterpret_cast<volatile unsigned *>(hout + 63) = epoch;
+            }
+        }
     }
 }
 
@@ -371,14 +386,31 @@ int glm_nb_batch(ehmm_session *s, int ncols, const int *columns, const double *p
     double *part = s->glm_part.as<double>();
     double *out = part + (size_t)EHMM_MAX_K * 148 * 4 * 4;
     dim3 grid((unsigned)nblk, (unsigned)ncols);
+    const unsigned epoch = ++s->glm_epoch ? s->glm_epoch : ++s->glm_epoch;  // never 0
     PROF(s, KID_GLM), glm_nb_batch_kernel<<<grid, GLM_NT, 0, s->stream>>>(
         s->G, s->rc_buckets.as<double>(), s->u_chip.as<double>(), s->u_off.as<double>(), s->u_ctrl.as<double>(), B, part,
-        s->glm_ticket.as<unsigned>(), out);
+        s->glm_ticket.as<unsigned>(), out, s->d_glm, epoch);
     EHMM_CK(cudaGetLastError());
-    EHMM_CK(cudaMemcpyAsync(s->h_pinned + 128, out, sizeof(double) * 4 * ncols, cudaMemcpyDeviceToHost, s->stream));
-    EHMM_CK(cudaStreamSynchronize(s->stream));
+    // poll the mapped flag (a few microseconds after the kernel ends) instead of a copy + stream
+    // synchronisation; a kernel that never reports falls back to the synchronising path for the error
+    {
+        volatile unsigned *flag = reinterpret_cast<volatile unsigned *>(s->h_glm + 63);
+        const auto t0 = std::chrono::steady_clock::now();
+        unsigned spins = 0;
+        while (*flag != epoch) {
+            if ((++spins & 0x3ff) == 0) {
+                if (cudaStreamQuery(s->stream) != cudaErrorNotReady) break;  // finished (or failed) without the flag
+                if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(30)) break;
+            }
+        }
+        if (*flag != epoch) {
+            EHMM_CK(cudaStreamSynchronize(s->stream));
+            EHMM_REQUIRE(*flag == epoch, EHMM_ERR_CUDA, "glmNB batch: the kernel did not report its result");
+        }
+        std::atomic_thread_fence(std::memory_order_acquire);
+    }
     for (int q = 0; q < ncols; q++) {
-        const double *o = s->h_pinned + 128 + 4 * q;
+        const double *o = s->h_glm + 4 * q;
         values[q] = -o[0];
         if (grads) {
             double *g = grads + (size_t)q * (P_ + 1);

@@ -211,6 +211,9 @@ int ehmm_session_open(const char *key, int64_t M, int K, int device, ehmm_sessio
     EHMM_CK(cudaEventCreateWithFlags(&s->ev, cudaEventDisableTiming));
     EHMM_CK(cudaEventCreateWithFlags(&s->ev2, cudaEventDisableTiming));
     EHMM_CK(cudaMallocHost(&s->h_pinned, sizeof(double) * 1024));
+    EHMM_CK(cudaHostAlloc(&s->h_glm, sizeof(double) * 64, cudaHostAllocMapped));
+    memset(s->h_glm, 0, sizeof(double) * 64);
+    EHMM_CK(cudaHostGetDevicePointer(&s->d_glm, s->h_glm, 0));
     {
         std::lock_guard<std::mutex> lk(g_mu);
         auto it = g_sessions.find(s->key);
@@ -259,6 +262,7 @@ int ehmm_session_close(ehmm_session *s) {
     if (s->stream_up) cudaStreamDestroy(s->stream_up);
     for (cudaEvent_t e : s->prof_pool) cudaEventDestroy(e);
     if (s->h_pinned) cudaFreeHost(s->h_pinned);
+    if (s->h_glm) cudaFreeHost(s->h_glm);
     if (s->ev) cudaEventDestroy(s->ev);
     if (s->ev2) cudaEventDestroy(s->ev2);
     if (s->stream) cudaStreamDestroy(s->stream);
