@@ -220,3 +220,41 @@ def test_call_patterns_types():
     assert idx.tolist() == [2, 4] and r.shape == (2, 3)
     with pytest.raises(ValueError):
         em.callPatterns(B(), peaks, names, type="fdr", fdr=0.2, pattern="C")
+
+
+def test_sharded_host_helpers_properties():
+    """rc_offsets: the ranks' slices of the uniform stream are disjoint, ordered column-major then by block, and
+    cover [0, total); combine_carries: forward / backward carries equal the brute-force operator products"""
+    from epigrahmm_b200.sharded import combine_carries, rc_offsets
+    rng = np.random.default_rng(3)
+    for _ in range(50):
+        P, Ccols = int(rng.integers(1, 9)), int(rng.integers(1, 33))
+        counts = rng.integers(0, 1000, (P, Ccols))
+        spans = []
+        for r in range(P):
+            offs, total = rc_offsets(counts, r)
+            assert total == counts.sum()
+            spans += [(int(offs[c]), int(offs[c] + counts[r, c]), c, r) for c in range(Ccols)]
+        spans.sort()
+        pos = 0
+        for lo, hi, c, r in spans:
+            assert lo == pos
+            pos = hi
+        assert pos == counts.sum()
+        order = [(c, r) for lo, hi, c, r in spans if hi > lo]
+        assert order == sorted(order)                      # column-major, then ascending block
+    for K in (2, 3):
+        for _ in range(20):
+            P = int(rng.integers(1, 7))
+            ops = np.concatenate([rng.random((P, K * K)) + 0.01, rng.normal(-50, 30, (P, 1))], axis=1)
+            start = np.append(rng.dirichlet(np.ones(K)), 0.0)
+            for r in range(P):
+                fwd, bwd = combine_carries(ops, r, start, K)
+                v, ls = start[:K].copy(), 0.0
+                for q in range(r):
+                    v, ls = v @ ops[q, :K * K].reshape(K, K), ls + ops[q, K * K]
+                u, lu = np.ones(K), 0.0
+                for q in range(P - 1, r, -1):
+                    u, lu = ops[q, :K * K].reshape(K, K) @ u, lu + ops[q, K * K]
+                assert np.allclose(np.log(fwd[:K]) + fwd[K], np.log(v) + ls, rtol=0, atol=1e-10)
+                assert np.allclose(np.log(bwd[:K]) + bwd[K], np.log(u) + lu, rtol=0, atol=1e-10)
