@@ -112,7 +112,7 @@ int ehmm_loglik_differential_hmm_zinb(ehmm_session *s, const double *delta, cons
 int ehmm_inner_expstep(ehmm_session *s, const double *delta, const double *psi, double minZero);
 int ehmm_inner_expstep_zinb(ehmm_session *s, const double *delta, const double *psi, double minZero);
 
-/* ---- E-step / M-step (src/*.cpp) ---------------------------------------------------- */
+/* ---- E-step / M-step (the C++ sources under src/) ------------------------------------ */
 /* expStep, src/expStep.cpp:45-123. logf: host M x K matrix, or NULL to use the
  * device-resident logLikelihood written by an ehmm_loglik_* call. */
 int ehmm_expstep(ehmm_session *s, const double *pi, const double *gamma, const double *logf);

@@ -60,3 +60,22 @@ def test_product_does_not_import_oracle():
                 txt = open(os.path.join(dp, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
                 assert "libehmm_oracle" not in txt, f
+
+
+def test_header_is_plain_c_and_links_without_python(ehmm, tmp_path):
+    """include/ehmm.h compiles as C99 (no torch / C++ types in the signatures) and a plain C program that
+    takes the address of every declared entry point links against the shared library and runs"""
+    names = _declared()
+    lines = ['#include <stdio.h>', '#include "ehmm.h"', 'typedef void (*anyfn)(void);', 'int main(void) {', '    anyfn fn[] = {']
+    lines += ['        (anyfn)%s,' % n for n in names]
+    lines += ['    };', '    int n = 0;', '    unsigned i;',
+              '    for (i = 0; i < sizeof(fn) / sizeof(fn[0]); i++) n += fn[i] != 0;',
+              '    printf("%d %d\\n", n, ehmm_version());', '    return 0;', '}', '']
+    src = tmp_path / "abi_link.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "abi_link"
+    libdir = os.path.dirname(ehmm.SO_PATH)
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                    "-L", libdir, "-l:" + os.path.basename(ehmm.SO_PATH), "-Wl,-rpath," + libdir], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
+    assert int(out[0]) == len(names) and int(out[1]) >= 100
