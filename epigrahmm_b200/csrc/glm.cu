@@ -56,30 +56,7 @@ struct NBPar {
     int has_ctrl;
 };
 
-// out: [0] = sum w*l, [1] = sum w*r, [2] = sum w*r*ctrl, [3] = sum w*dphi
-__global__ void __launch_bounds__(GLM_NT)
-    glm_nb_kernel(int64_t G, const double *__restrict__ wt, const double *__restrict__ y, const double *__restrict__ off,
-                  const double *__restrict__ ctrl, NBPar P, double *__restrict__ part) {
-    double acc[4] = {0, 0, 0, 0};
-    for (int64_t g = 1 + (int64_t)blockIdx.x * GLM_NT + threadIdx.x; g <= G; g += (int64_t)gridDim.x * GLM_NT) {
-        const double w = wt[g];
-        if (w == 0.0) continue;
-        const double yy = y[g], cv = P.has_ctrl ? ctrl[g] : 0.0;
-        const double eta = (P.has_ctrl ? (P.b0 + cv * P.b1) : P.b0) + off[g];
-        const double mu = exp(eta);
-        double l = nb_logpmf_direct(yy, eta, P.size, P.lsize, P.lgs);
-        if (isinf(l)) l = -690.77552789821368;  // log(1e-300), R/base-optim.R:112
-        const double den = 1.0 + P.phi * mu;
-        const double r = (yy - mu) / den;
-        const double dphi = (log(den) + P.phi * (yy - mu) / den - digamma_pos(yy + P.size) + P.dg_size) / (P.phi * P.phi);
-        acc[0] += w * l;
-        acc[1] += w * r;
-        acc[2] += w * r * cv;
-        acc[3] += w * dphi;
-    }
-    block_store<4>(acc, part);
-}
-
+// out per evaluation: [0] = sum w*l, [1] = sum w*r, [2] = sum w*r*ctrl, [3] = sum w*dphi
 // Batched form: blockIdx.y selects the (column, parameter) pair, so the optimiser can evaluate all
 // states in one launch; the last block to finish (ticket counter) reduces the per-block partials in
 // a fixed order, so no second launch is needed and the result is deterministic.

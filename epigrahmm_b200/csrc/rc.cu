@@ -296,7 +296,6 @@ int run_rc(ehmm_session *s, const RCSrc &S, double p, int nrep, const double *un
         EHMM_CK(cudaMemsetAsync(s->rc_scan.p, 0, sizeof(int64_t) * (ncnt + 1), s->stream));
     }
     const int32_t *grp = s->group.as<int32_t>();
-    bool state_back = false;
     if (uniforms) {
         EHMM_REQUIRE(total <= n_uniforms, EHMM_ERR_RNG, "rejection control needs %lld uniforms, buffer holds %lld",
                      (long long)total, (long long)n_uniforms);
@@ -323,7 +322,6 @@ int run_rc(ehmm_session *s, const RCSrc &S, double p, int nrep, const double *un
             EHMM_TRY(mt_generate(s, total, s->rc_unif.as<uint32_t>()));
             EHMM_CK(cudaMemcpyAsync(s->h_pinned + 512, s->mt_raw.p, sizeof(uint32_t) * 625, cudaMemcpyDeviceToHost, s->stream));
             rng_note_advance(s, total);
-            state_back = true;
         }
         PROF(s, KID_RC_APPLY), rc_apply_kernel<uint32_t><<<apply_grid(nblk, S.columns), RC_NT, 0, s->stream>>>(S, p, nblk, s->rc_scan.as<int64_t>(),
                                                                  s->rc_unif.as<uint32_t>(), grp, nrep, s->G,
@@ -338,7 +336,7 @@ int run_rc(ehmm_session *s, const RCSrc &S, double p, int nrep, const double *un
         if (est > (int64_t)S.columns * s->M) est = (int64_t)S.columns * s->M;
         EHMM_TRY(mt_prefetch(s, est));
     }
-    (void)state_back;  // the host does not wait for the tables: the next reader of the stream does
+    // the host does not wait for the tables: the next reader of the stream does
     s->rc_columns = S.columns;
     s->rc_N = nrep;
     if (consumed) *consumed = total;
@@ -386,7 +384,6 @@ int rc_apply_block(ehmm_session *s, const RCSrc &S, double p, int nrep, const in
     EHMM_CK(cudaMemsetAsync(s->rc_buckets.p, 0, sizeof(double) * (size_t)S.columns * (s->G + 1), s->stream));
     EHMM_TRY(s->rc_unif.reserve(sizeof(uint32_t) * (size_t)(local > 0 ? local : 1)));
     EHMM_TRY(s->mt_raw.reserve(sizeof(uint32_t) * 625));
-    bool state_back = false;
     if (total > 0) {
         if (!s->rng_dev_valid) {
             memcpy(s->h_pinned + 512, s->rng_state, sizeof(uint32_t) * 625);
@@ -404,7 +401,6 @@ int rc_apply_block(ehmm_session *s, const RCSrc &S, double p, int nrep, const in
             EHMM_TRY(mt_generate_range(s, col_offsets[c], s->rc_colcount[c], s->rc_unif.as<uint32_t>() + at));
             at += s->rc_colcount[c];
         }
-        state_back = true;
     }
     dim3 grid((unsigned)nblk, (unsigned)S.columns);
     PROF(s, KID_RC_APPLY), rc_apply_kernel<uint32_t><<<apply_grid(nblk, S.columns), RC_NT, 0, s->stream>>>(
@@ -418,7 +414,6 @@ int rc_apply_block(ehmm_session *s, const RCSrc &S, double p, int nrep, const in
         rng_note_advance(s, total);
         EHMM_TRY(mt_prefetch_ranges(s, S.columns, col_offsets, s->rc_colcount, total, 2));
     }
-    (void)state_back;
     s->rc_columns = S.columns;
     s->rc_N = nrep;
     s->rc_count_cols = 0;
