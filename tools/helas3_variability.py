@@ -1,4 +1,4 @@
-import os, sys
+import sys
 import numpy as np
 sys.path.insert(0, "."); sys.path.insert(0, "tests")
 import epigrahmm_b200 as E

@@ -1,7 +1,6 @@
 """Short driver for ncu: a few EM iterations of the consensus workload at a given size."""
 import sys
 
-import numpy as np
 
 sys.path.insert(0, ".")
 import bench
