@@ -1,26 +1,35 @@
 #!/usr/bin/env python
 """bench.py -- EM iterations/s and bin-states/s of the epigraHMM EM hot path on B200.
 
-A step is one full EM iteration of the consensus model (R/base-EM.R:106-175) at fixed theta:
-NB emission -> expStep (forward-backward + posteriors) -> maxStepProb -> rejection control
-(p = 0.05, uniforms from R's Mersenne-Twister generated on the device) -> L-BFGS-B over the NB-GLM
-value/gradient reductions for both states -> BIC and Q.
+A step is one EM iteration at fixed theta of the configuration --config names (BASELINE.json):
 
-Workload at N = 1: BASELINE.json configs[1] -- synthetic human genome, 200 bp bins
-(15 000 000 bins) x 4 replicates, consensus peak calling (K = 2), generated as SURVEY.md 8(d).
-At N > 1 the genome is sharded as contiguous bin blocks of 15 000 000 bins per GPU (weak scaling);
-the single global chain is kept exact by exchanging the blocks' scan operators and all-reducing
-the sufficient statistics (torch.distributed / NCCL).
+  c3 (default) configs[2]: genome-wide differential peak calling, 3 conditions x 2 replicates
+               (B = 2^3 - 2 = 6 mixture patterns), 15 000 000 bins of 200 bp, K = 3.  One OUTER iteration
+               of R/base-EM.R:242-293: mixture emission -> expStep -> maxStepProb -> the reference's
+               5 INNER iterations (controlEM's maxIterInnerEM, R/base-EM.R:191-225: innerExpStep ->
+               innerMaxStepProb -> differentialRejectionControlled -> L-BFGS-B over glmMixNB) -> BIC, Q.
+  c2           configs[1]: consensus peak calling, 15 000 000 bins x 4 replicates, K = 2: one iteration of
+               R/base-EM.R:106-175.
+  c5           configs[4]: 50 bp bins, 60 000 000 bins x (4 conditions x 3 replicates), B = 14, sharded
+               over the GPUs of the run (7 500 000 bins per GPU at --gpus 8).
+
+At N > 1 GPUs the chain is cut into contiguous bin blocks, one per GPU, kept exact by exchanging
+the blocks' scan operators and adding the sufficient statistics and the rejection tables (NCCL).
+--scaling weak (default): every GPU holds the configuration's full bin count; strong: the
+configuration's bins are divided among the GPUs (c5 is always strong: it is defined on 8 GPUs).
 
   value : bin-states/s with the count matrix already resident in HBM
-  e2e   : the same iteration through the host-pointer C ABI: every step uploads counts, offsets
-          and group ids from pinned host memory and reads the updated parameters back
-  --impl reference : the reference's CPU path (the oracle restatement; R is not installable
-          here) on a bounded sample of the same workload, single-threaded like the reference
+  e2e   : the same iteration through the host-pointer C ABI; every step uploads the long table from
+          pinned host memory (counts + offsets; dt$Group is rebuilt on the device) and reads the
+          updated parameters back.  Two cheaper forms are reported next to it.
+  --impl reference : the reference's CPU path (the oracle restatement; R is not installable here) on a
+          bounded sample of the same workload, single-threaded like the reference; does not load
+          the product library.
 """
 from __future__ import annotations
 
 import argparse
+import importlib.util
 import json
 import os
 import subprocess
@@ -33,14 +42,36 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-M_FULL = 15_000_000
-N_SAMPLES = 4
-K = 2
 MINZERO = 2.2250738585072014e-308
 P_CUT = 0.05
-SEED = 20261002
-CPU_SAMPLE_BINS = 1_000_000
 METRIC = "bin-states/s"
+
+CONFIGS = {
+    "c2": dict(model="consensus", M=15_000_000, N=4, K=2, seed=20261002, cpu_bins=1_000_000,
+               workload="BASELINE configs[1]: synthetic human genome 200 bp bins (15 000 000) x 4 replicates, consensus "
+                        "broad-peak calling (K = 2), one EM iteration per step at fixed theta (SURVEY.md 8d), rejection cut p = 0.05"),
+    "c3": dict(model="differential", M=15_000_000, n_cond=3, n_rep=2, N=6, K=3, seed=20261003, cpu_bins=150_000,
+               workload="BASELINE configs[2]: synthetic genome-wide differential peak calling, 3 conditions x 2 replicates "
+                        "(2^3 - 2 = 6 mixture patterns), 15 000 000 bins of 200 bp (K = 3); one outer EM iteration with the "
+                        "reference's 5 inner iterations per step at fixed theta, rejection cut p = 0.05"),
+    "c5": dict(model="differential", M=60_000_000, n_cond=4, n_rep=3, N=12, K=3, seed=20261005, cpu_bins=60_000,
+               workload="BASELINE configs[4]: synthetic 50 bp fine-bin differential run, 60 000 000 bins x (4 conditions x 3 "
+                        "replicates), 14 mixture patterns (K = 3), bin blocks sharded across the GPUs; one outer EM iteration "
+                        "with 5 inner iterations per step at fixed theta, rejection cut p = 0.05"),
+}
+
+
+def host_module(name):
+    """epigrahmm_b200/<name>.py loaded by path: pure host code (numpy / scipy), so the CPU arm can use the
+    EM driver and the data generator without importing the package, which would load the CUDA library"""
+    key = "_ehmm_host_" + name
+    if key in sys.modules:
+        return sys.modules[key]
+    spec = importlib.util.spec_from_file_location(key, os.path.join(ROOT, "epigrahmm_b200", name + ".py"))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[key] = mod
+    spec.loader.exec_module(mod)
+    return mod
 
 
 def peaks():
@@ -137,122 +168,220 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "samples": len(self.sm), "source": self.how}
 
 
-def pin_workload(d, g):
+# ---- workload -----------------------------------------------------------------------------------
+
+def make_data(cfg, M, seed):
+    synth = host_module("synth")
+    if cfg["model"] == "consensus":
+        return synth.make_consensus(M, cfg["N"], seed)
+    return synth.make_differential(M, cfg["n_cond"], cfg["n_rep"], seed)
+
+
+def theta_of(cfg, d):
+    synth = host_module("synth")
+    if cfg["model"] == "consensus":
+        th = synth.THETA_CONSENSUS
+        return dict(pi=th["pi"], gamma=th["gamma"], psi=th["psi"])
+    th = synth.THETA_DIFFERENTIAL
+    return dict(pi=th["pi"], gamma=th["gamma"], delta=np.full(d["B"], 1.0 / d["B"]),
+                psi=[th["psi"][:2].copy(), th["psi"][2:].copy()])
+
+
+def control_of(cfg):
+    em = host_module("em")
+    # the reference's defaults; the inner loop's early exit (epsilonInnerEM) is disabled so that every
+    # step runs all maxIterInnerEM = 5 inner iterations, like an early outer iteration of a real fit
+    return em.controlEM(epsilonInnerEM=1e-300) if cfg["model"] == "differential" else em.controlEM()
+
+
+def pin(a):
+    """copy into pinned host memory (kept alive by the returned tensor)"""
     import torch
-    if g["G"] < 65536:
-        g["group16"] = g["group"].astype(np.uint16)
-    tdt = {np.dtype(np.int32): torch.int32, np.dtype(np.float64): torch.float64, np.dtype(np.uint16): torch.uint16}
-    for k, src in (("counts", d), ("offsets", d), ("group", g), ("group16", g)):
-        if k not in src:
-            continue
-        a = src[k]
-        t = torch.empty(a.size, dtype=tdt[a.dtype]).pin_memory()
-        v = t.numpy().reshape(a.shape, order="F")
-        v[...] = a
-        src[k] = v
-        src["_pin_" + k] = t  # keep the pinned tensor alive
-    return d, g
+    tdt = {np.dtype(np.int32): torch.int32, np.dtype(np.float64): torch.float64, np.dtype(np.uint16): torch.uint16,
+           np.dtype(np.uint8): torch.uint8}
+    t = torch.empty(a.size, dtype=tdt[a.dtype]).pin_memory()
+    v = t.numpy().reshape(a.shape, order="F")
+    v[...] = a
+    return v, t
 
 
-def make_workload(M, N, seed, pinned=False):
-    from epigrahmm_b200 import synth
-    d = synth.make_consensus(M, N, seed)
-    g = synth.make_groups(d["counts"], d["offsets"])
-    return pin_workload(d, g) if pinned else (d, g)
+def upload(be, cfg, d, g, form):
+    """the step's host -> device traffic, through the public C ABI.
+    form 'table': the long table as the reference holds it (counts, offsets) + dt$Group built on the device;
+    'encoded': dt$Group + dtUnique only (the dictionary was built once per fit, outside the timed region);
+    'pipelined': encoded, the next step's Group column already in flight (ehmm_prefetch_groups)."""
+    if form == "table":
+        be.set_data(d["counts"], d["offsets"])
+        if cfg["model"] == "differential":
+            be.set_design(d["design"])
+        be.build_groups()
+        return
+    grp = g.get("group16", g["group"])
+    be.set_data_encoded(grp, g["u_chip"], g["u_offsets"], None, g.get("u_dsg"), d.get("design"))
+    if form == "pipelined":
+        be.prefetch_groups(grp)
 
 
-def em_iteration(be, theta, control, N, upload=None, p=None):
-    """one EM iteration at theta (the loop body of emConsensus); returns the updated parameters"""
-    from epigrahmm_b200 import em
-    if upload is not None:
-        d, g, encoded = upload[:3]
-        if encoded:   # dt$Group + dtUnique only: 2 B per cell when G < 65536, else 4 B
-            be.set_data_encoded(g.get("group16", g["group"]), g["u_chip"], g["u_offsets"])
-            if len(upload) > 3 and upload[3]:   # the next step's table starts uploading while this one computes
-                be.prefetch_groups(g.get("group16", g["group"]))
-        else:         # the full long table: counts, offsets and Group, 16 B per cell
-            be.set_data(d["counts"], d["offsets"])
-            be.set_groups(g["group"], g["u_chip"], g["u_offsets"])
-    be.loglik_consensus(theta["psi"], control["minZero"])
-    be.expstep(theta["pi"], theta["gamma"])
-    new = be.maxstepprob()
-    be.rc_consensus(P_CUT if p is None else p)
-    opt = em.optimNB_all(theta["psi"], be, control)
-    new["psi"] = [o["par"] for o in opt]
-    numPar = em.unlist(theta).size - 3
+def em_step(be, cfg, theta, control, p=P_CUT):
+    """one step = the loop body of emConsensus (R/base-EM.R:106-175) or of outerEMDifferential (:242-293,
+    with innerEMDifferential :191-225) at theta; returns the updated parameters, BIC and Q"""
+    em = host_module("em")
+    N = cfg["N"]
+    if cfg["model"] == "consensus":
+        be.loglik_consensus(theta["psi"], control["minZero"])
+        be.expstep(theta["pi"], theta["gamma"])
+        new = be.maxstepprob()
+        be.rc_consensus(p)
+        opt = em.optimNB_all(theta["psi"], be, control)
+        new["psi"] = [o["par"] for o in opt]
+        numPar = em.unlist(theta).size - 3
+    else:
+        psi_flat = np.concatenate([np.ravel(x) for x in theta["psi"]])
+        be.loglik_differential_hmm(theta["delta"], psi_flat, control["minZero"])
+        be.expstep(theta["pi"], theta["gamma"])
+        new = be.maxstepprob()
+        inner = em.innerEMDifferential(theta, be, p, control)
+        new["delta"], new["psi"] = inner["theta_new"]["delta"], inner["theta_new"]["psi"]
+        numPar = em.unlist(theta).size - 3
     new["bic"] = be.bic(numPar, N)
     new["q"] = be.qfunction(theta["pi"], theta["gamma"])
     return new
 
 
-ALGO_BYTES = {  # algorithmic bytes per bin of each streaming kernel (DESIGN.md section 4)
-    "fb_apply": 32 * K + 8 * K * K,          # logf in; logFP, logBP, logProb1, logProb2 out
-    "fb_reduce": 8 * K,                      # logf in
-    "emis_consensus": 12 * N_SAMPLES + 8 * K,  # int32 counts + fp64 offsets in; logf out
-    "emis_gather": 4 * N_SAMPLES + 8 * K,    # dictionary-encoded emission: int32 group ids in; logf out
-    "rc_count": 8 * K,                       # logProb1 in
-    "rc_apply": 8 * K + 4,                   # logProb1 + group id in (uniforms / buckets are O(flagged))
-}
+def algo_bytes(cfg, B):
+    """algorithmic bytes per bin of each streaming kernel"""
+    K, N = cfg["K"], cfg["N"]
+    t = {"fb_apply": 32 * K + 8 * K * K,   # logf in; logFP, logBP, logProb1, logProb2 out
+         "fb_apply_em": 16 * K,            # EM-internal E-step: logf in, P1 out (statistics and flag counts fused)
+         "fb_reduce": 8 * K}               # logf in
+    if cfg["model"] == "consensus":
+        t.update({"emis_consensus": 12 * N + 8 * K,   # int32 counts + fp64 offsets in; logf out
+                  "emis_gather": 4 * N + 8 * K,       # dictionary-encoded emission: group ids in; logf out
+                  "rc_count": 8 * K,                  # logProb1 in
+                  "rc_apply": 8 * K + 4})             # logProb1 + group id of replicate 1 in
+    else:
+        t.update({"emis_diff_hmm": 4 * N + 8 * K,     # group ids in (dictionary-encoded); logf out
+                  "emis_inner": 4 * N + 8 + 8 * B,    # group ids + P1[,2] in; mixtureProb out
+                  "rc_count": 8 * (K + B),            # logProb1 + mixtureProb in
+                  "rc_apply": 8 * (K + B) + 4 * N})   # ... + the N group ids of the bin
+    return t
 
 
-def run_reference(args):
-    """CPU arm: the oracle restatement of the reference path, 1 thread, bounded sample."""
+def config_dict(name, cfg, n_gpus, M_gpu, scaling):
+    return {"workload": cfg["workload"], "name": name, "bins_per_gpu": M_gpu, "bins_total": M_gpu * n_gpus if scaling == "weak" else cfg["M"],
+            "samples": cfg["N"], "states": cfg["K"], "seed": cfg["seed"],
+            "l2_policy": "inputs larger than L2 (every pass streams >= 0.36 GB per GPU against 126 MB of L2)" if M_gpu >= 4_000_000
+                         else "inputs of one pass fit L2 at this block size: between steps the E-step outputs (>= 5x larger) evict them",
+            "sharding": "contiguous bin blocks, one per GPU, scan carries exchanged" if n_gpus > 1 else "single GPU"}
+
+
+def block_of(cfg, world, scaling):
+    if scaling == "weak":
+        return cfg["M"]
+    return (cfg["M"] + world - 1) // world
+
+
+# ---- CPU arm ------------------------------------------------------------------------------------
+
+def oracle_backend(cfg, d, Ms):
     from oracle import oracle as O
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from oracle_backend import OracleBackend
-    from epigrahmm_b200 import em, synth
-    M = CPU_SAMPLE_BINS
-    d, g = make_workload(M, N_SAMPLES, SEED)
-    th = synth.THETA_CONSENSUS
-    theta = dict(pi=th["pi"], gamma=th["gamma"], psi=th["psi"])
-    ctl = em.controlEM()
-    be = OracleBackend(d["counts"], d["offsets"], K, groups=g, rng=O.RNG.set_seed(SEED))
+    synth = host_module("synth")
+    c, o = np.asfortranarray(d["counts"][:Ms]), np.asfortranarray(d["offsets"][:Ms])
+    design = d.get("design")
+    g = synth.make_groups(c, o, design=design)
+    return OracleBackend(c, o, cfg["K"], design=design, groups=g, rng=O.RNG.set_seed(cfg["seed"]))
+
+
+def run_reference(args, name, cfg):
+    """CPU arm: the oracle restatement of the reference path, 1 thread (the reference has no threads),
+    in memory (no HDF5 round trips), on a bounded sample: the first cpu_bins bins of the workload."""
+    Ms = cfg["cpu_bins"]
+    d = make_data(cfg, Ms, cfg["seed"])
+    theta, ctl = theta_of(cfg, d), control_of(cfg)
+    be = oracle_backend(cfg, d, Ms)
     for _ in range(args.warmup):
-        em_iteration(be, theta, ctl, N_SAMPLES)
+        em_step(be, cfg, theta, ctl)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        em_iteration(be, theta, ctl, N_SAMPLES)
+        em_step(be, cfg, theta, ctl)
     dt = time.perf_counter() - t0
-    val = M * K * args.steps / dt
-    sample = "first %d bins of the workload (%.1f%% of one GPU's block), one EM iteration per step" % (M, 100.0 * M / M_FULL)
+    val = Ms * cfg["K"] * args.steps / dt
+    scaling = "strong" if name == "c5" else args.scaling
+    M_gpu = block_of(cfg, args.gpus, scaling)
+    sample = ("%d bins generated like the workload's (%.2f%% of one GPU's block), one step = %s; the rate is per bin, so "
+              "it extrapolates linearly to the full block" % (Ms, 100.0 * Ms / M_gpu, "one EM iteration" if cfg["model"] == "consensus"
+                                                             else "one outer iteration with 5 inner iterations"))
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "bin-states/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": config_dict(args.gpus, reference=True),
+            "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config_dict(name, cfg, args.gpus, M_gpu, scaling),
             "cpu_baseline": {"value": val, "unit": "bin-states/s", "cores": 1, "kind": "port", "sample": sample,
-                             "host_cores_available": os.cpu_count()},
+                             "host_cores_available": os.cpu_count(),
+                             "why_one_core": "the reference path is single-threaded (no OpenMP pragma, no RcppParallel: SURVEY.md 0)"},
             "e2e": {"value": val, "unit": "bin-states/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "em_iterations_per_s": args.steps / dt}
     print(json.dumps(line))
 
 
-def config_dict(n_gpus, reference=False):
-    c = {"workload": "BASELINE configs[1]: synthetic human genome 200 bp bins, consensus broad-peak calling, "
-                     "one EM iteration per step at fixed theta (SURVEY.md 8d), rejection cut p=0.05",
-         "bins_per_gpu": M_FULL, "samples": N_SAMPLES, "states": K, "seed": SEED,
-         "l2_policy": "inputs larger than L2 (0.72 GB counts+offsets, 1.0 GB of E-step outputs per iteration vs 126 MB L2)",
-         "sharding": "contiguous bin blocks, one per GPU" if n_gpus > 1 else "single GPU"}
-    if reference:
-        c["cpu_sample_bins"] = CPU_SAMPLE_BINS
-    return c
+# ---- GPU arm ------------------------------------------------------------------------------------
+
+def sharded_parity(cfg, E, local, rank, world, dist, Mtot=1 << 20):
+    """Multi-GPU correctness signal inside the bench run (untimed): one step on a global table of Mtot bins
+    cut into one bin block per rank, against the same step on the whole table on rank 0's GPU alone.  Same
+    R stream on both sides; the largest relative difference over (BIC, Q, pi, gamma[, delta], psi) is reported."""
+    from epigrahmm_b200 import sharded
+    from epigrahmm_b200.rng import RState
+    em = host_module("em")
+    d = make_data(cfg, Mtot, cfg["seed"] + 1000)          # every rank generates the same table
+    theta, ctl = theta_of(cfg, d), control_of(cfg)
+    lo, hi = rank * Mtot // world, (rank + 1) * Mtot // world
+    ss = sharded.ShardedSession("parity", hi - lo, cfg["K"], local, dist)
+    ss.set_data(np.asfortranarray(d["counts"][lo:hi]), np.asfortranarray(d["offsets"][lo:hi]))
+    if cfg["model"] == "differential":
+        ss.set_design(d["design"])
+    sharded.global_groups_device(ss.local, ss.comm, ss.m0, ss.Mtot, design=d.get("design"))
+    ss.rng_set_state(RState(7).state)
+    a = em_step(ss, cfg, theta, ctl)
+    state_a = ss.rng_get_state()
+    ss.close()
+    if rank != 0:
+        return None
+    with E.Session("parity1", Mtot, cfg["K"], local) as s1:
+        s1.set_data(d["counts"], d["offsets"])
+        if cfg["model"] == "differential":
+            s1.set_design(d["design"])
+        s1.build_groups()
+        s1.rng_set_state(RState(7).state)
+        b = em_step(s1, cfg, theta, ctl)
+        state_b = s1.rng_get_state()
+    va = np.concatenate([em.unlist(a), [a["bic"], a["q"]]])
+    vb = np.concatenate([em.unlist(b), [b["bic"], b["q"]]])
+    return {"bins": Mtot, "blocks": world, "max_rel_diff": float(np.max(np.abs(va - vb) / np.maximum(np.abs(vb), 1e-300))),
+            "same_rng_state_after": bool(np.array_equal(state_a, state_b)), "bic_sharded": float(a["bic"]), "bic_unsharded": float(b["bic"])}
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--bins", type=int, default=M_FULL, help="bins per GPU (default: the configs[1] size)")
+    ap.add_argument("--config", default="c3", choices=sorted(CONFIGS))
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--bins", type=int, default=0, help="bins per GPU (default: from --config / --scaling)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="device-resident arm only (profiling runs)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    name, cfg = args.config, CONFIGS[args.config]
 
     if args.impl == "reference":
         if rank == 0:
-            run_reference(args)
+            run_reference(args, name, cfg)
         return
 
     # libraries (NCCL's version banner, ...) may write to fd 1: keep it for the one JSON line
@@ -260,7 +389,7 @@ def main():
     os.dup2(2, 1)
     import torch
     import epigrahmm_b200 as E
-    from epigrahmm_b200 import em, synth
+    from epigrahmm_b200.rng import RState
     if args.warmup < 3:
         args.warmup = 3
     torch.cuda.set_device(local)
@@ -268,24 +397,37 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    M = args.bins
-    th = synth.THETA_CONSENSUS
-    theta = dict(pi=th["pi"], gamma=th["gamma"], psi=th["psi"])
-    ctl = em.controlEM()
+    scaling = "strong" if name == "c5" else args.scaling
+    M = args.bins or block_of(cfg, world, scaling)
+    K, N = cfg["K"], cfg["N"]
+    diff = cfg["model"] == "differential"
+    # every rank draws its own block of the chain (block r of a global table of world * M bins)
+    d = make_data(cfg, M, cfg["seed"] + rank)
+    theta, ctl = theta_of(cfg, d), control_of(cfg)
+    B = d.get("B", 0)
+    keep = []
+    for k in ("counts", "offsets"):
+        d[k], t = pin(d[k])
+        keep.append(t)
 
     if world > 1:
         from epigrahmm_b200 import sharded
         s = sharded.ShardedSession("bench", M, K, local, dist)
-        d = synth.make_consensus(M, N_SAMPLES, SEED + rank)
-        # one dt$Group dictionary for the whole sharded table
-        g = sharded.global_groups(d["counts"], d["offsets"], s.comm, s.m0, s.Mtot)
-        d, g = pin_workload(d, g)
     else:
-        d, g = make_workload(M, N_SAMPLES, SEED + rank, pinned=True)
         s = E.Session("bench", M, K, local)
     s.set_data(d["counts"], d["offsets"])
-    s.set_groups(g["group"], g["u_chip"], g["u_offsets"])
-    s.rng_set_state(__import__("epigrahmm_b200.rng", fromlist=["RState"]).RState(SEED).state)
+    if diff:
+        s.set_design(d["design"])
+    # dt$Group / dtUnique: built on the device; a sharded table gets ONE dictionary (same numbering as unsharded)
+    t0 = time.perf_counter()
+    if world > 1:
+        sharded.global_groups_device(s.local, s.comm, s.m0, s.Mtot, design=d.get("design"))
+    else:
+        s.build_groups()
+        s.sync()
+    g = None
+    group_build_s = time.perf_counter() - t0
+    s.rng_set_state(RState(cfg["seed"]).state)
     stream = torch.cuda.ExternalStream(s.stream, device=torch.device("cuda", local))
 
     def barrier():
@@ -294,17 +436,18 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(nsteps, upload, p=None, pipelined=False):
+    def timed(nsteps, form=None, p=P_CUT):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         e0.record(stream)
         t0 = time.perf_counter()
         out = None
-        if pipelined:   # every upload is issued inside the timed region; the first one is not overlapped
-            s.prefetch_groups(upload[1].get("group16", upload[1]["group"]))
+        if form == "pipelined":   # every upload is issued inside the timed region; the first one is not overlapped
+            s.prefetch_groups(g.get("group16", g["group"]))
         for k in range(nsteps):
-            up = upload if not pipelined else tuple(upload) + (k + 1 < nsteps,)
-            out = em_iteration(s, theta, ctl, N_SAMPLES * 1, upload=up, p=p)
+            if form is not None:
+                upload(s, cfg, d, g, "encoded" if (form == "pipelined" and k + 1 == nsteps) else form)
+            out = em_step(s, cfg, theta, ctl, p)
         e1.record(stream)
         barrier()
         wall = time.perf_counter() - t0
@@ -317,102 +460,122 @@ def main():
 
     # ---- device-resident arm ----
     for _ in range(args.warmup):
-        em_iteration(s, theta, ctl, N_SAMPLES)
+        em_step(s, cfg, theta, ctl)
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
     s.profile(True)
-    ms, wall, out = timed(args.steps, None)
+    ms, wall, out = timed(args.steps)
     prof = s.profile_read()
     s.profile(False)
     clk = clocks.stop() if rank == 0 else None
-    # the first EM iteration's regime (rejectionCut = 0.9: most bins are thinned, ~M uniforms per state)
-    n09 = max(3, min(args.steps, 10))
-    for _ in range(2):
-        em_iteration(s, theta, ctl, N_SAMPLES, p=0.9)
-    ms_p09, _, _ = timed(n09, None, p=0.9)
+    # the first EM iteration's regime (rejectionCut = 0.9: most bins are thinned, ~M uniforms per column)
+    n09 = max(3, min(args.steps, 5))
+    em_step(s, cfg, theta, ctl, 0.9)
+    ms_p09, _, _ = timed(n09, p=0.9)
+
     # ---- end-to-end arm: host buffers through the C ABI every step ----
-    # (a) the table as the reference holds it (counts, offsets, Group); (b) dictionary-encoded
-    # (Group + dtUnique), which is all the device needs
-    for _ in range(2):
-        em_iteration(s, theta, ctl, N_SAMPLES, upload=(d, g, False))
-    ms_raw, _, _ = timed(args.steps, (d, g, False))
-    for _ in range(2):
-        em_iteration(s, theta, ctl, N_SAMPLES, upload=(d, g, True))
-    ms_seq, _, _ = timed(args.steps, (d, g, True))
-    # the same with the next step's upload overlapping the current step's iteration (ehmm_prefetch_groups);
-    # untimed warm-up first (it allocates the two staging buffers)
-    timed(3, (d, g, True), pipelined=True)
-    ms_e2e, wall_e2e, _ = timed(args.steps, (d, g, True), pipelined=True)
+    e2e = None
+    if not args.no_e2e:
+        # the dictionary-encoded forms need dt$Group / dtUnique on the host: fetched ONCE per fit, outside the timer
+        t0 = time.perf_counter()
+        if g is None:
+            g = s.groups_fetch()
+        if g["G"] < 65536:
+            g["group16"] = g["group"].astype(np.uint16)
+        gk = "group16" if "group16" in g else "group"
+        g[gk], t = pin(np.asfortranarray(g[gk]))
+        keep.append(t)
+        encode_s = time.perf_counter() - t0
+        res = {}
+        forms = ["table", "encoded", "pipelined"] if world == 1 else ["encoded", "pipelined"]
+        for form in forms:
+            timed(2, form)            # untimed warm-up (allocates the staging buffers)
+            res[form] = timed(args.steps, form)[0]
+        h2d_table = d["counts"].nbytes + d["offsets"].nbytes
+        h2d_enc = g[gk].nbytes + g["u_chip"].nbytes + g["u_offsets"].nbytes + (g["u_dsg"].nbytes if g.get("u_dsg") is not None else 0)
+        e2e = dict(res=res, h2d_table=h2d_table, h2d_enc=h2d_enc, encode_s=encode_s, head="table" if world == 1 else "encoded")
+
+    # ---- N > 1: the same global table sharded over the ranks against unsharded on one GPU ----
+    parity = sharded_parity(cfg, E, local, rank, world, dist) if world > 1 else None
 
     if rank != 0:
+        s.close()
         if dist is not None:
             dist.destroy_process_group()
         return
 
     units = M * K * world * args.steps
     value = units / (ms * 1e-3)
-    e2e_value = units / (ms_e2e * 1e-3)
     launches = sum(c for c, _ in prof.values())
-    dom = max(prof.items(), key=lambda kv: kv[1][1])
     pk = peaks()
     peak_gbs = pk["hbm_gbs"] if pk else 6650.0
+    AB = algo_bytes(cfg, B)
+    kernels = {}
+    for kname, (cnt, tms) in sorted(prof.items(), key=lambda kv: -kv[1][1]):
+        if cnt:
+            kk = {"launches_per_step": cnt / args.steps, "ms_per_step": tms / args.steps, "avg_launch_ms": tms / cnt}
+            if kname in AB and tms > 0:
+                kk["algorithmic_bytes_per_bin"] = AB[kname]
+                kk["achieved_gbs"] = AB[kname] * M * cnt / (tms * 1e-3) / 1e9
+                kk["frac_of_hbm_peak"] = kk["achieved_gbs"] / peak_gbs
+            kernels[kname] = kk
     roof = None
-    if dom[0] in ALGO_BYTES and dom[1][0] > 0:
-        per_launch = ALGO_BYTES[dom[0]] * M
+    stream_k = [(n, v) for n, v in prof.items() if n in AB and v[0] > 0]
+    if stream_k:
+        dom = max(stream_k, key=lambda kv: kv[1][1])
+        per_launch = AB[dom[0]] * M
         dur_ms = dom[1][1] / dom[1][0]
         ach = per_launch / (dur_ms * 1e-3) / 1e9
         traffic = None
         try:  # DRAM bytes per launch of the same kernel from the committed ncu --set full capture
             tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
-            if tj.get("bins") == M:
-                traffic = tj["traffic_bytes_per_launch"].get(dom[0])
+            ent = tj.get(name, {})
+            if ent.get("bins") == M:
+                traffic = ent["traffic_bytes_per_launch"].get(dom[0])
         except Exception:
             pass
         roof = {"bound": "hbm", "kernel": dom[0], "achieved": ach, "peak": peak_gbs, "unit": "GB/s",
                 "frac": ach / peak_gbs, "traffic": traffic, "peak_source": "measured (MEASURED_PEAKS.json)" if pk else "fallback",
-                "algorithmic_bytes_per_launch": per_launch, "avg_launch_ms": dur_ms,
+                "algorithmic_bytes_per_launch": per_launch, "avg_launch_ms": dur_ms, "launches_per_step": dom[1][0] / args.steps,
                 "share_of_step": dom[1][1] / ms}
-    kernels = {}
-    for name, (cnt, tms) in sorted(prof.items(), key=lambda kv: -kv[1][1]):
-        if cnt:
-            k = {"launches_per_step": cnt / args.steps, "ms_per_step": tms / args.steps}
-            if name in ALGO_BYTES and tms > 0:
-                k["achieved_gbs"] = ALGO_BYTES[name] * M * cnt / (tms * 1e-3) / 1e9
-                k["frac_of_hbm_peak"] = k["achieved_gbs"] / peak_gbs
-            kernels[name] = k
-    h2d_raw = d["counts"].nbytes + d["offsets"].nbytes + g["group"].nbytes + g["u_chip"].nbytes + g["u_offsets"].nbytes
-    h2d = g.get("group16", g["group"]).nbytes + g["u_chip"].nbytes + g["u_offsets"].nbytes
     line = {"metric": METRIC, "value": value, "unit": "bin-states/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_dict(world),
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": scaling,
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_dict(name, cfg, world, M, scaling),
             "em_iterations_per_s": args.steps / (ms * 1e-3), "wall_ms_per_step": 1e3 * wall / args.steps,
-            "clocks": clk, "gpu_launches": launches,
+            "clocks": clk, "gpu_launches": launches, "group_build_once_s": group_build_s,
             "first_iteration_regime": {"rejection_cut": 0.9, "ms_per_step": ms_p09 / n09, "steps": n09,
                                        "value": M * K * world * n09 / (ms_p09 * 1e-3), "unit": "bin-states/s"},
-            "e2e": {"value": e2e_value, "unit": "bin-states/s", "h2d_bytes_per_step": int(h2d) * 1,
-                    "d2h_bytes_per_step": 8 * (2 + 4 + 4 + 2) + 8 * 12, "ms_per_step": ms_e2e / args.steps,
-                    "upload": "dt$Group (uint16 when G < 65536, else int32) + dtUnique from pinned host memory every step (ehmm_set_data_encoded[16]); the copy of step k+1 is started right after step k's table is in place (ehmm_prefetch_groups) and overlaps step k's EM iteration; all uploads are issued inside the timed region",
-                    "unpipelined": {"value": units / (ms_seq * 1e-3), "ms_per_step": ms_seq / args.steps},
-                    "full_table_upload": {"value": units / (ms_raw * 1e-3), "ms_per_step": ms_raw / args.steps,
-                                          "h2d_bytes_per_step": int(h2d_raw),
-                                          "upload": "counts (int32) + offsets (fp64) + Group (int32) every step"}},
             "roofline": roof, "kernels": kernels,
             "result_check": {"bic": out["bic"], "q": out["q"], "pi": list(map(float, out["pi"]))}}
+    if parity is not None:
+        line["result_check"]["sharded_vs_unsharded"] = parity
+    if e2e is not None:
+        res, head = e2e["res"], e2e["head"]
+        d2h = 8 * (K + K * K + 2 + B + 4)
+        forms_out = {}
+        for form, fms in res.items():
+            forms_out[form] = {"value": units / (fms * 1e-3), "ms_per_step": fms / args.steps,
+                               "h2d_bytes_per_step": int(e2e["h2d_table"] if form == "table" else e2e["h2d_enc"])}
+        forms_out["what"] = {
+            "table": "counts (int32) + offsets (fp64) of the long table from pinned host memory every step, dt$Group / dtUnique "
+                     "rebuilt on the device every step (ehmm_set_data + ehmm_build_groups): nothing is prepared outside the timer",
+            "encoded": "dt$Group (uint16 when G < 65536, else int32) + dtUnique every step (ehmm_set_data_encoded[16]); the "
+                       "dictionary itself is built once per fit outside the timer (encode_once_s)",
+            "pipelined": "encoded, and the copy of step k+1 is started right after step k's table is in place "
+                         "(ehmm_prefetch_groups) so that it overlaps step k's iteration; all copies are issued inside the timer"}
+        line["e2e"] = {"value": forms_out[head]["value"], "unit": "bin-states/s", "h2d_bytes_per_step": forms_out[head]["h2d_bytes_per_step"],
+                       "d2h_bytes_per_step": d2h, "ms_per_step": forms_out[head]["ms_per_step"], "form": head,
+                       "forms": forms_out, "encode_once_s": e2e["encode_s"]}
     if not args.no_cpu_baseline and world == 1:
-        from oracle import oracle as O
-        sys.path.insert(0, os.path.join(ROOT, "tests"))
-        from oracle_backend import OracleBackend
-        Ms = min(CPU_SAMPLE_BINS, M)
-        dc = {"counts": np.asfortranarray(d["counts"][:Ms]), "offsets": np.asfortranarray(d["offsets"][:Ms])}
-        gc = synth.make_groups(dc["counts"], dc["offsets"])
-        be = OracleBackend(dc["counts"], dc["offsets"], K, groups=gc, rng=O.RNG.set_seed(SEED))
+        Ms = min(cfg["cpu_bins"], M)
+        be = oracle_backend(cfg, d, Ms)
         t0 = time.perf_counter()
-        em_iteration(be, theta, ctl, N_SAMPLES)
+        em_step(be, cfg, theta, ctl)
         dt = time.perf_counter() - t0
         line["cpu_baseline"] = {"value": Ms * K / dt, "unit": "bin-states/s", "cores": 1, "kind": "port",
-                                "sample": "one EM iteration over the first %d bins of the workload (%.1f s), oracle restatement "
-                                          "of the reference, in memory (no HDF5 round-trips), 1 thread as the reference" % (Ms, dt),
+                                "sample": "one step over the first %d bins of the workload (%.1f s), oracle restatement of the "
+                                          "reference, in memory (no HDF5 round trips), 1 thread as the reference" % (Ms, dt),
                                 "host_cores_available": os.cpu_count()}
     os.write(real_stdout, (json.dumps(line) + "\n").encode())
     s.close()

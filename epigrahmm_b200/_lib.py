@@ -49,9 +49,13 @@ PROTOTYPES = {
     "ehmm_session_set_block": [_sess, C.c_int64, C.c_int64],
     "ehmm_set_data": [_sess, C.c_int, _ip, _dp, _dp],
     "ehmm_set_data_device": [_sess, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p],
+    "ehmm_controls_first": [_sess, _dp],
+    "ehmm_set_controls_first": [_sess, C.c_double],
     "ehmm_set_groups": [_sess, _ip, C.c_int64, _dp, _dp, _dp, _bp],
     "ehmm_build_groups": [_sess, _lp],
     "ehmm_groups_fetch": [_sess, _ip, _dp, _dp, _dp, _bp],
+    "ehmm_groups_first_cell": [_sess, _lp],
+    "ehmm_groups_remap": [_sess, _ip, C.c_int64, _dp, _dp, _dp, _bp],
     "ehmm_set_data_encoded": [_sess, C.c_int, _ip, C.c_int64, _dp, _dp, _dp, _bp],
     "ehmm_set_data_encoded16": [_sess, C.c_int, C.POINTER(C.c_uint16), C.c_int64, _dp, _dp, _dp, _bp],
     "ehmm_prefetch_groups": [_sess, C.c_int, C.c_void_p, C.c_int],
@@ -87,7 +91,8 @@ PROTOTYPES = {
     "ehmm_rc_differential": [_sess, C.c_double, C.c_int, _dp, C.c_int64, _lp],
     "ehmm_rc_count": [_sess, C.c_int, C.c_double, _lp],
     "ehmm_rc_apply_at": [_sess, C.c_int, C.c_double, _lp, C.c_int64],
-    "ehmm_rc_buckets_device": [_sess, C.POINTER(C.c_void_p), _lp],
+    "ehmm_rc_buckets_device": [_sess, C.POINTER(C.c_void_p), _lp, C.POINTER(C.c_int)],
+    "ehmm_rc_finalize": [_sess],
     "ehmm_inner_mstep_sums": [_sess, _dp],
     "ehmm_rc_table_rows": [_sess, C.c_int, _lp],
     "ehmm_rc_table_fetch": [_sess, C.c_int, _dp, _dp],

@@ -68,13 +68,13 @@ enum : unsigned {
 enum KernelId : int {
     KID_EMIS_TAB, KID_EMIS_GATHER, KID_EMIS_CONSENSUS, KID_EMIS_DIFF, KID_EMIS_INNER, KID_INNER_MSTEP,
     KID_FB_REDUCE, KID_FB_CARRY, KID_FB_APPLY, KID_FB_FIX, KID_FB_STATS,
-    KID_RC_COUNT, KID_RC_SCAN, KID_MT, KID_RC_APPLY, KID_GLM, KID_GLM_FINAL,
+    KID_RC_COUNT, KID_RC_SCAN, KID_MT, KID_RC_APPLY, KID_RC_FINAL, KID_GLM, KID_GLM_FINAL,
     KID_VIT_FWD, KID_VIT_BWD, KID_MISC, KID_COUNT
 };
 static const char *const kKernelNames[KID_COUNT] = {
     "emis_tables", "emis_gather", "emis_consensus", "emis_diff_hmm", "emis_inner", "inner_mstep",
     "fb_reduce", "fb_carry", "fb_apply", "fb_boundary_fix", "fb_stats",
-    "rc_count", "rc_scan", "mt_generate", "rc_apply", "glm", "glm_final",
+    "rc_count", "rc_scan", "mt_generate", "rc_apply", "rc_finalize", "glm", "glm_final",
     "viterbi_forward", "viterbi_backtrace", "misc"};
 
 // forward-backward tiling (fb.cu)
@@ -110,9 +110,14 @@ struct ehmm_session {
     const int32_t *d_counts = nullptr;
     const double *d_offsets = nullptr;
     const double *d_controls = nullptr;
+    // controls[1] of the GLOBAL long table (bin 1 of sample 1): the only control the reference's emission
+    // uses (its ifelse() quirk, R/base-loglikelihood.R:113); a bin block with m0 > 0 gets it from block 0
+    double ctrl_first = 0.0;
+    bool have_ctrl_first = false;
     ehmm::DevBuf group;                     // int32 M x N
     ehmm::DevBuf u_chip, u_off, u_ctrl;     // dtUnique columns, index 0..G (0 unused)
     ehmm::DevBuf u_dsg;                     // uint8 (G+1) x B
+    std::vector<int64_t> group_first;       // build_groups: first cell (column-major, local) of groups 1..G
     uint8_t design[EHMM_MAX_B * 64] = {0};  // B x N
     bool have_design = false;
 
@@ -137,6 +142,9 @@ struct ehmm_session {
     uint32_t rng_state[625] = {624};
     bool rng_set = false;
     ehmm::DevBuf rc_flag, rc_scan, rc_buckets, rc_unif, rc_tmp, mt_raw, mt_raw2, mt_windows;
+    ehmm::DevBuf rc_limbs, rc_coltot;  // exact accumulators (2 x u64 per table entry); column totals + error flag
+    bool rc_exact = false;       // the last rejection tables were accumulated as exact limbs ...
+    bool rc_final = false;       // ... and have been rounded into rc_buckets
     int64_t mtj_valid = 0;       // sub-stream windows valid for the state in mt_raw
     bool mtj_pending = false;    // ... being computed on stream2 (event ev)
     bool mtj_base = false;       // window 0 is in place
@@ -235,6 +243,7 @@ int rc_consensus(ehmm_session *s, double p, const double *uniforms, int64_t n_un
 int rc_differential(ehmm_session *s, double p, int N, const double *uniforms, int64_t n_uniforms, int64_t *consumed);
 int rc_count(ehmm_session *s, int differential, double p, int64_t *counts);
 int rc_apply_at(ehmm_session *s, int differential, double p, const int64_t *col_offsets, int64_t total);
+int rc_finalize(ehmm_session *s);
 int rc_table_rows(ehmm_session *s, int column, int64_t *rows);
 int rc_table_fetch(ehmm_session *s, int column, double *sums, double *ids);
 int rc_reweight(int device, double *x, int64_t n, double p, const double *uniforms, int64_t n_uniforms, int64_t *consumed);
@@ -242,6 +251,7 @@ int rc_aggregate(int device, const double *x, int64_t n, const int32_t *f, int64
 // groups.cu
 int build_groups(ehmm_session *s, int64_t *G_out);
 int groups_fetch(ehmm_session *s, int32_t *group, double *u_chip, double *u_off, double *u_ctrl, uint8_t *u_dsg);
+int groups_remap(ehmm_session *s, const int32_t *new_id, int64_t G_new);
 // mtjump.cu
 int mt_generate(ehmm_session *s, int64_t n, uint32_t *out);
 int mt_generate_range(ehmm_session *s, int64_t lo_rel, int64_t n, uint32_t *out);

@@ -18,12 +18,11 @@ constexpr int MAX_DENS = 4;    // distinct (size) values per launch
 
 struct EmisParams {
     double b0[MAX_DENS];     // intercept
-    double b1[MAX_DENS];     // control coefficient (consensus) -- 0 when unused
     double size[MAX_DENS];   // NB size
     double lsize[MAX_DENS];  // log(size)
     double lgs[MAX_DENS];    // lgamma(size)
     double minZero, lminZero, thr;
-    double z0, z1;           // zero-inflation predictor of density 0 (ZINB background): z0 [+ z1*ctrl] + offset
+    double z0;               // zero-inflation predictor of density 0 (ZINB background): z0 + offset
     double zip;              // differential model with dist = 'zinb': constant zero-inflation probability of density 0
     int zi_diff;             // ... and the flag that switches it on
     int tabn;
@@ -77,31 +76,26 @@ __device__ __forceinline__ double dzinb_log(int x, double l, const EmisParams &P
     return log((x == 0 ? P.zip : 0.0) + (1.0 - P.zip) * (exp(l) + P.minZero));
 }
 
-// loglikConsensusHMM: LL[j,k] = sum_i log(NB(y_ji; mu=exp(th_k0 [+ th_k1*ctrl_ji] + o_ji), size_k) + minZero);
+// loglikConsensusHMM: LL[j,k] = sum_i log(NB(y_ji; mu=exp(b_k + o_ji), size_k) + minZero), where
+// b_k = th_k0 [+ th_k1*ctrl_11]: with a controls assay the reference adds theta[2]*controls[1], the
+// control of the table's FIRST cell, to every cell -- its ifelse(useControl, theta[2]*controls, 0) has
+// a length-1 test and so returns one element (R/base-loglikelihood.R:113,119,126-129,137).  That
+// scalar is folded into b_k on the host (emis_consensus), so no kernel reads the controls matrix.
 // ZI: the background state is zero-inflated (dist = 'zinb')
-template <bool CTRL, bool PLUS_MZ, bool ZI = false>
+template <bool PLUS_MZ, bool ZI = false>
 __global__ void __launch_bounds__(EM_NT)
     emis_consensus_kernel(int64_t M, int N, const int32_t *__restrict__ y, const double *__restrict__ off,
-                          const double *__restrict__ ctrl, const __grid_constant__ EmisParams P,
-                          const double *__restrict__ tab, double *__restrict__ LL) {
+                          const __grid_constant__ EmisParams P, const double *__restrict__ tab,
+                          double *__restrict__ LL) {
     for (int64_t j = (int64_t)blockIdx.x * EM_NT + threadIdx.x; j < M; j += (int64_t)gridDim.x * EM_NT) {
         double a0 = 0.0, a1 = 0.0;
         for (int i = 0; i < N; i++) {
             const int64_t c = j + (int64_t)i * M;
             const int x = __ldg(y + c);
             const double o = __ldg(off + c);
-            double e0, e1;
-            if (CTRL) {
-                const double cv = __ldg(ctrl + c);
-                e0 = (P.b0[0] + P.b1[0] * cv) + o;
-                e1 = (P.b0[1] + P.b1[1] * cv) + o;
-            } else {
-                e0 = P.b0[0] + o;
-                e1 = P.b0[1] + o;
-            }
-            double l0 = nb_logpmf(x, e0, 0, P, tab), l1 = nb_logpmf(x, e1, 1, P, tab);
+            double l0 = nb_logpmf(x, P.b0[0] + o, 0, P, tab), l1 = nb_logpmf(x, P.b0[1] + o, 1, P, tab);
             if (PLUS_MZ) { l0 = plus_min_zero(l0, P); l1 = plus_min_zero(l1, P); }
-            if (ZI) l0 = zinb_cell(x, l0, (CTRL ? (P.z0 + P.z1 * __ldg(ctrl + c)) : P.z0) + o);
+            if (ZI) l0 = zinb_cell(x, l0, P.z0 + o);
             a0 += l0;
             a1 += l1;
         }
@@ -116,28 +110,19 @@ __global__ void __launch_bounds__(EM_NT)
 // once per group into a table and each bin gathers them: 4N B/bin of ids instead of 12N B/bin of
 // counts+offsets, and no transcendental work in the M*N stream.  Values are bit-identical to the
 // per-cell kernels (same function of the same inputs, same summation order).
-template <bool CTRL, bool PLUS_MZ, bool ZI = false>
+template <bool PLUS_MZ, bool ZI = false>
 __global__ void __launch_bounds__(EM_NT)
     group_table_consensus_kernel(int64_t G, const double *__restrict__ uy, const double *__restrict__ uoff,
-                                 const double *__restrict__ uctrl, const __grid_constant__ EmisParams P,
-                                 const double *__restrict__ tab, double2 *__restrict__ E) {
+                                 const __grid_constant__ EmisParams P, const double *__restrict__ tab,
+                                 double2 *__restrict__ E) {
     const int64_t g = (int64_t)blockIdx.x * EM_NT + threadIdx.x;
     if (g > G) return;
     if (g == 0) { E[0] = make_double2(0.0, 0.0); return; }
     const int x = (int)uy[g];
     const double o = uoff[g];
-    double e0, e1;
-    if (CTRL) {
-        const double cv = uctrl[g];
-        e0 = (P.b0[0] + P.b1[0] * cv) + o;
-        e1 = (P.b0[1] + P.b1[1] * cv) + o;
-    } else {
-        e0 = P.b0[0] + o;
-        e1 = P.b0[1] + o;
-    }
-    double l0 = nb_logpmf(x, e0, 0, P, tab), l1 = nb_logpmf(x, e1, 1, P, tab);
+    double l0 = nb_logpmf(x, P.b0[0] + o, 0, P, tab), l1 = nb_logpmf(x, P.b0[1] + o, 1, P, tab);
     if (PLUS_MZ) { l0 = plus_min_zero(l0, P); l1 = plus_min_zero(l1, P); }
-    if (ZI) l0 = zinb_cell(x, l0, (CTRL ? (P.z0 + P.z1 * uctrl[g]) : P.z0) + o);
+    if (ZI) l0 = zinb_cell(x, l0, P.z0 + o);
     E[g] = make_double2(l0, l1);
 }
 
@@ -341,9 +326,8 @@ int require_data(ehmm_session *s, const char *who) {
     return EHMM_OK;
 }
 
-void fill_density(EmisParams &P, int d, double b0, double b1, double size) {
+void fill_density(EmisParams &P, int d, double b0, double size) {
     P.b0[d] = b0;
-    P.b1[d] = b1;
     P.size[d] = size;
     P.lsize[d] = log(size);
     P.lgs[d] = lgamma(size);
@@ -406,52 +390,51 @@ void fill_diff(EmisParams &P, const double *psi, int zinb) {
         P.zip = exp(psi[0]) / (1.0 + exp(psi[0]));
         psi += 1;
     }
-    fill_density(P, 0, psi[0], 0.0, exp(psi[1]));
-    fill_density(P, 1, psi[0] + psi[2], 0.0, exp(psi[1] + psi[3]));
+    fill_density(P, 0, psi[0], exp(psi[1]));
+    fill_density(P, 1, psi[0] + psi[2], exp(psi[1] + psi[3]));
 }
 
 }  // namespace
 
 namespace {
-template <bool CTRL, bool ZI> int launch_consensus(ehmm_session *s, const EmisParams &P) {
+template <bool ZI> int launch_consensus(ehmm_session *s, const EmisParams &P) {
     const int g = grid_for(s->M);
     if (use_groups(s, 2)) {
         EHMM_TRY(s->gtab.reserve(sizeof(double2) * (size_t)(s->G + 1)));
         const unsigned gb = (unsigned)((s->G + 1 + EM_NT - 1) / EM_NT);
-        PROF(s, KID_EMIS_TAB), group_table_consensus_kernel<CTRL, true, ZI><<<gb, EM_NT, 0, s->stream>>>(
-            s->G, s->u_chip.as<double>(), s->u_off.as<double>(), CTRL ? s->u_ctrl.as<double>() : nullptr, P,
-            s->lgtab.as<double>(), s->gtab.as<double2>());
+        PROF(s, KID_EMIS_TAB), group_table_consensus_kernel<true, ZI><<<gb, EM_NT, 0, s->stream>>>(
+            s->G, s->u_chip.as<double>(), s->u_off.as<double>(), P, s->lgtab.as<double>(), s->gtab.as<double2>());
         EHMM_CK(cudaGetLastError());
         PROF(s, KID_EMIS_GATHER), gather_consensus_kernel<<<g, EM_NT, 0, s->stream>>>(
             s->M, s->N, s->group.as<int32_t>(), s->gtab.as<double2>(), s->logf.as<double>());
         EHMM_CK(cudaGetLastError());
         return EHMM_OK;
     }
-    PROF(s, KID_EMIS_CONSENSUS), emis_consensus_kernel<CTRL, true, ZI><<<g, EM_NT, 0, s->stream>>>(
-        s->M, s->N, s->d_counts, s->d_offsets, CTRL ? s->d_controls : nullptr, P, s->lgtab.as<double>(), s->logf.as<double>());
+    PROF(s, KID_EMIS_CONSENSUS), emis_consensus_kernel<true, ZI><<<g, EM_NT, 0, s->stream>>>(
+        s->M, s->N, s->d_counts, s->d_offsets, P, s->lgtab.as<double>(), s->logf.as<double>());
     EHMM_CK(cudaGetLastError());
     return EHMM_OK;
 }
 }  // namespace
 
 // zi == nullptr: NB (th1 = (beta0[, beta_ctrl], size)); else zi = (lambda0[, lambda_ctrl]) of the
-// zero-inflated background (R/base-loglikelihood.R:123-141)
+// zero-inflated background (R/base-loglikelihood.R:123-141).
+// With controls (P_ == 3) every linear predictor gets coefficient * controls[1] -- the control of the
+// first cell of the whole long table (s->ctrl_first), not the cell's own: see emis_consensus_kernel.
 int emis_consensus(ehmm_session *s, const double *th1, const double *th2, int P_, double minZero, const double *zi) {
     EHMM_TRY(require_data(s, "loglikConsensusHMM"));
     EHMM_REQUIRE(s->K == 2, EHMM_ERR_ARG, "loglikConsensusHMM needs a K=2 session (K=%d)", s->K);
     EHMM_REQUIRE(P_ == 2 || P_ == 3, EHMM_ERR_ARG, "P must be 2 (beta0,size) or 3 (beta0,beta_ctrl,size)");
-    EHMM_REQUIRE(P_ == 2 || s->d_controls || (s->encoded && s->encoded_ctrl), EHMM_ERR_STATE, "P=3 needs a controls matrix");
+    EHMM_REQUIRE(P_ == 2 || s->have_ctrl_first, EHMM_ERR_STATE, "P=3 needs a controls matrix");
+    const double c1 = s->ctrl_first;
     EmisParams P = {};
-    fill_density(P, 0, th1[0], P_ == 3 ? th1[1] : 0.0, th1[P_ - 1]);
-    fill_density(P, 1, th2[0], P_ == 3 ? th2[1] : 0.0, th2[P_ - 1]);
-    if (zi) {
-        P.z0 = zi[0];
-        P.z1 = P_ == 3 ? zi[1] : 0.0;
-    }
+    // R evaluates theta[1] + theta[2]*controls[1] first and adds the offsets to that sum
+    fill_density(P, 0, P_ == 3 ? th1[0] + th1[1] * c1 : th1[0], th1[P_ - 1]);
+    fill_density(P, 1, P_ == 3 ? th2[0] + th2[1] * c1 : th2[0], th2[P_ - 1]);
+    if (zi) P.z0 = P_ == 3 ? zi[0] + zi[1] * c1 : zi[0];
     EHMM_TRY(prepare_tab(s, P, 2, minZero));
     EHMM_TRY(s->logf.reserve(sizeof(double) * s->M * 2));
-    if (P_ == 3) EHMM_TRY(zi ? (launch_consensus<true, true>(s, P)) : (launch_consensus<true, false>(s, P)));
-    else EHMM_TRY(zi ? (launch_consensus<false, true>(s, P)) : (launch_consensus<false, false>(s, P)));
+    EHMM_TRY(zi ? launch_consensus<true>(s, P) : launch_consensus<false>(s, P));
     s->valid |= DS_LOGF;
     return EHMM_OK;
 }
@@ -461,15 +444,15 @@ int emis_init(ehmm_session *s, const double *psi1, const double *psi2) {
     EHMM_REQUIRE(s->K == 2 && s->N == 1, EHMM_ERR_ARG, "the initializer supports one sample and K=2 (N=%d, K=%d)",
                  s->N, s->K);
     EmisParams P = {};
-    fill_density(P, 0, psi1[0], 0.0, psi1[1]);
-    fill_density(P, 1, psi2[0], 0.0, psi2[1]);
+    fill_density(P, 0, psi1[0], psi1[1]);
+    fill_density(P, 1, psi2[0], psi2[1]);
     EHMM_TRY(prepare_tab(s, P, 2, 2.2250738585072014e-308));
     EHMM_TRY(s->logf.reserve(sizeof(double) * s->M * 2));
     if (use_groups(s, 2)) {
         EHMM_TRY(s->gtab.reserve(sizeof(double2) * (size_t)(s->G + 1)));
         const unsigned gb = (unsigned)((s->G + 1 + EM_NT - 1) / EM_NT);
-        PROF(s, KID_EMIS_TAB), group_table_consensus_kernel<false, false><<<gb, EM_NT, 0, s->stream>>>(
-            s->G, s->u_chip.as<double>(), s->u_off.as<double>(), nullptr, P, s->lgtab.as<double>(), s->gtab.as<double2>());
+        PROF(s, KID_EMIS_TAB), group_table_consensus_kernel<false><<<gb, EM_NT, 0, s->stream>>>(
+            s->G, s->u_chip.as<double>(), s->u_off.as<double>(), P, s->lgtab.as<double>(), s->gtab.as<double2>());
         EHMM_CK(cudaGetLastError());
         PROF(s, KID_EMIS_GATHER), gather_consensus_kernel<<<grid_for(s->M), EM_NT, 0, s->stream>>>(
             s->M, 1, s->group.as<int32_t>(), s->gtab.as<double2>(), s->logf.as<double>());
@@ -477,8 +460,8 @@ int emis_init(ehmm_session *s, const double *psi1, const double *psi2) {
         s->valid |= DS_LOGF;
         return EHMM_OK;
     }
-    PROF(s, KID_EMIS_CONSENSUS), emis_consensus_kernel<false, false><<<grid_for(s->M), EM_NT, 0, s->stream>>>(
-        s->M, 1, s->d_counts, s->d_offsets, nullptr, P, s->lgtab.as<double>(), s->logf.as<double>());
+    PROF(s, KID_EMIS_CONSENSUS), emis_consensus_kernel<false><<<grid_for(s->M), EM_NT, 0, s->stream>>>(
+        s->M, 1, s->d_counts, s->d_offsets, P, s->lgtab.as<double>(), s->logf.as<double>());
     EHMM_CK(cudaGetLastError());
     s->valid |= DS_LOGF;
     return EHMM_OK;

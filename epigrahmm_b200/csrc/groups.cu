@@ -219,9 +219,34 @@ int build_groups(ehmm_session *s, int64_t *G_out) {
     EHMM_CK(cudaStreamSynchronize(s->stream));
     EHMM_REQUIRE(hf == 0, EHMM_ERR_STATE, "build_groups: 64-bit key-hash collision detected; group the table on the host instead");
     s->G = (int64_t)G;
+    s->group_first.assign(firstsorted.begin(), firstsorted.end());
     s->groups_consistent = true;
     s->rc_columns = 0;
     if (G_out) *G_out = (int64_t)G;
+    return EHMM_OK;
+}
+
+namespace {
+__global__ void grp_remap_kernel(int64_t n, const int32_t *__restrict__ map, int32_t *__restrict__ group) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        group[i] = map[group[i]];
+}
+}  // namespace
+
+int groups_remap(ehmm_session *s, const int32_t *new_id, int64_t G_new) {
+    EHMM_REQUIRE(s->G > 0 && s->group.p, EHMM_ERR_STATE, "groups_remap: no groups");
+    std::vector<int32_t> map((size_t)s->G + 1, 0);
+    for (int64_t g = 0; g < s->G; g++) {
+        EHMM_REQUIRE(new_id[g] >= 1 && new_id[g] <= G_new, EHMM_ERR_ARG, "groups_remap: new id %d of group %lld outside [1, %lld]",
+                     new_id[g], (long long)(g + 1), (long long)G_new);
+        map[(size_t)g + 1] = new_id[g];
+    }
+    EHMM_TRY(s->rc_tmp.reserve(sizeof(int32_t) * map.size()));
+    EHMM_CK(cudaMemcpyAsync(s->rc_tmp.p, map.data(), sizeof(int32_t) * map.size(), cudaMemcpyHostToDevice, s->stream));
+    PROF(s, KID_MISC), grp_remap_kernel<<<148 * 8, 256, 0, s->stream>>>(s->M * s->N, s->rc_tmp.as<int32_t>(), s->group.as<int32_t>());
+    EHMM_CK(cudaGetLastError());
+    EHMM_CK(cudaStreamSynchronize(s->stream));  // `map` is pageable host memory
+    s->group_first.clear();
     return EHMM_OK;
 }
 

@@ -4,23 +4,45 @@
 // R's global Mersenne-Twister).
 //
 // The r-th bin (state-major, then ascending bin) whose posterior weight x satisfies 0 < x < p
-// consumes the r-th uniform of the stream.  That order is recovered with a stream compaction:
-//   rc_count_kernel : flags per (column, block)                      (reads 8 B/bin/column)
-//   rc_scan_kernel  : exclusive scan of the block counts (column-major) -> uniform offsets
-//   rc_apply_kernel : in-block ranks, Bernoulli thinning exactly as R's rbinom(1, x/p), and
-//                     scatter-add of the surviving weights into the group buckets
+// consumes the r-th uniform of the stream.  That order is recovered with a stream compaction whose
+// unit is a WARP TILE of 256 consecutive bins (8 strips of 32), so ranks come from ballots alone --
+// no shared memory, no block barrier -- and every warp walks ALL columns of its bins (the first
+// version gave every column its own CTAs; the background column, which keeps a weight in almost
+// every bin, then ran on 1/columns of the machine):
+//   rc_count_kernel : flagged weights per (column, warp tile)
+//   rc_scan_kernel  : one CTA per column, exclusive scan of its tile counts -> offsets, column total
+//   rc_apply_kernel : ranks, Bernoulli thinning exactly as R's rbinom(1, x/p), and the sum of the
+//                     surviving weights by group
+//   rc_finalize_kernel : exact accumulators -> the fp64 tables the NB-GLM kernels read
+//
+// Sums by group are EXACT and therefore independent of the order in which the hardware performs
+// them: a weight w in [2^-9, 2) is the integer w * 2^62, which is split into two 31-bit limbs that
+// are added with native 64-bit integer atomics (REDG.E.ADD.64; 33 bits of headroom per limb, i.e.
+// 8e9 addends).  The table entry is that integer rounded once to fp64: bit-identical from run to
+// run, for any bin-block sharding (the limbs of all blocks are added before the rounding) and at
+// most half an ulp from the true sum -- the reference's own in-order fp64 sum
+// (src/aggregate.cpp:23-30) carries up to n roundings.  Every weight that survives a rejection cut
+// p >= 2^-9 qualifies (it is p itself or a posterior >= p; the reference's rejectionCut is
+// max(0.9^iter, probCut), probCut = 0.05 by default); for smaller cuts (and p = 0: no thinning,
+// which controlEM() cannot produce) the kernel falls back to fp64 atomics, whose result depends on
+// the order of the additions in the last bits.
 // Uniforms come either from a caller-supplied buffer (parity harness: the oracle consumes the same
 // buffer) or from R's MT19937 stream generated on the device from the session's .Random.seed.
 #include "common.cuh"
+#include <algorithm>
 #include <vector>
 
 namespace ehmm {
 
 namespace {
 
-constexpr int RC_NT = 256;
+constexpr int RC_NT = 256;                  // threads per CTA
+constexpr int RC_NW = RC_NT / 32;           // warps = warp tiles per CTA
 constexpr int RC_STRIPS = 8;
-constexpr int RC_TB = RC_NT * RC_STRIPS;  // bins per block
+constexpr int RC_WT = 32 * RC_STRIPS;       // bins per warp tile
+constexpr int RC_TB = RC_NT * RC_STRIPS;    // bins per block of the exported reweight() helper
+constexpr int RC_MAXCOL = EHMM_MAX_B + 2;   // 64
+constexpr double RC_EXACT_MIN_P = 0.001953125;  // 2^-9: smallest cut whose survivors are exact 62-bit fixed-point numbers
 
 // ---- R's unif_rand() (Mersenne-Twister) ------------------------------------------------------
 // MT_genrand() * 2^-32 followed by fixup() into (0,1)
@@ -42,44 +64,59 @@ struct RCSrc {
     int B;         // 0 = consensus
     int columns;
 };
+struct RCBase {
+    int64_t ubase[RC_MAXCOL];  // where the draws of each column start in the uniform buffer
+};
 
-__device__ __forceinline__ double rc_weight(const RCSrc &S, int c, int64_t j) {
-    if (S.B == 0) return exp(__ldg(S.lp1 + (int64_t)c * S.M + j));
-    if (c == 0) return exp(__ldg(S.lp1 + j));
-    if (c == S.B + 1) return exp(__ldg(S.lp1 + 2 * S.M + j));
-    return exp(__ldg(S.lp1 + S.M + j)) * __ldg(S.eta + (int64_t)(c - 1) * S.M + j);
+// posteriors of bin j (exp once per bin; the count and the apply kernel must see the same bits, so
+// both go through these two functions and nothing here can contract into an FMA)
+template <bool DIFF> __device__ __forceinline__ void rc_posteriors(const RCSrc &S, int64_t j, double (&p1)[3]) {
+    p1[0] = exp(__ldg(S.lp1 + j));
+    p1[1] = exp(__ldg(S.lp1 + S.M + j));
+    p1[2] = DIFF ? exp(__ldg(S.lp1 + 2 * S.M + j)) : 0.0;
 }
+template <bool DIFF> __device__ __forceinline__ double rc_weight(const RCSrc &S, const double (&p1)[3], int c, int64_t j) {
+    if (!DIFF) return c == 0 ? p1[0] : p1[1];
+    if (c == 0) return p1[0];
+    if (c == S.B + 1) return p1[2];
+    return __dmul_rn(p1[1], __ldg(S.eta + (int64_t)(c - 1) * S.M + j));
+}
+__device__ __forceinline__ bool rc_flagged(double x, double p) { return x < p && x / p != 0.0; }
 
-__global__ void __launch_bounds__(RC_NT) rc_count_kernel(RCSrc S, double p, int64_t nblk, int *__restrict__ counts) {
-    __shared__ int sh[RC_NT / 32];
-    const int c = blockIdx.y;
-    const int64_t base = (int64_t)blockIdx.x * RC_TB;
-    int cnt = 0;
-#pragma unroll
+// lane (c & 31) of the warp keeps the running count of column c (two registers cover 64 columns)
+template <bool DIFF>
+__global__ void __launch_bounds__(RC_NT) rc_count_kernel(RCSrc S, double p, int64_t nwt, int *__restrict__ counts) {
+    const int lane = threadIdx.x & 31;
+    const int64_t tile = (int64_t)blockIdx.x * RC_NW + (threadIdx.x >> 5);
+    if (tile >= nwt) return;
+    int cnt0 = 0, cnt1 = 0;
+#pragma unroll 1
     for (int r = 0; r < RC_STRIPS; r++) {
-        const int64_t j = base + r * RC_NT + threadIdx.x;
-        if (j < S.M) {
-            const double x = rc_weight(S, c, j);
-            cnt += (x < p && x / p != 0.0) ? 1 : 0;
+        const int64_t j = tile * RC_WT + r * 32 + lane;
+        const bool valid = j < S.M;
+        double p1[3] = {2.0, 2.0, 2.0};  // 2.0: never below p <= 1
+        if (valid) rc_posteriors<DIFF>(S, j, p1);
+#pragma unroll 1
+        for (int c = 0; c < S.columns; c++) {
+            const double x = valid ? rc_weight<DIFF>(S, p1, c, j) : 2.0;
+            const int n = __popc(__ballot_sync(0xffffffffu, rc_flagged(x, p)));
+            if (lane == (c & 31)) { if (c < 32) cnt0 += n; else cnt1 += n; }
         }
     }
-    for (int d = 16; d > 0; d >>= 1) cnt += __shfl_down_sync(0xffffffffu, cnt, d);
-    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = cnt;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int t = 0;
-        for (int i = 0; i < RC_NT / 32; i++) t += sh[i];
-        counts[(int64_t)c * nblk + blockIdx.x] = t;
-    }
+    if (lane < S.columns) counts[(int64_t)lane * nwt + tile] = cnt0;
+    if (lane + 32 < S.columns) counts[(int64_t)(lane + 32) * nwt + tile] = cnt1;
 }
 
-// exclusive scan of n ints into int64 offsets; offsets[n] = total.  One CTA; each thread owns 16
-// consecutive counts per round (warp-shuffle scan of the thread sums, then the warp sums).
-__global__ void __launch_bounds__(1024) rc_scan_kernel(const int *__restrict__ counts, int64_t n,
-                                                       int64_t *__restrict__ offsets) {
+// one CTA per column: exclusive scan of the column's n tile counts -> offsets (uint32: a column of one
+// bin block holds < 2^32 bins), coltot[column] = the column's total.  Each thread owns 16 consecutive
+// counts per round (warp-shuffle scan of the thread sums, then of the warp sums).
+__global__ void __launch_bounds__(1024) rc_scan_kernel(const int *__restrict__ counts_all, int64_t n,
+                                                       uint32_t *__restrict__ offsets_all, int64_t *__restrict__ coltot) {
     constexpr int IT = 16;
     __shared__ int64_t swarp[32];
     __shared__ int64_t carry;
+    const int *counts = counts_all + (int64_t)blockIdx.x * n;
+    uint32_t *offsets = offsets_all + (int64_t)blockIdx.x * n;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     if (threadIdx.x == 0) carry = 0;
     __syncthreads();
@@ -113,11 +150,37 @@ __global__ void __launch_bounds__(1024) rc_scan_kernel(const int *__restrict__ c
         int64_t run = carry + (w > 0 ? swarp[w - 1] : 0) + (incl - tsum);
 #pragma unroll
         for (int k = 0; k < IT; k++) {
-            if (i0 + k < n) offsets[i0 + k] = run;
+            if (i0 + k < n) offsets[i0 + k] = (uint32_t)run;
             run += v[k];
         }
         __syncthreads();
         if (threadIdx.x == 0) carry += swarp[31];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) coltot[blockIdx.x] = carry;
+}
+
+// exclusive scan of n ints into int64 offsets; offsets[n] = total (the exported reweight() helper)
+__global__ void __launch_bounds__(1024) rw_scan_kernel(const int *__restrict__ counts, int64_t n,
+                                                       int64_t *__restrict__ offsets) {
+    __shared__ int64_t sh[1024];
+    __shared__ int64_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int64_t base = 0; base < n; base += 1024) {
+        const int64_t i = base + threadIdx.x;
+        const int64_t v = (i < n) ? counts[i] : 0;
+        sh[threadIdx.x] = v;
+        __syncthreads();
+        for (int d = 1; d < 1024; d <<= 1) {
+            const int64_t t = ((int)threadIdx.x >= d) ? sh[threadIdx.x - d] : 0;
+            __syncthreads();
+            sh[threadIdx.x] += t;
+            __syncthreads();
+        }
+        if (i < n) offsets[i] = carry + sh[threadIdx.x] - v;
+        __syncthreads();
+        if (threadIdx.x == 0) carry += sh[1023];
         __syncthreads();
     }
     if (threadIdx.x == 0) offsets[n] = carry;
@@ -139,79 +202,94 @@ template <> __device__ __forceinline__ double get_unif<uint32_t>(const uint32_t 
     return mt_to_unif(__ldg(u + i));
 }
 
+// exact accumulation: w * 2^62 (an integer for w in [2^-9, 2)) as two 31-bit limbs in 64-bit words
+__device__ __forceinline__ void limb_add(unsigned long long *L, double w) {
+    const unsigned long long v = __double2ull_rz(w * 4611686018427387904.0);
+    atomicAdd(L, v & 0x7fffffffull);
+    atomicAdd(L + 1, v >> 31);
+}
+
 // nrep = 1 for the consensus model (only f[0..M-1] is read, Q6 in SURVEY.md); nrep = N for the
 // differential model (repmat(w, N, 1) against the M*N group ids).
-// Each thread owns RC_STRIPS consecutive bins, so ranks inside a tile come from one warp scan and
-// one block barrier; the weight loads of a warp still cover one contiguous 2 KB span.
-// Group ids are numbered by first appearance (data.table .GRP), so small ids are the frequent
-// (count, offset) combinations: ids < RC_HOT accumulate in a shared-memory histogram of a persistent
-// CTA (flushed once at the end) and only the long tail goes to global atomics.
-constexpr int RC_HOT = 4096;
-
-template <typename UT>
+// EXACT: integer limbs (acc = limbs, 2 words per (column, group)); else fp64 atomics (acc = buckets).
+template <bool DIFF, typename UT, bool EXACT>
 __global__ void __launch_bounds__(RC_NT)
-    rc_apply_kernel(RCSrc S, double p, int64_t nblk, const int64_t *__restrict__ offsets, const UT *__restrict__ unif,
-                    const int32_t *__restrict__ group, int nrep, int64_t G, double *__restrict__ buckets,
-                    double *__restrict__ wout) {
-    __shared__ double hot[RC_HOT];
-    __shared__ int sh[RC_NT / 32];
-    const int c = blockIdx.y;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    double *bk = buckets + (int64_t)c * (G + 1);
-    for (int i = threadIdx.x; i < RC_HOT; i += RC_NT) hot[i] = 0.0;
-    __syncthreads();
-    for (int64_t blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
-        const int64_t j0 = blk * RC_TB + (int64_t)threadIdx.x * RC_STRIPS;
-        double x[RC_STRIPS];
-        unsigned flags = 0;
-#pragma unroll
-        for (int r = 0; r < RC_STRIPS; r++) {
-            const int64_t j = j0 + r;
-            x[r] = (j < S.M) ? rc_weight(S, c, j) : 2.0;  // 2.0: never below p <= 1, never stored
-            if (x[r] < p && x[r] / p != 0.0) flags |= 1u << r;
-        }
-        const int cnt = __popc(flags);
-        int incl = cnt;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += t;
-        }
-        if (lane == 31) sh[w] = incl;
-        __syncthreads();
-        int before = incl - cnt;
-        for (int i = 0; i < w; i++) before += sh[i];
-        int64_t u = offsets[(int64_t)c * nblk + blk] + before;
-#pragma unroll
-        for (int r = 0; r < RC_STRIPS; r++) {
-            const int64_t j = j0 + r;
-            if (j < S.M) {
-                double wt = x[r];
-                if (wt < p) wt = ((flags >> r) & 1u) ? rbinom1(wt / p, get_unif<UT>(unif, u++)) * p : 0.0;
-                if (wout) wout[(int64_t)c * S.M + j] = wt;
-                if (wt != 0.0) {
-                    for (int i = 0; i < nrep; i++) {
-                        const int g = __ldg(group + j + (int64_t)i * S.M);
-                        if (g < RC_HOT) atomicAdd(&hot[g], wt);
-                        else atomicAdd(bk + g, wt);
-                    }
+    rc_apply_kernel(RCSrc S, double p, int64_t nwt, const uint32_t *__restrict__ tileoff, const __grid_constant__ RCBase ub,
+                    const UT *__restrict__ unif, const int32_t *__restrict__ group, int nrep, int64_t G,
+                    void *__restrict__ acc, const int *__restrict__ counts, int *__restrict__ err) {
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    const int64_t tile = (int64_t)blockIdx.x * RC_NW + (threadIdx.x >> 5);
+    if (tile >= nwt) return;
+    const bool thin = p > 0.0;
+    // lane (c & 31) holds the running rank and the uniform offset of column c (and of column c + 32)
+    int cnt0 = 0, cnt1 = 0;
+    int64_t off0 = 0, off1 = 0;
+    if (thin) {
+        if (lane < S.columns) off0 = ub.ubase[lane] + tileoff[(int64_t)lane * nwt + tile];
+        if (lane + 32 < S.columns) off1 = ub.ubase[lane + 32] + tileoff[(int64_t)(lane + 32) * nwt + tile];
+    }
+#pragma unroll 1
+    for (int r = 0; r < RC_STRIPS; r++) {
+        const int64_t j = tile * RC_WT + r * 32 + lane;
+        const bool valid = j < S.M;
+        double p1[3] = {2.0, 2.0, 2.0};
+        if (valid) rc_posteriors<DIFF>(S, j, p1);
+#pragma unroll 1
+        for (int c = 0; c < S.columns; c++) {
+            double x = valid ? rc_weight<DIFF>(S, p1, c, j) : 2.0;
+            const bool flag = rc_flagged(x, p);
+            const unsigned bal = __ballot_sync(0xffffffffu, flag);
+            if (bal) {
+                const int run = __shfl_sync(0xffffffffu, c < 32 ? cnt0 : cnt1, c & 31);
+                const int64_t base = __shfl_sync(0xffffffffu, c < 32 ? off0 : off1, c & 31);
+                if (flag) x = rbinom1(x / p, get_unif<UT>(unif, base + run + __popc(bal & lt))) * p;
+                if (lane == (c & 31)) { if (c < 32) cnt0 += __popc(bal); else cnt1 += __popc(bal); }
+            }
+            // x < p without a flag is x == 0 (x / p == 0): stays 0
+            if (valid && x != 0.0) {
+                const int64_t row = (int64_t)c * (G + 1);
+                for (int i = 0; i < nrep; i++) {
+                    const int g = __ldg(group + j + (int64_t)i * S.M);
+                    if (EXACT) limb_add(reinterpret_cast<unsigned long long *>(acc) + 2 * (row + g), x);
+                    else atomicAdd(reinterpret_cast<double *>(acc) + row + g, x);
                 }
             }
         }
-        __syncthreads();  // sh[] is reused by the next tile
     }
-    __syncthreads();
-    const int lim = (int)min((int64_t)RC_HOT, G + 1);
-    for (int i = threadIdx.x; i < lim; i += RC_NT)
-        if (hot[i] != 0.0) atomicAdd(bk + i, hot[i]);
+    // the ranks handed out must be the counts the offsets were scanned from
+    if (thin) {
+        bool bad = false;
+        if (lane < S.columns) bad = counts[(int64_t)lane * nwt + tile] != cnt0;
+        if (lane + 32 < S.columns) bad = bad || counts[(int64_t)(lane + 32) * nwt + tile] != cnt1;
+        if (bad) atomicOr(err, 1);
+    }
 }
 
-__global__ void aggregate_kernel(const double *__restrict__ x, int64_t n, const int32_t *__restrict__ f,
-                                 double *__restrict__ buckets) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const double v = x[i];
-        if (v != 0.0) atomicAdd(buckets + f[i], v);
+// limbs -> fp64 table entries: ((hi + carry) * 2^31 + lo) * 2^-62, rounded once (the integer is exact);
+// a rank/count mismatch in the apply kernel poisons the tables instead of leaving them plausible
+__global__ void __launch_bounds__(256) rc_finalize_kernel(const unsigned long long *__restrict__ limbs, int64_t n,
+                                                          double *__restrict__ buckets, const int *__restrict__ err) {
+    const bool bad = err && *err != 0;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+        const unsigned long long lo = limbs[2 * i], hi = limbs[2 * i + 1];
+        const unsigned long long A = hi + (lo >> 31), l = lo & 0x7fffffffull;
+        const double v = __dadd_rn((double)A * 4.656612873077392578125e-10, (double)l * 2.16840434497100886801e-19);
+        buckets[i] = bad ? __longlong_as_double(0x7ff8000000000000ll) : v;
     }
+}
+
+// exported aggregate(): the elements of every group are listed in ascending index order (a stable
+// counting sort done on the host, which has to walk f anyway to validate it) and one thread adds a
+// group's elements in that order -- the order of the reference's loop (src/aggregate.cpp:23-30), so
+// the sums carry the reference's own roundings bit for bit.
+__global__ void aggregate_kernel(const double *__restrict__ x, const int64_t *__restrict__ start,
+                                 const int64_t *__restrict__ perm, int64_t G, double *__restrict__ buckets) {
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g > G) return;
+    double acc = 0.0;
+    for (int64_t k = start[g]; k < start[g + 1]; k++) acc = __dadd_rn(acc, x[perm[k]]);
+    buckets[g] = acc;
 }
 
 // x -> exp-free variant for the exported reweight(): weights are given directly
@@ -265,69 +343,113 @@ __global__ void __launch_bounds__(RC_NT) rw_apply_kernel(double *__restrict__ x,
     }
 }
 
-// persistent CTAs: about four per SM in total (32 KB of shared memory each), split over the columns
-dim3 apply_grid(int64_t nblk, int columns) {
-    int64_t per = (148 * 4 + columns - 1) / columns;
-    if (per > nblk) per = nblk;
-    if (per < 1) per = 1;
-    return dim3((unsigned)per, (unsigned)columns);
+// ---- host side -----------------------------------------------------------------------------------
+inline int64_t num_wtiles(int64_t M) { return (M + RC_WT - 1) / RC_WT; }
+inline unsigned tile_grid(int64_t nwt) { return (unsigned)((nwt + RC_NW - 1) / RC_NW); }
+
+// rc_coltot layout: int64 [RC_MAXCOL] column totals, then one int: rank/count mismatch flag
+inline int *err_flag(ehmm_session *s) { return reinterpret_cast<int *>(s->rc_coltot.as<int64_t>() + RC_MAXCOL); }
+
+int reserve_rc(ehmm_session *s, const RCSrc &S) {
+    const int64_t nwt = num_wtiles(s->M);
+    EHMM_REQUIRE(S.columns <= RC_MAXCOL, EHMM_ERR_ARG, "too many columns (%d)", S.columns);
+    EHMM_REQUIRE(s->M < ((int64_t)1 << 32), EHMM_ERR_ARG, "a bin block holds at most 2^32 bins");
+    EHMM_TRY(s->rc_flag.reserve(sizeof(int) * nwt * S.columns));
+    EHMM_TRY(s->rc_scan.reserve(sizeof(uint32_t) * nwt * S.columns));
+    EHMM_TRY(s->rc_coltot.reserve(sizeof(int64_t) * RC_MAXCOL + 64));
+    EHMM_TRY(s->rc_buckets.reserve(sizeof(double) * (size_t)S.columns * (s->G + 1)));
+    EHMM_TRY(s->rc_limbs.reserve(2 * sizeof(unsigned long long) * (size_t)S.columns * (s->G + 1)));
+    return EHMM_OK;
 }
 
+// phase 1: flagged counts per (column, warp tile), per-column scan; the column totals come to the host
+// (it has to know how many uniforms to generate), which is the call's one synchronisation
+template <bool DIFF> int count_and_scan(ehmm_session *s, const RCSrc &S, double p, int64_t *coltot) {
+    const int64_t nwt = num_wtiles(s->M);
+    if (!(p > 0.0)) {
+        for (int c = 0; c < S.columns; c++) coltot[c] = 0;
+        return EHMM_OK;
+    }
+    PROF(s, KID_RC_COUNT), rc_count_kernel<DIFF><<<tile_grid(nwt), RC_NT, 0, s->stream>>>(S, p, nwt, s->rc_flag.as<int>());
+    EHMM_CK(cudaGetLastError());
+    PROF(s, KID_RC_SCAN), rc_scan_kernel<<<S.columns, 1024, 0, s->stream>>>(s->rc_flag.as<int>(), nwt, s->rc_scan.as<uint32_t>(),
+                                                                           s->rc_coltot.as<int64_t>());
+    EHMM_CK(cudaGetLastError());
+    int64_t *hp = reinterpret_cast<int64_t *>(s->h_pinned + 200);
+    EHMM_CK(cudaMemcpyAsync(hp, s->rc_coltot.p, sizeof(int64_t) * S.columns, cudaMemcpyDeviceToHost, s->stream));
+    EHMM_CK(cudaStreamSynchronize(s->stream));
+    for (int c = 0; c < S.columns; c++) coltot[c] = hp[c];
+    return EHMM_OK;
+}
+
+// phase 2: thin and sum by group.  ub: where each column's draws start in `unif`.
+template <bool DIFF, typename UT>
+int launch_apply(ehmm_session *s, const RCSrc &S, double p, int nrep, const RCBase &ub, const UT *unif) {
+    const int64_t nwt = num_wtiles(s->M);
+    const size_t cells = (size_t)S.columns * (s->G + 1);
+    const bool exact = p >= RC_EXACT_MIN_P;
+    EHMM_CK(cudaMemsetAsync(err_flag(s), 0, sizeof(int), s->stream));
+    if (exact) {
+        EHMM_CK(cudaMemsetAsync(s->rc_limbs.p, 0, 2 * sizeof(unsigned long long) * cells, s->stream));
+        PROF(s, KID_RC_APPLY), rc_apply_kernel<DIFF, UT, true><<<tile_grid(nwt), RC_NT, 0, s->stream>>>(
+            S, p, nwt, s->rc_scan.as<uint32_t>(), ub, unif, s->group.as<int32_t>(), nrep, s->G, s->rc_limbs.p,
+            s->rc_flag.as<int>(), err_flag(s));
+    } else {
+        EHMM_CK(cudaMemsetAsync(s->rc_buckets.p, 0, sizeof(double) * cells, s->stream));
+        PROF(s, KID_RC_APPLY), rc_apply_kernel<DIFF, UT, false><<<tile_grid(nwt), RC_NT, 0, s->stream>>>(
+            S, p, nwt, s->rc_scan.as<uint32_t>(), ub, unif, s->group.as<int32_t>(), nrep, s->G, s->rc_buckets.p,
+            s->rc_flag.as<int>(), err_flag(s));
+    }
+    EHMM_CK(cudaGetLastError());
+    s->rc_exact = exact;
+    s->rc_final = !exact;
+    s->rc_columns = S.columns;
+    s->rc_N = nrep;
+    return EHMM_OK;
+}
+
+int upload_state_if_needed(ehmm_session *s) {
+    EHMM_TRY(s->mt_raw.reserve(sizeof(uint32_t) * 625));
+    if (!s->rng_dev_valid) {
+        memcpy(s->h_pinned + 512, s->rng_state, sizeof(uint32_t) * 625);
+        EHMM_CK(cudaMemcpyAsync(s->mt_raw.p, s->h_pinned + 512, sizeof(uint32_t) * 625, cudaMemcpyHostToDevice, s->stream));
+        s->rng_dev_valid = true;
+        s->mtj_valid = 0;
+        s->mtj_niv = 0;
+        s->mtj_base = false;
+    }
+    return EHMM_OK;
+}
+
+template <bool DIFF>
 int run_rc(ehmm_session *s, const RCSrc &S, double p, int nrep, const double *uniforms, int64_t n_uniforms,
            int64_t *consumed) {
-    const int64_t nblk = (s->M + RC_TB - 1) / RC_TB;
-    const int64_t ncnt = nblk * S.columns;
-    EHMM_TRY(s->rc_flag.reserve(sizeof(int) * ncnt));
-    EHMM_TRY(s->rc_scan.reserve(sizeof(int64_t) * (ncnt + 1)));
-    EHMM_TRY(s->rc_buckets.reserve(sizeof(double) * (size_t)S.columns * (s->G + 1)));
-    EHMM_CK(cudaMemsetAsync(s->rc_buckets.p, 0, sizeof(double) * (size_t)S.columns * (s->G + 1), s->stream));
-    dim3 grid((unsigned)nblk, (unsigned)S.columns);
+    EHMM_TRY(reserve_rc(s, S));
+    int64_t coltot[RC_MAXCOL];
+    EHMM_TRY(count_and_scan<DIFF>(s, S, p, coltot));
+    RCBase ub;
     int64_t total = 0;
-    if (p > 0.0) {
-        PROF(s, KID_RC_COUNT), rc_count_kernel<<<grid, RC_NT, 0, s->stream>>>(S, p, nblk, s->rc_flag.as<int>());
-        EHMM_CK(cudaGetLastError());
-        PROF(s, KID_RC_SCAN), rc_scan_kernel<<<1, 1024, 0, s->stream>>>(s->rc_flag.as<int>(), ncnt, s->rc_scan.as<int64_t>());
-        EHMM_CK(cudaGetLastError());
-        EHMM_CK(cudaMemcpyAsync(s->h_pinned + 200, s->rc_scan.as<int64_t>() + ncnt, sizeof(int64_t), cudaMemcpyDeviceToHost,
-                                s->stream));
-        EHMM_CK(cudaStreamSynchronize(s->stream));
-        memcpy(&total, s->h_pinned + 200, sizeof(int64_t));
-    } else {
-        EHMM_CK(cudaMemsetAsync(s->rc_scan.p, 0, sizeof(int64_t) * (ncnt + 1), s->stream));
-    }
-    const int32_t *grp = s->group.as<int32_t>();
+    for (int c = 0; c < S.columns; c++) { ub.ubase[c] = total; total += coltot[c]; }
     if (uniforms) {
         EHMM_REQUIRE(total <= n_uniforms, EHMM_ERR_RNG, "rejection control needs %lld uniforms, buffer holds %lld",
                      (long long)total, (long long)n_uniforms);
         EHMM_TRY(s->rc_unif.reserve(sizeof(double) * (size_t)(total > 0 ? total : 1)));
         if (total > 0)
             EHMM_CK(cudaMemcpyAsync(s->rc_unif.p, uniforms, sizeof(double) * total, cudaMemcpyHostToDevice, s->stream));
-        PROF(s, KID_RC_APPLY), rc_apply_kernel<double><<<apply_grid(nblk, S.columns), RC_NT, 0, s->stream>>>(S, p, nblk, s->rc_scan.as<int64_t>(),
-                                                               s->rc_unif.as<double>(), grp, nrep, s->G,
-                                                               s->rc_buckets.as<double>(), nullptr);
+        EHMM_TRY((launch_apply<DIFF, double>(s, S, p, nrep, ub, s->rc_unif.as<double>())));
     } else {
         EHMM_REQUIRE(s->rng_set || total == 0, EHMM_ERR_RNG,
                      "rejection control needs %lld uniforms: pass a buffer or call ehmm_rng_set_state", (long long)total);
         EHMM_TRY(s->rc_unif.reserve(sizeof(uint32_t) * (size_t)(total > 0 ? total : 1)));
-        EHMM_TRY(s->mt_raw.reserve(sizeof(uint32_t) * 625));
         if (total > 0) {
-            if (!s->rng_dev_valid) {
-                memcpy(s->h_pinned + 512, s->rng_state, sizeof(uint32_t) * 625);
-                EHMM_CK(cudaMemcpyAsync(s->mt_raw.p, s->h_pinned + 512, sizeof(uint32_t) * 625, cudaMemcpyHostToDevice, s->stream));
-                s->rng_dev_valid = true;
-                s->mtj_valid = 0;
-                s->mtj_niv = 0;
-                s->mtj_base = false;
-            }
+            EHMM_TRY(upload_state_if_needed(s));
             EHMM_TRY(mt_generate(s, total, s->rc_unif.as<uint32_t>()));
             EHMM_CK(cudaMemcpyAsync(s->h_pinned + 512, s->mt_raw.p, sizeof(uint32_t) * 625, cudaMemcpyDeviceToHost, s->stream));
             rng_note_advance(s, total);
         }
-        PROF(s, KID_RC_APPLY), rc_apply_kernel<uint32_t><<<apply_grid(nblk, S.columns), RC_NT, 0, s->stream>>>(S, p, nblk, s->rc_scan.as<int64_t>(),
-                                                                 s->rc_unif.as<uint32_t>(), grp, nrep, s->G,
-                                                                 s->rc_buckets.as<double>(), nullptr);
+        EHMM_TRY((launch_apply<DIFF, uint32_t>(s, S, p, nrep, ub, s->rc_unif.as<uint32_t>())));
     }
-    EHMM_CK(cudaGetLastError());
+    EHMM_TRY(rc_finalize(s));
     // the next call's sub-stream windows depend only on the RNG state: prepare them on the side stream
     // (sized from this call's consumption with 25% headroom; a larger need falls back to preparing
     // the windows on the main stream)
@@ -337,76 +459,46 @@ int run_rc(ehmm_session *s, const RCSrc &S, double p, int nrep, const double *un
         EHMM_TRY(mt_prefetch(s, est));
     }
     // the host does not wait for the tables: the next reader of the stream does
-    s->rc_columns = S.columns;
-    s->rc_N = nrep;
     if (consumed) *consumed = total;
     return EHMM_OK;
 }
 
 // ---- sharded form: the caller owns the ordering across bin blocks --------------------------------
-// phase 1: flagged counts of this block per column (count + scan kernels; results stay in rc_scan)
-int rc_count_block(ehmm_session *s, const RCSrc &S, double p, int64_t *counts) {
-    const int64_t nblk = (s->M + RC_TB - 1) / RC_TB;
-    const int64_t ncnt = nblk * S.columns;
-    EHMM_REQUIRE(S.columns <= 64, EHMM_ERR_ARG, "too many columns");
-    EHMM_TRY(s->rc_flag.reserve(sizeof(int) * ncnt));
-    EHMM_TRY(s->rc_scan.reserve(sizeof(int64_t) * (ncnt + 1)));
-    dim3 grid((unsigned)nblk, (unsigned)S.columns);
-    if (p > 0.0) {
-        PROF(s, KID_RC_COUNT), rc_count_kernel<<<grid, RC_NT, 0, s->stream>>>(S, p, nblk, s->rc_flag.as<int>());
-        EHMM_CK(cudaGetLastError());
-        PROF(s, KID_RC_SCAN), rc_scan_kernel<<<1, 1024, 0, s->stream>>>(s->rc_flag.as<int>(), ncnt, s->rc_scan.as<int64_t>());
-        EHMM_CK(cudaGetLastError());
-    } else {
-        EHMM_CK(cudaMemsetAsync(s->rc_scan.p, 0, sizeof(int64_t) * (ncnt + 1), s->stream));
-    }
-    int64_t *hp = reinterpret_cast<int64_t *>(s->h_pinned + 200);
-    for (int c = 0; c <= S.columns; c++)
-        EHMM_CK(cudaMemcpyAsync(hp + c, s->rc_scan.as<int64_t>() + (int64_t)c * nblk, sizeof(int64_t), cudaMemcpyDeviceToHost,
-                                s->stream));
-    EHMM_CK(cudaStreamSynchronize(s->stream));
-    for (int c = 0; c < S.columns; c++) { counts[c] = hp[c + 1] - hp[c]; s->rc_colcount[c] = counts[c]; }
+// phase 1: flagged counts of this block per column (count + scan kernels; offsets stay in rc_scan)
+template <bool DIFF> int rc_count_block(ehmm_session *s, const RCSrc &S, double p, int64_t *counts) {
+    EHMM_TRY(reserve_rc(s, S));
+    EHMM_TRY(count_and_scan<DIFF>(s, S, p, counts));
+    for (int c = 0; c < S.columns; c++) s->rc_colcount[c] = counts[c];
     s->rc_count_p = p;
     s->rc_count_cols = S.columns;
     return EHMM_OK;
 }
 
 // phase 2: this block's draws of column c start at stream offset col_offsets[c] (relative to the
-// current RNG position); the stream advances by `total` (the draws of all blocks).
+// current RNG position); the stream advances by `total` (the draws of all blocks).  The tables are
+// left as exact limbs: the caller adds the limbs of all blocks (ehmm_rc_buckets_device) and then
+// calls ehmm_rc_finalize, so the rounded table is the same for every sharding.
+template <bool DIFF>
 int rc_apply_block(ehmm_session *s, const RCSrc &S, double p, int nrep, const int64_t *col_offsets, int64_t total) {
     EHMM_REQUIRE(s->rc_count_cols == S.columns && s->rc_count_p == p, EHMM_ERR_STATE,
                  "rc_apply_at must follow rc_count with the same p");
     EHMM_REQUIRE(s->rng_set || total == 0, EHMM_ERR_RNG, "rejection control needs the RNG state (ehmm_rng_set_state)");
-    const int64_t nblk = (s->M + RC_TB - 1) / RC_TB;
     int64_t local = 0;
     for (int c = 0; c < S.columns; c++) local += s->rc_colcount[c];
-    EHMM_TRY(s->rc_buckets.reserve(sizeof(double) * (size_t)S.columns * (s->G + 1)));
-    EHMM_CK(cudaMemsetAsync(s->rc_buckets.p, 0, sizeof(double) * (size_t)S.columns * (s->G + 1), s->stream));
     EHMM_TRY(s->rc_unif.reserve(sizeof(uint32_t) * (size_t)(local > 0 ? local : 1)));
-    EHMM_TRY(s->mt_raw.reserve(sizeof(uint32_t) * 625));
+    RCBase ub;
+    int64_t at = 0;
+    for (int c = 0; c < S.columns; c++) { ub.ubase[c] = at; at += s->rc_colcount[c]; }
     if (total > 0) {
-        if (!s->rng_dev_valid) {
-            memcpy(s->h_pinned + 512, s->rng_state, sizeof(uint32_t) * 625);
-            EHMM_CK(cudaMemcpyAsync(s->mt_raw.p, s->h_pinned + 512, sizeof(uint32_t) * 625, cudaMemcpyHostToDevice, s->stream));
-            s->rng_dev_valid = true;
-            s->mtj_valid = 0;
-            s->mtj_niv = 0;
-            s->mtj_base = false;
-        }
-        int64_t at = 0;
+        EHMM_TRY(upload_state_if_needed(s));
         for (int c = 0; c < S.columns; c++) {
             EHMM_REQUIRE(col_offsets[c] >= 0 && col_offsets[c] + s->rc_colcount[c] <= total, EHMM_ERR_ARG,
                          "column %d: draws [%lld, %lld) outside [0, %lld)", c, (long long)col_offsets[c],
                          (long long)(col_offsets[c] + s->rc_colcount[c]), (long long)total);
-            EHMM_TRY(mt_generate_range(s, col_offsets[c], s->rc_colcount[c], s->rc_unif.as<uint32_t>() + at));
-            at += s->rc_colcount[c];
+            EHMM_TRY(mt_generate_range(s, col_offsets[c], s->rc_colcount[c], s->rc_unif.as<uint32_t>() + ub.ubase[c]));
         }
     }
-    dim3 grid((unsigned)nblk, (unsigned)S.columns);
-    PROF(s, KID_RC_APPLY), rc_apply_kernel<uint32_t><<<apply_grid(nblk, S.columns), RC_NT, 0, s->stream>>>(
-        S, p, nblk, s->rc_scan.as<int64_t>(), s->rc_unif.as<uint32_t>(), s->group.as<int32_t>(), nrep, s->G,
-        s->rc_buckets.as<double>(), nullptr);
-    EHMM_CK(cudaGetLastError());
+    EHMM_TRY((launch_apply<DIFF, uint32_t>(s, S, p, nrep, ub, s->rc_unif.as<uint32_t>())));
     if (total > 0) {
         // side stream: the stream's state after all ranks' draws, then the windows of the next call's
         // slice, which sits where this one's did, give or take a few thousand draws
@@ -414,8 +506,6 @@ int rc_apply_block(ehmm_session *s, const RCSrc &S, double p, int nrep, const in
         rng_note_advance(s, total);
         EHMM_TRY(mt_prefetch_ranges(s, S.columns, col_offsets, s->rc_colcount, total, 2));
     }
-    s->rc_columns = S.columns;
-    s->rc_N = nrep;
     s->rc_count_cols = 0;
     return EHMM_OK;
 }
@@ -454,15 +544,17 @@ struct TmpDev {
 
 }  // namespace
 
-int rc_consensus(ehmm_session *s, double p, const double *uniforms, int64_t n_uniforms, int64_t *consumed) {
-    RCSrc S = {s->logProb1.as<double>(), nullptr, s->M, 0, s->K};
-    return run_rc(s, S, p, 1, uniforms, n_uniforms, consumed);
-}
-
-int rc_differential(ehmm_session *s, double p, int N, const double *uniforms, int64_t n_uniforms, int64_t *consumed) {
-    EHMM_REQUIRE(s->K == 3 && s->B > 0, EHMM_ERR_ARG, "differentialRejectionControlled needs K=3 and mixture components");
-    RCSrc S = {s->logProb1.as<double>(), s->eta.as<double>(), s->M, s->B, s->B + 2};
-    return run_rc(s, S, p, N, uniforms, n_uniforms, consumed);
+// limbs -> fp64 tables (no-op when the tables were accumulated in fp64 or are already final)
+int rc_finalize(ehmm_session *s) {
+    if (s->rc_final || !s->rc_exact) { s->rc_final = true; return EHMM_OK; }
+    const int64_t n = (int64_t)s->rc_columns * (s->G + 1);
+    const unsigned grid = (unsigned)std::min<int64_t>((n + 255) / 256, 148 * 8);
+    PROF(s, KID_RC_FINAL), rc_finalize_kernel<<<grid, 256, 0, s->stream>>>(s->rc_limbs.as<unsigned long long>(), n,
+                                                                        s->rc_buckets.as<double>(),
+                                                                        reinterpret_cast<const int *>(s->rc_coltot.as<int64_t>() + RC_MAXCOL));
+    EHMM_CK(cudaGetLastError());
+    s->rc_final = true;
+    return EHMM_OK;
 }
 
 static RCSrc rc_source(ehmm_session *s, int differential) {
@@ -470,15 +562,28 @@ static RCSrc rc_source(ehmm_session *s, int differential) {
     return RCSrc{s->logProb1.as<double>(), nullptr, s->M, 0, s->K};
 }
 
+int rc_consensus(ehmm_session *s, double p, const double *uniforms, int64_t n_uniforms, int64_t *consumed) {
+    EHMM_REQUIRE(s->K == 2, EHMM_ERR_ARG, "consensusRejectionControlled needs K=2");
+    return run_rc<false>(s, rc_source(s, 0), p, 1, uniforms, n_uniforms, consumed);
+}
+
+int rc_differential(ehmm_session *s, double p, int N, const double *uniforms, int64_t n_uniforms, int64_t *consumed) {
+    EHMM_REQUIRE(s->K == 3 && s->B > 0, EHMM_ERR_ARG, "differentialRejectionControlled needs K=3 and mixture components");
+    return run_rc<true>(s, rc_source(s, 1), p, N, uniforms, n_uniforms, consumed);
+}
+
 int rc_count(ehmm_session *s, int differential, double p, int64_t *counts) {
-    return rc_count_block(s, rc_source(s, differential), p, counts);
+    EHMM_REQUIRE(differential ? (s->K == 3 && s->B > 0) : s->K == 2, EHMM_ERR_ARG, "rc_count: model / session mismatch");
+    return differential ? rc_count_block<true>(s, rc_source(s, 1), p, counts) : rc_count_block<false>(s, rc_source(s, 0), p, counts);
 }
 
 int rc_apply_at(ehmm_session *s, int differential, double p, const int64_t *col_offsets, int64_t total) {
-    return rc_apply_block(s, rc_source(s, differential), p, differential ? s->N : 1, col_offsets, total);
+    return differential ? rc_apply_block<true>(s, rc_source(s, 1), p, s->N, col_offsets, total)
+                        : rc_apply_block<false>(s, rc_source(s, 0), p, 1, col_offsets, total);
 }
 
 static int fetch_column(ehmm_session *s, int column, std::vector<double> &h) {
+    EHMM_TRY(rc_finalize(s));
     h.resize((size_t)s->G + 1);
     EHMM_CK(cudaMemcpyAsync(h.data(), s->rc_buckets.as<double>() + (size_t)column * (s->G + 1), sizeof(double) * (s->G + 1),
                             cudaMemcpyDeviceToHost, s->stream));
@@ -515,7 +620,7 @@ int rc_reweight(int device, double *x, int64_t n, double p, const double *unifor
     EHMM_TRY(doff.alloc(sizeof(int64_t) * (nblk + 1)));
     EHMM_CK(cudaMemcpy(dx.p, x, sizeof(double) * n, cudaMemcpyHostToDevice));
     rw_count_kernel<<<(unsigned)nblk, RC_NT>>>((const double *)dx.p, n, p, (int *)dc.p);
-    rc_scan_kernel<<<1, 1024>>>((const int *)dc.p, nblk, (int64_t *)doff.p);
+    rw_scan_kernel<<<1, 1024>>>((const int *)dc.p, nblk, (int64_t *)doff.p);
     EHMM_CK(cudaGetLastError());
     int64_t total = 0;
     EHMM_CK(cudaMemcpy(&total, (int64_t *)doff.p + nblk, sizeof(int64_t), cudaMemcpyDeviceToHost));
@@ -533,17 +638,27 @@ int rc_reweight(int device, double *x, int64_t n, double p, const double *unifor
 
 int rc_aggregate(int device, const double *x, int64_t n, const int32_t *f, int64_t G, double *buckets) {
     EHMM_CK(cudaSetDevice(device));
-    for (int64_t i = 0; i < n; i++)
+    std::vector<int64_t> start((size_t)G + 2, 0), perm((size_t)n);
+    for (int64_t i = 0; i < n; i++) {
         EHMM_REQUIRE(f[i] >= 0 && f[i] <= G, EHMM_ERR_ARG, "aggregate: group id %d at %lld outside [0, %lld]", f[i],
                      (long long)i, (long long)G);
-    TmpDev dx, df, db;
+        start[(size_t)f[i] + 1]++;
+    }
+    for (int64_t g = 0; g <= G; g++) start[(size_t)g + 1] += start[(size_t)g];
+    {
+        std::vector<int64_t> at(start.begin(), start.end() - 1);
+        for (int64_t i = 0; i < n; i++) perm[(size_t)at[(size_t)f[i]]++] = i;  // ascending i inside every group
+    }
+    TmpDev dx, dp, ds, db;
     EHMM_TRY(dx.alloc(sizeof(double) * n));
-    EHMM_TRY(df.alloc(sizeof(int32_t) * n));
+    EHMM_TRY(dp.alloc(sizeof(int64_t) * n));
+    EHMM_TRY(ds.alloc(sizeof(int64_t) * (G + 2)));
     EHMM_TRY(db.alloc(sizeof(double) * (G + 1)));
     EHMM_CK(cudaMemcpy(dx.p, x, sizeof(double) * n, cudaMemcpyHostToDevice));
-    EHMM_CK(cudaMemcpy(df.p, f, sizeof(int32_t) * n, cudaMemcpyHostToDevice));
-    EHMM_CK(cudaMemset(db.p, 0, sizeof(double) * (G + 1)));
-    if (n) aggregate_kernel<<<148 * 4, 256>>>((const double *)dx.p, n, (const int32_t *)df.p, (double *)db.p);
+    EHMM_CK(cudaMemcpy(dp.p, perm.data(), sizeof(int64_t) * n, cudaMemcpyHostToDevice));
+    EHMM_CK(cudaMemcpy(ds.p, start.data(), sizeof(int64_t) * (G + 2), cudaMemcpyHostToDevice));
+    aggregate_kernel<<<(unsigned)((G + 1 + 255) / 256), 256>>>((const double *)dx.p, (const int64_t *)ds.p, (const int64_t *)dp.p, G,
+                                                              (double *)db.p);
     EHMM_CK(cudaGetLastError());
     EHMM_CK(cudaMemcpy(buckets, db.p, sizeof(double) * (G + 1), cudaMemcpyDeviceToHost));
     return EHMM_OK;

@@ -305,7 +305,9 @@ int ehmm_set_data(ehmm_session *s, int N, const int32_t *counts, const double *o
         EHMM_TRY(s->controls_own.reserve(n * sizeof(double)));
         EHMM_CK(cudaMemcpyAsync(s->controls_own.p, controls, n * sizeof(double), cudaMemcpyHostToDevice, s->stream));
         dc = s->controls_own.as<double>();
+        s->ctrl_first = controls[0];
     }
+    s->have_ctrl_first = controls != nullptr;
     s->N = N;
     s->groups_consistent = false;
     s->encoded = false;
@@ -324,7 +326,25 @@ int ehmm_set_data_device(ehmm_session *s, int N, const int32_t *counts, const do
     s->d_counts = counts;
     s->d_offsets = offsets;
     s->d_controls = controls;
+    s->have_ctrl_first = controls != nullptr;
+    if (controls) EHMM_CK(cudaMemcpy(&s->ctrl_first, controls, sizeof(double), cudaMemcpyDeviceToHost));
     return scan_counts(s);
+}
+
+int ehmm_controls_first(ehmm_session *s, double *value) {
+    EHMM_TRY(check_session(s));
+    EHMM_REQUIRE(value, EHMM_ERR_ARG, "null pointer");
+    EHMM_REQUIRE(s->have_ctrl_first, EHMM_ERR_STATE, "no controls matrix has been set");
+    *value = s->ctrl_first;
+    return EHMM_OK;
+}
+
+int ehmm_set_controls_first(ehmm_session *s, double value) {
+    EHMM_TRY(check_session(s));
+    EHMM_REQUIRE(isfinite(value), EHMM_ERR_ARG, "controls[1] = %g is not finite", value);
+    s->ctrl_first = value;
+    s->have_ctrl_first = true;
+    return EHMM_OK;
 }
 
 int ehmm_set_groups(ehmm_session *s, const int32_t *group, int64_t G, const double *u_chip, const double *u_offsets,
@@ -363,6 +383,28 @@ int ehmm_groups_fetch(ehmm_session *s, int32_t *group, double *u_chip, double *u
                       uint8_t *u_dsg) {
     EHMM_TRY(check_session(s));
     return groups_fetch(s, group, u_chip, u_offsets, u_controls, u_dsg);
+}
+
+int ehmm_groups_first_cell(ehmm_session *s, int64_t *first) {
+    EHMM_TRY(check_session(s));
+    EHMM_REQUIRE(first, EHMM_ERR_ARG, "null pointer");
+    EHMM_REQUIRE(s->G > 0 && (int64_t)s->group_first.size() == s->G, EHMM_ERR_STATE,
+                 "groups_first_cell: the groups were not built by ehmm_build_groups");
+    memcpy(first, s->group_first.data(), sizeof(int64_t) * s->G);
+    return EHMM_OK;
+}
+
+int ehmm_groups_remap(ehmm_session *s, const int32_t *new_id, int64_t G_new, const double *u_chip, const double *u_offsets,
+                      const double *u_controls, const uint8_t *u_dsg) {
+    EHMM_TRY(check_session(s));
+    EHMM_REQUIRE(new_id && G_new >= 1 && u_chip && u_offsets, EHMM_ERR_ARG, "groups_remap: bad arguments");
+    EHMM_TRY(groups_remap(s, new_id, G_new));
+    EHMM_TRY(upload_unique(s, G_new, u_chip, u_offsets, u_controls, u_dsg));
+    EHMM_CK(cudaStreamSynchronize(s->stream));
+    s->G = G_new;
+    s->groups_consistent = true;
+    s->rc_columns = 0;
+    return EHMM_OK;
 }
 
 int ehmm_set_design_n(ehmm_session *s, int N, int B, const uint8_t *design) {
@@ -436,6 +478,12 @@ static int set_encoded(ehmm_session *s, int N, const int32_t *group, const uint1
     s->d_controls = nullptr;
     s->encoded = true;
     s->encoded_ctrl = u_controls != nullptr;
+    s->have_ctrl_first = u_controls != nullptr;
+    if (u_controls) {
+        const int64_t g0 = group ? (int64_t)group[0] : (int64_t)group16[0];
+        EHMM_REQUIRE(g0 >= 1 && g0 <= G, EHMM_ERR_ARG, "set_data_encoded: group ids must lie in [1, G]");
+        s->ctrl_first = u_controls[g0 - 1];
+    }
     s->count_max = (int64_t)mx;
     const size_t n = (size_t)s->M * N;
     EHMM_TRY(s->group.reserve(n * sizeof(int32_t)));
@@ -813,12 +861,27 @@ int ehmm_rc_apply_at(ehmm_session *s, int differential, double p, const int64_t 
     return rc_apply_at(s, differential, p, col_offsets, total);
 }
 
-int ehmm_rc_buckets_device(ehmm_session *s, void **ptr, int64_t *n) {
-    EHMM_REQUIRE(s && ptr && n, EHMM_ERR_ARG, "null pointer");
+int ehmm_rc_buckets_device(ehmm_session *s, void **ptr, int64_t *n, int *is_integer) {
+    EHMM_REQUIRE(s && ptr && n && is_integer, EHMM_ERR_ARG, "null pointer");
     EHMM_REQUIRE(s->rc_columns > 0, EHMM_ERR_STATE, "no rejection tables");
-    *ptr = s->rc_buckets.p;
-    *n = (int64_t)s->rc_columns * (s->G + 1);
+    const int64_t cells = (int64_t)s->rc_columns * (s->G + 1);
+    if (s->rc_exact) {
+        *ptr = s->rc_limbs.p;
+        *n = 2 * cells;
+        *is_integer = 1;
+        s->rc_final = false;  // the caller is about to change the limbs: round them again
+    } else {
+        *ptr = s->rc_buckets.p;
+        *n = cells;
+        *is_integer = 0;
+    }
     return EHMM_OK;
+}
+
+int ehmm_rc_finalize(ehmm_session *s) {
+    EHMM_TRY(check_session(s));
+    EHMM_REQUIRE(s->rc_columns > 0, EHMM_ERR_STATE, "no rejection tables");
+    return rc_finalize(s);
 }
 
 int ehmm_inner_mstep_sums(ehmm_session *s, double *sums) {
@@ -842,6 +905,7 @@ int ehmm_rc_table_fetch(ehmm_session *s, int column, double *sums, double *ids) 
 int ehmm_rc_buckets_fetch(ehmm_session *s, int column, double *buckets) {
     EHMM_TRY(check_session(s));
     EHMM_REQUIRE(buckets && column >= 0 && column < s->rc_columns, EHMM_ERR_ARG, "bad column %d (have %d)", column, s->rc_columns);
+    EHMM_TRY(rc_finalize(s));
     EHMM_CK(cudaMemcpyAsync(buckets, s->rc_buckets.as<double>() + (size_t)column * (s->G + 1), sizeof(double) * (s->G + 1),
                             cudaMemcpyDeviceToHost, s->stream));
     EHMM_CK(cudaStreamSynchronize(s->stream));
@@ -862,18 +926,21 @@ int ehmm_glm_nb(ehmm_session *s, int column, const double *par, int P, double *v
     EHMM_TRY(check_session(s));
     EHMM_REQUIRE(par && value, EHMM_ERR_ARG, "null pointer");
     EHMM_REQUIRE(column >= 0 && column < s->rc_columns, EHMM_ERR_STATE, "glmNB: rejection table %d not available", column);
+    EHMM_TRY(rc_finalize(s));
     return glm_nb(s, column, par, P, value, grad);
 }
 
 int ehmm_glm_zinb(ehmm_session *s, int column, const double *par, int P, double minZero, double *value, double *grad) {
     EHMM_TRY(check_session(s));
     EHMM_REQUIRE(par && value, EHMM_ERR_ARG, "null pointer");
+    EHMM_TRY(rc_finalize(s));
     return glm_zinb(s, column, par, P, minZero, value, grad);
 }
 
 int ehmm_glm_nb_batch(ehmm_session *s, int n, const int *columns, const double *pars, int P, double *values, double *grads) {
     EHMM_TRY(check_session(s));
     EHMM_REQUIRE(columns && pars && values, EHMM_ERR_ARG, "null pointer");
+    EHMM_TRY(rc_finalize(s));
     return glm_nb_batch(s, n, columns, pars, P, values, grads);
 }
 
@@ -881,6 +948,7 @@ int ehmm_glm_mix_nb(ehmm_session *s, const double *par, double minZero, double *
     EHMM_TRY(check_session(s));
     EHMM_REQUIRE(par && value, EHMM_ERR_ARG, "null pointer");
     EHMM_REQUIRE(s->rc_columns == s->B + 2 && s->B > 0, EHMM_ERR_STATE, "glmMixNB: differential rejection tables not available");
+    EHMM_TRY(rc_finalize(s));
     return glm_mix_nb(s, par, minZero, value, grad);
 }
 
@@ -888,6 +956,7 @@ int ehmm_glm_mix_zinb(ehmm_session *s, const double *par, double minZero, double
     EHMM_TRY(check_session(s));
     EHMM_REQUIRE(par && value, EHMM_ERR_ARG, "null pointer");
     EHMM_REQUIRE(s->rc_columns == s->B + 2 && s->B > 0, EHMM_ERR_STATE, "glmMixZINB: differential rejection tables not available");
+    EHMM_TRY(rc_finalize(s));
     return glm_mix_zinb(s, par, minZero, value, grad);
 }
 

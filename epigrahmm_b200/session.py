@@ -77,6 +77,16 @@ class Session:
                                        C.c_void_p(controls_ptr) if controls_ptr else None))
         self.N = int(N)
 
+    def controls_first(self) -> float:
+        """controls[1] of the long table: the one control value the reference's emission uses
+        (R/base-loglikelihood.R:113; see include/ehmm.h)"""
+        v = C.c_double()
+        check(lib.ehmm_controls_first(self._h, C.byref(v)))
+        return v.value
+
+    def set_controls_first(self, value: float):
+        check(lib.ehmm_set_controls_first(self._h, float(value)))
+
     def build_groups(self) -> int:
         """dt$Group + dtUnique on the device (after set_data / set_design); returns G"""
         G = C.c_int64()
@@ -105,6 +115,22 @@ class Session:
             except _lib.EhmmError:
                 pass
         return out
+
+    def groups_first_cell(self):
+        """column-major cell index (sample * M + bin) of every group's first appearance (build_groups)"""
+        out = np.empty(self.G, dtype=np.int64)
+        check(lib.ehmm_groups_first_cell(self._h, out.ctypes.data_as(C.POINTER(C.c_int64))))
+        return out
+
+    def groups_remap(self, new_id, u_chip, u_offsets, u_controls=None, u_dsg=None):
+        """rewrite dt$Group in place: old id g -> new_id[g - 1]; dtUnique is replaced by the given columns"""
+        nid = np.ascontiguousarray(new_id, dtype=np.int32)
+        assert nid.size == self.G
+        uc, uo = _f64(u_chip), _f64(u_offsets)
+        uctrl = None if u_controls is None else _f64(u_controls)
+        udsg = None if u_dsg is None else np.asfortranarray(u_dsg, dtype=np.uint8)
+        check(lib.ehmm_groups_remap(self._h, iptr(nid), uc.size, dptr(uc), dptr(uo), dptr(uctrl), bptr(udsg)))
+        self.G = uc.size
 
     def set_data_encoded(self, group, u_chip, u_offsets, u_controls=None, u_dsg=None, design=None):
         """upload the table as dt$Group + dtUnique only (the counts/offsets matrices stay on the host)"""
@@ -308,10 +334,14 @@ class Session:
         self.rc_columns = off.size
 
     def rc_buckets_device(self):
-        """(device pointer, element count) of the dense bucket sums"""
-        p, n = C.c_void_p(), C.c_int64()
-        check(lib.ehmm_rc_buckets_device(self._h, C.byref(p), C.byref(n)))
-        return p.value, n.value
+        """(device pointer, element count, is_integer) of the rejection tables' accumulators: exact
+        uint64 limbs (is_integer) or, for cuts below 2^-9, fp64 sums"""
+        p, n, it = C.c_void_p(), C.c_int64(), C.c_int()
+        check(lib.ehmm_rc_buckets_device(self._h, C.byref(p), C.byref(n), C.byref(it)))
+        return p.value, n.value, bool(it.value)
+
+    def rc_finalize(self):
+        check(lib.ehmm_rc_finalize(self._h))
 
     def inner_mstep_sums(self):
         out = np.empty(self.B + 1)

@@ -110,14 +110,16 @@ class TorchComm:
     def broadcast(self, a, src):
         return self.all_gather(a)[src]
 
-    def all_reduce_device(self, ptr, n, stream=None):
-        """in-place sum of n doubles at device pointer ptr (NCCL over NVLink).  With `stream` (the
-        session's cudaStream_t) the collective is ordered on that stream -- after the kernels that
-        produced the data and before the ones that read it -- and the host does not wait."""
-        key = ("dev", ptr, n)
+    def all_reduce_device(self, ptr, n, stream=None, integer=False):
+        """in-place sum of n doubles (or, integer=True, n 64-bit integers) at device pointer ptr (NCCL
+        over NVLink).  With `stream` (the session's cudaStream_t) the collective is ordered on that
+        stream -- after the kernels that produced the data and before the ones that read it -- and the
+        host does not wait."""
+        key = ("dev", ptr, n, integer)
         if key not in self._bufs:
             class _Buf:
-                __cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 3}
+                __cuda_array_interface__ = {"shape": (n,), "typestr": "<i8" if integer else "<f8", "data": (ptr, False),
+                                            "version": 3}
             self._bufs[key] = self.torch.as_tensor(_Buf(), device=self.device)
         if stream is None:
             self.dist.all_reduce(self._bufs[key])
@@ -172,20 +174,16 @@ def make_comm(dist, device=None):
     return ShmComm(dist, device)
 
 
-def global_groups(counts, offsets, comm, m0, Mtot, controls=None, design=None):
-    """dt$Group over the whole sharded table: every rank gets the same dictionary, numbered by first
-    appearance in the column-major global table exactly as data.table's .GRP (R/base-core.R:97,187)."""
-    from .synth import make_groups
-    loc = make_groups(counts, offsets, controls, design)
-    M, N = np.asarray(counts).shape
-    # first appearance of each local group as a global column-major cell index
-    g = loc["group"].ravel(order="F")
-    first_local = np.full(loc["G"], M * N, dtype=np.int64)
-    np.minimum.at(first_local, g - 1, np.arange(M * N, dtype=np.int64))
+def _merge_dictionaries(comm, M, m0, Mtot, u_chip, u_offsets, u_controls, first_local, design):
+    """One dt$Group dictionary from the ranks' local ones.  first_local: column-major cell index
+    (sample * M + bin) of every local group's first appearance.  Returns (mine, G, rows, rep, samp):
+    mine[l] = global id of local group l + 1, numbered by first appearance in the column-major GLOBAL
+    table exactly as data.table's .GRP (R/base-core.R:97,187); rows[rep] = one record per global group."""
+    first_local = np.asarray(first_local, dtype=np.int64)
     first_global = (first_local // M) * Mtot + m0 + (first_local % M)
-    cols = [loc["u_chip"], loc["u_offsets"]]
-    if controls is not None:
-        cols.append(loc["u_controls"])
+    cols = [u_chip, u_offsets]
+    if u_controls is not None:
+        cols.append(u_controls)
     if design is not None:
         cols.append(first_local // M)  # the sample decides the Dsg.Mix columns
     rec = np.column_stack(cols + [first_global.astype(np.float64)])
@@ -207,18 +205,51 @@ def global_groups(counts, offsets, comm, m0, Mtot, controls=None, design=None):
     rank_of[order] = np.arange(order.size)
     gid = rank_of[inv] + 1                      # global id of every gathered record
     start = int(sizes[:comm.rank].sum())
-    mine = gid[start:start + loc["G"]]          # local group -> global id
-    out = dict(group=np.asfortranarray(mine[loc["group"] - 1].astype(np.int32)), G=int(order.size))
+    mine = gid[start:start + rec.shape[0]]      # local group -> global id
     rep = np.empty(order.size, dtype=np.int64)  # one gathered record per global group
     rep[gid - 1] = np.arange(gid.size)
-    out["u_chip"], out["u_offsets"] = rows[rep, 0].copy(), rows[rep, 1].copy()
-    out["u_controls"] = rows[rep, 2].copy() if controls is not None else None
+    return mine, int(order.size), rows, rep
+
+
+def _dictionary_columns(rows, rep, have_controls, design):
+    out = dict(u_chip=rows[rep, 0].copy(), u_offsets=rows[rep, 1].copy())
+    out["u_controls"] = rows[rep, 2].copy() if have_controls else None
     if design is not None:
         samp = rows[rep, -2].astype(np.int64)
         out["u_dsg"] = np.asfortranarray(np.asarray(design, dtype=np.uint8).T[samp])
     else:
         out["u_dsg"] = None
     return out
+
+
+def global_groups(counts, offsets, comm, m0, Mtot, controls=None, design=None):
+    """dt$Group over the whole sharded table, grouped on the host: every rank gets the same dictionary."""
+    from .synth import make_groups
+    loc = make_groups(counts, offsets, controls, design)
+    M, N = np.asarray(counts).shape
+    # first appearance of each local group as a column-major cell index
+    g = loc["group"].ravel(order="F")
+    first_local = np.full(loc["G"], M * N, dtype=np.int64)
+    np.minimum.at(first_local, g - 1, np.arange(M * N, dtype=np.int64))
+    mine, G, rows, rep = _merge_dictionaries(comm, M, m0, Mtot, loc["u_chip"], loc["u_offsets"],
+                                             loc["u_controls"] if controls is not None else None, first_local, design)
+    out = dict(group=np.asfortranarray(mine[loc["group"] - 1].astype(np.int32)), G=G)
+    out.update(_dictionary_columns(rows, rep, controls is not None, design))
+    return out
+
+
+def global_groups_device(session, comm, m0, Mtot, design=None):
+    """The same global dictionary with the per-cell work on the device: every rank groups its block
+    (ehmm_build_groups), the ranks merge their G-row dictionaries on the host (a few 1e5 rows), and the
+    local ids are rewritten in place (ehmm_groups_remap).  `session` already holds the block's data
+    (and design).  Returns G."""
+    session.build_groups()
+    loc = session.groups_fetch(with_group=False)
+    mine, G, rows, rep = _merge_dictionaries(comm, session.M, m0, Mtot, loc["u_chip"], loc["u_offsets"], loc["u_controls"],
+                                             session.groups_first_cell(), design)
+    cols = _dictionary_columns(rows, rep, loc["u_controls"] is not None, design)
+    session.groups_remap(mine, cols["u_chip"], cols["u_offsets"], cols["u_controls"], cols["u_dsg"])
+    return G
 
 
 class ShardedSession:
@@ -239,6 +270,22 @@ class ShardedSession:
 
     def close(self):
         self.local.close()
+
+    # data ------------------------------------------------------------------------------------
+    def _share_controls_first(self, have):
+        """the reference's emission uses controls[1] of the WHOLE table for every cell (its ifelse()
+        quirk, R/base-loglikelihood.R:113): every block takes block 0's value"""
+        if have:
+            v = self.local.controls_first() if self.rank == 0 else 0.0
+            self.local.set_controls_first(float(self.comm.broadcast(np.array([v]), 0)[0]))
+
+    def set_data(self, counts, offsets, controls=None):
+        self.local.set_data(counts, offsets, controls)
+        self._share_controls_first(controls is not None)
+
+    def set_data_encoded(self, group, u_chip, u_offsets, u_controls=None, u_dsg=None, design=None):
+        self.local.set_data_encoded(group, u_chip, u_offsets, u_controls, u_dsg, design)
+        self._share_controls_first(u_controls is not None)
 
     # E-step ----------------------------------------------------------------------------------
     def expstep(self, pi, gamma, logf=None):
@@ -267,8 +314,10 @@ class ShardedSession:
         if hasattr(self.local, "rc_buckets_host"):   # host-resident backend (CPU tests)
             self.local.rc_buckets_set(self.comm.all_reduce_sum(self.local.rc_buckets_host()))
         else:
-            ptr, n = self.local.rc_buckets_device()
-            self.comm.all_reduce_device(ptr, n, stream=self.local.stream)
+            # exact integer limbs: the sum over the blocks does not depend on how the chain was cut
+            ptr, n, integer = self.local.rc_buckets_device()
+            self.comm.all_reduce_device(ptr, n, stream=self.local.stream, integer=integer)
+            self.local.rc_finalize()
         return total
 
     def rc_consensus(self, p, uniforms=None):

@@ -64,6 +64,13 @@ int ehmm_session_set_block(ehmm_session *s, int64_t m0, int64_t Mtot);
 /* counts M x N int32, offsets M x N fp64, controls (already log1p'd, R/base-core.R:186) or NULL. */
 int ehmm_set_data(ehmm_session *s, int N, const int32_t *counts, const double *offsets, const double *controls);
 int ehmm_set_data_device(ehmm_session *s, int N, const int32_t *counts, const double *offsets, const double *controls);
+/* controls[1] -- the (log1p'd) control of bin 1 of sample 1 of the WHOLE long table.  It is the only
+ * control value the reference's emission uses: ifelse(useControl, theta[2]*controls, 0) has a
+ * length-1 test and returns one element (R/base-loglikelihood.R:113,119,126-129,137), which R then
+ * recycles over every row.  ehmm_set_data* record it; a bin block with m0 > 0 must be given block 0's
+ * value (ehmm_controls_first there, ehmm_set_controls_first here). */
+int ehmm_controls_first(ehmm_session *s, double *value);
+int ehmm_set_controls_first(ehmm_session *s, double value);
 /* dt$Group (M x N, 1-based) and dtUnique rows for groups 1..G: ChIP, offsets[, controls]
  * [, Dsg.Mix 0/1 as G x B column-major] (R/base-core.R:99-104,190-198). */
 int ehmm_set_groups(ehmm_session *s, const int32_t *group, int64_t G, const double *u_chip, const double *u_offsets,
@@ -75,6 +82,15 @@ int ehmm_set_groups(ehmm_session *s, const int32_t *group, int64_t G, const doub
 int ehmm_build_groups(ehmm_session *s, int64_t *G);
 int ehmm_groups_fetch(ehmm_session *s, int32_t *group, double *u_chip, double *u_offsets, double *u_controls,
                       uint8_t *u_dsg);
+/* Bin blocks of one sharded table need ONE dictionary (the chain and dt are global): after
+ * ehmm_build_groups on every block, ehmm_groups_first_cell gives the column-major cell index
+ * (sample * M + bin, local to the block) at which each of the block's G groups first appears, the
+ * caller merges the blocks' dtUnique rows into the global numbering (first appearance in the global
+ * column-major table, as .GRP numbers them) and ehmm_groups_remap rewrites the ids in place: old id g
+ * becomes new_id[g - 1]; dtUnique is replaced by the G_new global rows. */
+int ehmm_groups_first_cell(ehmm_session *s, int64_t *first);
+int ehmm_groups_remap(ehmm_session *s, const int32_t *new_id, int64_t G_new, const double *u_chip, const double *u_offsets,
+                      const double *u_controls, const uint8_t *u_dsg);
 /* Dictionary-encoded form of the same table: only dt$Group and dtUnique are uploaded (4 B per cell
  * instead of 12-20 B); counts/offsets are implied by dtUnique[group].  Replaces ehmm_set_data +
  * ehmm_set_groups.  For the differential model call ehmm_set_design_n(s, N, B, design) first. */
@@ -176,8 +192,14 @@ int ehmm_rc_differential(ehmm_session *s, double p, int N, const double *uniform
  * and advances the stream by `total` draws.  differential = 0: K columns; 1: B + 2 columns. */
 int ehmm_rc_count(ehmm_session *s, int differential, double p, int64_t *counts);
 int ehmm_rc_apply_at(ehmm_session *s, int differential, double p, const int64_t *col_offsets, int64_t total);
-/* device pointer to the dense bucket sums (columns x (G+1) doubles), e.g. for an NCCL all-reduce. */
-int ehmm_rc_buckets_device(ehmm_session *s, void **ptr, int64_t *n);
+/* Device pointer to the accumulators of the rejection tables, for adding the tables of several bin
+ * blocks in place (e.g. an NCCL all-reduce ordered on the session stream).  is_integer = 1: n
+ * unsigned 64-bit words, the exact fixed-point limbs (two per table entry) -- add them as integers
+ * and the rounded tables are bit-identical for every sharding; is_integer = 0 (cuts below 2^-9): n
+ * doubles.  ehmm_rc_finalize rounds the limbs into the fp64 tables (the readers below and the GLM
+ * entry points do it themselves when it is still pending). */
+int ehmm_rc_buckets_device(ehmm_session *s, void **ptr, int64_t *n, int *is_integer);
+int ehmm_rc_finalize(ehmm_session *s);
 /* the field<mat> result: table `column` has `rows` (sum, id) pairs with non-zero sum, ascending id. */
 int ehmm_rc_table_rows(ehmm_session *s, int column, int64_t *rows);
 int ehmm_rc_table_fetch(ehmm_session *s, int column, double *sums, double *ids);

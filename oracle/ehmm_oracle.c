@@ -505,7 +505,15 @@ EO_API void eo_viterbi(int64_t M, int K, const double *logFP, const double *pi, 
 /* ------------------------------------------------------------------------ */
 
 /* loglikConsensusHMM, NB branch: R/base-loglikelihood.R:104-122.
- * P = 2 (beta0,size) or 3 (beta0,beta_ctrl,size); ctrl = log1p(controls) or NULL. */
+ * P = 2 (beta0,size) or 3 (beta0,beta_ctrl,size); ctrl = log1p(controls) or NULL.
+ *
+ * QUIRK (reproduced, not fixed): the control term is written
+ *     ifelse(useControl, theta[2]*controls, 0)         (l.113, 119; ZINB l.126-129, 137)
+ * and R's ifelse() returns a value shaped like its TEST, which is the length-1 logical
+ * useControl -- so only the FIRST element of theta[2]*controls survives and is recycled over all
+ * M*N rows: every cell gets theta[2]*controls[1] (bin 1 of sample 1), not its own control.  The
+ * M-step (glmNB's x matrix, R/base-EM.R:131-136) does use the per-cell controls, so the reference
+ * is inconsistent with itself here and a faithful restatement has to be, too. */
 EO_API void eo_loglik_consensus(int64_t M, int N, const int32_t *y, const double *off, const double *ctrl,
                                 const double *th1, const double *th2, int P, double minZero, double *LL) {
     const double *th[2] = {th1, th2};
@@ -515,7 +523,7 @@ EO_API void eo_loglik_consensus(int64_t M, int N, const int32_t *y, const double
             long double acc = 0;
             for (int i = 0; i < N; i++) {
                 int64_t c = j + (int64_t)i * M;
-                double mu = exp(th[k][0] + (ctrl ? th[k][1] * ctrl[c] : 0) + off[c]);
+                double mu = exp(th[k][0] + (ctrl ? th[k][1] * ctrl[0] : 0) + off[c]);  /* ctrl[0]: see QUIRK */
                 acc += log(eo_dnbinom_mu((double)y[c], size, mu, 0) + minZero);
             }
             LL[j + k * M] = (double)acc;
@@ -534,8 +542,8 @@ EO_API void eo_loglik_consensus_zinb(int64_t M, int N, const int32_t *y, const d
         long double acc = 0;
         for (int i = 0; i < N; i++) {
             int64_t c = j + (int64_t)i * M;
-            double xbeta = (useC ? th1[0] + th1[1] * ctrl[c] : th1[0]) + off[c];
-            double mu = exp((useC ? th1[2] + th1[3] * ctrl[c] : th1[1]) + off[c]);
+            double xbeta = (useC ? th1[0] + th1[1] * ctrl[0] : th1[0]) + off[c];  /* ctrl[0]: the ifelse quirk above */
+            double mu = exp((useC ? th1[2] + th1[3] * ctrl[0] : th1[1]) + off[c]);
             double size = useC ? th1[4] : th1[2];
             double ll00 = log(eo_dnbinom_mu(0.0, size, mu, 0) + minZero);
             double ll01 = log(eo_dnbinom_mu((double)y[c], size, mu, 0) + minZero);
@@ -551,7 +559,7 @@ EO_API void eo_loglik_consensus_zinb(int64_t M, int N, const int32_t *y, const d
         long double acc = 0;
         for (int i = 0; i < N; i++) {
             int64_t c = j + (int64_t)i * M;
-            double mu = exp((useC ? th2[0] + th2[1] * ctrl[c] : th2[0]) + off[c]);
+            double mu = exp((useC ? th2[0] + th2[1] * ctrl[0] : th2[0]) + off[c]);
             acc += log(eo_dnbinom_mu((double)y[c], size2, mu, 0) + minZero);
         }
         LL[j + M] = (double)acc;

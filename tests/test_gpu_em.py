@@ -117,29 +117,24 @@ def test_rcpp_named_api(ehmm, oracle):
         api.maxStepProb(path)
 
 
-# Free-running trajectories: psi comes out of L-BFGS-B, whose stopping rule (factr = 1e7, i.e. a
-# relative decrease of f below 2.2e-9) only determines the optimum to ~1e-6, and the rejection
-# tables are summed with atomics (order varies from run to run at the 1e-16 level).  Almost always
-# both backends take the same optimiser path and agree to ~1e-12; occasionally a last-bit
-# difference tips one line search and psi differs by ~1e-7 for an iteration before the EM
-# contracts it again.  The free-running tests therefore assert 1e-9 whenever the
-# optimiser paths coincide and 1e-6 always; the strict per-iteration gate with every input shared
-# is test_teacher_forced_iterations below.
-FREE_TOL = 1e-6
+# Free-running trajectories (same driver, same R stream, backend swapped): north_star's gate, parameters
+# within 1e-9 relative at EVERY iteration.  psi comes out of L-BFGS-B, whose stopping rule only determines
+# the optimum to ~1e-6, so the gate holds only while both backends take the same optimiser path; with the
+# rejection tables accumulated exactly (csrc/rc.cu: order-independent integer limbs) the GPU's fn / gr are
+# the same bits on every run and agree with the oracle's to ~1e-14, which keeps the paths together.
+FREE_TOL = 1e-9
 
 
 def _compare_fits(fg, fo, par_tol):
     assert len(fg["parHist"]) == len(fo["parHist"])
-    worst, tight = 0.0, 0
+    worst = 0.0
     for it, (pg, po) in enumerate(zip(fg["parHist"], fo["parHist"])):
         r = _rel(em.unlist(pg), em.unlist(po))
         worst = max(worst, r)
-        tight += r <= par_tol
-        assert r <= FREE_TOL, (it + 1, r)
+        assert r <= min(par_tol, FREE_TOL), (it + 1, r)
         hg, ho = fg["controlHist"][it], fo["controlHist"][it]
-        assert _rel(hg["bic"], ho["bic"]) <= max(1e-9, 10 * worst) and _rel(hg["q"], ho["q"]) <= max(1e-9, 10 * worst), it + 1
+        assert _rel(hg["bic"], ho["bic"]) <= 1e-9 and _rel(hg["q"], ho["q"]) <= 1e-9, it + 1
         assert hg["convergence"] == ho["convergence"]
-    assert tight >= len(fg["parHist"]) // 2          # the 1e-9 gate holds for the bulk of the iterations
     return worst
 
 

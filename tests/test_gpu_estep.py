@@ -125,6 +125,32 @@ def test_loglik_consensus(ehmm, oracle, controls):
     assert np.max(np.abs(got - ref) / np.maximum(1.0, np.abs(ref))) <= 1e-11
 
 
+def test_controls_quirk_on_bin_blocks_and_encoded_tables(ehmm, oracle):
+    """the reference's emission uses controls[1] of the WHOLE table for every cell (its ifelse() quirk,
+    R/base-loglikelihood.R:113): a bin block with m0 > 0 must be given block 0's value, and the
+    dictionary-encoded upload finds it through the first cell's group"""
+    M, N = 6001, 3
+    d = synth.make_consensus(M, N, seed=13, controls=True)
+    g = synth.make_groups(d["counts"], d["offsets"], d["controls"])
+    psi = [np.array([np.log(2.0), 0.3, 3.0]), np.array([np.log(12.0), 0.1, 4.0])]
+    ref = oracle.loglikConsensusHMM(d["counts"], d["offsets"], psi, MINZERO, d["controls"])
+    lo = 2500
+    with ehmm.Session("t_ctrl_blk", M - lo, 2) as s:
+        s.set_block(lo, M)
+        s.set_data(d["counts"][lo:], d["offsets"][lo:], d["controls"][lo:])
+        assert s.controls_first() == d["controls"][lo, 0]          # the block's own first cell: wrong for the chain
+        s.set_controls_first(d["controls"][0, 0])
+        s.loglik_consensus(psi, MINZERO)
+        got = s.fetch("logLikelihood")
+    assert np.max(np.abs(got - ref[lo:]) / np.maximum(1.0, np.abs(ref[lo:]))) <= 1e-11
+    with ehmm.Session("t_ctrl_enc", M, 2) as s:
+        s.set_data_encoded(g["group"], g["u_chip"], g["u_offsets"], g["u_controls"])
+        assert s.controls_first() == d["controls"][0, 0]
+        s.loglik_consensus(psi, MINZERO)
+        got = s.fetch("logLikelihood")
+    assert np.max(np.abs(got - ref) / np.maximum(1.0, np.abs(ref))) <= 1e-11
+
+
 def test_loglik_init(ehmm, oracle):
     M = 9001
     d = synth.make_consensus(M, 1, seed=12)

@@ -114,6 +114,64 @@ def test_blocks_on_one_gpu(ehmm, oracle, K, cuts):
             s.close()
 
 
+def test_rc_tables_do_not_depend_on_the_sharding(ehmm, oracle):
+    """Given the same posteriors, the rejection tables of a chain cut into bin blocks are bit-identical to
+    the unsharded ones: the blocks' exact integer limbs are added (here with torch, in the sharded
+    driver with an NCCL all-reduce) before the single rounding of ehmm_rc_finalize."""
+    import torch
+    M, cuts = 50021, [0, 1, 4099, 30000, 50021]
+    d = synth.make_consensus(M, 3, seed=71)
+    g = synth.make_groups(d["counts"], d["offsets"])
+    th = synth.THETA_CONSENSUS
+    st0 = oracle.RNG.set_seed(17).state()
+
+    def view(s):
+        ptr, n, integer = s.rc_buckets_device()
+        assert integer
+
+        class _B:
+            __cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 3}
+        return torch.as_tensor(_B(), device="cuda")
+
+    with ehmm.Session("inv-whole", M, 2) as whole:
+        whole.set_data(d["counts"], d["offsets"])
+        whole.set_groups(g["group"], g["u_chip"], g["u_offsets"])
+        whole.loglik_consensus(th["psi"], MINZERO)
+        whole.expstep(th["pi"], th["gamma"])
+        lp1 = whole.fetch("logProb1")
+        whole.rng_set_state(st0)
+        n_ref = whole.rc_consensus(0.05)
+        want = [whole.rc_buckets(c) for c in range(2)]
+        blocks = []
+        try:
+            for r in range(len(cuts) - 1):
+                lo, hi = cuts[r], cuts[r + 1]
+                b = ehmm.Session("inv-blk%d" % r, hi - lo, 2)
+                b.set_block(lo, M)
+                b.set_data(d["counts"][lo:hi], d["offsets"][lo:hi])
+                b.set_groups(g["group"][lo:hi], g["u_chip"], g["u_offsets"])
+                b.store("logProb1", lp1[lo:hi])
+                b.rng_set_state(st0)
+                blocks.append(b)
+            cnts = np.stack([b.rc_count(0.05) for b in blocks])
+            assert cnts.sum() == n_ref
+            for r, b in enumerate(blocks):
+                offs, total = rc_offsets(cnts, r)
+                b.rc_apply_at(0.05, offs, total)
+            for b in blocks:
+                b.sync()
+            acc = view(blocks[0])
+            for b in blocks[1:]:
+                acc += view(b)                       # the "all-reduce"
+            torch.cuda.synchronize()
+            blocks[0].rc_finalize()
+            for c in range(2):
+                assert np.array_equal(blocks[0].rc_buckets(c), want[c]), c
+        finally:
+            for b in blocks:
+                b.close()
+
+
 def _nccl_worker(rank, world, initfile, outdir):
     sys.path.insert(0, ROOT)
     import torch

@@ -179,6 +179,52 @@ def test_helas3_fixture():
     assert a.sum(0).tolist() == [104862, 75257, 86302, 59193, 91121, 85604] and a.max() == 191
 
 
+def _r_ifelse(test, yes, no):
+    """R's ifelse(): the result has the SHAPE OF `test`; `yes` / `no` are recycled (or truncated) to it.
+    With a length-1 test only yes[1] or no[1] is returned -- base R semantics, ?ifelse: "ifelse returns
+    a value with the same shape as test"."""
+    test = np.atleast_1d(np.asarray(test, dtype=bool))
+    yes, no = np.atleast_1d(yes), np.atleast_1d(no)
+    return np.where(test, np.resize(yes, test.shape), np.resize(no, test.shape))
+
+
+def test_consensus_controls_follow_r_ifelse_semantics(oracle):
+    """loglikConsensusHMM with a controls assay, R/base-loglikelihood.R:110-122 transcribed line by line
+    with R's ifelse() semantics and scipy's nbinom: `ifelse(useControl, theta[2]*controls, 0)` has a
+    length-1 test, so the control of the table's first cell is used for every cell.  Checks the oracle
+    against that transcription (not against itself) and shows the per-cell reading differs."""
+    from scipy.stats import nbinom
+    rng = np.random.default_rng(5)
+    M, N = 211, 3
+    y = rng.negative_binomial(3, 0.3, (M, N)).astype(np.int32)
+    off = np.round(rng.normal(0, 0.1, (M, N)), 3)
+    ctrl = np.log1p(rng.poisson(4.0, (M, N)).astype(float))
+    mz = 2.2250738585072014e-308
+    th = [np.array([np.log(2.0), 0.3, 3.0]), np.array([np.log(12.0), 0.1, 4.0])]
+    assert _r_ifelse(True, np.array([7.0, 8.0, 9.0]), 0).tolist() == [7.0]        # R: ifelse(TRUE, c(7,8,9), 0) is 7
+    ChIP, offsets, controls = (a.ravel(order="F") for a in (y.astype(float), off, ctrl))  # dt's long columns
+    useControl = True
+    want = np.empty((M, 2))
+    for k in range(2):
+        mu = np.exp(th[k][0] + _r_ifelse(useControl, th[k][1] * controls, 0) + offsets)
+        size = _r_ifelse(useControl, th[k][2], th[k][1])
+        cell = np.log(nbinom.pmf(ChIP, size, size / (size + mu)) + mz)
+        want[:, k] = cell.reshape(M, N, order="F").sum(1)   # rowSums(matrix(..., nrow = M, ncol = N, byrow = FALSE))
+    got = oracle.loglikConsensusHMM(np.asfortranarray(y), np.asfortranarray(off), th, mz, np.asfortranarray(ctrl))
+    assert np.max(np.abs(got - want)) <= 1e-11
+    # hand-computed cell: bin 2 of sample 2 gets the control of bin 1 of sample 1
+    mu = np.exp(th[0][0] + th[0][1] * ctrl[0, 0] + off[1, 1])
+    p = th[0][2] / (th[0][2] + mu)
+    from math import lgamma, log
+    lp = lgamma(y[1, 1] + 3.0) - lgamma(3.0) - lgamma(y[1, 1] + 1.0) + 3.0 * log(p) + y[1, 1] * log(1 - p)
+    one = oracle.loglikConsensusHMM(np.asfortranarray(y[1:2, 1:2]), np.asfortranarray(off[1:2, 1:2]), th, mz,
+                                    np.asfortranarray(ctrl[0:1, 0:1]))
+    assert abs(one[0, 0] - lp) <= 1e-12 * abs(lp)
+    # the "natural" per-cell reading is a different function
+    percell = np.log(nbinom.pmf(y, 3.0, 3.0 / (3.0 + np.exp(th[0][0] + th[0][1] * ctrl + off))) + mz).sum(1)
+    assert np.max(np.abs(percell - want[:, 0])) > 1e-3
+
+
 # ---- dist = 'zinb'  ---------------------------------------------------------
 
 def test_zinb_emission_against_scipy_twin(oracle):
@@ -199,9 +245,11 @@ def test_zinb_emission_against_scipy_twin(oracle):
             [np.array([-1.0, 0.7, 3.0]), np.array([2.0, 4.0])]
         LL = oracle.loglikConsensusHMMzinb(np.asfortranarray(y), np.asfortranarray(off), psi, mz,
                                            np.asfortranarray(ctrl) if useC else None)
-        if useC:
-            xb, mu1, s1 = psi[0][0] + psi[0][1] * ctrl + off, np.exp(psi[0][2] + psi[0][3] * ctrl + off), psi[0][4]
-            mu2, s2 = np.exp(psi[1][0] + psi[1][1] * ctrl + off), psi[1][2]
+        if useC:   # l.126-129,137 word for word, with R's ifelse (see _r_ifelse)
+            cv = ctrl.ravel(order="F")
+            xb = _r_ifelse(useC, psi[0][0] + psi[0][1] * cv, psi[0][0]) + off
+            mu1, s1 = np.exp(_r_ifelse(useC, psi[0][2] + psi[0][3] * cv, psi[0][1]) + off), psi[0][4]
+            mu2, s2 = np.exp(_r_ifelse(useC, psi[1][0] + psi[1][1] * cv, psi[1][0]) + off), psi[1][2]
         else:
             xb, mu1, s1 = psi[0][0] + off, np.exp(psi[0][1] + off), psi[0][2]
             mu2, s2 = np.exp(psi[1][0] + off), psi[1][1]
