@@ -93,6 +93,7 @@ PROTOTYPES = {
     "ehmm_rc_apply_at": [_sess, C.c_int, C.c_double, _lp, C.c_int64],
     "ehmm_rc_buckets_device": [_sess, C.POINTER(C.c_void_p), _lp, C.POINTER(C.c_int)],
     "ehmm_rc_finalize": [_sess],
+    "ehmm_rc_hint": [_sess, C.c_double],
     "ehmm_inner_mstep_sums": [_sess, _dp],
     "ehmm_rc_table_rows": [_sess, C.c_int, _lp],
     "ehmm_rc_table_fetch": [_sess, C.c_int, _dp, _dp],

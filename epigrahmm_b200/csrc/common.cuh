@@ -68,13 +68,13 @@ enum : unsigned {
 enum KernelId : int {
     KID_EMIS_TAB, KID_EMIS_GATHER, KID_EMIS_CONSENSUS, KID_EMIS_DIFF, KID_EMIS_INNER, KID_INNER_MSTEP,
     KID_FB_REDUCE, KID_FB_CARRY, KID_FB_APPLY, KID_FB_FIX, KID_FB_STATS,
-    KID_RC_COUNT, KID_RC_SCAN, KID_MT, KID_RC_APPLY, KID_RC_FINAL, KID_GLM, KID_GLM_FINAL,
+    KID_RC_COUNT, KID_RC_SCAN, KID_MT, KID_RC_APPLY, KID_RC_STATIC, KID_RC_FINAL, KID_GLM, KID_GLM_FINAL,
     KID_VIT_FWD, KID_VIT_BWD, KID_MISC, KID_COUNT
 };
 static const char *const kKernelNames[KID_COUNT] = {
     "emis_tables", "emis_gather", "emis_consensus", "emis_diff_hmm", "emis_inner", "inner_mstep",
     "fb_reduce", "fb_carry", "fb_apply", "fb_boundary_fix", "fb_stats",
-    "rc_count", "rc_scan", "mt_generate", "rc_apply", "rc_finalize", "glm", "glm_final",
+    "rc_count", "rc_scan", "mt_generate", "rc_apply", "rc_static", "rc_finalize", "glm", "glm_final",
     "viterbi_forward", "viterbi_backtrace", "misc"};
 
 // forward-backward tiling (fb.cu)
@@ -161,6 +161,16 @@ struct ehmm_session {
     // ---- emission / GLM scratch ----
     ehmm::DevBuf lgtab, glm_part, glm_ticket, misc, gtab, inner_part;
     int inner_part_blocks = 0;  // > 0: inner_part holds innerMaxStepProb partial sums for the current eta / logProb1
+    // ---- what the rejection control may reuse ----
+    uint64_t lp1_gen = 1;        // bumped whenever logProb1, the groups or the block change
+    uint64_t post_gen = 1;       // bumped whenever logProb1 or mixtureProb change
+    double rc_hint_p = -1.0;     // cut announced for the next rejection-control call (ehmm_rc_hint), else the last one used
+    uint64_t rc_counts_gen = 0;  // rc_flag holds the flagged counts per (column, warp tile) of the posteriors of
+    double rc_counts_p = -1.0;   // generation post_gen for this cut (counted by the kernel that produced them)
+    int rc_counts_cols = 0;
+    ehmm::DevBuf rc_static;      // differential model: exact limbs of the weights >= p of columns 0 and B+1, which
+    uint64_t rc_static_gen = 0;  // stay the same through the inner iterations of one E-step (generation lp1_gen,
+    double rc_static_p = -1.0;   // cut rc_static_p)
     bool glm_ticket_ready = false;
     bool encoded = false;       // data given as dt$Group + dtUnique only (no count / offset matrices)
     bool encoded_ctrl = false;
@@ -231,6 +241,12 @@ int fb_fetch_stats(ehmm_session *s);
 void rng_note_advance(ehmm_session *s, int64_t n);
 int rng_sync_host(ehmm_session *s);
 inline bool has(const ehmm_session *s, unsigned bits) { return (s->valid & bits) == bits; }
+// logProb1 (or what it is summed against: the groups, the block) changed: nothing derived from it may be reused
+inline void posteriors_changed(ehmm_session *s) {
+    s->lp1_gen++;
+    s->post_gen++;
+    s->inner_part_blocks = 0;
+}
 // emission.cu
 int emis_consensus(ehmm_session *s, const double *th1, const double *th2, int P, double minZero, const double *zi = nullptr);
 int emis_init(ehmm_session *s, const double *psi1, const double *psi2);

@@ -7,6 +7,8 @@
 // The bracket depends only on the integer count and the state's size, so it is tabulated once per
 // call (lgtab); the rest costs one exp and one log1p per (bin, sample, density).
 #include "common.cuh"
+#include "rcweights.cuh"
+#include <algorithm>
 
 namespace ehmm {
 
@@ -220,44 +222,80 @@ __global__ void __launch_bounds__(EM_NT)
 }
 
 // innerExpStep, R/base-EM.R:302-314: eta[j,b] = exp(ll_b)/sum_b exp(ll_b) with exp(ll_b)==0 -> minZero.
-// Optional fusion of innerMaxStepProb's sums (src/innerMaxStepProb.cpp:33-35): with the posterior of
-// the differential state at hand, sum_j P1[j,1]*eta[j,b] and sum_j P1[j,1] need no extra pass
-// (part[blk*(B+1) + b], reduced by colsum_kernel).
-template <int NMAX, int BMAX, bool GROUPED>
+// Two fusions, both optional (lp1 == nullptr switches them off):
+//  * innerMaxStepProb's sums (src/innerMaxStepProb.cpp:33-35): with the posterior of the differential state
+//    at hand, sum_j P1[j,1]*eta[j,b] and sum_j P1[j,1] need no extra pass (part[blk*(B+1) + b], reduced
+//    by colsum_kernel);
+//  * COUNT: the rejection control's first pass (rc.cu).  The weights it thins are P1[j,0], P1[j,1]*eta[j,b]
+//    and P1[j,2]; all are in registers here, so the number of weights below the cut `pcut` is counted per
+//    (column, warp tile of 256 bins) on the way -- the bins are walked in warp tiles for that.
+template <int NMAX, int BMAX, bool GROUPED, bool COUNT>
 __global__ void __launch_bounds__(EM_NT)
     emis_inner_kernel(int64_t M, int N, const int32_t *__restrict__ y, const double *__restrict__ off,
                       const __grid_constant__ EmisParams P, const __grid_constant__ MixParams X,
-                      const double *__restrict__ tab, double *__restrict__ eta, const double *__restrict__ lp1_col1,
-                      double *__restrict__ part) {
+                      const double *__restrict__ tab, double *__restrict__ eta, const double *__restrict__ lp1,
+                      double *__restrict__ part, double pcut, int64_t nwt, int *__restrict__ counts) {
     double acc[BMAX + 1];
 #pragma unroll
     for (int b = 0; b <= BMAX; b++) acc[b] = 0.0;
-    for (int64_t j = (int64_t)blockIdx.x * EM_NT + threadIdx.x; j < M; j += (int64_t)gridDim.x * EM_NT) {
-        double LL0, LL2, d[NMAX];
-        diff_cells<NMAX, GROUPED>(j, M, N, y, off, P, tab, LL0, LL2, d);
-        double v[BMAX], s = 0.0;
+    const int lane = threadIdx.x & 31;
+    const int64_t nwarps = (int64_t)gridDim.x * (EM_NT / 32);
+    for (int64_t tile = ((int64_t)blockIdx.x * EM_NT + threadIdx.x) >> 5; tile < nwt; tile += nwarps) {
+        int cnt0 = 0, cnt1 = 0;  // lane (c & 31) counts column c (cnt1: columns 32..63)
+#pragma unroll 1
+        for (int r = 0; r < RC_STRIPS; r++) {
+            const int64_t j = tile * RC_WT + r * 32 + lane;
+            const bool valid = j < M;
+            double v[BMAX], s = 0.0, p1 = 0.0;
+            if (valid) {
+                double LL0, LL2, d[NMAX];
+                diff_cells<NMAX, GROUPED>(j, M, N, y, off, P, tab, LL0, LL2, d);
 #pragma unroll
-        for (int b = 0; b < BMAX; b++) {
-            if (b < X.B) {
-                v[b] = exp(mix_ll<NMAX>(b, LL0, d, X));
-                if (v[b] == 0.0) v[b] = P.minZero;
-                s += v[b];
+                for (int b = 0; b < BMAX; b++) {
+                    if (b < X.B) {
+                        v[b] = exp(mix_ll<NMAX>(b, LL0, d, X));
+                        if (v[b] == 0.0) v[b] = P.minZero;
+                        s += v[b];
+                    }
+                }
+                p1 = lp1 ? exp(__ldg(lp1 + M + j)) : 0.0;
+                acc[BMAX] += p1;
+            }
+            if (COUNT) {
+                const double w0 = valid ? exp(__ldg(lp1 + j)) : 2.0;  // 2.0: never below a cut <= 1
+                const int n = __popc(__ballot_sync(0xffffffffu, rc_flagged(w0, pcut)));
+                if (lane == 0) cnt0 += n;
+            }
+#pragma unroll
+            for (int b = 0; b < BMAX; b++) {
+                if (b < X.B) {
+                    double e = 0.0;
+                    if (valid) {
+                        e = v[b] / s;  // division as in the reference (exp(ll)/sumExpLL)
+                        eta[j + (int64_t)b * M] = e;
+                        acc[b] = fma(p1, e, acc[b]);
+                    }
+                    if (COUNT) {
+                        const int n = __popc(__ballot_sync(0xffffffffu, valid && rc_flagged(rc_mix_weight(p1, e), pcut)));
+                        if (lane == ((b + 1) & 31)) { if (b + 1 < 32) cnt0 += n; else cnt1 += n; }
+                    }
+                }
+            }
+            if (COUNT) {
+                const double w2 = valid ? exp(__ldg(lp1 + 2 * M + j)) : 2.0;
+                const int n = __popc(__ballot_sync(0xffffffffu, rc_flagged(w2, pcut)));
+                const int c = X.B + 1;
+                if (lane == (c & 31)) { if (c < 32) cnt0 += n; else cnt1 += n; }
             }
         }
-        const double p1 = lp1_col1 ? exp(__ldg(lp1_col1 + j)) : 0.0;
-        acc[BMAX] += p1;
-#pragma unroll
-        for (int b = 0; b < BMAX; b++) {
-            if (b < X.B) {
-                const double e = v[b] / s;  // division as in the reference (exp(ll)/sumExpLL)
-                eta[j + (int64_t)b * M] = e;
-                acc[b] = fma(p1, e, acc[b]);
-            }
+        if (COUNT) {
+            if (lane < X.B + 2) counts[(int64_t)lane * nwt + tile] = cnt0;
+            if (lane + 32 < X.B + 2) counts[(int64_t)(lane + 32) * nwt + tile] = cnt1;
         }
     }
-    if (lp1_col1) {
+    if (lp1) {
         __shared__ double sh[(EM_NT / 32) * (BMAX + 1)];
-        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+        const int w = threadIdx.x >> 5;
 #pragma unroll
         for (int b = 0; b <= BMAX; b++) {
 #pragma unroll
@@ -297,21 +335,20 @@ __global__ void __launch_bounds__(256) inner_mstep_kernel(int64_t M, int B, cons
     }
 }
 
+// out[c] = sum_i part[i*ncol + c]: one CTA per column, fixed order
 __global__ void __launch_bounds__(256) colsum_kernel(const double *__restrict__ part, int nblk, int ncol,
                                                      double *__restrict__ out) {
     __shared__ double sh[256];
-    for (int c = 0; c < ncol; c++) {
-        double s = 0.0;
-        for (int i = threadIdx.x; i < nblk; i += 256) s += part[(int64_t)i * ncol + c];
-        sh[threadIdx.x] = s;
-        __syncthreads();
-        for (int d = 128; d > 0; d >>= 1) {
-            if ((int)threadIdx.x < d) sh[threadIdx.x] += sh[threadIdx.x + d];
-            __syncthreads();
-        }
-        if (threadIdx.x == 0) out[c] = sh[0];
+    const int c = blockIdx.x;
+    double s = 0.0;
+    for (int i = threadIdx.x; i < nblk; i += 256) s += part[(int64_t)i * ncol + c];
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int d = 128; d > 0; d >>= 1) {
+        if ((int)threadIdx.x < d) sh[threadIdx.x] += sh[threadIdx.x + d];
         __syncthreads();
     }
+    if (threadIdx.x == 0) out[c] = sh[0];
 }
 
 int grid_for(int64_t M) {
@@ -507,19 +544,31 @@ int emis_inner_estep(ehmm_session *s, const double *delta, const double *psi, do
     EHMM_TRY(fill_mix(s, X, delta));
     EHMM_TRY(prepare_tab(s, P, 2, minZero));
     EHMM_TRY(s->eta.reserve(sizeof(double) * s->M * s->B));
-    const int g = grid_for(s->M);
+    // one warp tile per warp while that keeps the grid within a few waves
+    const int g = (int)std::min<int64_t>((rc_num_wtiles(s->M) + EM_NT / 32 - 1) / (EM_NT / 32), 148 * 64);
     const int32_t *src_y = s->d_counts;
     const double *src_off = s->d_offsets, *src_tab = s->lgtab.as<double>();
     EHMM_TRY(diff_source(s, P, src_y, src_off, src_tab));
-    // fuse innerMaxStepProb's sums when the posteriors of the current E-step are in place
+    // fuse innerMaxStepProb's sums when the posteriors of the current E-step are in place, and the
+    // rejection control's flagged counts when the cut its next call will use is known (ehmm_rc_hint, or
+    // the previous call's cut: max(0.9^iter, probCut) is constant once it has reached probCut)
     const bool fuse = has(s, DS_P1) && s->K == 3;
-    const double *lp1c = fuse ? s->logProb1.as<double>() + s->M : nullptr;
+    const double pcut = s->rc_hint_p;
+    const bool count = fuse && pcut > 0.0 && s->G > 0 && s->B + 2 <= 64;
+    const double *lp1 = fuse ? s->logProb1.as<double>() : nullptr;
+    const int64_t nwt = rc_num_wtiles(s->M);
+    if (count) EHMM_TRY(s->rc_flag.reserve(sizeof(int) * nwt * (s->B + 2)));
     EHMM_TRY(s->inner_part.reserve(sizeof(double) * ((size_t)g * (s->B + 1) + s->B + 1)));
     double *part = s->inner_part.as<double>();
     const bool grouped = (src_y == nullptr);
-#define EHMM_INNER(NM, BM, GR)                                                                                        \
-    PROF(s, KID_EMIS_INNER), emis_inner_kernel<NM, BM, GR><<<g, EM_NT, 0, s->stream>>>(s->M, s->N, src_y, src_off, P, X, \
-                                                                                       src_tab, s->eta.as<double>(), lp1c, part)
+#define EHMM_INNER2(NM, BM, GR, CT)                                                                                   \
+    PROF(s, KID_EMIS_INNER), emis_inner_kernel<NM, BM, GR, CT><<<g, EM_NT, 0, s->stream>>>(                           \
+        s->M, s->N, src_y, src_off, P, X, src_tab, s->eta.as<double>(), lp1, part, pcut, nwt, s->rc_flag.as<int>())
+#define EHMM_INNER(NM, BM, GR)                        \
+    do {                                              \
+        if (count) EHMM_INNER2(NM, BM, GR, true);     \
+        else EHMM_INNER2(NM, BM, GR, false);          \
+    } while (0)
     // the loops over samples and components are unrolled to the template bounds: tight bounds for the
     // dictionary-encoded source (B = 6 / 30 / 14 in BASELINE configs 3-5), wide ones for the per-cell fallback
 #define EHMM_INNER_B(NM)                               \
@@ -543,8 +592,15 @@ int emis_inner_estep(ehmm_session *s, const double *delta, const double *psi, do
     }
 #undef EHMM_INNER_B
 #undef EHMM_INNER
-    s->inner_part_blocks = fuse ? g : 0;
+#undef EHMM_INNER2
     EHMM_CK(cudaGetLastError());
+    s->post_gen++;  // mixtureProb changed
+    s->inner_part_blocks = fuse ? g : 0;
+    if (count) {
+        s->rc_counts_gen = s->post_gen;
+        s->rc_counts_p = pcut;
+        s->rc_counts_cols = s->B + 2;
+    }
     s->valid |= DS_ETA;
     return EHMM_OK;
 }
@@ -567,7 +623,7 @@ int inner_mstep_sums(ehmm_session *s, double *sums) {
         PROF(s, KID_INNER_MSTEP), inner_mstep_kernel<<<nblk, 256, 0, s->stream>>>(s->M, B, s->logProb1.as<double>() + s->M, s->eta.as<double>(), part);
         EHMM_CK(cudaGetLastError());
     }
-    PROF(s, KID_MISC), colsum_kernel<<<1, 256, 0, s->stream>>>(part, nblk, B + 1, out);
+    PROF(s, KID_MISC), colsum_kernel<<<B + 1, 256, 0, s->stream>>>(part, nblk, B + 1, out);
     EHMM_CK(cudaGetLastError());
     EHMM_CK(cudaMemcpyAsync(s->h_pinned + 64, out, sizeof(double) * (B + 1), cudaMemcpyDeviceToHost, s->stream));
     EHMM_CK(cudaStreamSynchronize(s->stream));

@@ -219,6 +219,7 @@ int build_groups(ehmm_session *s, int64_t *G_out) {
     EHMM_CK(cudaStreamSynchronize(s->stream));
     EHMM_REQUIRE(hf == 0, EHMM_ERR_STATE, "build_groups: 64-bit key-hash collision detected; group the table on the host instead");
     s->G = (int64_t)G;
+    posteriors_changed(s);
     s->group_first.assign(firstsorted.begin(), firstsorted.end());
     s->groups_consistent = true;
     s->rc_columns = 0;

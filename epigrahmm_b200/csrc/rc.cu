@@ -29,6 +29,7 @@
 // Uniforms come either from a caller-supplied buffer (parity harness: the oracle consumes the same
 // buffer) or from R's MT19937 stream generated on the device from the session's .Random.seed.
 #include "common.cuh"
+#include "rcweights.cuh"
 #include <algorithm>
 #include <vector>
 
@@ -38,8 +39,6 @@ namespace {
 
 constexpr int RC_NT = 256;                  // threads per CTA
 constexpr int RC_NW = RC_NT / 32;           // warps = warp tiles per CTA
-constexpr int RC_STRIPS = 8;
-constexpr int RC_WT = 32 * RC_STRIPS;       // bins per warp tile
 constexpr int RC_TB = RC_NT * RC_STRIPS;    // bins per block of the exported reweight() helper
 constexpr int RC_MAXCOL = EHMM_MAX_B + 2;   // 64
 constexpr double RC_EXACT_MIN_P = 0.001953125;  // 2^-9: smallest cut whose survivors are exact 62-bit fixed-point numbers
@@ -79,9 +78,8 @@ template <bool DIFF> __device__ __forceinline__ double rc_weight(const RCSrc &S,
     if (!DIFF) return c == 0 ? p1[0] : p1[1];
     if (c == 0) return p1[0];
     if (c == S.B + 1) return p1[2];
-    return __dmul_rn(p1[1], __ldg(S.eta + (int64_t)(c - 1) * S.M + j));
+    return rc_mix_weight(p1[1], __ldg(S.eta + (int64_t)(c - 1) * S.M + j));
 }
-__device__ __forceinline__ bool rc_flagged(double x, double p) { return x < p && x / p != 0.0; }
 
 // lane (c & 31) of the warp keeps the running count of column c (two registers cover 64 columns)
 template <bool DIFF>
@@ -202,17 +200,22 @@ template <> __device__ __forceinline__ double get_unif<uint32_t>(const uint32_t 
     return mt_to_unif(__ldg(u + i));
 }
 
-// exact accumulation: w * 2^62 (an integer for w in [2^-9, 2)) as two 31-bit limbs in 64-bit words
-__device__ __forceinline__ void limb_add(unsigned long long *L, double w) {
+// exact accumulation: w * 2^62 (an integer for w in [2^-9, 2)) as two 31-bit limbs in 64-bit words.  The
+// two limbs of an entry live in separate arrays (lo[i], hi[i] = lo[i + cells]): atomics on one 32-byte sector
+// serialise in L2, so adjacent limbs would double the cost of a frequent group
+// (tools/probes/red_probe.cu: 11.0 ms against 4.8 ms for 15 M adds over 200 zipf-distributed groups).
+__device__ __forceinline__ void limb_add(unsigned long long *lo, int64_t cells, double w) {
     const unsigned long long v = __double2ull_rz(w * 4611686018427387904.0);
-    atomicAdd(L, v & 0x7fffffffull);
-    atomicAdd(L + 1, v >> 31);
+    atomicAdd(lo, v & 0x7fffffffull);
+    atomicAdd(lo + cells, v >> 31);
 }
 
 // nrep = 1 for the consensus model (only f[0..M-1] is read, Q6 in SURVEY.md); nrep = N for the
 // differential model (repmat(w, N, 1) against the M*N group ids).
-// EXACT: integer limbs (acc = limbs, 2 words per (column, group)); else fp64 atomics (acc = buckets).
-template <bool DIFF, typename UT, bool EXACT>
+// EXACT: integer limbs (acc = limbs: lo[cells] then hi[cells]); else fp64 atomics (acc = buckets).
+// SKIPST (differential, exact): the weights >= p of columns 0 and B+1 were summed once for this E-step
+// (rc_static_kernel) and are already in the limbs; only the survivors of the thinning are added here.
+template <bool DIFF, typename UT, bool EXACT, bool SKIPST>
 __global__ void __launch_bounds__(RC_NT)
     rc_apply_kernel(RCSrc S, double p, int64_t nwt, const uint32_t *__restrict__ tileoff, const __grid_constant__ RCBase ub,
                     const UT *__restrict__ unif, const int32_t *__restrict__ group, int nrep, int64_t G,
@@ -222,6 +225,7 @@ __global__ void __launch_bounds__(RC_NT)
     const int64_t tile = (int64_t)blockIdx.x * RC_NW + (threadIdx.x >> 5);
     if (tile >= nwt) return;
     const bool thin = p > 0.0;
+    const int64_t cells = (int64_t)S.columns * (G + 1);
     // lane (c & 31) holds the running rank and the uniform offset of column c (and of column c + 32)
     int cnt0 = 0, cnt1 = 0;
     int64_t off0 = 0, off1 = 0;
@@ -229,13 +233,13 @@ __global__ void __launch_bounds__(RC_NT)
         if (lane < S.columns) off0 = ub.ubase[lane] + tileoff[(int64_t)lane * nwt + tile];
         if (lane + 32 < S.columns) off1 = ub.ubase[lane + 32] + tileoff[(int64_t)(lane + 32) * nwt + tile];
     }
-#pragma unroll 1
+#pragma unroll 2
     for (int r = 0; r < RC_STRIPS; r++) {
         const int64_t j = tile * RC_WT + r * 32 + lane;
         const bool valid = j < S.M;
         double p1[3] = {2.0, 2.0, 2.0};
         if (valid) rc_posteriors<DIFF>(S, j, p1);
-#pragma unroll 1
+#pragma unroll 4
         for (int c = 0; c < S.columns; c++) {
             double x = valid ? rc_weight<DIFF>(S, p1, c, j) : 2.0;
             const bool flag = rc_flagged(x, p);
@@ -247,11 +251,12 @@ __global__ void __launch_bounds__(RC_NT)
                 if (lane == (c & 31)) { if (c < 32) cnt0 += __popc(bal); else cnt1 += __popc(bal); }
             }
             // x < p without a flag is x == 0 (x / p == 0): stays 0
-            if (valid && x != 0.0) {
+            const bool cached = SKIPST && !flag && (c == 0 || c == S.columns - 1);
+            if (valid && x != 0.0 && !cached) {
                 const int64_t row = (int64_t)c * (G + 1);
                 for (int i = 0; i < nrep; i++) {
                     const int g = __ldg(group + j + (int64_t)i * S.M);
-                    if (EXACT) limb_add(reinterpret_cast<unsigned long long *>(acc) + 2 * (row + g), x);
+                    if (EXACT) limb_add(reinterpret_cast<unsigned long long *>(acc) + row + g, cells, x);
                     else atomicAdd(reinterpret_cast<double *>(acc) + row + g, x);
                 }
             }
@@ -266,23 +271,41 @@ __global__ void __launch_bounds__(RC_NT)
     }
 }
 
+// differential model: the weights >= p of the background and the enrichment column (P1[,0], P1[,2]) do not
+// change through the inner iterations that follow one E-step (only mixtureProb and the draws do), and
+// exact sums can be split any way: their limbs are accumulated once (st: lo[2*(G+1)] then hi[2*(G+1)],
+// column 0 first) and copied under every inner iteration's tables.
+__global__ void __launch_bounds__(RC_NT)
+    rc_static_kernel(RCSrc S, double p, const int32_t *__restrict__ group, int nrep, int64_t G,
+                     unsigned long long *__restrict__ st) {
+    const int64_t cells = 2 * (G + 1);
+    for (int64_t j = (int64_t)blockIdx.x * RC_NT + threadIdx.x; j < S.M; j += (int64_t)gridDim.x * RC_NT) {
+        double p1[3];
+        rc_posteriors<true>(S, j, p1);
+        const bool k0 = p1[0] >= p, k2 = p1[2] >= p;   // not below the cut: kept as they are
+        if (k0 || k2) {
+            for (int i = 0; i < nrep; i++) {
+                const int g = __ldg(group + j + (int64_t)i * S.M);
+                if (k0) limb_add(st + g, cells, p1[0]);
+                if (k2) limb_add(st + (G + 1) + g, cells, p1[2]);
+            }
+        }
+    }
+}
+
 // limbs -> fp64 table entries: ((hi + carry) * 2^31 + lo) * 2^-62, rounded once (the integer is exact);
 // a rank/count mismatch in the apply kernel poisons the tables instead of leaving them plausible
 __global__ void __launch_bounds__(256) rc_finalize_kernel(const unsigned long long *__restrict__ limbs, int64_t n,
                                                           double *__restrict__ buckets, const int *__restrict__ err) {
     const bool bad = err && *err != 0;
     for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
-        const unsigned long long lo = limbs[2 * i], hi = limbs[2 * i + 1];
+        const unsigned long long lo = limbs[i], hi = limbs[i + n];
         const unsigned long long A = hi + (lo >> 31), l = lo & 0x7fffffffull;
         const double v = __dadd_rn((double)A * 4.656612873077392578125e-10, (double)l * 2.16840434497100886801e-19);
         buckets[i] = bad ? __longlong_as_double(0x7ff8000000000000ll) : v;
     }
 }
 
-// exported aggregate(): the elements of every group are listed in ascending index order (a stable
-// counting sort done on the host, which has to walk f anyway to validate it) and one thread adds a
-// group's elements in that order -- the order of the reference's loop (src/aggregate.cpp:23-30), so
-// the sums carry the reference's own roundings bit for bit.
 __global__ void aggregate_kernel(const double *__restrict__ x, const int64_t *__restrict__ start,
                                  const int64_t *__restrict__ perm, int64_t G, double *__restrict__ buckets) {
     const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -366,12 +389,20 @@ int reserve_rc(ehmm_session *s, const RCSrc &S) {
 // (it has to know how many uniforms to generate), which is the call's one synchronisation
 template <bool DIFF> int count_and_scan(ehmm_session *s, const RCSrc &S, double p, int64_t *coltot) {
     const int64_t nwt = num_wtiles(s->M);
+    s->rc_hint_p = p;  // the next call most likely uses the same cut (max(0.9^iter, probCut) settles at probCut)
     if (!(p > 0.0)) {
         for (int c = 0; c < S.columns; c++) coltot[c] = 0;
         return EHMM_OK;
     }
-    PROF(s, KID_RC_COUNT), rc_count_kernel<DIFF><<<tile_grid(nwt), RC_NT, 0, s->stream>>>(S, p, nwt, s->rc_flag.as<int>());
-    EHMM_CK(cudaGetLastError());
+    // the kernel that produced these posteriors may have counted already (innerExpStep / the E-step, told the cut)
+    const bool counted = s->rc_counts_gen == s->post_gen && s->rc_counts_p == p && s->rc_counts_cols == S.columns;
+    if (!counted) {
+        PROF(s, KID_RC_COUNT), rc_count_kernel<DIFF><<<tile_grid(nwt), RC_NT, 0, s->stream>>>(S, p, nwt, s->rc_flag.as<int>());
+        EHMM_CK(cudaGetLastError());
+        s->rc_counts_gen = s->post_gen;
+        s->rc_counts_p = p;
+        s->rc_counts_cols = S.columns;
+    }
     PROF(s, KID_RC_SCAN), rc_scan_kernel<<<S.columns, 1024, 0, s->stream>>>(s->rc_flag.as<int>(), nwt, s->rc_scan.as<uint32_t>(),
                                                                            s->rc_coltot.as<int64_t>());
     EHMM_CK(cudaGetLastError());
@@ -388,15 +419,41 @@ int launch_apply(ehmm_session *s, const RCSrc &S, double p, int nrep, const RCBa
     const int64_t nwt = num_wtiles(s->M);
     const size_t cells = (size_t)S.columns * (s->G + 1);
     const bool exact = p >= RC_EXACT_MIN_P;
+    const size_t LW = sizeof(unsigned long long);
     EHMM_CK(cudaMemsetAsync(err_flag(s), 0, sizeof(int), s->stream));
     if (exact) {
-        EHMM_CK(cudaMemsetAsync(s->rc_limbs.p, 0, 2 * sizeof(unsigned long long) * cells, s->stream));
-        PROF(s, KID_RC_APPLY), rc_apply_kernel<DIFF, UT, true><<<tile_grid(nwt), RC_NT, 0, s->stream>>>(
-            S, p, nwt, s->rc_scan.as<uint32_t>(), ub, unif, s->group.as<int32_t>(), nrep, s->G, s->rc_limbs.p,
-            s->rc_flag.as<int>(), err_flag(s));
+        unsigned long long *limbs = s->rc_limbs.as<unsigned long long>();
+        EHMM_CK(cudaMemsetAsync(limbs, 0, 2 * LW * cells, s->stream));
+        if (DIFF) {
+            const size_t G1 = (size_t)s->G + 1;
+            if (!(s->rc_static_gen == s->lp1_gen && s->rc_static_p == p)) {
+                EHMM_TRY(s->rc_static.reserve(4 * LW * G1));
+                EHMM_CK(cudaMemsetAsync(s->rc_static.p, 0, 4 * LW * G1, s->stream));
+                const unsigned grid = (unsigned)std::min<int64_t>((s->M + RC_NT - 1) / RC_NT, 148 * 16);
+                PROF(s, KID_RC_STATIC), rc_static_kernel<<<grid, RC_NT, 0, s->stream>>>(S, p, s->group.as<int32_t>(), nrep, s->G,
+                                                                                     s->rc_static.as<unsigned long long>());
+                EHMM_CK(cudaGetLastError());
+                s->rc_static_gen = s->lp1_gen;
+                s->rc_static_p = p;
+            }
+            // static limbs (lo: column 0, column B+1; hi: the same) under this call's tables
+            const unsigned long long *st = s->rc_static.as<unsigned long long>();
+            const size_t last = (size_t)(S.columns - 1) * G1;
+            EHMM_CK(cudaMemcpyAsync(limbs, st, LW * G1, cudaMemcpyDeviceToDevice, s->stream));
+            EHMM_CK(cudaMemcpyAsync(limbs + last, st + G1, LW * G1, cudaMemcpyDeviceToDevice, s->stream));
+            EHMM_CK(cudaMemcpyAsync(limbs + cells, st + 2 * G1, LW * G1, cudaMemcpyDeviceToDevice, s->stream));
+            EHMM_CK(cudaMemcpyAsync(limbs + cells + last, st + 3 * G1, LW * G1, cudaMemcpyDeviceToDevice, s->stream));
+            PROF(s, KID_RC_APPLY), rc_apply_kernel<DIFF, UT, true, DIFF><<<tile_grid(nwt), RC_NT, 0, s->stream>>>(
+                S, p, nwt, s->rc_scan.as<uint32_t>(), ub, unif, s->group.as<int32_t>(), nrep, s->G, limbs, s->rc_flag.as<int>(),
+                err_flag(s));
+        } else {
+            PROF(s, KID_RC_APPLY), rc_apply_kernel<DIFF, UT, true, false><<<tile_grid(nwt), RC_NT, 0, s->stream>>>(
+                S, p, nwt, s->rc_scan.as<uint32_t>(), ub, unif, s->group.as<int32_t>(), nrep, s->G, limbs, s->rc_flag.as<int>(),
+                err_flag(s));
+        }
     } else {
         EHMM_CK(cudaMemsetAsync(s->rc_buckets.p, 0, sizeof(double) * cells, s->stream));
-        PROF(s, KID_RC_APPLY), rc_apply_kernel<DIFF, UT, false><<<tile_grid(nwt), RC_NT, 0, s->stream>>>(
+        PROF(s, KID_RC_APPLY), rc_apply_kernel<DIFF, UT, false, false><<<tile_grid(nwt), RC_NT, 0, s->stream>>>(
             S, p, nwt, s->rc_scan.as<uint32_t>(), ub, unif, s->group.as<int32_t>(), nrep, s->G, s->rc_buckets.p,
             s->rc_flag.as<int>(), err_flag(s));
     }

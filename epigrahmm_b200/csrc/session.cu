@@ -252,7 +252,7 @@ int ehmm_session_close(ehmm_session *s) {
     DevBuf *bufs[] = {&s->counts_own, &s->offsets_own, &s->controls_own, &s->group, &s->u_chip, &s->u_off, &s->u_ctrl,
                       &s->u_dsg, &s->logf, &s->logFP, &s->logBP, &s->logProb1, &s->logProb2, &s->eta, &s->viterbi, &s->vit_bp,
                       &s->tileops, &s->carries, &s->tilestats, &s->fbscal, &s->rangeops, &s->rangecarry, &s->rc_flag, &s->rc_scan,
-                      &s->rc_buckets, &s->rc_unif, &s->rc_tmp, &s->mt_raw, &s->mt_raw2, &s->mt_windows, &s->gtab, &s->glm_ticket, &s->inner_part, &s->lgtab, &s->glm_part, &s->misc};
+                      &s->rc_buckets, &s->rc_limbs, &s->rc_coltot, &s->rc_static, &s->rc_unif, &s->rc_tmp, &s->mt_raw, &s->mt_raw2, &s->mt_windows, &s->gtab, &s->glm_ticket, &s->inner_part, &s->lgtab, &s->glm_part, &s->misc};
     for (DevBuf *b : bufs) b->release();
     for (int i = 0; i < 2; i++) {
         s->stage[i].release();
@@ -288,6 +288,7 @@ int ehmm_session_set_block(ehmm_session *s, int64_t m0, int64_t Mtot) {
     EHMM_REQUIRE(m0 >= 0 && m0 + s->M <= Mtot, EHMM_ERR_ARG, "block [%lld, %lld) outside chain of %lld bins", (long long)m0,
                  (long long)(m0 + s->M), (long long)Mtot);
     s->m0 = m0;
+    posteriors_changed(s);
     s->Mtot = Mtot;
     return EHMM_OK;
 }
@@ -371,6 +372,7 @@ int ehmm_set_groups(ehmm_session *s, const int32_t *group, int64_t G, const doub
     s->groups_consistent = (hb == 0) && (!s->d_controls || u_controls);
     s->G = G;
     s->rc_columns = 0;
+    posteriors_changed(s);
     return EHMM_OK;
 }
 
@@ -402,6 +404,7 @@ int ehmm_groups_remap(ehmm_session *s, const int32_t *new_id, int64_t G_new, con
     EHMM_TRY(upload_unique(s, G_new, u_chip, u_offsets, u_controls, u_dsg));
     EHMM_CK(cudaStreamSynchronize(s->stream));
     s->G = G_new;
+    posteriors_changed(s);
     s->groups_consistent = true;
     s->rc_columns = 0;
     return EHMM_OK;
@@ -523,6 +526,7 @@ static int set_encoded(ehmm_session *s, int N, const int32_t *group, const uint1
     s->groups_consistent = true;
     s->G = G;
     s->rc_columns = 0;
+    posteriors_changed(s);
     return EHMM_OK;
 }
 
@@ -589,7 +593,7 @@ int ehmm_expstep(ehmm_session *s, const double *pi, const double *gamma, const d
     EHMM_TRY(fb_expstep(s, d_logf));
     s->valid |= DS_ESTEP;
     s->stats_stale = false;
-    s->inner_part_blocks = 0;
+    posteriors_changed(s);
     return EHMM_OK;
 }
 
@@ -600,7 +604,7 @@ int ehmm_expstep_device(ehmm_session *s, const double *pi, const double *gamma, 
     EHMM_TRY(fb_expstep(s, logf_device));
     s->valid |= DS_ESTEP;
     s->stats_stale = false;
-    s->inner_part_blocks = 0;
+    posteriors_changed(s);
     return EHMM_OK;
 }
 
@@ -623,7 +627,7 @@ int ehmm_expstep_apply(ehmm_session *s, const double *fwd_carry, const double *b
     s->reduce_pending = false;
     s->valid |= DS_ESTEP;
     s->stats_stale = false;
-    s->inner_part_blocks = 0;
+    posteriors_changed(s);
     return EHMM_OK;
 }
 
@@ -680,7 +684,7 @@ int ehmm_expstep_apply_ops(ehmm_session *s, const double *ops_all, int P, int ra
     s->reduce_pending = false;
     s->valid |= DS_ESTEP;
     s->stats_stale = false;
-    s->inner_part_blocks = 0;
+    posteriors_changed(s);
     return EHMM_OK;
 }
 
@@ -878,6 +882,12 @@ int ehmm_rc_buckets_device(ehmm_session *s, void **ptr, int64_t *n, int *is_inte
     return EHMM_OK;
 }
 
+int ehmm_rc_hint(ehmm_session *s, double p) {
+    EHMM_REQUIRE(s && p >= 0.0 && p <= 1.0, EHMM_ERR_ARG, "rc_hint: p must lie in [0, 1]");
+    s->rc_hint_p = p;
+    return EHMM_OK;
+}
+
 int ehmm_rc_finalize(ehmm_session *s) {
     EHMM_TRY(check_session(s));
     EHMM_REQUIRE(s->rc_columns > 0, EHMM_ERR_STATE, "no rejection tables");
@@ -1033,7 +1043,7 @@ int ehmm_store(ehmm_session *s, const char *name, const double *src, int64_t row
     EHMM_CK(cudaMemcpyAsync(d.buf->p, src, sizeof(double) * rows * cols, cudaMemcpyHostToDevice, s->stream));
     EHMM_CK(cudaStreamSynchronize(s->stream));
     s->valid |= d.bit;
-    s->inner_part_blocks = 0;
+    posteriors_changed(s);
     if (d.bit & (DS_ESTEP | DS_LOGF)) {
         // a dataset was replaced from the host: the fused statistics no longer describe it
         s->stats_on_host = false;

@@ -432,6 +432,8 @@ def innerEMDifferential(theta_old, backend, probCut, control, dist="nb"):
     tmp_old = copy.deepcopy(theta_old)
     tmp_new = copy.deepcopy(theta_old)
     optimMLE = None
+    if hasattr(backend, "rc_hint"):   # the cut is known before the posteriors are computed: let their kernel count for it
+        backend.rc_hint(probCut)
     while count < control["maxIterInnerEM"] and error > control["epsilonInnerEM"]:
         psi_flat = np.concatenate([np.ravel(p) for p in tmp_old["psi"]])
         inner_expstep(tmp_old["delta"], psi_flat, control["minZero"])

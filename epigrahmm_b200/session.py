@@ -307,6 +307,10 @@ class Session:
         check(lib.ehmm_rng_get_state(self._h, st.ctypes.data_as(C.POINTER(C.c_uint32))))
         return st
 
+    def rc_hint(self, p):
+        """announce the next rejection-control call's cut (lets the E-step / innerExpStep count for it)"""
+        check(lib.ehmm_rc_hint(self._h, float(p)))
+
     def rc_consensus(self, p, uniforms=None) -> int:
         u = None if uniforms is None else _f64(uniforms)
         n = C.c_int64()

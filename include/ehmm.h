@@ -179,6 +179,12 @@ int ehmm_estep_set_stats(ehmm_session *s, const double *stats, const double *log
 /* R's Mersenne-Twister state: state[0] = mti, state[1..624] = mt (.Random.seed[2:626]). */
 int ehmm_rng_set_state(ehmm_session *s, const uint32_t *state625);
 int ehmm_rng_get_state(ehmm_session *s, uint32_t *state625);
+/* Optional: announce the cut p of the NEXT rejection-control call.  The kernels that produce the posterior
+ * weights (innerExpStep; the E-step) then count the weights below p on the way and the rejection control
+ * skips its own counting pass.  Without a hint the previous call's cut is assumed (the reference's
+ * rejectionCut = max(0.9^iter, probCut), R/base-EM.R:119-121, is constant once it has reached probCut); a
+ * call with another cut simply counts for itself, so a wrong hint costs time, never correctness. */
+int ehmm_rc_hint(ehmm_session *s, double p);
 /* consensusRejectionControlled, src/consensusRejectionControlled.cpp:14-31.
  * uniforms: host buffer of unif_rand() draws to consume in order, or NULL to draw
  * from the session's Mersenne-Twister on the device.  consumed: draws used. */
