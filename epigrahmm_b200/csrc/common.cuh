@@ -145,6 +145,7 @@ struct ehmm_session {
     ehmm::DevBuf rc_limbs, rc_coltot;  // exact accumulators (2 x u64 per table entry); column totals + error flag
     bool rc_exact = false;       // the last rejection tables were accumulated as exact limbs ...
     bool rc_final = false;       // ... and have been rounded into rc_buckets
+    int mt_shift = 0;            // sub-streams are 2^(17 + mt_shift) words long (mt_choose_stride)
     int64_t mtj_valid = 0;       // sub-stream windows valid for the state in mt_raw
     bool mtj_pending = false;    // ... being computed on stream2 (event ev)
     bool mtj_base = false;       // window 0 is in place
@@ -274,6 +275,7 @@ int mt_generate_range(ehmm_session *s, int64_t lo_rel, int64_t n, uint32_t *out)
 int mt_advance(ehmm_session *s, int64_t n);
 int mt_advance_side(ehmm_session *s, int64_t n, void *h_state);
 int mt_prefetch(ehmm_session *s, int64_t max_draws);
+int mt_choose_stride(ehmm_session *s, int64_t draws);
 int mt_prefetch_ranges(ehmm_session *s, int nr, const int64_t *lo, const int64_t *n, int64_t total, int margin);
 // glm.cu
 int glm_nb(ehmm_session *s, int column, const double *par, int P, double *value, double *grad);

@@ -198,7 +198,8 @@ __device__ __forceinline__ double mix_ll(int b, double LL0, const double *d, con
     double s = 0.0;
     const uint64_t mk = X.mask[b];
 #pragma unroll
-    for (int i = 0; i < NMAX; i++) s += ((mk >> i) & 1ull) ? d[i] : 0.0;
+    for (int i = 0; i < NMAX; i++)
+        if ((mk >> i) & 1ull) s += d[i];  // mk is uniform: a predicated add (adding 0.0 instead is the same sum)
     return X.ldelta[b] + (LL0 + s);
 }
 

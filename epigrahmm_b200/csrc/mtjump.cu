@@ -92,14 +92,15 @@ __global__ void __launch_bounds__(JUMP_NT) mt_jump_kernel(const uint16_t *__rest
 // containing the last drawn word, and mti).
 __global__ void __launch_bounds__(GEN_NT)
     mt_generate_kernel(const uint32_t *__restrict__ state, const uint32_t *__restrict__ S, int s_first, int64_t lo_rel,
-                       int64_t hi_rel, uint32_t *__restrict__ out, int64_t n_state, uint32_t *__restrict__ state_out) {
+                       int64_t hi_rel, uint32_t *__restrict__ out, int64_t n_state, uint32_t *__restrict__ state_out,
+                       int64_t jw) {
     __shared__ uint32_t buf[2][MT_N];
     const int tid = threadIdx.x;
     const int s = s_first + blockIdx.x;
     const int64_t pos = state[0];
     const int64_t lo_abs = pos + lo_rel, hi_abs = pos + hi_rel;
-    const int64_t a0 = (s == 0) ? 0 : 1 + (int64_t)s * JW;
-    const int64_t nxt = 1 + (int64_t)(s + 1) * JW;
+    const int64_t a0 = (s == 0) ? 0 : 1 + (int64_t)s * jw;
+    const int64_t nxt = 1 + (int64_t)(s + 1) * jw;
     const int64_t lo = max(lo_abs, a0), hi = min(hi_abs, nxt);
     int64_t gen_end = (lo < hi) ? hi : a0;
     int64_t st_lo = 0, st_hi = 0, st_end = 0;  // this CTA writes state words [max(a0, st_lo), st_end)
@@ -179,10 +180,15 @@ int device_polys(int device, const uint16_t **out) {
     return EHMM_OK;
 }
 
-int64_t substreams_for(int64_t pos, int64_t n) {  // sub-streams touched by draws [pos, pos + n)
+// Sub-streams are JW << mt_shift words long: a call that draws 1e8 uniforms would otherwise need 800
+// windows, and the jump that produces a window costs as much as generating a fifth of a sub-stream.  The
+// squaring chain x^(JW * 2^k) already holds the polynomials of the longer strides (level k + mt_shift).
+inline int64_t jw_of(const ehmm_session *s) { return JW << s->mt_shift; }
+
+int64_t substreams_for(const ehmm_session *s, int64_t pos, int64_t n) {  // sub-streams touched by draws [pos, pos + n)
     if (n <= 0) return 0;
     const int64_t last = pos + n - 1;
-    return (last <= 0 ? 0 : (last - 1) / JW) + 1;
+    return (last <= 0 ? 0 : (last - 1) / jw_of(s)) + 1;
 }
 
 }  // namespace
@@ -191,7 +197,9 @@ namespace {
 
 int launch_jump(ehmm_session *s, cudaStream_t st, const uint16_t *idx, int k, const uint32_t *src, uint32_t *dst, int64_t cnt) {
     EHMM_CK(cudaMemsetAsync(dst, 0, sizeof(uint32_t) * MT_N * (size_t)cnt, st));
-    mt_jump_kernel<<<dim3((unsigned)cnt, JUMP_SPLIT), JUMP_NT, JUMP_SMEM, st>>>(idx + (size_t)k * MAX_IDX, g_nidx[k], src, dst);
+    const int lv = k + s->mt_shift;  // level of the polynomial x^(jw_of(s) * 2^k)
+    EHMM_REQUIRE(lv < LEVELS, EHMM_ERR_RNG, "draw position beyond the prepared jump polynomials");
+    mt_jump_kernel<<<dim3((unsigned)cnt, JUMP_SPLIT), JUMP_NT, JUMP_SMEM, st>>>(idx + (size_t)lv * MAX_IDX, g_nidx[lv], src, dst);
     EHMM_CK(cudaGetLastError());
     s->launches[KID_MT]++;
     return EHMM_OK;
@@ -234,9 +242,9 @@ bool windows_cover(const ehmm_session *s, int64_t lo, int64_t hi) {
 
 // Prepare the windows of sub-streams 1..P-1 for the stream whose state is in s->mt_raw (device).
 int mt_prepare(ehmm_session *s, cudaStream_t st, int64_t max_draws) {
-    const int64_t P = substreams_for(624, max_draws);
+    const int64_t P = substreams_for(s, 624, max_draws);
     if (P <= 1) { if (s->mtj_valid < 1) s->mtj_valid = 1; return EHMM_OK; }
-    EHMM_REQUIRE(P <= ((int64_t)1 << LEVELS), EHMM_ERR_RNG, "too many uniforms in one call (%lld)", (long long)max_draws);
+    EHMM_REQUIRE(P <= ((int64_t)1 << (LEVELS - s->mt_shift)), EHMM_ERR_RNG, "too many uniforms in one call (%lld)", (long long)max_draws);
     const uint16_t *idx = nullptr;
     EHMM_TRY(device_polys(s->device, &idx));
     EHMM_TRY(reserve_windows(s, P));
@@ -258,7 +266,7 @@ int mt_prepare(ehmm_session *s, cudaStream_t st, int64_t max_draws) {
 int mt_prepare_range(ehmm_session *s, cudaStream_t st, int64_t q_lo, int64_t q_hi) {
     if (q_lo < 0) q_lo = 0;
     if (q_hi < q_lo || windows_cover(s, q_lo, q_hi)) return EHMM_OK;
-    EHMM_REQUIRE(q_hi < ((int64_t)1 << LEVELS), EHMM_ERR_RNG, "draw position beyond 2^%d sub-streams", LEVELS);
+    EHMM_REQUIRE(q_hi < ((int64_t)1 << (LEVELS - s->mt_shift)), EHMM_ERR_RNG, "draw position beyond 2^%d sub-streams", LEVELS - s->mt_shift);
     const uint16_t *idx = nullptr;
     EHMM_TRY(device_polys(s->device, &idx));
     EHMM_TRY(reserve_windows(s, q_hi + 1));
@@ -269,8 +277,8 @@ int mt_prepare_range(ehmm_session *s, cudaStream_t st, int64_t q_lo, int64_t q_h
     if (q_lo > 0) {
         const uint32_t *cur = S;
         int bits = 0, done = 0;
-        for (int k = 0; k < LEVELS; k++) bits += (q_lo >> k) & 1;
-        for (int k = 0; k < LEVELS; k++) {
+        for (int k = 0; k < LEVELS - s->mt_shift; k++) bits += (q_lo >> k) & 1;
+        for (int k = 0; k < LEVELS - s->mt_shift; k++) {
             if (!((q_lo >> k) & 1)) continue;
             uint32_t *dst = (++done == bits) ? S + (size_t)q_lo * MT_N : scratch[done & 1];
             EHMM_TRY(launch_jump(s, st, idx, k, cur, dst, 1));
@@ -292,7 +300,7 @@ int mt_prepare_range(ehmm_session *s, cudaStream_t st, int64_t q_lo, int64_t q_h
     return EHMM_OK;
 }
 
-static int64_t substream_of(int64_t a) { return a <= 0 ? 0 : (a - 1) / JW; }
+static int64_t substream_of(const ehmm_session *s, int64_t a) { return a <= 0 ? 0 : (a - 1) / jw_of(s); }
 
 static int wait_pending(ehmm_session *s) {
     if (s->mtj_pending) {  // windows being prepared on the side stream
@@ -304,7 +312,7 @@ static int wait_pending(ehmm_session *s) {
 
 static int ensure_windows(ehmm_session *s, int64_t P) {
     EHMM_TRY(wait_pending(s));
-    if (P > 1 && s->mtj_valid < P) EHMM_TRY(mt_prepare(s, s->stream, (P - 1) * JW + 2));
+    if (P > 1 && s->mtj_valid < P) EHMM_TRY(mt_prepare(s, s->stream, (P - 1) * jw_of(s) + 2));
     return EHMM_OK;
 }
 
@@ -318,12 +326,12 @@ static int ensure_range(ehmm_session *s, int64_t q_lo, int64_t q_hi) {
 int mt_generate(ehmm_session *s, int64_t n, uint32_t *out) {
     if (n <= 0) return EHMM_OK;
     const int64_t pos = s->rng_state[0];
-    const int64_t P = substream_of(pos + n - 1) + 1;
+    const int64_t P = substream_of(s, pos + n - 1) + 1;
     EHMM_TRY(s->mt_raw2.reserve(sizeof(uint32_t) * 625));
     EHMM_TRY(ensure_windows(s, P));
     {
         PROF(s, KID_MT), mt_generate_kernel<<<(unsigned)P, GEN_NT, 0, s->stream>>>(
-            s->mt_raw.as<uint32_t>(), s->mt_windows.as<uint32_t>(), 0, 0, n, out, n, s->mt_raw2.as<uint32_t>());
+            s->mt_raw.as<uint32_t>(), s->mt_windows.as<uint32_t>(), 0, 0, n, out, n, s->mt_raw2.as<uint32_t>(), jw_of(s));
     }
     EHMM_CK(cudaGetLastError());
     std::swap(s->mt_raw, s->mt_raw2);
@@ -337,10 +345,10 @@ int mt_generate(ehmm_session *s, int64_t n, uint32_t *out) {
 int mt_generate_range(ehmm_session *s, int64_t lo_rel, int64_t n, uint32_t *out) {
     if (n <= 0) return EHMM_OK;
     const int64_t pos = s->rng_state[0];
-    const int64_t s0 = substream_of(pos + lo_rel), s1 = substream_of(pos + lo_rel + n - 1);
+    const int64_t s0 = substream_of(s, pos + lo_rel), s1 = substream_of(s, pos + lo_rel + n - 1);
     EHMM_TRY(ensure_range(s, s0, s1));
     PROF(s, KID_MT), mt_generate_kernel<<<(unsigned)(s1 - s0 + 1), GEN_NT, 0, s->stream>>>(
-        s->mt_raw.as<uint32_t>(), s->mt_windows.as<uint32_t>(), (int)s0, lo_rel, lo_rel + n, out, -1, nullptr);
+        s->mt_raw.as<uint32_t>(), s->mt_windows.as<uint32_t>(), (int)s0, lo_rel, lo_rel + n, out, -1, nullptr, jw_of(s));
     EHMM_CK(cudaGetLastError());
     return EHMM_OK;
 }
@@ -350,11 +358,11 @@ int mt_advance(ehmm_session *s, int64_t n) {
     if (n <= 0) return EHMM_OK;
     const int64_t pos = s->rng_state[0];
     const int64_t E = pos + n, st_lo = ((E - 1) / 624) * 624;
-    const int64_t s0 = substream_of(st_lo), s1 = substream_of(E - 1);
+    const int64_t s0 = substream_of(s, st_lo), s1 = substream_of(s, E - 1);
     EHMM_TRY(s->mt_raw2.reserve(sizeof(uint32_t) * 625));
     EHMM_TRY(ensure_range(s, s0, s1));
     PROF(s, KID_MT), mt_generate_kernel<<<(unsigned)(s1 - s0 + 1), GEN_NT, 0, s->stream>>>(
-        s->mt_raw.as<uint32_t>(), s->mt_windows.as<uint32_t>(), (int)s0, 0, 0, nullptr, n, s->mt_raw2.as<uint32_t>());
+        s->mt_raw.as<uint32_t>(), s->mt_windows.as<uint32_t>(), (int)s0, 0, 0, nullptr, n, s->mt_raw2.as<uint32_t>(), jw_of(s));
     EHMM_CK(cudaGetLastError());
     std::swap(s->mt_raw, s->mt_raw2);
     s->mtj_valid = 0;
@@ -370,14 +378,14 @@ int mt_advance_side(ehmm_session *s, int64_t n, void *h_state) {
     if (n <= 0) return EHMM_OK;
     const int64_t pos = s->rng_state[0];
     const int64_t E = pos + n, st_lo = ((E - 1) / 624) * 624;
-    const int64_t s0 = substream_of(st_lo), s1 = substream_of(E - 1);
+    const int64_t s0 = substream_of(s, st_lo), s1 = substream_of(s, E - 1);
     EHMM_TRY(s->mt_raw2.reserve(sizeof(uint32_t) * 625));
     EHMM_TRY(wait_pending(s));
     EHMM_CK(cudaEventRecord(s->ev2, s->stream));
     EHMM_CK(cudaStreamWaitEvent(s->stream2, s->ev2, 0));
     if (s1 >= 1) EHMM_TRY(mt_prepare_range(s, s->stream2, s0, s1));
     mt_generate_kernel<<<(unsigned)(s1 - s0 + 1), GEN_NT, 0, s->stream2>>>(
-        s->mt_raw.as<uint32_t>(), s->mt_windows.as<uint32_t>(), (int)s0, 0, 0, nullptr, n, s->mt_raw2.as<uint32_t>());
+        s->mt_raw.as<uint32_t>(), s->mt_windows.as<uint32_t>(), (int)s0, 0, 0, nullptr, n, s->mt_raw2.as<uint32_t>(), jw_of(s));
     EHMM_CK(cudaGetLastError());
     s->launches[KID_MT]++;
     std::swap(s->mt_raw, s->mt_raw2);
@@ -388,9 +396,26 @@ int mt_advance_side(ehmm_session *s, int64_t n, void *h_state) {
     return EHMM_OK;
 }
 
+// Choose the sub-stream length for calls that draw about `draws` uniforms: about 150-300 sub-streams (one
+// generating CTA each, all resident at once) when there are that many draws, never shorter than JW.
+// Changing it drops the prepared windows (they are spaced by the old length).
+int mt_choose_stride(ehmm_session *s, int64_t draws) {
+    int shift = 0;
+    while (shift < 5 && (draws >> (LOG2J + shift + 1)) >= 150) shift++;
+    if (shift == s->mt_shift) return EHMM_OK;
+    if (s->mtj_pending) {
+        EHMM_CK(cudaStreamSynchronize(s->stream2));
+        s->mtj_pending = false;
+    }
+    s->mt_shift = shift;
+    s->mtj_valid = 0;
+    s->mtj_niv = 0;
+    return EHMM_OK;
+}
+
 // After a call: start preparing the windows for the next one on the side stream.
 int mt_prefetch(ehmm_session *s, int64_t max_draws) {
-    if (substreams_for(624, max_draws) <= 1) return EHMM_OK;
+    if (substreams_for(s, 624, max_draws) <= 1) return EHMM_OK;
     EHMM_CK(cudaEventRecord(s->ev2, s->stream));
     EHMM_CK(cudaStreamWaitEvent(s->stream2, s->ev2, 0));
     EHMM_TRY(mt_prepare(s, s->stream2, max_draws));
@@ -408,11 +433,11 @@ int mt_prefetch_ranges(ehmm_session *s, int nr, const int64_t *lo, const int64_t
     const int64_t pos = s->rng_state[0];
     for (int i = 0; i < nr; i++) {
         if (n[i] <= 0) continue;
-        EHMM_TRY(mt_prepare_range(s, s->stream2, substream_of(pos + lo[i]) - margin, substream_of(pos + lo[i] + n[i] - 1) + margin));
+        EHMM_TRY(mt_prepare_range(s, s->stream2, substream_of(s, pos + lo[i]) - margin, substream_of(s, pos + lo[i] + n[i] - 1) + margin));
     }
     if (total > 0) {
         const int64_t E = pos + total, st_lo = ((E - 1) / MT_N) * MT_N;
-        EHMM_TRY(mt_prepare_range(s, s->stream2, substream_of(st_lo) - margin, substream_of(E - 1) + margin));
+        EHMM_TRY(mt_prepare_range(s, s->stream2, substream_of(s, st_lo) - margin, substream_of(s, E - 1) + margin));
     }
     EHMM_CK(cudaEventRecord(s->ev, s->stream2));
     s->mtj_pending = true;

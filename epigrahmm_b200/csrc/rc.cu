@@ -215,58 +215,110 @@ __device__ __forceinline__ void limb_add(unsigned long long *lo, int64_t cells, 
 // EXACT: integer limbs (acc = limbs: lo[cells] then hi[cells]); else fp64 atomics (acc = buckets).
 // SKIPST (differential, exact): the weights >= p of columns 0 and B+1 were summed once for this E-step
 // (rc_static_kernel) and are already in the limbs; only the survivors of the thinning are added here.
-template <bool DIFF, typename UT, bool EXACT, bool SKIPST>
+// CMAX > 0: at most CMAX columns, whose next uniform index (warp-uniform) is held in registers and the
+// column loop is unrolled; CMAX = 0: any number of columns, lane (c & 31) holds the state of column c.
+struct RCCut {
+    double p, rp;  // the cut and RN(1 / p)
+};
+
+template <typename UT> __device__ __forceinline__ double rc_thin(double x, const RCCut &cut, const UT *unif, int64_t at) {
+    return rbinom1(rc_div_cut(x, cut.p, cut.rp), get_unif<UT>(unif, at)) * cut.p;
+}
+
+template <bool EXACT>
+__device__ __forceinline__ void rc_scatter(void *acc, int64_t row, int64_t cells, const int32_t *__restrict__ group, int64_t j,
+                                           int64_t M, int nrep, double x) {
+    for (int i = 0; i < nrep; i++) {
+        const int g = __ldg(group + j + (int64_t)i * M);
+        if (EXACT) limb_add(reinterpret_cast<unsigned long long *>(acc) + row + g, cells, x);
+        else atomicAdd(reinterpret_cast<double *>(acc) + row + g, x);
+    }
+}
+
+template <bool DIFF, typename UT, bool EXACT, bool SKIPST, int CMAX>
 __global__ void __launch_bounds__(RC_NT)
-    rc_apply_kernel(RCSrc S, double p, int64_t nwt, const uint32_t *__restrict__ tileoff, const __grid_constant__ RCBase ub,
+    rc_apply_kernel(RCSrc S, RCCut cut, int64_t nwt, const uint32_t *__restrict__ tileoff, const __grid_constant__ RCBase ub,
                     const UT *__restrict__ unif, const int32_t *__restrict__ group, int nrep, int64_t G,
                     void *__restrict__ acc, const int *__restrict__ counts, int *__restrict__ err) {
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
     const int64_t tile = (int64_t)blockIdx.x * RC_NW + (threadIdx.x >> 5);
     if (tile >= nwt) return;
+    const double p = cut.p;
     const bool thin = p > 0.0;
     const int64_t cells = (int64_t)S.columns * (G + 1);
+    const int C = S.columns;
+    if (CMAX > 0) {
+        int64_t next[CMAX > 0 ? CMAX : 1], first[CMAX > 0 ? CMAX : 1];
+#pragma unroll
+        for (int c = 0; c < CMAX; c++) {
+            first[c] = (thin && c < C) ? ub.ubase[c] + tileoff[(int64_t)c * nwt + tile] : 0;
+            next[c] = first[c];
+        }
+#pragma unroll 1
+        for (int r = 0; r < RC_STRIPS; r++) {
+            const int64_t j = tile * RC_WT + r * 32 + lane;
+            const bool valid = j < S.M;
+            double p1[3] = {2.0, 2.0, 2.0};
+            double x[CMAX > 0 ? CMAX : 1];
+            if (valid) rc_posteriors<DIFF>(S, j, p1);
+#pragma unroll
+            for (int c = 0; c < CMAX; c++) x[c] = (valid && c < C) ? rc_weight<DIFF>(S, p1, c, j) : 2.0;  // the loads of all columns in flight
+#pragma unroll
+            for (int c = 0; c < CMAX; c++) {
+                if (c < C) {
+                    const bool flag = rc_flagged(x[c], p);
+                    const unsigned bal = __ballot_sync(0xffffffffu, flag);
+                    if (flag) x[c] = rc_thin<UT>(x[c], cut, unif, next[c] + __popc(bal & lt));
+                    next[c] += __popc(bal);
+                    // x < p without a flag is x == 0: stays 0
+                    const bool cached = SKIPST && !flag && (c == 0 || c == C - 1);
+                    if (valid && x[c] != 0.0 && !cached) rc_scatter<EXACT>(acc, (int64_t)c * (G + 1), cells, group, j, S.M, nrep, x[c]);
+                }
+            }
+        }
+        // the ranks handed out must be the counts the offsets were scanned from
+        if (thin) {
+            bool bad = false;
+#pragma unroll
+            for (int c = 0; c < CMAX; c++)
+                if (c < C) bad = bad || (next[c] - first[c] != counts[(int64_t)c * nwt + tile]);
+            if (bad && lane == 0) atomicOr(err, 1);
+        }
+        return;
+    }
     // lane (c & 31) holds the running rank and the uniform offset of column c (and of column c + 32)
     int cnt0 = 0, cnt1 = 0;
     int64_t off0 = 0, off1 = 0;
     if (thin) {
-        if (lane < S.columns) off0 = ub.ubase[lane] + tileoff[(int64_t)lane * nwt + tile];
-        if (lane + 32 < S.columns) off1 = ub.ubase[lane + 32] + tileoff[(int64_t)(lane + 32) * nwt + tile];
+        if (lane < C) off0 = ub.ubase[lane] + tileoff[(int64_t)lane * nwt + tile];
+        if (lane + 32 < C) off1 = ub.ubase[lane + 32] + tileoff[(int64_t)(lane + 32) * nwt + tile];
     }
-#pragma unroll 2
+#pragma unroll 1
     for (int r = 0; r < RC_STRIPS; r++) {
         const int64_t j = tile * RC_WT + r * 32 + lane;
         const bool valid = j < S.M;
         double p1[3] = {2.0, 2.0, 2.0};
         if (valid) rc_posteriors<DIFF>(S, j, p1);
 #pragma unroll 4
-        for (int c = 0; c < S.columns; c++) {
+        for (int c = 0; c < C; c++) {
             double x = valid ? rc_weight<DIFF>(S, p1, c, j) : 2.0;
             const bool flag = rc_flagged(x, p);
             const unsigned bal = __ballot_sync(0xffffffffu, flag);
             if (bal) {
                 const int run = __shfl_sync(0xffffffffu, c < 32 ? cnt0 : cnt1, c & 31);
                 const int64_t base = __shfl_sync(0xffffffffu, c < 32 ? off0 : off1, c & 31);
-                if (flag) x = rbinom1(x / p, get_unif<UT>(unif, base + run + __popc(bal & lt))) * p;
+                if (flag) x = rc_thin<UT>(x, cut, unif, base + run + __popc(bal & lt));
                 if (lane == (c & 31)) { if (c < 32) cnt0 += __popc(bal); else cnt1 += __popc(bal); }
             }
-            // x < p without a flag is x == 0 (x / p == 0): stays 0
-            const bool cached = SKIPST && !flag && (c == 0 || c == S.columns - 1);
-            if (valid && x != 0.0 && !cached) {
-                const int64_t row = (int64_t)c * (G + 1);
-                for (int i = 0; i < nrep; i++) {
-                    const int g = __ldg(group + j + (int64_t)i * S.M);
-                    if (EXACT) limb_add(reinterpret_cast<unsigned long long *>(acc) + row + g, cells, x);
-                    else atomicAdd(reinterpret_cast<double *>(acc) + row + g, x);
-                }
-            }
+            const bool cached = SKIPST && !flag && (c == 0 || c == C - 1);
+            if (valid && x != 0.0 && !cached) rc_scatter<EXACT>(acc, (int64_t)c * (G + 1), cells, group, j, S.M, nrep, x);
         }
     }
-    // the ranks handed out must be the counts the offsets were scanned from
     if (thin) {
         bool bad = false;
-        if (lane < S.columns) bad = counts[(int64_t)lane * nwt + tile] != cnt0;
-        if (lane + 32 < S.columns) bad = bad || counts[(int64_t)(lane + 32) * nwt + tile] != cnt1;
+        if (lane < C) bad = counts[(int64_t)lane * nwt + tile] != cnt0;
+        if (lane + 32 < C) bad = bad || counts[(int64_t)(lane + 32) * nwt + tile] != cnt1;
         if (bad) atomicOr(err, 1);
     }
 }
@@ -414,9 +466,24 @@ template <bool DIFF> int count_and_scan(ehmm_session *s, const RCSrc &S, double 
 }
 
 // phase 2: thin and sum by group.  ub: where each column's draws start in `unif`.
+template <bool DIFF, typename UT, bool EXACT, bool SKIPST>
+int launch_apply_kernel(ehmm_session *s, const RCSrc &S, double p, int nrep, const RCBase &ub, const UT *unif, void *acc) {
+    const int64_t nwt = num_wtiles(s->M);
+    const RCCut cut = {p, p > 0.0 ? 1.0 / p : 0.0};
+#define EHMM_APPLY(CM)                                                                                             \
+    PROF(s, KID_RC_APPLY), rc_apply_kernel<DIFF, UT, EXACT, SKIPST, CM><<<tile_grid(nwt), RC_NT, 0, s->stream>>>(   \
+        S, cut, nwt, s->rc_scan.as<uint32_t>(), ub, unif, s->group.as<int32_t>(), nrep, s->G, acc, s->rc_flag.as<int>(), err_flag(s))
+    if (!DIFF) EHMM_APPLY(2);
+    else if (S.columns <= 8) EHMM_APPLY(8);     // B = 6: BASELINE configs[2]
+    else if (S.columns <= 16) EHMM_APPLY(16);   // B = 14: configs[4]
+    else EHMM_APPLY(0);
+#undef EHMM_APPLY
+    EHMM_CK(cudaGetLastError());
+    return EHMM_OK;
+}
+
 template <bool DIFF, typename UT>
 int launch_apply(ehmm_session *s, const RCSrc &S, double p, int nrep, const RCBase &ub, const UT *unif) {
-    const int64_t nwt = num_wtiles(s->M);
     const size_t cells = (size_t)S.columns * (s->G + 1);
     const bool exact = p >= RC_EXACT_MIN_P;
     const size_t LW = sizeof(unsigned long long);
@@ -443,21 +510,14 @@ int launch_apply(ehmm_session *s, const RCSrc &S, double p, int nrep, const RCBa
             EHMM_CK(cudaMemcpyAsync(limbs + last, st + G1, LW * G1, cudaMemcpyDeviceToDevice, s->stream));
             EHMM_CK(cudaMemcpyAsync(limbs + cells, st + 2 * G1, LW * G1, cudaMemcpyDeviceToDevice, s->stream));
             EHMM_CK(cudaMemcpyAsync(limbs + cells + last, st + 3 * G1, LW * G1, cudaMemcpyDeviceToDevice, s->stream));
-            PROF(s, KID_RC_APPLY), rc_apply_kernel<DIFF, UT, true, DIFF><<<tile_grid(nwt), RC_NT, 0, s->stream>>>(
-                S, p, nwt, s->rc_scan.as<uint32_t>(), ub, unif, s->group.as<int32_t>(), nrep, s->G, limbs, s->rc_flag.as<int>(),
-                err_flag(s));
+            EHMM_TRY((launch_apply_kernel<DIFF, UT, true, DIFF>(s, S, p, nrep, ub, unif, limbs)));
         } else {
-            PROF(s, KID_RC_APPLY), rc_apply_kernel<DIFF, UT, true, false><<<tile_grid(nwt), RC_NT, 0, s->stream>>>(
-                S, p, nwt, s->rc_scan.as<uint32_t>(), ub, unif, s->group.as<int32_t>(), nrep, s->G, limbs, s->rc_flag.as<int>(),
-                err_flag(s));
+            EHMM_TRY((launch_apply_kernel<DIFF, UT, true, false>(s, S, p, nrep, ub, unif, limbs)));
         }
     } else {
         EHMM_CK(cudaMemsetAsync(s->rc_buckets.p, 0, sizeof(double) * cells, s->stream));
-        PROF(s, KID_RC_APPLY), rc_apply_kernel<DIFF, UT, false, false><<<tile_grid(nwt), RC_NT, 0, s->stream>>>(
-            S, p, nwt, s->rc_scan.as<uint32_t>(), ub, unif, s->group.as<int32_t>(), nrep, s->G, s->rc_buckets.p,
-            s->rc_flag.as<int>(), err_flag(s));
+        EHMM_TRY((launch_apply_kernel<DIFF, UT, false, false>(s, S, p, nrep, ub, unif, s->rc_buckets.p)));
     }
-    EHMM_CK(cudaGetLastError());
     s->rc_exact = exact;
     s->rc_final = !exact;
     s->rc_columns = S.columns;
@@ -500,6 +560,7 @@ int run_rc(ehmm_session *s, const RCSrc &S, double p, int nrep, const double *un
         EHMM_TRY(s->rc_unif.reserve(sizeof(uint32_t) * (size_t)(total > 0 ? total : 1)));
         if (total > 0) {
             EHMM_TRY(upload_state_if_needed(s));
+            EHMM_TRY(mt_choose_stride(s, total));
             EHMM_TRY(mt_generate(s, total, s->rc_unif.as<uint32_t>()));
             EHMM_CK(cudaMemcpyAsync(s->h_pinned + 512, s->mt_raw.p, sizeof(uint32_t) * 625, cudaMemcpyDeviceToHost, s->stream));
             rng_note_advance(s, total);
@@ -548,6 +609,7 @@ int rc_apply_block(ehmm_session *s, const RCSrc &S, double p, int nrep, const in
     for (int c = 0; c < S.columns; c++) { ub.ubase[c] = at; at += s->rc_colcount[c]; }
     if (total > 0) {
         EHMM_TRY(upload_state_if_needed(s));
+        EHMM_TRY(mt_choose_stride(s, total));
         for (int c = 0; c < S.columns; c++) {
             EHMM_REQUIRE(col_offsets[c] >= 0 && col_offsets[c] + s->rc_colcount[c] <= total, EHMM_ERR_ARG,
                          "column %d: draws [%lld, %lld) outside [0, %lld)", c, (long long)col_offsets[c],

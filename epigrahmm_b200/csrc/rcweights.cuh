@@ -12,8 +12,20 @@ constexpr int RC_WT = 32 * RC_STRIPS;  // bins per warp tile: the unit of the fl
 
 inline int64_t rc_num_wtiles(int64_t M) { return (M + RC_WT - 1) / RC_WT; }
 
-// x < p draws rbinom(1, x / p); R's rbinom returns 0 without drawing when the probability is 0
-__device__ __forceinline__ bool rc_flagged(double x, double p) { return x < p && x / p != 0.0; }
+// x < p draws rbinom(1, x / p) (src/reweight.cpp:18-19); R's rbinom returns 0 WITHOUT drawing when the
+// probability x / p is 0.  For a cut 0 < p <= 1 (a probability: the entry points reject anything else) and
+// a weight x >= 0, x / p >= x, so the quotient is 0 exactly when x is: no division needed.
+__device__ __forceinline__ bool rc_flagged(double x, double p) { return x < p && x != 0.0; }
+
+// x / p for the thinning probability, with the cut's reciprocal rp = RN(1 / p) computed once on the host:
+// q = RN(x * rp), r = x - q * p (exact: one FMA), q' = RN(q + r * rp).  Markstein's correction step: q' is the
+// correctly rounded quotient (the significand of a cut 0.9^iter or probCut is never all ones, the one
+// excluded case), i.e. the very double the reference's `x / p` holds, at 3 instructions instead of ~25.
+__device__ __forceinline__ double rc_div_cut(double x, double p, double rp) {
+    const double q = __dmul_rn(x, rp);
+    const double r = __fma_rn(-q, p, x);
+    return __fma_rn(r, rp, q);
+}
 
 // weight of mixture component b in the differential model: P1[j,1] * eta[j,b]
 // (src/differentialRejectionControlled.cpp:38-41)

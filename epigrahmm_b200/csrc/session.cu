@@ -840,6 +840,7 @@ int ehmm_rc_consensus(ehmm_session *s, double p, const double *uniforms, int64_t
     EHMM_TRY(check_session(s));
     EHMM_REQUIRE(has(s, DS_P1), EHMM_ERR_STATE, "consensusRejectionControlled: expStep has not run");
     EHMM_REQUIRE(s->G > 0, EHMM_ERR_STATE, "consensusRejectionControlled: ehmm_set_groups has not been called");
+    EHMM_REQUIRE(p >= 0.0 && p <= 1.0, EHMM_ERR_ARG, "the rejection cut p = %g is not a probability", p);
     return rc_consensus(s, p, uniforms, n_uniforms, consumed);
 }
 
@@ -847,6 +848,7 @@ int ehmm_rc_differential(ehmm_session *s, double p, int N, const double *uniform
     EHMM_TRY(check_session(s));
     EHMM_REQUIRE(has(s, DS_P1 | DS_ETA), EHMM_ERR_STATE, "differentialRejectionControlled: needs logProb1 and mixtureProb");
     EHMM_REQUIRE(s->G > 0, EHMM_ERR_STATE, "differentialRejectionControlled: ehmm_set_groups has not been called");
+    EHMM_REQUIRE(p >= 0.0 && p <= 1.0, EHMM_ERR_ARG, "the rejection cut p = %g is not a probability", p);
     EHMM_REQUIRE(N == s->N, EHMM_ERR_ARG, "N=%d does not match the data (N=%d)", N, s->N);
     return rc_differential(s, p, N, uniforms, n_uniforms, consumed);
 }
@@ -856,6 +858,7 @@ int ehmm_rc_count(ehmm_session *s, int differential, double p, int64_t *counts) 
     EHMM_REQUIRE(counts, EHMM_ERR_ARG, "null pointer");
     EHMM_REQUIRE(has(s, differential ? (DS_P1 | DS_ETA) : DS_P1), EHMM_ERR_STATE, "rc_count: posteriors not available");
     EHMM_REQUIRE(s->G > 0, EHMM_ERR_STATE, "rc_count: ehmm_set_groups has not been called");
+    EHMM_REQUIRE(p >= 0.0 && p <= 1.0, EHMM_ERR_ARG, "the rejection cut p = %g is not a probability", p);
     return rc_count(s, differential, p, counts);
 }
 
