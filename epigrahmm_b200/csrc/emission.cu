@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(EM_NT)
 //    and P1[j,2]; all are in registers here, so the number of weights below the cut `pcut` is counted per
 //    (column, warp tile of 256 bins) on the way -- the bins are walked in warp tiles for that.
 template <int NMAX, int BMAX, bool GROUPED, bool COUNT>
-__global__ void __launch_bounds__(EM_NT)
+__global__ void __launch_bounds__(EM_NT, (GROUPED && BMAX <= 14) ? 3 : 1)
     emis_inner_kernel(int64_t M, int N, const int32_t *__restrict__ y, const double *__restrict__ off,
                       const __grid_constant__ EmisParams P, const __grid_constant__ MixParams X,
                       const double *__restrict__ tab, double *__restrict__ eta, const double *__restrict__ lp1,

@@ -41,6 +41,7 @@ constexpr int RC_NT = 256;                  // threads per CTA
 constexpr int RC_NW = RC_NT / 32;           // warps = warp tiles per CTA
 constexpr int RC_TB = RC_NT * RC_STRIPS;    // bins per block of the exported reweight() helper
 constexpr int RC_MAXCOL = EHMM_MAX_B + 2;   // 64
+constexpr int64_t RC_UNIF_SLACK = 32 * RC_STRIPS;  // the apply kernel stages up to this many words past a column's last draw
 constexpr double RC_EXACT_MIN_P = 0.001953125;  // 2^-9: smallest cut whose survivors are exact 62-bit fixed-point numbers
 
 // ---- R's unif_rand() (Mersenne-Twister) ------------------------------------------------------
@@ -235,8 +236,15 @@ __device__ __forceinline__ void rc_scatter(void *acc, int64_t row, int64_t cells
     }
 }
 
+// strips per staging group: the uniforms a group of strips can consume (at most 32 per strip and column) are
+// copied to shared memory with all loads in flight at once, 4 KB per warp whatever the column count
+template <int CMAX, typename UT> struct RCStage {
+    static constexpr int SG = (CMAX <= 2 ? 8 : CMAX <= 8 ? 4 : 2) / (sizeof(UT) == 8 ? 2 : 1);
+    static constexpr int WORDS = CMAX * 32 * SG;  // per warp
+};
+
 template <bool DIFF, typename UT, bool EXACT, bool SKIPST, int CMAX>
-__global__ void __launch_bounds__(RC_NT)
+__global__ void __launch_bounds__(RC_NT, CMAX > 0 ? 4 : 1)
     rc_apply_kernel(RCSrc S, RCCut cut, int64_t nwt, const uint32_t *__restrict__ tileoff, const __grid_constant__ RCBase ub,
                     const UT *__restrict__ unif, const int32_t *__restrict__ group, int nrep, int64_t G,
                     void *__restrict__ acc, const int *__restrict__ counts, int *__restrict__ err) {
@@ -249,40 +257,78 @@ __global__ void __launch_bounds__(RC_NT)
     const int64_t cells = (int64_t)S.columns * (G + 1);
     const int C = S.columns;
     if (CMAX > 0) {
-        int64_t next[CMAX > 0 ? CMAX : 1], first[CMAX > 0 ? CMAX : 1];
+        constexpr int CM = CMAX > 0 ? CMAX : 1;
+        constexpr int SG = RCStage<CM, UT>::SG;
+        extern __shared__ unsigned char rc_smem[];
+        UT *stage = reinterpret_cast<UT *>(rc_smem) + (size_t)(threadIdx.x >> 5) * RCStage<CM, UT>::WORDS;
+        int64_t next[CM];    // index of the column's next uniform (warp-uniform)
+        int used[CM];        // ... and how many of the staged ones the current group has consumed
 #pragma unroll
-        for (int c = 0; c < CMAX; c++) {
-            first[c] = (thin && c < C) ? ub.ubase[c] + tileoff[(int64_t)c * nwt + tile] : 0;
-            next[c] = first[c];
-        }
+        for (int c = 0; c < CM; c++) next[c] = (thin && c < C) ? ub.ubase[c] + tileoff[(int64_t)c * nwt + tile] : 0;
 #pragma unroll 1
-        for (int r = 0; r < RC_STRIPS; r++) {
-            const int64_t j = tile * RC_WT + r * 32 + lane;
-            const bool valid = j < S.M;
-            double p1[3] = {2.0, 2.0, 2.0};
-            double x[CMAX > 0 ? CMAX : 1];
-            if (valid) rc_posteriors<DIFF>(S, j, p1);
+        for (int r0 = 0; r0 < RC_STRIPS; r0 += SG) {
+            if (thin) {  // the next 32 * SG uniforms of every column (the buffer has that much slack behind its end)
+                __syncwarp();
 #pragma unroll
-            for (int c = 0; c < CMAX; c++) x[c] = (valid && c < C) ? rc_weight<DIFF>(S, p1, c, j) : 2.0;  // the loads of all columns in flight
+                for (int c = 0; c < CM; c++)
+                    if (c < C) {
 #pragma unroll
-            for (int c = 0; c < CMAX; c++) {
-                if (c < C) {
-                    const bool flag = rc_flagged(x[c], p);
-                    const unsigned bal = __ballot_sync(0xffffffffu, flag);
-                    if (flag) x[c] = rc_thin<UT>(x[c], cut, unif, next[c] + __popc(bal & lt));
-                    next[c] += __popc(bal);
-                    // x < p without a flag is x == 0: stays 0
-                    const bool cached = SKIPST && !flag && (c == 0 || c == C - 1);
-                    if (valid && x[c] != 0.0 && !cached) rc_scatter<EXACT>(acc, (int64_t)c * (G + 1), cells, group, j, S.M, nrep, x[c]);
+                        for (int k = 0; k < SG; k++) stage[(c * SG + k) * 32 + lane] = __ldg(unif + next[c] + k * 32 + lane);
+                    }
+                __syncwarp();
+            }
+#pragma unroll
+            for (int c = 0; c < CM; c++) used[c] = 0;
+#pragma unroll 1
+            for (int r = r0; r < r0 + SG; r++) {
+                const int64_t j = tile * RC_WT + r * 32 + lane;
+                const bool valid = j < S.M;
+                double p1[3] = {2.0, 2.0, 2.0};
+                double x[CM];
+                if (valid) rc_posteriors<DIFF>(S, j, p1);
+#pragma unroll
+                for (int c = 0; c < CM; c++) x[c] = (valid && c < C) ? rc_weight<DIFF>(S, p1, c, j) : 2.0;  // all loads in flight
+                unsigned need = 0;
+#pragma unroll
+                for (int c = 0; c < CM; c++) {
+                    if (c < C) {
+                        const bool flag = rc_flagged(x[c], p);
+                        const unsigned bal = __ballot_sync(0xffffffffu, flag);
+                        if (flag) {
+                            const UT uw = stage[c * SG * 32 + used[c] + __popc(bal & lt)];
+                            double u;
+                            if (sizeof(UT) == 8) u = *reinterpret_cast<const double *>(&uw);
+                            else u = mt_to_unif(*reinterpret_cast<const uint32_t *>(&uw));
+                            x[c] = rbinom1(rc_div_cut(x[c], cut.p, cut.rp), u) * cut.p;
+                        }
+                        used[c] += __popc(bal);
+                        // x < p without a flag is x == 0: stays 0
+                        const bool cached = SKIPST && !flag && (c == 0 || c == C - 1);
+                        if (valid && x[c] != 0.0 && !cached) need |= 1u << c;
+                    }
+                }
+                if (need) {  // the bin's group ids once, whatever the number of columns it adds to
+                    for (int i = 0; i < nrep; i++) {
+                        const int g = __ldg(group + j + (int64_t)i * S.M);
+#pragma unroll
+                        for (int c = 0; c < CM; c++)
+                            if ((need >> c) & 1u) {
+                                const int64_t at = (int64_t)c * (G + 1) + g;
+                                if (EXACT) limb_add(reinterpret_cast<unsigned long long *>(acc) + at, cells, x[c]);
+                                else atomicAdd(reinterpret_cast<double *>(acc) + at, x[c]);
+                            }
+                    }
                 }
             }
+#pragma unroll
+            for (int c = 0; c < CM; c++) next[c] += used[c];
         }
         // the ranks handed out must be the counts the offsets were scanned from
         if (thin) {
             bool bad = false;
 #pragma unroll
-            for (int c = 0; c < CMAX; c++)
-                if (c < C) bad = bad || (next[c] - first[c] != counts[(int64_t)c * nwt + tile]);
+            for (int c = 0; c < CM; c++)
+                if (c < C) bad = bad || (next[c] - (ub.ubase[c] + tileoff[(int64_t)c * nwt + tile]) != counts[(int64_t)c * nwt + tile]);
             if (bad && lane == 0) atomicOr(err, 1);
         }
         return;
@@ -466,20 +512,24 @@ template <bool DIFF> int count_and_scan(ehmm_session *s, const RCSrc &S, double 
 }
 
 // phase 2: thin and sum by group.  ub: where each column's draws start in `unif`.
-template <bool DIFF, typename UT, bool EXACT, bool SKIPST>
-int launch_apply_kernel(ehmm_session *s, const RCSrc &S, double p, int nrep, const RCBase &ub, const UT *unif, void *acc) {
+template <bool DIFF, typename UT, bool EXACT, bool SKIPST, int CM>
+int launch_apply_cm(ehmm_session *s, const RCSrc &S, const RCCut &cut, int nrep, const RCBase &ub, const UT *unif, void *acc) {
     const int64_t nwt = num_wtiles(s->M);
-    const RCCut cut = {p, p > 0.0 ? 1.0 / p : 0.0};
-#define EHMM_APPLY(CM)                                                                                             \
-    PROF(s, KID_RC_APPLY), rc_apply_kernel<DIFF, UT, EXACT, SKIPST, CM><<<tile_grid(nwt), RC_NT, 0, s->stream>>>(   \
-        S, cut, nwt, s->rc_scan.as<uint32_t>(), ub, unif, s->group.as<int32_t>(), nrep, s->G, acc, s->rc_flag.as<int>(), err_flag(s))
-    if (!DIFF) EHMM_APPLY(2);
-    else if (S.columns <= 8) EHMM_APPLY(8);     // B = 6: BASELINE configs[2]
-    else if (S.columns <= 16) EHMM_APPLY(16);   // B = 14: configs[4]
-    else EHMM_APPLY(0);
-#undef EHMM_APPLY
+    constexpr int CS = CM > 0 ? CM : 1;
+    const size_t smem = CM > 0 ? sizeof(UT) * RCStage<CS, UT>::WORDS * RC_NW : 0;
+    PROF(s, KID_RC_APPLY), rc_apply_kernel<DIFF, UT, EXACT, SKIPST, CM><<<tile_grid(nwt), RC_NT, smem, s->stream>>>(
+        S, cut, nwt, s->rc_scan.as<uint32_t>(), ub, unif, s->group.as<int32_t>(), nrep, s->G, acc, s->rc_flag.as<int>(), err_flag(s));
     EHMM_CK(cudaGetLastError());
     return EHMM_OK;
+}
+
+template <bool DIFF, typename UT, bool EXACT, bool SKIPST>
+int launch_apply_kernel(ehmm_session *s, const RCSrc &S, double p, int nrep, const RCBase &ub, const UT *unif, void *acc) {
+    const RCCut cut = {p, p > 0.0 ? 1.0 / p : 0.0};
+    if (!DIFF) return launch_apply_cm<DIFF, UT, EXACT, SKIPST, 2>(s, S, cut, nrep, ub, unif, acc);
+    if (S.columns <= 8) return launch_apply_cm<DIFF, UT, EXACT, SKIPST, 8>(s, S, cut, nrep, ub, unif, acc);    // B = 6: BASELINE configs[2]
+    if (S.columns <= 16) return launch_apply_cm<DIFF, UT, EXACT, SKIPST, 16>(s, S, cut, nrep, ub, unif, acc);  // B = 14: configs[4]
+    return launch_apply_cm<DIFF, UT, EXACT, SKIPST, 0>(s, S, cut, nrep, ub, unif, acc);
 }
 
 template <bool DIFF, typename UT>
@@ -550,14 +600,14 @@ int run_rc(ehmm_session *s, const RCSrc &S, double p, int nrep, const double *un
     if (uniforms) {
         EHMM_REQUIRE(total <= n_uniforms, EHMM_ERR_RNG, "rejection control needs %lld uniforms, buffer holds %lld",
                      (long long)total, (long long)n_uniforms);
-        EHMM_TRY(s->rc_unif.reserve(sizeof(double) * (size_t)(total > 0 ? total : 1)));
+        EHMM_TRY(s->rc_unif.reserve(sizeof(double) * (size_t)(total + RC_UNIF_SLACK)));
         if (total > 0)
             EHMM_CK(cudaMemcpyAsync(s->rc_unif.p, uniforms, sizeof(double) * total, cudaMemcpyHostToDevice, s->stream));
         EHMM_TRY((launch_apply<DIFF, double>(s, S, p, nrep, ub, s->rc_unif.as<double>())));
     } else {
         EHMM_REQUIRE(s->rng_set || total == 0, EHMM_ERR_RNG,
                      "rejection control needs %lld uniforms: pass a buffer or call ehmm_rng_set_state", (long long)total);
-        EHMM_TRY(s->rc_unif.reserve(sizeof(uint32_t) * (size_t)(total > 0 ? total : 1)));
+        EHMM_TRY(s->rc_unif.reserve(sizeof(uint32_t) * (size_t)(total + RC_UNIF_SLACK)));
         if (total > 0) {
             EHMM_TRY(upload_state_if_needed(s));
             EHMM_TRY(mt_choose_stride(s, total));
@@ -603,7 +653,7 @@ int rc_apply_block(ehmm_session *s, const RCSrc &S, double p, int nrep, const in
     EHMM_REQUIRE(s->rng_set || total == 0, EHMM_ERR_RNG, "rejection control needs the RNG state (ehmm_rng_set_state)");
     int64_t local = 0;
     for (int c = 0; c < S.columns; c++) local += s->rc_colcount[c];
-    EHMM_TRY(s->rc_unif.reserve(sizeof(uint32_t) * (size_t)(local > 0 ? local : 1)));
+    EHMM_TRY(s->rc_unif.reserve(sizeof(uint32_t) * (size_t)(local + RC_UNIF_SLACK)));
     RCBase ub;
     int64_t at = 0;
     for (int c = 0; c < S.columns; c++) { ub.ubase[c] = at; at += s->rc_colcount[c]; }
