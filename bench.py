@@ -227,6 +227,8 @@ def em_step(be, cfg, theta, control, p=P_CUT):
     with innerEMDifferential :191-225) at theta; returns the updated parameters, BIC and Q"""
     em = host_module("em")
     N = cfg["N"]
+    if hasattr(be, "rc_hint"):   # the iteration's cut is known up front (R/base-EM.R:119-121): em.py announces it likewise
+        be.rc_hint(p)
     if cfg["model"] == "consensus":
         be.loglik_consensus(theta["psi"], control["minZero"])
         be.expstep(theta["pi"], theta["gamma"])

@@ -142,6 +142,8 @@ struct ehmm_session {
     uint32_t rng_state[625] = {624};
     bool rng_set = false;
     ehmm::DevBuf rc_flag, rc_scan, rc_buckets, rc_unif, rc_tmp, mt_raw, mt_raw2, mt_windows;
+    ehmm::DevBuf rc_unif_spec;   // uniforms generated ahead of the next call on the side stream (mt_speculate)
+    int64_t spec_n = 0;          // ... that many words from the current stream position (0: none)
     ehmm::DevBuf rc_limbs, rc_coltot;  // exact accumulators (2 x u64 per table entry); column totals + error flag
     bool rc_exact = false;       // the last rejection tables were accumulated as exact limbs ...
     bool rc_final = false;       // ... and have been rounded into rc_buckets
@@ -172,6 +174,8 @@ struct ehmm_session {
     ehmm::DevBuf rc_static;      // differential model: exact limbs of the weights >= p of columns 0 and B+1, which
     uint64_t rc_static_gen = 0;  // stay the same through the inner iterations of one E-step (generation lp1_gen,
     double rc_static_p = -1.0;   // cut rc_static_p)
+    cudaEvent_t ev_static = nullptr;  // recorded behind a build of rc_static on the side stream
+    bool static_pending = false;
     bool glm_ticket_ready = false;
     bool encoded = false;       // data given as dt$Group + dtUnique only (no count / offset matrices)
     bool encoded_ctrl = false;
@@ -261,6 +265,7 @@ int rc_differential(ehmm_session *s, double p, int N, const double *uniforms, in
 int rc_count(ehmm_session *s, int differential, double p, int64_t *counts);
 int rc_apply_at(ehmm_session *s, int differential, double p, const int64_t *col_offsets, int64_t total);
 int rc_finalize(ehmm_session *s);
+int rc_static_prefetch(ehmm_session *s);
 int rc_table_rows(ehmm_session *s, int column, int64_t *rows);
 int rc_table_fetch(ehmm_session *s, int column, double *sums, double *ids);
 int rc_reweight(int device, double *x, int64_t n, double p, const double *uniforms, int64_t n_uniforms, int64_t *consumed);
@@ -276,6 +281,8 @@ int mt_advance(ehmm_session *s, int64_t n);
 int mt_advance_side(ehmm_session *s, int64_t n, void *h_state);
 int mt_prefetch(ehmm_session *s, int64_t max_draws);
 int mt_choose_stride(ehmm_session *s, int64_t draws);
+int mt_speculate(ehmm_session *s, int64_t est, uint32_t *out);
+int mt_wait_side(ehmm_session *s);
 int mt_prefetch_ranges(ehmm_session *s, int nr, const int64_t *lo, const int64_t *n, int64_t total, int margin);
 // glm.cu
 int glm_nb(ehmm_session *s, int column, const double *par, int P, double *value, double *grad);

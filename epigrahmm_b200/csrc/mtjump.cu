@@ -310,6 +310,8 @@ static int wait_pending(ehmm_session *s) {
     return EHMM_OK;
 }
 
+int mt_wait_side(ehmm_session *s) { return wait_pending(s); }
+
 static int ensure_windows(ehmm_session *s, int64_t P) {
     EHMM_TRY(wait_pending(s));
     if (P > 1 && s->mtj_valid < P) EHMM_TRY(mt_prepare(s, s->stream, (P - 1) * jw_of(s) + 2));
@@ -419,6 +421,25 @@ int mt_prefetch(ehmm_session *s, int64_t max_draws) {
     EHMM_CK(cudaEventRecord(s->ev2, s->stream));
     EHMM_CK(cudaStreamWaitEvent(s->stream2, s->ev2, 0));
     EHMM_TRY(mt_prepare(s, s->stream2, max_draws));
+    EHMM_CK(cudaEventRecord(s->ev, s->stream2));
+    s->mtj_pending = true;
+    return EHMM_OK;
+}
+
+// After a call (and after mt_advance_side has queued the new state on the side stream): generate the next
+// `est` words of the stream into `out` on the side stream, ahead of the call that will consume them -- how many
+// it needs is only known once its posteriors have been counted, but a call draws about as many uniforms
+// as the one before it.  Nothing is advanced; the consumer takes the words it needs (mt_spec_ready orders the
+// main stream behind the generation) and advances the stream itself.
+int mt_speculate(ehmm_session *s, int64_t est, uint32_t *out) {
+    if (est <= 0) return EHMM_OK;
+    const int64_t pos = s->rng_state[0];
+    EHMM_TRY(mt_prepare(s, s->stream2, est + MT_N));
+    const int64_t P = substream_of(s, pos + est - 1) + 1;
+    mt_generate_kernel<<<(unsigned)P, GEN_NT, 0, s->stream2>>>(s->mt_raw.as<uint32_t>(), s->mt_windows.as<uint32_t>(), 0, 0, est, out,
+                                                             -1, nullptr, jw_of(s));
+    EHMM_CK(cudaGetLastError());
+    s->launches[KID_MT]++;
     EHMM_CK(cudaEventRecord(s->ev, s->stream2));
     s->mtj_pending = true;
     return EHMM_OK;

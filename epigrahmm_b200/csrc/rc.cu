@@ -279,12 +279,14 @@ __global__ void __launch_bounds__(RC_NT, CMAX > 0 ? 4 : 1)
             }
 #pragma unroll
             for (int c = 0; c < CM; c++) used[c] = 0;
-#pragma unroll 1
+#pragma unroll(CM <= 2 ? 2 : 1)
             for (int r = r0; r < r0 + SG; r++) {
                 const int64_t j = tile * RC_WT + r * 32 + lane;
                 const bool valid = j < S.M;
                 double p1[3] = {2.0, 2.0, 2.0};
                 double x[CM];
+                // consensus: nearly every bin keeps its background weight, so its one group id is fetched with the weights
+                const int g0 = (!DIFF && valid) ? __ldg(group + j) : 0;
                 if (valid) rc_posteriors<DIFF>(S, j, p1);
 #pragma unroll
                 for (int c = 0; c < CM; c++) x[c] = (valid && c < C) ? rc_weight<DIFF>(S, p1, c, j) : 2.0;  // all loads in flight
@@ -308,8 +310,8 @@ __global__ void __launch_bounds__(RC_NT, CMAX > 0 ? 4 : 1)
                     }
                 }
                 if (need) {  // the bin's group ids once, whatever the number of columns it adds to
-                    for (int i = 0; i < nrep; i++) {
-                        const int g = __ldg(group + j + (int64_t)i * S.M);
+                    for (int i = 0; i < (DIFF ? nrep : 1); i++) {
+                        const int g = DIFF ? __ldg(group + j + (int64_t)i * S.M) : g0;
 #pragma unroll
                         for (int c = 0; c < CM; c++)
                             if ((need >> c) & 1u) {
@@ -511,6 +513,26 @@ template <bool DIFF> int count_and_scan(ehmm_session *s, const RCSrc &S, double 
     return EHMM_OK;
 }
 
+// limbs of the weights >= p of columns 0 and B+1 for the current logProb1 (no-op when they are in place)
+int rc_static_build(ehmm_session *s, const RCSrc &S, double p, int nrep, cudaStream_t st) {
+    if (s->rc_static_gen == s->lp1_gen && s->rc_static_p == p) return EHMM_OK;
+    const size_t G1 = (size_t)s->G + 1, LW = sizeof(unsigned long long);
+    EHMM_TRY(s->rc_static.reserve(4 * LW * G1));
+    EHMM_CK(cudaMemsetAsync(s->rc_static.p, 0, 4 * LW * G1, st));
+    const unsigned grid = (unsigned)std::min<int64_t>((s->M + RC_NT - 1) / RC_NT, 148 * 16);
+    if (st == s->stream) {
+        PROF(s, KID_RC_STATIC), rc_static_kernel<<<grid, RC_NT, 0, st>>>(S, p, s->group.as<int32_t>(), nrep, s->G,
+                                                                      s->rc_static.as<unsigned long long>());
+    } else {
+        rc_static_kernel<<<grid, RC_NT, 0, st>>>(S, p, s->group.as<int32_t>(), nrep, s->G, s->rc_static.as<unsigned long long>());
+        s->launches[KID_RC_STATIC]++;
+    }
+    EHMM_CK(cudaGetLastError());
+    s->rc_static_gen = s->lp1_gen;
+    s->rc_static_p = p;
+    return EHMM_OK;
+}
+
 // phase 2: thin and sum by group.  ub: where each column's draws start in `unif`.
 template <bool DIFF, typename UT, bool EXACT, bool SKIPST, int CM>
 int launch_apply_cm(ehmm_session *s, const RCSrc &S, const RCCut &cut, int nrep, const RCBase &ub, const UT *unif, void *acc) {
@@ -543,15 +565,10 @@ int launch_apply(ehmm_session *s, const RCSrc &S, double p, int nrep, const RCBa
         EHMM_CK(cudaMemsetAsync(limbs, 0, 2 * LW * cells, s->stream));
         if (DIFF) {
             const size_t G1 = (size_t)s->G + 1;
-            if (!(s->rc_static_gen == s->lp1_gen && s->rc_static_p == p)) {
-                EHMM_TRY(s->rc_static.reserve(4 * LW * G1));
-                EHMM_CK(cudaMemsetAsync(s->rc_static.p, 0, 4 * LW * G1, s->stream));
-                const unsigned grid = (unsigned)std::min<int64_t>((s->M + RC_NT - 1) / RC_NT, 148 * 16);
-                PROF(s, KID_RC_STATIC), rc_static_kernel<<<grid, RC_NT, 0, s->stream>>>(S, p, s->group.as<int32_t>(), nrep, s->G,
-                                                                                     s->rc_static.as<unsigned long long>());
-                EHMM_CK(cudaGetLastError());
-                s->rc_static_gen = s->lp1_gen;
-                s->rc_static_p = p;
+            EHMM_TRY(rc_static_build(s, S, p, nrep, s->stream));
+            if (s->static_pending) {  // built on the side stream right after the E-step (rc_static_prefetch)
+                EHMM_CK(cudaStreamWaitEvent(s->stream, s->ev_static, 0));
+                s->static_pending = false;
             }
             // static limbs (lo: column 0, column B+1; hi: the same) under this call's tables
             const unsigned long long *st = s->rc_static.as<unsigned long long>();
@@ -607,25 +624,34 @@ int run_rc(ehmm_session *s, const RCSrc &S, double p, int nrep, const double *un
     } else {
         EHMM_REQUIRE(s->rng_set || total == 0, EHMM_ERR_RNG,
                      "rejection control needs %lld uniforms: pass a buffer or call ehmm_rng_set_state", (long long)total);
-        EHMM_TRY(s->rc_unif.reserve(sizeof(uint32_t) * (size_t)(total + RC_UNIF_SLACK)));
         if (total > 0) {
             EHMM_TRY(upload_state_if_needed(s));
-            EHMM_TRY(mt_choose_stride(s, total));
-            EHMM_TRY(mt_generate(s, total, s->rc_unif.as<uint32_t>()));
-            EHMM_CK(cudaMemcpyAsync(s->h_pinned + 512, s->mt_raw.p, sizeof(uint32_t) * 625, cudaMemcpyDeviceToHost, s->stream));
+            if (s->spec_n >= total) {
+                // generated ahead on the side stream while the posteriors were being computed
+                EHMM_TRY(mt_wait_side(s));
+                std::swap(s->rc_unif, s->rc_unif_spec);
+            } else {
+                EHMM_TRY(mt_choose_stride(s, total));
+                EHMM_TRY(s->rc_unif.reserve(sizeof(uint32_t) * (size_t)(total + RC_UNIF_SLACK)));
+                EHMM_TRY(mt_generate_range(s, 0, total, s->rc_unif.as<uint32_t>()));
+            }
+            s->spec_n = 0;
+            // side stream from here on: the state after this call's draws (R's .Random.seed), the windows of the
+            // new position, and the next call's uniforms -- sized from this call's consumption with 25% headroom
+            EHMM_TRY(mt_advance_side(s, total, s->h_pinned + 512));
             rng_note_advance(s, total);
+            int64_t est = total + total / 4 + 2 * 131072;
+            if (est > (int64_t)S.columns * s->M) est = (int64_t)S.columns * s->M;
+            EHMM_TRY(mt_choose_stride(s, est));
+            EHMM_TRY(s->rc_unif_spec.reserve(sizeof(uint32_t) * (size_t)(est + RC_UNIF_SLACK)));
+            EHMM_TRY(mt_speculate(s, est, s->rc_unif_spec.as<uint32_t>()));
+            s->spec_n = est;
+        } else {
+            EHMM_TRY(s->rc_unif.reserve(sizeof(uint32_t) * (size_t)RC_UNIF_SLACK));
         }
         EHMM_TRY((launch_apply<DIFF, uint32_t>(s, S, p, nrep, ub, s->rc_unif.as<uint32_t>())));
     }
     EHMM_TRY(rc_finalize(s));
-    // the next call's sub-stream windows depend only on the RNG state: prepare them on the side stream
-    // (sized from this call's consumption with 25% headroom; a larger need falls back to preparing
-    // the windows on the main stream)
-    if (!uniforms && total > 0) {
-        int64_t est = total + total / 4 + 2 * 131072;
-        if (est > (int64_t)S.columns * s->M) est = (int64_t)S.columns * s->M;
-        EHMM_TRY(mt_prefetch(s, est));
-    }
     // the host does not wait for the tables: the next reader of the stream does
     if (consumed) *consumed = total;
     return EHMM_OK;
@@ -729,6 +755,23 @@ int rc_finalize(ehmm_session *s) {
 static RCSrc rc_source(ehmm_session *s, int differential) {
     if (differential) return RCSrc{s->logProb1.as<double>(), s->eta.as<double>(), s->M, s->B, s->B + 2};
     return RCSrc{s->logProb1.as<double>(), nullptr, s->M, 0, s->K};
+}
+
+// Differential model, right after an E-step: the part of the rejection tables that the coming inner
+// iterations share (rc_static_kernel) depends only on logProb1 and the cut, so when the cut is known
+// (ehmm_rc_hint, or the previous call's) it is summed on the side stream while the main stream goes on with
+// maxStepProb and the first innerExpStep.
+int rc_static_prefetch(ehmm_session *s) {
+    const double p = s->rc_hint_p;
+    if (!(s->K == 3 && s->B > 0 && s->G > 0 && s->group.p && s->N > 0 && p >= RC_EXACT_MIN_P && p <= 1.0 && has(s, DS_P1)))
+        return EHMM_OK;
+    if (s->rc_static_gen == s->lp1_gen && s->rc_static_p == p) return EHMM_OK;
+    EHMM_CK(cudaEventRecord(s->ev2, s->stream));
+    EHMM_CK(cudaStreamWaitEvent(s->stream2, s->ev2, 0));
+    EHMM_TRY(rc_static_build(s, rc_source(s, 1), p, s->N, s->stream2));
+    EHMM_CK(cudaEventRecord(s->ev_static, s->stream2));
+    s->static_pending = true;
+    return EHMM_OK;
 }
 
 int rc_consensus(ehmm_session *s, double p, const double *uniforms, int64_t n_uniforms, int64_t *consumed) {

@@ -210,6 +210,7 @@ int ehmm_session_open(const char *key, int64_t M, int K, int device, ehmm_sessio
     }
     EHMM_CK(cudaEventCreateWithFlags(&s->ev, cudaEventDisableTiming));
     EHMM_CK(cudaEventCreateWithFlags(&s->ev2, cudaEventDisableTiming));
+    EHMM_CK(cudaEventCreateWithFlags(&s->ev_static, cudaEventDisableTiming));
     EHMM_CK(cudaMallocHost(&s->h_pinned, sizeof(double) * 1024));
     EHMM_CK(cudaHostAlloc(&s->h_glm, sizeof(double) * 64, cudaHostAllocMapped));
     memset(s->h_glm, 0, sizeof(double) * 64);
@@ -252,7 +253,7 @@ int ehmm_session_close(ehmm_session *s) {
     DevBuf *bufs[] = {&s->counts_own, &s->offsets_own, &s->controls_own, &s->group, &s->u_chip, &s->u_off, &s->u_ctrl,
                       &s->u_dsg, &s->logf, &s->logFP, &s->logBP, &s->logProb1, &s->logProb2, &s->eta, &s->viterbi, &s->vit_bp,
                       &s->tileops, &s->carries, &s->tilestats, &s->fbscal, &s->rangeops, &s->rangecarry, &s->rc_flag, &s->rc_scan,
-                      &s->rc_buckets, &s->rc_limbs, &s->rc_coltot, &s->rc_static, &s->rc_unif, &s->rc_tmp, &s->mt_raw, &s->mt_raw2, &s->mt_windows, &s->gtab, &s->glm_ticket, &s->inner_part, &s->lgtab, &s->glm_part, &s->misc};
+                      &s->rc_buckets, &s->rc_limbs, &s->rc_coltot, &s->rc_static, &s->rc_unif, &s->rc_unif_spec, &s->rc_tmp, &s->mt_raw, &s->mt_raw2, &s->mt_windows, &s->gtab, &s->glm_ticket, &s->inner_part, &s->lgtab, &s->glm_part, &s->misc};
     for (DevBuf *b : bufs) b->release();
     for (int i = 0; i < 2; i++) {
         s->stage[i].release();
@@ -265,6 +266,7 @@ int ehmm_session_close(ehmm_session *s) {
     if (s->h_glm) cudaFreeHost(s->h_glm);
     if (s->ev) cudaEventDestroy(s->ev);
     if (s->ev2) cudaEventDestroy(s->ev2);
+    if (s->ev_static) cudaEventDestroy(s->ev_static);
     if (s->stream) cudaStreamDestroy(s->stream);
     if (s->stream2) cudaStreamDestroy(s->stream2);
     delete s;
@@ -594,7 +596,7 @@ int ehmm_expstep(ehmm_session *s, const double *pi, const double *gamma, const d
     s->valid |= DS_ESTEP;
     s->stats_stale = false;
     posteriors_changed(s);
-    return EHMM_OK;
+    return rc_static_prefetch(s);
 }
 
 int ehmm_expstep_device(ehmm_session *s, const double *pi, const double *gamma, const double *logf_device) {
@@ -605,7 +607,7 @@ int ehmm_expstep_device(ehmm_session *s, const double *pi, const double *gamma, 
     s->valid |= DS_ESTEP;
     s->stats_stale = false;
     posteriors_changed(s);
-    return EHMM_OK;
+    return rc_static_prefetch(s);
 }
 
 int ehmm_expstep_reduce(ehmm_session *s, const double *pi, const double *gamma, const double *logf, double *op) {
@@ -628,7 +630,7 @@ int ehmm_expstep_apply(ehmm_session *s, const double *fwd_carry, const double *b
     s->valid |= DS_ESTEP;
     s->stats_stale = false;
     posteriors_changed(s);
-    return EHMM_OK;
+    return rc_static_prefetch(s);
 }
 
 namespace {
@@ -685,7 +687,7 @@ int ehmm_expstep_apply_ops(ehmm_session *s, const double *ops_all, int P, int ra
     s->valid |= DS_ESTEP;
     s->stats_stale = false;
     posteriors_changed(s);
-    return EHMM_OK;
+    return rc_static_prefetch(s);
 }
 
 int ehmm_estep_stats(ehmm_session *s, double *stats) {
@@ -826,6 +828,7 @@ int ehmm_rng_set_state(ehmm_session *s, const uint32_t *state625) {
     s->rng_set = true;
     s->rng_dev_valid = false;
     s->rng_pending = false;
+    s->spec_n = 0;
     return EHMM_OK;
 }
 

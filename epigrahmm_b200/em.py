@@ -349,6 +349,13 @@ def _rejection_cut(iteration, control):
     return (control["probCut"] > 0) * rejectionCut
 
 
+def _hint(backend, p):
+    """the iteration's rejection cut is known before its posteriors are computed (it depends on the iteration number
+    only, R/base-EM.R:119-121): announce it, so that the kernels producing the posteriors count for it on the way"""
+    if hasattr(backend, "rc_hint"):
+        backend.rc_hint(p)
+
+
 def _update_hist(controlHist, parHist, theta_new, control, init_time, bic, q, conv):
     cur = controlHist[-1]
     parHist.append(copy.deepcopy(theta_new))
@@ -381,6 +388,7 @@ def emConsensus(theta_old, backend, N, control, dist="nb", callback=None):
     while _continue(controlHist, control):
         cur = controlHist[-1]
         cur["iteration"] += 1
+        _hint(backend, _rejection_cut(cur["iteration"], control))
         loglik(theta_old["psi"], control["minZero"])
         backend.expstep(theta_old["pi"], theta_old["gamma"])
         theta_new.update(backend.maxstepprob())
@@ -407,6 +415,7 @@ def emInitialization(theta_old, backend, control, callback=None):
     while _continue(controlHist, control):
         cur = controlHist[-1]
         cur["iteration"] += 1
+        _hint(backend, _rejection_cut(cur["iteration"], control))
         backend.loglik_init(theta_old["psi"])
         backend.expstep(theta_old["pi"], theta_old["gamma"])
         theta_new.update(backend.maxstepprob())
@@ -432,8 +441,7 @@ def innerEMDifferential(theta_old, backend, probCut, control, dist="nb"):
     tmp_old = copy.deepcopy(theta_old)
     tmp_new = copy.deepcopy(theta_old)
     optimMLE = None
-    if hasattr(backend, "rc_hint"):   # the cut is known before the posteriors are computed: let their kernel count for it
-        backend.rc_hint(probCut)
+    _hint(backend, probCut)
     while count < control["maxIterInnerEM"] and error > control["epsilonInnerEM"]:
         psi_flat = np.concatenate([np.ravel(p) for p in tmp_old["psi"]])
         inner_expstep(tmp_old["delta"], psi_flat, control["minZero"])
@@ -465,6 +473,7 @@ def outerEMDifferential(theta_old, backend, N, control, dist="nb", callback=None
         cur = controlHist[-1]
         cur["iteration"] += 1
         psi_flat = np.concatenate([np.ravel(p) for p in theta_old["psi"]])
+        _hint(backend, _rejection_cut(cur["iteration"], control))
         loglik(theta_old["delta"], psi_flat, control["minZero"])
         backend.expstep(theta_old["pi"], theta_old["gamma"])
         theta_new.update(backend.maxstepprob())
