@@ -243,8 +243,28 @@ template <int CMAX, typename UT> struct RCStage {
     static constexpr int WORDS = CMAX * 32 * SG;  // per warp
 };
 
+// what a bin's weights are made of, as loaded (the next strip's are fetched while the current one is worked on)
+template <int CM> struct RCRaw {
+    double lp[3];                  // logProb1[j, 0..2]
+    double et[CM > 2 ? CM - 2 : 1];  // mixtureProb[j, b]
+    int g0;                        // consensus: the bin's one group id
+};
+
+template <bool DIFF, int CM>
+__device__ __forceinline__ void rc_load_raw(const RCSrc &S, const int32_t *__restrict__ group, int64_t j, int C, RCRaw<CM> &w) {
+    const bool valid = j < S.M;
+    w.lp[0] = valid ? __ldg(S.lp1 + j) : 1.0;  // exp(1) > 1 >= p: never flagged, never added (valid is re-checked)
+    w.lp[1] = valid ? __ldg(S.lp1 + S.M + j) : 1.0;
+    w.lp[2] = (DIFF && valid) ? __ldg(S.lp1 + 2 * S.M + j) : 1.0;
+    w.g0 = (!DIFF && valid) ? __ldg(group + j) : 0;
+    if (DIFF) {
+#pragma unroll
+        for (int b = 0; b < CM - 2; b++) w.et[b] = (valid && b < C - 2) ? __ldg(S.eta + (int64_t)b * S.M + j) : 0.0;
+    }
+}
+
 template <bool DIFF, typename UT, bool EXACT, bool SKIPST, int CMAX>
-__global__ void __launch_bounds__(RC_NT, CMAX > 0 ? 4 : 1)
+__global__ void __launch_bounds__(RC_NT, CMAX == 0 ? 1 : (CMAX <= 2 ? 4 : 3))
     rc_apply_kernel(RCSrc S, RCCut cut, int64_t nwt, const uint32_t *__restrict__ tileoff, const __grid_constant__ RCBase ub,
                     const UT *__restrict__ unif, const int32_t *__restrict__ group, int nrep, int64_t G,
                     void *__restrict__ acc, const int *__restrict__ counts, int *__restrict__ err) {
@@ -265,6 +285,8 @@ __global__ void __launch_bounds__(RC_NT, CMAX > 0 ? 4 : 1)
         int used[CM];        // ... and how many of the staged ones the current group has consumed
 #pragma unroll
         for (int c = 0; c < CM; c++) next[c] = (thin && c < C) ? ub.ubase[c] + tileoff[(int64_t)c * nwt + tile] : 0;
+        RCRaw<CM> cur, nxt;
+        rc_load_raw<DIFF, CM>(S, group, tile * RC_WT + lane, C, cur);
 #pragma unroll 1
         for (int r0 = 0; r0 < RC_STRIPS; r0 += SG) {
             if (thin) {  // the next 32 * SG uniforms of every column (the buffer has that much slack behind its end)
@@ -279,17 +301,22 @@ __global__ void __launch_bounds__(RC_NT, CMAX > 0 ? 4 : 1)
             }
 #pragma unroll
             for (int c = 0; c < CM; c++) used[c] = 0;
-#pragma unroll(CM <= 2 ? 2 : 1)
+#pragma unroll 1
             for (int r = r0; r < r0 + SG; r++) {
                 const int64_t j = tile * RC_WT + r * 32 + lane;
                 const bool valid = j < S.M;
-                double p1[3] = {2.0, 2.0, 2.0};
-                double x[CM];
-                // consensus: nearly every bin keeps its background weight, so its one group id is fetched with the weights
-                const int g0 = (!DIFF && valid) ? __ldg(group + j) : 0;
-                if (valid) rc_posteriors<DIFF>(S, j, p1);
+                // the next strip's loads go out before this strip's arithmetic
+                rc_load_raw<DIFF, CM>(S, group, (r + 1 < RC_STRIPS) ? j + 32 : S.M, C, nxt);
+                double p1[3], x[CM];
+                p1[0] = exp(cur.lp[0]);
+                p1[1] = exp(cur.lp[1]);
+                p1[2] = DIFF ? exp(cur.lp[2]) : 0.0;
 #pragma unroll
-                for (int c = 0; c < CM; c++) x[c] = (valid && c < C) ? rc_weight<DIFF>(S, p1, c, j) : 2.0;  // all loads in flight
+                for (int c = 0; c < CM; c++) {
+                    if (!DIFF) x[c] = c == 0 ? p1[0] : p1[1];
+                    else x[c] = c == 0 ? p1[0] : (c == C - 1 ? p1[2] : rc_mix_weight(p1[1], cur.et[c > 0 ? c - 1 : 0]));
+                    if (!(valid && c < C)) x[c] = 2.0;
+                }
                 unsigned need = 0;
 #pragma unroll
                 for (int c = 0; c < CM; c++) {
@@ -311,7 +338,7 @@ __global__ void __launch_bounds__(RC_NT, CMAX > 0 ? 4 : 1)
                 }
                 if (need) {  // the bin's group ids once, whatever the number of columns it adds to
                     for (int i = 0; i < (DIFF ? nrep : 1); i++) {
-                        const int g = DIFF ? __ldg(group + j + (int64_t)i * S.M) : g0;
+                        const int g = DIFF ? __ldg(group + j + (int64_t)i * S.M) : cur.g0;
 #pragma unroll
                         for (int c = 0; c < CM; c++)
                             if ((need >> c) & 1u) {
@@ -321,6 +348,7 @@ __global__ void __launch_bounds__(RC_NT, CMAX > 0 ? 4 : 1)
                             }
                     }
                 }
+                cur = nxt;
             }
 #pragma unroll
             for (int c = 0; c < CM; c++) next[c] += used[c];
