@@ -201,14 +201,48 @@ template <> __device__ __forceinline__ double get_unif<uint32_t>(const uint32_t 
     return mt_to_unif(__ldg(u + i));
 }
 
-// exact accumulation: w * 2^62 (an integer for w in [2^-9, 2)) as two 31-bit limbs in 64-bit words.  The
-// two limbs of an entry live in separate arrays (lo[i], hi[i] = lo[i + cells]): atomics on one 32-byte sector
-// serialise in L2, so adjacent limbs would double the cost of a frequent group
-// (tools/probes/red_probe.cu: 11.0 ms against 4.8 ms for 15 M adds over 200 zipf-distributed groups).
-__device__ __forceinline__ void limb_add(unsigned long long *lo, int64_t cells, double w) {
+// exact accumulation: w * 2^62 (an integer for w in [2^-9, 2)) as two 31-bit limbs in 64-bit words.
+// Layout of an accumulator set for C columns and G groups (cells = C * (G + 1) entries, 64-bit words):
+//   [0, cells) low limbs | [cells, 2 cells) high limbs | RC_REP replicas of the low limbs of groups < H of
+//   every column | the same for the high limbs        (H = min(RC_HOT, G + 1))
+// * the two limbs of an entry live in separate arrays: atomics on one 32-byte sector serialise in L2
+//   (3.4 clocks each), so adjacent limbs would double the cost of a frequent group
+//   (tools/probes/red_probe.cu: 11.0 ms against 4.8 ms for 15 M adds over 200 zipf-distributed groups);
+// * data.table numbers groups by first appearance, so the frequent ones have the small ids (ids <= 4096 take
+//   82 % of the adds of BASELINE configs[1]; real tracks with all-zero offsets have a few hundred groups in
+//   all): their adds are spread over RC_REP replicas chosen by the warp tile, and the finalisation adds
+//   the replicas up -- integer additions, so the split changes nothing in the result.
+constexpr int RC_HOT = 4096;
+constexpr int RC_REP = 8;
+
+struct RCAcc {
+    unsigned long long *w;  // the accumulator set
+    int64_t cells;          // C * (G + 1)
+    int64_t hot;            // H
+    int64_t hotcells;       // RC_REP * C * H
+};
+inline int64_t rc_hot_groups(int64_t G) { return std::min<int64_t>(RC_HOT, G + 1); }
+inline size_t rc_acc_words(int columns, int64_t G) {
+    return 2 * ((size_t)columns * (G + 1) + (size_t)RC_REP * columns * rc_hot_groups(G));
+}
+inline RCAcc rc_acc(unsigned long long *w, int columns, int64_t G) {
+    return RCAcc{w, (int64_t)columns * (G + 1), rc_hot_groups(G), (int64_t)RC_REP * columns * rc_hot_groups(G)};
+}
+
+// entry (column c, group g), replica rep in [0, RC_REP)
+__device__ __forceinline__ void limb_add(const RCAcc &A, int c, int64_t G, int g, int rep, int C, double w) {
     const unsigned long long v = __double2ull_rz(w * 4611686018427387904.0);
+    unsigned long long *lo;
+    int64_t hi_off;
+    if (g < A.hot) {
+        lo = A.w + 2 * A.cells + ((int64_t)rep * C + c) * A.hot + g;
+        hi_off = A.hotcells;
+    } else {
+        lo = A.w + (int64_t)c * (G + 1) + g;
+        hi_off = A.cells;
+    }
     atomicAdd(lo, v & 0x7fffffffull);
-    atomicAdd(lo + cells, v >> 31);
+    atomicAdd(lo + hi_off, v >> 31);
 }
 
 // nrep = 1 for the consensus model (only f[0..M-1] is read, Q6 in SURVEY.md); nrep = N for the
@@ -227,12 +261,12 @@ template <typename UT> __device__ __forceinline__ double rc_thin(double x, const
 }
 
 template <bool EXACT>
-__device__ __forceinline__ void rc_scatter(void *acc, int64_t row, int64_t cells, const int32_t *__restrict__ group, int64_t j,
-                                           int64_t M, int nrep, double x) {
+__device__ __forceinline__ void rc_scatter(const RCAcc &A, int c, int C, int64_t G, int rep, const int32_t *__restrict__ group,
+                                           int64_t j, int64_t M, int nrep, double x) {
     for (int i = 0; i < nrep; i++) {
         const int g = __ldg(group + j + (int64_t)i * M);
-        if (EXACT) limb_add(reinterpret_cast<unsigned long long *>(acc) + row + g, cells, x);
-        else atomicAdd(reinterpret_cast<double *>(acc) + row + g, x);
+        if (EXACT) limb_add(A, c, G, g, rep, C, x);
+        else atomicAdd(reinterpret_cast<double *>(A.w) + (int64_t)c * (G + 1) + g, x);
     }
 }
 
@@ -267,15 +301,15 @@ template <bool DIFF, typename UT, bool EXACT, bool SKIPST, int CMAX>
 __global__ void __launch_bounds__(RC_NT, CMAX == 0 ? 1 : (CMAX <= 2 ? 4 : 3))
     rc_apply_kernel(RCSrc S, RCCut cut, int64_t nwt, const uint32_t *__restrict__ tileoff, const __grid_constant__ RCBase ub,
                     const UT *__restrict__ unif, const int32_t *__restrict__ group, int nrep, int64_t G,
-                    void *__restrict__ acc, const int *__restrict__ counts, int *__restrict__ err) {
+                    const RCAcc A, const int *__restrict__ counts, int *__restrict__ err) {
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
     const int64_t tile = (int64_t)blockIdx.x * RC_NW + (threadIdx.x >> 5);
     if (tile >= nwt) return;
     const double p = cut.p;
     const bool thin = p > 0.0;
-    const int64_t cells = (int64_t)S.columns * (G + 1);
     const int C = S.columns;
+    const int rep = (int)(tile & (RC_REP - 1));
     if (CMAX > 0) {
         constexpr int CM = CMAX > 0 ? CMAX : 1;
         constexpr int SG = RCStage<CM, UT>::SG;
@@ -342,9 +376,8 @@ __global__ void __launch_bounds__(RC_NT, CMAX == 0 ? 1 : (CMAX <= 2 ? 4 : 3))
 #pragma unroll
                         for (int c = 0; c < CM; c++)
                             if ((need >> c) & 1u) {
-                                const int64_t at = (int64_t)c * (G + 1) + g;
-                                if (EXACT) limb_add(reinterpret_cast<unsigned long long *>(acc) + at, cells, x[c]);
-                                else atomicAdd(reinterpret_cast<double *>(acc) + at, x[c]);
+                                if (EXACT) limb_add(A, c, G, g, rep, C, x[c]);
+                                else atomicAdd(reinterpret_cast<double *>(A.w) + (int64_t)c * (G + 1) + g, x[c]);
                             }
                     }
                 }
@@ -388,7 +421,7 @@ __global__ void __launch_bounds__(RC_NT, CMAX == 0 ? 1 : (CMAX <= 2 ? 4 : 3))
                 if (lane == (c & 31)) { if (c < 32) cnt0 += __popc(bal); else cnt1 += __popc(bal); }
             }
             const bool cached = SKIPST && !flag && (c == 0 || c == C - 1);
-            if (valid && x != 0.0 && !cached) rc_scatter<EXACT>(acc, (int64_t)c * (G + 1), cells, group, j, S.M, nrep, x);
+            if (valid && x != 0.0 && !cached) rc_scatter<EXACT>(A, c, C, G, rep, group, j, S.M, nrep, x);
         }
     }
     if (thin) {
@@ -404,9 +437,8 @@ __global__ void __launch_bounds__(RC_NT, CMAX == 0 ? 1 : (CMAX <= 2 ? 4 : 3))
 // exact sums can be split any way: their limbs are accumulated once (st: lo[2*(G+1)] then hi[2*(G+1)],
 // column 0 first) and copied under every inner iteration's tables.
 __global__ void __launch_bounds__(RC_NT)
-    rc_static_kernel(RCSrc S, double p, const int32_t *__restrict__ group, int nrep, int64_t G,
-                     unsigned long long *__restrict__ st) {
-    const int64_t cells = 2 * (G + 1);
+    rc_static_kernel(RCSrc S, double p, const int32_t *__restrict__ group, int nrep, int64_t G, const RCAcc A) {
+    const int rep = (int)((((int64_t)blockIdx.x * RC_NT + threadIdx.x) >> 5) & (RC_REP - 1));
     for (int64_t j = (int64_t)blockIdx.x * RC_NT + threadIdx.x; j < S.M; j += (int64_t)gridDim.x * RC_NT) {
         double p1[3];
         rc_posteriors<true>(S, j, p1);
@@ -414,26 +446,58 @@ __global__ void __launch_bounds__(RC_NT)
         if (k0 || k2) {
             for (int i = 0; i < nrep; i++) {
                 const int g = __ldg(group + j + (int64_t)i * S.M);
-                if (k0) limb_add(st + g, cells, p1[0]);
-                if (k2) limb_add(st + (G + 1) + g, cells, p1[2]);
+                if (k0) limb_add(A, 0, G, g, rep, 2, p1[0]);
+                if (k2) limb_add(A, 1, G, g, rep, 2, p1[2]);
             }
         }
     }
 }
 
+// fold the replicas of the frequent groups into the main limb arrays (and clear them): the folded set can then be
+// copied under other accumulator sets as two plain arrays
+__global__ void rc_fold_kernel(const RCAcc A, int C, int64_t G) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)C * A.hot) return;
+    const int c = (int)(i / A.hot);
+    const int64_t g = i - (int64_t)c * A.hot;
+    unsigned long long lo = 0, hi = 0;
+    for (int r = 0; r < RC_REP; r++) {
+        unsigned long long *q = A.w + 2 * A.cells + ((int64_t)r * C + c) * A.hot + g;
+        lo += q[0];
+        hi += q[A.hotcells];
+        q[0] = 0;
+        q[A.hotcells] = 0;
+    }
+    A.w[(int64_t)c * (G + 1) + g] += lo;
+    A.w[A.cells + (int64_t)c * (G + 1) + g] += hi;
+}
+
 // limbs -> fp64 table entries: ((hi + carry) * 2^31 + lo) * 2^-62, rounded once (the integer is exact);
 // a rank/count mismatch in the apply kernel poisons the tables instead of leaving them plausible
-__global__ void __launch_bounds__(256) rc_finalize_kernel(const unsigned long long *__restrict__ limbs, int64_t n,
-                                                          double *__restrict__ buckets, const int *__restrict__ err) {
+__global__ void __launch_bounds__(256) rc_finalize_kernel(const RCAcc A, int C, int64_t G, double *__restrict__ buckets,
+                                                          const int *__restrict__ err) {
     const bool bad = err && *err != 0;
-    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
-        const unsigned long long lo = limbs[i], hi = limbs[i + n];
-        const unsigned long long A = hi + (lo >> 31), l = lo & 0x7fffffffull;
-        const double v = __dadd_rn((double)A * 4.656612873077392578125e-10, (double)l * 2.16840434497100886801e-19);
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < A.cells; i += (int64_t)gridDim.x * 256) {
+        unsigned long long lo = A.w[i], hi = A.w[i + A.cells];
+        const int c = (int)(i / (G + 1));
+        const int64_t g = i - (int64_t)c * (G + 1);
+        if (g < A.hot) {
+            for (int r = 0; r < RC_REP; r++) {
+                const unsigned long long *q = A.w + 2 * A.cells + ((int64_t)r * C + c) * A.hot + g;
+                lo += q[0];
+                hi += q[A.hotcells];
+            }
+        }
+        const unsigned long long a = hi + (lo >> 31), l = lo & 0x7fffffffull;
+        const double v = __dadd_rn((double)a * 4.656612873077392578125e-10, (double)l * 2.16840434497100886801e-19);
         buckets[i] = bad ? __longlong_as_double(0x7ff8000000000000ll) : v;
     }
 }
 
+// exported aggregate(): the elements of every group are listed in ascending index order (a stable
+// counting sort done on the host, which has to walk f anyway to validate it) and one thread adds a
+// group's elements in that order -- the order of the reference's loop (src/aggregate.cpp:23-30), so
+// the sums carry the reference's own roundings bit for bit.
 __global__ void aggregate_kernel(const double *__restrict__ x, const int64_t *__restrict__ start,
                                  const int64_t *__restrict__ perm, int64_t G, double *__restrict__ buckets) {
     const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -509,7 +573,7 @@ int reserve_rc(ehmm_session *s, const RCSrc &S) {
     EHMM_TRY(s->rc_scan.reserve(sizeof(uint32_t) * nwt * S.columns));
     EHMM_TRY(s->rc_coltot.reserve(sizeof(int64_t) * RC_MAXCOL + 64));
     EHMM_TRY(s->rc_buckets.reserve(sizeof(double) * (size_t)S.columns * (s->G + 1)));
-    EHMM_TRY(s->rc_limbs.reserve(2 * sizeof(unsigned long long) * (size_t)S.columns * (s->G + 1)));
+    EHMM_TRY(s->rc_limbs.reserve(sizeof(unsigned long long) * rc_acc_words(S.columns, s->G)));
     return EHMM_OK;
 }
 
@@ -544,17 +608,19 @@ template <bool DIFF> int count_and_scan(ehmm_session *s, const RCSrc &S, double 
 // limbs of the weights >= p of columns 0 and B+1 for the current logProb1 (no-op when they are in place)
 int rc_static_build(ehmm_session *s, const RCSrc &S, double p, int nrep, cudaStream_t st) {
     if (s->rc_static_gen == s->lp1_gen && s->rc_static_p == p) return EHMM_OK;
-    const size_t G1 = (size_t)s->G + 1, LW = sizeof(unsigned long long);
-    EHMM_TRY(s->rc_static.reserve(4 * LW * G1));
-    EHMM_CK(cudaMemsetAsync(s->rc_static.p, 0, 4 * LW * G1, st));
+    const size_t LW = sizeof(unsigned long long);
+    EHMM_TRY(s->rc_static.reserve(LW * rc_acc_words(2, s->G)));
+    EHMM_CK(cudaMemsetAsync(s->rc_static.p, 0, LW * rc_acc_words(2, s->G), st));
+    const RCAcc A = rc_acc(s->rc_static.as<unsigned long long>(), 2, s->G);
     const unsigned grid = (unsigned)std::min<int64_t>((s->M + RC_NT - 1) / RC_NT, 148 * 16);
     if (st == s->stream) {
-        PROF(s, KID_RC_STATIC), rc_static_kernel<<<grid, RC_NT, 0, st>>>(S, p, s->group.as<int32_t>(), nrep, s->G,
-                                                                      s->rc_static.as<unsigned long long>());
+        PROF(s, KID_RC_STATIC), rc_static_kernel<<<grid, RC_NT, 0, st>>>(S, p, s->group.as<int32_t>(), nrep, s->G, A);
     } else {
-        rc_static_kernel<<<grid, RC_NT, 0, st>>>(S, p, s->group.as<int32_t>(), nrep, s->G, s->rc_static.as<unsigned long long>());
+        rc_static_kernel<<<grid, RC_NT, 0, st>>>(S, p, s->group.as<int32_t>(), nrep, s->G, A);
         s->launches[KID_RC_STATIC]++;
     }
+    EHMM_CK(cudaGetLastError());
+    rc_fold_kernel<<<(unsigned)((2 * A.hot + 255) / 256), 256, 0, st>>>(A, 2, s->G);
     EHMM_CK(cudaGetLastError());
     s->rc_static_gen = s->lp1_gen;
     s->rc_static_p = p;
@@ -563,7 +629,8 @@ int rc_static_build(ehmm_session *s, const RCSrc &S, double p, int nrep, cudaStr
 
 // phase 2: thin and sum by group.  ub: where each column's draws start in `unif`.
 template <bool DIFF, typename UT, bool EXACT, bool SKIPST, int CM>
-int launch_apply_cm(ehmm_session *s, const RCSrc &S, const RCCut &cut, int nrep, const RCBase &ub, const UT *unif, void *acc) {
+int launch_apply_cm(ehmm_session *s, const RCSrc &S, const RCCut &cut, int nrep, const RCBase &ub, const UT *unif, void *accp) {
+    const RCAcc acc = rc_acc(reinterpret_cast<unsigned long long *>(accp), S.columns, s->G);  // fp64 mode: only .w is used
     const int64_t nwt = num_wtiles(s->M);
     constexpr int CS = CM > 0 ? CM : 1;
     const size_t smem = CM > 0 ? sizeof(UT) * RCStage<CS, UT>::WORDS * RC_NW : 0;
@@ -590,7 +657,7 @@ int launch_apply(ehmm_session *s, const RCSrc &S, double p, int nrep, const RCBa
     EHMM_CK(cudaMemsetAsync(err_flag(s), 0, sizeof(int), s->stream));
     if (exact) {
         unsigned long long *limbs = s->rc_limbs.as<unsigned long long>();
-        EHMM_CK(cudaMemsetAsync(limbs, 0, 2 * LW * cells, s->stream));
+        EHMM_CK(cudaMemsetAsync(limbs, 0, LW * rc_acc_words(S.columns, s->G), s->stream));
         if (DIFF) {
             const size_t G1 = (size_t)s->G + 1;
             EHMM_TRY(rc_static_build(s, S, p, nrep, s->stream));
@@ -767,14 +834,16 @@ struct TmpDev {
 
 }  // namespace
 
+int64_t rc_limb_words(const ehmm_session *s) { return (int64_t)rc_acc_words(s->rc_columns, s->G); }
+
 // limbs -> fp64 tables (no-op when the tables were accumulated in fp64 or are already final)
 int rc_finalize(ehmm_session *s) {
     if (s->rc_final || !s->rc_exact) { s->rc_final = true; return EHMM_OK; }
     const int64_t n = (int64_t)s->rc_columns * (s->G + 1);
     const unsigned grid = (unsigned)std::min<int64_t>((n + 255) / 256, 148 * 8);
-    PROF(s, KID_RC_FINAL), rc_finalize_kernel<<<grid, 256, 0, s->stream>>>(s->rc_limbs.as<unsigned long long>(), n,
-                                                                        s->rc_buckets.as<double>(),
-                                                                        reinterpret_cast<const int *>(s->rc_coltot.as<int64_t>() + RC_MAXCOL));
+    PROF(s, KID_RC_FINAL), rc_finalize_kernel<<<grid, 256, 0, s->stream>>>(
+        rc_acc(s->rc_limbs.as<unsigned long long>(), s->rc_columns, s->G), s->rc_columns, s->G, s->rc_buckets.as<double>(),
+        reinterpret_cast<const int *>(s->rc_coltot.as<int64_t>() + RC_MAXCOL));
     EHMM_CK(cudaGetLastError());
     s->rc_final = true;
     return EHMM_OK;

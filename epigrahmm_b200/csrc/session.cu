@@ -877,7 +877,7 @@ int ehmm_rc_buckets_device(ehmm_session *s, void **ptr, int64_t *n, int *is_inte
     const int64_t cells = (int64_t)s->rc_columns * (s->G + 1);
     if (s->rc_exact) {
         *ptr = s->rc_limbs.p;
-        *n = 2 * cells;
+        *n = rc_limb_words(s);  // both limb arrays and the replicas of the frequent groups
         *is_integer = 1;
         s->rc_final = false;  // the caller is about to change the limbs: round them again
     } else {
