@@ -340,6 +340,55 @@ EO_API void eo_expstep(int64_t M, int K, const double *pi, const double *gamma, 
     }
 }
 
+/* NOT a restatement of the reference: the yardstick of SURVEY.md H4.  The same forward-backward with every
+ * vector normalised at every bin and long double (x87, 64-bit significand) arithmetic, so that its posteriors
+ * carry ~1e-19 relative error instead of the ulp(|logLik|) ~ 1e-8 that the reference's unscaled log-space
+ * recursion accumulates at 15 M bins.  Used only to say which of two differing results is the
+ * accurate one.  P1: M x K posteriors; returns the log-likelihood. */
+EO_API double eo_expstep_truth(int64_t M, int K, const double *pi, const double *gamma, const double *logf, double *P1) {
+    long double *A = (long double *)malloc(sizeof(long double) * (size_t)M * K);
+    long double ll = 0.0L, a[16], b[16], e[16], t[16];
+    if (!A) return NAN;
+    for (int64_t j = 0; j < M; j++) {
+        long double mx = logf[j];
+        for (int k = 1; k < K; k++) if (logf[j + k * M] > mx) mx = logf[j + k * M];
+        for (int k = 0; k < K; k++) e[k] = expl((long double)logf[j + k * M] - mx);
+        if (j == 0) {
+            for (int k = 0; k < K; k++) a[k] = (long double)pi[k] * e[k];
+        } else {
+            for (int k = 0; k < K; k++) {
+                long double s = 0.0L;
+                for (int i = 0; i < K; i++) s += A[(j - 1) * K + i] * (long double)gamma[i + k * K];
+                a[k] = s * e[k];
+            }
+        }
+        long double c = 0.0L;
+        for (int k = 0; k < K; k++) c += a[k];
+        for (int k = 0; k < K; k++) A[j * K + k] = a[k] / c;
+        ll += logl(c) + mx;
+    }
+    for (int k = 0; k < K; k++) b[k] = 1.0L;
+    for (int64_t j = M - 1; j >= 0; j--) {
+        long double z = 0.0L;
+        for (int k = 0; k < K; k++) z += A[j * K + k] * b[k];
+        for (int k = 0; k < K; k++) P1[j + k * M] = (double)(A[j * K + k] * b[k] / z);
+        if (j == 0) break;
+        long double mx = logf[j];
+        for (int k = 1; k < K; k++) if (logf[j + k * M] > mx) mx = logf[j + k * M];
+        for (int k = 0; k < K; k++) e[k] = expl((long double)logf[j + k * M] - mx) * b[k];
+        long double c = 0.0L;
+        for (int i = 0; i < K; i++) {
+            long double s = 0.0L;
+            for (int k = 0; k < K; k++) s += (long double)gamma[i + k * K] * e[k];
+            t[i] = s;
+            c += s;
+        }
+        for (int i = 0; i < K; i++) b[i] = t[i] / c;
+    }
+    free(A);
+    return (double)ll;
+}
+
 /* maxStepProb: src/maxStepProb.cpp:37-81.  gamma_out column-major K x K. */
 EO_API void eo_maxstepprob(int64_t M, int K, const double *logProb1, const double *logProb2,
                            double *pi_out, double *gamma_out) {

@@ -129,6 +129,18 @@ def expStep(pi, gamma, logf):
     return out
 
 
+def expStepTruth(pi, gamma, logf):
+    """NOT the reference: the scaled, long-double forward-backward used as the accuracy yardstick.
+    Returns (posteriors M x K, log-likelihood)."""
+    logf = _colmajor(logf)
+    M, K = logf.shape
+    P1 = np.empty((M, K), order="F")
+    f = lib().eo_expstep_truth
+    f.restype = C.c_double
+    ll = f(C.c_int64(M), K, _p(_f64(pi)), _p(_colmajor(gamma)), _p(logf), _p(P1))
+    return P1, float(ll)
+
+
 def maxStepProb(h):
     """src/maxStepProb.cpp:37-81 -> {'pi','gamma'}."""
     L1, L2 = _colmajor(h["logProb1"]), _colmajor(h["logProb2"])
