@@ -124,6 +124,9 @@ struct ehmm_session {
     // ---- datasets ----
     ehmm::DevBuf logf, logFP, logBP, logProb1, logProb2, eta, viterbi, vit_bp;
     bool vit_forward_done = false;
+    ehmm::DevBuf vit_work;       // tile sums, plan, look-back state and backtrace maps of the Viterbi scan
+    int vit_mode = 0;            // 0: parallel scan (sequential kernel where the integer model does not hold), 1: sequential kernel
+    int64_t vit_info[4] = {0};   // last forward pass: path (0 scan, 1 sequential, 2 scan abandoned), break tiles, half-way tiles, tiles
     unsigned valid = 0;        // DS_* bits: which datasets hold data
     bool stats_stale = false;  // datasets were replaced from the host; statistics must be recomputed
 

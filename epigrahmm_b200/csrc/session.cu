@@ -251,7 +251,7 @@ int ehmm_session_close(ehmm_session *s) {
         if (it != g_sessions.end() && it->second == s) g_sessions.erase(it);
     }
     DevBuf *bufs[] = {&s->counts_own, &s->offsets_own, &s->controls_own, &s->group, &s->u_chip, &s->u_off, &s->u_ctrl,
-                      &s->u_dsg, &s->logf, &s->logFP, &s->logBP, &s->logProb1, &s->logProb2, &s->eta, &s->viterbi, &s->vit_bp,
+                      &s->u_dsg, &s->logf, &s->logFP, &s->logBP, &s->logProb1, &s->logProb2, &s->eta, &s->viterbi, &s->vit_bp, &s->vit_work,
                       &s->tileops, &s->carries, &s->tilestats, &s->fbscal, &s->rangeops, &s->rangecarry, &s->rc_flag, &s->rc_scan,
                       &s->rc_buckets, &s->rc_limbs, &s->rc_coltot, &s->rc_static, &s->rc_unif, &s->rc_unif_spec, &s->rc_tmp, &s->mt_raw, &s->mt_raw2, &s->mt_windows, &s->gtab, &s->glm_ticket, &s->inner_part, &s->lgtab, &s->glm_part, &s->misc};
     for (DevBuf *b : bufs) b->release();
@@ -819,6 +819,18 @@ int ehmm_viterbi_forward(ehmm_session *s, const double *pi, const double *gamma,
 int ehmm_viterbi_backtrace(ehmm_session *s, int state_last, int *state_prev, double *states_out) {
     EHMM_TRY(check_session(s));
     return viterbi_backtrace(s, state_last, state_prev, states_out);
+}
+
+int ehmm_viterbi_mode(ehmm_session *s, int mode) {
+    EHMM_REQUIRE(s && (mode == 0 || mode == 1), EHMM_ERR_ARG, "viterbi_mode: 0 (parallel scan) or 1 (sequential kernel)");
+    s->vit_mode = mode;
+    return EHMM_OK;
+}
+
+int ehmm_viterbi_info(ehmm_session *s, int64_t *info4) {
+    EHMM_REQUIRE(s && info4, EHMM_ERR_ARG, "null pointer");
+    for (int i = 0; i < 4; i++) info4[i] = s->vit_info[i];
+    return EHMM_OK;
 }
 
 int ehmm_rng_set_state(ehmm_session *s, const uint32_t *state625) {

@@ -284,6 +284,16 @@ class Session:
         check(lib.ehmm_viterbi(self._h, dptr(_f64(pi)), dptr(_cm(gamma)), dptr(out)))
         return out
 
+    def viterbi_mode(self, mode):
+        """0: parallel scan (default), 1: the sequential kernel; the states are bit-identical"""
+        check(lib.ehmm_viterbi_mode(self._h, int(mode)))
+
+    def viterbi_info(self):
+        info = (C.c_int64 * 4)()
+        check(lib.ehmm_viterbi_info(self._h, info))
+        return {"path": ("scan", "sequential", "scan abandoned")[info[0]], "break_tiles": int(info[1]),
+                "halfway_tiles": int(info[2]), "tiles": int(info[3])}
+
     def viterbi_forward(self, pi, gamma, v_in=None):
         v_out = np.empty(self.K)
         check(lib.ehmm_viterbi_forward(self._h, dptr(_f64(pi)), dptr(_cm(gamma)), dptr(None if v_in is None else _f64(v_in)),

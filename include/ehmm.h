@@ -150,6 +150,14 @@ int ehmm_inner_mstep_sums(ehmm_session *s, double *sums);
 int ehmm_marginal_probability(ehmm_session *s, double *out);
 /* computeViterbiSequence, src/computeViterbiSequence.cpp:12-54 (states_out: M doubles or NULL). */
 int ehmm_viterbi(ehmm_session *s, const double *pi, const double *gamma, double *states_out);
+/* How the (max,+) recursion is run.  mode 0 (default): parallel scan -- inside one binade of LOGV the
+ * reference's fp64 recursion is exact integer arithmetic, hence associative; tiles that cross a binade or
+ * hold a half-way rounding case run the reference's operation order on one thread, and the whole chain
+ * does if the integer model is ever left.  mode 1: the sequential kernel for every bin.  The states are
+ * bit-identical either way.  info4 (last forward pass): path taken (0 scan, 1 sequential, 2 scan abandoned
+ * for the sequential kernel), tiles planned sequential, tiles that found a half-way case, tiles. */
+int ehmm_viterbi_mode(ehmm_session *s, int mode);
+int ehmm_viterbi_info(ehmm_session *s, int64_t *info4);
 
 /* Bin-block form of computeViterbiSequence: the (max,+) recursion is serial over the chain, so the
  * blocks run one after the other handing on K doubles (forward) and one state (backtrace).
