@@ -77,6 +77,8 @@ PROTOTYPES = {
     "ehmm_inner_maxstepprob": [_sess, _dp],
     "ehmm_marginal_probability": [_sess, _dp],
     "ehmm_viterbi": [_sess, _dp, _dp, _dp],
+    "ehmm_expstep_mode": [_sess, C.c_int],
+    "ehmm_materialize": [_sess],
     "ehmm_viterbi_mode": [_sess, C.c_int],
     "ehmm_viterbi_info": [_sess, C.POINTER(C.c_int64)],
     "ehmm_viterbi_forward": [_sess, _dp, _dp, _dp, _dp],

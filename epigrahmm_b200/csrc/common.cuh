@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <math.h>
 #include <string>
+#include <utility>
 #include <vector>
 #include "../../include/ehmm.h"
 
@@ -61,19 +62,20 @@ struct DevBuf {
 
 enum : unsigned {
     DS_LOGF = 1, DS_FP = 2, DS_BP = 4, DS_P1 = 8, DS_P2 = 16, DS_ETA = 32, DS_VIT = 64,
+    DS_P1LIN = 128,  // the posteriors P1 themselves (the lean E-step writes these instead of logProb1)
     DS_ESTEP = DS_FP | DS_BP | DS_P1 | DS_P2
 };
 
 // kernel ids for the launch counters / optional CUDA-event profile (ehmm_profile*)
 enum KernelId : int {
     KID_EMIS_TAB, KID_EMIS_GATHER, KID_EMIS_CONSENSUS, KID_EMIS_DIFF, KID_EMIS_INNER, KID_INNER_MSTEP,
-    KID_FB_REDUCE, KID_FB_CARRY, KID_FB_APPLY, KID_FB_FIX, KID_FB_STATS,
+    KID_FB_REDUCE, KID_FB_CARRY, KID_FB_APPLY, KID_FB_APPLY_LEAN, KID_FB_FIX, KID_FB_STATS,
     KID_RC_COUNT, KID_RC_SCAN, KID_MT, KID_RC_APPLY, KID_RC_STATIC, KID_RC_FINAL, KID_GLM, KID_GLM_FINAL,
     KID_VIT_FWD, KID_VIT_BWD, KID_MISC, KID_COUNT
 };
 static const char *const kKernelNames[KID_COUNT] = {
     "emis_tables", "emis_gather", "emis_consensus", "emis_diff_hmm", "emis_inner", "inner_mstep",
-    "fb_reduce", "fb_carry", "fb_apply", "fb_boundary_fix", "fb_stats",
+    "fb_reduce", "fb_carry", "fb_apply", "fb_apply_em", "fb_boundary_fix", "fb_stats",
     "rc_count", "rc_scan", "mt_generate", "rc_apply", "rc_static", "rc_finalize", "glm", "glm_final",
     "viterbi_forward", "viterbi_backtrace", "misc"};
 
@@ -123,6 +125,15 @@ struct ehmm_session {
 
     // ---- datasets ----
     ehmm::DevBuf logf, logFP, logBP, logProb1, logProb2, eta, viterbi, vit_bp;
+    // ---- lean (EM-internal) E-step ----
+    ehmm::DevBuf prob1;          // M x K posteriors, linear (DS_P1LIN)
+    ehmm::DevBuf logf_alt;       // second emission buffer: an emission computed while the datasets of the last lean
+                                 // E-step are still owed goes here, so that they can be produced from the old one
+    bool lean_mode = false;      // ehmm_expstep_mode: E-steps write P1 + statistics only
+    bool lazy_full = false;      // logFP / logBP / logProb1 / logProb2 of the last E-step have not been produced yet
+    const double *estep_logf = nullptr;          // emission the last E-step ran on
+    double estep_cin[2][EHMM_MAX_K + 1] = {{0}};  // ... and the vectors entering / leaving its block
+    bool fb_counted = false;     // the last lean E-step (K = 2) counted the weights below rc_hint_p per warp tile
     bool vit_forward_done = false;
     ehmm::DevBuf vit_work;       // tile sums, plan, look-back state and backtrace maps of the Viterbi scan
     int vit_mode = 0;            // 0: parallel scan (sequential kernel where the integer model does not hold), 1: sequential kernel
@@ -244,11 +255,37 @@ int fb_expstep(ehmm_session *s, const double *d_logf);
 int fb_reduce(ehmm_session *s, const double *d_logf, double *op_host);
 int fb_apply(ehmm_session *s, const double *fwd_carry, const double *bwd_carry, double *fwd_out);
 int fb_fetch_stats(ehmm_session *s);
+int fb_materialize(ehmm_session *s);
 // RNG state on the host: a draw only books the new position (rng_note_advance) and queues the copy
 // of the 624 words; whoever needs the words waits for it here.
 void rng_note_advance(ehmm_session *s, int64_t n);
 int rng_sync_host(ehmm_session *s);
 inline bool has(const ehmm_session *s, unsigned bits) { return (s->valid & bits) == bits; }
+// datasets that exist or can be produced on demand from the last lean E-step
+inline bool avail(const ehmm_session *s, unsigned bits) {
+    return ((s->valid | (s->lazy_full ? (unsigned)DS_ESTEP : 0u)) & bits) == bits;
+}
+// posteriors in either form
+inline bool has_post(const ehmm_session *s) { return (s->valid & (DS_P1 | DS_P1LIN)) != 0; }
+// produce the datasets `bits` names if a lean E-step still owes them
+inline int ensure(ehmm_session *s, unsigned bits) {
+    if (s->lazy_full && (bits & DS_ESTEP & ~s->valid)) return fb_materialize(s);
+    return EHMM_OK;
+}
+// where kernels read the posteriors P1[j,k] from: the linear copy when there is one, else exp(logProb1)
+struct P1Src {
+    const double *p;
+    int lin;
+};
+inline P1Src p1_source(const ehmm_session *s) {
+    if (s->valid & DS_P1LIN) return P1Src{s->prob1.as<double>(), 1};
+    return P1Src{s->logProb1.as<double>(), 0};
+}
+// the buffer the next emission is written to (see logf_alt)
+inline int logf_for_write(ehmm_session *s, size_t bytes) {
+    if (s->lazy_full && s->estep_logf == s->logf.p && s->logf.p) std::swap(s->logf, s->logf_alt);
+    return s->logf.reserve(bytes);
+}
 // logProb1 (or what it is summed against: the groups, the block) changed: nothing derived from it may be reused
 inline void posteriors_changed(ehmm_session *s) {
     s->lp1_gen++;

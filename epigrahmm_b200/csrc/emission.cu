@@ -234,7 +234,7 @@ template <int NMAX, int BMAX, bool GROUPED, bool COUNT>
 __global__ void __launch_bounds__(EM_NT, (GROUPED && BMAX <= 14) ? 3 : 1)
     emis_inner_kernel(int64_t M, int N, const int32_t *__restrict__ y, const double *__restrict__ off,
                       const __grid_constant__ EmisParams P, const __grid_constant__ MixParams X,
-                      const double *__restrict__ tab, double *__restrict__ eta, const double *__restrict__ lp1,
+                      const double *__restrict__ tab, double *__restrict__ eta, const double *__restrict__ lp1, int lin,
                       double *__restrict__ part, double pcut, int64_t nwt, int *__restrict__ counts) {
     double acc[BMAX + 1];
 #pragma unroll
@@ -259,11 +259,11 @@ __global__ void __launch_bounds__(EM_NT, (GROUPED && BMAX <= 14) ? 3 : 1)
                         s += v[b];
                     }
                 }
-                p1 = lp1 ? exp(__ldg(lp1 + M + j)) : 0.0;
+                p1 = lp1 ? rc_post(__ldg(lp1 + M + j), lin) : 0.0;
                 acc[BMAX] += p1;
             }
             if (COUNT) {
-                const double w0 = valid ? exp(__ldg(lp1 + j)) : 2.0;  // 2.0: never below a cut <= 1
+                const double w0 = valid ? rc_post(__ldg(lp1 + j), lin) : 2.0;  // 2.0: never below a cut <= 1
                 const int n = __popc(__ballot_sync(0xffffffffu, rc_flagged(w0, pcut)));
                 if (lane == 0) cnt0 += n;
             }
@@ -283,7 +283,7 @@ __global__ void __launch_bounds__(EM_NT, (GROUPED && BMAX <= 14) ? 3 : 1)
                 }
             }
             if (COUNT) {
-                const double w2 = valid ? exp(__ldg(lp1 + 2 * M + j)) : 2.0;
+                const double w2 = valid ? rc_post(__ldg(lp1 + 2 * M + j), lin) : 2.0;
                 const int n = __popc(__ballot_sync(0xffffffffu, rc_flagged(w2, pcut)));
                 const int c = X.B + 1;
                 if (lane == (c & 31)) { if (c < 32) cnt0 += n; else cnt1 += n; }
@@ -314,14 +314,14 @@ __global__ void __launch_bounds__(EM_NT, (GROUPED && BMAX <= 14) ? 3 : 1)
 }
 
 // innerMaxStepProb partial sums: part[blk*(B+1) + b] = sum_j p1[j]*eta[j,b], [.. + B] = sum_j p1[j]
-__global__ void __launch_bounds__(256) inner_mstep_kernel(int64_t M, int B, const double *__restrict__ lp1_col1,
+__global__ void __launch_bounds__(256) inner_mstep_kernel(int64_t M, int B, const double *__restrict__ lp1_col1, int lin,
                                                           const double *__restrict__ eta, double *__restrict__ part) {
     __shared__ double sh[8];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     for (int b = 0; b <= B; b++) {
         double s = 0.0;
         for (int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x; j < M; j += (int64_t)gridDim.x * 256) {
-            const double p = exp(__ldg(lp1_col1 + j));
+            const double p = rc_post(__ldg(lp1_col1 + j), lin);
             s += (b < B) ? p * __ldg(eta + j + (int64_t)b * M) : p;
         }
         for (int dd = 16; dd > 0; dd >>= 1) s += __shfl_down_sync(0xffffffffu, s, dd);
@@ -471,7 +471,7 @@ int emis_consensus(ehmm_session *s, const double *th1, const double *th2, int P_
     fill_density(P, 1, P_ == 3 ? th2[0] + th2[1] * c1 : th2[0], th2[P_ - 1]);
     if (zi) P.z0 = P_ == 3 ? zi[0] + zi[1] * c1 : zi[0];
     EHMM_TRY(prepare_tab(s, P, 2, minZero));
-    EHMM_TRY(s->logf.reserve(sizeof(double) * s->M * 2));
+    EHMM_TRY(logf_for_write(s, sizeof(double) * s->M * 2));
     EHMM_TRY(zi ? launch_consensus<true>(s, P) : launch_consensus<false>(s, P));
     s->valid |= DS_LOGF;
     return EHMM_OK;
@@ -485,7 +485,7 @@ int emis_init(ehmm_session *s, const double *psi1, const double *psi2) {
     fill_density(P, 0, psi1[0], psi1[1]);
     fill_density(P, 1, psi2[0], psi2[1]);
     EHMM_TRY(prepare_tab(s, P, 2, 2.2250738585072014e-308));
-    EHMM_TRY(s->logf.reserve(sizeof(double) * s->M * 2));
+    EHMM_TRY(logf_for_write(s, sizeof(double) * s->M * 2));
     if (use_groups(s, 2)) {
         EHMM_TRY(s->gtab.reserve(sizeof(double2) * (size_t)(s->G + 1)));
         const unsigned gb = (unsigned)((s->G + 1 + EM_NT - 1) / EM_NT);
@@ -513,7 +513,7 @@ int emis_differential_hmm(ehmm_session *s, const double *delta, const double *ps
     fill_diff(P, psi, zinb);
     EHMM_TRY(fill_mix(s, X, delta));
     EHMM_TRY(prepare_tab(s, P, 2, minZero));
-    EHMM_TRY(s->logf.reserve(sizeof(double) * s->M * 3));
+    EHMM_TRY(logf_for_write(s, sizeof(double) * s->M * 3));
     const int g = grid_for(s->M);
     const int32_t *src_y = s->d_counts;
     const double *src_off = s->d_offsets, *src_tab = s->lgtab.as<double>();
@@ -553,10 +553,11 @@ int emis_inner_estep(ehmm_session *s, const double *delta, const double *psi, do
     // fuse innerMaxStepProb's sums when the posteriors of the current E-step are in place, and the
     // rejection control's flagged counts when the cut its next call will use is known (ehmm_rc_hint, or
     // the previous call's cut: max(0.9^iter, probCut) is constant once it has reached probCut)
-    const bool fuse = has(s, DS_P1) && s->K == 3;
+    const bool fuse = has_post(s) && s->K == 3;
+    const P1Src ps = p1_source(s);
     const double pcut = s->rc_hint_p;
     const bool count = fuse && pcut > 0.0 && s->G > 0 && s->B + 2 <= 64;
-    const double *lp1 = fuse ? s->logProb1.as<double>() : nullptr;
+    const double *lp1 = fuse ? ps.p : nullptr;
     const int64_t nwt = rc_num_wtiles(s->M);
     if (count) EHMM_TRY(s->rc_flag.reserve(sizeof(int) * nwt * (s->B + 2)));
     EHMM_TRY(s->inner_part.reserve(sizeof(double) * ((size_t)g * (s->B + 1) + s->B + 1)));
@@ -564,7 +565,7 @@ int emis_inner_estep(ehmm_session *s, const double *delta, const double *psi, do
     const bool grouped = (src_y == nullptr);
 #define EHMM_INNER2(NM, BM, GR, CT)                                                                                   \
     PROF(s, KID_EMIS_INNER), emis_inner_kernel<NM, BM, GR, CT><<<g, EM_NT, 0, s->stream>>>(                           \
-        s->M, s->N, src_y, src_off, P, X, src_tab, s->eta.as<double>(), lp1, part, pcut, nwt, s->rc_flag.as<int>())
+        s->M, s->N, src_y, src_off, P, X, src_tab, s->eta.as<double>(), lp1, ps.lin, part, pcut, nwt, s->rc_flag.as<int>())
 #define EHMM_INNER(NM, BM, GR)                        \
     do {                                              \
         if (count) EHMM_INNER2(NM, BM, GR, true);     \
@@ -608,7 +609,7 @@ int emis_inner_estep(ehmm_session *s, const double *delta, const double *psi, do
 
 // sums[b] = sum_j P1[j,1]*eta[j,b] (b < B), sums[B] = sum_j P1[j,1]  (additive across bin blocks)
 int inner_mstep_sums(ehmm_session *s, double *sums) {
-    EHMM_REQUIRE(has(s, DS_ETA | DS_P1), EHMM_ERR_STATE, "innerMaxStepProb needs mixtureProb and logProb1");
+    EHMM_REQUIRE(has(s, DS_ETA) && has_post(s), EHMM_ERR_STATE, "innerMaxStepProb needs mixtureProb and logProb1");
     EHMM_REQUIRE(s->K == 3, EHMM_ERR_ARG, "innerMaxStepProb needs K=3");
     const int B = s->B;
     int nblk = 148 * 4;
@@ -621,7 +622,7 @@ int inner_mstep_sums(ehmm_session *s, double *sums) {
         EHMM_TRY(s->misc.reserve(sizeof(double) * ((size_t)nblk * (B + 1) + B + 1)));
         part = s->misc.as<double>();
         out = part + (size_t)nblk * (B + 1);
-        PROF(s, KID_INNER_MSTEP), inner_mstep_kernel<<<nblk, 256, 0, s->stream>>>(s->M, B, s->logProb1.as<double>() + s->M, s->eta.as<double>(), part);
+        PROF(s, KID_INNER_MSTEP), inner_mstep_kernel<<<nblk, 256, 0, s->stream>>>(s->M, B, p1_source(s).p + s->M, p1_source(s).lin, s->eta.as<double>(), part);
         EHMM_CK(cudaGetLastError());
     }
     PROF(s, KID_MISC), colsum_kernel<<<B + 1, 256, 0, s->stream>>>(part, nblk, B + 1, out);

@@ -17,6 +17,7 @@
 // followed by a deterministic reduction of the per-tile statistics.
 #include "common.cuh"
 #include "logtab.h"
+#include "rcweights.cuh"
 
 namespace ehmm {
 
@@ -498,12 +499,34 @@ __global__ void __launch_bounds__(64) fb_range_apply_kernel(const double *__rest
     for (int i = threadIdx.x; i < n * CN; i += 64) carries[t0 * CN + i] = sOut[i];
 }
 
+// what the EM-internal form of the kernel writes instead of the four log-domain datasets
+struct LeanOut {
+    double *prob1;     // M x K posteriors P1 (linear)
+    int *counts;       // K = 2: weights below the rejection cut per (state, warp tile of RC_WT bins), or nullptr
+    double pcut;       // the cut
+    int64_t nwt;       // warp tiles in the block
+};
+
+// posterior of one state where the linear product al * be / Z left the normal range (or an operand of it
+// did): exp of the log-domain value the full kernel stores, so that "is it exactly 0" -- which decides
+// whether the rejection control draws a uniform for it -- has the reference's meaning
+__device__ __noinline__ double post_slow(double al, double be, double Z, double a, double f, double dscale) {
+    const double lf = not_tiny(al) ? log(al) : (log(a) + f + dscale);
+    return exp(fmin((lf + log(be)) - log(Z), 0.0));
+}
+
 // ---- kernel C: tile -> all outputs + statistics -------------------------------------------------
-template <int K, int NT, int L>
+// LEAN (the E-step inside the EM loop): nothing there reads logFP, logBP or logProb2 -- maxStepProb, Q and
+// BIC come from the fused statistics, the rejection control and innerMaxStepProb want exp(logProb1)
+// (R/base-EM.R:113-158, 191-225) -- so only the posteriors P1 are written, linear, and for K = 2 the
+// rejection control's counting pass is done on the way.  The datasets are produced by the full form of the
+// kernel when somebody asks for them (fb_materialize).
+template <int K, int NT, int L, bool LEAN>
 __global__ void __launch_bounds__(NT, FBCfg<K>::APPLY_CTAS)
     fb_apply_kernel(const double *__restrict__ logf, int64_t M, int first_is_start, const __grid_constant__ FBParams P,
                     const double *__restrict__ carries, double *__restrict__ logFP, double *__restrict__ logBP,
-                    double *__restrict__ logProb1, double *__restrict__ logProb2, double *__restrict__ tilestats) {
+                    double *__restrict__ logProb1, double *__restrict__ logProb2, double *__restrict__ tilestats,
+                    double *__restrict__ row0, const LeanOut lean) {
     constexpr int TB = NT * L, NW = NT / 32, OPN = K * K + 1, NS = K * K + 1;
     extern __shared__ double smem[];
     double2 *sT = reinterpret_cast<double2 *>(smem);  // 128 entries of the log table
@@ -520,7 +543,9 @@ __global__ void __launch_bounds__(NT, FBCfg<K>::APPLY_CTAS)
     const bool special0 = first_is_start && blockIdx.x == 0;
     const double *cr = carries + (int64_t)blockIdx.x * (2 * K + 2);
 
-    if (tid < 128) sT[tid] = kLogTab[tid];
+    __shared__ int sCnt[L * K];
+    if (!LEAN && tid < 128) sT[tid] = kLogTab[tid];
+    if (LEAN && tid < L * K) sCnt[tid] = 0;
     load_tile<K, NT, L, false>(logf, M, s0, nvalid, nullptr, sM, sA);
     __syncthreads();
     {
@@ -635,6 +660,102 @@ __global__ void __launch_bounds__(NT, FBCfg<K>::APPLY_CTAS)
         }
         return log(av) + __ldg(logf + (int64_t)k * M + s0 + bb) + (scp - sScF[bb]);
     };
+    if constexpr (LEAN) {
+        const bool count = (K == 2) && lean.counts != nullptr;
+#pragma unroll 1
+        for (int r = 0; r < L; r++) {
+            const int b = r * NT + tid;
+            const bool valid = b < nvalid;
+            const int64_t j = s0 + b;
+            const bool isfirst = special0 && b == 0;
+            double al[K], be[K], f[K], alp[K], a[K], p1[K];
+            if (valid) {
+#pragma unroll
+                for (int k = 0; k < K; k++) { al[k] = sA[k * TB + b]; be[k] = sB[k * TB + b]; f[k] = __ldg(logf + (int64_t)k * M + j); }
+                if (b > 0) {
+#pragma unroll
+                    for (int k = 0; k < K; k++) alp[k] = sA[k * TB + b - 1];
+                } else {
+#pragma unroll
+                    for (int k = 0; k < K; k++) alp[k] = cr[k];
+                }
+                if (isfirst) {
+#pragma unroll
+                    for (int k = 0; k < K; k++) a[k] = alp[k];
+                } else {
+#pragma unroll
+                    for (int c = 0; c < K; c++) {
+                        double t = alp[0] * P.g[c];
+#pragma unroll
+                        for (int i = 1; i < K; i++) t = fma(alp[i], P.g[i * K + c], t);
+                        a[c] = t;
+                    }
+                }
+                double Z = 0.0;
+#pragma unroll
+                for (int k = 0; k < K; k++) Z = fma(al[k], be[k], Z);
+                bool fast = normal_pos(Z);
+#pragma unroll
+                for (int k = 0; k < K; k++) fast = fast && not_tiny(al[k]) && normal_pos(be[k]);
+                const double rZ = rcp_fast(Z);
+#pragma unroll
+                for (int k = 0; k < K; k++) {
+                    p1[k] = fmin(al[k] * be[k] * rZ, 1.0);
+                    fast = fast && normal_pos(p1[k]);
+                }
+                double x[K];
+                if (fast) {
+#pragma unroll
+                    for (int k = 0; k < K; k++) x[k] = p1[k];
+                } else {
+                    const double d = (b > 0 ? sScF[b - 1] : 0.0) - sScF[b];
+#pragma unroll
+                    for (int k = 0; k < K; k++) x[k] = post_slow(al[k], be[k], Z, a[k], f[k], d);
+                }
+#pragma unroll
+                for (int k = 0; k < K; k++) {
+                    lean.prob1[(int64_t)k * M + j] = x[k];
+                    acc[K * K] = fma(p1[k], f[k], acc[K * K]);
+                }
+                if (blockIdx.x == 0 && b == 0) {  // logProb1[0,] for maxStepProb's pi and Q (the block's first bin)
+                    const double d = -sScF[0];
+                    const double lZ = log(Z);
+#pragma unroll
+                    for (int k = 0; k < K; k++) {
+                        const double lf = not_tiny(al[k]) ? log(al[k]) : (log(a[k]) + f[k] + d);
+                        row0[k] = fmin((lf + log(be[k])) - lZ, 0.0);
+                    }
+                }
+                if (!isfirst) {
+#pragma unroll
+                    for (int l = 0; l < K; l++) {
+                        const double ra = p1[l] * rcp_fast(a[l]);
+#pragma unroll
+                        for (int i = 0; i < K; i++) acc[i * K + l] = fma(alp[i] * P.g[i * K + l], ra, acc[i * K + l]);
+                    }
+                }
+                if (count) {
+#pragma unroll
+                    for (int k = 0; k < K; k++) p1[k] = x[k];
+                }
+            }
+            if (count) {
+#pragma unroll
+                for (int k = 0; k < K; k++) {
+                    const int n = __popc(__ballot_sync(0xffffffffu, valid && rc_flagged(p1[k], lean.pcut)));
+                    if (lane == 0 && n) atomicAdd(&sCnt[r * K + k], n);
+                }
+            }
+        }
+        if (count) {
+            __syncthreads();
+            if (tid < L * K) {  // row r of the tile is warp tile L * blockIdx.x + r of the rejection control
+                const int r = tid / K, k = tid - r * K;
+                const int64_t wt = (int64_t)blockIdx.x * L + r;
+                if (wt < lean.nwt) lean.counts[(int64_t)k * lean.nwt + wt] = sCnt[tid];
+            }
+        }
+    } else {
     // lane 0 of every 32-bin row needs log alpha~ of the bin before the row (another warp's bin)
     for (int idx = tid; idx < (TB / 32) * K; idx += NT) {
         const int row = idx / K, k = idx - row * K, bb = 32 * row - 1;
@@ -726,6 +847,10 @@ __global__ void __launch_bounds__(NT, FBCfg<K>::APPLY_CTAS)
                 logProb1[(int64_t)k * M + j] = lp1[k];
                 acc[K * K] = fma(p1[k], f[k], acc[K * K]);
             }
+            if (blockIdx.x == 0 && b == 0) {
+#pragma unroll
+                for (int k = 0; k < K; k++) row0[k] = lp1[k];
+            }
             if (isfirst) {
 #pragma unroll
                 for (int c = 0; c < K * K; c++) logProb2[(int64_t)c * M + j] = lKK;
@@ -745,6 +870,7 @@ __global__ void __launch_bounds__(NT, FBCfg<K>::APPLY_CTAS)
             }
         }
     }
+    }  // !LEAN
     // ---- block reduction of the statistics (fixed order -> deterministic) ----
 #pragma unroll
     for (int i = 0; i < NS; i++) {
@@ -863,9 +989,10 @@ void fill_params(const ehmm_session *s, FBParams &P) {
 }
 
 // scal layout (doubles): [0] ll | [1 .. OPN] block operator | [OPN+1 .. OPN+1+K] fwd vector after block
-// | [OPN+2+K .. OPN+2+2K] bwd vector in front of block | [OPN+3+2K ..] statistics (NS)
+// | [OPN+2+K .. OPN+2+2K] bwd vector in front of block | [OPN+3+2K ..] statistics (NS) | logProb1[0,] (K)
 template <int K> constexpr int scal_stats_off() { return (K * K + 1) + 3 + 2 * K; }
-template <int K> constexpr int scal_len() { return scal_stats_off<K>() + K * K + 1; }
+template <int K> constexpr int scal_row0_off() { return scal_stats_off<K>() + K * K + 1; }
+template <int K> constexpr int scal_len() { return scal_row0_off<K>() + K; }
 
 template <int K> int64_t num_tiles(int64_t M) {
     constexpr int64_t TB = (int64_t)FBCfg<K>::NT * FBCfg<K>::L;
@@ -893,16 +1020,14 @@ template <int K> int ensure_scratch(ehmm_session *s) {
     EHMM_TRY(s->fbscal.reserve(sizeof(double) * scal_len<K>()));
     EHMM_TRY(s->rangeops.reserve(sizeof(double) * MAX_RANGES * (K * K + 1)));
     EHMM_TRY(s->rangecarry.reserve(sizeof(double) * MAX_RANGES * (2 * K + 2)));
-    EHMM_TRY(s->logFP.reserve(sizeof(double) * s->M * K));
-    EHMM_TRY(s->logBP.reserve(sizeof(double) * s->M * K));
-    EHMM_TRY(s->logProb1.reserve(sizeof(double) * s->M * K));
-    EHMM_TRY(s->logProb2.reserve(sizeof(double) * s->M * K * K));
     static bool attr_done[EHMM_MAX_K + 1] = {false};
     if (!attr_done[K]) {
         using C = FBCfg<K>;
         EHMM_CK(cudaFuncSetAttribute(fb_reduce_kernel<K, C::NT, C::L>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)reduce_smem<K>()));
-        EHMM_CK(cudaFuncSetAttribute(fb_apply_kernel<K, C::NT, C::L>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        EHMM_CK(cudaFuncSetAttribute(fb_apply_kernel<K, C::NT, C::L, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)apply_smem<K>()));
+        EHMM_CK(cudaFuncSetAttribute(fb_apply_kernel<K, C::NT, C::L, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)apply_smem<K>()));
         // the range kernels stage up to MAX_Q tile operators in shared memory
         EHMM_CK(cudaFuncSetAttribute(fb_range_reduce_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -938,7 +1063,7 @@ template <int K> int launch_reduce(ehmm_session *s, const double *d_logf, int mo
     return EHMM_OK;
 }
 
-template <int K> int launch_apply(ehmm_session *s, const double *d_logf, const CarryIn &cin) {
+template <int K> int launch_apply(ehmm_session *s, const double *d_logf, const CarryIn &cin, bool lean) {
     using C = FBCfg<K>;
     FBParams P;
     fill_params(s, P);
@@ -953,18 +1078,45 @@ template <int K> int launch_apply(ehmm_session *s, const double *d_logf, const C
     PROF(s, KID_FB_CARRY), fb_range_apply_kernel<K><<<R, 64, sizeof(double) * q * (K * K + 1 + 2 * K + 2), s->stream>>>(
         s->tileops.as<double>(), nT, q, s->rangecarry.as<double>(), s->carries.as<double>());
     EHMM_CK(cudaGetLastError());
-    PROF(s, KID_FB_APPLY), fb_apply_kernel<K, C::NT, C::L><<<(unsigned)nT, C::NT, apply_smem<K>(), s->stream>>>(
-        d_logf, s->M, first, P, s->carries.as<double>(), s->logFP.as<double>(), s->logBP.as<double>(),
-        s->logProb1.as<double>(), s->logProb2.as<double>(), s->tilestats.as<double>());
-    EHMM_CK(cudaGetLastError());
-    if (nT > 1) {
-        PROF(s, KID_FB_FIX), fb_boundary_fix_kernel<K><<<(unsigned)((nT - 1 + 255) / 256), 256, 0, s->stream>>>(
-            s->M, nT, C::NT * C::L, P, s->carries.as<double>(), d_logf, s->logFP.as<double>(), s->logProb1.as<double>(),
-            s->logProb2.as<double>());
+    double *row0 = scal + scal_row0_off<K>();
+    if (lean) {
+        EHMM_TRY(s->prob1.reserve(sizeof(double) * s->M * K));
+        LeanOut lo = {s->prob1.as<double>(), nullptr, 0.0, rc_num_wtiles(s->M)};
+        s->fb_counted = false;
+        // K = 2: the tile's rows are the rejection control's warp tiles, so its counting pass rides along when
+        // the cut of the coming call is known (ehmm_rc_hint, or the previous call's)
+        if (K == 2 && C::NT == RC_WT && s->rc_hint_p > 0.0 && s->rc_hint_p <= 1.0) {
+            EHMM_TRY(s->rc_flag.reserve(sizeof(int) * lo.nwt * K));
+            lo.counts = s->rc_flag.as<int>();
+            lo.pcut = s->rc_hint_p;
+            s->fb_counted = true;
+        }
+        PROF(s, KID_FB_APPLY_LEAN), fb_apply_kernel<K, C::NT, C::L, true><<<(unsigned)nT, C::NT, apply_smem<K>(), s->stream>>>(
+            d_logf, s->M, first, P, s->carries.as<double>(), nullptr, nullptr, nullptr, nullptr, s->tilestats.as<double>(), row0, lo);
         EHMM_CK(cudaGetLastError());
+    } else {
+        EHMM_TRY(s->logFP.reserve(sizeof(double) * s->M * K));
+        EHMM_TRY(s->logBP.reserve(sizeof(double) * s->M * K));
+        EHMM_TRY(s->logProb1.reserve(sizeof(double) * s->M * K));
+        EHMM_TRY(s->logProb2.reserve(sizeof(double) * s->M * K * K));
+        const LeanOut lo = {nullptr, nullptr, 0.0, 0};
+        PROF(s, KID_FB_APPLY), fb_apply_kernel<K, C::NT, C::L, false><<<(unsigned)nT, C::NT, apply_smem<K>(), s->stream>>>(
+            d_logf, s->M, first, P, s->carries.as<double>(), s->logFP.as<double>(), s->logBP.as<double>(),
+            s->logProb1.as<double>(), s->logProb2.as<double>(), s->tilestats.as<double>(), row0, lo);
+        EHMM_CK(cudaGetLastError());
+        if (nT > 1) {
+            PROF(s, KID_FB_FIX), fb_boundary_fix_kernel<K><<<(unsigned)((nT - 1 + 255) / 256), 256, 0, s->stream>>>(
+                s->M, nT, C::NT * C::L, P, s->carries.as<double>(), d_logf, s->logFP.as<double>(), s->logProb1.as<double>(),
+                s->logProb2.as<double>());
+            EHMM_CK(cudaGetLastError());
+        }
     }
     PROF(s, KID_FB_STATS), fb_stats_kernel<<<K * K + 1, 256, 0, s->stream>>>(s->tilestats.as<double>(), nT, K * K + 1, scal + scal_stats_off<K>());
     EHMM_CK(cudaGetLastError());
+    // what fb_materialize needs to produce the datasets of this E-step later
+    s->estep_logf = d_logf;
+    for (int k = 0; k <= K; k++) { s->estep_cin[0][k] = cin.start[k]; s->estep_cin[1][k] = cin.end[k]; }
+    s->lazy_full = lean;
     return EHMM_OK;
 }
 
@@ -973,7 +1125,15 @@ template <int K> int expstep_impl(ehmm_session *s, const double *d_logf) {
     EHMM_TRY(launch_reduce<K>(s, d_logf, 0));
     CarryIn cin = {};  // start vector (pi, 0), end vector (1, 0)
     for (int k = 0; k < K; k++) { cin.start[k] = s->h_pi[k]; cin.end[k] = 1.0; }
-    EHMM_TRY(launch_apply<K>(s, d_logf, cin));
+    EHMM_TRY(launch_apply<K>(s, d_logf, cin, s->lean_mode));
+    return EHMM_OK;
+}
+
+// the four log-domain datasets of the last (lean) E-step: same logf, same carries, same kernel as a full E-step
+template <int K> int materialize_impl(ehmm_session *s) {
+    CarryIn cin = {};
+    for (int k = 0; k <= K; k++) { cin.start[k] = s->estep_cin[0][k]; cin.end[k] = s->estep_cin[1][k]; }
+    EHMM_TRY(launch_apply<K>(s, s->estep_logf, cin, false));
     return EHMM_OK;
 }
 
@@ -992,7 +1152,7 @@ template <int K> int apply_impl(ehmm_session *s, const double *d_logf, const dou
     double *scal = s->fbscal.as<double>();
     CarryIn cin = {};
     for (int k = 0; k <= K; k++) { cin.start[k] = fwd[k]; cin.end[k] = bwd[k]; }
-    EHMM_TRY(launch_apply<K>(s, d_logf, cin));
+    EHMM_TRY(launch_apply<K>(s, d_logf, cin, s->lean_mode));
     if (fwd_out) {
         EHMM_CK(cudaMemcpyAsync(s->h_pinned + 16, scal + (K * K + 1) + 1, sizeof(double) * (K + 1),
                                 cudaMemcpyDeviceToHost, s->stream));
@@ -1045,11 +1205,9 @@ template <int K> int fetch_stats_impl(ehmm_session *s) {
     }
     double *scal = s->fbscal.as<double>();
     EHMM_CK(cudaMemcpyAsync(hp, scal, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
-    EHMM_CK(cudaMemcpyAsync(hp + 1, scal + scal_stats_off<K>(), sizeof(double) * (K * K + 1), cudaMemcpyDeviceToHost,
+    // statistics and logProb1[0,] sit next to each other
+    EHMM_CK(cudaMemcpyAsync(hp + 1, scal + scal_stats_off<K>(), sizeof(double) * (K * K + 1 + K), cudaMemcpyDeviceToHost,
                             s->stream));
-    for (int k = 0; k < K; k++)
-        EHMM_CK(cudaMemcpyAsync(hp + 1 + K * K + 1 + k, s->logProb1.as<double>() + (int64_t)k * s->M, sizeof(double),
-                                cudaMemcpyDeviceToHost, s->stream));
     EHMM_CK(cudaStreamSynchronize(s->stream));
     s->h_ll = hp[0];
     for (int i = 0; i < K * K + 1; i++) s->h_stats[i] = hp[1 + i];
@@ -1083,6 +1241,15 @@ int fb_apply(ehmm_session *s, const double *fwd_carry, const double *bwd_carry, 
     if (s->K == 3) return apply_impl<3>(s, d_logf, fwd_carry, bwd_carry, fwd_out);
     set_error("expStep: K=%d unsupported (K must be 2 or 3)", s->K);
     return EHMM_ERR_ARG;
+}
+
+int fb_materialize(ehmm_session *s) {
+    if (!s->lazy_full) return EHMM_OK;
+    EHMM_REQUIRE(s->estep_logf != nullptr, EHMM_ERR_STATE, "the E-step's emission is no longer available");
+    if (s->K == 2) EHMM_TRY(materialize_impl<2>(s));
+    else EHMM_TRY(materialize_impl<3>(s));
+    s->valid |= DS_ESTEP;
+    return EHMM_OK;
 }
 
 int fb_fetch_stats(ehmm_session *s) {

@@ -58,11 +58,12 @@ __device__ __forceinline__ double mt_to_unif(uint32_t tempered) {
 // column c of the consensus model: exp(logProb1[:,c]); of the differential model: background,
 // B mixture components P1[:,1]*eta[:,b], enrichment (src/differentialRejectionControlled.cpp:34-45)
 struct RCSrc {
-    const double *lp1;
+    const double *lp1;  // logProb1, or P1 itself when lin is set
     const double *eta;
     int64_t M;
     int B;         // 0 = consensus
     int columns;
+    int lin;
 };
 struct RCBase {
     int64_t ubase[RC_MAXCOL];  // where the draws of each column start in the uniform buffer
@@ -71,9 +72,9 @@ struct RCBase {
 // posteriors of bin j (exp once per bin; the count and the apply kernel must see the same bits, so
 // both go through these two functions and nothing here can contract into an FMA)
 template <bool DIFF> __device__ __forceinline__ void rc_posteriors(const RCSrc &S, int64_t j, double (&p1)[3]) {
-    p1[0] = exp(__ldg(S.lp1 + j));
-    p1[1] = exp(__ldg(S.lp1 + S.M + j));
-    p1[2] = DIFF ? exp(__ldg(S.lp1 + 2 * S.M + j)) : 0.0;
+    p1[0] = rc_post(__ldg(S.lp1 + j), S.lin);
+    p1[1] = rc_post(__ldg(S.lp1 + S.M + j), S.lin);
+    p1[2] = DIFF ? rc_post(__ldg(S.lp1 + 2 * S.M + j), S.lin) : 0.0;
 }
 template <bool DIFF> __device__ __forceinline__ double rc_weight(const RCSrc &S, const double (&p1)[3], int c, int64_t j) {
     if (!DIFF) return c == 0 ? p1[0] : p1[1];
@@ -287,9 +288,9 @@ template <int CM> struct RCRaw {
 template <bool DIFF, int CM>
 __device__ __forceinline__ void rc_load_raw(const RCSrc &S, const int32_t *__restrict__ group, int64_t j, int C, RCRaw<CM> &w) {
     const bool valid = j < S.M;
-    w.lp[0] = valid ? __ldg(S.lp1 + j) : 1.0;  // exp(1) > 1 >= p: never flagged, never added (valid is re-checked)
-    w.lp[1] = valid ? __ldg(S.lp1 + S.M + j) : 1.0;
-    w.lp[2] = (DIFF && valid) ? __ldg(S.lp1 + 2 * S.M + j) : 1.0;
+    w.lp[0] = valid ? __ldg(S.lp1 + j) : 2.0;  // 2 and exp(2) > 1 >= p: never flagged, never added (valid is re-checked)
+    w.lp[1] = valid ? __ldg(S.lp1 + S.M + j) : 2.0;
+    w.lp[2] = (DIFF && valid) ? __ldg(S.lp1 + 2 * S.M + j) : 2.0;
     w.g0 = (!DIFF && valid) ? __ldg(group + j) : 0;
     if (DIFF) {
 #pragma unroll
@@ -342,9 +343,9 @@ __global__ void __launch_bounds__(RC_NT, CMAX == 0 ? 1 : (CMAX <= 2 ? 4 : 3))
                 // the next strip's loads go out before this strip's arithmetic
                 rc_load_raw<DIFF, CM>(S, group, (r + 1 < RC_STRIPS) ? j + 32 : S.M, C, nxt);
                 double p1[3], x[CM];
-                p1[0] = exp(cur.lp[0]);
-                p1[1] = exp(cur.lp[1]);
-                p1[2] = DIFF ? exp(cur.lp[2]) : 0.0;
+                p1[0] = rc_post(cur.lp[0], S.lin);
+                p1[1] = rc_post(cur.lp[1], S.lin);
+                p1[2] = DIFF ? rc_post(cur.lp[2], S.lin) : 0.0;
 #pragma unroll
                 for (int c = 0; c < CM; c++) {
                     if (!DIFF) x[c] = c == 0 ? p1[0] : p1[1];
@@ -850,8 +851,9 @@ int rc_finalize(ehmm_session *s) {
 }
 
 static RCSrc rc_source(ehmm_session *s, int differential) {
-    if (differential) return RCSrc{s->logProb1.as<double>(), s->eta.as<double>(), s->M, s->B, s->B + 2};
-    return RCSrc{s->logProb1.as<double>(), nullptr, s->M, 0, s->K};
+    const P1Src ps = p1_source(s);
+    if (differential) return RCSrc{ps.p, s->eta.as<double>(), s->M, s->B, s->B + 2, ps.lin};
+    return RCSrc{ps.p, nullptr, s->M, 0, s->K, ps.lin};
 }
 
 // Differential model, right after an E-step: the part of the rejection tables that the coming inner
@@ -860,7 +862,7 @@ static RCSrc rc_source(ehmm_session *s, int differential) {
 // maxStepProb and the first innerExpStep.
 int rc_static_prefetch(ehmm_session *s) {
     const double p = s->rc_hint_p;
-    if (!(s->K == 3 && s->B > 0 && s->G > 0 && s->group.p && s->N > 0 && p >= RC_EXACT_MIN_P && p <= 1.0 && has(s, DS_P1)))
+    if (!(s->K == 3 && s->B > 0 && s->G > 0 && s->group.p && s->N > 0 && p >= RC_EXACT_MIN_P && p <= 1.0 && has_post(s)))
         return EHMM_OK;
     if (s->rc_static_gen == s->lp1_gen && s->rc_static_p == p) return EHMM_OK;
     EHMM_CK(cudaEventRecord(s->ev2, s->stream));

@@ -27,6 +27,9 @@ __device__ __forceinline__ double rc_div_cut(double x, double p, double rp) {
     return __fma_rn(r, rp, q);
 }
 
+// posterior from where the session keeps it: P1 itself (lin, written by the lean E-step) or logProb1
+__device__ __forceinline__ double rc_post(double stored, int lin) { return lin ? stored : exp(stored); }
+
 // weight of mixture component b in the differential model: P1[j,1] * eta[j,b]
 // (src/differentialRejectionControlled.cpp:38-41)
 __device__ __forceinline__ double rc_mix_weight(double p1_diff, double eta_b) { return __dmul_rn(p1_diff, eta_b); }

@@ -158,13 +158,27 @@ int set_theta(ehmm_session *s, const double *pi, const double *gamma) {
 
 int upload_logf(ehmm_session *s, const double *logf, const double **d_out) {
     if (logf) {
-        EHMM_TRY(s->logf.reserve(sizeof(double) * s->M * s->K));
+        EHMM_TRY(logf_for_write(s, sizeof(double) * s->M * s->K));
         EHMM_CK(cudaMemcpyAsync(s->logf.p, logf, sizeof(double) * s->M * s->K, cudaMemcpyHostToDevice, s->stream));
         s->valid |= DS_LOGF;
     }
     EHMM_REQUIRE(has(s, DS_LOGF), EHMM_ERR_STATE, "expStep: no logf given and no emission has been computed");
     *d_out = s->logf.as<double>();
     return EHMM_OK;
+}
+
+// bookkeeping behind every E-step: which datasets exist now, what may be reused downstream
+int estep_done(ehmm_session *s) {
+    if (s->lazy_full) s->valid = (s->valid & ~(unsigned)DS_ESTEP) | DS_P1LIN;   // lean: P1 only, the rest on demand
+    else s->valid = (s->valid | DS_ESTEP) & ~(unsigned)DS_P1LIN;
+    s->stats_stale = false;
+    posteriors_changed(s);
+    if (s->lazy_full && s->fb_counted) {  // the kernel counted the weights below the announced cut on the way
+        s->rc_counts_gen = s->post_gen;
+        s->rc_counts_p = s->rc_hint_p;
+        s->rc_counts_cols = s->K;
+    }
+    return rc_static_prefetch(s);
 }
 
 }  // namespace
@@ -251,7 +265,7 @@ int ehmm_session_close(ehmm_session *s) {
         if (it != g_sessions.end() && it->second == s) g_sessions.erase(it);
     }
     DevBuf *bufs[] = {&s->counts_own, &s->offsets_own, &s->controls_own, &s->group, &s->u_chip, &s->u_off, &s->u_ctrl,
-                      &s->u_dsg, &s->logf, &s->logFP, &s->logBP, &s->logProb1, &s->logProb2, &s->eta, &s->viterbi, &s->vit_bp, &s->vit_work,
+                      &s->u_dsg, &s->logf, &s->logFP, &s->logBP, &s->logProb1, &s->logProb2, &s->prob1, &s->logf_alt, &s->eta, &s->viterbi, &s->vit_bp, &s->vit_work,
                       &s->tileops, &s->carries, &s->tilestats, &s->fbscal, &s->rangeops, &s->rangecarry, &s->rc_flag, &s->rc_scan,
                       &s->rc_buckets, &s->rc_limbs, &s->rc_coltot, &s->rc_static, &s->rc_unif, &s->rc_unif_spec, &s->rc_tmp, &s->mt_raw, &s->mt_raw2, &s->mt_windows, &s->gtab, &s->glm_ticket, &s->inner_part, &s->lgtab, &s->glm_part, &s->misc};
     for (DevBuf *b : bufs) b->release();
@@ -593,21 +607,20 @@ int ehmm_expstep(ehmm_session *s, const double *pi, const double *gamma, const d
     const double *d_logf = nullptr;
     EHMM_TRY(upload_logf(s, logf, &d_logf));
     EHMM_TRY(fb_expstep(s, d_logf));
-    s->valid |= DS_ESTEP;
-    s->stats_stale = false;
-    posteriors_changed(s);
-    return rc_static_prefetch(s);
+    return estep_done(s);
 }
 
 int ehmm_expstep_device(ehmm_session *s, const double *pi, const double *gamma, const double *logf_device) {
     EHMM_TRY(check_session(s));
     EHMM_TRY(set_theta(s, pi, gamma));
     EHMM_REQUIRE(logf_device, EHMM_ERR_ARG, "null logf");
-    EHMM_TRY(fb_expstep(s, logf_device));
-    s->valid |= DS_ESTEP;
-    s->stats_stale = false;
-    posteriors_changed(s);
-    return rc_static_prefetch(s);
+    // the caller owns this emission: nothing can be owed against it, so the datasets are written at once
+    const bool lean = s->lean_mode;
+    s->lean_mode = false;
+    const int rc = fb_expstep(s, logf_device);
+    s->lean_mode = lean;
+    EHMM_TRY(rc);
+    return estep_done(s);
 }
 
 int ehmm_expstep_reduce(ehmm_session *s, const double *pi, const double *gamma, const double *logf, double *op) {
@@ -627,10 +640,7 @@ int ehmm_expstep_apply(ehmm_session *s, const double *fwd_carry, const double *b
     EHMM_REQUIRE(fwd_carry && bwd_carry, EHMM_ERR_ARG, "null carry");
     EHMM_TRY(fb_apply(s, fwd_carry, bwd_carry, fwd_out));
     s->reduce_pending = false;
-    s->valid |= DS_ESTEP;
-    s->stats_stale = false;
-    posteriors_changed(s);
-    return rc_static_prefetch(s);
+    return estep_done(s);
 }
 
 namespace {
@@ -684,15 +694,12 @@ int ehmm_expstep_apply_ops(ehmm_session *s, const double *ops_all, int P, int ra
     }
     EHMM_TRY(fb_apply(s, fwd, bwd, nullptr));
     s->reduce_pending = false;
-    s->valid |= DS_ESTEP;
-    s->stats_stale = false;
-    posteriors_changed(s);
-    return rc_static_prefetch(s);
+    return estep_done(s);
 }
 
 int ehmm_estep_stats(ehmm_session *s, double *stats) {
     EHMM_TRY(check_session(s));
-    EHMM_REQUIRE(has(s, DS_P1 | DS_P2) && stats, EHMM_ERR_STATE, "estep_stats: expStep has not run");
+    EHMM_REQUIRE(avail(s, DS_P1 | DS_P2) && stats, EHMM_ERR_STATE, "estep_stats: expStep has not run");
     EHMM_TRY(fb_fetch_stats(s));
     for (int i = 0; i < s->K * s->K + 1; i++) stats[i] = s->h_stats[i];
     return EHMM_OK;
@@ -700,7 +707,7 @@ int ehmm_estep_stats(ehmm_session *s, double *stats) {
 
 int ehmm_estep_row0(ehmm_session *s, double *row0) {
     EHMM_TRY(check_session(s));
-    EHMM_REQUIRE(has(s, DS_P1) && row0, EHMM_ERR_STATE, "estep_row0: expStep has not run");
+    EHMM_REQUIRE(avail(s, DS_P1) && row0, EHMM_ERR_STATE, "estep_row0: expStep has not run");
     EHMM_TRY(fb_fetch_stats(s));
     for (int k = 0; k < s->K; k++) row0[k] = s->h_lp1_row0[k];
     return EHMM_OK;
@@ -718,7 +725,7 @@ int ehmm_estep_set_stats(ehmm_session *s, const double *stats, const double *log
 
 int ehmm_loglik_value(ehmm_session *s, double *ll) {
     EHMM_TRY(check_session(s));
-    EHMM_REQUIRE(has(s, DS_FP) && ll, EHMM_ERR_STATE, "loglik: expStep has not run");
+    EHMM_REQUIRE(avail(s, DS_FP) && ll, EHMM_ERR_STATE, "loglik: expStep has not run");
     EHMM_TRY(fb_fetch_stats(s));
     *ll = s->h_ll;
     return EHMM_OK;
@@ -728,7 +735,7 @@ int ehmm_loglik_value(ehmm_session *s, double *ll) {
 // the E-step kernel; only the K*K divisions, the 1e-6 floor and the renormalisation run here.
 int ehmm_maxstepprob(ehmm_session *s, double *pi_out, double *gamma_out) {
     EHMM_TRY(check_session(s));
-    EHMM_REQUIRE(has(s, DS_P1 | DS_P2), EHMM_ERR_STATE, "maxStepProb: expStep has not run for '%s'", s->key.c_str());
+    EHMM_REQUIRE(avail(s, DS_P1 | DS_P2), EHMM_ERR_STATE, "maxStepProb: expStep has not run for '%s'", s->key.c_str());
     EHMM_REQUIRE(pi_out && gamma_out, EHMM_ERR_ARG, "null output");
     EHMM_TRY(fb_fetch_stats(s));
     const int K = s->K;
@@ -763,7 +770,7 @@ int ehmm_maxstepprob(ehmm_session *s, double *pi_out, double *gamma_out) {
 // computeQFunction (src/computeQFunction.cpp:30)
 int ehmm_qfunction(ehmm_session *s, const double *pi, const double *gamma, double *q) {
     EHMM_TRY(check_session(s));
-    EHMM_REQUIRE(has(s, DS_LOGF | DS_P1 | DS_P2), EHMM_ERR_STATE, "computeQFunction: expStep has not run");
+    EHMM_REQUIRE(avail(s, DS_LOGF | DS_P1 | DS_P2), EHMM_ERR_STATE, "computeQFunction: expStep has not run");
     EHMM_REQUIRE(pi && gamma && q, EHMM_ERR_ARG, "null pointer");
     EHMM_TRY(fb_fetch_stats(s));
     const int K = s->K;
@@ -778,7 +785,7 @@ int ehmm_qfunction(ehmm_session *s, const double *pi, const double *gamma, doubl
 // computeBIC (src/computeBIC.cpp:23-26)
 int ehmm_bic(ehmm_session *s, int numPar, int numSamples, double *bic) {
     EHMM_TRY(check_session(s));
-    EHMM_REQUIRE(has(s, DS_FP) && bic, EHMM_ERR_STATE, "computeBIC: expStep has not run");
+    EHMM_REQUIRE(avail(s, DS_FP) && bic, EHMM_ERR_STATE, "computeBIC: expStep has not run");
     EHMM_TRY(fb_fetch_stats(s));
     *bic = -2 * s->h_ll + numPar * log((double)((int64_t)numSamples * s->Mtot));
     return EHMM_OK;
@@ -792,7 +799,8 @@ int ehmm_inner_maxstepprob(ehmm_session *s, double *delta_out) {
 
 int ehmm_marginal_probability(ehmm_session *s, double *out) {
     EHMM_TRY(check_session(s));
-    EHMM_REQUIRE(has(s, DS_P1) && out, EHMM_ERR_STATE, "getMarginalProbability: expStep has not run");
+    EHMM_REQUIRE(avail(s, DS_P1) && out, EHMM_ERR_STATE, "getMarginalProbability: expStep has not run");
+    EHMM_TRY(ensure(s, DS_P1));  // exp(logProb1), the reference's expression, not the linear copy
     const int64_t n = s->M * s->K;
     EHMM_TRY(s->rc_tmp.reserve(sizeof(double) * n));
     PROF(s, KID_MISC), exp_kernel<<<148 * 8, 256, 0, s->stream>>>(s->logProb1.as<double>(), n, s->rc_tmp.as<double>());
@@ -804,21 +812,34 @@ int ehmm_marginal_probability(ehmm_session *s, double *out) {
 
 int ehmm_viterbi(ehmm_session *s, const double *pi, const double *gamma, double *states_out) {
     EHMM_TRY(check_session(s));
-    EHMM_REQUIRE(has(s, DS_FP), EHMM_ERR_STATE, "computeViterbiSequence: no logFP dataset (expStep has not run)");
+    EHMM_REQUIRE(avail(s, DS_FP), EHMM_ERR_STATE, "computeViterbiSequence: no logFP dataset (expStep has not run)");
     EHMM_REQUIRE(pi && gamma, EHMM_ERR_ARG, "null pointer");
+    EHMM_TRY(ensure(s, DS_FP));
     return viterbi(s, pi, gamma, states_out);
 }
 
 int ehmm_viterbi_forward(ehmm_session *s, const double *pi, const double *gamma, const double *v_in, double *v_out) {
     EHMM_TRY(check_session(s));
-    EHMM_REQUIRE(has(s, DS_FP), EHMM_ERR_STATE, "computeViterbiSequence: no logFP dataset (expStep has not run)");
+    EHMM_REQUIRE(avail(s, DS_FP), EHMM_ERR_STATE, "computeViterbiSequence: no logFP dataset (expStep has not run)");
     EHMM_REQUIRE(pi && gamma && v_out, EHMM_ERR_ARG, "null pointer");
+    EHMM_TRY(ensure(s, DS_FP));
     return viterbi_forward(s, pi, gamma, v_in, v_out);
 }
 
 int ehmm_viterbi_backtrace(ehmm_session *s, int state_last, int *state_prev, double *states_out) {
     EHMM_TRY(check_session(s));
     return viterbi_backtrace(s, state_last, state_prev, states_out);
+}
+
+int ehmm_expstep_mode(ehmm_session *s, int lean) {
+    EHMM_REQUIRE(s && (lean == 0 || lean == 1), EHMM_ERR_ARG, "expstep_mode: 0 (all datasets at once) or 1 (EM-internal)");
+    s->lean_mode = lean != 0;
+    return EHMM_OK;
+}
+
+int ehmm_materialize(ehmm_session *s) {
+    EHMM_TRY(check_session(s));
+    return fb_materialize(s);
 }
 
 int ehmm_viterbi_mode(ehmm_session *s, int mode) {
@@ -853,7 +874,7 @@ int ehmm_rng_get_state(ehmm_session *s, uint32_t *state625) {
 
 int ehmm_rc_consensus(ehmm_session *s, double p, const double *uniforms, int64_t n_uniforms, int64_t *consumed) {
     EHMM_TRY(check_session(s));
-    EHMM_REQUIRE(has(s, DS_P1), EHMM_ERR_STATE, "consensusRejectionControlled: expStep has not run");
+    EHMM_REQUIRE(has_post(s), EHMM_ERR_STATE, "consensusRejectionControlled: expStep has not run");
     EHMM_REQUIRE(s->G > 0, EHMM_ERR_STATE, "consensusRejectionControlled: ehmm_set_groups has not been called");
     EHMM_REQUIRE(p >= 0.0 && p <= 1.0, EHMM_ERR_ARG, "the rejection cut p = %g is not a probability", p);
     return rc_consensus(s, p, uniforms, n_uniforms, consumed);
@@ -861,7 +882,7 @@ int ehmm_rc_consensus(ehmm_session *s, double p, const double *uniforms, int64_t
 
 int ehmm_rc_differential(ehmm_session *s, double p, int N, const double *uniforms, int64_t n_uniforms, int64_t *consumed) {
     EHMM_TRY(check_session(s));
-    EHMM_REQUIRE(has(s, DS_P1 | DS_ETA), EHMM_ERR_STATE, "differentialRejectionControlled: needs logProb1 and mixtureProb");
+    EHMM_REQUIRE(has_post(s) && has(s, DS_ETA), EHMM_ERR_STATE, "differentialRejectionControlled: needs logProb1 and mixtureProb");
     EHMM_REQUIRE(s->G > 0, EHMM_ERR_STATE, "differentialRejectionControlled: ehmm_set_groups has not been called");
     EHMM_REQUIRE(p >= 0.0 && p <= 1.0, EHMM_ERR_ARG, "the rejection cut p = %g is not a probability", p);
     EHMM_REQUIRE(N == s->N, EHMM_ERR_ARG, "N=%d does not match the data (N=%d)", N, s->N);
@@ -871,7 +892,7 @@ int ehmm_rc_differential(ehmm_session *s, double p, int N, const double *uniform
 int ehmm_rc_count(ehmm_session *s, int differential, double p, int64_t *counts) {
     EHMM_TRY(check_session(s));
     EHMM_REQUIRE(counts, EHMM_ERR_ARG, "null pointer");
-    EHMM_REQUIRE(has(s, differential ? (DS_P1 | DS_ETA) : DS_P1), EHMM_ERR_STATE, "rc_count: posteriors not available");
+    EHMM_REQUIRE(has_post(s) && (!differential || has(s, DS_ETA)), EHMM_ERR_STATE, "rc_count: posteriors not available");
     EHMM_REQUIRE(s->G > 0, EHMM_ERR_STATE, "rc_count: ehmm_set_groups has not been called");
     EHMM_REQUIRE(p >= 0.0 && p <= 1.0, EHMM_ERR_ARG, "the rejection cut p = %g is not a probability", p);
     return rc_count(s, differential, p, counts);
@@ -1021,7 +1042,7 @@ int ehmm_dataset_dims(ehmm_session *s, const char *name, int64_t *rows, int64_t 
     EHMM_REQUIRE(s && name && rows && cols, EHMM_ERR_ARG, "null pointer");
     DS d;
     EHMM_TRY(lookup(s, name, d));
-    EHMM_REQUIRE(has(s, d.bit), EHMM_ERR_STATE, "dataset '%s' has not been written", name);
+    EHMM_REQUIRE(avail(s, d.bit), EHMM_ERR_STATE, "dataset '%s' has not been written", name);
     *rows = d.rows;
     *cols = d.cols;
     return EHMM_OK;
@@ -1032,7 +1053,8 @@ int ehmm_fetch(ehmm_session *s, const char *name, double *dst, int64_t n) {
     EHMM_REQUIRE(name && dst, EHMM_ERR_ARG, "null pointer");
     DS d;
     EHMM_TRY(lookup(s, name, d));
-    EHMM_REQUIRE(has(s, d.bit), EHMM_ERR_STATE, "dataset '%s' has not been written", name);
+    EHMM_REQUIRE(avail(s, d.bit), EHMM_ERR_STATE, "dataset '%s' has not been written", name);
+    EHMM_TRY(ensure(s, d.bit));
     EHMM_REQUIRE(n == d.rows * d.cols, EHMM_ERR_ARG, "dataset '%s' has %lld elements, buffer has %lld", name,
                  (long long)(d.rows * d.cols), (long long)n);
     EHMM_CK(cudaMemcpyAsync(dst, d.buf->p, sizeof(double) * n, cudaMemcpyDeviceToHost, s->stream));
@@ -1044,7 +1066,9 @@ int ehmm_device_ptr(ehmm_session *s, const char *name, void **ptr) {
     EHMM_REQUIRE(s && name && ptr, EHMM_ERR_ARG, "null pointer");
     DS d;
     EHMM_TRY(lookup(s, name, d));
-    EHMM_REQUIRE(has(s, d.bit), EHMM_ERR_STATE, "dataset '%s' has not been written", name);
+    EHMM_REQUIRE(avail(s, d.bit), EHMM_ERR_STATE, "dataset '%s' has not been written", name);
+    EHMM_TRY(check_session(s));
+    EHMM_TRY(ensure(s, d.bit));
     *ptr = d.buf->p;
     return EHMM_OK;
 }
@@ -1057,7 +1081,11 @@ int ehmm_store(ehmm_session *s, const char *name, const double *src, int64_t row
     EHMM_TRY(lookup(s, name, d));
     EHMM_REQUIRE(rows == d.rows && cols == d.cols, EHMM_ERR_ARG, "dataset '%s' must be %lld x %lld (got %lld x %lld)", name,
                  (long long)d.rows, (long long)d.cols, (long long)rows, (long long)cols);
-    EHMM_TRY(d.buf->reserve(sizeof(double) * rows * cols));
+    // a dataset of the last E-step is about to be replaced: the others must exist as that E-step left them
+    if (d.bit & DS_ESTEP) EHMM_TRY(ensure(s, DS_ESTEP));
+    if (d.bit == DS_LOGF) EHMM_TRY(logf_for_write(s, sizeof(double) * rows * cols));
+    else EHMM_TRY(d.buf->reserve(sizeof(double) * rows * cols));
+    if (d.bit & DS_ESTEP) { s->lazy_full = false; s->valid &= ~(unsigned)DS_P1LIN; }
     EHMM_CK(cudaMemcpyAsync(d.buf->p, src, sizeof(double) * rows * cols, cudaMemcpyHostToDevice, s->stream));
     EHMM_CK(cudaStreamSynchronize(s->stream));
     s->valid |= d.bit;

@@ -356,6 +356,13 @@ def _hint(backend, p):
         backend.rc_hint(p)
 
 
+def _lean(backend, on):
+    """inside the EM loops nothing reads logFP, logBP or logProb2 (R/base-EM.R:113-158, 191-225): the E-steps there
+    write the posteriors and the statistics only; the datasets of the last E-step appear when they are asked for"""
+    if hasattr(backend, "expstep_mode"):
+        backend.expstep_mode(on)
+
+
 def _update_hist(controlHist, parHist, theta_new, control, init_time, bic, q, conv):
     cur = controlHist[-1]
     parHist.append(copy.deepcopy(theta_new))
@@ -384,6 +391,7 @@ def emConsensus(theta_old, backend, N, control, dist="nb", callback=None):
     theta_old = copy.deepcopy(theta_old)
     theta_new = copy.deepcopy(theta_old)
     numPar = unlist(theta_old).size - 3
+    _lean(backend, True)
     t0 = time.time()
     while _continue(controlHist, control):
         cur = controlHist[-1]
@@ -402,6 +410,7 @@ def emConsensus(theta_old, backend, N, control, dist="nb", callback=None):
         theta_old = copy.deepcopy(theta_new)
         if callback:
             callback(controlHist[-2], theta_new)
+    _lean(backend, False)
     return dict(theta_new=theta_new, controlHist=controlHist, parHist=parHist)
 
 
@@ -411,6 +420,7 @@ def emInitialization(theta_old, backend, control, callback=None):
     theta_old = copy.deepcopy(theta_old)
     theta_new = copy.deepcopy(theta_old)
     numPar = unlist(theta_old).size - 3
+    _lean(backend, True)
     t0 = time.time()
     while _continue(controlHist, control):
         cur = controlHist[-1]
@@ -430,6 +440,7 @@ def emInitialization(theta_old, backend, control, callback=None):
         theta_old = copy.deepcopy(theta_new)
         if callback:
             callback(controlHist[-2], theta_new)
+    _lean(backend, False)
     return dict(theta_new=theta_new, controlHist=controlHist, parHist=parHist)
 
 
@@ -468,6 +479,7 @@ def outerEMDifferential(theta_old, backend, N, control, dist="nb", callback=None
     theta_new = copy.deepcopy(theta_old)
     npat = len(control["pattern"]) if control.get("pattern") else 0
     numPar = unlist(theta_old).size - npat - 3
+    _lean(backend, True)
     t0 = time.time()
     while _continue(controlHist, control):
         cur = controlHist[-1]
@@ -486,6 +498,7 @@ def outerEMDifferential(theta_old, backend, N, control, dist="nb", callback=None
         theta_old = copy.deepcopy(theta_new)
         if callback:
             callback(controlHist[-2], theta_new)
+    _lean(backend, False)
     return dict(theta_new=theta_new, controlHist=controlHist, parHist=parHist)
 
 

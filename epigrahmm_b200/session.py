@@ -284,6 +284,14 @@ class Session:
         check(lib.ehmm_viterbi(self._h, dptr(_f64(pi)), dptr(_cm(gamma)), dptr(out)))
         return out
 
+    def expstep_mode(self, lean):
+        """1: E-steps inside an EM loop write the posteriors and the statistics only; logFP / logBP / logProb1 /
+        logProb2 of the last E-step are produced when somebody asks for them.  0: the reference's contract."""
+        check(lib.ehmm_expstep_mode(self._h, int(bool(lean))))
+
+    def materialize(self):
+        check(lib.ehmm_materialize(self._h))
+
     def viterbi_mode(self, mode):
         """0: parallel scan (default), 1: the sequential kernel; the states are bit-identical"""
         check(lib.ehmm_viterbi_mode(self._h, int(mode)))

@@ -148,6 +148,15 @@ int ehmm_inner_maxstepprob(ehmm_session *s, double *delta_out);
 int ehmm_inner_mstep_sums(ehmm_session *s, double *sums);
 /* getMarginalProbability, src/getMarginalProbability.cpp:12-21 (out: M x K). */
 int ehmm_marginal_probability(ehmm_session *s, double *out);
+/* How expStep delivers its results.  lean = 0 (default): the reference's contract -- logFP, logBP, logProb1
+ * and logProb2 are written by the E-step (src/expStep.cpp:116-122).  lean = 1, for E-steps inside the EM
+ * loop: only the posteriors P1 and the sufficient statistics are produced (nothing in R/base-EM.R:113-158,
+ * 191-225 reads more: maxStepProb, Q and BIC use the statistics, the rejection control and innerMaxStepProb
+ * use exp(logProb1)); the four datasets of the LAST E-step are produced on demand -- by ehmm_fetch,
+ * ehmm_device_ptr, ehmm_store, ehmm_viterbi*, ehmm_marginal_probability or ehmm_materialize -- by the same
+ * kernel on the same inputs, so they hold the same bits as with lean = 0. */
+int ehmm_expstep_mode(ehmm_session *s, int lean);
+int ehmm_materialize(ehmm_session *s);
 /* computeViterbiSequence, src/computeViterbiSequence.cpp:12-54 (states_out: M doubles or NULL). */
 int ehmm_viterbi(ehmm_session *s, const double *pi, const double *gamma, double *states_out);
 /* How the (max,+) recursion is run.  mode 0 (default): parallel scan -- inside one binade of LOGV the

@@ -306,3 +306,106 @@ def test_dictionary_encoded_upload(ehmm, model):
             b.inner_expstep(delta, psi, MINZERO)
             assert np.array_equal(a.fetch("logLikelihood"), b.fetch("logLikelihood"))
             assert np.array_equal(a.fetch("mixtureProb"), b.fetch("mixtureProb"))
+
+
+# ---- the EM-internal form of the E-step (ehmm_expstep_mode) ---------------------------------------
+
+def _lean_logf(K, M, seed):
+    rng = np.random.default_rng(seed)
+    z = synth.markov_chain(M, synth.GAMMA2 if K == 2 else synth.GAMMA3, rng)
+    logf = rng.normal(-6.0, 2.0, (M, K))
+    logf[np.arange(M), z] += 5.0
+    for j in (0, 5, 100, 959, 960, 1279, 1280, 1500, M - 1):   # emissions that underflow exp()
+        if j < M:
+            logf[j, 1] = -900.0
+    if M > 2000:
+        logf[2000, 0] = -1500.0
+    return logf
+
+
+@pytest.mark.parametrize("K", [2, 3])
+@pytest.mark.parametrize("M", [1, 2, 959, 1281, 7000, 100003])
+def test_lean_expstep_owes_the_same_datasets(ehmm, oracle, K, M):
+    """mode 1 writes P1 and the statistics only; what it produces on demand holds the bits of a mode-0 E-step,
+    and everything the EM loop derives from it (pi, gamma, Q, BIC, log-likelihood) is the same number"""
+    logf = _lean_logf(K, M, 50 * K + M)
+    pi, gamma = _theta(K)
+    with ehmm.Session("t_full", M, K) as s:
+        s.expstep(pi, gamma, logf)
+        full = s.datasets()
+        ref = (s.maxstepprob() if M >= 2 else None, s.qfunction(pi, gamma), s.bic(5, 2), s.loglik())
+    with ehmm.Session("t_lean", M, K) as s:
+        s.expstep_mode(1)
+        s.expstep(pi, gamma, logf)
+        got = (s.maxstepprob() if M >= 2 else None, s.qfunction(pi, gamma), s.bic(5, 2), s.loglik())
+        lean = s.datasets()
+    for n in ("logLikelihood", "logFP", "logBP", "logProb1", "logProb2"):
+        assert np.array_equal(full[n], lean[n]), n
+    assert got[1:] == ref[1:]
+    if M >= 2:
+        assert np.array_equal(got[0]["pi"], ref[0]["pi"]) and np.array_equal(got[0]["gamma"], ref[0]["gamma"], equal_nan=True)
+
+
+def test_lean_expstep_survives_the_next_emission(ehmm, oracle):
+    """the datasets are those of the LAST E-step even when a new emission has been computed since (the
+    reference's file still holds the old E-step at that point)"""
+    M, N = 30011, 3
+    d = synth.make_consensus(M, N, seed=11)
+    th = synth.THETA_CONSENSUS
+    psi2 = [th["psi"][0] * np.array([1.1, 0.9]), th["psi"][1] * np.array([0.95, 1.2])]
+    with ehmm.Session("t_keep", M, 2) as s:
+        s.set_data(d["counts"], d["offsets"])
+        s.loglik_consensus(th["psi"], MINZERO)
+        s.expstep(th["pi"], th["gamma"])
+        want = s.datasets()
+        s.expstep_mode(1)
+        s.loglik_consensus(th["psi"], MINZERO)
+        s.expstep(th["pi"], th["gamma"])
+        s.loglik_consensus(psi2, MINZERO)          # the next iteration's emission
+        newer = s.fetch("logLikelihood")
+        got = s.datasets()
+        assert np.array_equal(got["logLikelihood"], newer) and not np.array_equal(newer, want["logLikelihood"])
+        for n in ("logFP", "logBP", "logProb1", "logProb2"):
+            assert np.array_equal(got[n], want[n]), n
+        # and the E-step after that one runs on the new emission
+        s.expstep(th["pi"], th["gamma"])
+        h = oracle.expStep(th["pi"], th["gamma"], newer)
+        assert np.max(np.abs(np.exp(s.fetch("logProb1")) - np.exp(h["logProb1"]))) <= 1e-8
+
+
+@pytest.mark.parametrize("p", [0.9, 0.05])
+def test_lean_expstep_feeds_the_rejection_control(ehmm, oracle, p):
+    """K = 2: the lean kernel counts the weights below the announced cut itself and the rejection control thins
+    the linear posteriors; support, draw count and sums as from the oracle's posteriors"""
+    M, N = 40009, 3
+    d = synth.make_consensus(M, N, seed=3)
+    g = synth.make_groups(d["counts"], d["offsets"])
+    th = synth.THETA_CONSENSUS
+    u = oracle.RNG.set_seed(5).runif(2 * M)
+    logf = oracle.loglikConsensusHMM(d["counts"], d["offsets"], th["psi"], MINZERO)
+    h = oracle.expStep(th["pi"], th["gamma"], logf)
+    # bins whose posterior underflows: exp(logProb1) == 0 draws nothing, a subnormal does
+    ref, n_ref = oracle.consensusRejectionControlled(h, g["group"], p, uniforms=u, dense=True)
+    with ehmm.Session("t_lean_rc", M, 2) as s:
+        s.set_data(d["counts"], d["offsets"])
+        s.set_groups(g["group"], g["u_chip"], g["u_offsets"])
+        s.expstep_mode(1)
+        s.rc_hint(p)
+        s.loglik_consensus(th["psi"], MINZERO)
+        s.profile(True)
+        s.expstep(th["pi"], th["gamma"])
+        n = s.rc_consensus(p, uniforms=u)
+        prof = s.profile_read()
+        s.profile(False)
+        assert prof["fb_apply_em"][0] == 1 and prof["fb_apply"][0] == 0 and prof["rc_count"][0] == 0
+        assert n == n_ref
+        for c in range(2):
+            got = s.rc_buckets(c)
+            assert np.array_equal(got != 0, ref[c] != 0)
+            # (the oracle's own posteriors carry ulp(|logLik|) of noise: 1e-9 as in the trajectory gates)
+            assert np.max(np.abs(got - ref[c]) / np.maximum(np.abs(ref[c]), 1e-300)) <= 1e-9
+        # a cut that was not announced: the counting kernel runs after all
+        s.profile(True)
+        s.rc_consensus(0.5 * p, uniforms=u)
+        assert s.profile_read()["rc_count"][0] == 1
+        s.profile(False)
