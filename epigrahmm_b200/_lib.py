@@ -77,6 +77,12 @@ PROTOTYPES = {
     "ehmm_inner_maxstepprob": [_sess, _dp],
     "ehmm_marginal_probability": [_sess, _dp],
     "ehmm_viterbi": [_sess, _dp, _dp, _dp],
+    "ehmm_call_peaks": [_sess, C.c_double, _bp, _lp, _dp],
+    "ehmm_call_peaks_viterbi": [_sess, _bp, _lp],
+    "ehmm_call_peaks_exact": [_sess, C.c_int],
+    "ehmm_call_peaks_path": [_sess, C.POINTER(C.c_int)],
+    "ehmm_peak_runs": [_sess, _lp, C.c_int, C.c_int64, _lp, _lp, _lp],
+    "ehmm_flush": [_sess, _dp, _dp, _dp, _dp, _dp, _dp, _dp],
     "ehmm_expstep_mode": [_sess, C.c_int],
     "ehmm_materialize": [_sess],
     "ehmm_viterbi_mode": [_sess, C.c_int],

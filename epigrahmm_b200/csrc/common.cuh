@@ -71,13 +71,13 @@ enum KernelId : int {
     KID_EMIS_TAB, KID_EMIS_GATHER, KID_EMIS_CONSENSUS, KID_EMIS_DIFF, KID_EMIS_INNER, KID_INNER_MSTEP,
     KID_FB_REDUCE, KID_FB_CARRY, KID_FB_APPLY, KID_FB_APPLY_LEAN, KID_FB_FIX, KID_FB_STATS,
     KID_RC_COUNT, KID_RC_SCAN, KID_MT, KID_RC_APPLY, KID_RC_STATIC, KID_RC_FINAL, KID_GLM, KID_GLM_FINAL,
-    KID_VIT_FWD, KID_VIT_BWD, KID_MISC, KID_COUNT
+    KID_VIT_FWD, KID_VIT_BWD, KID_PEAKS, KID_MISC, KID_COUNT
 };
 static const char *const kKernelNames[KID_COUNT] = {
     "emis_tables", "emis_gather", "emis_consensus", "emis_diff_hmm", "emis_inner", "inner_mstep",
     "fb_reduce", "fb_carry", "fb_apply", "fb_apply_em", "fb_boundary_fix", "fb_stats",
     "rc_count", "rc_scan", "mt_generate", "rc_apply", "rc_static", "rc_finalize", "glm", "glm_final",
-    "viterbi_forward", "viterbi_backtrace", "misc"};
+    "viterbi_forward", "viterbi_backtrace", "call_peaks", "misc"};
 
 // forward-backward tiling (fb.cu)
 constexpr int FB_MAX_STATS = EHMM_MAX_K * EHMM_MAX_K + 1;
@@ -134,6 +134,11 @@ struct ehmm_session {
     const double *estep_logf = nullptr;          // emission the last E-step ran on
     double estep_cin[2][EHMM_MAX_K + 1] = {{0}};  // ... and the vectors entering / leaving its block
     bool fb_counted = false;     // the last lean E-step (K = 2) counted the weights below rc_hint_p per warp tile
+    // ---- callPeaks ----
+    ehmm::DevBuf peak_work, peak_calls;  // sort buffers; the last calls (one byte per window)
+    bool peaks_exact = false;            // ehmm_call_peaks_exact: always add in emulated long double
+    int peaks_path = 0;                  // last fdr call: 0 fp64 prefix sum (certified), 1 emulated (forced), 2 emulated (margin too small)
+    bool peaks_valid = false;
     bool vit_forward_done = false;
     ehmm::DevBuf vit_work;       // tile sums, plan, look-back state and backtrace maps of the Viterbi scan
     int vit_mode = 0;            // 0: parallel scan (sequential kernel where the integer model does not hold), 1: sequential kernel
@@ -331,6 +336,10 @@ int glm_zinb(ehmm_session *s, int column, const double *par, int P, double minZe
 int glm_nb_batch(ehmm_session *s, int ncols, const int *columns, const double *pars, int P, double *values, double *grads);
 int glm_mix_nb(ehmm_session *s, const double *par, double minZero, double *value, double *grad);
 int glm_mix_zinb(ehmm_session *s, const double *par, double minZero, double *value, double *grad);
+// peaks.cu
+int call_peaks_fdr(ehmm_session *s, double fdr, uint8_t *calls_out, int64_t *n_called, double *cutoff);
+int call_peaks_viterbi(ehmm_session *s, uint8_t *calls_out, int64_t *n_called);
+int peak_runs(ehmm_session *s, const int64_t *breaks, int nbreaks, int64_t cap, int64_t *starts, int64_t *ends, int64_t *nruns);
 // viterbi.cu
 int viterbi(ehmm_session *s, const double *pi, const double *gamma, double *states_out);
 int viterbi_forward(ehmm_session *s, const double *pi, const double *gamma, const double *v_in, double *v_out);

@@ -265,7 +265,7 @@ int ehmm_session_close(ehmm_session *s) {
         if (it != g_sessions.end() && it->second == s) g_sessions.erase(it);
     }
     DevBuf *bufs[] = {&s->counts_own, &s->offsets_own, &s->controls_own, &s->group, &s->u_chip, &s->u_off, &s->u_ctrl,
-                      &s->u_dsg, &s->logf, &s->logFP, &s->logBP, &s->logProb1, &s->logProb2, &s->prob1, &s->logf_alt, &s->eta, &s->viterbi, &s->vit_bp, &s->vit_work,
+                      &s->u_dsg, &s->logf, &s->logFP, &s->logBP, &s->logProb1, &s->logProb2, &s->prob1, &s->logf_alt, &s->eta, &s->viterbi, &s->vit_bp, &s->vit_work, &s->peak_work, &s->peak_calls,
                       &s->tileops, &s->carries, &s->tilestats, &s->fbscal, &s->rangeops, &s->rangecarry, &s->rc_flag, &s->rc_scan,
                       &s->rc_buckets, &s->rc_limbs, &s->rc_coltot, &s->rc_static, &s->rc_unif, &s->rc_unif_spec, &s->rc_tmp, &s->mt_raw, &s->mt_raw2, &s->mt_windows, &s->gtab, &s->glm_ticket, &s->inner_part, &s->lgtab, &s->glm_part, &s->misc};
     for (DevBuf *b : bufs) b->release();
@@ -829,6 +829,62 @@ int ehmm_viterbi_forward(ehmm_session *s, const double *pi, const double *gamma,
 int ehmm_viterbi_backtrace(ehmm_session *s, int state_last, int *state_prev, double *states_out) {
     EHMM_TRY(check_session(s));
     return viterbi_backtrace(s, state_last, state_prev, states_out);
+}
+
+int ehmm_call_peaks(ehmm_session *s, double fdr, uint8_t *calls, int64_t *n_called, double *cutoff) {
+    EHMM_TRY(check_session(s));
+    EHMM_REQUIRE(avail(s, DS_P1), EHMM_ERR_STATE, "callPeaks: no logProb1 dataset (expStep has not run)");
+    EHMM_TRY(ensure(s, DS_P1));
+    return call_peaks_fdr(s, fdr, calls, n_called, cutoff);
+}
+
+int ehmm_call_peaks_viterbi(ehmm_session *s, uint8_t *calls, int64_t *n_called) {
+    EHMM_TRY(check_session(s));
+    EHMM_REQUIRE(has(s, DS_VIT), EHMM_ERR_STATE, "callPeaks(method = 'viterbi'): computeViterbiSequence has not run");
+    return call_peaks_viterbi(s, calls, n_called);
+}
+
+int ehmm_call_peaks_exact(ehmm_session *s, int force) {
+    EHMM_REQUIRE(s, EHMM_ERR_ARG, "null session");
+    s->peaks_exact = force != 0;
+    return EHMM_OK;
+}
+
+int ehmm_call_peaks_path(ehmm_session *s, int *path) {
+    EHMM_REQUIRE(s && path, EHMM_ERR_ARG, "null pointer");
+    *path = s->peaks_path;
+    return EHMM_OK;
+}
+
+int ehmm_peak_runs(ehmm_session *s, const int64_t *chrom_starts, int n_chrom_starts, int64_t cap, int64_t *starts, int64_t *ends,
+                   int64_t *n_runs) {
+    EHMM_TRY(check_session(s));
+    EHMM_REQUIRE(n_runs && n_chrom_starts >= 0 && (n_chrom_starts == 0 || chrom_starts) && cap >= 0, EHMM_ERR_ARG, "peak_runs: bad arguments");
+    return peak_runs(s, chrom_starts, n_chrom_starts, cap, starts, ends, n_runs);
+}
+
+// every dataset the reference's HDF5 file holds at the end of a fit, in one call.  Armadillo writes an
+// M x K column-major matrix as an HDF5 dataset of dims (K, M) (src/expStep.cpp:116-122): the bytes copied
+// here are exactly that dataset's, so the glue hands each buffer to H5Dwrite as it is.  NULL = skip.
+int ehmm_flush(ehmm_session *s, double *logLikelihood, double *logFP, double *logBP, double *logProb1, double *logProb2,
+               double *mixtureProb, double *viterbi) {
+    EHMM_TRY(check_session(s));
+    const int64_t M = s->M;
+    const int K = s->K;
+    struct { double *dst; DevBuf *buf; int64_t n; unsigned bit; const char *name; } d[] = {
+        {logLikelihood, &s->logf, M * K, DS_LOGF, "logLikelihood"}, {logFP, &s->logFP, M * K, DS_FP, "logFP"},
+        {logBP, &s->logBP, M * K, DS_BP, "logBP"},                  {logProb1, &s->logProb1, M * K, DS_P1, "logProb1"},
+        {logProb2, &s->logProb2, M * K * K, DS_P2, "logProb2"},     {mixtureProb, &s->eta, M * s->B, DS_ETA, "mixtureProb"},
+        {viterbi, &s->viterbi, M, DS_VIT, "viterbi"}};
+    for (auto &e : d) {
+        if (!e.dst) continue;
+        EHMM_REQUIRE(avail(s, e.bit), EHMM_ERR_STATE, "flush: dataset '%s' has not been written", e.name);
+        EHMM_TRY(ensure(s, e.bit));
+    }
+    for (auto &e : d)
+        if (e.dst) EHMM_CK(cudaMemcpyAsync(e.dst, e.buf->p, sizeof(double) * e.n, cudaMemcpyDeviceToHost, s->stream));
+    EHMM_CK(cudaStreamSynchronize(s->stream));
+    return EHMM_OK;
 }
 
 int ehmm_expstep_mode(ehmm_session *s, int lean) {

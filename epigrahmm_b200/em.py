@@ -533,7 +533,9 @@ def fdrControl(prob, fdr=0.05):
         raise ValueError("fdr must be between 0 and 1")
     notpp = 1.0 - prob
     order = np.argsort(notpp, kind="stable")
-    ok = np.cumsum(notpp[order]) / np.arange(1, prob.size + 1) < fdr
+    # R's cumsum adds in long double and stores doubles (src/main/cum.c); numpy's longdouble is that type on x86
+    csum = np.cumsum(notpp[order].astype(np.longdouble)).astype(np.float64)
+    ok = csum / np.arange(1, prob.size + 1) < fdr
     out = np.zeros(prob.size, dtype=bool)
     out[order] = ok
     return out
@@ -541,6 +543,8 @@ def fdrControl(prob, fdr=0.05):
 
 def callPeaks(backend, method="viterbi"):
     """R/callPeaks.R:61-62 without the GRanges post-processing: boolean peak index per bin."""
+    if hasattr(backend, "call_peaks"):      # sort, prefix sum and comparison on the device
+        return backend.call_peaks(method)
     if method == "viterbi":
         return backend.fetch("viterbi")[:, 0] == 1
     return fdrControl(np.exp(backend.fetch("logProb1")[:, 1]), fdr=float(method))

@@ -284,6 +284,52 @@ class Session:
         check(lib.ehmm_viterbi(self._h, dptr(_f64(pi)), dptr(_cm(gamma)), dptr(out)))
         return out
 
+    # -- callPeaks --------------------------------------------------------------------------
+    def call_peaks(self, method="viterbi", exact=False):
+        """R/callPeaks.R:61-62: boolean peak index per window; method 'viterbi' or an FDR level"""
+        calls = np.empty(self.M, dtype=np.uint8)
+        n = C.c_int64()
+        if method == "viterbi":
+            check(lib.ehmm_call_peaks_viterbi(self._h, calls.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(n)))
+        else:
+            cut = C.c_double()
+            check(lib.ehmm_call_peaks_exact(self._h, int(bool(exact))))
+            check(lib.ehmm_call_peaks(self._h, float(method), calls.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(n), C.byref(cut)))
+            self.peaks_cutoff = cut.value
+        assert int(calls.sum()) == n.value
+        return calls.astype(bool)
+
+    def call_peaks_path(self):
+        p = C.c_int()
+        check(lib.ehmm_call_peaks_path(self._h, C.byref(p)))
+        return ("fp64 prefix sum, margins certified", "emulated long double (forced)", "emulated long double (margin too small)")[p.value]
+
+    def peak_runs(self, chrom_starts=()):
+        """(starts, ends), inclusive window indices of the merged peaks of the last call_peaks"""
+        b = np.ascontiguousarray(chrom_starts, dtype=np.int64)
+        bp = b.ctypes.data_as(C.POINTER(C.c_int64)) if b.size else None
+        n = C.c_int64()
+        check(lib.ehmm_peak_runs(self._h, bp, b.size, 0, None, None, C.byref(n)))
+        st, en = np.empty(n.value, dtype=np.int64), np.empty(n.value, dtype=np.int64)
+        if n.value:
+            check(lib.ehmm_peak_runs(self._h, bp, b.size, n.value, st.ctypes.data_as(C.POINTER(C.c_int64)),
+                                     en.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(n)))
+        return st, en
+
+    def flush(self):
+        """every dataset of the fit, one device -> host pass (the end of the fit, R/base-core.R:212-226)"""
+        out, args = {}, []
+        for nm, cols, bit in (("logLikelihood", self.K, True), ("logFP", self.K, True), ("logBP", self.K, True), ("logProb1", self.K, True),
+                              ("logProb2", self.K * self.K, True), ("mixtureProb", self.B, self.B > 0), ("viterbi", 1, True)):
+            try:
+                self.dims(nm)
+                out[nm] = np.empty((self.M, cols), order="F")
+                args.append(dptr(out[nm]))
+            except _lib.EhmmError:
+                args.append(None)
+        check(lib.ehmm_flush(self._h, *args))
+        return out
+
     def expstep_mode(self, lean):
         """1: E-steps inside an EM loop write the posteriors and the statistics only; logFP / logBP / logProb1 /
         logProb2 of the last E-step are produced when somebody asks for them.  0: the reference's contract."""

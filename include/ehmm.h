@@ -148,6 +148,29 @@ int ehmm_inner_maxstepprob(ehmm_session *s, double *delta_out);
 int ehmm_inner_mstep_sums(ehmm_session *s, double *sums);
 /* getMarginalProbability, src/getMarginalProbability.cpp:12-21 (out: M x K). */
 int ehmm_marginal_probability(ehmm_session *s, double *out);
+/* ---- after the fit: callPeaks (R/callPeaks.R:61-68) ------------------------------------------------ */
+/* fdrControl(prob = exp(logProb1[, 2]), fdr), R/base-utils.R:11-25: calls[j] = 1 where the running mean of the
+ * ascending-sorted 1 - prob is below fdr (ties in window order, as data.table's order() leaves them); R's cumsum
+ * adds in long double and stores doubles -- reproduced exactly (see csrc/peaks.cu).  calls (M bytes, host) may
+ * be NULL: the calls stay on the device for ehmm_peak_runs.  cutoff: the largest 1 - prob called. */
+int ehmm_call_peaks(ehmm_session *s, double fdr, uint8_t *calls, int64_t *n_called, double *cutoff);
+/* method = 'viterbi' (R/callPeaks.R:62): calls[j] = (viterbi[j] == 1). */
+int ehmm_call_peaks_viterbi(ehmm_session *s, uint8_t *calls, int64_t *n_called);
+/* force = 1: every ehmm_call_peaks adds in emulated long double (the path taken on its own only when a running
+ * mean lies within rounding distance of the level).  path: 0 fp64 prefix sum with certified margins,
+ * 1 emulated (forced), 2 emulated (margin too small). */
+int ehmm_call_peaks_exact(ehmm_session *s, int force);
+int ehmm_call_peaks_path(ehmm_session *s, int *path);
+/* GenomicRanges::reduce over the called bins (R/callPeaks.R:67-68): maximal runs of consecutive called windows that
+ * do not cross a chromosome start (chrom_starts: ascending 0-based window indices where a chromosome begins; may be
+ * empty).  starts / ends (cap entries each, inclusive window indices, ascending) may be NULL to ask for the count. */
+int ehmm_peak_runs(ehmm_session *s, const int64_t *chrom_starts, int n_chrom_starts, int64_t cap, int64_t *starts, int64_t *ends,
+                   int64_t *n_runs);
+/* All datasets of the fit in one call, each as the bytes of the reference's HDF5 dataset (an M x K column-major
+ * matrix is the (K, M) dataset Armadillo writes, src/expStep.cpp:116-122).  NULL pointers are skipped. */
+int ehmm_flush(ehmm_session *s, double *logLikelihood, double *logFP, double *logBP, double *logProb1, double *logProb2,
+               double *mixtureProb, double *viterbi);
+
 /* How expStep delivers its results.  lean = 0 (default): the reference's contract -- logFP, logBP, logProb1
  * and logProb2 are written by the E-step (src/expStep.cpp:116-122).  lean = 1, for E-steps inside the EM
  * loop: only the posteriors P1 and the sufficient statistics are produced (nothing in R/base-EM.R:113-158,

@@ -899,3 +899,38 @@ EO_API double eo_glm_mix_nb(int64_t n, int B, int maxid, const double *par, cons
 }
 
 EO_API int eo_version(void) { return 1; }
+
+/* ------------------------------------------------------------------------ */
+/* fdrControl: R/base-utils.R:11-25.  notpp = 1 - prob; data.table's order()  */
+/* is a stable sort (ties keep window order); [EXT-R] cumsum() accumulates in */
+/* long double and stores each partial sum as a double (src/main/cum.c);      */
+/* FDR = cumsum / seq_len(.N) < fdr, put back in window order.                */
+/* Returns -1 when a probability lies outside [0, 1] (the reference stops).   */
+/* ------------------------------------------------------------------------ */
+typedef struct { double v; int64_t i; } eo_kv;
+static int eo_kv_cmp(const void *a, const void *b) {
+    const eo_kv *x = (const eo_kv *)a, *y = (const eo_kv *)b;
+    if (x->v < y->v) return -1;
+    if (x->v > y->v) return 1;
+    return (x->i > y->i) - (x->i < y->i);   /* ties: ascending window = a stable sort */
+}
+EO_API int64_t eo_fdr_control(int64_t n, const double *prob, double fdr, unsigned char *out) {
+    eo_kv *kv = (eo_kv *)malloc(sizeof(eo_kv) * (size_t)(n > 0 ? n : 1));
+    for (int64_t i = 0; i < n; i++) {
+        if (!(prob[i] >= 0.0 && prob[i] <= 1.0)) { free(kv); return -1; }
+        kv[i].v = 1.0 - prob[i];
+        kv[i].i = i;
+    }
+    qsort(kv, (size_t)n, sizeof(eo_kv), eo_kv_cmp);
+    long double sum = 0.0L;
+    int64_t called = 0;
+    for (int64_t r = 0; r < n; r++) {
+        sum += kv[r].v;
+        const double s = (double)sum;
+        const unsigned char c = (s / (double)(r + 1)) < fdr;
+        out[kv[r].i] = c;
+        called += c;
+    }
+    free(kv);
+    return called;
+}

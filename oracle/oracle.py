@@ -44,7 +44,7 @@ def lib():
         _lib.eo_glm_zinb.restype = C.c_double
         _lib.eo_glm_mix_zinb.restype = C.c_double
         _lib.eo_glm_mix_nb.restype = C.c_double
-        for n in ("eo_reweight", "eo_reweight_buf", "eo_aggregate_compact", "eo_consensus_rc", "eo_differential_rc"):
+        for n in ("eo_reweight", "eo_reweight_buf", "eo_aggregate_compact", "eo_consensus_rc", "eo_differential_rc", "eo_fdr_control"):
             getattr(_lib, n).restype = C.c_int64
     return _lib
 
@@ -382,3 +382,13 @@ def glmMixNB(par, id, weights, y, offsets, dsg, maxid, minZero, grad=True):
                             _p(_f64(y)), _p(_f64(offsets)), _p(dsg, C.c_uint8), C.c_double(minZero),
                             _p(g) if grad else None)
     return v, g
+
+
+def fdrControl(prob, fdr=0.05):
+    """R/base-utils.R:11-25 with R's long double cumsum: boolean vector in window order."""
+    prob = _f64(prob)
+    out = np.empty(prob.size, dtype=np.uint8)
+    n = lib().eo_fdr_control(C.c_int64(prob.size), _p(prob), C.c_double(fdr), out.ctypes.data_as(C.POINTER(C.c_ubyte)))
+    if n < 0:
+        raise ValueError("Posterior probabilities must be between 0 and 1")
+    return out.astype(bool)

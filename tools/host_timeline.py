@@ -1,45 +1,60 @@
-"""Wall-clock per host call of one EM iteration (where the non-kernel time goes)."""
+"""Wall-clock per host call of one EM step of a bench configuration (where the non-kernel time goes).
+usage: python tools/host_timeline.py [c2|c3|c5] [bins] [steps]"""
+import json
+import os
 import sys
 import time
 
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench  # noqa: E402
+import epigrahmm_b200 as E  # noqa: E402
+from epigrahmm_b200.rng import RState  # noqa: E402
 
-sys.path.insert(0, ".")
-import bench
-import epigrahmm_b200 as E
-from epigrahmm_b200 import em, synth
-from epigrahmm_b200.rng import RState
-
-M = int(float(sys.argv[1])) if len(sys.argv) > 1 else 15_000_000
-d, g = bench.make_workload(M, bench.N_SAMPLES, bench.SEED)
-th = synth.THETA_CONSENSUS
-theta = dict(pi=th["pi"], gamma=th["gamma"], psi=th["psi"])
-ctl = em.controlEM()
-s = E.Session("tl", M, 2)
+name = sys.argv[1] if len(sys.argv) > 1 else "c3"
+cfg = bench.CONFIGS[name]
+M = int(float(sys.argv[2])) if len(sys.argv) > 2 else cfg["M"]
+steps = int(sys.argv[3]) if len(sys.argv) > 3 else 10
+d = bench.make_data(cfg, M, cfg["seed"])
+theta, ctl = bench.theta_of(cfg, d), bench.control_of(cfg)
+s = E.Session("tl", M, cfg["K"])
 s.set_data(d["counts"], d["offsets"])
-s.set_groups(g["group"], g["u_chip"], g["u_offsets"])
+if cfg["model"] == "differential":
+    s.set_design(d["design"])
+s.build_groups()
 s.rng_set_state(RState(1).state)
-acc = {}
-nev = [0]
-orig = s.glm_nb
+
+acc, cnt = {}, {}
+on = [False]
 
 
-def glm(c, p, grad=True):
-    nev[0] += 1
-    return orig(c, p, grad)
+def wrap(nm):
+    f = getattr(s, nm)
+
+    def g(*a, **k):
+        t0 = time.perf_counter()
+        r = f(*a, **k)
+        if on[0]:
+            acc[nm] = acc.get(nm, 0.0) + time.perf_counter() - t0
+            cnt[nm] = cnt.get(nm, 0) + 1
+        return r
+    setattr(s, nm, g)
 
 
-s.glm_nb = glm
-for it in range(25):
-    t = [time.perf_counter()]
-    s.loglik_consensus(theta["psi"], ctl["minZero"]); t.append(time.perf_counter())
-    s.expstep(theta["pi"], theta["gamma"]); t.append(time.perf_counter())
-    s.maxstepprob(); t.append(time.perf_counter())
-    s.rc_consensus(0.05); t.append(time.perf_counter())
-    o0 = em.optimNB(theta["psi"][0], s, 0, ctl); t.append(time.perf_counter())
-    o1 = em.optimNB(theta["psi"][1], s, 1, ctl); t.append(time.perf_counter())
-    s.bic(5, 4); s.qfunction(theta["pi"], theta["gamma"]); t.append(time.perf_counter())
-    if it >= 5:
-        for n, a, b in zip(["loglik(launch)", "expstep(launch)", "maxstepprob(sync)", "rc", "optim0", "optim1", "bic+q"], t[:-1], t[1:]):
-            acc[n] = acc.get(n, 0.0) + (b - a) / 20
-print({k: round(v * 1e3, 3) for k, v in acc.items()}, "total ms", round(sum(acc.values()) * 1e3, 3), "glm evals/iter", nev[0] / 25)
+for nm in ("loglik_consensus", "loglik_differential_hmm", "expstep", "maxstepprob", "rc_consensus", "rc_differential",
+           "inner_expstep", "inner_maxstepprob", "glm_nb_batch", "glm_mix_nb", "bic", "qfunction", "rc_hint", "expstep_mode"):
+    wrap(nm)
+for _ in range(3):
+    bench.em_step(s, cfg, theta, ctl)
+s.sync()
+on[0] = True
+t0 = time.perf_counter()
+for _ in range(steps):
+    bench.em_step(s, cfg, theta, ctl)
+s.sync()
+tot = (time.perf_counter() - t0) / steps
+out = {"config": name, "bins": M, "wall_ms_per_step": round(1e3 * tot, 3),
+       "calls": {k: {"n_per_step": cnt[k] / steps, "ms_per_step": round(1e3 * acc[k] / steps, 3)} for k in sorted(acc, key=lambda k: -acc[k])}}
+out["inside_calls_ms"] = round(sum(v["ms_per_step"] for v in out["calls"].values()), 3)
+out["python_between_calls_ms"] = round(out["wall_ms_per_step"] - out["inside_calls_ms"], 3)
+print(json.dumps(out))
 s.close()
