@@ -163,6 +163,13 @@ struct ehmm_session {
     ehmm::DevBuf rc_flag, rc_scan, rc_buckets, rc_unif, rc_tmp, mt_raw, mt_raw2, mt_windows;
     ehmm::DevBuf rc_unif_spec;   // uniforms generated ahead of the next call on the side stream (mt_speculate)
     int64_t spec_n = 0;          // ... that many words from the current stream position (0: none)
+    // sharded form: this block's column slices generated ahead, with a margin either side (mt_speculate_ranges)
+    ehmm::DevBuf rc_unif_specr[2];
+    int specr_next = 0;          // buffer the next speculation writes
+    int specr_cols = 0;          // 0: nothing generated ahead
+    uint64_t specr_epoch = 0;    // rng_epoch the ranges are relative to
+    int64_t specr_lo[64] = {0}, specr_n[64] = {0}, specr_off[64] = {0};
+    uint64_t rng_epoch = 1;      // bumped whenever the stream position changes
     ehmm::DevBuf rc_limbs, rc_coltot;  // exact accumulators (2 x u64 per table entry); column totals + error flag
     bool rc_exact = false;       // the last rejection tables were accumulated as exact limbs ...
     bool rc_final = false;       // ... and have been rounded into rc_buckets
@@ -170,7 +177,7 @@ struct ehmm_session {
     int64_t mtj_valid = 0;       // sub-stream windows valid for the state in mt_raw
     bool mtj_pending = false;    // ... being computed on stream2 (event ev)
     bool mtj_base = false;       // window 0 is in place
-    int64_t mtj_iv[8][2] = {{0}};  // further valid runs of windows [lo, hi] (sharded fits prepare only their slice)
+    int64_t mtj_iv[80][2] = {{0}};  // further valid runs of windows [lo, hi] (sharded fits prepare only their slice)
     int mtj_niv = 0;
     bool rng_dev_valid = false;  // mt_raw holds rng_state
     bool rng_pending = false;    // the state after the last draw is on its way to h_pinned + 512 (rng_state[0] is already current)
@@ -323,6 +330,8 @@ int groups_remap(ehmm_session *s, const int32_t *new_id, int64_t G_new);
 // mtjump.cu
 int mt_generate(ehmm_session *s, int64_t n, uint32_t *out);
 int mt_generate_range(ehmm_session *s, int64_t lo_rel, int64_t n, uint32_t *out);
+int mt_generate_ranges(ehmm_session *s, int nr, const int64_t *lo_rel, const int64_t *n, const int64_t *out_off, uint32_t *out);
+int mt_speculate_ranges(ehmm_session *s, int nr, const int64_t *lo_rel, const int64_t *n, const int64_t *out_off, uint32_t *out);
 int mt_advance(ehmm_session *s, int64_t n);
 int mt_advance_side(ehmm_session *s, int64_t n, void *h_state);
 int mt_prefetch(ehmm_session *s, int64_t max_draws);

@@ -193,6 +193,28 @@ __device__ __forceinline__ void diff_cells(int64_t j, int64_t M, int N, const in
     }
 }
 
+// dictionary-encoded source with the group ids already in registers (the caller fetched them one strip ahead, so
+// the table gathers of this strip do not wait for an id load first)
+template <int NMAX>
+__device__ __forceinline__ void diff_cells_ids(const int (&gid)[NMAX], int N, const double2 *__restrict__ E, double &LL0,
+                                               double &LL2, double *d) {
+    double2 e[NMAX];
+#pragma unroll
+    for (int i = 0; i < NMAX; i++) e[i] = (i < N) ? __ldg(E + gid[i]) : make_double2(0.0, 0.0);
+    LL0 = 0.0;
+    LL2 = 0.0;
+#pragma unroll
+    for (int i = 0; i < NMAX; i++) {
+        if (i < N) {
+            LL0 += e[i].x;
+            LL2 += e[i].y;
+            d[i] = e[i].y - e[i].x;
+        } else {
+            d[i] = 0.0;
+        }
+    }
+}
+
 template <int NMAX>
 __device__ __forceinline__ double mix_ll(int b, double LL0, const double *d, const MixParams &X) {
     double s = 0.0;
@@ -243,14 +265,32 @@ __global__ void __launch_bounds__(EM_NT, (GROUPED && BMAX <= 14) ? 3 : 1)
     const int64_t nwarps = (int64_t)gridDim.x * (EM_NT / 32);
     for (int64_t tile = ((int64_t)blockIdx.x * EM_NT + threadIdx.x) >> 5; tile < nwt; tile += nwarps) {
         int cnt0 = 0, cnt1 = 0;  // lane (c & 31) counts column c (cnt1: columns 32..63)
+        int gnext[NMAX];         // GROUPED: the group ids of the coming strip
+        if (GROUPED) {
+            const int64_t j0 = tile * RC_WT + lane;
+#pragma unroll
+            for (int i = 0; i < NMAX; i++)
+                gnext[i] = (i < N && j0 < M) ? __ldg(reinterpret_cast<const int32_t *>(tab) + j0 + (int64_t)i * M) : 0;
+        }
 #pragma unroll 1
         for (int r = 0; r < RC_STRIPS; r++) {
             const int64_t j = tile * RC_WT + r * 32 + lane;
             const bool valid = j < M;
             double v[BMAX], s = 0.0, p1 = 0.0;
+            double LL0 = 0.0, LL2 = 0.0, d[NMAX];
+            if (GROUPED) {
+                int gcur[NMAX];
+#pragma unroll
+                for (int i = 0; i < NMAX; i++) gcur[i] = gnext[i];
+                diff_cells_ids<NMAX>(gcur, N, reinterpret_cast<const double2 *>(off), LL0, LL2, d);  // row 0 of the table for idle lanes
+                const int64_t jn = j + 32;
+                const bool more = (r + 1 < RC_STRIPS) && jn < M;
+#pragma unroll
+                for (int i = 0; i < NMAX; i++)
+                    gnext[i] = (i < N && more) ? __ldg(reinterpret_cast<const int32_t *>(tab) + jn + (int64_t)i * M) : 0;
+            }
             if (valid) {
-                double LL0, LL2, d[NMAX];
-                diff_cells<NMAX, GROUPED>(j, M, N, y, off, P, tab, LL0, LL2, d);
+                if (!GROUPED) diff_cells<NMAX, GROUPED>(j, M, N, y, off, P, tab, LL0, LL2, d);
 #pragma unroll
                 for (int b = 0; b < BMAX; b++) {
                     if (b < X.B) {

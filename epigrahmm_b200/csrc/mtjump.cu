@@ -12,8 +12,11 @@
 // stream while the E-step runs.
 #include "common.cuh"
 #include "mtpoly.h"
+#include <algorithm>
 #include <map>
 #include <mutex>
+#include <utility>
+#include <vector>
 
 namespace ehmm {
 
@@ -53,14 +56,11 @@ __global__ void mt_base_kernel(const uint32_t *__restrict__ state, uint32_t *__r
 // (nidx entries, padded to a multiple of 8 with ZERO_IDX, which addresses a zeroed region).  The
 // coefficient list is split over gridDim.y CTAs (a window is latency-bound in one CTA and the
 // doubling rounds are serial); the destination windows are zeroed beforehand and accumulate by XOR.
-__global__ void __launch_bounds__(JUMP_NT) mt_jump_kernel(const uint16_t *__restrict__ idx, int nidx,
-                                                          const uint32_t *__restrict__ srcw, uint32_t *__restrict__ dstw) {
-    extern __shared__ uint32_t sm[];
+__device__ __forceinline__ void jump_body(const uint16_t *__restrict__ idx, int nidx, const uint32_t *__restrict__ src,
+                                          uint32_t *__restrict__ dst, uint32_t *sm) {
     uint32_t *buf = sm;                                                   // EXPW words + zero pad
     uint16_t *sidx = reinterpret_cast<uint16_t *>(sm + BUFW);             // this CTA's slice of the list
     const int tid = threadIdx.x;
-    const uint32_t *src = srcw + (size_t)blockIdx.x * MT_N;  // window blockIdx.x of the source run
-    uint32_t *dst = dstw + (size_t)blockIdx.x * MT_N;        // ... jumps to window blockIdx.x of the destination run
     const int per = ((nidx / 8 + gridDim.y - 1) / gridDim.y) * 8;         // entries per slice (multiple of 8)
     const int q0 = min(nidx, (int)blockIdx.y * per), q1 = min(nidx, q0 + per);
     for (int i = tid; i < MT_N; i += JUMP_NT) buf[i] = src[i];
@@ -86,17 +86,52 @@ __global__ void __launch_bounds__(JUMP_NT) mt_jump_kernel(const uint16_t *__rest
     }
 }
 
-// CTA b handles sub-stream s = s_first + b.  It writes the tempered words of the absolute range
+__global__ void __launch_bounds__(JUMP_NT) mt_jump_kernel(const uint16_t *__restrict__ idx, int nidx,
+                                                          const uint32_t *__restrict__ srcw, uint32_t *__restrict__ dstw) {
+    extern __shared__ uint32_t sm[];
+    // window blockIdx.x of the source run jumps to window blockIdx.x of the destination run
+    jump_body(idx, nidx, srcw + (size_t)blockIdx.x * MT_N, dstw + (size_t)blockIdx.x * MT_N, sm);
+}
+
+// several runs of windows in one launch, each with its own polynomial: entry e takes windows src[e] + c to dst[e] + c
+// (c < cta0[e + 1] - cta0[e]) by the polynomial of level lv[e].  The windows a bin block needs lie in several
+// separate stretches of the stream (one per column of the rejection control); prepared one stretch after the
+// other, the ~100 dependent launches of a call took longer than the call's own kernels.
+constexpr int JB_MAX = 72;
+struct JumpBatch {
+    int n;
+    int cta0[JB_MAX + 1];
+    int src[JB_MAX], dst[JB_MAX], lv[JB_MAX], nidx[JB_MAX];
+};
+__global__ void __launch_bounds__(JUMP_NT) mt_jump_multi_kernel(const uint16_t *__restrict__ idx_all, const __grid_constant__ JumpBatch B,
+                                                                uint32_t *__restrict__ S) {
+    extern __shared__ uint32_t sm[];
+    int e = 0;
+    while (e + 1 < B.n && (int)blockIdx.x >= B.cta0[e + 1]) e++;
+    const int c = (int)blockIdx.x - B.cta0[e];
+    jump_body(idx_all + (size_t)B.lv[e] * MAX_IDX, B.nidx[e], S + (size_t)(B.src[e] + c) * MT_N, S + (size_t)(B.dst[e] + c) * MT_N, sm);
+}
+
+struct ZeroRuns {
+    int n;
+    int first[JB_MAX], count[JB_MAX];
+};
+__global__ void mt_zero_runs_kernel(const __grid_constant__ ZeroRuns Z, uint32_t *__restrict__ S) {
+    for (int r = 0; r < Z.n; r++) {
+        uint32_t *p = S + (size_t)Z.first[r] * MT_N;
+        const int64_t n = (int64_t)Z.count[r] * MT_N;
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = 0u;
+    }
+}
+
+// One CTA walks sub-stream s.  It writes the tempered words of the absolute range
 // [pos + lo_rel, pos + hi_rel) that fall into its sub-stream (out[a - (pos + lo_rel)]) and, when
 // n_state > 0, the raw words of R's state array after n_state draws (the aligned 624-word block
 // containing the last drawn word, and mti).
-__global__ void __launch_bounds__(GEN_NT)
-    mt_generate_kernel(const uint32_t *__restrict__ state, const uint32_t *__restrict__ S, int s_first, int64_t lo_rel,
-                       int64_t hi_rel, uint32_t *__restrict__ out, int64_t n_state, uint32_t *__restrict__ state_out,
-                       int64_t jw) {
-    __shared__ uint32_t buf[2][MT_N];
+__device__ __forceinline__ void gen_substream(const uint32_t *__restrict__ state, const uint32_t *__restrict__ S, int s, int64_t lo_rel,
+                                              int64_t hi_rel, uint32_t *__restrict__ out, int64_t n_state,
+                                              uint32_t *__restrict__ state_out, int64_t jw, uint32_t (*buf)[MT_N]) {
     const int tid = threadIdx.x;
-    const int s = s_first + blockIdx.x;
     const int64_t pos = state[0];
     const int64_t lo_abs = pos + lo_rel, hi_abs = pos + hi_rel;
     const int64_t a0 = (s == 0) ? 0 : 1 + (int64_t)s * jw;
@@ -144,6 +179,34 @@ __global__ void __launch_bounds__(GEN_NT)
     }
 }
 
+// CTA b handles sub-stream s_first + b of one range
+__global__ void __launch_bounds__(GEN_NT)
+    mt_generate_kernel(const uint32_t *__restrict__ state, const uint32_t *__restrict__ S, int s_first, int64_t lo_rel,
+                       int64_t hi_rel, uint32_t *__restrict__ out, int64_t n_state, uint32_t *__restrict__ state_out,
+                       int64_t jw) {
+    __shared__ uint32_t buf[2][MT_N];
+    gen_substream(state, S, s_first + (int)blockIdx.x, lo_rel, hi_rel, out, n_state, state_out, jw, buf);
+}
+
+// several ranges of the stream in one launch (a bin block's slices of the rejection control's columns): CTAs
+// [cta0[r], cta0[r + 1]) walk the sub-streams of range r, whose words go to out + out_off[r]
+constexpr int GEN_MAXR = 64;
+struct GenRanges {
+    int n;
+    int cta0[GEN_MAXR + 1];
+    int s_first[GEN_MAXR];
+    int64_t lo_rel[GEN_MAXR], hi_rel[GEN_MAXR], out_off[GEN_MAXR];
+};
+
+__global__ void __launch_bounds__(GEN_NT)
+    mt_generate_multi_kernel(const uint32_t *__restrict__ state, const uint32_t *__restrict__ S, const __grid_constant__ GenRanges R,
+                             uint32_t *__restrict__ out, int64_t jw) {
+    __shared__ uint32_t buf[2][MT_N];
+    int r = 0;
+    while (r + 1 < R.n && (int)blockIdx.x >= R.cta0[r + 1]) r++;
+    gen_substream(state, S, R.s_first[r] + ((int)blockIdx.x - R.cta0[r]), R.lo_rel[r], R.hi_rel[r], out + R.out_off[r], -1, nullptr, jw, buf);
+}
+
 // jump polynomials: computed once per process on the host, uploaded once per device
 std::mutex g_mu;
 std::vector<uint16_t> g_idx;    // LEVELS * MAX_IDX coefficient positions
@@ -174,6 +237,7 @@ int device_polys(int device, const uint16_t **out) {
         EHMM_CK(cudaMalloc(&d, sizeof(uint16_t) * g_idx.size()));
         EHMM_CK(cudaMemcpy(d, g_idx.data(), sizeof(uint16_t) * g_idx.size(), cudaMemcpyHostToDevice));
         EHMM_CK(cudaFuncSetAttribute(mt_jump_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)JUMP_SMEM));
+        EHMM_CK(cudaFuncSetAttribute(mt_jump_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)JUMP_SMEM));
         it = g_dev_idx.emplace(device, d).first;
     }
     *out = it->second;
@@ -205,9 +269,11 @@ int launch_jump(ehmm_session *s, cudaStream_t st, const uint16_t *idx, int k, co
     return EHMM_OK;
 }
 
-// window buffer for sub-streams [0, P) plus two scratch windows; growing it invalidates what it held
+// window buffer for sub-streams [0, P) plus scratch windows (two for mt_prepare_range, LEVELS per run for
+// mt_prepare_ranges); growing it invalidates what it held
+constexpr int SCRATCH_W = 2 + JB_MAX * LEVELS;
 int reserve_windows(ehmm_session *s, int64_t P) {
-    const size_t need = sizeof(uint32_t) * MT_N * (size_t)(P + 2);
+    const size_t need = sizeof(uint32_t) * MT_N * (size_t)(P + SCRATCH_W);
     if (s->mt_windows.bytes < need) {
         if (s->mtj_pending) {  // kernels on the side stream may still write the old buffer
             EHMM_CK(cudaStreamSynchronize(s->stream2));
@@ -292,9 +358,118 @@ int mt_prepare_range(ehmm_session *s, cudaStream_t st, int64_t q_lo, int64_t q_h
         const int64_t cnt = (len - base < base) ? (len - base) : base;
         EHMM_TRY(launch_jump(s, st, idx, k, R, R + (size_t)base * MT_N, cnt));
     }
-    if (s->mtj_niv < 8) {
+    if (s->mtj_niv < 80) {
         s->mtj_iv[s->mtj_niv][0] = q_lo;
         s->mtj_iv[s->mtj_niv][1] = q_hi;
+        s->mtj_niv++;
+    }
+    return EHMM_OK;
+}
+
+// Windows of several stretches [q_lo[i], q_hi[i]] of sub-streams at once: the stretches are merged where they touch,
+// every run reaches its first window from window 0 by one jump per set bit of its index, and then doubles; all
+// runs take their t-th step in the same launch (popcount + log2(length) launches in all instead of per run).
+int mt_prepare_ranges(ehmm_session *s, cudaStream_t st, int nr, const int64_t *q_lo_in, const int64_t *q_hi_in) {
+    std::vector<std::pair<int64_t, int64_t>> iv;
+    int64_t qmax = 0;
+    for (int i = 0; i < nr; i++) {
+        const int64_t lo = std::max<int64_t>(0, q_lo_in[i]), hi = q_hi_in[i];
+        if (hi < lo || hi < 1 || windows_cover(s, lo, hi)) continue;
+        iv.push_back({lo, hi});
+        qmax = std::max(qmax, hi);
+    }
+    if (iv.empty()) return EHMM_OK;
+    std::sort(iv.begin(), iv.end());
+    std::vector<std::pair<int64_t, int64_t>> runs;
+    for (const auto &v : iv) {
+        if (!runs.empty() && v.first <= runs.back().second + 1) runs.back().second = std::max(runs.back().second, v.second);
+        else runs.push_back(v);
+    }
+    if ((int)runs.size() > JB_MAX) {  // (never with <= 64 columns) one run after the other
+        for (const auto &r : runs) EHMM_TRY(mt_prepare_range(s, st, r.first, r.second));
+        return EHMM_OK;
+    }
+    EHMM_REQUIRE(qmax < ((int64_t)1 << (LEVELS - s->mt_shift)), EHMM_ERR_RNG, "draw position beyond 2^%d sub-streams", LEVELS - s->mt_shift);
+    const uint16_t *idx = nullptr;
+    EHMM_TRY(device_polys(s->device, &idx));
+    EHMM_TRY(reserve_windows(s, qmax + 1));
+    // (a growing buffer dropped the runs found covered above: they are simply prepared again by the next caller)
+    uint32_t *S = s->mt_windows.as<uint32_t>();
+    const int64_t cap = (int64_t)(s->mt_windows.bytes / (sizeof(uint32_t) * MT_N));
+    const int64_t scratch0 = cap - SCRATCH_W;  // LEVELS scratch windows per run (the last two belong to mt_prepare_range)
+    EHMM_TRY(base_window(s, st));
+    const int R = (int)runs.size();
+    {   // every destination window is written once: zero them all first
+        ZeroRuns Z;
+        Z.n = 0;
+        for (int r = 0; r < R; r++) {
+            Z.first[Z.n] = (int)std::max<int64_t>(1, runs[r].first);  // window 0 is the base window
+            Z.count[Z.n] = (int)(runs[r].second - Z.first[Z.n] + 1);
+            if (Z.count[Z.n] > 0) Z.n++;
+        }
+        EHMM_CK(cudaMemsetAsync(S + (size_t)scratch0 * MT_N, 0, sizeof(uint32_t) * MT_N * (size_t)(JB_MAX * LEVELS), st));
+        mt_zero_runs_kernel<<<148, 256, 0, st>>>(Z, S);
+        EHMM_CK(cudaGetLastError());
+    }
+    const int nlev = LEVELS - s->mt_shift;
+    auto launch = [&](const JumpBatch &B) -> int {
+        if (B.n == 0) return EHMM_OK;
+        mt_jump_multi_kernel<<<dim3((unsigned)B.cta0[B.n], JUMP_SPLIT), JUMP_NT, JUMP_SMEM, st>>>(idx, B, S);
+        EHMM_CK(cudaGetLastError());
+        s->launches[KID_MT]++;
+        return EHMM_OK;
+    };
+    auto add = [&](JumpBatch &B, int64_t src, int64_t dst, int k, int64_t cnt) {
+        const int lv = k + s->mt_shift;
+        B.src[B.n] = (int)src;
+        B.dst[B.n] = (int)dst;
+        B.lv[B.n] = lv;
+        B.nidx[B.n] = g_nidx[lv];
+        B.cta0[B.n + 1] = B.cta0[B.n] + (int)cnt;
+        B.n++;
+    };
+    // reach the first window of every run
+    std::vector<int64_t> cur((size_t)R, 0);
+    std::vector<int> done((size_t)R, 0), bits((size_t)R, 0), nextk((size_t)R, 0);
+    int maxbits = 0;
+    for (int r = 0; r < R; r++) {
+        for (int k = 0; k < nlev; k++) bits[(size_t)r] += (int)((runs[r].first >> k) & 1);
+        maxbits = std::max(maxbits, bits[(size_t)r]);
+    }
+    for (int t = 0; t < maxbits; t++) {
+        JumpBatch B;
+        B.n = 0;
+        B.cta0[0] = 0;
+        for (int r = 0; r < R; r++) {
+            if (done[(size_t)r] >= bits[(size_t)r]) continue;
+            int k = nextk[(size_t)r];
+            while (!((runs[r].first >> k) & 1)) k++;
+            nextk[(size_t)r] = k + 1;
+            done[(size_t)r]++;
+            const int64_t dst = (done[(size_t)r] == bits[(size_t)r]) ? runs[r].first : scratch0 + (int64_t)r * LEVELS + t;
+            add(B, cur[(size_t)r], dst, k, 1);
+            cur[(size_t)r] = dst;
+        }
+        EHMM_TRY(launch(B));
+    }
+    // double inside every run
+    int64_t maxlen = 0;
+    for (int r = 0; r < R; r++) maxlen = std::max(maxlen, runs[r].second - runs[r].first + 1);
+    for (int k = 0; ((int64_t)1 << k) < maxlen; k++) {
+        JumpBatch B;
+        B.n = 0;
+        B.cta0[0] = 0;
+        const int64_t base = (int64_t)1 << k;
+        for (int r = 0; r < R; r++) {
+            const int64_t len = runs[r].second - runs[r].first + 1;
+            if (len <= base) continue;
+            add(B, runs[r].first, runs[r].first + base, k, std::min(base, len - base));
+        }
+        EHMM_TRY(launch(B));
+    }
+    for (int r = 0; r < R && s->mtj_niv < 80; r++) {
+        s->mtj_iv[s->mtj_niv][0] = runs[r].first;
+        s->mtj_iv[s->mtj_niv][1] = runs[r].second;
         s->mtj_niv++;
     }
     return EHMM_OK;
@@ -352,6 +527,105 @@ int mt_generate_range(ehmm_session *s, int64_t lo_rel, int64_t n, uint32_t *out)
     PROF(s, KID_MT), mt_generate_kernel<<<(unsigned)(s1 - s0 + 1), GEN_NT, 0, s->stream>>>(
         s->mt_raw.as<uint32_t>(), s->mt_windows.as<uint32_t>(), (int)s0, lo_rel, lo_rel + n, out, -1, nullptr, jw_of(s));
     EHMM_CK(cudaGetLastError());
+    return EHMM_OK;
+}
+
+// nr ranges [lo_rel[i], lo_rel[i] + n[i]) of the stream (relative to the current position) in ONE launch, range i to
+// out + out_off[i]; nothing is advanced.  A range is walked by one CTA per sub-stream it touches, so launching the
+// ranges one by one leaves most of the machine idle (a column's slice of a sharded fit is a few sub-streams long).
+int mt_generate_ranges(ehmm_session *s, int nr, const int64_t *lo_rel, const int64_t *n, const int64_t *out_off, uint32_t *out) {
+    EHMM_REQUIRE(nr <= GEN_MAXR, EHMM_ERR_ARG, "at most %d ranges per launch", GEN_MAXR);
+    const int64_t pos = s->rng_state[0];
+    // the window buffer must not grow between the ranges (growing drops what it holds): size it for the farthest one first
+    int64_t qmax = 0;
+    for (int i = 0; i < nr; i++)
+        if (n[i] > 0) qmax = std::max(qmax, substream_of(s, pos + lo_rel[i] + n[i] - 1));
+    EHMM_TRY(wait_pending(s));
+    if (qmax >= 1) EHMM_TRY(reserve_windows(s, qmax + 1));
+    {
+        int64_t qlo[GEN_MAXR], qhi[GEN_MAXR];
+        int m = 0;
+        for (int i = 0; i < nr; i++) {
+            if (n[i] <= 0) continue;
+            qlo[m] = substream_of(s, pos + lo_rel[i]);
+            qhi[m] = substream_of(s, pos + lo_rel[i] + n[i] - 1);
+            m++;
+        }
+        EHMM_TRY(mt_prepare_ranges(s, s->stream, m, qlo, qhi));
+    }
+    GenRanges R;
+    R.n = 0;
+    int ctas = 0;
+    for (int i = 0; i < nr; i++) {
+        if (n[i] <= 0) continue;
+        const int64_t s0 = substream_of(s, pos + lo_rel[i]), s1 = substream_of(s, pos + lo_rel[i] + n[i] - 1);
+        EHMM_REQUIRE(s1 < 1 || windows_cover(s, s0, s1), EHMM_ERR_RNG, "sub-stream windows [%lld, %lld] are not in place", (long long)s0,
+                     (long long)s1);
+        R.cta0[R.n] = ctas;
+        R.s_first[R.n] = (int)s0;
+        R.lo_rel[R.n] = lo_rel[i];
+        R.hi_rel[R.n] = lo_rel[i] + n[i];
+        R.out_off[R.n] = out_off[i];
+        ctas += (int)(s1 - s0 + 1);
+        R.n++;
+    }
+    if (R.n == 0) return EHMM_OK;
+    R.cta0[R.n] = ctas;
+    PROF(s, KID_MT), mt_generate_multi_kernel<<<(unsigned)ctas, GEN_NT, 0, s->stream>>>(s->mt_raw.as<uint32_t>(), s->mt_windows.as<uint32_t>(), R, out,
+                                                                                 jw_of(s));
+    EHMM_CK(cudaGetLastError());
+    return EHMM_OK;
+}
+
+// The same on the side stream, ahead of the call that will consume the words (sharded fits: a block's column slices
+// sit where the previous call's did, give or take the change of the counts in between, so the caller asks for the
+// previous slices with a margin either side).  Call after mt_advance_side: the ranges are relative to the NEW
+// position.  The main stream meets the side stream again at the next wait_pending.
+int mt_speculate_ranges(ehmm_session *s, int nr, const int64_t *lo_rel, const int64_t *n, const int64_t *out_off, uint32_t *out) {
+    EHMM_REQUIRE(nr <= GEN_MAXR, EHMM_ERR_ARG, "at most %d ranges per launch", GEN_MAXR);
+    const int64_t pos = s->rng_state[0];
+    int64_t qmax = 0;
+    for (int i = 0; i < nr; i++)
+        if (n[i] > 0) qmax = std::max(qmax, substream_of(s, pos + lo_rel[i] + n[i] - 1));
+    if (qmax >= 1) EHMM_TRY(reserve_windows(s, qmax + 1));
+    {
+        int64_t qlo[GEN_MAXR], qhi[GEN_MAXR];
+        int m = 0;
+        for (int i = 0; i < nr; i++) {
+            if (n[i] <= 0) continue;
+            qlo[m] = substream_of(s, pos + lo_rel[i]);
+            qhi[m] = substream_of(s, pos + lo_rel[i] + n[i] - 1);
+            m++;
+        }
+        EHMM_TRY(mt_prepare_ranges(s, s->stream2, m, qlo, qhi));
+    }
+    GenRanges R;
+    R.n = 0;
+    int ctas = 0;
+    for (int i = 0; i < nr; i++) {
+        if (n[i] <= 0) continue;
+        const int64_t s0 = substream_of(s, pos + lo_rel[i]), s1 = substream_of(s, pos + lo_rel[i] + n[i] - 1);
+        R.cta0[R.n] = ctas;
+        R.s_first[R.n] = (int)s0;
+        R.lo_rel[R.n] = lo_rel[i];
+        R.hi_rel[R.n] = lo_rel[i] + n[i];
+        R.out_off[R.n] = out_off[i];
+        ctas += (int)(s1 - s0 + 1);
+        R.n++;
+    }
+    if (R.n > 0) {
+        R.cta0[R.n] = ctas;
+        for (int r = 0; r < R.n; r++)  // (a growing window buffer drops earlier ranges: then nothing is generated and the caller misses)
+            EHMM_REQUIRE(substream_of(s, pos + R.hi_rel[r] - 1) < 1 ||
+                             windows_cover(s, R.s_first[r], substream_of(s, pos + R.hi_rel[r] - 1)),
+                         EHMM_ERR_RNG, "speculative generation: sub-stream windows are not in place");
+        mt_generate_multi_kernel<<<(unsigned)ctas, GEN_NT, 0, s->stream2>>>(s->mt_raw.as<uint32_t>(), s->mt_windows.as<uint32_t>(), R, out,
+                                                                         jw_of(s));
+        EHMM_CK(cudaGetLastError());
+        s->launches[KID_MT]++;
+    }
+    EHMM_CK(cudaEventRecord(s->ev, s->stream2));
+    s->mtj_pending = true;
     return EHMM_OK;
 }
 
@@ -452,14 +726,21 @@ int mt_prefetch_ranges(ehmm_session *s, int nr, const int64_t *lo, const int64_t
     EHMM_CK(cudaEventRecord(s->ev2, s->stream));
     EHMM_CK(cudaStreamWaitEvent(s->stream2, s->ev2, 0));
     const int64_t pos = s->rng_state[0];
-    for (int i = 0; i < nr; i++) {
+    int64_t qlo[GEN_MAXR + 1], qhi[GEN_MAXR + 1];
+    int m = 0;
+    for (int i = 0; i < nr && m < GEN_MAXR; i++) {
         if (n[i] <= 0) continue;
-        EHMM_TRY(mt_prepare_range(s, s->stream2, substream_of(s, pos + lo[i]) - margin, substream_of(s, pos + lo[i] + n[i] - 1) + margin));
+        qlo[m] = substream_of(s, pos + lo[i]) - margin;
+        qhi[m] = substream_of(s, pos + lo[i] + n[i] - 1) + margin;
+        m++;
     }
     if (total > 0) {
         const int64_t E = pos + total, st_lo = ((E - 1) / MT_N) * MT_N;
-        EHMM_TRY(mt_prepare_range(s, s->stream2, substream_of(s, st_lo) - margin, substream_of(s, E - 1) + margin));
+        qlo[m] = substream_of(s, st_lo) - margin;
+        qhi[m] = substream_of(s, E - 1) + margin;
+        m++;
     }
+    EHMM_TRY(mt_prepare_ranges(s, s->stream2, m, qlo, qhi));
     EHMM_CK(cudaEventRecord(s->ev, s->stream2));
     s->mtj_pending = true;
     return EHMM_OK;

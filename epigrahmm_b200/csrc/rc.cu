@@ -775,27 +775,63 @@ int rc_apply_block(ehmm_session *s, const RCSrc &S, double p, int nrep, const in
     EHMM_REQUIRE(s->rng_set || total == 0, EHMM_ERR_RNG, "rejection control needs the RNG state (ehmm_rng_set_state)");
     int64_t local = 0;
     for (int c = 0; c < S.columns; c++) local += s->rc_colcount[c];
-    EHMM_TRY(s->rc_unif.reserve(sizeof(uint32_t) * (size_t)(local + RC_UNIF_SLACK)));
     RCBase ub;
-    int64_t at = 0;
-    for (int c = 0; c < S.columns; c++) { ub.ubase[c] = at; at += s->rc_colcount[c]; }
+    const uint32_t *unif = nullptr;
+    // generated ahead on the side stream?  every column's slice (plus what the kernel stages past its end) must lie
+    // inside what was generated for it, relative to the same stream position
+    bool hit = total > 0 && s->specr_cols == S.columns && s->specr_epoch == s->rng_epoch;
+    for (int c = 0; hit && c < S.columns; c++)
+        hit = col_offsets[c] >= s->specr_lo[c] && col_offsets[c] + s->rc_colcount[c] + RC_UNIF_SLACK <= s->specr_lo[c] + s->specr_n[c];
     if (total > 0) {
         EHMM_TRY(upload_state_if_needed(s));
-        EHMM_TRY(mt_choose_stride(s, total));
-        for (int c = 0; c < S.columns; c++) {
+        for (int c = 0; c < S.columns; c++)
             EHMM_REQUIRE(col_offsets[c] >= 0 && col_offsets[c] + s->rc_colcount[c] <= total, EHMM_ERR_ARG,
                          "column %d: draws [%lld, %lld) outside [0, %lld)", c, (long long)col_offsets[c],
                          (long long)(col_offsets[c] + s->rc_colcount[c]), (long long)total);
-            EHMM_TRY(mt_generate_range(s, col_offsets[c], s->rc_colcount[c], s->rc_unif.as<uint32_t>() + ub.ubase[c]));
-        }
     }
-    EHMM_TRY((launch_apply<DIFF, uint32_t>(s, S, p, nrep, ub, s->rc_unif.as<uint32_t>())));
+    if (hit) {
+        EHMM_TRY(mt_wait_side(s));
+        unif = s->rc_unif_specr[s->specr_next ^ 1].as<uint32_t>();
+        for (int c = 0; c < S.columns; c++) ub.ubase[c] = s->specr_off[c] + (col_offsets[c] - s->specr_lo[c]);
+    } else {
+        EHMM_TRY(s->rc_unif.reserve(sizeof(uint32_t) * (size_t)(local + RC_UNIF_SLACK)));
+        int64_t at = 0;
+        for (int c = 0; c < S.columns; c++) { ub.ubase[c] = at; at += s->rc_colcount[c]; }
+        if (total > 0) {
+            // sub-stream length from THIS block's draws: its column slices together should keep a few hundred generating
+            // CTAs busy (sized from the global total, a slice was a handful of sub-streams and the launch a handful of CTAs)
+            EHMM_TRY(mt_choose_stride(s, local));
+            int64_t out_off[RC_MAXCOL];
+            for (int c = 0; c < S.columns; c++) out_off[c] = ub.ubase[c];
+            EHMM_TRY(mt_generate_ranges(s, S.columns, col_offsets, s->rc_colcount, out_off, s->rc_unif.as<uint32_t>()));
+        }
+        unif = s->rc_unif.as<uint32_t>();
+    }
+    s->specr_cols = 0;
+    EHMM_TRY((launch_apply<DIFF, uint32_t>(s, S, p, nrep, ub, unif)));
     if (total > 0) {
         // side stream: the stream's state after all ranks' draws, then the windows of the next call's
         // slice, which sits where this one's did, give or take a few thousand draws
         EHMM_TRY(mt_advance_side(s, total, s->h_pinned + 512));
         rng_note_advance(s, total);
-        EHMM_TRY(mt_prefetch_ranges(s, S.columns, col_offsets, s->rc_colcount, total, 2));
+        EHMM_TRY(mt_choose_stride(s, local));
+        // ... and the slices themselves, with a margin of 1/16 of a slice (at least 2^17 words) either side
+        int64_t lo[RC_MAXCOL], n[RC_MAXCOL], off[RC_MAXCOL], words = 0;
+        for (int c = 0; c < S.columns; c++) {
+            const int64_t m = std::max<int64_t>(131072, s->rc_colcount[c] / 16);
+            lo[c] = std::max<int64_t>(0, col_offsets[c] - m);
+            n[c] = (col_offsets[c] - lo[c]) + s->rc_colcount[c] + m + RC_UNIF_SLACK;
+            off[c] = words;
+            words += n[c];
+        }
+        DevBuf &buf = s->rc_unif_specr[s->specr_next];
+        EHMM_TRY(buf.reserve(sizeof(uint32_t) * (size_t)(words + words / 8)));
+        EHMM_TRY(mt_prefetch_ranges(s, S.columns, lo, n, total, 1));
+        EHMM_TRY(mt_speculate_ranges(s, S.columns, lo, n, off, buf.as<uint32_t>()));
+        for (int c = 0; c < S.columns; c++) { s->specr_lo[c] = lo[c]; s->specr_n[c] = n[c]; s->specr_off[c] = off[c]; }
+        s->specr_cols = S.columns;
+        s->specr_epoch = s->rng_epoch;
+        s->specr_next ^= 1;
     }
     s->rc_count_cols = 0;
     return EHMM_OK;
@@ -804,6 +840,7 @@ int rc_apply_block(ehmm_session *s, const RCSrc &S, double p, int nrep, const in
 }  // namespace
 
 void rng_note_advance(ehmm_session *s, int64_t n) {
+    s->rng_epoch++;
     const int64_t E = (int64_t)s->rng_state[0] + n;  // R: mti counts the words used of the current block of 624
     s->rng_state[0] = (uint32_t)(E <= 624 ? E : (E - 1) % 624 + 1);
     s->rng_pending = true;

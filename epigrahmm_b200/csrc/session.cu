@@ -267,7 +267,7 @@ int ehmm_session_close(ehmm_session *s) {
     DevBuf *bufs[] = {&s->counts_own, &s->offsets_own, &s->controls_own, &s->group, &s->u_chip, &s->u_off, &s->u_ctrl,
                       &s->u_dsg, &s->logf, &s->logFP, &s->logBP, &s->logProb1, &s->logProb2, &s->prob1, &s->logf_alt, &s->eta, &s->viterbi, &s->vit_bp, &s->vit_work, &s->peak_work, &s->peak_calls,
                       &s->tileops, &s->carries, &s->tilestats, &s->fbscal, &s->rangeops, &s->rangecarry, &s->rc_flag, &s->rc_scan,
-                      &s->rc_buckets, &s->rc_limbs, &s->rc_coltot, &s->rc_static, &s->rc_unif, &s->rc_unif_spec, &s->rc_tmp, &s->mt_raw, &s->mt_raw2, &s->mt_windows, &s->gtab, &s->glm_ticket, &s->inner_part, &s->lgtab, &s->glm_part, &s->misc};
+                      &s->rc_buckets, &s->rc_limbs, &s->rc_coltot, &s->rc_static, &s->rc_unif, &s->rc_unif_spec, &s->rc_unif_specr[0], &s->rc_unif_specr[1], &s->rc_tmp, &s->mt_raw, &s->mt_raw2, &s->mt_windows, &s->gtab, &s->glm_ticket, &s->inner_part, &s->lgtab, &s->glm_part, &s->misc};
     for (DevBuf *b : bufs) b->release();
     for (int i = 0; i < 2; i++) {
         s->stage[i].release();
@@ -915,6 +915,8 @@ int ehmm_rng_set_state(ehmm_session *s, const uint32_t *state625) {
     EHMM_REQUIRE(state625[0] <= 624, EHMM_ERR_ARG, "mti = %u out of range", state625[0]);
     memcpy(s->rng_state, state625, sizeof(uint32_t) * 625);
     s->rng_set = true;
+    s->rng_epoch++;
+    s->specr_cols = 0;
     s->rng_dev_valid = false;
     s->rng_pending = false;
     s->spec_n = 0;
