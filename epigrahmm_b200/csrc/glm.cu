@@ -194,36 +194,68 @@ struct MixPar {
     int B;
 };
 
-// out: [0] = value, [1..4] = gradient wrt (b, db, l, dl)
+// out: [0] = value, [1..4] = gradient wrt (b, db, l, dl).
+// One thread per dtUnique row: a row's count and offset are shared by all B + 2 tables, and a table entry enters
+// with the D = 0 or the D = 1 density only, so the two densities (and their digammas) are evaluated once per row and
+// weighted by the row's summed D = 0 / D = 1 weights -- (B + 2) / 2 times less transcendental work than one
+// evaluation per table entry.  The last block to finish (ticket) adds the block partials in a fixed order and stores
+// the five sums in the host's mapped result slot, then the epoch flag the host polls.
 __global__ void __launch_bounds__(GLM_NT)
     glm_mix_kernel(int64_t G, int ncol, const double *__restrict__ buckets, const double *__restrict__ y,
-                   const double *__restrict__ off, const uint8_t *__restrict__ dsg, MixPar P, double *__restrict__ part) {
+                   const double *__restrict__ off, const uint8_t *__restrict__ dsg, MixPar P, double *__restrict__ part,
+                   unsigned *__restrict__ ticket, double *__restrict__ hout, unsigned epoch) {
     double acc[5] = {0, 0, 0, 0, 0};
-    const int64_t total = (int64_t)ncol * (G + 1);
-    for (int64_t idx = (int64_t)blockIdx.x * GLM_NT + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * GLM_NT) {
-        const double w = buckets[idx];
-        if (w == 0.0) continue;
-        const int c = (int)(idx / (G + 1));
-        const int64_t g = idx - (int64_t)c * (G + 1);
-        int D;
-        if (c == 0) D = 0;
-        else if (c == ncol - 1) D = 1;
-        else D = dsg[g + (int64_t)(c - 1) * (G + 1)];
-        const double yy = y[g];
-        // background: b + off; mixture: (b + db*D) + off; enrichment: (b + db) + off  -- same values
-        const double eta = (D ? (P.b + P.db) : P.b) + off[g];
-        const double mu = exp(eta), ph = P.size[D];
-        const double lpmf = nb_logpmf_direct(yy, eta, ph, P.lsize[D], P.lgs[D]);
-        const double lv = (lpmf > P.thr) ? lpmf : log(exp(lpmf) + P.minZero);
-        acc[0] += -w * lv;
-        const double a = -w * (yy / mu - ((yy + ph) / (mu + ph))) * mu;
-        const double cc = -w * (digamma_pos(yy + ph) - P.dg[D] + 1.0 + P.lsize[D] - (yy + ph) / (mu + ph) - log(mu + ph)) * ph;
-        acc[1] += a;
-        acc[2] += a * D;
-        acc[3] += cc;
-        acc[4] += cc * D;
+    for (int64_t g = 1 + (int64_t)blockIdx.x * GLM_NT + threadIdx.x; g <= G; g += (int64_t)gridDim.x * GLM_NT) {
+        double W[2] = {buckets[g], buckets[(int64_t)(ncol - 1) * (G + 1) + g]};  // background: D = 0; enrichment: D = 1
+        for (int c = 1; c < ncol - 1; c++) {
+            const double w = buckets[(int64_t)c * (G + 1) + g];
+            if (w != 0.0) W[dsg[g + (int64_t)(c - 1) * (G + 1)] ? 1 : 0] += w;
+        }
+        if (W[0] == 0.0 && W[1] == 0.0) continue;
+        const double yy = y[g], o = off[g];
+#pragma unroll
+        for (int D = 0; D < 2; D++) {
+            const double w = W[D];
+            if (w == 0.0) continue;
+            // background: b + off; mixture: (b + db*D) + off; enrichment: (b + db) + off  -- same values
+            const double eta = (D ? (P.b + P.db) : P.b) + o;
+            const double mu = exp(eta), ph = P.size[D];
+            const double lpmf = nb_logpmf_direct(yy, eta, ph, P.lsize[D], P.lgs[D]);
+            const double lv = (lpmf > P.thr) ? lpmf : log(exp(lpmf) + P.minZero);
+            acc[0] += -w * lv;
+            const double a = -w * (yy / mu - ((yy + ph) / (mu + ph))) * mu;
+            const double cc = -w * (digamma_pos(yy + ph) - P.dg[D] + 1.0 + P.lsize[D] - (yy + ph) / (mu + ph) - log(mu + ph)) * ph;
+            acc[1] += a;
+            acc[3] += cc;
+            if (D) { acc[2] += a; acc[4] += cc; }
+        }
     }
     block_store<5>(acc, part);
+    __shared__ bool is_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (is_last) {
+        __shared__ double red[GLM_NT];
+        for (int c = 0; c < 5; c++) {
+            double t = 0.0;
+            for (int i = threadIdx.x; i < (int)gridDim.x; i += GLM_NT) t += __ldcg(part + (size_t)i * 5 + c);
+            red[threadIdx.x] = t;
+            __syncthreads();
+            for (int d = GLM_NT / 2; d > 0; d >>= 1) {
+                if ((int)threadIdx.x < d) red[threadIdx.x] += red[threadIdx.x + d];
+                __syncthreads();
+            }
+            if (threadIdx.x == 0) hout[c] = red[0];  // zero-copy: straight into the host's mapped result slot
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            *ticket = 0u;
+            __threadfence_system();
+            *reinterpret_cast<volatile unsigned *>(hout + 63) = epoch;
+        }
+    }
 }
 
 // glmMixZINB / derivMixZINB (R/base-optim.R:261-362): rows of column 0 (background) and mixture rows
@@ -327,6 +359,35 @@ int finish(ehmm_session *s, int nblk, int nout, double *host_out) {
 int glm_nb_batch(ehmm_session *s, int ncols, const int *columns, const double *pars, int P_, double *values,
                  double *grads);
 
+// wait for a kernel's epoch in the mapped result slot (a few microseconds after it ends) instead of a copy + stream
+// synchronisation; a kernel that never reports falls back to the synchronising path for the error
+static int poll_epoch(ehmm_session *s, unsigned epoch, const char *who) {
+    volatile unsigned *flag = reinterpret_cast<volatile unsigned *>(s->h_glm + 63);
+    const auto t0 = std::chrono::steady_clock::now();
+    unsigned spins = 0;
+    while (*flag != epoch) {
+        if ((++spins & 0x3ff) == 0) {
+            if (cudaStreamQuery(s->stream) != cudaErrorNotReady) break;  // finished (or failed) without the flag
+            if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(30)) break;
+        }
+    }
+    if (*flag != epoch) {
+        EHMM_CK(cudaStreamSynchronize(s->stream));
+        EHMM_REQUIRE(*flag == epoch, EHMM_ERR_CUDA, "%s: the kernel did not report its result", who);
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    return EHMM_OK;
+}
+
+static int ensure_ticket(ehmm_session *s) {
+    if (!s->glm_ticket_ready) {
+        EHMM_TRY(s->glm_ticket.reserve(64));
+        EHMM_CK(cudaMemsetAsync(s->glm_ticket.p, 0, 64, s->stream));
+        s->glm_ticket_ready = true;
+    }
+    return EHMM_OK;
+}
+
 int glm_nb(ehmm_session *s, int column, const double *par, int P_, double *value, double *grad) {
     return glm_nb_batch(s, 1, &column, par, P_, value, grad);
 }
@@ -353,13 +414,9 @@ int glm_nb_batch(ehmm_session *s, int ncols, const int *columns, const double *p
         B.column[q] = columns[q];
     }
     const int nblk = blocks_for(s->G);
-    const size_t need = sizeof(double) * ((size_t)EHMM_MAX_K * 148 * 4 * 4 + EHMM_MAX_K * 4) + 64;
-    if (s->glm_part.bytes < need || !s->glm_ticket_ready) {
-        EHMM_TRY(s->glm_part.reserve(need > sizeof(double) * ((size_t)148 * 4 * GLM_MAXOUT + GLM_MAXOUT) ? need : sizeof(double) * ((size_t)148 * 4 * GLM_MAXOUT + GLM_MAXOUT)));
-        EHMM_TRY(s->glm_ticket.reserve(64));
-        EHMM_CK(cudaMemsetAsync(s->glm_ticket.p, 0, 64, s->stream));
-        s->glm_ticket_ready = true;
-    }
+    EHMM_TRY(s->glm_part.reserve(sizeof(double) * ((size_t)EHMM_MAX_K * 148 * 4 * 4 + EHMM_MAX_K * 4) + 64 +
+                                 sizeof(double) * ((size_t)148 * 4 * GLM_MAXOUT + GLM_MAXOUT)));
+    EHMM_TRY(ensure_ticket(s));
     double *part = s->glm_part.as<double>();
     double *out = part + (size_t)EHMM_MAX_K * 148 * 4 * 4;
     dim3 grid((unsigned)nblk, (unsigned)ncols);
@@ -368,24 +425,7 @@ int glm_nb_batch(ehmm_session *s, int ncols, const int *columns, const double *p
         s->G, s->rc_buckets.as<double>(), s->u_chip.as<double>(), s->u_off.as<double>(), s->u_ctrl.as<double>(), B, part,
         s->glm_ticket.as<unsigned>(), out, s->d_glm, epoch);
     EHMM_CK(cudaGetLastError());
-    // poll the mapped flag (a few microseconds after the kernel ends) instead of a copy + stream
-    // synchronisation; a kernel that never reports falls back to the synchronising path for the error
-    {
-        volatile unsigned *flag = reinterpret_cast<volatile unsigned *>(s->h_glm + 63);
-        const auto t0 = std::chrono::steady_clock::now();
-        unsigned spins = 0;
-        while (*flag != epoch) {
-            if ((++spins & 0x3ff) == 0) {
-                if (cudaStreamQuery(s->stream) != cudaErrorNotReady) break;  // finished (or failed) without the flag
-                if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(30)) break;
-            }
-        }
-        if (*flag != epoch) {
-            EHMM_CK(cudaStreamSynchronize(s->stream));
-            EHMM_REQUIRE(*flag == epoch, EHMM_ERR_CUDA, "glmNB batch: the kernel did not report its result");
-        }
-        std::atomic_thread_fence(std::memory_order_acquire);
-    }
+    EHMM_TRY(poll_epoch(s, epoch, "glmNB batch"));
     for (int q = 0; q < ncols; q++) {
         const double *o = s->h_glm + 4 * q;
         values[q] = -o[0];
@@ -455,18 +495,20 @@ int glm_mix_nb(ehmm_session *s, const double *par, double minZero, double *value
         P.lgs[D] = lgamma(P.size[D]);
         P.dg[D] = host_digamma(P.size[D]);
     }
-    EHMM_TRY(s->glm_part.reserve(sizeof(double) * ((size_t)148 * 4 * GLM_MAXOUT + GLM_MAXOUT)));
+    EHMM_TRY(s->glm_part.reserve(sizeof(double) * ((size_t)EHMM_MAX_K * 148 * 4 * 4 + EHMM_MAX_K * 4) + 64 +
+                                 sizeof(double) * ((size_t)148 * 4 * GLM_MAXOUT + GLM_MAXOUT)));
+    EHMM_TRY(ensure_ticket(s));
     const int ncol = s->B + 2;
-    const int nblk = blocks_for((int64_t)ncol * (s->G + 1));
+    const int nblk = blocks_for(s->G);
+    const unsigned epoch = ++s->glm_epoch ? s->glm_epoch : ++s->glm_epoch;  // never 0
     PROF(s, KID_GLM), glm_mix_kernel<<<nblk, GLM_NT, 0, s->stream>>>(s->G, ncol, s->rc_buckets.as<double>(), s->u_chip.as<double>(),
-                                                  s->u_off.as<double>(), s->u_dsg.as<uint8_t>(), P,
-                                                  s->glm_part.as<double>());
+                                                  s->u_off.as<double>(), s->u_dsg.as<uint8_t>(), P, s->glm_part.as<double>(),
+                                                  s->glm_ticket.as<unsigned>() + 8, s->d_glm, epoch);
     EHMM_CK(cudaGetLastError());
-    double o[5];
-    EHMM_TRY(finish(s, nblk, 5, o));
-    *value = o[0];
+    EHMM_TRY(poll_epoch(s, epoch, "glmMixNB"));
+    *value = s->h_glm[0];
     if (grad)
-        for (int i = 0; i < 4; i++) grad[i] = o[1 + i];
+        for (int i = 0; i < 4; i++) grad[i] = s->h_glm[1 + i];
     return EHMM_OK;
 }
 

@@ -109,18 +109,20 @@ __global__ void __launch_bounds__(RC_NT) rc_count_kernel(RCSrc S, double p, int6
 
 // one CTA per column: exclusive scan of the column's n tile counts -> offsets (uint32: a column of one
 // bin block holds < 2^32 bins), coltot[column] = the column's total.  Each thread owns 16 consecutive
-// counts per round (warp-shuffle scan of the thread sums, then of the warp sums).
-__global__ void __launch_bounds__(1024) rc_scan_kernel(const int *__restrict__ counts_all, int64_t n,
-                                                       uint32_t *__restrict__ offsets_all, int64_t *__restrict__ coltot) {
-    constexpr int IT = 16;
-    __shared__ int64_t swarp[32];
+// counts per round (warp-shuffle scan of the thread sums, then of the warp sums).  256 threads: a CTA of
+// 1024 does not fit next to the side stream's resident CTAs and waited for them to drain (0.2 ms per call).
+constexpr int SCAN_NT = 256;
+__global__ void __launch_bounds__(SCAN_NT) rc_scan_kernel(const int *__restrict__ counts_all, int64_t n,
+                                                          uint32_t *__restrict__ offsets_all, int64_t *__restrict__ coltot) {
+    constexpr int IT = 16, NW = SCAN_NT / 32;
+    __shared__ int64_t swarp[NW];
     __shared__ int64_t carry;
     const int *counts = counts_all + (int64_t)blockIdx.x * n;
     uint32_t *offsets = offsets_all + (int64_t)blockIdx.x * n;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     if (threadIdx.x == 0) carry = 0;
     __syncthreads();
-    for (int64_t base = 0; base < n; base += 1024 * IT) {
+    for (int64_t base = 0; base < n; base += SCAN_NT * IT) {
         const int64_t i0 = base + (int64_t)threadIdx.x * IT;
         int v[IT];
         int64_t tsum = 0;
@@ -137,24 +139,21 @@ __global__ void __launch_bounds__(1024) rc_scan_kernel(const int *__restrict__ c
         }
         if (lane == 31) swarp[w] = incl;
         __syncthreads();
-        if (w == 0) {
-            int64_t x = swarp[lane];
+        int64_t before = 0, all = 0;  // the warps in front of this one; the whole round
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const int64_t t = __shfl_up_sync(0xffffffffu, x, d);
-                if (lane >= d) x += t;
-            }
-            swarp[lane] = x;  // inclusive sums of the warps
+        for (int i = 0; i < NW; i++) {
+            const int64_t t = swarp[i];
+            if (i < w) before += t;
+            all += t;
         }
-        __syncthreads();
-        int64_t run = carry + (w > 0 ? swarp[w - 1] : 0) + (incl - tsum);
+        int64_t run = carry + before + (incl - tsum);
 #pragma unroll
         for (int k = 0; k < IT; k++) {
             if (i0 + k < n) offsets[i0 + k] = (uint32_t)run;
             run += v[k];
         }
         __syncthreads();
-        if (threadIdx.x == 0) carry += swarp[31];
+        if (threadIdx.x == 0) carry += all;
         __syncthreads();
     }
     if (threadIdx.x == 0) coltot[blockIdx.x] = carry;
@@ -596,7 +595,7 @@ template <bool DIFF> int count_and_scan(ehmm_session *s, const RCSrc &S, double 
         s->rc_counts_p = p;
         s->rc_counts_cols = S.columns;
     }
-    PROF(s, KID_RC_SCAN), rc_scan_kernel<<<S.columns, 1024, 0, s->stream>>>(s->rc_flag.as<int>(), nwt, s->rc_scan.as<uint32_t>(),
+    PROF(s, KID_RC_SCAN), rc_scan_kernel<<<S.columns, SCAN_NT, 0, s->stream>>>(s->rc_flag.as<int>(), nwt, s->rc_scan.as<uint32_t>(),
                                                                            s->rc_coltot.as<int64_t>());
     EHMM_CK(cudaGetLastError());
     int64_t *hp = reinterpret_cast<int64_t *>(s->h_pinned + 200);

@@ -4,6 +4,7 @@
 #include "common.cuh"
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <map>
 #include <mutex>
@@ -215,9 +216,16 @@ int ehmm_session_open(const char *key, int64_t M, int K, int device, ehmm_sessio
     s->M = M;
     s->Mtot = M;
     s->K = K;
-    EHMM_CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
-    EHMM_CK(cudaStreamCreateWithFlags(&s->stream2, cudaStreamNonBlocking));
-    EHMM_CK(cudaStreamCreateWithFlags(&s->stream_up, cudaStreamNonBlocking));
+    {   // the EM iteration's own kernels go first; what runs ahead of need (uniform generation, jump windows, static
+        // table parts, staged uploads) fills the machine behind them
+        int lo = 0, hi = 0;
+        EHMM_CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        const char *e = getenv("EHMM_STREAM_PRIORITY");
+        const bool prio = !(e && e[0] == '0');
+        EHMM_CK(cudaStreamCreateWithPriority(&s->stream, cudaStreamNonBlocking, prio ? hi : lo));
+        EHMM_CK(cudaStreamCreateWithPriority(&s->stream2, cudaStreamNonBlocking, lo));
+        EHMM_CK(cudaStreamCreateWithPriority(&s->stream_up, cudaStreamNonBlocking, lo));
+    }
     for (int i = 0; i < 2; i++) {
         EHMM_CK(cudaEventCreateWithFlags(&s->ev_up[i], cudaEventDisableTiming));
         EHMM_CK(cudaEventCreateWithFlags(&s->ev_used[i], cudaEventDisableTiming));
