@@ -529,8 +529,8 @@ __global__ void __launch_bounds__(NT, FBCfg<K>::APPLY_CTAS)
                     double *__restrict__ row0, const LeanOut lean) {
     constexpr int TB = NT * L, NW = NT / 32, OPN = K * K + 1, NS = K * K + 1;
     extern __shared__ double smem[];
-    double2 *sT = reinterpret_cast<double2 *>(smem);  // 128 entries of the log table
-    double *sM = smem + 256;       // TB    per-bin max
+    double2 *sT = reinterpret_cast<double2 *>(smem);  // 128 entries of the log table (not in the lean form: 4 CTAs fit then)
+    double *sM = smem + (LEAN ? 0 : 256);  // TB    per-bin max
     double *sA = sM + TB;          // K*TB  e_j, then alpha~_j (post-emission, chunk scale)
     double *sB = sA + K * TB;      // K*TB  beta~_j
     double *sScF = sM;             // the forward pass replaces m_j by the tile-local log scale of alpha~_j
@@ -972,10 +972,10 @@ template <int K> size_t reduce_smem() {
     using C = FBCfg<K>;
     return sizeof(double) * ((size_t)(K + 1) * C::NT * C::L + (C::NT / 32) * (K * K + 1));
 }
-template <int K> size_t apply_smem() {
+template <int K> size_t apply_smem(bool lean = false) {
     using C = FBCfg<K>;
     size_t TB = (size_t)C::NT * C::L;
-    return sizeof(double) * (256 + (2 * K + 1) * TB + C::NT + (TB / 32) * K + (C::NT / 32) * (K * K + 1));
+    return sizeof(double) * ((lean ? 0 : 256) + (2 * K + 1) * TB + C::NT + (TB / 32) * K + (C::NT / 32) * (K * K + 1));
 }
 
 void fill_params(const ehmm_session *s, FBParams &P) {
@@ -1091,7 +1091,7 @@ template <int K> int launch_apply(ehmm_session *s, const double *d_logf, const C
             lo.pcut = s->rc_hint_p;
             s->fb_counted = true;
         }
-        PROF(s, KID_FB_APPLY_LEAN), fb_apply_kernel<K, C::NT, C::L, true><<<(unsigned)nT, C::NT, apply_smem<K>(), s->stream>>>(
+        PROF(s, KID_FB_APPLY_LEAN), fb_apply_kernel<K, C::NT, C::L, true><<<(unsigned)nT, C::NT, apply_smem<K>(true), s->stream>>>(
             d_logf, s->M, first, P, s->carries.as<double>(), nullptr, nullptr, nullptr, nullptr, s->tilestats.as<double>(), row0, lo);
         EHMM_CK(cudaGetLastError());
     } else {

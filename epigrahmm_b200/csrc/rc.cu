@@ -298,7 +298,7 @@ __device__ __forceinline__ void rc_load_raw(const RCSrc &S, const int32_t *__res
 }
 
 template <bool DIFF, typename UT, bool EXACT, bool SKIPST, int CMAX>
-__global__ void __launch_bounds__(RC_NT, CMAX == 0 ? 1 : (CMAX <= 2 ? 4 : (CMAX <= 8 ? 4 : 3)))
+__global__ void __launch_bounds__(RC_NT, CMAX == 0 ? 1 : (CMAX <= 8 ? 4 : 3))
     rc_apply_kernel(RCSrc S, RCCut cut, int64_t nwt, const uint32_t *__restrict__ tileoff, const __grid_constant__ RCBase ub,
                     const UT *__restrict__ unif, const int32_t *__restrict__ group, int nrep, int64_t G,
                     const RCAcc A, const int *__restrict__ counts, int *__restrict__ err) {
