@@ -302,6 +302,7 @@ __global__ void __launch_bounds__(EM_NT, (GROUPED && BMAX <= 14) ? 3 : 1)
                 p1 = lp1 ? rc_post(__ldg(lp1 + M + j), lin) : 0.0;
                 acc[BMAX] += p1;
             }
+            const double rs = valid ? 1.0 / s : 0.0;
             if (COUNT) {
                 const double w0 = valid ? rc_post(__ldg(lp1 + j), lin) : 2.0;  // 2.0: never below a cut <= 1
                 const int n = __popc(__ballot_sync(0xffffffffu, rc_flagged(w0, pcut)));
@@ -312,7 +313,9 @@ __global__ void __launch_bounds__(EM_NT, (GROUPED && BMAX <= 14) ? 3 : 1)
                 if (b < X.B) {
                     double e = 0.0;
                     if (valid) {
-                        e = v[b] / s;  // division as in the reference (exp(ll)/sumExpLL)
+                        // exp(ll) / sumExpLL as in the reference: the correctly rounded quotient from one reciprocal per
+                        // bin and Markstein's correction (rc_div_cut; exact unless the significand of the sum is all ones)
+                        e = rc_div_cut(v[b], s, rs);
                         eta[j + (int64_t)b * M] = e;
                         acc[b] = fma(p1, e, acc[b]);
                     }
