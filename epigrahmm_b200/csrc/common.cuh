@@ -318,6 +318,7 @@ int rc_count(ehmm_session *s, int differential, double p, int64_t *counts);
 int rc_apply_at(ehmm_session *s, int differential, double p, const int64_t *col_offsets, int64_t total);
 int rc_finalize(ehmm_session *s);
 int64_t rc_limb_words(const ehmm_session *s);
+int rc_fold(ehmm_session *s, int64_t *words);
 int rc_static_prefetch(ehmm_session *s);
 int rc_table_rows(ehmm_session *s, int column, int64_t *rows);
 int rc_table_fetch(ehmm_session *s, int column, double *sums, double *ids);

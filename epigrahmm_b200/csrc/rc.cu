@@ -213,7 +213,7 @@ template <> __device__ __forceinline__ double get_unif<uint32_t>(const uint32_t 
 //   all): their adds are spread over RC_REP replicas chosen by the warp tile, and the finalisation adds
 //   the replicas up -- integer additions, so the split changes nothing in the result.
 constexpr int RC_HOT = 4096;
-constexpr int RC_REP = 8;
+constexpr int RC_REP = 32;
 
 struct RCAcc {
     unsigned long long *w;  // the accumulator set
@@ -872,6 +872,16 @@ struct TmpDev {
 }  // namespace
 
 int64_t rc_limb_words(const ehmm_session *s) { return (int64_t)rc_acc_words(s->rc_columns, s->G); }
+
+// the replicas of the frequent groups added into the main limb arrays (and cleared): what is left to exchange
+// between bin blocks is the two plain arrays, 2 * columns * (G + 1) words
+int rc_fold(ehmm_session *s, int64_t *words) {
+    const RCAcc A = rc_acc(s->rc_limbs.as<unsigned long long>(), s->rc_columns, s->G);
+    PROF(s, KID_RC_FINAL), rc_fold_kernel<<<(unsigned)((s->rc_columns * A.hot + 255) / 256), 256, 0, s->stream>>>(A, s->rc_columns, s->G);
+    EHMM_CK(cudaGetLastError());
+    *words = 2 * A.cells;
+    return EHMM_OK;
+}
 
 // limbs -> fp64 tables (no-op when the tables were accumulated in fp64 or are already final)
 int rc_finalize(ehmm_session *s) {

@@ -975,8 +975,9 @@ int ehmm_rc_buckets_device(ehmm_session *s, void **ptr, int64_t *n, int *is_inte
     EHMM_REQUIRE(s->rc_columns > 0, EHMM_ERR_STATE, "no rejection tables");
     const int64_t cells = (int64_t)s->rc_columns * (s->G + 1);
     if (s->rc_exact) {
+        EHMM_TRY(check_session(s));
         *ptr = s->rc_limbs.p;
-        *n = rc_limb_words(s);  // both limb arrays and the replicas of the frequent groups
+        EHMM_TRY(rc_fold(s, n));  // the replicas of the frequent groups are folded in: two plain limb arrays remain
         *is_integer = 1;
         s->rc_final = false;  // the caller is about to change the limbs: round them again
     } else {

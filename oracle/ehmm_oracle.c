@@ -24,7 +24,16 @@
  *   [EXT-R]    digamma (R uses AMOS dpsifn; here: recurrence + asymptotic
  *              series, checked against scipy/mpmath to 1e-14 in tests).
  *   [EXT-ARMA] Armadillo accu() two-accumulator order, zero-filled mat(),
- *              index_max first-maximum -- Armadillo 10.5+.
+ *              index_max first-maximum -- Armadillo 10.5+.  The order restated
+ *              here is Armadillo's single-threaded one.  src/Makevars:15-16
+ *              passes the OpenMP flags, and with ARMA_USE_OPENMP
+ *              accu(exp(...)) over a large matrix (src/maxStepProb.cpp:60,63)
+ *              takes Armadillo's multi-threaded path, whose summation order
+ *              depends on the thread count: "bit-faithful" for maxStepProb and
+ *              computeQFunction can therefore only mean "to the rounding of a
+ *              differently ordered sum" (~1e-16 * sqrt(M) relative), which is
+ *              what the 1e-9 gates allow for.
+ *   [EXT-R]    cumsum() (fdrControl): long double accumulation, doubles stored.
  * dnbinom is additionally pinned against the closed forms used by the
  * reference's only emission KAT (tests/testthat/test-base.R:6-42) and
  * against scipy.stats.nbinom in tests/.
