@@ -935,7 +935,7 @@ __global__ void __launch_bounds__(256) fb_stats_kernel(const double *__restrict_
 // i.e. maxStepProb / computeQFunction called on their own inputs as the reference allows)
 template <int K>
 __global__ void __launch_bounds__(256)
-    fb_stats_from_datasets_kernel(int64_t M, const double *__restrict__ logf, const double *__restrict__ lp1,
+    fb_stats_from_datasets_kernel(int64_t M, int skip_first, const double *__restrict__ logf, const double *__restrict__ lp1,
                                   const double *__restrict__ lp2, double *__restrict__ part) {
     constexpr int NS = K * K + 1;
     __shared__ double sh[8 * NS];
@@ -943,7 +943,7 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
     for (int i = 0; i < NS; i++) acc[i] = 0.0;
     for (int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x; j < M; j += (int64_t)gridDim.x * 256) {
-        if (j >= 1) {
+        if (j >= skip_first) {  // the chain's first bin has no transition into it; a later block's first bin has
 #pragma unroll
             for (int c = 0; c < K * K; c++) acc[c] += exp(__ldg(lp2 + (int64_t)c * M + j));
         }
@@ -1172,7 +1172,7 @@ template <int K> int fetch_stats_impl(ehmm_session *s) {
         const bool p12 = has(s, DS_P1 | DS_P2);
         if (p12) {
             PROF(s, KID_MISC), fb_stats_from_datasets_kernel<K><<<nblk, 256, 0, s->stream>>>(
-                s->M, has(s, DS_LOGF) ? s->logf.as<double>() : nullptr, s->logProb1.as<double>(),
+                s->M, s->m0 == 0 ? 1 : 0, has(s, DS_LOGF) ? s->logf.as<double>() : nullptr, s->logProb1.as<double>(),
                 s->logProb2.as<double>(), s->tilestats.as<double>());
             EHMM_CK(cudaGetLastError());
             PROF(s, KID_FB_STATS), fb_stats_kernel<<<NS, 256, 0, s->stream>>>(s->tilestats.as<double>(), nblk, NS,

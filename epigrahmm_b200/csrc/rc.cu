@@ -31,6 +31,9 @@
 #include "common.cuh"
 #include "rcweights.cuh"
 #include <algorithm>
+#include <chrono>
+#include <stdio.h>
+#include <stdlib.h>
 #include <vector>
 
 namespace ehmm {
@@ -712,7 +715,7 @@ int run_rc(ehmm_session *s, const RCSrc &S, double p, int nrep, const double *un
     if (uniforms) {
         EHMM_REQUIRE(total <= n_uniforms, EHMM_ERR_RNG, "rejection control needs %lld uniforms, buffer holds %lld",
                      (long long)total, (long long)n_uniforms);
-        EHMM_TRY(s->rc_unif.reserve(sizeof(double) * (size_t)(total + RC_UNIF_SLACK)));
+        EHMM_TRY(s->rc_unif.reserve_growing(sizeof(double) * (size_t)(total + RC_UNIF_SLACK)));
         if (total > 0)
             EHMM_CK(cudaMemcpyAsync(s->rc_unif.p, uniforms, sizeof(double) * total, cudaMemcpyHostToDevice, s->stream));
         EHMM_TRY((launch_apply<DIFF, double>(s, S, p, nrep, ub, s->rc_unif.as<double>())));
@@ -727,7 +730,7 @@ int run_rc(ehmm_session *s, const RCSrc &S, double p, int nrep, const double *un
                 std::swap(s->rc_unif, s->rc_unif_spec);
             } else {
                 EHMM_TRY(mt_choose_stride(s, total));
-                EHMM_TRY(s->rc_unif.reserve(sizeof(uint32_t) * (size_t)(total + RC_UNIF_SLACK)));
+                EHMM_TRY(s->rc_unif.reserve_growing(sizeof(uint32_t) * (size_t)(total + RC_UNIF_SLACK)));
                 EHMM_TRY(mt_generate_range(s, 0, total, s->rc_unif.as<uint32_t>()));
             }
             s->spec_n = 0;
@@ -738,7 +741,7 @@ int run_rc(ehmm_session *s, const RCSrc &S, double p, int nrep, const double *un
             int64_t est = total + total / 4 + 2 * 131072;
             if (est > (int64_t)S.columns * s->M) est = (int64_t)S.columns * s->M;
             EHMM_TRY(mt_choose_stride(s, est));
-            EHMM_TRY(s->rc_unif_spec.reserve(sizeof(uint32_t) * (size_t)(est + RC_UNIF_SLACK)));
+            EHMM_TRY(s->rc_unif_spec.reserve_growing(sizeof(uint32_t) * (size_t)(est + RC_UNIF_SLACK)));
             EHMM_TRY(mt_speculate(s, est, s->rc_unif_spec.as<uint32_t>()));
             s->spec_n = est;
         } else {
@@ -774,6 +777,14 @@ int rc_apply_block(ehmm_session *s, const RCSrc &S, double p, int nrep, const in
     EHMM_REQUIRE(s->rng_set || total == 0, EHMM_ERR_RNG, "rejection control needs the RNG state (ehmm_rng_set_state)");
     int64_t local = 0;
     for (int c = 0; c < S.columns; c++) local += s->rc_colcount[c];
+    static const bool trace = getenv("EHMM_TRACE") != nullptr;
+    auto t_prev = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) {
+        if (!trace) return;
+        const auto t = std::chrono::steady_clock::now();
+        fprintf(stderr, "[rc_apply_at] %-18s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t - t_prev).count());
+        t_prev = t;
+    };
     RCBase ub;
     const uint32_t *unif = nullptr;
     // generated ahead on the side stream?  every column's slice (plus what the kernel stages past its end) must lie
@@ -793,7 +804,7 @@ int rc_apply_block(ehmm_session *s, const RCSrc &S, double p, int nrep, const in
         unif = s->rc_unif_specr[s->specr_next ^ 1].as<uint32_t>();
         for (int c = 0; c < S.columns; c++) ub.ubase[c] = s->specr_off[c] + (col_offsets[c] - s->specr_lo[c]);
     } else {
-        EHMM_TRY(s->rc_unif.reserve(sizeof(uint32_t) * (size_t)(local + RC_UNIF_SLACK)));
+        EHMM_TRY(s->rc_unif.reserve_growing(sizeof(uint32_t) * (size_t)(local + RC_UNIF_SLACK)));
         int64_t at = 0;
         for (int c = 0; c < S.columns; c++) { ub.ubase[c] = at; at += s->rc_colcount[c]; }
         if (total > 0) {
@@ -807,13 +818,16 @@ int rc_apply_block(ehmm_session *s, const RCSrc &S, double p, int nrep, const in
         unif = s->rc_unif.as<uint32_t>();
     }
     s->specr_cols = 0;
+    lap(hit ? "uniforms (hit)" : "uniforms (miss)");
     EHMM_TRY((launch_apply<DIFF, uint32_t>(s, S, p, nrep, ub, unif)));
+    lap("launch_apply");
     if (total > 0) {
         // side stream: the stream's state after all ranks' draws, then the windows of the next call's
         // slice, which sits where this one's did, give or take a few thousand draws
         EHMM_TRY(mt_advance_side(s, total, s->h_pinned + 512));
         rng_note_advance(s, total);
         EHMM_TRY(mt_choose_stride(s, local));
+        lap("advance_side");
         // ... and the slices themselves, with a margin of 1/16 of a slice (at least 2^17 words) either side
         int64_t lo[RC_MAXCOL], n[RC_MAXCOL], off[RC_MAXCOL], words = 0;
         for (int c = 0; c < S.columns; c++) {
@@ -824,9 +838,12 @@ int rc_apply_block(ehmm_session *s, const RCSrc &S, double p, int nrep, const in
             words += n[c];
         }
         DevBuf &buf = s->rc_unif_specr[s->specr_next];
-        EHMM_TRY(buf.reserve(sizeof(uint32_t) * (size_t)(words + words / 8)));
+        EHMM_TRY(buf.reserve_growing(sizeof(uint32_t) * (size_t)words));
+        lap("reserve");
         EHMM_TRY(mt_prefetch_ranges(s, S.columns, lo, n, total, 1));
+        lap("prefetch_ranges");
         EHMM_TRY(mt_speculate_ranges(s, S.columns, lo, n, off, buf.as<uint32_t>()));
+        lap("speculate_ranges");
         for (int c = 0; c < S.columns; c++) { s->specr_lo[c] = lo[c]; s->specr_n[c] = n[c]; s->specr_off[c] = off[c]; }
         s->specr_cols = S.columns;
         s->specr_epoch = s->rng_epoch;

@@ -263,6 +263,8 @@ class ShardedSession:
         self.local = local if local is not None else Session("%s.rank%d" % (key, self.rank), M, K, device)
         self.local.set_block(self.m0, self.Mtot)
         self.M, self.K = M, K
+        self._hint = None        # rejection cut announced for the coming call (rc_hint)
+        self._counts = None      # (p, differential, counts of all blocks): gathered along with another exchange
 
     # plain delegation -----------------------------------------------------------------------
     def __getattr__(self, name):
@@ -270,6 +272,23 @@ class ShardedSession:
 
     def close(self):
         self.local.close()
+
+    def rc_hint(self, p):
+        """the cut of the coming rejection-control call (R/base-EM.R:119-121 knows it before the E-step): the kernels
+        that produce the posteriors count for it on the way, and the blocks' counts travel with the exchange that
+        follows those kernels anyway instead of in one of their own"""
+        self._hint = float(p)
+        if hasattr(self.local, "rc_hint"):
+            self.local.rc_hint(p)
+
+    def _early_counts(self, differential):
+        """this block's flagged counts for the announced cut, or None (no cut announced, no groups yet, ...)"""
+        if self._hint is None or not (self._hint > 0.0):
+            return None
+        try:
+            return np.asarray(self.local.rc_count(self._hint, differential), dtype=np.float64)
+        except Exception:
+            return None
 
     # data ------------------------------------------------------------------------------------
     def _share_controls_first(self, have):
@@ -290,6 +309,7 @@ class ShardedSession:
     # E-step ----------------------------------------------------------------------------------
     def expstep(self, pi, gamma, logf=None):
         K = self.K
+        self._counts = None
         op = self.local.expstep_reduce(pi, gamma, logf)
         ops = self.comm.all_gather(op)
         if hasattr(self.local, "expstep_apply_ops"):       # carries composed inside the library, no wait
@@ -301,15 +321,25 @@ class ShardedSession:
             tail = self.local.expstep_apply(fwd, bwd)      # forward vector after this block
             ll_local = float(tail[K] + np.log(np.sum(tail[:K])))
             stats = self.local.estep_stats()
-        # one exchange: statistics (summed), logProb1[0,] (first block's), log-likelihood (last block's)
-        packed = self.comm.all_gather(np.concatenate([stats, self.local.fetch_logprob1_row0(), [ll_local]]))
+        # one exchange: statistics (summed), logProb1[0,] (first block's), log-likelihood (last block's) and, for the
+        # consensus model, the flagged counts of the rejection control that follows (every block or none has them:
+        # the cut is announced on all ranks alike)
+        cnt = self._early_counts(False) if K == 2 else None
+        parts = [stats, self.local.fetch_logprob1_row0(), [ll_local]] + ([cnt] if cnt is not None else [])
+        packed = self.comm.all_gather(np.concatenate(parts))
         ns = K * K + 1
-        self.local.estep_set_stats(packed[:, :ns].sum(axis=0), packed[0, ns:ns + K], float(packed[-1, -1]))
+        self.local.estep_set_stats(packed[:, :ns].sum(axis=0), packed[0, ns:ns + K], float(packed[-1, ns + K]))
+        if cnt is not None:
+            self._counts = (self._hint, False, np.rint(packed[:, ns + K + 1:]).astype(np.int64))
 
     # rejection control -----------------------------------------------------------------------
     def _rc(self, p, differential):
-        cnt = self.local.rc_count(p, differential)
-        offs, total = rc_offsets(self.comm.all_gather(cnt), self.rank)
+        if self._counts is not None and self._counts[0] == p and self._counts[1] == differential:
+            allc = self._counts[2]          # gathered with the exchange behind the kernel that counted
+        else:
+            allc = self.comm.all_gather(self.local.rc_count(p, differential))
+        self._counts = None
+        offs, total = rc_offsets(allc, self.rank)
         self.local.rc_apply_at(p, offs, total, differential)
         if hasattr(self.local, "rc_buckets_host"):   # host-resident backend (CPU tests)
             self.local.rc_buckets_set(self.comm.all_reduce_sum(self.local.rc_buckets_host()))
@@ -330,8 +360,23 @@ class ShardedSession:
             raise ValueError("the sharded driver draws from the device generator")
         return self._rc(p, True)
 
+    def inner_expstep(self, *a, **k):
+        self._counts = None
+        return self.local.inner_expstep(*a, **k)
+
+    def inner_expstep_zinb(self, *a, **k):
+        self._counts = None
+        return self.local.inner_expstep_zinb(*a, **k)
+
     def inner_maxstepprob(self):
-        s = self.comm.all_reduce_sum(self.local.inner_mstep_sums())
+        sums = np.asarray(self.local.inner_mstep_sums(), dtype=np.float64)
+        cnt = self._early_counts(True)     # innerExpStep counted for the announced cut: one exchange for both
+        if cnt is None:
+            s = self.comm.all_reduce_sum(sums)
+        else:
+            packed = self.comm.all_gather(np.concatenate([sums, cnt]))
+            s = packed[:, :sums.size].sum(axis=0)
+            self._counts = (self._hint, True, np.rint(packed[:, sums.size:]).astype(np.int64))
         return s[:-1] / s[-1]
 
     def viterbi(self, pi, gamma, fetch=True):
