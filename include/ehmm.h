@@ -240,9 +240,10 @@ int ehmm_rc_count(ehmm_session *s, int differential, double p, int64_t *counts);
 int ehmm_rc_apply_at(ehmm_session *s, int differential, double p, const int64_t *col_offsets, int64_t total);
 /* Device pointer to the accumulators of the rejection tables, for adding the tables of several bin
  * blocks in place (e.g. an NCCL all-reduce ordered on the session stream).  is_integer = 1: n
- * unsigned 64-bit words, the exact fixed-point limbs (two per table entry) -- add them as integers
- * and the rounded tables are bit-identical for every sharding; is_integer = 0 (cuts below 2^-9): n
- * doubles.  ehmm_rc_finalize rounds the limbs into the fp64 tables (the readers below and the GLM
+ * unsigned 64-bit words, the exact fixed-point limbs (two per table entry; the call first folds the
+ * replicas of the frequent groups into them ON THE SESSION STREAM -- add on that stream or
+ * synchronise it first) -- add them as integers and the rounded tables are bit-identical for every
+ * sharding; is_integer = 0 (cuts below 2^-9): n doubles.  ehmm_rc_finalize rounds the limbs into the fp64 tables (the readers below and the GLM
  * entry points do it themselves when it is still pending). */
 int ehmm_rc_buckets_device(ehmm_session *s, void **ptr, int64_t *n, int *is_integer);
 int ehmm_rc_finalize(ehmm_session *s);

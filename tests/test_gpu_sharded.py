@@ -160,9 +160,12 @@ def test_rc_tables_do_not_depend_on_the_sharding(ehmm, oracle):
                 b.rc_apply_at(0.05, offs, total)
             for b in blocks:
                 b.sync()
-            acc = view(blocks[0])
-            for b in blocks[1:]:
-                acc += view(b)                       # the "all-reduce"
+            views = [view(b) for b in blocks]        # (folds the frequent groups' replicas in, on each session's stream)
+            for b in blocks:
+                b.sync()                             # torch adds on its own stream; the driver's NCCL call uses the session's
+            acc = views[0]
+            for v in views[1:]:
+                acc += v                             # the "all-reduce"
             torch.cuda.synchronize()
             blocks[0].rc_finalize()
             for c in range(2):
