@@ -486,6 +486,33 @@ def main():
     prof09 = s.profile_read()
     s.profile(False)
 
+    # ---- after the fit (untimed extras, once per fit in a real run): the Viterbi decode and the FDR peak calls on the
+    # datasets of the last E-step (produced on demand here: the timed steps ran the EM-internal E-step) ----
+    after = {}
+    try:
+        def ev_ms(fn, reps=3):
+            fn()
+            best = None
+            for _ in range(reps):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                fn()
+                e1.record(stream)
+                torch.cuda.synchronize()
+                t = e0.elapsed_time(e1)
+                best = t if best is None else min(best, t)
+            return best
+        s.materialize()
+        after["viterbi_ms"] = ev_ms(lambda: s.viterbi(theta["pi"], theta["gamma"], fetch=False))
+        if world == 1:
+            after["viterbi_path"] = s.viterbi_info()["path"]
+            after["call_peaks_fdr_ms"] = ev_ms(lambda: s.call_peaks(0.05), reps=2)
+            after["call_peaks_path"] = s.call_peaks_path()
+            after["peaks_called"] = int(s.call_peaks(0.05).sum())
+            after["peak_runs"] = int(s.peak_runs()[0].size)
+    except Exception as e:   # the extras must not cost the bench line
+        after["error"] = str(e)[:200]
+
     # ---- end-to-end arm: host buffers through the C ABI every step ----
     e2e = None
     if not args.no_e2e:
@@ -559,7 +586,7 @@ def main():
             "first_iteration_regime": {"rejection_cut": 0.9, "ms_per_step": ms_p09 / n09, "steps": n09,
                                        "value": M * K * world * n09 / (ms_p09 * 1e-3), "unit": "bin-states/s",
                                        "kernels_ms_per_step": {k: round(v[1] / n09, 4) for k, v in prof09.items() if v[0] and v[1] > 0}},
-            "roofline": roof, "kernels": kernels,
+            "roofline": roof, "kernels": kernels, "after_fit": after,
             "result_check": {"bic": out["bic"], "q": out["q"], "pi": list(map(float, out["pi"]))}}
     if parity is not None:
         line["result_check"]["sharded_vs_unsharded"] = parity

@@ -300,7 +300,9 @@ __device__ __forceinline__ void rc_load_raw(const RCSrc &S, const int32_t *__res
     }
 }
 
-template <bool DIFF, typename UT, bool EXACT, bool SKIPST, int CMAX>
+// FULL: the call has exactly CMAX columns (B = 6 -> 8, B = 14 -> 16, the consensus model's 2), so the column loop's
+// bounds and the "last column" tests are compile-time constants.
+template <bool DIFF, typename UT, bool EXACT, bool SKIPST, int CMAX, bool FULL>
 __global__ void __launch_bounds__(RC_NT, CMAX == 0 ? 1 : (CMAX <= 8 ? 4 : 3))
     rc_apply_kernel(RCSrc S, RCCut cut, int64_t nwt, const uint32_t *__restrict__ tileoff, const __grid_constant__ RCBase ub,
                     const UT *__restrict__ unif, const int32_t *__restrict__ group, int nrep, int64_t G,
@@ -311,7 +313,7 @@ __global__ void __launch_bounds__(RC_NT, CMAX == 0 ? 1 : (CMAX <= 8 ? 4 : 3))
     if (tile >= nwt) return;
     const double p = cut.p;
     const bool thin = p > 0.0;
-    const int C = S.columns;
+    const int C = FULL ? CMAX : S.columns;
     const int rep = (int)(tile & (RC_REP - 1));
     if (CMAX > 0) {
         constexpr int CM = CMAX > 0 ? CMAX : 1;
@@ -360,12 +362,13 @@ __global__ void __launch_bounds__(RC_NT, CMAX == 0 ? 1 : (CMAX <= 8 ? 4 : 3))
                     if (c < C) {
                         const bool flag = rc_flagged(x[c], p);
                         const unsigned bal = __ballot_sync(0xffffffffu, flag);
-                        if (flag) {
-                            const UT uw = stage[c * SG * 32 + used[c] + __popc(bal & lt)];
+                        {   // branch-free: every lane reads a staged word (its own rank's, or the first) and thins; most are flagged
+                            const UT uw = stage[c * SG * 32 + (flag ? used[c] + __popc(bal & lt) : 0)];
                             double u;
                             if (sizeof(UT) == 8) u = *reinterpret_cast<const double *>(&uw);
                             else u = mt_to_unif(*reinterpret_cast<const uint32_t *>(&uw));
-                            x[c] = rbinom1(rc_div_cut(x[c], cut.p, cut.rp), u) * cut.p;
+                            const double thinned = rbinom1(rc_div_cut(x[c], cut.p, cut.rp), u) * cut.p;
+                            x[c] = flag ? thinned : x[c];
                         }
                         used[c] += __popc(bal);
                         // x < p without a flag is x == 0: stays 0
@@ -631,13 +634,13 @@ int rc_static_build(ehmm_session *s, const RCSrc &S, double p, int nrep, cudaStr
 }
 
 // phase 2: thin and sum by group.  ub: where each column's draws start in `unif`.
-template <bool DIFF, typename UT, bool EXACT, bool SKIPST, int CM>
+template <bool DIFF, typename UT, bool EXACT, bool SKIPST, int CM, bool FULL>
 int launch_apply_cm(ehmm_session *s, const RCSrc &S, const RCCut &cut, int nrep, const RCBase &ub, const UT *unif, void *accp) {
     const RCAcc acc = rc_acc(reinterpret_cast<unsigned long long *>(accp), S.columns, s->G);  // fp64 mode: only .w is used
     const int64_t nwt = num_wtiles(s->M);
     constexpr int CS = CM > 0 ? CM : 1;
     const size_t smem = CM > 0 ? sizeof(UT) * RCStage<CS, UT>::WORDS * RC_NW : 0;
-    PROF(s, KID_RC_APPLY), rc_apply_kernel<DIFF, UT, EXACT, SKIPST, CM><<<tile_grid(nwt), RC_NT, smem, s->stream>>>(
+    PROF(s, KID_RC_APPLY), rc_apply_kernel<DIFF, UT, EXACT, SKIPST, CM, FULL><<<tile_grid(nwt), RC_NT, smem, s->stream>>>(
         S, cut, nwt, s->rc_scan.as<uint32_t>(), ub, unif, s->group.as<int32_t>(), nrep, s->G, acc, s->rc_flag.as<int>(), err_flag(s));
     EHMM_CK(cudaGetLastError());
     return EHMM_OK;
@@ -646,10 +649,12 @@ int launch_apply_cm(ehmm_session *s, const RCSrc &S, const RCCut &cut, int nrep,
 template <bool DIFF, typename UT, bool EXACT, bool SKIPST>
 int launch_apply_kernel(ehmm_session *s, const RCSrc &S, double p, int nrep, const RCBase &ub, const UT *unif, void *acc) {
     const RCCut cut = {p, p > 0.0 ? 1.0 / p : 0.0};
-    if (!DIFF) return launch_apply_cm<DIFF, UT, EXACT, SKIPST, 2>(s, S, cut, nrep, ub, unif, acc);
-    if (S.columns <= 8) return launch_apply_cm<DIFF, UT, EXACT, SKIPST, 8>(s, S, cut, nrep, ub, unif, acc);    // B = 6: BASELINE configs[2]
-    if (S.columns <= 16) return launch_apply_cm<DIFF, UT, EXACT, SKIPST, 16>(s, S, cut, nrep, ub, unif, acc);  // B = 14: configs[4]
-    return launch_apply_cm<DIFF, UT, EXACT, SKIPST, 0>(s, S, cut, nrep, ub, unif, acc);
+    if (!DIFF) return launch_apply_cm<DIFF, UT, EXACT, SKIPST, 2, true>(s, S, cut, nrep, ub, unif, acc);  // K = 2 columns, always
+    if (S.columns == 8) return launch_apply_cm<DIFF, UT, EXACT, SKIPST, 8, true>(s, S, cut, nrep, ub, unif, acc);    // B = 6: BASELINE configs[2]
+    if (S.columns < 8) return launch_apply_cm<DIFF, UT, EXACT, SKIPST, 8, false>(s, S, cut, nrep, ub, unif, acc);
+    if (S.columns == 16) return launch_apply_cm<DIFF, UT, EXACT, SKIPST, 16, true>(s, S, cut, nrep, ub, unif, acc);  // B = 14: configs[4]
+    if (S.columns < 16) return launch_apply_cm<DIFF, UT, EXACT, SKIPST, 16, false>(s, S, cut, nrep, ub, unif, acc);
+    return launch_apply_cm<DIFF, UT, EXACT, SKIPST, 0, false>(s, S, cut, nrep, ub, unif, acc);
 }
 
 template <bool DIFF, typename UT>
