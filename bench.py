@@ -324,7 +324,8 @@ def run_reference(args, name, cfg):
             "config": config_dict(name, cfg, args.gpus, M_gpu, scaling),
             "cpu_baseline": {"value": val, "unit": "bin-states/s", "cores": 1, "kind": "port", "sample": sample,
                              "host_cores_available": os.cpu_count(),
-                             "why_one_core": "the reference path is single-threaded (no OpenMP pragma, no RcppParallel: SURVEY.md 0)"},
+                             "why_one_core": "the reference path is single-threaded (no OpenMP pragma, no RcppParallel: SURVEY.md 0)",
+                             "bound_if_it_scaled_perfectly_over_all_host_cores": val * (os.cpu_count() or 1)},
             "e2e": {"value": val, "unit": "bin-states/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "em_iterations_per_s": args.steps / dt}
     print(json.dumps(line))

@@ -309,11 +309,20 @@ __global__ void __launch_bounds__(RC_NT, CMAX == 0 ? 1 : (CMAX <= 8 ? 4 : 3))
                     const RCAcc A, const int *__restrict__ counts, int *__restrict__ err) {
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
-    const int64_t tile = (int64_t)blockIdx.x * RC_NW + (threadIdx.x >> 5);
-    if (tile >= nwt) return;
     const double p = cut.p;
     const bool thin = p > 0.0;
     const int C = FULL ? CMAX : S.columns;
+    // Warp tiles are handed out by a counter (err[1], zeroed with the error flag): tiles inside peaks scatter many more
+    // weights than background tiles, and with a fixed tile per warp a CTA kept its registers and shared memory until
+    // its slowest warp was done (ncu: 15.8 of 32 resident warps active on average).
+    for (;;) {
+    int64_t tile;
+    {
+        int t = 0;
+        if (lane == 0) t = atomicAdd(err + 1, 1);
+        tile = __shfl_sync(0xffffffffu, t, 0);
+    }
+    if (tile >= nwt) return;
     const int rep = (int)(tile & (RC_REP - 1));
     if (CMAX > 0) {
         constexpr int CM = CMAX > 0 ? CMAX : 1;
@@ -400,7 +409,7 @@ __global__ void __launch_bounds__(RC_NT, CMAX == 0 ? 1 : (CMAX <= 8 ? 4 : 3))
                 if (c < C) bad = bad || (next[c] - (ub.ubase[c] + tileoff[(int64_t)c * nwt + tile]) != counts[(int64_t)c * nwt + tile]);
             if (bad && lane == 0) atomicOr(err, 1);
         }
-        return;
+        continue;
     }
     // lane (c & 31) holds the running rank and the uniform offset of column c (and of column c + 32)
     int cnt0 = 0, cnt1 = 0;
@@ -436,6 +445,7 @@ __global__ void __launch_bounds__(RC_NT, CMAX == 0 ? 1 : (CMAX <= 8 ? 4 : 3))
         if (lane + 32 < C) bad = bad || counts[(int64_t)(lane + 32) * nwt + tile] != cnt1;
         if (bad) atomicOr(err, 1);
     }
+    }  // next tile
 }
 
 // differential model: the weights >= p of the background and the enrichment column (P1[,0], P1[,2]) do not
@@ -640,7 +650,9 @@ int launch_apply_cm(ehmm_session *s, const RCSrc &S, const RCCut &cut, int nrep,
     const int64_t nwt = num_wtiles(s->M);
     constexpr int CS = CM > 0 ? CM : 1;
     const size_t smem = CM > 0 ? sizeof(UT) * RCStage<CS, UT>::WORDS * RC_NW : 0;
-    PROF(s, KID_RC_APPLY), rc_apply_kernel<DIFF, UT, EXACT, SKIPST, CM, FULL><<<tile_grid(nwt), RC_NT, smem, s->stream>>>(
+    // as many CTAs as can be resident (4 per SM where the kernel's bounds allow it), each warp fetching tiles until none is left
+    const unsigned grid = std::min<unsigned>(tile_grid(nwt), 148u * (CM == 0 ? 1u : (CM <= 8 ? 4u : 3u)));
+    PROF(s, KID_RC_APPLY), rc_apply_kernel<DIFF, UT, EXACT, SKIPST, CM, FULL><<<grid, RC_NT, smem, s->stream>>>(
         S, cut, nwt, s->rc_scan.as<uint32_t>(), ub, unif, s->group.as<int32_t>(), nrep, s->G, acc, s->rc_flag.as<int>(), err_flag(s));
     EHMM_CK(cudaGetLastError());
     return EHMM_OK;
@@ -662,7 +674,7 @@ int launch_apply(ehmm_session *s, const RCSrc &S, double p, int nrep, const RCBa
     const size_t cells = (size_t)S.columns * (s->G + 1);
     const bool exact = p >= RC_EXACT_MIN_P;
     const size_t LW = sizeof(unsigned long long);
-    EHMM_CK(cudaMemsetAsync(err_flag(s), 0, sizeof(int), s->stream));
+    EHMM_CK(cudaMemsetAsync(err_flag(s), 0, 2 * sizeof(int), s->stream));  // error flag and the kernel's tile counter
     if (exact) {
         unsigned long long *limbs = s->rc_limbs.as<unsigned long long>();
         EHMM_CK(cudaMemsetAsync(limbs, 0, LW * rc_acc_words(S.columns, s->G), s->stream));
