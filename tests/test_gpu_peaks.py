@@ -43,6 +43,18 @@ def test_fdr_calls_match_the_oracle(ehmm, oracle, M, fdr):
             assert s.peaks_cutoff == np.max(1.0 - pr[want])
 
 
+def test_reference_known_answer(ehmm, oracle):
+    """tests/testthat/test-base.R:1-4: sum(fdrControl(seq(0, 1, 0.001), 0.05)) == 101, a vector whose 101st running mean
+    IS the level up to rounding.  The oracle reproduces the 101 on the exact sequence (tests/test_ldsum.py); the device
+    receives the probabilities as logProb1, i.e. exp(log(.)) of the sequence, and must agree with the oracle on those,
+    window by window -- through the emulated long double, the margin being too small to certify"""
+    s, pr = _session_with_posteriors(ehmm, np.arange(1001) * 0.001)
+    with s:
+        got = s.call_peaks(0.05)
+        assert s.call_peaks_path() == "emulated long double (margin too small)"
+    assert got.sum() in (100, 101) and np.array_equal(got, oracle.fdrControl(pr, 0.05))
+
+
 def test_margin_too_small_falls_to_r_arithmetic(ehmm, oracle):
     """running means that sit ON the level (every notpp equal to it, so each mean is the level up to rounding): the
     fp64 prefix sum cannot certify the comparison and the emulated long double decides, as R would"""

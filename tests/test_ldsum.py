@@ -31,7 +31,8 @@ def _twin(prob, fdr):
 @pytest.mark.skipif(np.finfo(np.longdouble).nmant != 63, reason="needs the x87 extended type")
 def test_oracle_fdr_control(oracle):
     rng = np.random.default_rng(3)
-    # the reference's own test (tests/testthat/test-base.R:1-4): fdrControl(c(0.99, 0.5, 0.01), 0.05)
+    # the reference's own known-answer test (tests/testthat/test-base.R:1-4): sum(fdrControl(seq(0, 1, 0.001), 0.05)) == 101
+    assert oracle.fdrControl(np.arange(1001) * 0.001, 0.05).sum() == 101
     assert list(oracle.fdrControl(np.array([0.99, 0.5, 0.01]), 0.05)) == [True, False, False]
     for n, fdr in ((1, 0.05), (17, 0.2), (5000, 0.05), (200_000, 0.01)):
         prob = np.where(rng.random(n) < 0.1, 1.0 - rng.random(n) * 1e-3, rng.random(n) ** 4)
