@@ -29,6 +29,10 @@ void ehmm_R_set_data(StringVector, IntegerMatrix, NumericMatrix, Nullable<Numeri
 double ehmm_R_build_groups(StringVector);
 void ehmm_R_loglik_consensus(StringVector, NumericVector, NumericVector, double, std::string);
 void ehmm_R_em_hints(StringVector, double, bool);
+void ehmm_R_set_design(StringVector, IntegerMatrix);
+void ehmm_R_loglik_differential(StringVector, NumericVector, NumericVector, double, std::string);
+void ehmm_R_inner_expstep(StringVector, NumericVector, NumericVector, double, std::string);
+List ehmm_R_glm_mix(StringVector, NumericVector, double, std::string);
 List ehmm_R_glm_nb(StringVector, int, NumericVector);
 NumericMatrix ehmm_R_fetch(StringVector, std::string);
 LogicalVector ehmm_R_call_peaks(StringVector, double);
@@ -61,10 +65,26 @@ int main(int argc, char **argv) {
     in.read((char *)gamma.begin(), 32);
     in.read((char *)t1.begin(), 16);
     in.read((char *)t2.begin(), 16);
+    // differential block: int64 M2, N2, B; counts, offsets, design (B x N2, int32), delta[B], psi[4], pi[3], gamma[9]
+    int64_t M2, N2, B;
+    in.read((char *)&M2, 8);
+    in.read((char *)&N2, 8);
+    in.read((char *)&B, 8);
+    IntegerMatrix counts2((int)M2, (int)N2), design((int)B, (int)N2);
+    NumericMatrix offsets2((int)M2, (int)N2), gamma3(3, 3);
+    NumericVector delta((int)B), psi(4), pi3(3);
+    in.read((char *)counts2.begin(), 4 * M2 * N2);
+    in.read((char *)offsets2.begin(), 8 * M2 * N2);
+    in.read((char *)design.begin(), 4 * B * N2);
+    in.read((char *)delta.begin(), 8 * B);
+    in.read((char *)psi.begin(), 32);
+    in.read((char *)pi3.begin(), 24);
+    in.read((char *)gamma3.begin(), 72);
     out = std::fopen(argv[2], "w");
     try {
         StringVector h5{"/tmp/glue_harness.h5"};
         Environment g = Environment::global_env();
+        const IntegerVector seed0 = clone(seed);   // (vectors are handles: the rejection control advances `seed` in place)
         g[".Random.seed"] = seed;
         ehmm_R_open(h5, (double)M, 2);
         ehmm_R_set_data(h5, counts, offsets, Nullable<NumericMatrix>());
@@ -117,6 +137,37 @@ int main(int argc, char **argv) {
         put("rbinom", rbinomVectorized(x));
         ehmm_R_close(h5);
         ehmm_R_close(h5b);
+        // the differential model's exports
+        {
+            StringVector h5d{"/tmp/glue_harness_d.h5"};
+            g[".Random.seed"] = clone(seed0);
+            ehmm_R_open(h5d, (double)M2, 3);
+            ehmm_R_set_data(h5d, counts2, offsets2, Nullable<NumericMatrix>());
+            ehmm_R_set_design(h5d, design);
+            const double Gd = ehmm_R_build_groups(h5d);
+            put("d_G", &Gd, 1);
+            ehmm_R_em_hints(h5d, 0.05, true);
+            ehmm_R_loglik_differential(h5d, delta, psi, 2.2250738585072014e-308, "nb");
+            expStep(pi3, gamma3, Nullable<NumericMatrix>(), h5d);
+            List md = maxStepProb(h5d);
+            put("d_gamma", md.get<NumericMatrix>("gamma"));
+            ehmm_R_inner_expstep(h5d, delta, psi, 2.2250738585072014e-308, "nb");
+            put("d_delta", innerMaxStepProb(h5d));
+            NumericVector fd((int)(M2 * N2));
+            List rcd = differentialRejectionControlled(h5d, fd, 0.05, (int)N2);
+            for (int c = 0; c < (int)B + 2; c++) {
+                char nm[16];
+                std::snprintf(nm, sizeof nm, "d_rc%d", c);
+                put(nm, rcd.get<NumericMatrix>(c));
+            }
+            NumericVector par{psi[0], psi[2], psi[1], psi[3]};   // optimDifferential's order (b, db, l, dl)
+            List gm = ehmm_R_glm_mix(h5d, par, 2.2250738585072014e-308, "nb");
+            const double gmv = gm.get<double>("value");
+            put("d_glm_value", &gmv, 1);
+            put("d_glm_grad", gm.get<NumericVector>("gradient"));
+            put("d_mixtureProb", ehmm_R_fetch(h5d, "mixtureProb"));
+            ehmm_R_close(h5d);
+        }
         // errors become R errors (stop): a path nobody opened
         try {
             maxStepProb(StringVector{"/tmp/never_opened.h5"});

@@ -67,6 +67,20 @@ def test_glue_exports_equal_the_ctypes_path(tmp_path, ehmm, oracle):
         f.write(np.asfortranarray(th["gamma"], dtype=np.float64).tobytes(order="F"))
         f.write(np.asarray(th["psi"][0], dtype=np.float64).tobytes())
         f.write(np.asarray(th["psi"][1], dtype=np.float64).tobytes())
+        # the differential block: 3 conditions x 1 replicate, 6 mixture patterns
+        M2 = 15_013
+        dd = synth.make_differential(M2, 3, 1, seed=9)
+        td = synth.THETA_DIFFERENTIAL
+        Bd = dd["B"]
+        delta = np.full(Bd, 1.0 / Bd)
+        f.write(struct.pack("qqq", M2, 3, Bd))
+        f.write(np.asfortranarray(dd["counts"], dtype=np.int32).tobytes(order="F"))
+        f.write(np.asfortranarray(dd["offsets"], dtype=np.float64).tobytes(order="F"))
+        f.write(np.asfortranarray(dd["design"].astype(np.int32)).tobytes(order="F"))
+        f.write(delta.tobytes())
+        f.write(np.asarray(td["psi"], dtype=np.float64).tobytes())
+        f.write(np.asarray(td["pi"], dtype=np.float64).tobytes())
+        f.write(np.asfortranarray(td["gamma"], dtype=np.float64).tobytes(order="F"))
     r = subprocess.run([exe, fin, fout], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     got = {}
@@ -103,6 +117,31 @@ def test_glue_exports_equal_the_ctypes_path(tmp_path, ehmm, oracle):
         lfp = np.ravel(s.fetch("logFP"), order="F")
         assert np.array_equal(got["logFP"], lfp) and np.array_equal(got["logFP_b"], lfp)
         assert np.array_equal(got["peaks"].astype(bool), s.call_peaks(0.05))
+
+    with ehmm.Session("glue_ref_d", M2, 3) as s:
+        s.set_data(dd["counts"], dd["offsets"])
+        s.set_design(dd["design"])
+        Gd = s.build_groups()
+        s.rng_set_state(seed)
+        s.rc_hint(0.05)
+        s.expstep_mode(1)
+        s.loglik_differential_hmm(delta, td["psi"], 2.2250738585072014e-308)
+        s.expstep(td["pi"], td["gamma"])
+        md = s.maxstepprob()
+        s.inner_expstep(delta, td["psi"], 2.2250738585072014e-308)
+        dl = s.inner_maxstepprob()
+        s.rc_differential(0.05)
+        assert got["d_G"][0] == Gd
+        assert np.array_equal(got["d_gamma"], np.ravel(md["gamma"], order="F")) and np.array_equal(got["d_delta"], dl)
+        for c in range(Bd + 2):
+            b = s.rc_buckets(c)
+            ids = np.flatnonzero(b)
+            tab = got["d_rc%d" % c].reshape(-1, 2, order="F")
+            assert np.array_equal(tab[:, 1], ids) and np.array_equal(tab[:, 0], b[ids]), c
+        psi = td["psi"]
+        v, gr = s.glm_mix_nb([psi[0], psi[2], psi[1], psi[3]], 2.2250738585072014e-308)
+        assert got["d_glm_value"][0] == v and np.array_equal(got["d_glm_grad"], gr)
+        assert np.array_equal(got["d_mixtureProb"], np.ravel(s.fetch("mixtureProb"), order="F"))
 
     # the stand-alone helpers, with the mock generator's uniforms replayed here
     x = ((np.arange(M) * 37) % 101) / 100.0
