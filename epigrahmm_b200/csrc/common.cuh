@@ -120,6 +120,7 @@ struct ehmm_session {
     // uses (its ifelse() quirk, R/base-loglikelihood.R:113); a bin block with m0 > 0 gets it from block 0
     double ctrl_first = 0.0;
     bool have_ctrl_first = false;
+    ehmm::DevBuf grp_tags, grp_first, grp_list, grp_rank, grp_misc, grp_sort;  // build_groups work space (kept between calls)
     ehmm::DevBuf group;                     // int32 M x N
     ehmm::DevBuf u_chip, u_off, u_ctrl;     // dtUnique columns, index 0..G (0 unused)
     ehmm::DevBuf u_dsg;                     // uint8 (G+1) x B
@@ -353,6 +354,8 @@ int glm_mix_zinb(ehmm_session *s, const double *par, double minZero, double *val
 // peaks.cu
 int call_peaks_fdr(ehmm_session *s, double fdr, uint8_t *calls_out, int64_t *n_called, double *cutoff);
 int call_peaks_viterbi(ehmm_session *s, uint8_t *calls_out, int64_t *n_called);
+int radix_sort_pairs(ehmm_session *s, uint64_t *k0, uint64_t *k1, uint32_t *v0, uint32_t *v1, unsigned *hist, int64_t n,
+                     const uint32_t *vinit, uint64_t **k_sorted, uint32_t **v_sorted);
 int peak_runs(ehmm_session *s, const int64_t *breaks, int nbreaks, int64_t cap, int64_t *starts, int64_t *ends, int64_t *nruns);
 // viterbi.cu
 int viterbi(ehmm_session *s, const double *pi, const double *gamma, double *states_out);

@@ -60,16 +60,23 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// the occupied slots as (first cell, slot) pairs, in no particular order: keys[i] = first cell, slots[i] = slot
 __global__ void grp_compact_kernel(unsigned long long cap, const unsigned long long *__restrict__ tags,
-                                   const unsigned long long *__restrict__ first, unsigned long long *__restrict__ list,
-                                   unsigned long long maxlist, unsigned long long *__restrict__ count) {
+                                   const unsigned long long *__restrict__ first, unsigned long long *__restrict__ keys,
+                                   uint32_t *__restrict__ slots, unsigned long long maxlist, unsigned long long *__restrict__ count) {
     for (unsigned long long s = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; s < cap;
          s += (unsigned long long)gridDim.x * blockDim.x) {
         if (tags[s] != 0ULL) {
             const unsigned long long i = atomicAdd(count, 1ULL);
-            if (i < maxlist) { list[2 * i] = first[s]; list[2 * i + 1] = s; }
+            if (i < maxlist) { keys[i] = first[s]; slots[i] = (uint32_t)s; }
         }
     }
+}
+
+// .GRP numbers the groups by first appearance: the pairs sorted by first cell give slot -> rank
+__global__ void grp_rank_kernel(int64_t G, const uint32_t *__restrict__ slots_sorted, int32_t *__restrict__ slotrank) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < G) slotrank[slots_sorted[i]] = (int32_t)i;
 }
 
 // group[c] = rank of the cell's slot; verify the full key against the group's first cell
@@ -141,16 +148,15 @@ int build_groups(ehmm_session *s, int64_t *G_out) {
     EHMM_TRY(s->group.reserve(sizeof(int32_t) * n));
     EHMM_TRY(s->rc_tmp.reserve(sizeof(int32_t) * n));
     int32_t *cellslot = s->rc_tmp.as<int32_t>();
-    DevBuf tags, first, list, rank, misc2;
-    struct Guard {
-        DevBuf *b[5];
-        ~Guard() { for (auto p : b) p->release(); }
-    } guard{{&tags, &first, &list, &rank, &misc2}};
+    // work space kept in the session: allocating and freeing 100 MB of tables per call cost more than the kernels
+    DevBuf &tags = s->grp_tags, &first = s->grp_first, &list = s->grp_list, &rank = s->grp_rank, &misc2 = s->grp_misc, &sortb = s->grp_sort;
     // flags / counter in the first 64 bytes, the design matrix behind them: sized once, because a
     // growing reserve() reallocates and would drop the verification flag written in between
     EHMM_TRY(misc2.reserve(64 + (size_t)EHMM_MAX_B * 64));
-    std::vector<unsigned long long> h;
     unsigned long long cap = 1ULL << 22, G = 0;
+    unsigned long long *keys0 = nullptr, *keys1 = nullptr;
+    uint32_t *v0 = nullptr, *v1 = nullptr;
+    unsigned *hist = nullptr;
     for (int attempt = 0;; attempt++) {
         EHMM_TRY(tags.reserve(sizeof(unsigned long long) * cap));
         EHMM_TRY(first.reserve(sizeof(unsigned long long) * cap));
@@ -164,12 +170,19 @@ int build_groups(ehmm_session *s, int64_t *G_out) {
             first.as<unsigned long long>(), cap - 1, cellslot, fail);
         EHMM_CK(cudaGetLastError());
         const unsigned long long maxlist = cap / 2;
-        EHMM_TRY(list.reserve(sizeof(unsigned long long) * 2 * maxlist));
+        // sort buffers: two key arrays, two value arrays, the radix sort's counters (one 256-bin histogram per 4096 pairs)
+        const size_t kb = sizeof(unsigned long long) * maxlist, vb = sizeof(uint32_t) * maxlist, hb = sizeof(unsigned) * 256 * (maxlist / 4096 + 1);
+        EHMM_TRY(sortb.reserve(2 * kb + 2 * vb + hb));
+        keys0 = sortb.as<unsigned long long>();
+        keys1 = keys0 + maxlist;
+        v0 = reinterpret_cast<uint32_t *>(keys1 + maxlist);
+        v1 = v0 + maxlist;
+        hist = reinterpret_cast<unsigned *>(v1 + maxlist);
         PROF(s, KID_MISC), grp_compact_kernel<<<148 * 8, 256, 0, s->stream>>>(
-            cap, tags.as<unsigned long long>(), first.as<unsigned long long>(), list.as<unsigned long long>(), maxlist, count);
+            cap, tags.as<unsigned long long>(), first.as<unsigned long long>(), keys0, v1, maxlist, count);
         EHMM_CK(cudaGetLastError());
-        unsigned long long hc[2];
-        EHMM_CK(cudaMemcpyAsync(hc, misc2.p, sizeof(hc), cudaMemcpyDeviceToHost, s->stream));
+        unsigned long long *hc = reinterpret_cast<unsigned long long *>(s->h_pinned + 420);
+        EHMM_CK(cudaMemcpyAsync(hc, misc2.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->stream));
         EHMM_CK(cudaStreamSynchronize(s->stream));
         const int failed = (int)(hc[0] & 0xffffffffULL);
         G = hc[1];
@@ -177,18 +190,15 @@ int build_groups(ehmm_session *s, int64_t *G_out) {
         EHMM_REQUIRE(attempt == 0, EHMM_ERR_NOMEM, "build_groups: more than %llu distinct groups", maxlist);
         cap <<= 3;  // one retry with an 8x larger table
     }
-    h.resize(2 * G);
-    EHMM_CK(cudaMemcpyAsync(h.data(), list.p, sizeof(unsigned long long) * 2 * G, cudaMemcpyDeviceToHost, s->stream));
-    EHMM_CK(cudaStreamSynchronize(s->stream));
-    // .GRP: groups numbered by first appearance
-    std::vector<std::pair<unsigned long long, unsigned long long>> ent(G);
-    for (unsigned long long i = 0; i < G; i++) ent[i] = {h[2 * i], h[2 * i + 1]};
-    std::sort(ent.begin(), ent.end());
-    std::vector<int32_t> slotrank(cap, -1);
-    std::vector<unsigned long long> firstsorted(G);
-    for (unsigned long long i = 0; i < G; i++) { slotrank[ent[i].second] = (int32_t)i; firstsorted[i] = ent[i].first; }
+    // .GRP: groups numbered by first appearance -- the (first cell, slot) pairs sorted by first cell, on the device
+    uint64_t *ksorted = nullptr;
+    uint32_t *vsorted = nullptr;
+    EHMM_TRY(radix_sort_pairs(s, reinterpret_cast<uint64_t *>(keys0), reinterpret_cast<uint64_t *>(keys1), v0, v1, hist, (int64_t)G, v1,
+                              &ksorted, &vsorted));
     EHMM_TRY(rank.reserve(sizeof(int32_t) * cap));
-    EHMM_CK(cudaMemcpyAsync(rank.p, slotrank.data(), sizeof(int32_t) * cap, cudaMemcpyHostToDevice, s->stream));
+    EHMM_CK(cudaMemsetAsync(rank.p, 0xff, sizeof(int32_t) * cap, s->stream));
+    PROF(s, KID_MISC), grp_rank_kernel<<<(unsigned)((G + 255) / 256), 256, 0, s->stream>>>((int64_t)G, vsorted, rank.as<int32_t>());
+    EHMM_CK(cudaGetLastError());
     EHMM_CK(cudaMemsetAsync(misc2.p, 0, 64, s->stream));
     PROF(s, KID_MISC), grp_assign_kernel<<<148 * 8, 256, 0, s->stream>>>(
         M, s->N, s->d_counts, s->d_offsets, s->d_controls, D, cellslot, rank.as<int32_t>(),
@@ -200,7 +210,7 @@ int build_groups(ehmm_session *s, int64_t *G_out) {
     EHMM_TRY(s->u_off.reserve(gb));
     if (s->d_controls) EHMM_TRY(s->u_ctrl.reserve(gb)); else s->u_ctrl.release();
     EHMM_TRY(list.reserve(sizeof(unsigned long long) * (G + 1) + sizeof(int32_t) * (G + 1)));
-    EHMM_CK(cudaMemcpyAsync(list.p, firstsorted.data(), sizeof(unsigned long long) * G, cudaMemcpyHostToDevice, s->stream));
+    EHMM_CK(cudaMemcpyAsync(list.p, ksorted, sizeof(unsigned long long) * G, cudaMemcpyDeviceToDevice, s->stream));
     int32_t *usample = reinterpret_cast<int32_t *>(list.as<unsigned long long>() + (G + 1));
     PROF(s, KID_MISC), grp_unique_kernel<<<(unsigned)((G + 1 + 255) / 256), 256, 0, s->stream>>>(
         (int64_t)G, M, list.as<unsigned long long>(), s->d_counts, s->d_offsets, s->d_controls, s->u_chip.as<double>(),
@@ -214,13 +224,15 @@ int build_groups(ehmm_session *s, int64_t *G_out) {
             (int64_t)G, s->B, s->N, usample, misc2.as<uint8_t>() + 64, s->u_dsg.as<uint8_t>());
         EHMM_CK(cudaGetLastError());
     }
-    int hf = 0;
-    EHMM_CK(cudaMemcpyAsync(&hf, misc2.p, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    int *hf = reinterpret_cast<int *>(s->h_pinned + 424);
+    EHMM_CK(cudaMemcpyAsync(hf, misc2.p, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    // first cell of every group (ehmm_groups_first_cell: bin blocks merge their dictionaries with it)
+    s->group_first.resize(G);
+    EHMM_CK(cudaMemcpyAsync(s->group_first.data(), list.p, sizeof(int64_t) * G, cudaMemcpyDeviceToHost, s->stream));
     EHMM_CK(cudaStreamSynchronize(s->stream));
-    EHMM_REQUIRE(hf == 0, EHMM_ERR_STATE, "build_groups: 64-bit key-hash collision detected; group the table on the host instead");
+    EHMM_REQUIRE(*hf == 0, EHMM_ERR_STATE, "build_groups: 64-bit key-hash collision detected; group the table on the host instead");
     s->G = (int64_t)G;
     posteriors_changed(s);
-    s->group_first.assign(firstsorted.begin(), firstsorted.end());
     s->groups_consistent = true;
     s->rc_columns = 0;
     if (G_out) *G_out = (int64_t)G;

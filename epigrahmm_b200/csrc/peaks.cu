@@ -368,6 +368,30 @@ int reserve_peaks(ehmm_session *s, PeakBufs &B) {
 
 }  // namespace
 
+// Stable LSD radix sort of n (64-bit key, 32-bit value) pairs on the session stream: 8 passes of 8 bits, ping-pong
+// between (k0, v0) and (k1, v1); the keys start in k0, the values in vinit (nullptr: the indices 0..n-1) -- vinit may be
+// v1 but not v0.  hist: 256 * ceil(n / 4096) counters.  Also used to number dt$Group by first appearance (groups.cu).
+int radix_sort_pairs(ehmm_session *s, uint64_t *k0, uint64_t *k1, uint32_t *v0, uint32_t *v1, unsigned *hist, int64_t n,
+                     const uint32_t *vinit, uint64_t **k_sorted, uint32_t **v_sorted) {
+    const int nblk = (int)((n + RS_TILE - 1) / RS_TILE);
+    uint64_t *kin = k0, *kout = k1;
+    const uint32_t *vin = vinit;
+    uint32_t *vout = v0, *vother = v1;
+    for (int pass = 0; pass < 8; pass++) {
+        const int shift = 8 * pass;
+        PROF(s, KID_PEAKS), rs_hist_kernel<<<nblk, RS_NT, 0, s->stream>>>(kin, n, shift, hist, nblk);
+        PROF(s, KID_PEAKS), rs_scan_kernel<<<1, 1024, 0, s->stream>>>(hist, (int64_t)256 * nblk);
+        PROF(s, KID_PEAKS), rs_scatter_kernel<<<nblk, RS_NT, 0, s->stream>>>(kin, vin, kout, vout, n, shift, hist, nblk);
+        EHMM_CK(cudaGetLastError());
+        std::swap(kin, kout);
+        vin = vout;
+        std::swap(vout, vother);
+    }
+    *k_sorted = kin;                          // back in k0 after an even number of passes
+    *v_sorted = const_cast<uint32_t *>(vin);  // the buffer written last
+    return EHMM_OK;
+}
+
 // fdrControl(prob = exp(logProb1[, 2]), fdr) -> calls[M] (0/1, by window; also kept on the device for peak_runs)
 int call_peaks_fdr(ehmm_session *s, double fdr, uint8_t *calls_out, int64_t *n_called, double *cutoff) {
     EHMM_REQUIRE(fdr > 0.0 && fdr < 1.0, EHMM_ERR_ARG, "fdr must be between 0 and 1");  // R/base-utils.R:15-16
@@ -381,18 +405,9 @@ int call_peaks_fdr(ehmm_session *s, double fdr, uint8_t *calls_out, int64_t *n_c
     EHMM_CK(cudaMemsetAsync(B.scal, 0, 32, s->stream));
     PROF(s, KID_PEAKS), notpp_kernel<<<148 * 8, 256, 0, s->stream>>>(s->logProb1.as<double>() + M, M, B.k0, flags + 1);
     EHMM_CK(cudaGetLastError());
-    uint64_t *kin = B.k0, *kout = B.k1;
-    uint32_t *vin = nullptr, *vout = B.v0, *vother = B.v1;
-    for (int pass = 0; pass < 8; pass++) {
-        const int shift = 8 * pass;
-        PROF(s, KID_PEAKS), rs_hist_kernel<<<nblk, RS_NT, 0, s->stream>>>(kin, M, shift, B.hist, nblk);
-        PROF(s, KID_PEAKS), rs_scan_kernel<<<1, 1024, 0, s->stream>>>(B.hist, (int64_t)256 * nblk);
-        PROF(s, KID_PEAKS), rs_scatter_kernel<<<nblk, RS_NT, 0, s->stream>>>(kin, vin, kout, vout, M, shift, B.hist, nblk);
-        EHMM_CK(cudaGetLastError());
-        std::swap(kin, kout);
-        vin = vout;
-        std::swap(vout, vother);
-    }
+    uint64_t *kin = nullptr;
+    uint32_t *vin = nullptr;
+    EHMM_TRY(radix_sort_pairs(s, B.k0, B.k1, B.v0, B.v1, B.hist, M, nullptr, &kin, &vin));
     // after 8 passes the sorted keys are back in k0 and the windows in the buffer written last
     const FdrOut O = {s->peak_calls.as<uint8_t>(), B.scal, flags, B.scal + 1};
     if (s->peaks_exact) {

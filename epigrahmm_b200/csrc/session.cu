@@ -272,7 +272,7 @@ int ehmm_session_close(ehmm_session *s) {
         auto it = g_sessions.find(s->key);
         if (it != g_sessions.end() && it->second == s) g_sessions.erase(it);
     }
-    DevBuf *bufs[] = {&s->counts_own, &s->offsets_own, &s->controls_own, &s->group, &s->u_chip, &s->u_off, &s->u_ctrl,
+    DevBuf *bufs[] = {&s->counts_own, &s->offsets_own, &s->controls_own, &s->grp_tags, &s->grp_first, &s->grp_list, &s->grp_rank, &s->grp_misc, &s->grp_sort, &s->group, &s->u_chip, &s->u_off, &s->u_ctrl,
                       &s->u_dsg, &s->logf, &s->logFP, &s->logBP, &s->logProb1, &s->logProb2, &s->prob1, &s->logf_alt, &s->eta, &s->viterbi, &s->vit_bp, &s->vit_work, &s->peak_work, &s->peak_calls,
                       &s->tileops, &s->carries, &s->tilestats, &s->fbscal, &s->rangeops, &s->rangecarry, &s->rc_flag, &s->rc_scan,
                       &s->rc_buckets, &s->rc_limbs, &s->rc_coltot, &s->rc_static, &s->rc_unif, &s->rc_unif_spec, &s->rc_unif_specr[0], &s->rc_unif_specr[1], &s->rc_tmp, &s->mt_raw, &s->mt_raw2, &s->mt_windows, &s->gtab, &s->glm_ticket, &s->inner_part, &s->lgtab, &s->glm_part, &s->misc};
