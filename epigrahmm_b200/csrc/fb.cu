@@ -51,7 +51,9 @@ template <int K> struct FBCfg;
 // APPLY_CTAS = resident apply CTAs per SM the register budget is set for (4 spills and is slower)
 template <> struct FBCfg<2> { static constexpr int NT = 256, L = 5, APPLY_CTAS = 3; };
 template <> struct FBCfg<3> { static constexpr int NT = 192, L = 5, APPLY_CTAS = 3; };
-template <int K> struct CarryCfg { static constexpr int NT = (K <= 2) ? 1024 : 512; };  // K = 3 needs > 64 registers
+// 256 threads: a larger CTA does not fit next to the side stream's resident CTAs and waits for them to drain; the scan
+// is over at most 592 range operators anyway
+template <int K> struct CarryCfg { static constexpr int NT = 256; };
 
 // 2^-e for the binary exponent e encoded in the high word `hi` of a non-negative double
 // (normal numbers only; e = 0 for zero / subnormal / inf / nan)
