@@ -282,13 +282,17 @@ class ShardedSession:
             self.local.rc_hint(p)
 
     def _early_counts(self, differential):
-        """this block's flagged counts for the announced cut, or None (no cut announced, no groups yet, ...)"""
+        """this block's flagged counts for the announced cut, or None when no cut is announced or no groups are set.
+        Both conditions hold on all ranks alike (the driver announces the cut and sets the groups everywhere), so every
+        rank packs the same fields into the exchange; an error inside the count is raised, not swallowed"""
         if self._hint is None or not (self._hint > 0.0):
             return None
-        try:
-            return np.asarray(self.local.rc_count(self._hint, differential), dtype=np.float64)
-        except Exception:
+        groups = getattr(self.local, "G", None)
+        if groups is None:                       # host-resident backend (CPU tests): a dict of group columns or None
+            groups = 0 if getattr(self.local, "g", None) is None else 1
+        if not groups:
             return None
+        return np.asarray(self.local.rc_count(self._hint, differential), dtype=np.float64)
 
     # data ------------------------------------------------------------------------------------
     def _share_controls_first(self, have):
