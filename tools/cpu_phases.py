@@ -19,10 +19,13 @@ from epigrahmm_b200 import em, synth
 
 M = int(float(sys.argv[1])) if len(sys.argv) > 1 else 1_000_000
 REP = 5
-d, g = bench.make_workload(M, bench.N_SAMPLES, bench.SEED)
+CFG = bench.CONFIGS["c2"]          # BASELINE configs[1]: the consensus workload of bench.py --config c2
+N_SAMPLES, SEED = CFG["N"], CFG["seed"]
+d = bench.make_data(CFG, M, SEED)
+g = synth.make_groups(d["counts"], d["offsets"])
 th = synth.THETA_CONSENSUS
 ctl = em.controlEM()
-be = OracleBackend(d["counts"], d["offsets"], 2, groups=g, rng=O.RNG.set_seed(bench.SEED))
+be = OracleBackend(d["counts"], d["offsets"], 2, groups=g, rng=O.RNG.set_seed(SEED))
 
 
 def med(f):
@@ -47,12 +50,12 @@ pool = ThreadPoolExecutor(ncores)
 ph["emission_all_cores"] = med(lambda: list(pool.map(lambda cs: O.loglikConsensusHMM(cs[0], cs[1], th["psi"], ctl["minZero"]), slices)))
 ph["expStep"] = med(lambda: be.expstep(th["pi"], th["gamma"]))
 ph["maxStepProb"] = med(lambda: be.maxstepprob())
-ph["computeQFunction+computeBIC"] = med(lambda: (be.qfunction(th["pi"], th["gamma"]), be.bic(5, bench.N_SAMPLES)))
+ph["computeQFunction+computeBIC"] = med(lambda: (be.qfunction(th["pi"], th["gamma"]), be.bic(5, N_SAMPLES)))
 ph["consensusRejectionControlled"] = med(lambda: be.rc_consensus(bench.P_CUT))
 ph["optimNB (both states)"] = med(lambda: em.optimNB_all(th["psi"], be, ctl))
 ph["computeViterbiSequence"] = med(lambda: be.viterbi(th["pi"], th["gamma"]))
 it = sum(v for k, v in ph.items() if k not in ("emission_all_cores", "computeViterbiSequence"))
-print(json.dumps({"bins": M, "samples": bench.N_SAMPLES, "states": 2, "threads": 1, "host_cores": ncores,
+print(json.dumps({"bins": M, "samples": N_SAMPLES, "states": 2, "threads": 1, "host_cores": ncores,
                   "seconds": {k: round(v, 4) for k, v in ph.items()}, "em_iteration_seconds": round(it, 4),
                   "bin_states_per_s": M * 2 / it,
                   "note": "oracle restatement of the reference, in memory (no HDF5 round trips, which flatters the reference); "
