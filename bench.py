@@ -10,6 +10,8 @@ A step is one EM iteration at fixed theta of the configuration --config names (B
                innerMaxStepProb -> differentialRejectionControlled -> L-BFGS-B over glmMixNB) -> BIC, Q.
   c2           configs[1]: consensus peak calling, 15 000 000 bins x 4 replicates, K = 2: one iteration of
                R/base-EM.R:106-175.
+  c4           configs[3]: genomic segmentation, 6 000 000 bins of 500 bp x (5 marks x 2 replicates), B = 30, offsets that
+               carry an input control.
   c5           configs[4]: 50 bp bins, 60 000 000 bins x (4 conditions x 3 replicates), B = 14, sharded
                over the GPUs of the run (7 500 000 bins per GPU at --gpus 8).
 
@@ -55,6 +57,10 @@ CONFIGS = {
                workload="BASELINE configs[2]: synthetic genome-wide differential peak calling, 3 conditions x 2 replicates "
                         "(2^3 - 2 = 6 mixture patterns), 15 000 000 bins of 200 bp (K = 3); one outer EM iteration with the "
                         "reference's 5 inner iterations per step at fixed theta, rejection cut p = 0.05"),
+    "c4": dict(model="differential", M=6_000_000, n_cond=5, n_rep=2, N=10, K=3, seed=20261004, cpu_bins=40_000, control_offsets=True,
+               workload="BASELINE configs[3]: synthetic genomic segmentation, 5 epigenomic marks x 2 replicates (2^5 - 2 = 30 mixture "
+                        "patterns), 6 000 000 bins of 500 bp with input-control offsets (K = 3); one outer EM iteration with 5 inner "
+                        "iterations per step at fixed theta, rejection cut p = 0.05"),
     "c5": dict(model="differential", M=60_000_000, n_cond=4, n_rep=3, N=12, K=3, seed=20261005, cpu_bins=60_000,
                workload="BASELINE configs[4]: synthetic 50 bp fine-bin differential run, 60 000 000 bins x (4 conditions x 3 "
                         "replicates), 14 mixture patterns (K = 3), bin blocks sharded across the GPUs; one outer EM iteration "
@@ -175,7 +181,11 @@ def make_data(cfg, M, seed):
     synth = host_module("synth")
     if cfg["model"] == "consensus":
         return synth.make_consensus(M, cfg["N"], seed)
-    return synth.make_differential(M, cfg["n_cond"], cfg["n_rep"], seed)
+    d = synth.make_differential(M, cfg["n_cond"], cfg["n_rep"], seed)
+    if cfg.get("control_offsets"):   # the input control enters through the offsets
+        rng = np.random.default_rng(seed + 77)
+        d["offsets"] = np.asfortranarray(d["offsets"] + np.round(0.3 * np.log1p(rng.poisson(5.0, d["offsets"].shape)), 3))
+    return d
 
 
 def theta_of(cfg, d):

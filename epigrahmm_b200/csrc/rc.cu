@@ -280,38 +280,50 @@ template <int CMAX, typename UT> struct RCStage {
     static constexpr int WORDS = CMAX * 32 * SG;  // per warp
 };
 
-// what a bin's weights are made of, as loaded (the next strip's are fetched while the current one is worked on)
-template <int CM> struct RCRaw {
-    double lp[3];                  // logProb1[j, 0..2]
-    double et[CM > 2 ? CM - 2 : 1];  // mixtureProb[j, b]
-    int g0;                        // consensus: the bin's one group id
+// what a bin's weights are made of, as loaded (the next strip's are fetched while the current one is worked on).
+// CHUNK: the launch handles columns [c0, c0 + CM) of a call with more columns than fit the registers (B = 30: 32
+// columns in four launches of 8); et[c] then belongs to the launch's column c, else to mixture component c - 1.
+template <int CM, bool CHUNK> struct RCRaw {
+    double lp[3];                                        // logProb1[j, 0..2] (or P1 itself)
+    double et[CHUNK ? CM : (CM > 2 ? CM - 2 : 1)];       // mixtureProb[j, b]
+    int g0;                                              // consensus: the bin's one group id
 };
 
-template <bool DIFF, int CM>
-__device__ __forceinline__ void rc_load_raw(const RCSrc &S, const int32_t *__restrict__ group, int64_t j, int C, RCRaw<CM> &w) {
+template <bool DIFF, int CM, bool CHUNK>
+__device__ __forceinline__ void rc_load_raw(const RCSrc &S, const int32_t *__restrict__ group, int64_t j, int C, int c0, int CT,
+                                            RCRaw<CM, CHUNK> &w) {
     const bool valid = j < S.M;
     w.lp[0] = valid ? __ldg(S.lp1 + j) : 2.0;  // 2 and exp(2) > 1 >= p: never flagged, never added (valid is re-checked)
     w.lp[1] = valid ? __ldg(S.lp1 + S.M + j) : 2.0;
     w.lp[2] = (DIFF && valid) ? __ldg(S.lp1 + 2 * S.M + j) : 2.0;
     w.g0 = (!DIFF && valid) ? __ldg(group + j) : 0;
     if (DIFF) {
+        if (CHUNK) {
 #pragma unroll
-        for (int b = 0; b < CM - 2; b++) w.et[b] = (valid && b < C - 2) ? __ldg(S.eta + (int64_t)b * S.M + j) : 0.0;
+            for (int c = 0; c < CM; c++) {
+                const int cg = c0 + c;
+                w.et[c] = (valid && c < C && cg >= 1 && cg <= CT - 2) ? __ldg(S.eta + (int64_t)(cg - 1) * S.M + j) : 0.0;
+            }
+        } else {
+#pragma unroll
+            for (int b = 0; b < CM - 2; b++) w.et[b] = (valid && b < C - 2) ? __ldg(S.eta + (int64_t)b * S.M + j) : 0.0;
+        }
     }
 }
 
 // FULL: the call has exactly CMAX columns (B = 6 -> 8, B = 14 -> 16, the consensus model's 2), so the column loop's
 // bounds and the "last column" tests are compile-time constants.
-template <bool DIFF, typename UT, bool EXACT, bool SKIPST, int CMAX, bool FULL>
+template <bool DIFF, typename UT, bool EXACT, bool SKIPST, int CMAX, bool FULL, bool CHUNK = false>
 __global__ void __launch_bounds__(RC_NT, CMAX == 0 ? 1 : (CMAX <= 8 ? 4 : 3))
     rc_apply_kernel(RCSrc S, RCCut cut, int64_t nwt, const uint32_t *__restrict__ tileoff, const __grid_constant__ RCBase ub,
                     const UT *__restrict__ unif, const int32_t *__restrict__ group, int nrep, int64_t G,
-                    const RCAcc A, const int *__restrict__ counts, int *__restrict__ err) {
+                    const RCAcc A, const int *__restrict__ counts, int *__restrict__ err, int c0, int Ctot) {
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
     const double p = cut.p;
     const bool thin = p > 0.0;
-    const int C = FULL ? CMAX : S.columns;
+    const int C = FULL ? CMAX : (CHUNK ? min(CMAX, Ctot - c0) : S.columns);  // columns of this launch
+    const int CT = CHUNK ? Ctot : C;                                             // columns of the call
     // Warp tiles are handed out by a counter (err[1], zeroed with the error flag): tiles inside peaks scatter many more
     // weights than background tiles, and with a fixed tile per warp a CTA kept its registers and shared memory until
     // its slowest warp was done (ncu: 15.8 of 32 resident warps active on average).
@@ -332,9 +344,12 @@ __global__ void __launch_bounds__(RC_NT, CMAX == 0 ? 1 : (CMAX <= 8 ? 4 : 3))
         int64_t next[CM];    // index of the column's next uniform (warp-uniform)
         int used[CM];        // ... and how many of the staged ones the current group has consumed
 #pragma unroll
-        for (int c = 0; c < CM; c++) next[c] = (thin && c < C) ? ub.ubase[c] + tileoff[(int64_t)c * nwt + tile] : 0;
-        RCRaw<CM> cur, nxt;
-        rc_load_raw<DIFF, CM>(S, group, tile * RC_WT + lane, C, cur);
+        for (int c = 0; c < CM; c++) {
+            const int cg = CHUNK ? c0 + c : c;
+            next[c] = (thin && c < C) ? ub.ubase[cg] + tileoff[(int64_t)cg * nwt + tile] : 0;
+        }
+        RCRaw<CM, CHUNK> cur, nxt;
+        rc_load_raw<DIFF, CM, CHUNK>(S, group, tile * RC_WT + lane, C, c0, CT, cur);
 #pragma unroll 1
         for (int r0 = 0; r0 < RC_STRIPS; r0 += SG) {
             if (thin) {  // the next 32 * SG uniforms of every column (the buffer has that much slack behind its end)
@@ -354,7 +369,7 @@ __global__ void __launch_bounds__(RC_NT, CMAX == 0 ? 1 : (CMAX <= 8 ? 4 : 3))
                 const int64_t j = tile * RC_WT + r * 32 + lane;
                 const bool valid = j < S.M;
                 // the next strip's loads go out before this strip's arithmetic
-                rc_load_raw<DIFF, CM>(S, group, (r + 1 < RC_STRIPS) ? j + 32 : S.M, C, nxt);
+                rc_load_raw<DIFF, CM, CHUNK>(S, group, (r + 1 < RC_STRIPS) ? j + 32 : S.M, C, c0, CT, nxt);
                 double p1[3], x[CM];
                 p1[0] = rc_post(cur.lp[0], S.lin);
                 p1[1] = rc_post(cur.lp[1], S.lin);
@@ -362,6 +377,7 @@ __global__ void __launch_bounds__(RC_NT, CMAX == 0 ? 1 : (CMAX <= 8 ? 4 : 3))
 #pragma unroll
                 for (int c = 0; c < CM; c++) {
                     if (!DIFF) x[c] = c == 0 ? p1[0] : p1[1];
+                    else if (CHUNK) x[c] = (c0 + c == 0) ? p1[0] : (c0 + c == CT - 1 ? p1[2] : rc_mix_weight(p1[1], cur.et[c]));
                     else x[c] = c == 0 ? p1[0] : (c == C - 1 ? p1[2] : rc_mix_weight(p1[1], cur.et[c > 0 ? c - 1 : 0]));
                     if (!(valid && c < C)) x[c] = 2.0;
                 }
@@ -381,7 +397,8 @@ __global__ void __launch_bounds__(RC_NT, CMAX == 0 ? 1 : (CMAX <= 8 ? 4 : 3))
                         }
                         used[c] += __popc(bal);
                         // x < p without a flag is x == 0: stays 0
-                        const bool cached = SKIPST && !flag && (c == 0 || c == C - 1);
+                        const int cg = CHUNK ? c0 + c : c;
+                        const bool cached = SKIPST && !flag && (cg == 0 || cg == CT - 1);
                         if (valid && x[c] != 0.0 && !cached) need |= 1u << c;
                     }
                 }
@@ -391,8 +408,9 @@ __global__ void __launch_bounds__(RC_NT, CMAX == 0 ? 1 : (CMAX <= 8 ? 4 : 3))
 #pragma unroll
                         for (int c = 0; c < CM; c++)
                             if ((need >> c) & 1u) {
-                                if (EXACT) limb_add(A, c, G, g, rep, C, x[c]);
-                                else atomicAdd(reinterpret_cast<double *>(A.w) + (int64_t)c * (G + 1) + g, x[c]);
+                                const int cg = CHUNK ? c0 + c : c;
+                                if (EXACT) limb_add(A, cg, G, g, rep, CT, x[c]);
+                                else atomicAdd(reinterpret_cast<double *>(A.w) + (int64_t)cg * (G + 1) + g, x[c]);
                             }
                     }
                 }
@@ -405,8 +423,10 @@ __global__ void __launch_bounds__(RC_NT, CMAX == 0 ? 1 : (CMAX <= 8 ? 4 : 3))
         if (thin) {
             bool bad = false;
 #pragma unroll
-            for (int c = 0; c < CM; c++)
-                if (c < C) bad = bad || (next[c] - (ub.ubase[c] + tileoff[(int64_t)c * nwt + tile]) != counts[(int64_t)c * nwt + tile]);
+            for (int c = 0; c < CM; c++) {
+                const int cg = CHUNK ? c0 + c : c;
+                if (c < C) bad = bad || (next[c] - (ub.ubase[cg] + tileoff[(int64_t)cg * nwt + tile]) != counts[(int64_t)cg * nwt + tile]);
+            }
             if (bad && lane == 0) atomicOr(err, 1);
         }
         continue;
@@ -644,16 +664,18 @@ int rc_static_build(ehmm_session *s, const RCSrc &S, double p, int nrep, cudaStr
 }
 
 // phase 2: thin and sum by group.  ub: where each column's draws start in `unif`.
-template <bool DIFF, typename UT, bool EXACT, bool SKIPST, int CM, bool FULL>
-int launch_apply_cm(ehmm_session *s, const RCSrc &S, const RCCut &cut, int nrep, const RCBase &ub, const UT *unif, void *accp) {
+template <bool DIFF, typename UT, bool EXACT, bool SKIPST, int CM, bool FULL, bool CHUNK = false>
+int launch_apply_cm(ehmm_session *s, const RCSrc &S, const RCCut &cut, int nrep, const RCBase &ub, const UT *unif, void *accp, int c0 = 0) {
     const RCAcc acc = rc_acc(reinterpret_cast<unsigned long long *>(accp), S.columns, s->G);  // fp64 mode: only .w is used
     const int64_t nwt = num_wtiles(s->M);
     constexpr int CS = CM > 0 ? CM : 1;
     const size_t smem = CM > 0 ? sizeof(UT) * RCStage<CS, UT>::WORDS * RC_NW : 0;
     // as many CTAs as can be resident (4 per SM where the kernel's bounds allow it), each warp fetching tiles until none is left
     const unsigned grid = std::min<unsigned>(tile_grid(nwt), 148u * (CM == 0 ? 1u : (CM <= 8 ? 4u : 3u)));
-    PROF(s, KID_RC_APPLY), rc_apply_kernel<DIFF, UT, EXACT, SKIPST, CM, FULL><<<grid, RC_NT, smem, s->stream>>>(
-        S, cut, nwt, s->rc_scan.as<uint32_t>(), ub, unif, s->group.as<int32_t>(), nrep, s->G, acc, s->rc_flag.as<int>(), err_flag(s));
+    if (CHUNK && c0 > 0) EHMM_CK(cudaMemsetAsync(err_flag(s) + 1, 0, sizeof(int), s->stream));  // the tile counter, not the error flag
+    PROF(s, KID_RC_APPLY), rc_apply_kernel<DIFF, UT, EXACT, SKIPST, CM, FULL, CHUNK><<<grid, RC_NT, smem, s->stream>>>(
+        S, cut, nwt, s->rc_scan.as<uint32_t>(), ub, unif, s->group.as<int32_t>(), nrep, s->G, acc, s->rc_flag.as<int>(), err_flag(s), c0,
+        S.columns);
     EHMM_CK(cudaGetLastError());
     return EHMM_OK;
 }
@@ -666,6 +688,16 @@ int launch_apply_kernel(ehmm_session *s, const RCSrc &S, double p, int nrep, con
     if (S.columns < 8) return launch_apply_cm<DIFF, UT, EXACT, SKIPST, 8, false>(s, S, cut, nrep, ub, unif, acc);
     if (S.columns == 16) return launch_apply_cm<DIFF, UT, EXACT, SKIPST, 16, true>(s, S, cut, nrep, ub, unif, acc);  // B = 14: configs[4]
     if (S.columns < 16) return launch_apply_cm<DIFF, UT, EXACT, SKIPST, 16, false>(s, S, cut, nrep, ub, unif, acc);
+    if (DIFF && S.columns <= RC_MAXCOL) {
+        // more columns than one launch can keep in registers (B = 30: BASELINE configs[3]): eight at a time; every launch
+        // walks all tiles for its columns (the generic kernel below keeps per-column state in lanes, one CTA per SM,
+        // and took ten times longer per column)
+        for (int c0 = 0; c0 < S.columns; c0 += 8) {
+            if (c0 + 8 <= S.columns) EHMM_TRY((launch_apply_cm<DIFF, UT, EXACT, SKIPST, 8, true, true>(s, S, cut, nrep, ub, unif, acc, c0)));
+            else EHMM_TRY((launch_apply_cm<DIFF, UT, EXACT, SKIPST, 8, false, true>(s, S, cut, nrep, ub, unif, acc, c0)));
+        }
+        return EHMM_OK;
+    }
     return launch_apply_cm<DIFF, UT, EXACT, SKIPST, 0, false>(s, S, cut, nrep, ub, unif, acc);
 }
 

@@ -41,9 +41,9 @@ def test_workloads_name_the_baseline_configurations():
     import importlib
     bench = importlib.import_module("bench")
     base = json.load(open(os.path.join(ROOT, "BASELINE.json")))
-    assert set(bench.CONFIGS) == {"c2", "c3", "c5"}
+    assert set(bench.CONFIGS) == {"c2", "c3", "c4", "c5"}
     for name, idx, words in (("c2", 1, ("15", "4 replicates", "consensus")), ("c3", 2, ("3 conditions", "2 replicates", "differential")),
-                             ("c5", 4, ("60", "4 conditions", "3 rep"))):
+                             ("c4", 3, ("5 epigenomic marks", "2 replicates", "500 bp")), ("c5", 4, ("60", "4 conditions", "3 rep"))):
         w = bench.CONFIGS[name]["workload"]
         assert "configs[%d]" % idx in w
         for word in words:

@@ -109,6 +109,24 @@ def test_rc_differential(ehmm, oracle, p):
             assert np.allclose(b, ref[c], rtol=1e-12, atol=0)
 
 
+@pytest.mark.parametrize("n_cond,n_rep", [(5, 1), (4, 2), (5, 2)])
+def test_rc_differential_many_columns(ehmm, oracle, n_cond, n_rep):
+    """B = 30 (BASELINE configs[3]: 32 columns, handled eight at a time) and B = 14 (16 columns): tables, support and
+    draw count against the oracle on the same posteriors and the same uniform buffer"""
+    d, g, h, _ = _differential_case(oracle, M=6011, n_cond=n_cond, n_rep=n_rep, seed=31 + n_cond)
+    M, N = d["counts"].shape
+    B = d["B"]
+    u = oracle.RNG.set_seed(11).runif((B + 2) * M)
+    for p in (0.9, 0.05):
+        ref, n_ref = oracle.differentialRejectionControlled(h, g["group"], p, N, uniforms=u, dense=True)
+        with _open(ehmm, "t_rcd_many", d, g, 3, h, design=d["design"]) as s:
+            assert s.rc_differential(p, uniforms=u) == n_ref
+            for c in range(B + 2):
+                b = s.rc_buckets(c)
+                assert np.array_equal(b != 0, ref[c] != 0), c
+                assert np.allclose(b, ref[c], rtol=1e-12, atol=0), c
+
+
 def _exact_tables(weights, group_cols, G):
     """correctly rounded sums by group (math.fsum): what the exact accumulators must return"""
     import math
